@@ -1,0 +1,153 @@
+// misc.cu -- fused multi-tensor Adam over a flat parameter arena, and layout conversion kernels
+// between the reference's fp32 NCHW tensors and the bf16 NHWC activations of the conv family.
+#include "common.cuh"
+
+namespace faln {
+namespace {
+
+// torch.optim.Adam (no amsgrad), as configured at /root/reference/Train_Stage1_K.py:177-181.
+// One pass over the arena: reads p, g, m, v; writes p, m, v and the bf16 shadow weights.
+__global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
+                                                   float4* __restrict__ m, float4* __restrict__ v,
+                                                   __nv_bfloat162* __restrict__ w16, long long n4, float step_size,
+                                                   float beta1, float beta2, float inv_sqrt_bc2, float eps, float wd,
+                                                   float gscale) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 P = p[i], G = g[i], M = m[i], V = v[i];
+    float* pp = reinterpret_cast<float*>(&P);
+    float* gg = reinterpret_cast<float*>(&G);
+    float* mm = reinterpret_cast<float*>(&M);
+    float* vv = reinterpret_cast<float*>(&V);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gr = fmaf(wd, pp[k], gg[k] * gscale);
+      mm[k] = fmaf(beta1, mm[k], (1.f - beta1) * gr);
+      vv[k] = fmaf(beta2, vv[k], (1.f - beta2) * gr * gr);
+      float denom = fmaf(sqrtf(vv[k]), inv_sqrt_bc2, eps);
+      pp[k] = pp[k] - step_size * (mm[k] / denom);
+    }
+    p[i] = P;
+    m[i] = M;
+    v[i] = V;
+    if (w16) {
+      w16[2 * i] = __floats2bfloat162_rn(pp[0], pp[1]);
+      w16[2 * i + 1] = __floats2bfloat162_rn(pp[2], pp[3]);
+    }
+  }
+}
+
+// fp32 NCHW -> bf16 NHWC, one thread per pixel (C small: the 3-channel input image).
+__global__ void __launch_bounds__(256) nchw_to_nhwc_small(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                          int B, int C, int H, int W, int Cp, int flip_x) {
+  const long long npx = (long long)B * H * W;
+  const long long hw = (long long)H * W;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < npx; i += (long long)gridDim.x * 256) {
+    const int x = (int)(i % W);
+    const long long b = i / hw;
+    const long long rem = i % hw;
+    const long long so = flip_x ? rem - x + (W - 1 - x) : rem;
+    __nv_bfloat16* d = dst + i * Cp;
+    for (int c = 0; c < Cp; ++c) d[c] = __float2bfloat16(c < C ? __ldg(src + (b * C + c) * hw + so) : 0.f);
+  }
+}
+
+// Tiled transposes between fp32 planar [B,C,H,pitch] and bf16 NHWC [B,H,W,Cp]: a block owns 32 pixels
+// of one row and walks the channels in groups of 32 through a padded shared tile, so both the planar
+// side (x fastest) and the NHWC side (c fastest) are accessed in full 128-byte / 64-byte segments.
+__global__ void __launch_bounds__(256) planar_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                             int C, int H, int W, int Cp, long long pitch) {
+  __shared__ float tile[32][33];
+  const int xt = blockIdx.x * 32;
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32
+  for (int c0 = 0; c0 < Cp; c0 += 32) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + ty + 8 * k, x = xt + tx;
+      tile[ty + 8 * k][tx] = (c < C && x < W) ? __ldg(src + (((long long)b * C + c) * H + y) * pitch + x) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int px = ty + 8 * k, c = c0 + tx, x = xt + px;
+      if (x < W && c < Cp) dst[(((long long)b * H + y) * W + x) * Cp + c] = __float2bfloat16(tile[tx][px]);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) nhwc_to_planar_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
+                                                             int C, int H, int W, int Cp, long long pitch) {
+  __shared__ float tile[32][33];
+  const int xt = blockIdx.x * 32;
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int px = ty + 8 * k, c = c0 + tx, x = xt + px;
+      tile[px][tx] = (x < W && c < Cp) ? __bfloat162float(src[(((long long)b * H + y) * W + x) * Cp + c]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + ty + 8 * k, x = xt + tx;
+      if (c < C && x < W) dst[(((long long)b * C + c) * H + y) * pitch + x] = tile[tx][ty + 8 * k];
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+}  // namespace faln
+
+using namespace faln;
+
+extern "C" int faln_adam(float* p, const float* g, float* m, float* v, void* w16, long long n, float lr, float beta1,
+                         float beta2, float eps, float weight_decay, int step, float grad_scale, faln_stream_t stream) {
+  FALN_REQUIRE(p && g && m && v && n > 0 && (n & 3) == 0 && step >= 1, "faln_adam: n must be a positive multiple of 4");
+  FALN_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                 reinterpret_cast<uintptr_t>(v)) & 15) == 0, "faln_adam: arenas must be 16-byte aligned");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const long long n4 = n / 4;
+  long long grid = (n4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  adam_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+      reinterpret_cast<float4*>(v), static_cast<__nv_bfloat162*>(w16), n4, (float)(lr / bc1), beta1, beta2,
+      (float)(1.0 / sqrt(bc2)), eps, weight_decay, grad_scale);
+  return after_launch("adam_kernel");
+}
+
+extern "C" int faln_nchw_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, int W, int Cp, int flip_x,
+                                      faln_stream_t stream) {
+  FALN_REQUIRE(src && dst && B > 0 && C > 0 && Cp >= C && Cp <= 16, "faln_nchw_to_nhwc_bf16: need C <= Cp <= 16");
+  const long long npx = (long long)B * H * W;
+  long long grid = (npx + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  nchw_to_nhwc_small<<<(int)grid, 256, 0, as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), B, C, H, W, Cp,
+                                                               flip_x);
+  return after_launch("nchw_to_nhwc_small");
+}
+
+extern "C" int faln_planar_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, int W, int Cp, long long pitch,
+                                        faln_stream_t stream) {
+  FALN_REQUIRE(src && dst && B > 0 && C > 0 && Cp >= C && pitch >= W && H <= 65535 && B <= 65535,
+               "faln_planar_to_nhwc_bf16: bad argument");
+  dim3 grid((W + 31) / 32, H, B);
+  planar_to_nhwc_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), C, H, W, Cp, pitch);
+  return after_launch("planar_to_nhwc_kernel");
+}
+
+extern "C" int faln_nhwc_bf16_to_planar(const void* src, float* dst, int B, int C, int H, int W, int Cp, long long pitch,
+                                        faln_stream_t stream) {
+  FALN_REQUIRE(src && dst && B > 0 && C > 0 && Cp >= C && pitch >= W && H <= 65535 && B <= 65535,
+               "faln_nhwc_bf16_to_planar: bad argument");
+  dim3 grid((W + 31) / 32, H, B);
+  nhwc_to_planar_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(src), dst, C, H, W, Cp,
+                                                             pitch);
+  return after_launch("nhwc_to_planar_kernel");
+}

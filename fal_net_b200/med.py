@@ -1,0 +1,146 @@
+"""MED view synthesis on the fused sm_100a kernels (csrc/med.cu).
+
+Host-side mirror of /root/reference/models/FAL_netB.py:200-297 from ``dlog0`` onwards: the level
+tables are computed with the reference's own torch expressions (so their fp32 values are the
+reference's), everything per-pixel happens in ``faln_med_fwd`` / ``faln_med_bwd``.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def level_tables(min_disp: torch.Tensor, max_disp: torch.Tensor, no_levels: int, W: int):
+    """d [B,N] (pixels) and x_of [B,N] (normalised grid units) of the exponential disparity levels,
+    written exactly like /root/reference/models/FAL_netB.py:204-205,224-225,241 (fp32, same op order)."""
+    x_pix_min = 2 * min_disp / W
+    x_pix_max = 2 * max_disp / W
+    lg_d = torch.log(max_disp / min_disp)
+    lg_x = torch.log(x_pix_max / x_pix_min)
+    d, xo = [], []
+    for n in range(no_levels):
+        c = n / (no_levels - 1)
+        d.append(max_disp * torch.exp(lg_d * (c - 1)))
+        xo.append(x_pix_max * torch.exp(lg_x * (c - 1)))
+    return torch.cat(d, 2).squeeze(1).contiguous(), torch.cat(xo, 2).squeeze(1).contiguous()
+
+
+_G0X_CACHE: dict = {}
+
+
+def grid_row(W: int, device) -> torch.Tensor:
+    """x row of F.affine_grid(identity, align_corners=True) (/root/reference/models/FAL_netB.py:231-234)."""
+    key = (W, str(device))
+    g = _G0X_CACHE.get(key)
+    if g is None:
+        th = torch.zeros(1, 2, 3, device=device)
+        th[:, 0, 0] = 1
+        th[:, 1, 1] = 1
+        g = F.affine_grid(th, [1, 1, 2, W], align_corners=True)[0, 0, :, 0].contiguous()
+        _G0X_CACHE[key] = g
+    return g
+
+
+def _pitch_of(logits: torch.Tensor) -> int:
+    B, N, H, W = logits.shape
+    sb, sn, sh, sw = logits.stride()
+    if sw != 1 or sn != H * sh or sb != N * H * sh or sh < W:
+        raise RuntimeError("logits must be [B,N,H,W] with unit x stride and a uniform row pitch")
+    return sh
+
+
+def med_forward_raw(logits, image, x_of, d_lvl, g0x, want_pan=True, want_disp=True, want_masks=False, flags=0):
+    """Direct kernel call.  Returns dict(pan, disp, maskL, maskR, lse0, lsew) (None where not wanted)."""
+    L = _lib.lib()
+    B, N, H, W = logits.shape
+    assert logits.dtype == torch.float32 and logits.is_cuda
+    pitch = _pitch_of(logits)
+    image = _lib.f32c(image, "image")
+    assert image.shape == (B, 3, H, W)
+    dev = logits.device
+    opt = dict(device=dev, dtype=torch.float32)
+    pan = torch.empty(B, 3, H, W, **opt) if want_pan else None
+    disp = torch.empty(B, 1, H, W, **opt) if want_disp else None
+    mL = torch.empty(B, 1, H, W, **opt) if want_masks else None
+    mR = torch.empty(B, 1, H, W, **opt) if want_masks else None
+    lse0 = torch.empty(B, 1, H, W, **opt)
+    lsew = torch.empty(B, 1, H, W, **opt)
+    rc = L.faln_med_fwd(_lib.ptr(logits), _lib.ptr(image), _lib.ptr(g0x), _lib.ptr(x_of), _lib.ptr(d_lvl),
+                        _lib.ptr(pan), _lib.ptr(disp), _lib.ptr(mL), _lib.ptr(mR), _lib.ptr(lse0), _lib.ptr(lsew),
+                        B, N, H, W, pitch, flags, _lib.cur_stream())
+    _lib.check(rc, "faln_med_fwd")
+    return dict(pan=pan, disp=disp, maskL=mL, maskR=mR, lse0=lse0, lsew=lsew)
+
+
+def med_backward_raw(logits, image, x_of, d_lvl, g0x, pan, disp, lse0, lsew, g_pan, g_disp, flags=0, out=None):
+    L = _lib.lib()
+    B, N, H, W = logits.shape
+    pitch = _pitch_of(logits)
+    if out is None:
+        out = torch.empty_like(logits)
+    g_pitch = _pitch_of(out)
+    g_pan = _lib.f32c(g_pan, "g_pan") if g_pan is not None else None
+    g_disp = _lib.f32c(g_disp, "g_disp") if g_disp is not None else None
+    rc = L.faln_med_bwd(_lib.ptr(logits), _lib.ptr(image), _lib.ptr(g0x), _lib.ptr(x_of), _lib.ptr(d_lvl),
+                        _lib.ptr(pan), _lib.ptr(disp), _lib.ptr(lse0), _lib.ptr(lsew), _lib.ptr(g_pan),
+                        _lib.ptr(g_disp), _lib.ptr(out), B, N, H, W, pitch, g_pitch, flags, _lib.cur_stream())
+    _lib.check(rc, "faln_med_bwd")
+    return out
+
+
+def med_disp_only(logits, d_lvl):
+    """Inference epilogue: disparity expectation only (/root/reference/models/FAL_netB.py:216-229)."""
+    L = _lib.lib()
+    B, N, H, W = logits.shape
+    disp = torch.empty(B, 1, H, W, device=logits.device, dtype=torch.float32)
+    rc = L.faln_med_disp(_lib.ptr(logits), _lib.ptr(d_lvl), _lib.ptr(disp), B, N, H, W, _pitch_of(logits),
+                         _lib.cur_stream())
+    _lib.check(rc, "faln_med_disp")
+    return disp
+
+
+class MedSynthesis(torch.autograd.Function):
+    """(logits, image) -> (pan, disp, maskL, maskR); gradient flows to the logits only, from pan and disp
+    only -- exactly the reference's autograd graph (masks are built under no_grad on detached inputs,
+    /root/reference/models/FAL_netB.py:256-273; the image is a leaf without grad)."""
+
+    @staticmethod
+    def forward(ctx, logits, image, x_of, d_lvl, g0x, want_masks):
+        r = med_forward_raw(logits, image, x_of, d_lvl, g0x, True, True, want_masks)
+        ctx.save_for_backward(logits, image, x_of, d_lvl, g0x, r["pan"], r["disp"], r["lse0"], r["lsew"])
+        outs = (r["pan"], r["disp"])
+        if want_masks:
+            ctx.mark_non_differentiable(r["maskL"], r["maskR"])
+            outs = outs + (r["maskL"], r["maskR"])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_pan, g_disp, *_):
+        logits, image, x_of, d_lvl, g0x, pan, disp, lse0, lsew = ctx.saved_tensors
+        g = med_backward_raw(logits, image, x_of, d_lvl, g0x, pan, disp, lse0, lsew, g_pan, g_disp)
+        return g, None, None, None, None, None
+
+
+def med_section(dlog0, image, min_disp, max_disp, ret_disp=True, ret_subocc=False, ret_pan=False):
+    """FAL_net.forward from ``dlog0`` on, same return convention as the reference
+    (/root/reference/models/FAL_netB.py:228-229,285-297): a bare tensor when only the disparity is asked
+    for, else a list ordered [pan?, disp?, maskL?, maskR?]."""
+    B, N, H, W = dlog0.shape
+    d_lvl, x_of = level_tables(min_disp, max_disp, N, W)
+    if ret_disp and not ret_subocc and not ret_pan:
+        if dlog0.requires_grad and torch.is_grad_enabled():
+            g0x = grid_row(W, dlog0.device)
+            return MedSynthesis.apply(dlog0, image, x_of, d_lvl, g0x, False)[1]
+        return med_disp_only(dlog0, d_lvl)
+    g0x = grid_row(W, dlog0.device)
+    res = MedSynthesis.apply(dlog0, image, x_of, d_lvl, g0x, bool(ret_subocc))
+    out = []
+    if ret_pan:
+        out.append(res[0])
+    if ret_disp:
+        out.append(res[1])
+    if ret_subocc:
+        out.extend([res[2], res[3]])
+    return out

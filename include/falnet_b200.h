@@ -1,0 +1,164 @@
+/* falnet_b200.h -- C ABI of libfalnet_sm100.so (hand-written sm_100a kernels for the FAL-net hot path).
+ *
+ * The reference (JuanLuisGonzalez/FAL_net) has NO native/FFI layer: its hot path is Python calling
+ * ATen/cuDNN.  Each entry point below therefore cites the reference *Python*
+ * code whose device work it replaces; the Python side of the boundary (fal_net_b200/*.py) keeps the
+ * reference's names and signatures and calls these functions through ctypes with raw device
+ * pointers + the current CUDA stream (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every function is extern "C", takes plain pointers / sizes, returns int: 0 = ok, <0 = error
+ *     (faln_last_error() gives the thread-local message).  No allocation, no host sync, no
+ *     exceptions inside: every call only enqueues work on `stream` and is CUDA-graph capturable.
+ *   - all pointers are DEVICE pointers unless named h_*.  Tensors are contiguous in the stated
+ *     layout; "pitch" arguments are in ELEMENTS.
+ *   - fp32 tensors are NCHW like the reference's; bf16 activations/weights of the conv family are
+ *     NHWC / KRSC (channels innermost).
+ */
+#ifndef FALNET_B200_H_
+#define FALNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* faln_stream_t; /* cudaStream_t */
+
+#define FALN_OK 0
+#define FALN_ERR_ARG (-1)     /* bad argument (null pointer, unsupported size, misalignment) */
+#define FALN_ERR_LAUNCH (-2)  /* CUDA launch error; see faln_last_error() */
+#define FALN_ERR_UNSUPPORTED (-3)
+
+int faln_version(void);
+const char* faln_last_error(void);
+/* Number of kernels this library has launched from the calling process since load (all threads). */
+long long faln_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * MED view synthesis (the fused hot kernel).
+ *
+ * Replaces, in /root/reference/models/FAL_netB.py: softmax :216, disparity expectation :219-226,
+ * affine_grid + 2N grid clones :231-243,258-262,270-271, the N grid_sample + O(N^2) cat :244-247,
+ * softmax :248, the blend loop :279-282 and the sub-occlusion masks :264-273,290-294.
+ *
+ *   logits  [B,N,H,Wp] fp32   dlog0 (row pitch `logit_pitch` >= W elements, plane stride H*pitch)
+ *   image   [B,3,H,W]  fp32   the input view
+ *   g0x     [W]        fp32   x row of F.affine_grid(identity, align_corners=True): linspace(-1,1,W)
+ *   x_of    [B,N]      fp32   normalised-grid offset of level n (reference :241)
+ *   d_lvl   [B,N]      fp32   disparity of level n in pixels   (reference :225)
+ * outputs (any of pan / disp / maskL+maskR may be NULL = not wanted):
+ *   pan     [B,3,H,W], disp [B,1,H,W], maskL/maskR [B,1,H,W] (already clamped to <= 1)
+ *   lse0    [B,1,H,W]  log-sum-exp over planes of the un-warped logits   (saved for backward)
+ *   lsew    [B,1,H,W]  log-sum-exp over planes of the warped logits      (saved for backward)
+ * flags: FALN_MED_FORCE_GENERIC forces the per-pixel floor path on every plane (testing).
+ */
+#define FALN_MED_FORCE_GENERIC 1u
+int faln_med_fwd(const float* logits, const float* image, const float* g0x, const float* x_of,
+                 const float* d_lvl, float* pan, float* disp, float* maskL, float* maskR, float* lse0,
+                 float* lsew, int B, int N, int H, int W, long long logit_pitch, unsigned flags,
+                 faln_stream_t stream);
+
+/* Backward of the MED section w.r.t. the logits (autograd of reference :216-282; the image, the level
+ * tables and the masks carry no gradient, :223,237,256).  Single sweep over the planes: uses the
+ * forward's saved pan / disp / lse0 / lsew (dot(x) = <g_pan(x), pan(x)>), gather-only, no atomics.
+ *   g_pan [B,3,H,W] or NULL, g_disp [B,1,H,W] or NULL  ->  g_logits [B,N,H,Wp] (pitch = g_pitch)
+ */
+int faln_med_bwd(const float* logits, const float* image, const float* g0x, const float* x_of,
+                 const float* d_lvl, const float* pan, const float* disp, const float* lse0,
+                 const float* lsew, const float* g_pan, const float* g_disp, float* g_logits, int B,
+                 int N, int H, int W, long long logit_pitch, long long g_pitch, unsigned flags,
+                 faln_stream_t stream);
+
+/* Disparity-only epilogue (inference path, reference :216-229): disp = sum_n d_n softmax_n(logits). */
+int faln_med_disp(const float* logits, const float* d_lvl, float* disp, int B, int N, int H, int W,
+                  long long logit_pitch, faln_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Losses.  All reductions are deterministic two-stage sums: each call writes per-block partials to
+ * `partials` (>= faln_loss_partials_len() floats) and a last-block-done pass folds them, in fixed
+ * order, into out[0] (+= semantics are NOT used: out[0] is overwritten).
+ * ---------------------------------------------------------------------------------------------- */
+int faln_loss_partials_len(void);
+
+/* Masked L1 reconstruction + (optionally) the blended image fed to VGG
+ * (/root/reference/loss_functions.py:52-56):
+ *   out[0]   = mean(mask * |synth - label|)          over B*3*H*W elements
+ *   blend    = mask*synth + (1-mask)*label            (written if blend != NULL)
+ *   g_synth  = g_scale * mask * sign(synth-label)/(B*3*H*W) (+ g_blend*mask if g_blend != NULL)
+ * mask is [B,1,H,W] or NULL (the integer 1 of Stage-1, Train_Stage1_K.py:247).
+ * If flip_x != 0, synth is read (and g_synth written) x-reversed -- the exact index flip that replaces
+ * the reference's grid_sample un-flip, Train_Stage2_K.py:283-286; label/mask/blend stay un-flipped. */
+int faln_loss_rec_l1(const float* synth, const float* label, const float* mask, float* blend,
+                     float* out, float* partials, int B, int H, int W, int flip_x,
+                     faln_stream_t stream);
+/* Backward kernels scale by g_scale * (g_dev ? *g_dev : 1): g_dev is an optional DEVICE scalar (the
+ * upstream gradient of the loss value) so that no host sync is needed to chain losses. */
+int faln_loss_rec_l1_bwd(const float* synth, const float* label, const float* mask, const float* g_blend,
+                         float g_scale, const float* g_dev, float* g_synth, int B, int H, int W, int flip_x,
+                         faln_stream_t stream);
+
+/* Edge-aware smoothness on the column window [x_lo, x_hi) of img [B,3,H,W] / disp [B,1,H,W]
+ * (/root/reference/loss_functions.py:70-109 applied to the slices of Train_Stage1_K.py:255 /
+ * Train_Stage2_K.py:312-313; stencils are zero-padded at the WINDOW border like the reference's
+ * conv2d on the sliced tensor).  flip_x: disp is read x-reversed. */
+int faln_loss_smooth(const float* img, const float* disp, float gamma, float* out, float* partials,
+                     int B, int H, int W, int x_lo, int x_hi, int flip_x, faln_stream_t stream);
+int faln_loss_smooth_bwd(const float* img, const float* disp, float gamma, float g_scale, const float* g_dev,
+                         float* g_disp, int accumulate, int B, int H, int W, int x_lo, int x_hi, int flip_x,
+                         faln_stream_t stream);
+
+/* Mirror loss (/root/reference/Train_Stage2_K.py:319-324) on the window [x_lo,x_hi):
+ *   out[0] = mean_{b,y,x in window} (1/max_b(mdisp)) * (1 - occ) * |disp - mdisp|
+ * inv_max [B] = 1 / max over the whole image of mdisp[b]. */
+int faln_loss_mirror(const float* disp, const float* mdisp, const float* occ, const float* inv_max,
+                     float* out, float* partials, int B, int H, int W, int x_lo, int x_hi, int flip_x,
+                     faln_stream_t stream);
+int faln_loss_mirror_bwd(const float* disp, const float* mdisp, const float* occ, const float* inv_max,
+                         float g_scale, const float* g_dev, float* g_disp, int accumulate, int B, int H, int W,
+                         int x_lo, int x_hi, int flip_x, faln_stream_t stream);
+
+/* mean((a-b)^2) over n elements of bf16 NHWC feature maps (perceptual loss,
+ * /root/reference/loss_functions.py:59-67) and its gradient w.r.t. a. */
+int faln_mse_bf16(const void* a, const void* b, long long n, float* out, float* partials,
+                  faln_stream_t stream);
+int faln_mse_bf16_bwd(const void* a, const void* b, long long n, float g_scale, const float* g_dev, void* g_a,
+                      faln_stream_t stream);
+
+/* Per-image max of a [B,1,H,W] fp32 map -> inv_max[b] = 1/max (F.max_pool2d(kernel=(H,W)),
+ * /root/reference/Train_Stage2_K.py:319-320). */
+int faln_inv_rowmax(const float* x, float* inv_max, int B, long long n_per_image, faln_stream_t stream);
+
+/* Occlusion masks of Stage-2 (/root/reference/Train_Stage2_K.py:295-299):
+ *   O = flip_a?(a) * flip_b?(b);  O[..., one_lo:one_hi] = 1     (flips are exact x index reversals) */
+int faln_occ_mask(const float* a, const float* b, float* out, int B, int H, int W, int flip_a, int flip_b,
+                  int one_lo, int one_hi, faln_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser: fused multi-tensor Adam (torch.optim.Adam as configured at
+ * /root/reference/Train_Stage1_K.py:177-181: betas (0.5, 0.999), eps 1e-8, wd 0), over one flat
+ * fp32 arena: p, g, m, v are [n] device arrays.  Also refreshes the bf16 shadow copy used by the conv
+ * kernels (w16 may be NULL).  grad_scale multiplies g first (1/world_size after an allreduce-SUM).
+ * ---------------------------------------------------------------------------------------------- */
+int faln_adam(float* p, const float* g, float* m, float* v, void* w16, long long n, float lr, float beta1,
+              float beta2, float eps, float weight_decay, int step, float grad_scale,
+              faln_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout / elementwise helpers of the conv pipeline (bf16 NHWC activations).
+ * ---------------------------------------------------------------------------------------------- */
+/* fp32 NCHW [B,C,H,W] -> bf16 NHWC [B,H,W,Cp] (channels C..Cp-1 zero); flip_x reverses x. */
+int faln_nchw_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, int W, int Cp, int flip_x,
+                           faln_stream_t stream);
+/* bf16 NHWC [B,H,W,Cp] -> fp32 planar [B,C,H,pitch] (first C channels). */
+int faln_nhwc_bf16_to_planar(const void* src, float* dst, int B, int C, int H, int W, int Cp,
+                             long long pitch, faln_stream_t stream);
+int faln_planar_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, int W, int Cp,
+                             long long pitch, faln_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FALNET_B200_H_ */

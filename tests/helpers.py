@@ -1,0 +1,36 @@
+"""Shared test utilities: seeded synthetic inputs (the same recipes tests/golden/make_golden.py used)."""
+import hashlib
+
+import torch
+
+MEAN = (0.411, 0.432, 0.45)
+
+
+def images(B, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(B, 3, H, W, generator=g) - torch.tensor(MEAN).view(1, 3, 1, 1)
+
+
+def disp_range(B, max_disp=300.0, min_disp=2.0):
+    mx = torch.full((B, 1, 1), float(max_disp))
+    return mx * min_disp / max_disp, mx
+
+
+def sha(t):
+    return hashlib.sha256(t.detach().contiguous().numpy().tobytes()).hexdigest()[:16]
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b|  -- the tolerance metric of SURVEY.md 8c(iv)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def med_case_inputs(tag, B, N, H, W):
+    """Inputs of golden MED case `tag` (tests/golden/make_golden.py section 2)."""
+    g = torch.Generator().manual_seed(7 + len(tag) + N + W)
+    logits = 2 * torch.randn(B, N, H, W, generator=g)
+    img = images(B, H, W, 1234 + W)
+    gp = torch.randn(B, 3, H, W, generator=g)
+    gd = torch.randn(B, 1, H, W, generator=g)
+    return logits, img, gp, gd

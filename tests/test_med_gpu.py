@@ -1,0 +1,188 @@
+"""GPU parity of the fused MED kernels (through the C ABI) against
+  (1) the committed reference outputs (tests/golden/med_cases.npz),
+  (2) the CPU oracle on seeded inputs, incl. ragged / misaligned / pitched layouts,
+  (3) at BASELINE.json's full sizes, the oracle evaluated on a random subset of image rows
+      (rows are independent units of the computation) plus linearity in the image.
+Tolerance: <= 1e-4 relative (max|a-b| / max|b|), the fp32-mode bound of BASELINE.json north_star.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import falnet_oracle as O
+from tests.helpers import disp_range, images, med_case_inputs, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _run(logits, img, d, xo, gp=None, gd=None, masks=True, flags=0, pitch=None):
+    from fal_net_b200 import med
+    dev = _dev()
+    B, N, H, W = logits.shape
+    if pitch is None:
+        lg = logits.to(dev)
+    else:
+        buf = torch.full((B, N, H, pitch), float("nan"), device=dev)   # poison the padding
+        buf[..., :W] = logits.to(dev)
+        lg = buf[..., :W]
+    g0x = O.identity_grid(1, 1, 2, W)[0, 0, :, 0].contiguous().to(dev)     # CPU-computed table, bit-equal to the oracle's
+    r = med.med_forward_raw(lg, img.to(dev), xo.to(dev), d.to(dev), g0x, True, True, masks, flags)
+    if gp is not None:
+        out = None
+        if pitch is not None:
+            out = torch.zeros((B, N, H, pitch), device=dev)[..., :W]
+        r["glogits"] = med.med_backward_raw(lg, img.to(dev), xo.to(dev), d.to(dev), g0x, r["pan"], r["disp"], r["lse0"],
+                                            r["lsew"], gp.to(dev), gd.to(dev), flags, out=out)
+    torch.cuda.synchronize()
+    return r
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+def test_golden_cases(golden_dir, flags):
+    g = np.load(os.path.join(golden_dir, "med_cases.npz"))
+    for tag in "abcdef":
+        B, N, H, W = (int(v) for v in g[f"{tag}_meta"])
+        logits, img, gp, gd = med_case_inputs(tag, B, N, H, W)
+        mn, mx = torch.from_numpy(g[f"{tag}_min"]), torch.from_numpy(g[f"{tag}_max"])
+        d, xo = O.level_tables(mn, mx, N, W)
+        r = _run(logits, img, d, xo, gp, gd, flags=flags)
+        for nm in ("pan", "disp", "maskL", "maskR", "glogits"):
+            e = rel_err(r[nm], torch.from_numpy(g[f"{tag}_{nm}"]))
+            assert e < TOL, (tag, nm, e, flags)
+        # far tighter in practice: the kernel replays the reference's fp32 coordinates
+        assert rel_err(r["pan"], torch.from_numpy(g[f"{tag}_pan"])) < 2e-5, tag
+
+
+@pytest.mark.parametrize("B,N,H,W,pitch,maxd,mind", [
+    (2, 49, 7, 640, None, 300.0, 2.0),
+    (1, 49, 5, 1242, None, 300.0, 2.0),      # rows alternate 16B / 8B alignment; odd row count -> clamped tail
+    (3, 33, 3, 321, None, 120.0, 1.5),       # odd width: 4-byte row alignment, ragged last pixel group
+    (2, 17, 4, 100, 104, 40.0, 0.5),         # pitched logits (our conv epilogue's layout), NaN in the padding
+    (1, 65, 2, 2048, None, 300.0, 2.0),
+    (2, 2, 3, 8, None, 3.0, 1.0),            # smallest supported: N=2, W=8
+    (1, 49, 2, 640, None, 256.0, 4.0),       # integer shifts on several planes -> generic path mixed with fast path
+])
+def test_against_oracle(B, N, H, W, pitch, maxd, mind):
+    g = torch.Generator().manual_seed(B * 1000 + N * 10 + W)
+    logits = 2 * torch.randn(B, N, H, W, generator=g)
+    img = images(B, H, W, 99 + W)
+    gp, gd = torch.randn(B, 3, H, W, generator=g), torch.randn(B, 1, H, W, generator=g)
+    mn, mx = disp_range(B, maxd, mind)
+    d, xo = O.level_tables(mn, mx, N, W)
+    ref = O.med_forward_closed(logits, img, d, xo)
+    ref_ops = O.med_forward_ops(logits, img, mn, mx, True, True, True)
+    ref["glogits"] = O.med_backward_closed(logits, img, d, xo, gp, gd)
+    r = _run(logits, img, d, xo, gp, gd, pitch=pitch)
+    for nm in ("pan", "disp", "maskL", "maskR", "glogits", "lse0", "lsew"):
+        e = rel_err(r[nm], ref[nm])
+        assert e < TOL, (nm, e)
+    for nm, t in zip(("pan", "disp", "maskL", "maskR"), ref_ops):
+        assert rel_err(r[nm], t) < TOL, nm
+    # fast path and generic path agree
+    r2 = _run(logits, img, d, xo, gp, gd, flags=1, pitch=pitch)
+    for nm in ("pan", "disp", "maskL", "maskR", "glogits"):
+        assert rel_err(r2[nm], r[nm]) < 2e-5, nm
+
+
+def test_no_mask_variant_and_autograd_wrapper():
+    from fal_net_b200 import med
+    dev = _dev()
+    B, N, H, W = 2, 49, 6, 640
+    g = torch.Generator().manual_seed(5)
+    logits = (2 * torch.randn(B, N, H, W, generator=g)).to(dev).requires_grad_(True)
+    img = images(B, H, W, 3).to(dev)
+    mn, mx = (t.to(dev) for t in disp_range(B))
+    pan, disp = med.med_section(logits, img, mn, mx, ret_disp=True, ret_pan=True)
+    gp, gd = torch.randn_like(pan), torch.randn_like(disp)
+    (gl,) = torch.autograd.grad((pan * gp).sum() + (disp * gd).sum(), logits)
+    lc = logits.detach().cpu().requires_grad_(True)
+    rp, rd = O.med_forward_ops(lc, img.cpu(), mn.cpu(), mx.cpu(), True, False, True)
+    (rgl,) = torch.autograd.grad((rp * gp.cpu()).sum() + (rd * gd.cpu()).sum(), lc)
+    assert rel_err(pan, rp) < TOL and rel_err(disp, rd) < TOL and rel_err(gl, rgl) < TOL
+    # disparity-only call returns a bare tensor (reference :228-229) and uses the streaming epilogue
+    with torch.no_grad():
+        donly = med.med_section(logits.detach(), img, mn, mx)
+    assert isinstance(donly, torch.Tensor) and rel_err(donly, rd) < TOL
+    # all four outputs, list order [pan, disp, maskL, maskR] (reference :285-297)
+    outs = med.med_section(logits.detach(), img, mn, mx, ret_disp=True, ret_subocc=True, ret_pan=True)
+    assert len(outs) == 4 and float(outs[2].max()) <= 1.0 and float(outs[3].max()) <= 1.0
+
+
+@pytest.mark.parametrize("B,N,H,W", [(8, 49, 375, 1242), (2, 65, 1024, 2048), (8, 33, 375, 1242), (16, 49, 192, 640)])
+def test_full_size_rows_and_linearity(B, N, H, W):
+    """BASELINE.json config #5 / #3 sizes: oracle on random rows + linearity of pan in the image."""
+    from fal_net_b200 import med
+    dev = _dev()
+    gen = torch.Generator(device=dev).manual_seed(7)
+    logits = 2 * torch.randn(B, N, H, W, generator=gen, device=dev)
+    img = torch.rand(B, 3, H, W, generator=gen, device=dev) - 0.43
+    gp = torch.randn(B, 3, H, W, generator=gen, device=dev)
+    gd = torch.randn(B, 1, H, W, generator=gen, device=dev)
+    mn, mx = disp_range(B)
+    d, xo = O.level_tables(mn, mx, N, W)
+    g0x = O.identity_grid(1, 1, 2, W)[0, 0, :, 0].contiguous().to(dev)
+    r = med.med_forward_raw(logits, img, xo.to(dev), d.to(dev), g0x, True, True, True)
+    gl = med.med_backward_raw(logits, img, xo.to(dev), d.to(dev), g0x, r["pan"], r["disp"], r["lse0"], r["lsew"], gp, gd)
+    rows = [(0, 0), (B - 1, H - 1), (B // 2, H // 2), (B - 1, 1), (0, H - 2), (B // 3, (2 * H) // 3)]
+    for b, y in rows:
+        lo = logits[b:b + 1, :, y:y + 1].cpu()
+        im = img[b:b + 1, :, y:y + 1].cpu()
+        ref = O.med_forward_closed(lo, im, d[b:b + 1], xo[b:b + 1])
+        for nm in ("pan", "disp", "maskL", "maskR"):
+            e = rel_err(r[nm][b:b + 1, :, y:y + 1], ref[nm])
+            assert e < TOL, (b, y, nm, e)
+        rg = O.med_backward_closed(lo, im, d[b:b + 1], xo[b:b + 1], gp[b:b + 1, :, y:y + 1].cpu(), gd[b:b + 1, :, y:y + 1].cpu())
+        e = rel_err(gl[b:b + 1, :, y:y + 1], rg)
+        assert e < TOL, (b, y, "glogits", e)
+    # linearity in the image (same logits): pan(I1 + I2) == pan(I1) + pan(I2)
+    img2 = torch.rand(B, 3, H, W, generator=gen, device=dev) - 0.5
+    p2 = med.med_forward_raw(logits, img2, xo.to(dev), d.to(dev), g0x, True, False, False)["pan"]
+    p12 = med.med_forward_raw(logits, img + img2, xo.to(dev), d.to(dev), g0x, True, False, False)["pan"]
+    assert rel_err(p12, r["pan"] + p2) < 2e-5
+    # masks are clamped, disparity stays inside [min_disp, max_disp]
+    assert float(r["maskL"].max()) <= 1.0 and float(r["maskR"].max()) <= 1.0
+    assert float(r["disp"].min()) >= 2.0 * (1 - 1e-5) and float(r["disp"].max()) <= 300.0 * (1 + 1e-5)
+    assert torch.isfinite(gl).all()
+
+
+def test_device_tables_match_cpu_tables():
+    """The product computes g0x / x_of / d on the device with the reference's torch expressions; check they
+    are (near-)identical to the CPU oracle's tables, so the 1e-4 bound carries over to a CUDA reference."""
+    from fal_net_b200 import med
+    dev = _dev()
+    for W in (640, 1242, 2048):
+        g_dev = med.grid_row(W, dev).cpu()
+        g_cpu = O.identity_grid(1, 1, 2, W)[0, 0, :, 0]
+        assert float((g_dev - g_cpu).abs().max()) <= 1.2e-7
+        mn, mx = disp_range(2)
+        d1, x1 = med.level_tables(mn.to(dev), mx.to(dev), 49, W)
+        d0, x0 = O.level_tables(mn, mx, 49, W)
+        assert rel_err(d1, d0) < 1e-6 and rel_err(x1, x0) < 1e-6
+
+
+def test_integer_and_near_integer_shifts():
+    """Hand-made level tables whose pixel shift is exactly / almost an integer: floor() of the fp32 coordinate
+    wobbles by one across the row, which only the per-pixel generic path reproduces."""
+    B, N, H, W = 1, 12, 3, 640
+    g = torch.Generator().manual_seed(11)
+    logits = 2 * torch.randn(B, N, H, W, generator=g)
+    img = images(B, H, W, 17)
+    gp, gd = torch.randn(B, 3, H, W, generator=g), torch.randn(B, 1, H, W, generator=g)
+    ks = torch.tensor([0.0, 1.0, 2.0, 5.0, 17.0, 64.0, 100.0, 255.0, 300.0, 638.0, 639.0, 700.0])
+    eps = torch.tensor([0, 1e-7, -1e-7, 3e-5, -3e-5, 0, 1e-4, -1e-4, 0, 0, 0, 0])
+    xo = ((ks + eps) * 2.0 / (W - 1)).float().view(1, N)
+    d = (ks + 1.0).view(1, N).float()
+    ref = O.med_forward_closed(logits, img, d, xo)
+    ref["glogits"] = O.med_backward_closed(logits, img, d, xo, gp, gd)
+    r = _run(logits, img, d, xo, gp, gd)
+    for nm in ("pan", "disp", "maskL", "maskR", "glogits"):
+        e = rel_err(r[nm], ref[nm])
+        assert e < TOL, (nm, e)
