@@ -106,11 +106,21 @@ def test_no_mask_variant_and_autograd_wrapper():
     lc = logits.detach().cpu().requires_grad_(True)
     rp, rd = O.med_forward_ops(lc, img.cpu(), mn.cpu(), mx.cpu(), True, False, True)
     (rgl,) = torch.autograd.grad((rp * gp.cpu()).sum() + (rd * gd.cpu()).sum(), lc)
-    assert rel_err(pan, rp) < TOL and rel_err(disp, rd) < TOL and rel_err(gl, rgl) < TOL
+    # med_section builds its level tables with CUDA libm; the oracle's come from CPU libm and differ by
+    # an ulp, i.e. ~2e-5 px of shift -- on white-noise inputs that alone is ~1e-4 of gradient
+    # (coordinate sensitivity).  The strict 1e-4 checks above/below use identical tables.
+    assert rel_err(pan, rp) < 3e-4 and rel_err(disp, rd) < TOL and rel_err(gl, rgl) < 5e-4
     # disparity-only call returns a bare tensor (reference :228-229) and uses the streaming epilogue
     with torch.no_grad():
         donly = med.med_section(logits.detach(), img, mn, mx)
     assert isinstance(donly, torch.Tensor) and rel_err(donly, rd) < TOL
+    # identical (CPU-computed) tables -> strict bound through the same autograd wrapper
+    d0, x0 = O.level_tables(mn.cpu(), mx.cpu(), N, W)
+    g0 = O.identity_grid(1, 1, 2, W)[0, 0, :, 0].contiguous().to(dev)
+    l2 = logits.detach().clone().requires_grad_(True)
+    p2, d2 = med.MedSynthesis.apply(l2, img, x0.to(dev), d0.to(dev), g0, False)
+    (gl2,) = torch.autograd.grad((p2 * gp).sum() + (d2 * gd).sum(), l2)
+    assert rel_err(p2, rp) < TOL and rel_err(d2, rd) < TOL and rel_err(gl2, rgl) < TOL
     # all four outputs, list order [pan, disp, maskL, maskR] (reference :285-297)
     outs = med.med_section(logits.detach(), img, mn, mx, ret_disp=True, ret_subocc=True, ret_pan=True)
     assert len(outs) == 4 and float(outs[2].max()) <= 1.0 and float(outs[3].max()) <= 1.0

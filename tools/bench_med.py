@@ -58,7 +58,12 @@ def bench(B, N, H, W, iters=10, sets=3, peak=6557.8):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--profile", default="", help="B,N,H,W: run each kernel a few times only (for ncu)")
     a = ap.parse_args()
+    if a.profile:
+        B, N, H, W = (int(v) for v in a.profile.split(","))
+        print(json.dumps(bench(B, N, H, W, iters=2, sets=2)))
+        sys.exit(0)
     peak = 6557.8
     try:
         with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) as f:
