@@ -1,0 +1,388 @@
+// conv_tc.cu -- 3x3 convolution as a tcgen05 / TMEM implicit GEMM (bf16 in, fp32 accumulate), sm_100a.
+//
+// Replaces the cuDNN calls behind nn.Conv2d in /root/reference/models/FAL_netB.py:99-127,144-174 and the VGG
+// slices of /root/reference/loss_functions.py:21-29, with bias / ELU / ReLU / residual fused in the epilogue
+// (the reference runs them as separate ATen kernels, :47,59,79).
+//
+// GEMM view:  D[pixel, cout] = sum over (tap, cin) of  A[pixel shifted by tap, cin] * Wt[cout, tap, cin]
+//   * activations are NHWC bf16; an output tile is 8 rows x 16 columns = 128 pixels = the UMMA M dimension
+//   * per K step (one filter tap x one block of BK input channels) the TMA unit fetches
+//       A: a 4-D box [1, 8*s, 16*s, BK] of the input at the tap's offset (element stride s = conv stride),
+//          out-of-image taps zero-filled by the TMA bounds check = the conv's zero padding
+//       B: a 2-D box [BN, BK] of the KRSC weight matrix
+//     both land in shared memory in the 128B(64B)-swizzled K-major layout tcgen05.mma consumes directly
+//   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a TMEM accumulator; tcgen05.commit
+//     releases the smem stage / signals the epilogue through mbarriers
+//   * a second (concatenated) source is just more K steps with its own tensor map: torch.cat never happens
+//   * epilogue warps read TMEM with tcgen05.ld, add bias / residual, apply ELU / ReLU, and write either bf16
+//     NHWC or fp32 planar (the logits layout the MED kernels stream).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace faln {
+namespace {
+
+constexpr int kTH = 8, kTW = 16;  // output tile: 8 x 16 pixels = 128 = UMMA_M
+
+struct ConvParams {
+  int B, H, W, Ho, Wo;
+  int C1, C2, Cin, Cout;
+  int stride, act, planar;
+  int tiles_w, tiles_h;
+  int kblocks1, kblocks2;  // BK-channel blocks of source 1 / source 2
+  const float* bias;
+  const __nv_bfloat16* residual;
+  void* out;
+  long long out_pitch;
+  int out_c;  // channel count (stride) of the NHWC output tensor
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, M = 128, N from idesc, K = 16
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4, [16,30) LBO >> 4 (unused for swizzled K-major), [32,46) SBO >> 4 = 8 rows * row bytes,
+//   [46,48) version = 1 (sm_100), [61,64) layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+template <int BK>
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  constexpr uint64_t row_bytes = BK * 2;
+  constexpr uint64_t sbo = 8 * row_bytes;
+  constexpr uint64_t layout = (BK == 64) ? 2 : 4;
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ULL << 16) | ((sbo >> 4) << 32) | (1ULL << 46) | (layout << 61);
+}
+// tcgen05 instruction descriptor, kind::f16 (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format BF16
+// (bits 7, 10), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : (__expf(v) - 1.0f); }
+
+template <int BK, int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int kA = 128 * BK * 2;
+  static constexpr int kB = BN * BK * 2;
+  static constexpr int kStage = kA + kB;
+  static constexpr int kBars = 1024;  // barriers + tmem pointer
+  static constexpr int kTotal = kBars + STAGES * kStage + 1024 /* alignment slack */;
+};
+
+template <int BK, int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+  using SL = SmemLayout<BK, BN, STAGES>;
+  extern __shared__ unsigned char smem_raw[];
+  // barriers first, then 1024B-aligned operand stages
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  unsigned char* stages = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + SL::kBars + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
+  const int n0 = blockIdx.y * BN;
+  const int ho0 = th * kTH, wo0 = tw * kTW;
+  const int ksteps = 9 * (p.kblocks1 + p.kblocks2);
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmW);
+    if (p.kblocks2) prefetch_tmap(&tmA2);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, BN < 32 ? 32 : BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================================================= TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int kh = tap / 3, kw = tap % 3;
+        const int hi = ho0 * p.stride + kh - 1, wi = wo0 * p.stride + kw - 1;
+        for (int cb = 0; cb < p.kblocks1 + p.kblocks2; ++cb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          unsigned char* a_dst = stages + (size_t)s * SL::kStage;
+          unsigned char* b_dst = a_dst + SL::kA;
+          mbar_arrive_expect_tx(&full[s], SL::kStage);
+          if (cb < p.kblocks1) {
+            tma_load_4d(a_dst, &tmA1, cb * BK, wi, hi, b, &full[s]);
+            tma_load_2d(b_dst, &tmW, tap * p.Cin + cb * BK, n0, &full[s]);
+          } else {
+            tma_load_4d(a_dst, &tmA2, (cb - p.kblocks1) * BK, wi, hi, b, &full[s]);
+            tma_load_2d(b_dst, &tmW, tap * p.Cin + p.C1 + (cb - p.kblocks1) * BK, n0, &full[s]);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int k = 0; k < ksteps; ++k) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(stages + (size_t)s * SL::kStage);
+        const uint64_t adesc = make_desc<BK>(a_addr);
+        const uint64_t bdesc = make_desc<BK>(a_addr + SL::kA);
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
+        }
+        umma_commit(&empty[s]);  // frees the smem stage when these MMAs have read it
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(acc_full);  // accumulator complete
+    }
+  } else {
+    // ================================================================= epilogue (warps 2..5)
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int m = quad * 32 + lane;       // row of the tile = pixel
+    const int ho = ho0 + m / kTW, wo = wo0 + m % kTW;
+    const bool valid = ho < p.Ho && wo < p.Wo;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const size_t pix = ((size_t)b * p.Ho + ho) * p.Wo + wo;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + c0, r);
+      const int cg = n0 + c0;  // first global output channel of this chunk
+      if (!valid || cg >= p.Cout) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (cg + j < p.Cout) v[j] += __ldg(p.bias + cg + j);
+      }
+      if (p.residual) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.out_c + cg);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u = __ldg(rp + q);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 f = __bfloat1622float2(h2[e]);
+            v[q * 8 + 2 * e] += f.x;
+            v[q * 8 + 2 * e + 1] += f.y;
+          }
+        }
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = elu1(v[j]);
+      } else if (p.act == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (p.planar) {
+        float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (cg + j < p.Cout) o[(((size_t)b * p.Cout + cg + j) * p.Ho + ho) * p.out_pitch + wo] = v[j];
+      } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_c + cg;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+          *reinterpret_cast<uint4*>(o + q * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host: tensor maps
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+bool make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int BK, int stride) {
+  auto fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(kTW * stride), (cuuint32_t)(kTH * stride), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool make_w_map(CUtensorMap* m, const void* ptr, int rows, int K, int BK, int BN) {
+  auto fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BK, int BN, int STAGES>
+int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const ConvParams& p, cudaStream_t st) {
+  using SL = SmemLayout<BK, BN, STAGES>;
+  auto kern = conv3x3_tc_kernel<BK, BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal);
+    attr_set = true;
+  }
+  dim3 grid(p.tiles_w * p.tiles_h * p.B, (p.Cout + BN - 1) / BN);
+  kern<<<grid, 192, SL::kTotal, st>>>(a1, a2, w, p);
+  return after_launch("conv3x3_tc_kernel");
+}
+
+}  // namespace
+}  // namespace faln
+
+using namespace faln;
+
+// x [B,H,W,C1] bf16 NHWC, x2 [B,H,W,C2] or NULL (channel-concatenated after x), w [Cout_pad, 3, 3, C1+C2] bf16 (KRSC, rows
+// beyond Cout zero), bias [Cout] fp32 or NULL, residual [B,Ho,Wo,out_c] bf16 or NULL.
+// y: bf16 NHWC [B,Ho,Wo,out_c] (planar = 0) or fp32 planar [B,Cout,Ho,out_pitch] (planar = 1).
+extern "C" int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, const float* bias, const void* residual,
+                                void* y, int B, int H, int W, int C1, int C2, int Cout, int Cout_pad, int stride, int act,
+                                int planar, long long out_pitch, int out_c, faln_stream_t stream) {
+  FALN_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0, "faln_conv3x3_fwd: null pointer / bad shape");
+  FALN_REQUIRE(stride == 1 || stride == 2, "faln_conv3x3_fwd: stride must be 1 or 2");
+  FALN_REQUIRE(C1 % 32 == 0 && C2 % 32 == 0 && C1 > 0 && (x2 != nullptr) == (C2 > 0),
+               "faln_conv3x3_fwd: channel counts must be multiples of 32 (got %d + %d)", C1, C2);
+  FALN_REQUIRE(Cout > 0 && Cout_pad >= Cout && Cout_pad % 32 == 0, "faln_conv3x3_fwd: Cout_pad must be a multiple of 32");
+  FALN_REQUIRE(planar || (out_c % 8 == 0 && out_c >= Cout && Cout % 32 == 0),
+               "faln_conv3x3_fwd: NHWC output needs Cout %% 32 == 0 and out_c %% 8 == 0, out_c >= Cout");
+  FALN_REQUIRE(!planar || out_pitch >= (W - 1) / stride + 1, "faln_conv3x3_fwd: out_pitch too small");
+  const int BK = (C1 % 64 == 0 && C2 % 64 == 0) ? 64 : 32;
+  int BN = Cout_pad % 256 == 0 ? 256 : (Cout_pad % 128 == 0 ? 128 : (Cout_pad % 64 == 0 ? 64 : 32));
+  ConvParams p{};
+  p.B = B; p.H = H; p.W = W;
+  p.Ho = (H - 1) / stride + 1; p.Wo = (W - 1) / stride + 1;
+  p.C1 = C1; p.C2 = C2; p.Cin = C1 + C2; p.Cout = Cout;
+  p.stride = stride; p.act = act; p.planar = planar;
+  p.tiles_w = (p.Wo + kTW - 1) / kTW; p.tiles_h = (p.Ho + kTH - 1) / kTH;
+  p.kblocks1 = C1 / BK; p.kblocks2 = C2 / BK;
+  p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual); p.out = y;
+  p.out_pitch = out_pitch; p.out_c = out_c;
+  CUtensorMap a1, a2, wm;
+  if (!make_act_map(&a1, x, B, H, W, C1, BK, stride) || !make_w_map(&wm, w, Cout_pad, 9 * (C1 + C2), BK, BN) ||
+      (x2 && !make_act_map(&a2, x2, B, H, W, C2, BK, stride))) {
+    set_error("faln_conv3x3_fwd: cuTensorMapEncodeTiled failed (driver entry point missing or bad tensor geometry)");
+    return FALN_ERR_LAUNCH;
+  }
+  if (!x2) a2 = a1;
+  cudaStream_t st = as_stream(stream);
+  if (BK == 64) {
+    switch (BN) {
+      case 256: return launch<64, 256, 4>(a1, a2, wm, p, st);
+      case 128: return launch<64, 128, 6>(a1, a2, wm, p, st);
+      case 64: return launch<64, 64, 8>(a1, a2, wm, p, st);
+      default: return launch<64, 32, 8>(a1, a2, wm, p, st);
+    }
+  } else {
+    switch (BN) {
+      case 256: return launch<32, 256, 6>(a1, a2, wm, p, st);
+      case 128: return launch<32, 128, 8>(a1, a2, wm, p, st);
+      case 64: return launch<32, 64, 8>(a1, a2, wm, p, st);
+      default: return launch<32, 32, 8>(a1, a2, wm, p, st);
+    }
+  }
+}

@@ -1,0 +1,219 @@
+"""Drop-in for /root/reference/loss_functions.py on the fused sm_100a loss kernels.
+
+Same public names and argument meaning: ``vgg`` (callable returning the three pooled VGG19 activations,
+:7-48), ``rec_loss_fnc(mask, synth, label, vgg_label, a_p)`` (:52-56), ``perceptual_loss`` (:59-67),
+``smoothness(img, disp, gamma)`` (:70-101), ``getGrayscale`` (:104-109).  Every function returns a 0-d
+CUDA tensor wired into autograd; values are produced by one kernel each (csrc/losses.cu) instead of
+the reference's ~60 ATen launches, and nothing synchronises with the host.
+
+Extras used by the step bodies (``steps.py``): the ``flip_x`` variants that fold the Stage-2 un-flip
+(/root/reference/Train_Stage2_K.py:283-286) into the loss kernels' indexing, and ``mirror_loss``.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+
+import torch
+
+from . import conv as C
+from . import losses as K
+
+_MEAN = (0.411, 0.432, 0.45)
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers: recover (base tensor, column window) from a column-sliced view such as x[..., c0:]
+# ------------------------------------------------------------------------------------------------
+def _column_window(t: torch.Tensor):
+    """If ``t`` is a view ``base[..., x_lo:x_hi]`` of a contiguous [B,C,H,W] tensor, return
+    (base, x_lo, x_hi); otherwise (t.contiguous(), 0, W')."""
+    B, Cc, H, Wv = t.shape
+    sb, sc, sh, sw = t.stride()
+    if sw == 1 and sh >= Wv and sc == H * sh and sb == Cc * H * sh:
+        Wf = sh
+        x_lo = t.storage_offset() % Wf
+        if x_lo + Wv <= Wf and (t.storage_offset() - x_lo) % (Cc * H * Wf) == 0:
+            try:
+                base = torch.as_strided(t, (B, Cc, H, Wf), (sb, sc, sh, 1), t.storage_offset() - x_lo)
+                return base, x_lo, x_lo + Wv
+            except RuntimeError:
+                pass
+    return t.contiguous(), 0, Wv
+
+
+class _RecL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, synth, label, mask, want_blend, flip_x):
+        synth_c, label_c = synth.contiguous(), label.contiguous()
+        mask_c = mask.contiguous() if mask is not None else None
+        r = K.rec_l1(synth_c, label_c, mask_c, want_blend=want_blend, flip_x=flip_x)
+        ctx.save_for_backward(synth_c, label_c, mask_c)
+        ctx.flip_x = flip_x
+        if want_blend:
+            return r[0], r[1]
+        return r, None
+
+    @staticmethod
+    def backward(ctx, g_val, g_blend):
+        synth, label, mask = ctx.saved_tensors
+        g_dev = g_val.contiguous().float() if g_val is not None else None
+        gs = K.rec_l1_bwd(synth, label, mask, g_blend, 1.0 if g_dev is not None else 0.0, ctx.flip_x, g_dev=g_dev)
+        return gs, None, None, None, None
+
+
+class _Smooth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, disp, gamma, x_lo, x_hi, flip_x):
+        img_c, disp_c = img.contiguous(), disp.contiguous()
+        ctx.save_for_backward(img_c, disp_c)
+        ctx.cfg = (float(gamma), x_lo, x_hi, flip_x)
+        return K.smoothness(img_c, disp_c, gamma, x_lo, x_hi, flip_x)
+
+    @staticmethod
+    def backward(ctx, g_val):
+        img, disp = ctx.saved_tensors
+        gamma, x_lo, x_hi, flip_x = ctx.cfg
+        g = torch.zeros_like(disp)
+        K.smoothness_bwd(img, disp, gamma, 1.0, g, x_lo, x_hi, flip_x, g_dev=g_val.contiguous().float())
+        return None, g, None, None, None, None
+
+
+class _Mirror(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, mdisp, occ, inv_max, x_lo, x_hi, flip_x):
+        disp_c = disp.contiguous()
+        ctx.save_for_backward(disp_c, mdisp, occ, inv_max)
+        ctx.cfg = (x_lo, x_hi, flip_x)
+        return K.mirror(disp_c, mdisp, occ, inv_max, x_lo, x_hi, flip_x)
+
+    @staticmethod
+    def backward(ctx, g_val):
+        disp, mdisp, occ, inv_max = ctx.saved_tensors
+        x_lo, x_hi, flip_x = ctx.cfg
+        g = torch.zeros_like(disp)
+        K.mirror_bwd(disp, mdisp, occ, inv_max, 1.0, g, x_lo, x_hi, flip_x, g_dev=g_val.contiguous().float())
+        return g, None, None, None, None, None, None
+
+
+class _MseBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a_c, b_c = a.contiguous(memory_format=C.CL), b.contiguous(memory_format=C.CL)
+        ctx.save_for_backward(a_c, b_c)
+        return K.mse_bf16(_flat(a_c), _flat(b_c))
+
+    @staticmethod
+    def backward(ctx, g_val):
+        a, b = ctx.saved_tensors
+        g = K.mse_bf16_bwd(_flat(a), _flat(b), 1.0, g_dev=g_val.contiguous().float())
+        return g.view(a.permute(0, 2, 3, 1).shape).permute(0, 3, 1, 2), None
+
+
+def _flat(t):
+    """1-D view over the NHWC memory of a channels_last tensor."""
+    return t.permute(0, 2, 3, 1).reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------------
+# VGG19 perceptual features
+# ------------------------------------------------------------------------------------------------
+class Vgg19_pc(torch.nn.Module):
+    """torchvision VGG19 ``features[0:19]`` -> activations after pool1/pool2/pool3
+    (/root/reference/loss_functions.py:7-44), frozen, evaluated in bf16 NHWC.
+
+    The reference downloads ImageNet weights (``pretrained=True``, :10).  If that checkpoint is present in
+    the torch hub cache it is used; otherwise (no network) a seeded random stand-in is built, which is what
+    BASELINE.json's "random-init weights" benchmark configuration uses."""
+
+    _CONV_IDX = (0, 2, 5, 7, 10, 12, 14, 16)
+
+    def __init__(self, requires_grad=False, seed=2):
+        super().__init__()
+        import torchvision
+        ck = os.path.join(torch.hub.get_dir(), "checkpoints", "vgg19-dcbb9e9d.pth")
+        if os.path.exists(ck):
+            sd = torch.load(ck, map_location="cpu")
+        else:
+            warnings.warn("VGG19 ImageNet weights not found offline; using a seeded random stand-in", stacklevel=2)
+            rng = torch.random.get_rng_state()
+            torch.manual_seed(seed)
+            sd = torchvision.models.vgg19().state_dict()
+            torch.random.set_rng_state(rng)
+        self.weights = torch.nn.ParameterList(
+            [torch.nn.Parameter(sd[f"features.{i}.weight"].clone(), requires_grad=requires_grad) for i in self._CONV_IDX])
+        self.biases = torch.nn.ParameterList(
+            [torch.nn.Parameter(sd[f"features.{i}.bias"].clone(), requires_grad=requires_grad) for i in self._CONV_IDX])
+
+    def forward(self, x, full=False):
+        if full:
+            raise NotImplementedError("slice4 (pool4) is never used on the hot path (reference :36-44)")
+        if x.dtype != torch.bfloat16:
+            x = C.input_to_nhwc(x)
+        return tuple(C.vgg_features(list(zip(self.weights, self.biases)), x))
+
+
+class _LazyVgg:
+    """Module-level ``vgg`` like the reference's global (:48), built on first use on the current device."""
+
+    def __init__(self):
+        self._m = None
+
+    def module(self):
+        if self._m is None:
+            self._m = Vgg19_pc().cuda()
+        return self._m
+
+    def __call__(self, x, full=False):
+        return self.module()(x, full)
+
+
+vgg = _LazyVgg()
+
+
+# ------------------------------------------------------------------------------------------------
+# public loss functions (reference names)
+# ------------------------------------------------------------------------------------------------
+def perceptual_loss(out_vgg, label_vgg, layer=None):
+    if layer is not None:
+        return _MseBf16.apply(out_vgg[layer], label_vgg[layer])
+    l_p = 0
+    for i in range(3):
+        l_p = l_p + _MseBf16.apply(out_vgg[i], label_vgg[i])
+    return l_p
+
+
+def rec_loss_fnc(mask, synth, label, vgg_label, a_p, flip_x=False):
+    """mean(mask*|synth-label|) + a_p * perceptual(vgg(mask*synth + (1-mask)*label), vgg_label)."""
+    m = None if (isinstance(mask, (int, float)) and mask == 1) else mask
+    want_blend = a_p > 0 and vgg_label is not None
+    val, blend = _RecL1.apply(synth, label, m, want_blend, bool(flip_x))
+    if want_blend:
+        val = val + a_p * perceptual_loss(vgg(blend), vgg_label)
+    return val
+
+
+def smoothness(img, disp, gamma=1, flip_x=False, window=None):
+    """Edge-aware smoothness.  Accepts the reference's call style -- column-sliced views such as
+    ``smoothness(left[..., c0:], disp[..., c0:], gamma=2)`` (Train_Stage1_K.py:255) -- in which case the
+    window is recovered from the view; or full tensors plus ``window=(x_lo, x_hi)``."""
+    if window is None:
+        img_b, x_lo, x_hi = _column_window(img)
+        disp_b, d_lo, d_hi = _column_window(disp)          # as_strided is differentiable: grads reach the view
+        if (d_lo, d_hi) != (x_lo, x_hi) or disp_b.shape[3] != img_b.shape[3]:
+            img_b, disp_b, x_lo, x_hi = img.contiguous(), disp.contiguous(), 0, img.shape[3]
+        return _Smooth.apply(img_b, disp_b, gamma, x_lo, x_hi, bool(flip_x))
+    return _Smooth.apply(img, disp, gamma, window[0], window[1], bool(flip_x))
+
+
+def mirror_loss(disp, mdisp, occ, window, flip_x=False, inv_max=None):
+    """mean over the window of (1/max(mdisp_b)) * (1-occ) * |disp - mdisp|  (Train_Stage2_K.py:319-324)."""
+    if inv_max is None:
+        inv_max = K.inv_rowmax(mdisp)
+    return _Mirror.apply(disp, mdisp.contiguous(), occ.contiguous(), inv_max, window[0], window[1], bool(flip_x))
+
+
+def getGrayscale(input):
+    """0.299 R + 0.587 G + 0.114 B as [B,1,H,W] (:104-109).  Plain torch: not on the hot path (the fused
+    smoothness kernel computes the grey value in registers)."""
+    return (0.299 * input[:, 0] + 0.587 * input[:, 1] + 0.114 * input[:, 2]).unsqueeze(1)

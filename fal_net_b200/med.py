@@ -29,6 +29,18 @@ def level_tables(min_disp: torch.Tensor, max_disp: torch.Tensor, no_levels: int,
 
 _G0X_CACHE: dict = {}
 
+# bench.py sets this to a list to collect (kind, start_event, end_event, algorithmic_bytes) per MED launch
+TIMING = None
+
+
+def _timed(kind, nbytes):
+    if TIMING is None:
+        return None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    TIMING.append((kind, e0, e1, nbytes))
+    e0.record()
+    return e1
+
 
 def grid_row(W: int, device) -> torch.Tensor:
     """x row of F.affine_grid(identity, align_corners=True) (/root/reference/models/FAL_netB.py:231-234)."""
@@ -67,9 +79,13 @@ def med_forward_raw(logits, image, x_of, d_lvl, g0x, want_pan=True, want_disp=Tr
     mR = torch.empty(B, 1, H, W, **opt) if want_masks else None
     lse0 = torch.empty(B, 1, H, W, **opt)
     lsew = torch.empty(B, 1, H, W, **opt)
+    # algorithmic bytes: read N logits + 3 image, write 3 pan + 1 disp + 2 stats (+ 2 masks)
+    ev = _timed("med_fwd_masks" if want_masks else "med_fwd", 4 * (N + 3 + 3 + 1 + 2 + (2 if want_masks else 0)) * B * H * W)
     rc = L.faln_med_fwd(_lib.ptr(logits), _lib.ptr(image), _lib.ptr(g0x), _lib.ptr(x_of), _lib.ptr(d_lvl),
                         _lib.ptr(pan), _lib.ptr(disp), _lib.ptr(mL), _lib.ptr(mR), _lib.ptr(lse0), _lib.ptr(lsew),
                         B, N, H, W, pitch, flags, _lib.cur_stream())
+    if ev is not None:
+        ev.record()
     _lib.check(rc, "faln_med_fwd")
     return dict(pan=pan, disp=disp, maskL=mL, maskR=mR, lse0=lse0, lsew=lsew)
 
@@ -83,9 +99,12 @@ def med_backward_raw(logits, image, x_of, d_lvl, g0x, pan, disp, lse0, lsew, g_p
     g_pitch = _pitch_of(out)
     g_pan = _lib.f32c(g_pan, "g_pan") if g_pan is not None else None
     g_disp = _lib.f32c(g_disp, "g_disp") if g_disp is not None else None
+    ev = _timed("med_bwd", 4 * (2 * N + 7) * B * H * W)
     rc = L.faln_med_bwd(_lib.ptr(logits), _lib.ptr(image), _lib.ptr(g0x), _lib.ptr(x_of), _lib.ptr(d_lvl),
                         _lib.ptr(pan), _lib.ptr(disp), _lib.ptr(lse0), _lib.ptr(lsew), _lib.ptr(g_pan),
                         _lib.ptr(g_disp), _lib.ptr(out), B, N, H, W, pitch, g_pitch, flags, _lib.cur_stream())
+    if ev is not None:
+        ev.record()
     _lib.check(rc, "faln_med_bwd")
     return out
 

@@ -1,0 +1,113 @@
+"""Step bodies of the three entry points, on the fused kernels.
+
+  stage1_loss  <- /root/reference/Train_Stage1_K.py:236-258
+  stage2_loss  <- /root/reference/Train_Stage2_K.py:247-327
+  test_disp    <- /root/reference/Test_KITTI.py:196-205, 287-300
+
+Differences from the reference that do not change results beyond fp rounding:
+  * horizontal flips are exact index reversals folded into kernel indexing (``flip_x``) instead of seven
+    bilinear grid_sample calls per step (the reference's flip is only ~1e-4 exact);
+  * no ``.cpu()`` synchronisation inside the step: losses stay on the device.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import loss_functions as LF
+from . import losses as K
+
+
+def stage1_loss(model, left, right, min_disp, max_disp, a_p=0.01, a_sm=0.2 * 2 / 512, vgg=None):
+    """Returns (loss, rec_loss, sm_loss, rpan, ldisp); all device tensors."""
+    W = left.shape[3]
+    rpan, ldisp = model(left, min_disp, max_disp, ret_disp=True, ret_pan=True, ret_subocc=False)
+    vgg_right = None
+    if a_p > 0:
+        with torch.no_grad():
+            vgg_right = (vgg or LF.vgg)(right)
+    rec = LF.rec_loss_fnc(1, rpan, right, vgg_right, a_p)
+    sm = 0
+    if a_sm > 0:
+        # the 20 % left dis-occluded band has no supervision (Train_Stage1_K.py:254-255)
+        sm = LF.smoothness(left, ldisp, gamma=2, window=(int(0.20 * W), W))
+    loss = rec + a_sm * sm
+    return loss, rec, sm, rpan, ldisp
+
+
+def stage2_loss(model, fix_model, left, right, min_disp, max_disp, a_p=0.01, a_sm=0.4 * 2 / 512, a_mr=1.0, vgg=None):
+    """Returns dict(loss, rec, sm, mirror, ...).  ``fix_model`` is the frozen Stage-1 network."""
+    B, _, H, W = left.shape
+    c20, c80 = int(0.20 * W), int(0.80 * W)
+    mn2, mx2 = torch.cat((min_disp, min_disp), 0), torch.cat((max_disp, max_disp), 0)
+    left_f, right_f = torch.flip(left, dims=[3]), torch.flip(right, dims=[3])
+    vgg = vgg or LF.vgg
+
+    mldisp = mrdisp = None
+    if a_mr > 0:
+        with torch.no_grad():                                            # :255-264
+            dfix = fix_model(torch.cat((left_f, right), 0), mn2, mx2, ret_disp=True, ret_pan=False, ret_subocc=False)
+            mldisp = torch.flip(dfix[:B], dims=[3]).contiguous()
+            mrdisp = dfix[B:].contiguous()
+
+    pan, disp, mask0, mask1 = model(torch.cat((left, right_f), 0), mn2, mx2,
+                                    ret_disp=True, ret_pan=True, ret_subocc=True)        # :267-271
+    # second half of the batch lives in flipped coordinates; the un-flip (:283-286) is folded into the kernels
+    rpan, lpan_f = pan[:B], pan[B:]
+    ldisp, rdisp_f = disp[:B], disp[B:]
+
+    vgg_right = vgg_left = None
+    if a_p > 0:
+        with torch.no_grad():
+            vgg_right, vgg_left = vgg(right), vgg(left)
+
+    if a_mr > 0:                                                         # :295-299
+        O_L = K.occ_mask(mask0[:B], mask1[B:], False, True, 0, c20)      # lmask * unflip(lrmask); first 20 % := 1
+        O_R = K.occ_mask(mask0[B:], mask1[:B], True, False, c80, W)      # unflip(rmask) * rlmask; last 20 % := 1
+    else:
+        O_L = O_R = 1
+
+    rec = (LF.rec_loss_fnc(O_R, rpan, right, vgg_right, a_p) +
+           LF.rec_loss_fnc(O_L, lpan_f, left, vgg_left, a_p, flip_x=True)) / 2
+    sm = 0
+    if a_sm > 0:
+        sm = (LF.smoothness(left, ldisp, gamma=2, window=(c20, W)) +
+              LF.smoothness(right, rdisp_f, gamma=2, window=(0, c80), flip_x=True)) / 2
+    mirror = 0
+    if a_mr > 0:
+        mirror = (LF.mirror_loss(ldisp, mldisp, O_L, (c20, W)) +
+                  LF.mirror_loss(rdisp_f, mrdisp, O_R, (0, c80), flip_x=True)) / 2
+    loss = rec + a_sm * sm + a_mr * mirror
+    return dict(loss=loss, rec=rec, sm=sm, mirror=mirror, rpan=rpan, lpan_f=lpan_f, ldisp=ldisp, rdisp_f=rdisp_f,
+                O_L=O_L, O_R=O_R)
+
+
+@torch.no_grad()
+def test_disp(model, image, min_disp, max_disp, f_post_process=False, ms_post_process=False):
+    """Disparity prediction with the reference's two post-processing modes (Test_KITTI.py:196-205)."""
+    disp = model(image, min_disp, max_disp, ret_disp=True, ret_subocc=False, ret_pan=False)
+    if f_post_process:
+        flip_disp = model(torch.flip(image, dims=[3]), min_disp, max_disp, ret_disp=True, ret_subocc=False, ret_pan=False)
+        disp = (disp + torch.flip(flip_disp, dims=[3])) / 2
+    elif ms_post_process:
+        disp = ms_pp(image, model, disp, min_disp, max_disp)
+    return disp
+
+
+@torch.no_grad()
+def ms_pp(input_view, model, disp, min_disp, max_pix):
+    """Multi-scale post-processing (Test_KITTI.py:287-300); the 95th percentile is taken per call over the
+    whole tensor like the reference (which runs with batch 1), on the device (torch.quantile, no host sync)."""
+    B, C, H, W = input_view.shape
+    up_fac = 2 / 3
+    small = F.interpolate(torch.flip(input_view, dims=[3]), scale_factor=up_fac, mode="bilinear", align_corners=True)
+    d2 = model(small, min_disp, max_pix, ret_disp=True, ret_pan=False, ret_subocc=False)
+    d2 = (1 / up_fac) * F.interpolate(d2, size=(H, W), mode="nearest")
+    d2 = torch.flip(d2, dims=[3])
+    flat = disp.reshape(-1).float()
+    k = 0.95 * (flat.numel() - 1)                       # numpy.percentile 'linear' interpolation
+    lo = torch.kthvalue(flat, int(k) + 1).values
+    hi = torch.kthvalue(flat, min(int(k) + 2, flat.numel())).values
+    p95 = lo + (hi - lo) * (k - int(k))
+    norm = torch.clamp(disp / (p95 + 1e-6), max=1.0)
+    return (1 - norm) * disp + norm * d2

@@ -1,0 +1,122 @@
+"""Optimiser + data-parallel plumbing for the Stage-1 / Stage-2 steps.
+
+* All trainable parameters that actually receive gradient (the reference's ``amask_conv`` never does,
+  SURVEY.md 7) are re-homed into ONE flat fp32 arena; their ``.grad`` are views into a second arena.
+  The Adam update of /root/reference/Train_Stage1_K.py:177-181 (two param groups, betas (0.5, 0.999),
+  wd 0) is then a single fused kernel over the arena (csrc/misc.cu) instead of ~150 foreach launches.
+* Data parallelism is one process per GPU (torch.distributed / NCCL over NVLink): the gradient arena is
+  cut into contiguous buckets laid out in the order gradients become ready (decoder first); each bucket
+  is all-reduced asynchronously as soon as its last gradient has been accumulated, overlapping the rest
+  of backward.  ``step()`` waits for the buckets and applies Adam with grad_scale = 1/world_size.
+  (The reference has no distributed code: it wraps the model in single-device DataParallel.)
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import optim
+
+
+class FlatAdamDDP:
+    def __init__(self, model, lr, betas=(0.5, 0.999), eps=1e-8, weight_decay=0.0, bias_decay=0.0,
+                 bucket_mb: float = 16.0, process_group=None, overlap=True, _update=None):
+        if weight_decay != bias_decay:
+            raise NotImplementedError("weight_decay != bias_decay is not supported by the flat arena (both default to 0)")
+        named = model.used_parameters() if hasattr(model, "used_parameters") else list(model.named_parameters())
+        named = [(n, p) for n, p in named if p.requires_grad]
+        # arena order = reverse registration order ~ the order in which backward produces gradients
+        named = list(reversed(named))
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        dev = self.params[0].device
+        sizes = [p.numel() for p in self.params]
+        offs, o = [], 0
+        for s in sizes:
+            offs.append(o)
+            o += (s + 3) // 4 * 4                       # keep every tensor 16-byte aligned inside the arena
+        self.n = (o + 3) // 4 * 4
+        self.offsets = offs
+        self.p = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.g = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        for p, off, s in zip(self.params, offs, sizes):
+            self.p[off:off + s].copy_(p.data.reshape(-1))
+            p.data = self.p[off:off + s].view_as(p.data)
+            p.grad = self.g[off:off + s].view_as(p.data)
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.t = 0
+        self._update = _update or optim.adam_step_     # tests inject a CPU update to exercise the host logic on gloo
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.overlap = overlap and self.world > 1
+        # ---- buckets: contiguous arena ranges of ~bucket_mb
+        self.buckets = []                                # (start, end, [param indices])
+        cap = int(bucket_mb * (1 << 20) / 4)
+        start, members = 0, []
+        for i, (off, s) in enumerate(zip(offs, sizes)):
+            members.append(i)
+            end = off + (s + 3) // 4 * 4
+            if end - start >= cap or i == len(sizes) - 1:
+                self.buckets.append((start, end, members))
+                start, members = end, []
+        self._bucket_of = {}
+        for b, (_, _, mem) in enumerate(self.buckets):
+            for i in mem:
+                self._bucket_of[i] = b
+        self._pending = [0] * len(self.buckets)
+        self._works = []
+        if self.overlap:
+            for i, p in enumerate(self.params):
+                p.register_post_accumulate_grad_hook(self._make_hook(i))
+        self._reset_counts()
+
+    # ------------------------------------------------------------------------------------------
+    def _reset_counts(self):
+        for b, (_, _, mem) in enumerate(self.buckets):
+            self._pending[b] = len(mem)
+        self._works = []
+
+    def _make_hook(self, i):
+        def hook(_p):
+            b = self._bucket_of[i]
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                s, e, _ = self.buckets[b]
+                self._works.append(dist.all_reduce(self.g[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        return hook
+
+    def zero_grad(self):
+        self.g.zero_()
+        for p, off in zip(self.params, self.offsets):      # autograd may have replaced .grad; re-point it
+            if p.grad is None or p.grad.data_ptr() != self.g.data_ptr() + 4 * off:
+                p.grad = self.g[off:off + p.numel()].view_as(p.data)
+        self._reset_counts()
+
+    def broadcast_parameters(self, src=0):
+        if self.world > 1:
+            dist.broadcast(self.p, src=src, group=self.pg)
+
+    def step(self):
+        if self.world > 1:
+            if self.overlap:
+                for w in self._works:
+                    w.wait()
+                # buckets whose hooks did not all fire (should not happen) are reduced here
+                for b, (s, e, _) in enumerate(self.buckets):
+                    if self._pending[b] > 0:
+                        dist.all_reduce(self.g[s:e], op=dist.ReduceOp.SUM, group=self.pg)
+            else:
+                dist.all_reduce(self.g, op=dist.ReduceOp.SUM, group=self.pg)
+        self.t += 1
+        self._update(self.p, self.g, self.m, self.v, None, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
+                         eps=self.eps, weight_decay=self.wd, step=self.t, grad_scale=1.0 / self.world)
+
+    # torch.optim-like conveniences used by the entry points
+    @property
+    def param_groups(self):
+        return [{"lr": self.lr}]
+
+    def set_lr(self, lr):
+        self.lr = lr

@@ -158,6 +158,22 @@ int faln_nhwc_bf16_to_planar(const void* src, float* dst, int B, int C, int H, i
 int faln_planar_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, int W, int Cp,
                              long long pitch, faln_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * tcgen05 / TMEM implicit-GEMM 3x3 convolution, pad 1, stride 1|2 (bf16 in, fp32 accumulate): replaces the
+ * cuDNN calls behind nn.Conv2d at /root/reference/models/FAL_netB.py:99-127,144-174 and the VGG slices at
+ * /root/reference/loss_functions.py:21-29, with bias / ELU / ReLU / residual add (:47,59,79) fused.
+ *   x  [B,H,W,C1] bf16 NHWC; x2 [B,H,W,C2] bf16 or NULL = second source, channel-concatenated after x
+ *      (the skip connections of :153-173 -- torch.cat never materialises); C1, C2 multiples of 32
+ *   w  [Cout_pad,3,3,C1+C2] bf16 (KRSC; rows >= Cout are zero), bias [Cout] fp32 or NULL
+ *   residual [B,Ho,Wo,out_c] bf16 or NULL;  act: 0 none, 1 ELU, 2 ReLU
+ *   y  planar == 0: bf16 NHWC [B,Ho,Wo,out_c];  planar == 1: fp32 [B,Cout,Ho,out_pitch] (the logits layout
+ *      the MED kernels stream; lets the last layer emit fp32 straight from the accumulator)
+ * Ho = (H-1)/stride + 1, Wo likewise.
+ * ---------------------------------------------------------------------------------------------- */
+int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, const float* bias, const void* residual,
+                     void* y, int B, int H, int W, int C1, int C2, int Cout, int Cout_pad, int stride, int act,
+                     int planar, long long out_pitch, int out_c, faln_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,72 @@
+"""GPU: the tcgen05 implicit-GEMM convolution against torch conv2d on the same bf16 operands (fp32 reference math).
+Tolerance: 2e-2 relative (BASELINE north_star, bf16 convolutions); in practice ~4e-3 (bf16 output rounding)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, w, b, stride, act, res):
+    y = F.conv2d(x.float(), w.float(), None if b is None else b.float(), stride, 1)
+    if res is not None:
+        y = y + res.float()
+    if act == 1:
+        y = F.elu(y)
+    elif act == 2:
+        y = F.relu(y)
+    return y
+
+
+@pytest.mark.parametrize("B,H,W,C1,C2,Cout,stride,act,bias,res", [
+    (2, 24, 40, 64, 0, 64, 1, 1, True, False),       # BK=64, BN=64
+    (1, 16, 32, 64, 0, 64, 1, 0, False, False),      # exact tiles, no epilogue extras
+    (2, 24, 80, 128, 0, 256, 2, 1, True, False),     # stride 2, BN=256
+    (2, 47, 156, 32, 0, 32, 1, 1, False, True),      # BK=32 (64B swizzle), residual + ELU, ragged tiles
+    (1, 19, 33, 128, 0, 128, 1, 2, True, False),     # ReLU, odd sizes
+    (2, 12, 40, 128, 256, 256, 1, 1, True, False),   # two sources (skip concat), K = 9*384
+    (3, 3, 10, 512, 0, 512, 1, 1, False, True),      # bottleneck map smaller than one tile
+    (2, 375 // 8, 1242 // 8, 256, 0, 256, 2, 1, True, False),
+    (1, 6, 20, 256, 0, 512, 2, 1, True, False),
+])
+def test_conv3x3_bf16_nhwc(B, H, W, C1, C2, Cout, stride, act, bias, res):
+    from fal_net_b200 import conv_native as CN
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(H * 1000 + W + C1 + Cout)
+    CL = torch.channels_last
+    x = torch.randn(B, C1, H, W, generator=g).bfloat16().to(dev).contiguous(memory_format=CL)
+    x2 = torch.randn(B, C2, H, W, generator=g).bfloat16().to(dev).contiguous(memory_format=CL) if C2 else None
+    Cin = C1 + C2
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5).bfloat16().to(dev)
+    b = torch.randn(Cout, generator=g).to(dev) if bias else None
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    r = torch.randn(B, Cout, Ho, Wo, generator=g).bfloat16().to(dev).contiguous(memory_format=CL) if res else None
+    y = CN.conv3x3_fwd(x, CN.pack_weight(w), b, stride, act, r, x2)
+    torch.cuda.synchronize()
+    xin = x if x2 is None else torch.cat((x, x2), 1)
+    ref = _ref(xin, w, b, stride, act, r)
+    assert y.shape == ref.shape
+    e = rel_err(y.float(), ref)
+    assert e < 2e-2, e
+    assert e < 8e-3, e
+
+
+def test_conv3x3_planar_fp32_logits():
+    """Last layer: concat(64 + 32) -> 49 planes, fp32 planar output with a padded row pitch."""
+    from fal_net_b200 import conv_native as CN, layout
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    CL = torch.channels_last
+    B, H, W, N = 2, 21, 70, 49
+    u = torch.randn(B, 64, H, W, generator=g).bfloat16().to(dev).contiguous(memory_format=CL)
+    s = torch.randn(B, 32, H, W, generator=g).bfloat16().to(dev).contiguous(memory_format=CL)
+    w = (torch.randn(N, 96, 3, 3, generator=g) * 0.05).bfloat16().to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    out = layout.alloc_planar(B, N, H, W, dev)
+    assert out.stride(2) == 72
+    CN.conv3x3_fwd(u, CN.pack_weight(w, 64), b, 1, 0, None, s, cout=N, planar_out=out)
+    torch.cuda.synchronize()
+    ref = _ref(torch.cat((u, s), 1), w, b, 1, 0, None)
+    assert rel_err(out, ref) < 1e-3          # fp32 straight from the accumulator: only operand rounding is shared

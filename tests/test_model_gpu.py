@@ -1,0 +1,130 @@
+"""GPU: the whole FAL_netB path (bf16 convolutions + fused MED + fused losses) against the CPU oracle with the
+same weights and inputs.  Tolerances are BASELINE.json north_star's: bf16 convolutions <= 2e-2 relative on
+outputs, <= 1e-2 on losses."""
+import pytest
+import torch
+
+from oracle import falnet_oracle as O
+from tests.helpers import disp_range, images, rel_err
+
+pytestmark = pytest.mark.gpu
+OUT_TOL, LOSS_TOL = 2e-2, 1e-2
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _model(seed=0, N=49):
+    from fal_net_b200 import models
+    torch.manual_seed(seed)
+    m = models.__dict__["FAL_netB"](None, no_levels=N).to(_dev())
+    p = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    return m, p
+
+
+def _vgg_ws():
+    import torchvision
+    torch.manual_seed(2)
+    sd = torchvision.models.vgg19().state_dict()
+    return [(sd[f"features.{i}.weight"], sd[f"features.{i}.bias"]) for i in (0, 2, 5, 7, 10, 12, 14, 16)]
+
+
+def test_state_dict_contract():
+    m, p = _model()
+    assert list(p.keys()) == list(O.param_shapes(49).keys())
+    assert len(m.weight_parameters()) == 36 and len(m.bias_parameters()) == 14
+    from fal_net_b200 import models
+    m2 = models.FAL_netB({"state_dict": p}, no_levels=49)          # checkpoint dict contract (reference :28-32)
+    assert all(torch.equal(a, b) for a, b in zip(m2.state_dict().values(), p.values()))
+
+
+@pytest.mark.parametrize("H,W", [(48, 160), (50, 166)])
+def test_forward_all_outputs(H, W):
+    dev = _dev()
+    m, p = _model()
+    B = 2
+    left = images(B, H, W, 1234)
+    mn, mx = disp_range(B)
+    with torch.no_grad():
+        pan, disp, mL, mR = m(left.to(dev), mn.to(dev), mx.to(dev), ret_disp=True, ret_subocc=True, ret_pan=True)
+        donly = m(left.to(dev), mn.to(dev), mx.to(dev))
+    rp, rd, rmL, rmR = O.falnet_forward(p, left, mn, mx, True, True, True)
+    assert isinstance(donly, torch.Tensor) and rel_err(donly, rd) < OUT_TOL
+    assert rel_err(disp, rd) < OUT_TOL
+    assert rel_err(pan, rp) < OUT_TOL
+    assert rel_err(mL, rmL) < 5e-2 and rel_err(mR, rmR) < 5e-2
+
+
+def test_stage1_step_loss_and_gradients():
+    from fal_net_b200 import steps
+    dev = _dev()
+    m, p = _model()
+    B, H, W = 2, 48, 160
+    left, right = images(B, H, W, 1234), images(B, H, W, 1235)
+    mn, mx = disp_range(B)
+    loss, rec, sm, _, _ = steps.stage1_loss(m, left.to(dev), right.to(dev), mn.to(dev), mx.to(dev), a_p=0.0)
+    loss.backward()
+    pp = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    lo, rrec, rsm, _, _ = O.stage1_loss(pp, left, right, mn, mx, a_p=0.0)
+    lo.backward()
+    assert rel_err(loss, lo) < LOSS_TOL and rel_err(rec, rrec) < LOSS_TOL and rel_err(sm, rsm) < 3e-2
+    named = dict(m.named_parameters())
+    for k in ("conv0.bias", "conv0.weight", "backbone.iconv1.weight", "backbone.iconv2.0.weight", "backbone.conv3.0.weight",
+              "backbone.conv0.0.weight"):
+        g, r = named[k].grad.cpu().flatten(), pp[k].grad.flatten()
+        cos = float(torch.dot(g, r) / (g.norm() * r.norm()))
+        assert cos > 0.98, (k, cos)
+        assert 0.9 < float(g.norm() / r.norm()) < 1.1, k
+    assert named["backbone.amask_conv.0.weight"].grad is None
+
+
+def test_stage1_with_perceptual_loss():
+    from fal_net_b200 import loss_functions as LF, steps
+    dev = _dev()
+    m, p = _model()
+    B, H, W = 2, 48, 160
+    left, right = images(B, H, W, 1234), images(B, H, W, 1235)
+    mn, mx = disp_range(B)
+    ws = _vgg_ws()
+    vgg = LF.Vgg19_pc().to(dev)
+    for a, (w, _) in zip(vgg.weights, ws):
+        assert torch.equal(a.detach().cpu(), w)
+    loss = steps.stage1_loss(m, left.to(dev), right.to(dev), mn.to(dev), mx.to(dev), a_p=0.01, vgg=vgg)[0]
+    lo = O.stage1_loss(p, left, right, mn, mx, a_p=0.01, vgg_ws=ws)[0]
+    assert rel_err(loss, lo) < LOSS_TOL
+
+
+def test_stage2_loss():
+    from fal_net_b200 import loss_functions as LF, steps
+    dev = _dev()
+    m, p = _model(0)
+    mf, pf = _model(1)
+    B, H, W = 2, 48, 160
+    left, right = images(B, H, W, 1234), images(B, H, W, 1235)
+    mn, mx = disp_range(B)
+    ws = _vgg_ws()
+    vgg = LF.Vgg19_pc().to(dev)
+    res = steps.stage2_loss(m, mf, left.to(dev), right.to(dev), mn.to(dev), mx.to(dev), a_p=0.01, vgg=vgg)
+    res["loss"].backward()
+    # the oracle with exact index flips injected on both sides
+    ref = O.stage2_loss(p, pf, left, right, mn, mx, a_p=0.01, vgg_ws=ws, flip=lambda t: torch.flip(t, dims=[3]))
+    for k, tol in (("loss", LOSS_TOL), ("rec", LOSS_TOL), ("sm", 3e-2), ("mirror", 3e-2)):
+        assert rel_err(res[k], ref[k]) < tol, (k, float(res[k]), float(ref[k]))
+    assert rel_err(res["O_L"], ref["O_L"]) < 5e-2 and rel_err(res["O_R"], ref["O_R"]) < 5e-2
+    assert all(torch.isfinite(q.grad).all() for _, q in m.used_parameters())
+
+
+def test_inference_post_processing():
+    from fal_net_b200 import steps
+    dev = _dev()
+    m, p = _model()
+    B, H, W = 1, 54, 180
+    img = images(B, H, W, 77)
+    mn, mx = disp_range(B)
+    flip = lambda t: torch.flip(t, dims=[3])
+    d_fpp = steps.test_disp(m, img.to(dev), mn.to(dev), mx.to(dev), f_post_process=True)
+    assert rel_err(d_fpp, O.test_disp_fpp(p, img, mn, mx, flip=flip)) < OUT_TOL
+    d_ms = steps.test_disp(m, img.to(dev), mn.to(dev), mx.to(dev), ms_post_process=True)
+    assert rel_err(d_ms, O.test_disp_mspp(p, img, mn, mx, flip=flip)) < 3e-2
