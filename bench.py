@@ -290,7 +290,7 @@ def run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP
         step_dev(*devb[i % nb])
     sync_all()
     med.TIMING = []
-    lib_conv0 = C.LIBRARY_CALLS["conv2d"]
+    lib_conv0 = C.LIBRARY_CALLS["conv_backward"]
     launches0 = _lib.launch_count()
     clocks = ClockSampler(dev.index or 0)
     if rank == 0:
@@ -305,7 +305,7 @@ def run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP
     ms = e0.elapsed_time(e1) / a.steps
     clk = clocks.stop() if rank == 0 else None
     launches = _lib.launch_count() - launches0
-    lib_convs = C.LIBRARY_CALLS["conv2d"] - lib_conv0
+    lib_convs = C.LIBRARY_CALLS["conv_backward"] - lib_conv0
     timing, med.TIMING = med.TIMING, None
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -356,7 +356,7 @@ def run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP
         "e2e": {"value": frames_per_step / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
-        "library_conv_calls_in_timed_region": lib_convs,
+        "library_conv_backward_calls_in_timed_region": lib_convs,
         "roofline": roofline,
     }
     if rank == 0 and not a.no_cpu_baseline and world == 1:

@@ -43,7 +43,10 @@ _SIGNATURES = {
     "faln_nchw_to_nhwc_bf16": [_p, _p] + [_i] * 6 + [_p],
     "faln_nhwc_bf16_to_planar": [_p, _p] + [_i] * 5 + [_ll, _p],
     "faln_planar_to_nhwc_bf16": [_p, _p] + [_i] * 5 + [_ll, _p],
-    "faln_conv3x3_fwd": [_p] * 6 + [_i] * 10 + [_ll, _i, _p],
+    "faln_conv3x3_fwd": [_p] * 8 + [_i] * 10 + [_ll, _i, _p],
+    "faln_stem_conv": [_p] * 4 + [_i] * 6 + [_p],
+    "faln_upsample_nearest_nhwc": [_p, _p] + [_i] * 6 + [_p],
+    "faln_maxpool2_nhwc": [_p, _p] + [_i] * 4 + [_p],
 }
 _RESTYPES = {"faln_last_error": _C.c_char_p, "faln_launch_count": _C.c_longlong}
 

@@ -1,56 +1,182 @@
 """Convolution front-end of the encoder-decoder and the VGG perceptual slices.
 
-Activations are bf16 tensors of logical shape [B,C,H,W] in ``torch.channels_last`` memory format,
-i.e. NHWC in memory -- the layout the tcgen05 implicit-GEMM kernels (csrc/conv_tc.cu) consume.
+Activations are bf16 tensors of logical shape [B,C,H,W] in ``torch.channels_last`` memory format, i.e. NHWC
+in memory -- the layout the tcgen05 implicit-GEMM kernels (csrc/conv_tc.cu) consume through TMA.
 
-STATUS (round 1): the hand-written tcgen05 kernels are being brought up layer family by layer family;
-every call that is not yet served natively goes through ``torch.nn.functional.conv2d`` (cuDNN, bf16,
-fp32 accumulate) and is COUNTED in ``LIBRARY_CALLS`` so that bench.py can report which share of the
-step still runs on library kernels.  This is a temporary bring-up path on the GPU, not a CPU fallback:
-nothing here runs without CUDA.
+FORWARD is always the hand-written sm_100a path: the stem kernel for the 3-channel image, tcgen05/TMEM
+implicit GEMM for every other 3x3 conv with bias / ELU / ReLU / residual fused in the epilogue, the skip
+concatenation expressed as a second TMA source (no torch.cat), the constant max_disp/100 plane folded into
+a border-class bias table, and the logit 1x1 conv folded into the last 3x3 conv whose epilogue writes fp32
+planar logits.
+
+BACKWARD (round 1 status): data- and weight-gradients of the convolutions are still computed with
+``aten.convolution_backward`` (cuDNN, bf16) -- counted in ``LIBRARY_CALLS`` so bench.py reports how much of
+the step is library code.  Native tcgen05 dgrad / wgrad kernels are the next milestone.  Nothing here
+runs without CUDA.
 """
 from __future__ import annotations
 
 import torch
 import torch.nn.functional as F
 
-LIBRARY_CALLS = {"conv2d": 0}
+from . import conv_native as CN
+
+LIBRARY_CALLS = {"conv_backward": 0}
+
+# packed bf16 KRSC weights, keyed by (id(param), param._version, generation): parameters that do not change
+# (frozen Stage-1 model, VGG, inference) are packed once; the trainer bumps GENERATION after each fused-Adam
+# step because the kernel updates the arena behind torch's version counter.
+_PACKED: dict = {}
+GENERATION = [0]
+
+
+def invalidate_packed_weights():
+    GENERATION[0] += 1
+    if len(_PACKED) > 4096:
+        _PACKED.clear()
+
+
+def _packed(weight, cin, tag):
+    if weight.grad_fn is not None:                   # derived tensor (the folded logit conv): pack every call
+        return CN.pack_weight(weight[:, :cin])
+    key = (id(weight), weight._version, GENERATION[0] if weight.requires_grad else -1, cin, tag)
+    hit = _PACKED.get(key)
+    if hit is None:
+        hit = CN.pack_weight(weight[:, :cin])
+        _PACKED[key] = hit
+    return hit
 CL = torch.channels_last
+_ACT = CN.ACT
 
 
 def input_to_nhwc(x: torch.Tensor) -> torch.Tensor:
-    """fp32 NCHW image -> bf16 NHWC activation."""
+    """fp32 NCHW image -> bf16 NHWC activation (only used where the stem kernel is not)."""
     return x.to(dtype=torch.bfloat16, memory_format=CL)
 
 
-def _act(y, act):
-    if act == "elu":
-        return F.elu(y)
-    if act == "relu":
-        return F.relu(y)
-    return y
+def _act_grad(g, y, act):
+    """gradient w.r.t. the pre-activation, from the (saved) activation output y."""
+    if act == 1:                                   # ELU: d/dx = 1 (x>0) else exp(x) = y + 1
+        return g * torch.where(y > 0, torch.ones_like(y), y + 1)
+    if act == 2:
+        return g * (y > 0).to(g.dtype)
+    return g
+
+
+def _conv_backward(g_pre, xin, w16, want_x, want_w, want_b, stride):
+    LIBRARY_CALLS["conv_backward"] += 1
+    return torch.ops.aten.convolution_backward(g_pre, xin, w16, [w16.shape[0]] if want_b else None, [stride, stride],
+                                               [1, 1], [1, 1], False, [0, 0], 1, [want_x, want_w, want_b])
+
+
+class _Conv3x3(torch.autograd.Function):
+    """y = act(conv3x3(cat(up(x), x2, const)) + bias + residual); forward native, backward see module docstring."""
+
+    @staticmethod
+    def forward(ctx, x, x2, residual, weight, bias, const_val, stride, act, up_to, planar):
+        xu = CN.upsample_nearest(x, up_to) if up_to is not None else x.contiguous(memory_format=CL)
+        C1 = xu.shape[1]
+        C2 = x2.shape[1] if x2 is not None else 0
+        ctab = None
+        if const_val is not None:
+            ctab = CN.const_channel_table(weight[:, C1 + C2].detach())
+            const_val = const_val.detach().float().contiguous()
+        wk = _packed(weight, C1 + C2, "w")
+        if planar:
+            from . import layout
+            B, _, H, W = xu.shape
+            out = layout.alloc_planar(B, weight.shape[0], H, W, xu.device)
+            y = CN.conv3x3_fwd(xu, wk, bias, stride, act, None, x2, cout=weight.shape[0], planar_out=out)
+        else:
+            y = CN.conv3x3_fwd(xu, wk, bias, stride, act, residual, x2, cout=weight.shape[0], ctab=ctab, cscale=const_val)
+        ctx.save_for_backward(x, xu if up_to is not None else None, x2, weight, const_val, y if act else None)
+        ctx.cfg = (stride, act, up_to, bias is not None, residual is not None, planar)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, xu, x2, weight, const_val, y = ctx.saved_tensors
+        stride, act, up_to, has_bias, has_res, planar = ctx.cfg
+        if planar:
+            g = g.to(dtype=torch.bfloat16, memory_format=CL)
+        else:
+            g = g.contiguous(memory_format=CL)
+        g_pre = _act_grad(g, y, act).contiguous(memory_format=CL)
+        src = xu if xu is not None else x
+        parts = [src.contiguous(memory_format=CL)]
+        if x2 is not None:
+            parts.append(x2)
+        if const_val is not None:
+            B, _, H, W = src.shape
+            parts.append(const_val.to(src.dtype).view(B, 1, 1, 1).expand(B, 1, H, W))
+        xin = parts[0] if len(parts) == 1 else torch.cat(parts, 1).contiguous(memory_format=CL)
+        need_x = ctx.needs_input_grad[0] or (x2 is not None and ctx.needs_input_grad[1])
+        gx, gw, gb = _conv_backward(g_pre, xin, weight.to(torch.bfloat16), need_x, ctx.needs_input_grad[3],
+                                    has_bias and ctx.needs_input_grad[4], stride)
+        g_x = g_x2 = None
+        if need_x:
+            C1 = src.shape[1]
+            g_src = gx[:, :C1]
+            if x2 is not None and ctx.needs_input_grad[1]:
+                g_x2 = gx[:, C1:C1 + x2.shape[1]]
+            if ctx.needs_input_grad[0]:
+                if up_to is not None and tuple(x.shape[2:]) != tuple(up_to):
+                    g_x = torch.ops.aten.upsample_nearest2d_backward(g_src.contiguous(memory_format=CL), list(up_to),
+                                                                     list(x.shape), None, None)
+                else:
+                    g_x = g_src
+        g_res = g_pre if (has_res and ctx.needs_input_grad[2]) else None
+        return (g_x, g_x2, g_res, None if gw is None else gw.float(), None if gb is None else gb.float(), None, None,
+                None, None, None)
+
+
+class _Stem(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        y = CN.stem_conv(x, weight, bias, act)
+        ctx.save_for_backward(x, weight, y if act else None)
+        ctx.cfg = (act, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, y = ctx.saved_tensors
+        act, has_bias = ctx.cfg
+        g_pre = _act_grad(g.contiguous(memory_format=CL), y, act).contiguous(memory_format=CL)
+        gx, gw, gb = _conv_backward(g_pre, input_to_nhwc(x), weight.to(torch.bfloat16), ctx.needs_input_grad[0],
+                                    ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2], 1)
+        return (None if gx is None else gx.float().contiguous(), None if gw is None else gw.float(),
+                None if gb is None else gb.float(), None)
+
+
+class _MaxPool2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = CN.maxpool2(x)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        with torch.enable_grad():
+            xr = x.detach().requires_grad_(True)
+            F.max_pool2d(xr, 2, 2).backward(g)
+        return xr.grad
+
+
+def stem(x, weight, bias, act="elu"):
+    """First layer on the fp32 NCHW image (reads it directly, writes bf16 NHWC)."""
+    return _Stem.apply(x, weight, bias, _ACT[act])
 
 
 def conv3x3(x, weight, bias=None, stride=1, act=None, residual=None, const_channel=None, upsample_to=None, concat=None):
-    """y = act(conv3x3(gather(x)) + bias [+ residual]) with pad 1.
+    """y = act(conv3x3(gather(x)) + bias [+ residual]), pad 1.
 
-    gather(x) = nearest-upsample to ``upsample_to`` (reference deconv, models/FAL_netB.py:58), then channel
-    concat with ``concat`` (skip connection, :153-173) and/or with a per-sample constant plane
-    ``const_channel`` [B] (the max_disp/100 "flow" channel, :145,208-209)."""
-    if upsample_to is not None and tuple(x.shape[2:]) != tuple(upsample_to):
-        x = F.interpolate(x, size=upsample_to, mode="nearest")
-    if concat is not None:
-        x = torch.cat((x, concat), 1)
-    if const_channel is not None:
-        B, _, H, W = x.shape
-        plane = const_channel.to(x.dtype).view(B, 1, 1, 1).expand(B, 1, H, W)
-        x = torch.cat((x, plane), 1)
-    x = x.contiguous(memory_format=CL)
-    LIBRARY_CALLS["conv2d"] += 1
-    y = F.conv2d(x, weight.to(torch.bfloat16), None if bias is None else bias.to(torch.bfloat16), stride, 1)
-    if residual is not None:
-        y = y + residual
-    return _act(y, act)
+    gather(x) = nearest-upsample to ``upsample_to`` (reference deconv, models/FAL_netB.py:58), channel concat with
+    ``concat`` (skip connection, :153-173) and/or with a per-sample constant plane ``const_channel`` [B] (the
+    max_disp/100 "flow" channel, :145,208-209)."""
+    return _Conv3x3.apply(x, concat, residual, weight, bias, const_channel, stride, _ACT[act], upsample_to, False)
 
 
 def fold_logit_conv(w_iconv1, w0, b0):
@@ -60,12 +186,10 @@ def fold_logit_conv(w_iconv1, w0, b0):
 
 
 def conv3x3_logits(u, skip, w_iconv1, w0, b0):
-    """Last layer: concat(u, skip) -> folded 3x3 conv -> fp32 planar logits [B,N,H,W]."""
+    """Last layer: (u, skip) as two TMA sources -> folded 3x3 conv -> fp32 planar logits [B,N,H,W] (row pitch a
+    multiple of 16 bytes), written straight from the fp32 accumulator."""
     w, b = fold_logit_conv(w_iconv1, w0, b0)
-    x = torch.cat((u, skip), 1).contiguous(memory_format=CL)
-    LIBRARY_CALLS["conv2d"] += 1
-    y = F.conv2d(x, w.to(torch.bfloat16), None, 1, 1)
-    return (y.float() + b.view(1, -1, 1, 1)).contiguous()
+    return _Conv3x3.apply(u, skip, None, w, b, None, 1, 0, None, True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -75,14 +199,14 @@ VGG_CFG = (64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M")
 
 
 def vgg_features(ws, x):
-    """ws: list of (weight fp32 [Co,Ci,3,3], bias fp32 [Co]) for the 8 convs; x bf16 NHWC (3 channels)."""
+    """ws: list of (weight fp32 [Co,Ci,3,3], bias fp32 [Co]) for the 8 convs; x fp32 NCHW image [B,3,H,W]."""
     outs, i = [], 0
     for v in VGG_CFG:
         if v == "M":
-            x = F.max_pool2d(x, 2, 2)
+            x = _MaxPool2.apply(x)
             outs.append(x)
         else:
             w, b = ws[i]
-            x = conv3x3(x, w, b, act="relu")
+            x = stem(x, w, b, "relu") if i == 0 else conv3x3(x, w, b, act="relu")
             i += 1
     return outs

@@ -1,4 +1,6 @@
-"""Thin torch wrappers over the tcgen05 implicit-GEMM convolution kernels (csrc/conv_tc.cu)."""
+"""Thin torch wrappers over the tcgen05 implicit-GEMM convolution kernels (csrc/conv_tc.cu, csrc/conv_aux.cu).
+
+Activations: bf16 tensors of logical shape [B,C,H,W] in channels_last memory format (= NHWC in memory)."""
 from __future__ import annotations
 
 import torch
@@ -6,6 +8,7 @@ import torch
 from . import _lib
 
 CL = torch.channels_last
+ACT = {None: 0, "none": 0, "elu": 1, "relu": 2}
 
 
 def pack_weight(w: torch.Tensor, cout_pad: int | None = None) -> torch.Tensor:
@@ -17,12 +20,25 @@ def pack_weight(w: torch.Tensor, cout_pad: int | None = None) -> torch.Tensor:
     return out
 
 
+def const_channel_table(wf: torch.Tensor, cout_pad=None) -> torch.Tensor:
+    """wf [Cout,3,3]: weights of a spatially constant input channel -> [16,Cout] sums over the taps that stay inside
+    the image, per border class rc*4+cc (bit0: first tap outside, bit1: last tap outside)."""
+    rows = []
+    for rc in range(4):
+        kh = [k for k in range(3) if not ((k == 0 and rc & 1) or (k == 2 and rc & 2))]
+        for cc in range(4):
+            kw = [k for k in range(3) if not ((k == 0 and cc & 1) or (k == 2 and cc & 2))]
+            rows.append(wf[:, kh][:, :, kw].sum(dim=(1, 2)))
+    return torch.stack(rows, 0).float().contiguous()
+
+
 def _nhwc(t: torch.Tensor) -> torch.Tensor:
     assert t.dtype == torch.bfloat16 and t.is_cuda
     return t.contiguous(memory_format=CL)
 
 
-def conv3x3_fwd(x, w_krsc, bias=None, stride=1, act=0, residual=None, x2=None, cout=None, planar_out=None):
+def conv3x3_fwd(x, w_krsc, bias=None, stride=1, act=0, residual=None, x2=None, cout=None, planar_out=None, ctab=None,
+                cscale=None):
     """x, x2, residual: bf16 [B,C,H,W] channels_last.  Returns bf16 [B,Cout,Ho,Wo] channels_last, or fills and returns
     ``planar_out`` (fp32 [B,Cout,Ho,Wo] with uniform row pitch) when given."""
     x = _nhwc(x)
@@ -47,8 +63,42 @@ def conv3x3_fwd(x, w_krsc, bias=None, stride=1, act=0, residual=None, x2=None, c
     else:
         y = torch.empty((B, cout, Ho, Wo), device=x.device, dtype=torch.bfloat16, memory_format=CL)
         planar, pitch, out_c = 0, 0, cout
-    rc = _lib.lib().faln_conv3x3_fwd(_lib.ptr(x), _lib.ptr(x2), _lib.ptr(w_krsc), _lib.ptr(bias), _lib.ptr(residual),
-                                     _lib.ptr(y), B, H, W, C1, C2, cout, cout_pad, stride, act, planar, pitch, out_c,
-                                     _lib.cur_stream())
+    rc = _lib.lib().faln_conv3x3_fwd(_lib.ptr(x), _lib.ptr(x2), _lib.ptr(w_krsc), _lib.ptr(bias), _lib.ptr(ctab),
+                                     _lib.ptr(cscale), _lib.ptr(residual), _lib.ptr(y), B, H, W, C1, C2, cout, cout_pad,
+                                     stride, int(act), planar, pitch, out_c, _lib.cur_stream())
     _lib.check(rc, "faln_conv3x3_fwd")
+    return y
+
+
+def stem_conv(x, w, bias, act, flip_x=False):
+    """fp32 NCHW image [B,3,H,W] -> bf16 channels_last [B,Cout,H,W]; w [Cout,3,3,3] fp32."""
+    x = _lib.f32c(x)
+    B, _, H, W = x.shape
+    Cout = w.shape[0]
+    y = torch.empty((B, Cout, H, W), device=x.device, dtype=torch.bfloat16, memory_format=CL)
+    rc = _lib.lib().faln_stem_conv(_lib.ptr(x), _lib.ptr(w.detach().float().contiguous()),
+                                   _lib.ptr(None if bias is None else bias.detach().float().contiguous()), _lib.ptr(y), B, H,
+                                   W, Cout, int(act), int(flip_x), _lib.cur_stream())
+    _lib.check(rc, "faln_stem_conv")
+    return y
+
+
+def upsample_nearest(x, size):
+    x = _nhwc(x)
+    B, C, Hi, Wi = x.shape
+    Ho, Wo = size
+    if (Hi, Wi) == (Ho, Wo):
+        return x
+    y = torch.empty((B, C, Ho, Wo), device=x.device, dtype=torch.bfloat16, memory_format=CL)
+    rc = _lib.lib().faln_upsample_nearest_nhwc(_lib.ptr(x), _lib.ptr(y), B, Hi, Wi, Ho, Wo, C, _lib.cur_stream())
+    _lib.check(rc, "faln_upsample_nearest_nhwc")
+    return y
+
+
+def maxpool2(x):
+    x = _nhwc(x)
+    B, C, Hi, Wi = x.shape
+    y = torch.empty((B, C, Hi // 2, Wi // 2), device=x.device, dtype=torch.bfloat16, memory_format=CL)
+    rc = _lib.lib().faln_maxpool2_nhwc(_lib.ptr(x), _lib.ptr(y), B, Hi, Wi, C, _lib.cur_stream())
+    _lib.check(rc, "faln_maxpool2_nhwc")
     return y

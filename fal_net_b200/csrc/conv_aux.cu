@@ -1,0 +1,156 @@
+// conv_aux.cu -- the small CUDA-core kernels around the tcgen05 convolution: the 3-channel stem convolution
+// (K = 27 is too thin for a tensor-core tile and its input is the fp32 NCHW image itself), nearest upsampling,
+// 2x2 max-pooling, all on bf16 NHWC activations.  All are HBM-bound streaming kernels.
+#include "common.cuh"
+
+namespace faln {
+namespace {
+
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : (__expf(v) - 1.0f); }
+
+// Stem: y[b,h,w,:] = act(bias + sum_{c<3,kh,kw} w[co,c,kh,kw] * x[b,c,h+kh-1,w+kw-1]), x fp32 NCHW (optionally read
+// x-reversed), y bf16 NHWC.  One thread per output pixel, COUT accumulators in registers, weights broadcast from
+// shared memory.  Replaces conv0.0 (/root/reference/models/FAL_netB.py:99) and VGG conv1_1.
+template <int COUT>
+__global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                        int B, int H, int W, int act, int flip_x) {
+  __shared__ float ws[27 * COUT];  // [tap][c][co] -> index (c*9 + kh*3 + kw) * COUT + co
+  __shared__ float bs[COUT];
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
+    const int co = i % COUT, t = i / COUT;  // t = c*9 + kh*3 + kw
+    ws[i] = __ldg(w + co * 27 + t);
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = bias ? __ldg(bias + i) : 0.f;
+  __syncthreads();
+  const long long npx = (long long)B * H * W;
+  const long long hw = (long long)H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+    const int xw = (int)(i % W);
+    const int yh = (int)((i / W) % H);
+    const long long b = i / hw;
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = bs[co];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int yy = yh + kh - 1;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int xx = xw + kw - 1;
+          float v = 0.f;
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const int xs = flip_x ? W - 1 - xx : xx;
+            v = __ldg(x + (b * 3 + c) * hw + (long long)yy * W + xs);
+          }
+          const float* wp = ws + (c * 9 + kh * 3 + kw) * COUT;
+#pragma unroll
+          for (int co = 0; co < COUT; ++co) acc[co] = fmaf(v, wp[co], acc[co]);
+        }
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(y + i * COUT);
+#pragma unroll
+    for (int q = 0; q < COUT / 8; ++q) {
+      uint4 u;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float a0 = acc[q * 8 + 2 * e], a1 = acc[q * 8 + 2 * e + 1];
+        if (act == 1) { a0 = elu1(a0); a1 = elu1(a1); }
+        else if (act == 2) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+        h2[e] = __floats2bfloat162_rn(a0, a1);
+      }
+      dst[q] = u;
+    }
+  }
+}
+
+// Nearest upsampling with PyTorch's legacy 'nearest' index rule src = min(floor(dst * in/out), in-1)
+// (F.interpolate(mode='nearest'), /root/reference/models/FAL_netB.py:58), bf16 NHWC, 16 bytes per thread.
+__global__ void __launch_bounds__(256) upsample_nearest_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B,
+                                                               int Hi, int Wi, int Ho, int Wo, int C8, float sh, float sw) {
+  const long long n = (long long)B * Ho * Wo * C8;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % C8);
+    long long r = i / C8;
+    const int wo = (int)(r % Wo);
+    r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    const int hi = min((int)floorf(ho * sh), Hi - 1), wi = min((int)floorf(wo * sw), Wi - 1);
+    dst[i] = __ldg(src + (((long long)b * Hi + hi) * Wi + wi) * C8 + c);
+  }
+}
+
+// 2x2 / stride-2 max pooling (floor mode), bf16 NHWC.
+__global__ void __launch_bounds__(256) maxpool2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int Hi,
+                                                       int Wi, int C8) {
+  const int Ho = Hi / 2, Wo = Wi / 2;
+  const long long n = (long long)B * Ho * Wo * C8;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % C8);
+    long long r = i / C8;
+    const int wo = (int)(r % Wo);
+    r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    const uint4* p = src + (((long long)b * Hi + 2 * ho) * Wi + 2 * wo) * C8 + c;
+    uint4 a = __ldg(p), bq = __ldg(p + C8), cq = __ldg(p + (long long)Wi * C8), d = __ldg(p + (long long)Wi * C8 + C8);
+    uint4 o;
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&bq);
+    const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&cq);
+    const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&d);
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o2[e] = __hmax2(__hmax2(a2[e], b2[e]), __hmax2(c2[e], d2[e]));
+    dst[i] = o;
+  }
+}
+
+inline int ew_grid(long long n, int threads) {
+  long long g = (n + threads - 1) / threads;
+  long long cap = (long long)sm_count() * 32;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+}  // namespace faln
+
+using namespace faln;
+
+extern "C" int faln_stem_conv(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int Cout,
+                              int act, int flip_x, faln_stream_t stream) {
+  FALN_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0, "faln_stem_conv: bad argument");
+  FALN_REQUIRE(Cout == 32 || Cout == 64, "faln_stem_conv: Cout must be 32 or 64 (got %d)", Cout);
+  const long long npx = (long long)B * H * W;
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(y);
+  if (Cout == 32)
+    stem_conv_kernel<32><<<ew_grid(npx, 128), 128, 0, as_stream(stream)>>>(x, w, bias, out, B, H, W, act, flip_x);
+  else
+    stem_conv_kernel<64><<<ew_grid(npx, 128), 128, 0, as_stream(stream)>>>(x, w, bias, out, B, H, W, act, flip_x);
+  return after_launch("stem_conv_kernel");
+}
+
+extern "C" int faln_upsample_nearest_nhwc(const void* src, void* dst, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                                          faln_stream_t stream) {
+  FALN_REQUIRE(src && dst && B > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C % 8 == 0, "faln_upsample_nearest_nhwc: C %% 8");
+  const long long n = (long long)B * Ho * Wo * (C / 8);
+  upsample_nearest_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(
+      static_cast<const uint4*>(src), static_cast<uint4*>(dst), B, Hi, Wi, Ho, Wo, C / 8, (float)Hi / (float)Ho,
+      (float)Wi / (float)Wo);
+  return after_launch("upsample_nearest_kernel");
+}
+
+extern "C" int faln_maxpool2_nhwc(const void* src, void* dst, int B, int Hi, int Wi, int C, faln_stream_t stream) {
+  FALN_REQUIRE(src && dst && B > 0 && Hi >= 2 && Wi >= 2 && C % 8 == 0, "faln_maxpool2_nhwc: bad argument");
+  const long long n = (long long)B * (Hi / 2) * (Wi / 2) * (C / 8);
+  maxpool2_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), B,
+                                                                  Hi, Wi, C / 8);
+  return after_launch("maxpool2_kernel");
+}

@@ -36,6 +36,8 @@ struct ConvParams {
   int tiles_w, tiles_h;
   int kblocks1, kblocks2;  // BK-channel blocks of source 1 / source 2
   const float* bias;
+  const float* ctab;    // [16][Cout] border-class sums of the constant-channel weights, or NULL
+  const float* cscale;  // [B] value of the constant channel per sample
   const __nv_bfloat16* residual;
   void* out;
   long long out_pitch;
@@ -231,6 +233,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         for (int j = 0; j < 32; ++j)
           if (cg + j < p.Cout) v[j] += __ldg(p.bias + cg + j);
       }
+      if (p.ctab) {
+        // a spatially constant extra input channel (the max_disp/100 plane of reference :145,208-209) contributes
+        // value * (sum of its weights over the taps that fall inside the image): a per-border-class bias
+        const int rc = (ho == 0 ? 1 : 0) | (p.stride * ho + 1 > p.H - 1 ? 2 : 0);
+        const int cc = (wo == 0 ? 1 : 0) | (p.stride * wo + 1 > p.W - 1 ? 2 : 0);
+        const float* t = p.ctab + (size_t)(rc * 4 + cc) * p.Cout + cg;
+        const float sc = __ldg(p.cscale + b);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (cg + j < p.Cout) v[j] = fmaf(sc, __ldg(t + j), v[j]);
+      }
       if (p.residual) {
         const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.out_c + cg);
 #pragma unroll
@@ -340,11 +353,12 @@ using namespace faln;
 // x [B,H,W,C1] bf16 NHWC, x2 [B,H,W,C2] or NULL (channel-concatenated after x), w [Cout_pad, 3, 3, C1+C2] bf16 (KRSC, rows
 // beyond Cout zero), bias [Cout] fp32 or NULL, residual [B,Ho,Wo,out_c] bf16 or NULL.
 // y: bf16 NHWC [B,Ho,Wo,out_c] (planar = 0) or fp32 planar [B,Cout,Ho,out_pitch] (planar = 1).
-extern "C" int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, const float* bias, const void* residual,
-                                void* y, int B, int H, int W, int C1, int C2, int Cout, int Cout_pad, int stride, int act,
+extern "C" int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, const float* bias, const float* ctab,
+                                const float* cscale, const void* residual, void* y, int B, int H, int W, int C1, int C2, int Cout, int Cout_pad, int stride, int act,
                                 int planar, long long out_pitch, int out_c, faln_stream_t stream) {
   FALN_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0, "faln_conv3x3_fwd: null pointer / bad shape");
   FALN_REQUIRE(stride == 1 || stride == 2, "faln_conv3x3_fwd: stride must be 1 or 2");
+  FALN_REQUIRE((ctab == nullptr) == (cscale == nullptr), "faln_conv3x3_fwd: ctab and cscale go together");
   FALN_REQUIRE(C1 % 32 == 0 && C2 % 32 == 0 && C1 > 0 && (x2 != nullptr) == (C2 > 0),
                "faln_conv3x3_fwd: channel counts must be multiples of 32 (got %d + %d)", C1, C2);
   FALN_REQUIRE(Cout > 0 && Cout_pad >= Cout && Cout_pad % 32 == 0, "faln_conv3x3_fwd: Cout_pad must be a multiple of 32");
@@ -360,7 +374,7 @@ extern "C" int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, co
   p.stride = stride; p.act = act; p.planar = planar;
   p.tiles_w = (p.Wo + kTW - 1) / kTW; p.tiles_h = (p.Ho + kTH - 1) / kTH;
   p.kblocks1 = C1 / BK; p.kblocks2 = C2 / BK;
-  p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual); p.out = y;
+  p.bias = bias; p.ctab = ctab; p.cscale = cscale; p.residual = static_cast<const __nv_bfloat16*>(residual); p.out = y;
   p.out_pitch = out_pitch; p.out_c = out_c;
   CUtensorMap a1, a2, wm;
   if (!make_act_map(&a1, x, B, H, W, C1, BK, stride) || !make_w_map(&wm, w, Cout_pad, 9 * (C1 + C2), BK, BN) ||

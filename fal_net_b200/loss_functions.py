@@ -148,9 +148,7 @@ class Vgg19_pc(torch.nn.Module):
     def forward(self, x, full=False):
         if full:
             raise NotImplementedError("slice4 (pool4) is never used on the hot path (reference :36-44)")
-        if x.dtype != torch.bfloat16:
-            x = C.input_to_nhwc(x)
-        return tuple(C.vgg_features(list(zip(self.weights, self.biases)), x))
+        return tuple(C.vgg_features(list(zip(self.weights, self.biases)), x.float()))
 
 
 class _LazyVgg:

@@ -12,19 +12,28 @@ import torch.nn.functional as F
 from . import _lib
 
 
+_CM1_CACHE: dict = {}
+
+
 def level_tables(min_disp: torch.Tensor, max_disp: torch.Tensor, no_levels: int, W: int):
-    """d [B,N] (pixels) and x_of [B,N] (normalised grid units) of the exponential disparity levels,
-    written exactly like /root/reference/models/FAL_netB.py:204-205,224-225,241 (fp32, same op order)."""
+    """d [B,N] (pixels) and x_of [B,N] (normalised grid units) of the exponential disparity levels.
+
+    Same fp32 expressions as /root/reference/models/FAL_netB.py:204-205,224-225,241, evaluated for all levels
+    at once (the reference launches ~6 tiny kernels per level per loop: ~300 launches per forward).  The
+    per-level factor (c - 1), a Python double in the reference, reaches the fp32 kernel rounded to fp32 --
+    which is what the cached fp32 vector below holds, so the tables are bit-identical to the per-level loop
+    (checked on CPU against the oracle in tests/test_oracle_golden.py and on the GPU in tests/test_med_gpu.py)."""
+    key = (no_levels, str(min_disp.device))
+    cm1 = _CM1_CACHE.get(key)
+    if cm1 is None:
+        cm1 = torch.tensor([n / (no_levels - 1) - 1 for n in range(no_levels)], dtype=torch.float64).to(torch.float32)
+        cm1 = cm1.to(min_disp.device)
+        _CM1_CACHE[key] = cm1
     x_pix_min = 2 * min_disp / W
     x_pix_max = 2 * max_disp / W
-    lg_d = torch.log(max_disp / min_disp)
-    lg_x = torch.log(x_pix_max / x_pix_min)
-    d, xo = [], []
-    for n in range(no_levels):
-        c = n / (no_levels - 1)
-        d.append(max_disp * torch.exp(lg_d * (c - 1)))
-        xo.append(x_pix_max * torch.exp(lg_x * (c - 1)))
-    return torch.cat(d, 2).squeeze(1).contiguous(), torch.cat(xo, 2).squeeze(1).contiguous()
+    d = max_disp * torch.exp(torch.log(max_disp / min_disp) * cm1)
+    xo = x_pix_max * torch.exp(torch.log(x_pix_max / x_pix_min) * cm1)
+    return d.squeeze(1).contiguous(), xo.squeeze(1).contiguous()
 
 
 _G0X_CACHE: dict = {}

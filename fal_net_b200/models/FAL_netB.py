@@ -121,13 +121,16 @@ class FAL_net(nn.Module):
             raise RuntimeError("fal_net_b200.FAL_netB runs on CUDA (sm_100a) only; there is no CPU path")
         bb = self.backbone
         B, _, H, W = input_left.shape
-        x = C.input_to_nhwc(input_left)
         flow_val = (max_disp.reshape(B).float() / 100.0)                       # :208-209, constant plane per sample
         skips = []
-        h = x
+        h = None
         for i, (name, _, _, stride) in enumerate(_ENC):
             head = getattr(bb, name)[0]
-            h = C.conv3x3(h, head.weight, head.bias, stride=stride, act="elu", const_channel=flow_val if i == 1 else None)
+            if i == 0:
+                h = C.stem(input_left, head.weight, head.bias, "elu")          # reads the fp32 NCHW image directly
+            else:
+                h = C.conv3x3(h, head.weight, head.bias, stride=stride, act="elu",
+                              const_channel=flow_val if i == 1 else None)
             blk = getattr(bb, name + "_1")
             r = C.conv3x3(h, blk.conv1.weight, None, act="elu")
             h = C.conv3x3(r, blk.conv2.weight, None, act="elu", residual=h)     # elu(conv2(elu(conv1(x))) + x), :79

@@ -112,6 +112,8 @@ class FlatAdamDDP:
         self.t += 1
         self._update(self.p, self.g, self.m, self.v, None, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
                          eps=self.eps, weight_decay=self.wd, step=self.t, grad_scale=1.0 / self.world)
+        from . import conv
+        conv.invalidate_packed_weights()      # the arena changed behind torch's version counters
 
     # torch.optim-like conveniences used by the entry points
     @property

@@ -165,14 +165,28 @@ int faln_planar_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, i
  *   x  [B,H,W,C1] bf16 NHWC; x2 [B,H,W,C2] bf16 or NULL = second source, channel-concatenated after x
  *      (the skip connections of :153-173 -- torch.cat never materialises); C1, C2 multiples of 32
  *   w  [Cout_pad,3,3,C1+C2] bf16 (KRSC; rows >= Cout are zero), bias [Cout] fp32 or NULL
+ *   ctab [16,Cout] + cscale [B] fp32 or NULL: a spatially constant extra input channel of value cscale[b] (the
+ *      max_disp/100 plane, :145,208-209) folded into a per-border-class bias: class = rc*4+cc,
+ *      rc = (top tap outside) | (bottom tap outside) << 1, cc likewise; ctab = sums of that channel's weights over
+ *      the taps inside the image
  *   residual [B,Ho,Wo,out_c] bf16 or NULL;  act: 0 none, 1 ELU, 2 ReLU
  *   y  planar == 0: bf16 NHWC [B,Ho,Wo,out_c];  planar == 1: fp32 [B,Cout,Ho,out_pitch] (the logits layout
  *      the MED kernels stream; lets the last layer emit fp32 straight from the accumulator)
  * Ho = (H-1)/stride + 1, Wo likewise.
  * ---------------------------------------------------------------------------------------------- */
-int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, const float* bias, const void* residual,
-                     void* y, int B, int H, int W, int C1, int C2, int Cout, int Cout_pad, int stride, int act,
+int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, const float* bias, const float* ctab,
+                     const float* cscale, const void* residual, void* y, int B, int H, int W, int C1, int C2, int Cout, int Cout_pad, int stride, int act,
                      int planar, long long out_pitch, int out_c, faln_stream_t stream);
+
+/* Stem convolution for 3-channel fp32 NCHW input (conv0.0 of :99 and VGG conv1_1): reads the image directly
+ * (flip_x: x-reversed), w [Cout,3,3,3] fp32 (torch OIHW), Cout 32 or 64, writes bf16 NHWC [B,H,W,Cout]. */
+int faln_stem_conv(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int Cout,
+                   int act, int flip_x, faln_stream_t stream);
+/* F.interpolate(mode='nearest') (:58) on bf16 NHWC: src index = min(floor(dst * in/out), in-1). */
+int faln_upsample_nearest_nhwc(const void* src, void* dst, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                               faln_stream_t stream);
+/* 2x2 stride-2 max pooling (VGG pools, /root/reference/loss_functions.py:21-29) on bf16 NHWC. */
+int faln_maxpool2_nhwc(const void* src, void* dst, int B, int Hi, int Wi, int C, faln_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -34,3 +34,9 @@ def med_case_inputs(tag, B, N, H, W):
     gp = torch.randn(B, 3, H, W, generator=g)
     gd = torch.randn(B, 1, H, W, generator=g)
     return logits, img, gp, gd
+
+
+def rel_l2(a, b):
+    """||a-b||_2 / ||b||_2."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))

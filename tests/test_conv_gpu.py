@@ -70,3 +70,37 @@ def test_conv3x3_planar_fp32_logits():
     torch.cuda.synchronize()
     ref = _ref(torch.cat((u, s), 1), w, b, 1, 0, None)
     assert rel_err(out, ref) < 1e-3          # fp32 straight from the accumulator: only operand rounding is shared
+
+
+def test_stem_upsample_pool_and_const_channel():
+    from fal_net_b200 import conv_native as CN
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(9)
+    CL = torch.channels_last
+    x = torch.randn(2, 3, 19, 45, generator=g).to(dev)
+    for Cout, act in ((32, 1), (64, 2)):
+        w = (torch.randn(Cout, 3, 3, 3, generator=g) * 0.3).to(dev)
+        b = torch.randn(Cout, generator=g).to(dev)
+        y = CN.stem_conv(x, w, b, act)
+        ref = _ref(x, w, b, 1, act, None)
+        assert rel_err(y.float(), ref) < 8e-3
+    # nearest upsample, non-integer ratios like the 375x1242 pyramid (24 -> 47, 78 -> 156)
+    a = torch.randn(2, 64, 24, 78, generator=g).bfloat16().to(dev).contiguous(memory_format=CL)
+    up = CN.upsample_nearest(a, (47, 156))
+    assert torch.equal(up, F.interpolate(a, size=(47, 156), mode="nearest"))
+    up2 = CN.upsample_nearest(a, (48, 156))
+    assert torch.equal(up2, F.interpolate(a, size=(48, 156), mode="nearest"))
+    assert torch.equal(CN.maxpool2(a), F.max_pool2d(a, 2, 2))
+    odd = torch.randn(1, 64, 23, 77, generator=g).bfloat16().to(dev).contiguous(memory_format=CL)
+    assert torch.equal(CN.maxpool2(odd), F.max_pool2d(odd, 2, 2))
+    # constant extra input channel folded into a border-class bias (conv1.0: 32 + 1 -> 64, stride 2), even and odd sizes
+    for H, W in ((24, 40), (25, 41)):
+        h = torch.randn(2, 32, H, W, generator=g).bfloat16().to(dev).contiguous(memory_format=CL)
+        w = (torch.randn(64, 33, 3, 3, generator=g) * 0.1).bfloat16().to(dev)
+        b = torch.randn(64, generator=g).to(dev)
+        cval = torch.tensor([3.0, 1.25], device=dev)
+        y = CN.conv3x3_fwd(h, CN.pack_weight(w[:, :32]), b, 2, 1, None, None, ctab=CN.const_channel_table(w[:, 32].float()),
+                           cscale=cval)
+        plane = cval.view(2, 1, 1, 1).expand(2, 1, H, W).to(torch.bfloat16)
+        ref = _ref(torch.cat((h, plane), 1), w, b, 2, 1, None)
+        assert rel_err(y.float(), ref) < 8e-3

@@ -92,3 +92,16 @@ def test_adam_matches_torch():
         O.adam_step(mine, grads, m, v, step, 1e-4)
         for k in ref:
             assert torch.allclose(ref[k].detach(), mine[k], rtol=1e-6, atol=1e-7)
+
+
+def test_product_level_tables_bit_identical_to_reference_loop():
+    """fal_net_b200.med.level_tables (vectorised) == the reference's per-level expressions, bit for bit (CPU)."""
+    from fal_net_b200 import med
+    for N in (9, 33, 49, 65):
+        for W in (160, 640, 1242, 2048):
+            for mx, mn in ((300.0, 2.0), (60.0, 0.75), (192.3, 1.7)):
+                mxx = torch.tensor([mx, mx * 0.7]).view(2, 1, 1)
+                mnn = torch.tensor([mn, mn * 1.3]).view(2, 1, 1)
+                d0, x0 = O.level_tables(mnn, mxx, N, W)
+                d1, x1 = med.level_tables(mnn, mxx, N, W)
+                assert torch.equal(d0, d1) and torch.equal(x0, x1)
