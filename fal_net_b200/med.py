@@ -88,8 +88,9 @@ def med_forward_raw(logits, image, x_of, d_lvl, g0x, want_pan=True, want_disp=Tr
     mR = torch.empty(B, 1, H, W, **opt) if want_masks else None
     lse0 = torch.empty(B, 1, H, W, **opt)
     lsew = torch.empty(B, 1, H, W, **opt)
-    # algorithmic bytes: read N logits + 3 image, write 3 pan + 1 disp + 2 stats (+ 2 masks)
-    ev = _timed("med_fwd_masks" if want_masks else "med_fwd", 4 * (N + 3 + 3 + 1 + 2 + (2 if want_masks else 0)) * B * H * W)
+    # algorithmic bytes: read N logits + 3 image, write 3 pan + 1 disp (+ 2 masks) = 4(N+9) / 4(N+7)
+    # B/px; the two saved log-sum-exp rows (8 B/px) are extra traffic of this design and are NOT counted
+    ev = _timed("med_fwd_masks" if want_masks else "med_fwd", 4 * (N + 7 + (2 if want_masks else 0)) * B * H * W)
     rc = L.faln_med_fwd(_lib.ptr(logits), _lib.ptr(image), _lib.ptr(g0x), _lib.ptr(x_of), _lib.ptr(d_lvl),
                         _lib.ptr(pan), _lib.ptr(disp), _lib.ptr(mL), _lib.ptr(mR), _lib.ptr(lse0), _lib.ptr(lsew),
                         B, N, H, W, pitch, flags, _lib.cur_stream())

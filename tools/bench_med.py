@@ -42,7 +42,7 @@ def bench(B, N, H, W, iters=10, sets=3, peak=6557.8):
         return e0.elapsed_time(e1) / iters
 
     t = timeit(lambda s: med.med_forward_raw(L[s], I[s], xo, d, g0x, True, True, False))
-    out["fwd"] = dict(ms=t, gbs=4 * (N + 7 + 2) * px / t / 1e6)   # + lse0/lsew stats written
+    out["fwd"] = dict(ms=t, gbs=4 * (N + 7) * px / t / 1e6)
     t = timeit(lambda s: med.med_forward_raw(L[s], I[s], xo, d, g0x, True, True, True))
     out["fwd_masks"] = dict(ms=t, gbs=4 * (N + 9) * px / t / 1e6)
     t = timeit(lambda s: med.med_backward_raw(L[s], I[s], xo, d, g0x, res[s]["pan"], res[s]["disp"], res[s]["lse0"],
