@@ -10,9 +10,13 @@
 //     issued by a producer warp and tracked by full/empty mbarriers, so the HBM stream never waits
 //     on the math warps
 //   * softmax over the planes is an online softmax held in registers (per pixel: running max, sum,
-//     disparity / colour accumulators); neither the probability volume nor a warped image exists
+//     disparity / colour accumulators) with lazy rescaling; neither the probability volume nor a
+//     warped image exists
 //   * the horizontal sub-pixel shift is a two-tap gather out of the staged row; sample coordinates
-//     replay the reference's fp32 normalised-grid arithmetic bit for bit
+//     replay the reference's fp32 normalised-grid arithmetic bit for bit.  The image
+//     row is staged as four phase-shifted, zero-padded copies so that every tap window is an aligned
+//     128-bit shared load with no bounds logic, laid out as natural register pairs for the packed
+//     FFMA2/FADD2/FMUL2 pipeline (two pixels per issue slot)
 //   * masks (Stage-2) need softmax normalisers of OTHER pixels of the row, so they take a second
 //     sweep over the planes of the same row (re-read hits L2: the row was just streamed)
 //   * backward is a single sweep: dot(x) = <g_pan(x), pan(x)> and the two log-sum-exps come from the
@@ -30,7 +34,9 @@ constexpr int kMaxW = 2048;    // 512 threads x 4 px
 constexpr int kPad = 8;        // front padding (floats) of every staged row
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
-constexpr float kLazy = 8.0f;  // lazy-rescale threshold of the online softmax, log2 units
+constexpr float kLazy = 64.0f;  // lazy-rescale threshold of the online softmax, log2 units: the running reference max
+                                // only moves when a logit exceeds it by 2^64 (fp32 has 2^127 of head-room), i.e. on the
+                                // first plane and on pathological inputs; precision is unaffected (floating point)
 
 struct MedParams {
   const float* logits;
@@ -57,9 +63,11 @@ struct MedParams {
   long long pitch;         // logits row pitch, elements
   long long logit_bytes;   // bytes addressable from `logits` (for the clamped tail of the last row)
   unsigned flags;
-  int S;                   // ring slots
+  int S;                   // ring groups (one full/empty mbarrier pair per group)
+  int G;                   // plane rows per group: one barrier wait / release per G planes
   int slotf;               // floats per ring slot
-  int wpad;                // floats per staged per-row array
+  int wpad;                // floats per staged per-row array (aux rows)
+  int wcopy;               // floats per image phase copy
 };
 
 struct Layout {
@@ -67,7 +75,7 @@ struct Layout {
   int total;
 };
 
-__host__ __device__ inline Layout make_layout(int S, int slotf, int wpad, int n_img_rows, int n_aux_rows) {
+__host__ __device__ inline Layout make_layout(int S, int G, int slotf, int wpad, int wcopy, int n_aux_rows) {
   Layout l;
   int o = 0;
   l.off_full = o;
@@ -76,16 +84,24 @@ __host__ __device__ inline Layout make_layout(int S, int slotf, int wpad, int n_
   o += S * 8;
   o = (o + 15) & ~15;
   l.off_tab = o;
-  o += kMaxN * 4 * 4;  // xof, d, k0, special
+  o += kMaxN * 32;  // PlaneInfo[kMaxN]
   l.off_img = o;
-  o += n_img_rows * wpad * 4;
+  o += 12 * wcopy * 4;  // 4 phases x 3 channels
   l.off_ring = o;
-  o += S * slotf * 4;
+  o += S * G * slotf * 4;
   l.off_aux = o;
   o += n_aux_rows * wpad * 4;
   l.total = o;
   return l;
 }
+
+// ------------------------------------------------------------------------------------------ packed fp32
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 ex2_2(float2 a) { return make_float2(ex2f(a.x), ex2f(a.y)); }
+__device__ __forceinline__ float max4(float2 a, float2 b) { return fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y)); }
 
 // v[j] = base[idx + j], j = 0..4, for idx with (idx & 3) == r (r warp-uniform); base 16B aligned.
 __device__ __forceinline__ void load_win5(const float* base, int idx, int r, float v[5]) {
@@ -109,14 +125,31 @@ __device__ __forceinline__ void load4(const float* base, int idx, int r, float v
   }
 }
 
-// Sample coordinate of pixel x on plane with normalised offset xof -- the reference's fp32 pipeline
+// Sample coordinate of pixel x on a plane with normalised offset xof -- the reference's fp32 pipeline
 // (affine_grid value + offset, then ATen's ((g+1)/2)*(W-1)); the *0.5 is folded into cW = (W-1)/2,
-// which is exact.  _rn intrinsics forbid FMA contraction.
+// which is exact.  _rn intrinsics (scalar and packed) forbid FMA contraction.
 __device__ __forceinline__ float coord_plus(float g0, float xof, float cW) {
   return __fmul_rn(__fadd_rn(__fadd_rn(g0, xof), 1.0f), cW);
 }
 __device__ __forceinline__ float coord_minus(float g0, float xof, float cW) {
   return __fmul_rn(__fadd_rn(__fsub_rn(g0, xof), 1.0f), cW);
+}
+// fractional tap weight of a pixel pair on a plane whose integer shift is the constant k:
+//   a = ((g0 + sxof) + 1) * cW + nk + nxf       (sxof = +-xof, nk = -k resp. +(k+1), nxf = -x)
+// NOTE: the product is formed with two SCALAR __fmul_rn: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2
+// into FFMA2, which skips the rounding of the un-normalised coordinate the reference performs (measured: 2e-4
+// relative error on pan at W = 1242).  Scalar mul.rn / add.rn are never contracted.
+__device__ __forceinline__ float2 frac2(float2 g0, float2 nxf, float sxof, float cW, float nk) {
+  const float2 u = add2(add2(g0, splat(sxof)), splat(1.0f));
+  const float2 t = make_float2(__fmul_rn(u.x, cW), __fmul_rn(u.y, cW));
+  return add2(add2(t, splat(nk)), nxf);
+}
+// same for the opposite shift (-xof): here t ~ x - s, so subtract x FIRST (exact, small result) and add k+1 last;
+// adding k+1 to t first would round at the larger magnitude (measured: 3e-5 on maskL).
+__device__ __forceinline__ float2 frac2_minus(float2 g0, float2 nxf, float xof, float cW, float k1f) {
+  const float2 u = add2(add2(g0, splat(-xof)), splat(1.0f));
+  const float2 t = make_float2(__fmul_rn(u.x, cW), __fmul_rn(u.y, cW));
+  return add2(add2(t, nxf), splat(k1f));
 }
 
 __device__ __forceinline__ float tap(const float* row, int j, int W) {
@@ -142,9 +175,49 @@ __device__ __forceinline__ void store_row4(float* rowp, int xb, const float v[4]
   }
 }
 
-// Cooperative load of a contiguous global row of W floats into a staged row (data at +kPad).
-__device__ __forceinline__ void stage_row(float* dst, const float* src, int W, int tid, int nthr) {
-  for (int x = tid; x < W; x += nthr) dst[kPad + x] = __ldg(src + x);
+// Stage the three image rows of (b, y) as 4 phase-shifted, zero-padded copies:
+//   copy[r][c][j] = image[c][j + r] (0 beyond the row), j in [0, wcopy).
+// A tap window starting at pixel x + k is then the aligned float4 at copy[k & 3][c][x + (k & ~3)].
+// All global loads of a thread are issued before the first shared store (one memory latency per row, not one per
+// element): each thread owns float4 #tid (+ nthr, ...) of every channel row.
+__device__ __forceinline__ float4 ld_img4(const float* src, int j, int W, bool vec) {
+  if (vec && j + 3 < W) return __ldg(reinterpret_cast<const float4*>(src + j));
+  float4 v;
+  v.x = j < W ? __ldg(src + j) : 0.f;
+  v.y = j + 1 < W ? __ldg(src + j + 1) : 0.f;
+  v.z = j + 2 < W ? __ldg(src + j + 2) : 0.f;
+  v.w = j + 3 < W ? __ldg(src + j + 3) : 0.f;
+  return v;
+}
+__device__ __forceinline__ void st_phases(float* copies, int c, int wcopy, int j, float4 v) {
+  if (j >= wcopy + 3) return;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float* dst = copies + (r * 3 + c) * wcopy;
+    if (j - r >= 0 && j - r < wcopy) dst[j - r] = v.x;
+    if (j + 1 - r >= 0 && j + 1 - r < wcopy) dst[j + 1 - r] = v.y;
+    if (j + 2 - r >= 0 && j + 2 - r < wcopy) dst[j + 2 - r] = v.z;
+    if (j + 3 - r >= 0 && j + 3 - r < wcopy) dst[j + 3 - r] = v.w;
+  }
+}
+__device__ __forceinline__ void stage_image(float* copies, const float* img_b, int y, int H, int W, int wcopy, int tid,
+                                            int nthr) {
+  const int nq = (wcopy + 3 + 3) / 4;  // float4 groups covering j in [0, wcopy + 3)
+  const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(img_b) & 15) == 0;
+  const float* s0 = img_b + (size_t)y * W;
+  const float* s1 = s0 + (size_t)H * W;
+  const float* s2 = s1 + (size_t)H * W;
+  for (int q0 = 0; q0 < nq; q0 += 2 * nthr) {
+    const int ja = (q0 + tid) * 4, jb = (q0 + nthr + tid) * 4;
+    const float4 a0 = ld_img4(s0, ja, W, vec), a1 = ld_img4(s1, ja, W, vec), a2 = ld_img4(s2, ja, W, vec);
+    const float4 b0 = ld_img4(s0, jb, W, vec), b1 = ld_img4(s1, jb, W, vec), b2 = ld_img4(s2, jb, W, vec);
+    st_phases(copies, 0, wcopy, ja, a0);
+    st_phases(copies, 1, wcopy, ja, a1);
+    st_phases(copies, 2, wcopy, ja, a2);
+    st_phases(copies, 0, wcopy, jb, b0);
+    st_phases(copies, 1, wcopy, jb, b1);
+    st_phases(copies, 2, wcopy, jb, b2);
+  }
 }
 
 struct RowLoad {
@@ -176,119 +249,147 @@ __device__ __forceinline__ RowLoad plan_row(const float* base, long long elem_of
 // ---------------------------------------------------------------------------------------------
 // Shared pieces of the consumer side
 // ---------------------------------------------------------------------------------------------
-struct PlaneTab {
-  float* xof;
-  float* d;
-  int* k0;
-  int* special;
+// Per-plane constants of sample b, precomputed once per (CTA, b) so the hot loop reads them with two broadcast
+// 128-bit shared loads instead of recomputing ~20 integer instructions per plane.
+struct __align__(16) PlaneInfo {
+  float xof;    // normalised-grid offset of the level
+  float d;      // disparity of the level (pixels)
+  float nk0f;   // -(float)k0
+  float k1f;    // (float)(k0 + 1)
+  int k0;       // integer part of the pixel shift (fast path)
+  int special;  // 1: shift within rounding distance of an integer -> generic per-pixel path
+  int pa_off;   // float offset of image phase copy (k0 & 3), channel 0
+  int pb_off;   // float offset of the copy holding taps 1..4
 };
+using PlaneTab = PlaneInfo*;
 
 __device__ __forceinline__ PlaneTab tab_ptrs(unsigned char* smem, const Layout& L) {
-  PlaneTab t;
-  float* f = reinterpret_cast<float*>(smem + L.off_tab);
-  t.xof = f;
-  t.d = f + kMaxN;
-  t.k0 = reinterpret_cast<int*>(f + 2 * kMaxN);
-  t.special = reinterpret_cast<int*>(f + 3 * kMaxN);
-  return t;
+  return reinterpret_cast<PlaneInfo*>(smem + L.off_tab);
 }
 
 // Level table of sample b: integer shift k0 = floor(s), and whether the shift is so close to an
 // integer that fp32 rounding of the coordinate could move floor() across it for some pixel
 // ("special": handled by the per-pixel generic path).
-__device__ __forceinline__ void fill_tab(const MedParams& p, const PlaneTab& t, int b, int tid, int nthr) {
+__device__ __forceinline__ void fill_tab(const MedParams& p, PlaneTab t, int b, int tid, int nthr) {
   const float cW = 0.5f * (float)(p.W - 1);
   const float delta = 4e-7f * (float)p.W + 2e-4f;
   for (int n = tid; n < p.N; n += nthr) {
-    float xo = __ldg(p.x_of + (size_t)b * p.N + n);
-    t.xof[n] = xo;
-    t.d[n] = __ldg(p.d_lvl + (size_t)b * p.N + n);
-    float s = xo * cW;
+    PlaneInfo pi;
+    pi.xof = __ldg(p.x_of + (size_t)b * p.N + n);
+    pi.d = __ldg(p.d_lvl + (size_t)b * p.N + n);
+    float s = pi.xof * cW;
     float fl = floorf(s);
     float fr = s - fl;
     bool sp = !(fr > delta && fr < 1.0f - delta) || !(s >= 0.0f) || !(s < 1.0e6f) ||
               (p.flags & FALN_MED_FORCE_GENERIC);
-    t.k0[n] = sp ? 0 : (int)fl;
-    t.special[n] = sp ? 1 : 0;
+    pi.k0 = sp ? 0 : (int)fl;
+    pi.special = sp ? 1 : 0;
+    pi.nk0f = -(float)pi.k0;
+    pi.k1f = (float)(pi.k0 + 1);
+    const int r = pi.k0 & 3;
+    pi.pa_off = (r * 3) * p.wcopy;
+    pi.pb_off = (r < 3) ? ((r + 1) * 3) * p.wcopy : 4;
+    t[n] = pi;
   }
 }
 
-// Producer: stream `sweeps` x N plane rows of image row (b, y) through the ring.
+// Producer: stream `sweeps` x N plane rows of image row (b, y) through the ring, G rows per mbarrier group.
 __device__ __forceinline__ void produce_row(const MedParams& p, unsigned char* smem, const Layout& L, int b, int y,
-                                            int sweeps, uint32_t& it) {
+                                            int sweeps, int& slot, uint32_t& par) {
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_full);
   uint64_t* empty = reinterpret_cast<uint64_t*>(smem + L.off_empty);
   float* ring = reinterpret_cast<float*>(smem + L.off_ring);
+  const long long plane = (long long)p.H * p.pitch;
   for (int sw = 0; sw < sweeps; ++sw) {
-    for (int n = 0; n < p.N; ++n, ++it) {
-      int slot = it % p.S;
-      uint32_t par = (it / p.S) & 1;
-      mbar_wait(&empty[slot], par ^ 1);
-      long long off = (((long long)b * p.N + n) * p.H + y) * p.pitch;
-      RowLoad r = plan_row(p.logits, off, p.W, p.logit_bytes);
-      float* dst = ring + (size_t)slot * p.slotf + kPad;  // element i of the row lands at dst[head + i]
-      for (int i = r.tail_from; i < p.W; ++i) dst[r.head + i] = __ldg(p.logits + off + i);
-      if (r.bytes) {
-        mbar_arrive_expect_tx(&full[slot], r.bytes);
-        bulk_g2s(dst, r.src, r.bytes, &full[slot]);
-      } else {
-        mbar_arrive(&full[slot]);
+    long long off = ((long long)b * p.N * p.H + y) * p.pitch;
+    for (int n0 = 0; n0 < p.N; n0 += p.G) {
+      const int cnt = min(p.G, p.N - n0);
+      while (!mbar_try_wait(&empty[slot], par ^ 1)) __nanosleep(32);
+      RowLoad r[4];
+      uint32_t total = 0;
+      for (int q = 0; q < cnt; ++q) {
+        r[q] = plan_row(p.logits, off + q * plane, p.W, p.logit_bytes);
+        total += r[q].bytes;
+        float* dst = ring + ((size_t)slot * p.G + q) * p.slotf + kPad;  // element i of the row lands at dst[head + i]
+        for (int i = r[q].tail_from; i < p.W; ++i) dst[r[q].head + i] = __ldg(p.logits + off + q * plane + i);
       }
+      if (total) mbar_arrive_expect_tx(&full[slot], total);
+      else mbar_arrive(&full[slot]);
+      for (int q = 0; q < cnt; ++q)
+        if (r[q].bytes) bulk_g2s(ring + ((size_t)slot * p.G + q) * p.slotf + kPad, r[q].src, r[q].bytes, &full[slot]);
+      off += (long long)cnt * plane;
+      if (++slot == p.S) { slot = 0; par ^= 1; }
     }
   }
 }
 
-__device__ __forceinline__ int row_head(const float* base, long long elem_off) {
-  return (int)(((reinterpret_cast<uintptr_t>(base) + (unsigned long long)elem_off * 4ULL) & 15ULL) >> 2);
-}
-
-// Two-tap interpolation windows for 4 consecutive pixels at integer shift k (taps xb+k .. xb+k+4),
-// zero beyond the right end of the row.  `row` points at element 0 of the row inside a staged buffer
-// whose address is (16B-aligned base + off0) with off0 & 3 == r0.
-__device__ __forceinline__ void win_right(const float* abase, int off0, int xb, int k, int W, float v[5]) {
-  int j0 = xb + k;
+// Two-tap interpolation window for 4 consecutive pixels at integer shift k (taps xb+k .. xb+k+4), zero beyond
+// the right end of the row.  abase: 16B-aligned buffer, element j of the row at abase[off0 + j].
+// `interior`: warp-uniform promise that no tap of this warp leaves the row.
+__device__ __forceinline__ void win_right(const float* abase, int off0, int xb, int k, int W, bool interior, float v[5]) {
+  const int j0 = xb + k;
+  if (interior) {
+    const int idx = off0 + j0;
+    load_win5(abase, idx, idx & 3, v);
+    return;
+  }
   if (j0 > W - 1) {
 #pragma unroll
     for (int j = 0; j < 5; ++j) v[j] = 0.0f;
     return;
   }
-  int idx = off0 + j0;
+  const int idx = off0 + j0;
   load_win5(abase, idx, idx & 3, v);
-  if (j0 + 4 > W - 1) {
 #pragma unroll
-    for (int j = 1; j < 5; ++j)
-      if (j0 + j > W - 1) v[j] = 0.0f;
-  }
+  for (int j = 1; j < 5; ++j)
+    if (j0 + j > W - 1) v[j] = 0.0f;
 }
-// Window at a (possibly negative) start j0 = xb + k, zero outside [0, W-1] on both sides.
-__device__ __forceinline__ void win_any(const float* abase, int off0, int j0, int W, float v[5]) {
+// Window at a (possibly negative) start j0, zero outside [0, W-1] on both sides.
+__device__ __forceinline__ void win_any(const float* abase, int off0, int j0, int W, bool interior, float v[5]) {
+  if (interior) {
+    const int idx = off0 + j0;
+    load_win5(abase, idx, idx & 3, v);
+    return;
+  }
   if (j0 > W - 1 || j0 + 4 < 0) {
 #pragma unroll
     for (int j = 0; j < 5; ++j) v[j] = 0.0f;
     return;
   }
-  int idx = off0 + j0;  // off0 >= kPad keeps the aligned-down address inside the buffer for j0 >= -4
+  const int idx = off0 + j0;  // off0 >= kPad keeps the aligned-down address inside the buffer for j0 >= -4
   load_win5(abase, idx, idx & 3, v);
 #pragma unroll
   for (int j = 0; j < 5; ++j)
     if (j0 + j < 0 || j0 + j > W - 1) v[j] = 0.0f;
 }
 
-struct Softmax4 {
-  float m[kPX], z[kPX];
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int i = 0; i < kPX; ++i) { m[i] = -INFINITY; z[i] = 0.0f; }
-  }
+// image tap windows out of the phase copies: A = taps 0..3 at pa[c*wcopy], Bq = taps 1..4 at pb[c*wcopy]
+struct ImgWin {
+  const float* pa;
+  const float* pb;
 };
+__device__ __forceinline__ ImgWin img_win(const float* copies, const PlaneInfo& pi, int xb, int wz) {
+  ImgWin w;
+  const int i0 = min(xb + (pi.k0 & ~3), wz);
+  w.pa = copies + pi.pa_off + i0;
+  w.pb = copies + pi.pb_off + i0;
+  return w;
+}
+
+// online-softmax update of one pixel when the lazy threshold is exceeded: nm = -(running max), log2 domain
+__device__ __forceinline__ float rescale_factor(float& nm, float ls) {
+  const float f = ex2f(-nm - ls);  // ex2(old_max - new_max); old_max = -inf -> 0
+  nm = -ls;
+  return f;
+}
 
 // =============================================================================================
 // Forward
 // =============================================================================================
-template <bool kMasks>
-__global__ void __launch_bounds__(544, 1) med_fwd_kernel(const MedParams p) {
+template <bool kMasks, int kMaxThreads, int kMaxRegs>
+__global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med_fwd_kernel(const MedParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const Layout L = make_layout(p.S, p.slotf, p.wpad, 3, kMasks ? 4 : 0);
+  const Layout L = make_layout(p.S, p.G, p.slotf, p.wpad, p.wcopy, kMasks ? 4 : 0);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_full);
   uint64_t* empty = reinterpret_cast<uint64_t*>(smem + L.off_empty);
   float* img = reinterpret_cast<float*>(smem + L.off_img);
@@ -314,9 +415,10 @@ __global__ void __launch_bounds__(544, 1) med_fwd_kernel(const MedParams p) {
   if (tid >= ncons) {
     // ------------------------------------------------------------------ producer warp
     if (tid == ncons) {
-      uint32_t it = 0;
+      int slot = 0;
+      uint32_t par = 0;
       for (int row = blockIdx.x; row < rows; row += gridDim.x)
-        produce_row(p, smem, L, row / p.H, row % p.H, kMasks ? 2 : 1, it);
+        produce_row(p, smem, L, row / p.H, row % p.H, kMasks ? 2 : 1, slot, par);
     }
     return;
   }
@@ -324,8 +426,12 @@ __global__ void __launch_bounds__(544, 1) med_fwd_kernel(const MedParams p) {
   // -------------------------------------------------------------------- consumers
   const int xb = tid * kPX;
   const bool active = xb < W;
+  const bool ragged = xb + 3 >= W;           // this thread owns pixels beyond the row end
   const float cW = 0.5f * (float)(W - 1);
   const int lane = tid & 31;
+  const int warp_last_xb = ((tid | 31)) * kPX;  // xb of lane 31 of this warp
+  const int wz = ((W + 3) & ~3) + 4;         // start of a guaranteed all-zero, 16B-aligned stretch of every image copy
+  const int wcopy = p.wcopy;
   float g0[kPX], xf[kPX];
 #pragma unroll
   for (int i = 0; i < kPX; ++i) {
@@ -333,8 +439,12 @@ __global__ void __launch_bounds__(544, 1) med_fwd_kernel(const MedParams p) {
     g0[i] = __ldg(p.g0x + x);
     xf[i] = (float)(xb + i);
   }
-  uint32_t it = 0;
+  const float2 g0p[2] = {make_float2(g0[0], g0[1]), make_float2(g0[2], g0[3])};
+  const float2 nxf[2] = {make_float2(-xf[0], -xf[1]), make_float2(-xf[2], -xf[3])};
+  int slot = 0;
+  uint32_t par = 0;
   int cur_b = -1;
+  const int plane_head_step = (int)(((long long)p.H * p.pitch) & 3);
 
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const int b = row / p.H, y = row % p.H;
@@ -343,200 +453,269 @@ __global__ void __launch_bounds__(544, 1) med_fwd_kernel(const MedParams p) {
       fill_tab(p, T, b, tid, ncons);
       cur_b = b;
     }
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      stage_row(img + c * p.wpad, p.image + (((size_t)b * 3 + c) * p.H + y) * W, W, tid, ncons);
+    stage_image(img, p.image + (size_t)b * 3 * p.H * W, y, p.H, W, p.wcopy, tid, ncons);
     named_bar_sync(1, ncons);
+    const int head0 = (int)(((reinterpret_cast<uintptr_t>(p.logits) >> 2) + ((long long)b * N * p.H + y) * p.pitch) & 3);
 
-    Softmax4 s0, sw;
-    s0.init();
-    sw.init();
-    float dacc[kPX], pacc[3][kPX];
+    float2 nm0[2], z0[2], dacc[2], nmw[2], zw[2], pacc[3][2];
 #pragma unroll
-    for (int i = 0; i < kPX; ++i) { dacc[i] = 0.f; pacc[0][i] = pacc[1][i] = pacc[2][i] = 0.f; }
+    for (int h = 0; h < 2; ++h) {
+      nm0[h] = nmw[h] = splat(INFINITY);
+      z0[h] = dacc[h] = zw[h] = splat(0.f);
+      pacc[0][h] = pacc[1][h] = pacc[2][h] = splat(0.f);
+    }
 
     // ---------------------------------------------------------------- sweep A: stats, disp, pan
-    for (int n = 0; n < N; ++n, ++it) {
-      const int slot = it % p.S;
-      mbar_wait(&full[slot], (it / p.S) & 1);
-      const float* sl = ring + (size_t)slot * p.slotf;  // 16B aligned
-      const int head = row_head(p.logits, (((long long)b * N + n) * p.H + y) * p.pitch);
+    int head = head0;
+    for (int n = 0, q = 0; n < N; ++n) {
+      if (q == 0) mbar_wait(&full[slot], par);
+      const float* sl = ring + ((size_t)slot * p.G + q) * p.slotf;  // 16B aligned
       const int off0 = kPad + head;
       if (active) {
-        const float xof = T.xof[n];
-        const float dn = T.d[n];
-        float l[kPX], wl[kPX], sc[3][kPX];
+        const PlaneInfo pi = T[n];
+        const float xof = pi.xof;
+        const float dn = pi.d;
+        float l[kPX];
+        float2 wl[2], a[2];
+        float2 sc0[3][2], sc1[3][2];  // image taps x0 / x0+1 per channel, pixel pairs
+        bool blend_direct = false;
         load4(sl, off0 + xb, (off0 + xb) & 3, l);
-        if (!T.special[n]) {
-          const int k0 = T.k0[n];
-          const float k0f = (float)k0;
-          float a[kPX], v[5];
-          win_right(sl, off0, xb, k0, W, v);
+        if (ragged) {
 #pragma unroll
-          for (int i = 0; i < kPX; ++i) {
-            float t = coord_plus(g0[i], xof, cW);
-            a[i] = __fsub_rn(__fsub_rn(t, k0f), xf[i]);
-            wl[i] = fmaf(a[i], v[i + 1] - v[i], v[i]);
-          }
+          for (int i = 0; i < kPX; ++i)
+            if (xb + i >= W) l[i] = 0.f;
+        }
+        if (!pi.special) {
+          const int k0 = pi.k0;
+          const float nk0f = pi.nk0f;
+          const bool interior = warp_last_xb + k0 + 4 <= W - 1;
+          float v[5];
+          win_right(sl, off0, xb, k0, W, interior, v);
+          a[0] = frac2(g0p[0], nxf[0], xof, cW, nk0f);
+          a[1] = frac2(g0p[1], nxf[1], xof, cW, nk0f);
+          wl[0] = make_float2(fmaf(a[0].x, v[1] - v[0], v[0]), fmaf(a[0].y, v[2] - v[1], v[1]));
+          wl[1] = make_float2(fmaf(a[1].x, v[3] - v[2], v[2]), fmaf(a[1].y, v[4] - v[3], v[3]));
+          const ImgWin iw = img_win(img, pi, xb, wz);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            win_right(img + c * p.wpad, kPad, xb, k0, W, v);
-#pragma unroll
-            for (int i = 0; i < kPX; ++i) sc[c][i] = fmaf(a[i], v[i + 1] - v[i], v[i]);
+            const float4 A = *reinterpret_cast<const float4*>(iw.pa + c * wcopy);
+            const float4 Bq = *reinterpret_cast<const float4*>(iw.pb + c * wcopy);
+            sc0[c][0] = make_float2(A.x, A.y);
+            sc0[c][1] = make_float2(A.z, A.w);
+            sc1[c][0] = make_float2(Bq.x, Bq.y);
+            sc1[c][1] = make_float2(Bq.z, Bq.w);
           }
         } else {
+          // generic per-pixel path (shift within rounding distance of an integer): resolve the two taps here
+          blend_direct = true;
           const float* lrow = sl + off0;
+          float wlv[kPX], av[kPX];
 #pragma unroll
           for (int i = 0; i < kPX; ++i) {
             float t = coord_plus(g0[i], xof, cW);
             float x0f = floorf(t);
-            float a = t - x0f;
+            av[i] = t - x0f;
             int x0 = (int)x0f;
             float f0 = tap(lrow, x0, W), f1 = tap(lrow, x0 + 1, W);
-            wl[i] = fmaf(a, f1 - f0, f0);
+            wlv[i] = fmaf(av[i], f1 - f0, f0);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              const float* ir = img + c * p.wpad + kPad;
+              const float* ir = img + c * p.wcopy;  // phase-0 copy = the row itself
               float i0 = tap(ir, x0, W), i1 = tap(ir, x0 + 1, W);
-              sc[c][i] = fmaf(a, i1 - i0, i0);
+              if (i & 1) { (&sc0[c][i >> 1].x)[1] = i0; (&sc1[c][i >> 1].x)[1] = i1; }
+              else { sc0[c][i >> 1].x = i0; sc1[c][i >> 1].x = i1; }
+            }
+          }
+          a[0] = make_float2(av[0], av[1]);
+          a[1] = make_float2(av[2], av[3]);
+          wl[0] = make_float2(wlv[0], wlv[1]);
+          wl[1] = make_float2(wlv[2], wlv[3]);
+        }
+        (void)blend_direct;
+        const float2 l2[2] = {make_float2(l[0], l[1]), make_float2(l[2], l[3])};
+        float2 arg0[2], argw[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          arg0[h] = fma2(l2[h], splat(kLog2e), nm0[h]);
+          argw[h] = fma2(wl[h], splat(kLog2e), nmw[h]);
+        }
+        if (fmaxf(max4(arg0[0], arg0[1]), max4(argw[0], argw[1])) > kLazy) {
+          // rare: some running max must move.  Per pixel, rescale the sums that depend on it.
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              float& a0 = e ? arg0[h].y : arg0[h].x;
+              if (a0 > kLazy) {
+                float& nm = e ? nm0[h].y : nm0[h].x;
+                const float f = rescale_factor(nm, (e ? l2[h].y : l2[h].x) * kLog2e);
+                (e ? z0[h].y : z0[h].x) *= f;
+                (e ? dacc[h].y : dacc[h].x) *= f;
+                a0 = 0.f;
+              }
+              float& aw = e ? argw[h].y : argw[h].x;
+              if (aw > kLazy) {
+                float& nm = e ? nmw[h].y : nmw[h].x;
+                const float f = rescale_factor(nm, (e ? wl[h].y : wl[h].x) * kLog2e);
+                (e ? zw[h].y : zw[h].x) *= f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) (e ? pacc[c][h].y : pacc[c][h].x) *= f;
+                aw = 0.f;
+              }
             }
           }
         }
 #pragma unroll
-        for (int i = 0; i < kPX; ++i) {
+        for (int h = 0; h < 2; ++h) {
           // un-warped softmax + disparity expectation (reference :216-226)
-          float ls = l[i] * kLog2e;
-          if (ls > s0.m[i] + kLazy) {
-            float f = ex2f(s0.m[i] - ls);
-            s0.z[i] *= f;
-            dacc[i] *= f;
-            s0.m[i] = ls;
+          const float2 e0 = ex2_2(arg0[h]);
+          z0[h] = add2(z0[h], e0);
+          dacc[h] = fma2(splat(dn), e0, dacc[h]);
+          // warped softmax + colour blend (reference :245-248, 279-282): pan += ew*(1-a)*I[x0] + ew*a*I[x0+1]
+          const float2 ew = ex2_2(argw[h]);
+          zw[h] = add2(zw[h], ew);
+          const float2 w1 = mul2(ew, a[h]);
+          const float2 w0 = fma2(w1, splat(-1.0f), ew);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            pacc[c][h] = fma2(w0, sc0[c][h], pacc[c][h]);
+            pacc[c][h] = fma2(w1, sc1[c][h], pacc[c][h]);
           }
-          float e = ex2f(ls - s0.m[i]);
-          s0.z[i] += e;
-          dacc[i] = fmaf(dn, e, dacc[i]);
-          // warped softmax + colour blend (reference :245-248, 279-282)
-          float ws = wl[i] * kLog2e;
-          if (ws > sw.m[i] + kLazy) {
-            float f = ex2f(sw.m[i] - ws);
-            sw.z[i] *= f;
-            pacc[0][i] *= f; pacc[1][i] *= f; pacc[2][i] *= f;
-            sw.m[i] = ws;
-          }
-          float ew = ex2f(ws - sw.m[i]);
-          sw.z[i] += ew;
-          pacc[0][i] = fmaf(sc[0][i], ew, pacc[0][i]);
-          pacc[1][i] = fmaf(sc[1][i], ew, pacc[1][i]);
-          pacc[2][i] = fmaf(sc[2][i], ew, pacc[2][i]);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[slot]);
+      if (++q == p.G || n == N - 1) {  // last plane of the group: hand the G slots back to the producer
+        q = 0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+        if (++slot == p.S) { slot = 0; par ^= 1; }
+      }
+      head = (head + plane_head_step) & 3;
     }
 
     // ---------------------------------------------------------------- row results of sweep A
-    float lse0s[kPX], lsews[kPX];  // log2-domain log-sum-exps, reused by sweep B
+    float nlse0[kPX], nlsew[kPX];  // NEGATED log2-domain log-sum-exps, reused by sweep B
     if (active) {
       float o[kPX];
       const size_t r1 = ((size_t)b * p.H + y) * W;
+      const float m0v[4] = {-nm0[0].x, -nm0[0].y, -nm0[1].x, -nm0[1].y};
+      const float mwv[4] = {-nmw[0].x, -nmw[0].y, -nmw[1].x, -nmw[1].y};
+      const float z0v[4] = {z0[0].x, z0[0].y, z0[1].x, z0[1].y};
+      const float zwv[4] = {zw[0].x, zw[0].y, zw[1].x, zw[1].y};
 #pragma unroll
       for (int i = 0; i < kPX; ++i) {
-        lse0s[i] = s0.m[i] + lg2f(s0.z[i]);
-        lsews[i] = sw.m[i] + lg2f(sw.z[i]);
+        nlse0[i] = -(m0v[i] + lg2f(z0v[i]));
+        nlsew[i] = -(mwv[i] + lg2f(zwv[i]));
       }
       if (p.disp) {
+        const float dv[4] = {dacc[0].x, dacc[0].y, dacc[1].x, dacc[1].y};
 #pragma unroll
-        for (int i = 0; i < kPX; ++i) o[i] = dacc[i] / s0.z[i];
+        for (int i = 0; i < kPX; ++i) o[i] = dv[i] / z0v[i];
         store_row4(p.disp + r1, xb, o, W);
       }
       if (p.pan) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
+          const float pv[4] = {pacc[c][0].x, pacc[c][0].y, pacc[c][1].x, pacc[c][1].y};
 #pragma unroll
-          for (int i = 0; i < kPX; ++i) o[i] = pacc[c][i] / sw.z[i];
+          for (int i = 0; i < kPX; ++i) o[i] = pv[i] / zwv[i];
           store_row4(p.pan + (((size_t)b * 3 + c) * p.H + y) * W, xb, o, W);
         }
       }
       if (p.lse0) {
 #pragma unroll
-        for (int i = 0; i < kPX; ++i) o[i] = lse0s[i] * kLn2;
+        for (int i = 0; i < kPX; ++i) o[i] = -nlse0[i] * kLn2;
         store_row4(p.lse0 + r1, xb, o, W);
       }
       if (p.lsew) {
 #pragma unroll
-        for (int i = 0; i < kPX; ++i) o[i] = lsews[i] * kLn2;
+        for (int i = 0; i < kPX; ++i) o[i] = -nlsew[i] * kLn2;
         store_row4(p.lsew + r1, xb, o, W);
       }
     }
 
     if (kMasks) {
       // -------------------------------------------------------------- sweep B: occlusion masks
+      const float2 nl0[2] = {make_float2(nlse0[0], nlse0[1]), make_float2(nlse0[2], nlse0[3])};
+      const float2 nlw[2] = {make_float2(nlsew[0], nlsew[1]), make_float2(nlsew[2], nlsew[3])};
       float mR[kPX], mL[kPX];
 #pragma unroll
       for (int i = 0; i < kPX; ++i) mR[i] = mL[i] = 0.f;
-      for (int n = 0; n < N; ++n, ++it) {
-        const int slot = it % p.S;
-        mbar_wait(&full[slot], (it / p.S) & 1);
-        const float* sl = ring + (size_t)slot * p.slotf;
-        const int head = row_head(p.logits, (((long long)b * N + n) * p.H + y) * p.pitch);
+      head = head0;
+      for (int n = 0, q = 0; n < N; ++n) {
+        if (q == 0) mbar_wait(&full[slot], par);
+        const float* sl = ring + ((size_t)slot * p.G + q) * p.slotf;
         const int off0 = kPad + head;
         float* EA = aux + (size_t)(n & 1) * 2 * p.wpad;  // softmax(L)_n        at every pixel of the row
         float* EB = EA + p.wpad;                          // softmax(warped L)_n at every pixel of the row
-        const float xof = T.xof[n];
-        const bool special = T.special[n] != 0;
-        const int k0 = T.k0[n];
-        float ap[kPX];  // +shift fractional weights (fast path)
+        const PlaneInfo pi = T[n];
+        const float xof = pi.xof;
+        const bool special = pi.special != 0;
+        const int k0 = pi.k0;
+        const bool interior = warp_last_xb + k0 + 4 <= W - 1;
+        float2 ap[2];  // +shift fractional weights (fast path)
         if (active) {
-          float l[kPX], wl[kPX], e0[kPX], ew[kPX];
+          float l[kPX];
+          float2 wl[2];
           load4(sl, off0 + xb, (off0 + xb) & 3, l);
           if (!special) {
-            const float k0f = (float)k0;
             float v[5];
-            win_right(sl, off0, xb, k0, W, v);
-#pragma unroll
-            for (int i = 0; i < kPX; ++i) {
-              float t = coord_plus(g0[i], xof, cW);
-              ap[i] = __fsub_rn(__fsub_rn(t, k0f), xf[i]);
-              wl[i] = fmaf(ap[i], v[i + 1] - v[i], v[i]);
-            }
+            win_right(sl, off0, xb, k0, W, interior, v);
+            ap[0] = frac2(g0p[0], nxf[0], xof, cW, pi.nk0f);
+            ap[1] = frac2(g0p[1], nxf[1], xof, cW, pi.nk0f);
+            wl[0] = make_float2(fmaf(ap[0].x, v[1] - v[0], v[0]), fmaf(ap[0].y, v[2] - v[1], v[1]));
+            wl[1] = make_float2(fmaf(ap[1].x, v[3] - v[2], v[2]), fmaf(ap[1].y, v[4] - v[3], v[3]));
           } else {
             const float* lrow = sl + off0;
+            float wlv[kPX];
 #pragma unroll
             for (int i = 0; i < kPX; ++i) {
               float t = coord_plus(g0[i], xof, cW);
               float x0f = floorf(t);
-              float a = t - x0f;
+              float aa = t - x0f;
               int x0 = (int)x0f;
               float f0 = tap(lrow, x0, W), f1 = tap(lrow, x0 + 1, W);
-              wl[i] = fmaf(a, f1 - f0, f0);
+              wlv[i] = fmaf(aa, f1 - f0, f0);
             }
+            wl[0] = make_float2(wlv[0], wlv[1]);
+            wl[1] = make_float2(wlv[2], wlv[3]);
           }
-#pragma unroll
-          for (int i = 0; i < kPX; ++i) {
-            bool ok = xb + i < W;
-            e0[i] = ok ? ex2f(fmaf(l[i], kLog2e, -lse0s[i])) : 0.f;
-            ew[i] = ok ? ex2f(fmaf(wl[i], kLog2e, -lsews[i])) : 0.f;
+          float2 e0[2], ew[2];
+          e0[0] = ex2_2(fma2(make_float2(l[0], l[1]), splat(kLog2e), nl0[0]));
+          e0[1] = ex2_2(fma2(make_float2(l[2], l[3]), splat(kLog2e), nl0[1]));
+          ew[0] = ex2_2(fma2(wl[0], splat(kLog2e), nlw[0]));
+          ew[1] = ex2_2(fma2(wl[1], splat(kLog2e), nlw[1]));
+          if (ragged) {
+            if (xb + 1 >= W) { e0[0].y = 0.f; ew[0].y = 0.f; }
+            if (xb + 2 >= W) { e0[1].x = 0.f; ew[1].x = 0.f; }
+            if (xb + 3 >= W) { e0[1].y = 0.f; ew[1].y = 0.f; }
           }
-          *reinterpret_cast<float4*>(EA + kPad + xb) = make_float4(e0[0], e0[1], e0[2], e0[3]);
-          *reinterpret_cast<float4*>(EB + kPad + xb) = make_float4(ew[0], ew[1], ew[2], ew[3]);
+          *reinterpret_cast<float4*>(EA + kPad + xb) = make_float4(e0[0].x, e0[0].y, e0[1].x, e0[1].y);
+          *reinterpret_cast<float4*>(EB + kPad + xb) = make_float4(ew[0].x, ew[0].y, ew[1].x, ew[1].y);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[slot]);  // the plane row itself is no longer needed
+        if (++q == p.G || n == N - 1) {  // the plane rows of this group are no longer needed
+          q = 0;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[slot]);
+          if (++slot == p.S) { slot = 0; par ^= 1; }
+        }
+        head = (head + plane_head_step) & 3;
         named_bar_sync(2, ncons);
         if (active) {
           if (!special) {
             float v[5];
-            win_right(EA, kPad, xb, k0, W, v);          // maskR: softmax(L)_n shifted by +s_n (:266)
-#pragma unroll
-            for (int i = 0; i < kPX; ++i) mR[i] += fmaf(ap[i], v[i + 1] - v[i], v[i]);
-            const float k1f = (float)(k0 + 1);
-            win_any(EB, kPad, xb - k0 - 1, W, v);        // maskL: softmax(warped)_n shifted by -s_n (:270-273)
-#pragma unroll
-            for (int i = 0; i < kPX; ++i) {
-              float t = coord_minus(g0[i], xof, cW);
-              float a = __fadd_rn(__fsub_rn(t, xf[i]), k1f);
-              mL[i] += fmaf(a, v[i + 1] - v[i], v[i]);
-            }
+            win_right(EA, kPad, xb, k0, W, interior, v);          // maskR: softmax(L)_n shifted by +s_n (:266)
+            mR[0] += fmaf(ap[0].x, v[1] - v[0], v[0]);
+            mR[1] += fmaf(ap[0].y, v[2] - v[1], v[1]);
+            mR[2] += fmaf(ap[1].x, v[3] - v[2], v[2]);
+            mR[3] += fmaf(ap[1].y, v[4] - v[3], v[3]);
+            const bool interior_l = (tid & ~31) * kPX - k0 - 1 >= 0 && warp_last_xb - k0 + 3 <= W - 1;
+            win_any(EB, kPad, xb - k0 - 1, W, interior_l, v);      // maskL: softmax(warped)_n shifted by -s_n (:270-273)
+            const float2 am0 = frac2_minus(g0p[0], nxf[0], xof, cW, pi.k1f);
+            const float2 am1 = frac2_minus(g0p[1], nxf[1], xof, cW, pi.k1f);
+            mL[0] += fmaf(am0.x, v[1] - v[0], v[0]);
+            mL[1] += fmaf(am0.y, v[2] - v[1], v[1]);
+            mL[2] += fmaf(am1.x, v[3] - v[2], v[2]);
+            mL[3] += fmaf(am1.y, v[4] - v[3], v[3]);
           } else {
             const float* ea = EA + kPad;
             const float* eb = EB + kPad;
@@ -544,17 +723,17 @@ __global__ void __launch_bounds__(544, 1) med_fwd_kernel(const MedParams p) {
             for (int i = 0; i < kPX; ++i) {
               float t = coord_plus(g0[i], xof, cW);
               float x0f = floorf(t);
-              float a = t - x0f;
+              float aa = t - x0f;
               int x0 = (int)x0f;
               float f0 = tap(ea, x0, W), f1 = tap(ea, x0 + 1, W);
-              mR[i] += fmaf(a, f1 - f0, f0);
+              mR[i] += fmaf(aa, f1 - f0, f0);
               t = coord_minus(g0[i], xof, cW);
               x0f = floorf(t);
-              a = t - x0f;
+              aa = t - x0f;
               x0 = (int)x0f;
               f0 = tap(eb, x0, W);
               f1 = tap(eb, x0 + 1, W);
-              mL[i] += fmaf(a, f1 - f0, f0);
+              mL[i] += fmaf(aa, f1 - f0, f0);
             }
           }
         }
@@ -576,9 +755,10 @@ __global__ void __launch_bounds__(544, 1) med_fwd_kernel(const MedParams p) {
 // =============================================================================================
 // Backward
 // =============================================================================================
-__global__ void __launch_bounds__(544, 1) med_bwd_kernel(const MedParams p) {
+template <int kMaxThreads, int kMaxRegs>
+__global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med_bwd_kernel(const MedParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const Layout L = make_layout(p.S, p.slotf, p.wpad, 3, 6);
+  const Layout L = make_layout(p.S, p.G, p.slotf, p.wpad, p.wcopy, 6);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_full);
   uint64_t* empty = reinterpret_cast<uint64_t*>(smem + L.off_empty);
   float* img = reinterpret_cast<float*>(smem + L.off_img);
@@ -603,8 +783,9 @@ __global__ void __launch_bounds__(544, 1) med_bwd_kernel(const MedParams p) {
 
   if (tid >= ncons) {
     if (tid == ncons) {
-      uint32_t it = 0;
-      for (int row = blockIdx.x; row < rows; row += gridDim.x) produce_row(p, smem, L, row / p.H, row % p.H, 1, it);
+      int slot = 0;
+      uint32_t par = 0;
+      for (int row = blockIdx.x; row < rows; row += gridDim.x) produce_row(p, smem, L, row / p.H, row % p.H, 1, slot, par);
     }
     return;
   }
@@ -613,6 +794,9 @@ __global__ void __launch_bounds__(544, 1) med_bwd_kernel(const MedParams p) {
   const bool active = xb < W;
   const float cW = 0.5f * (float)(W - 1);
   const int lane = tid & 31;
+  const int warp_first_xb = (tid & ~31) * kPX, warp_last_xb = (tid | 31) * kPX;
+  const int wz = ((W + 3) & ~3) + 4;
+  const int wcopy = p.wcopy;
   float g0[kPX], xf[kPX];
 #pragma unroll
   for (int i = 0; i < kPX; ++i) {
@@ -620,8 +804,12 @@ __global__ void __launch_bounds__(544, 1) med_bwd_kernel(const MedParams p) {
     g0[i] = __ldg(p.g0x + x);
     xf[i] = (float)(xb + i);
   }
-  uint32_t it = 0;
+  const float2 g0p[2] = {make_float2(g0[0], g0[1]), make_float2(g0[2], g0[3])};
+  const float2 nxf[2] = {make_float2(-xf[0], -xf[1]), make_float2(-xf[2], -xf[3])};
+  int slot = 0;
+  uint32_t par = 0;
   int cur_b = -1;
+  const int plane_head_step = (int)(((long long)p.H * p.pitch) & 3);
 
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const int b = row / p.H, y = row % p.H;
@@ -630,125 +818,158 @@ __global__ void __launch_bounds__(544, 1) med_bwd_kernel(const MedParams p) {
       fill_tab(p, T, b, tid, ncons);
       cur_b = b;
     }
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      stage_row(img + c * p.wpad, p.image + (((size_t)b * 3 + c) * p.H + y) * W, W, tid, ncons);
+    stage_image(img, p.image + (size_t)b * 3 * p.H * W, y, p.H, W, p.wcopy, tid, ncons);
     named_bar_sync(1, ncons);
+    const int head0 = (int)(((reinterpret_cast<uintptr_t>(p.logits) >> 2) + ((long long)b * N * p.H + y) * p.pitch) & 3);
 
     // per-pixel row constants
-    float gp[3][kPX], dot[kPX], lsews[kPX], lse0s[kPX], gd[kPX], dsp[kPX];
+    float gpv[3][kPX], dotv[kPX], nlsewv[kPX], nlse0v[kPX], gdv[kPX], dspv[kPX];
     const size_t r1 = ((size_t)b * p.H + y) * W;
 #pragma unroll
     for (int i = 0; i < kPX; ++i) {
       const bool ok = xb + i < W;
       const size_t x = r1 + min(xb + i, W - 1);
-      dot[i] = 0.f;
+      dotv[i] = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const size_t xc = (((size_t)b * 3 + c) * p.H + y) * W + min(xb + i, W - 1);
-        gp[c][i] = (ok && p.g_pan) ? __ldg(p.g_pan + xc) : 0.f;
-        dot[i] = fmaf(gp[c][i], p.g_pan ? __ldg(p.pan_in + xc) : 0.f, dot[i]);
+        gpv[c][i] = (ok && p.g_pan) ? __ldg(p.g_pan + xc) : 0.f;
+        dotv[i] = fmaf(gpv[c][i], p.g_pan ? __ldg(p.pan_in + xc) : 0.f, dotv[i]);
       }
-      lsews[i] = __ldg(p.lsew_in + x) * kLog2e;
-      lse0s[i] = __ldg(p.lse0_in + x) * kLog2e;
-      gd[i] = (ok && p.g_disp) ? __ldg(p.g_disp + x) : 0.f;
-      dsp[i] = __ldg(p.disp_in + x);
+      nlsewv[i] = -__ldg(p.lsew_in + x) * kLog2e;
+      nlse0v[i] = -__ldg(p.lse0_in + x) * kLog2e;
+      gdv[i] = (ok && p.g_disp) ? __ldg(p.g_disp + x) : 0.f;
+      dspv[i] = __ldg(p.disp_in + x);
+    }
+    float2 gp[3][2], ndot[2], nlw[2], nl0[2], gd[2], ndsp[2], okm[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gp[c][h] = make_float2(gpv[c][2 * h], gpv[c][2 * h + 1]);
+      ndot[h] = make_float2(-dotv[2 * h], -dotv[2 * h + 1]);
+      nlw[h] = make_float2(nlsewv[2 * h], nlsewv[2 * h + 1]);
+      nl0[h] = make_float2(nlse0v[2 * h], nlse0v[2 * h + 1]);
+      gd[h] = make_float2(gdv[2 * h], gdv[2 * h + 1]);
+      ndsp[h] = make_float2(-dspv[2 * h], -dspv[2 * h + 1]);
+      okm[h] = make_float2(xb + 2 * h < W ? 1.f : 0.f, xb + 2 * h + 1 < W ? 1.f : 0.f);
     }
 
-    for (int n = 0; n < N; ++n, ++it) {
-      const int slot = it % p.S;
-      mbar_wait(&full[slot], (it / p.S) & 1);
-      const float* sl = ring + (size_t)slot * p.slotf;
+    int head = head0;
+    for (int n = 0, q = 0; n < N; ++n) {
+      if (q == 0) mbar_wait(&full[slot], par);
+      const float* sl = ring + ((size_t)slot * p.G + q) * p.slotf;
       const long long roff = (((long long)b * N + n) * p.H + y);
-      const int head = row_head(p.logits, roff * p.pitch);
       const int off0 = kPad + head;
       float* RA = aux + (size_t)(n & 1) * 3 * p.wpad;  // (1-a) * dwl  (or dwl on special planes)
       float* RB = RA + p.wpad;                          // a * dwl      (or a)
       float* RC = RB + p.wpad;                          //              (or x0 as float)
-      const float xof = T.xof[n];
-      const float dn = T.d[n];
-      const bool special = T.special[n] != 0;
-      const int k0 = T.k0[n];
+      const PlaneInfo pi = T[n];
+      const float xof = pi.xof;
+      const float dn = pi.d;
+      const bool special = pi.special != 0;
+      const int k0 = pi.k0;
       float l[kPX];
       if (active) {
-        float wl[kPX], sc[3][kPX], a[kPX], x0s[kPX];
         load4(sl, off0 + xb, (off0 + xb) & 3, l);
         if (!special) {
-          const float k0f = (float)k0;
+          const bool interior = warp_last_xb + k0 + 4 <= W - 1;
           float v[5];
-          win_right(sl, off0, xb, k0, W, v);
-#pragma unroll
-          for (int i = 0; i < kPX; ++i) {
-            float t = coord_plus(g0[i], xof, cW);
-            a[i] = __fsub_rn(__fsub_rn(t, k0f), xf[i]);
-            wl[i] = fmaf(a[i], v[i + 1] - v[i], v[i]);
-          }
+          float2 a[2], wl[2], dP[2];
+          win_right(sl, off0, xb, k0, W, interior, v);
+          a[0] = frac2(g0p[0], nxf[0], xof, cW, pi.nk0f);
+          a[1] = frac2(g0p[1], nxf[1], xof, cW, pi.nk0f);
+          wl[0] = make_float2(fmaf(a[0].x, v[1] - v[0], v[0]), fmaf(a[0].y, v[2] - v[1], v[1]));
+          wl[1] = make_float2(fmaf(a[1].x, v[3] - v[2], v[2]), fmaf(a[1].y, v[4] - v[3], v[3]));
+          const ImgWin iw = img_win(img, pi, xb, wz);
+          float2 oma[2] = {fma2(a[0], splat(-1.f), splat(1.f)), fma2(a[1], splat(-1.f), splat(1.f))};
+          dP[0] = dP[1] = splat(0.f);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            win_right(img + c * p.wpad, kPad, xb, k0, W, v);
-#pragma unroll
-            for (int i = 0; i < kPX; ++i) sc[c][i] = fmaf(a[i], v[i + 1] - v[i], v[i]);
+            const float4 A = *reinterpret_cast<const float4*>(iw.pa + c * wcopy);
+            const float4 Bq = *reinterpret_cast<const float4*>(iw.pb + c * wcopy);
+            // sampled colour = (1-a) I[x0] + a I[x0+1];  dP += g_pan_c * colour
+            float2 s0 = fma2(a[0], make_float2(Bq.x, Bq.y), mul2(oma[0], make_float2(A.x, A.y)));
+            float2 s1 = fma2(a[1], make_float2(Bq.z, Bq.w), mul2(oma[1], make_float2(A.z, A.w)));
+            dP[0] = fma2(gp[c][0], s0, dP[0]);
+            dP[1] = fma2(gp[c][1], s1, dP[1]);
           }
+          float2 ra[2], rb[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float2 P = ex2_2(fma2(wl[h], splat(kLog2e), nlw[h]));
+            const float2 dwl = mul2(mul2(P, add2(dP[h], ndot[h])), okm[h]);
+            rb[h] = mul2(a[h], dwl);
+            ra[h] = fma2(rb[h], splat(-1.f), dwl);
+          }
+          if (!interior) {
+            // taps beyond the row end carry no gradient (zero padding)
+            float* rav = &ra[0].x;  // ra[0..1] are contiguous float2s
+            float* rbv = &rb[0].x;
+#pragma unroll
+            for (int i = 0; i < kPX; ++i) {
+              if (xb + i + k0 > W - 1) (i < 2 ? (&ra[0].x)[i] : (&ra[1].x)[i - 2]) = 0.f;
+              if (xb + i + k0 + 1 > W - 1) (i < 2 ? (&rb[0].x)[i] : (&rb[1].x)[i - 2]) = 0.f;
+            }
+            (void)rav; (void)rbv;
+          }
+          *reinterpret_cast<float4*>(RA + kPad + xb) = make_float4(ra[0].x, ra[0].y, ra[1].x, ra[1].y);
+          *reinterpret_cast<float4*>(RB + kPad + xb) = make_float4(rb[0].x, rb[0].y, rb[1].x, rb[1].y);
         } else {
           const float* lrow = sl + off0;
+          float ra[kPX], rb[kPX], x0s[kPX];
 #pragma unroll
           for (int i = 0; i < kPX; ++i) {
+            const bool ok = xb + i < W;
             float t = coord_plus(g0[i], xof, cW);
             float x0f = floorf(t);
-            a[i] = t - x0f;
+            float aa = t - x0f;
             x0s[i] = x0f;
             int x0 = (int)x0f;
             float f0 = tap(lrow, x0, W), f1 = tap(lrow, x0 + 1, W);
-            wl[i] = fmaf(a[i], f1 - f0, f0);
+            float wlv = fmaf(aa, f1 - f0, f0);
+            float dPv = 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              const float* ir = img + c * p.wpad + kPad;
+              const float* ir = img + c * p.wcopy;
               float i0 = tap(ir, x0, W), i1 = tap(ir, x0 + 1, W);
-              sc[c][i] = fmaf(a[i], i1 - i0, i0);
+              dPv = fmaf(gpv[c][i], fmaf(aa, i1 - i0, i0), dPv);
             }
+            float P = ex2f(fmaf(wlv, kLog2e, nlsewv[i]));
+            ra[i] = ok ? P * (dPv - dotv[i]) : 0.f;
+            rb[i] = aa;
           }
+          *reinterpret_cast<float4*>(RA + kPad + xb) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+          *reinterpret_cast<float4*>(RB + kPad + xb) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+          *reinterpret_cast<float4*>(RC + kPad + xb) = make_float4(x0s[0], x0s[1], x0s[2], x0s[3]);
         }
-        float ra[kPX], rb[kPX];
-#pragma unroll
-        for (int i = 0; i < kPX; ++i) {
-          const bool ok = xb + i < W;
-          float P = ex2f(fmaf(wl[i], kLog2e, -lsews[i]));
-          float dP = fmaf(gp[0][i], sc[0][i], fmaf(gp[1][i], sc[1][i], gp[2][i] * sc[2][i]));
-          float dwl = ok ? P * (dP - dot[i]) : 0.f;
-          if (!special) {
-            // taps beyond the row end carry no gradient (zero padding)
-            ra[i] = (xb + i + k0 <= W - 1) ? (1.0f - a[i]) * dwl : 0.f;
-            rb[i] = (xb + i + k0 + 1 <= W - 1) ? a[i] * dwl : 0.f;
-          } else {
-            ra[i] = dwl;
-            rb[i] = a[i];
-          }
-        }
-        *reinterpret_cast<float4*>(RA + kPad + xb) = make_float4(ra[0], ra[1], ra[2], ra[3]);
-        *reinterpret_cast<float4*>(RB + kPad + xb) = make_float4(rb[0], rb[1], rb[2], rb[3]);
-        if (special) *reinterpret_cast<float4*>(RC + kPad + xb) = make_float4(x0s[0], x0s[1], x0s[2], x0s[3]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[slot]);
+      if (++q == p.G || n == N - 1) {
+        q = 0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+        if (++slot == p.S) { slot = 0; par ^= 1; }
+      }
+      head = (head + plane_head_step) & 3;
       named_bar_sync(2, ncons);
       if (active) {
         float g[kPX];
         if (!special) {
+          const bool interior_g = warp_first_xb - k0 - 1 >= 0 && warp_last_xb - k0 + 3 <= W - 1;
           float va[5], vb[5];
-          win_any(RA, kPad, xb - k0, W, va);      // pixel x = j - k0 sampled tap x0 = j with weight (1-a)
-          win_any(RB, kPad, xb - k0 - 1, W, vb);  // pixel x = j - k0 - 1 sampled tap x0+1 = j with weight a
+          win_any(RA, kPad, xb - k0, W, interior_g, va);      // pixel x = j - k0 sampled tap x0 = j with weight (1-a)
+          win_any(RB, kPad, xb - k0 - 1, W, interior_g, vb);  // pixel x = j - k0 - 1 sampled tap x0+1 = j with weight a
 #pragma unroll
           for (int i = 0; i < kPX; ++i) g[i] = va[i] + vb[i];
         } else {
           const float* rd = RA + kPad;
           const float* rw = RB + kPad;
           const float* rx = RC + kPad;
+          const int kn = (int)floorf(xof * cW);
 #pragma unroll
           for (int i = 0; i < kPX; ++i) {
             const int j = xb + i;
             float acc = 0.f;
             // x0(x) - x is within +-1 of the nominal floor; scan the row window that can reach j
-            const int kn = (int)floorf(xof * cW);
             for (int x = j - kn - 2; x <= j - kn + 1; ++x) {
               if (x < 0 || x > W - 1) continue;
               const int x0 = (int)rx[x];
@@ -759,64 +980,104 @@ __global__ void __launch_bounds__(544, 1) med_bwd_kernel(const MedParams p) {
             g[i] = acc;
           }
         }
-#pragma unroll
-        for (int i = 0; i < kPX; ++i) {
-          float p0 = ex2f(fmaf(l[i], kLog2e, -lse0s[i]));
-          g[i] = fmaf(p0 * gd[i], dn - dsp[i], g[i]);
-        }
-        store_row4(p.g_logits + roff * p.g_pitch, xb, g, W);
+        // disparity branch: p0_n * g_disp * (d_n - disp)
+        const float2 p0a = ex2_2(fma2(make_float2(l[0], l[1]), splat(kLog2e), nl0[0]));
+        const float2 p0b = ex2_2(fma2(make_float2(l[2], l[3]), splat(kLog2e), nl0[1]));
+        const float2 ga = fma2(mul2(p0a, gd[0]), add2(splat(dn), ndsp[0]), make_float2(g[0], g[1]));
+        const float2 gb = fma2(mul2(p0b, gd[1]), add2(splat(dn), ndsp[1]), make_float2(g[2], g[3]));
+        const float go[4] = {ga.x, ga.y, gb.x, gb.y};
+        store_row4(p.g_logits + roff * p.g_pitch, xb, go, W);
       }
     }
   }
 }
 
 // =============================================================================================
-// Disparity-only epilogue (inference): pure streaming, no staging needed.
+// Disparity-only epilogue (inference): pure streaming, no staging needed.  4 pixels per thread,
+// all planes of a pixel quad in flight (MLP), float4 loads when the pitch allows.
 // =============================================================================================
 __global__ void __launch_bounds__(256) med_disp_kernel(const float* __restrict__ logits, const float* __restrict__ d_lvl,
                                                        float* __restrict__ disp, int B, int N, int H, int W,
-                                                       long long pitch) {
-  const long long total = (long long)B * H * W;
+                                                       long long pitch, int vec4) {
+  const int wq = (W + 3) / 4;
+  const long long total = (long long)B * H * wq;
+  const long long ps = (long long)H * pitch;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    const long long r = i / W;
+    const int xq = (int)(i % wq);
+    const long long r = i / wq;
     const int y = (int)(r % H);
     const int b = (int)(r / H);
+    const int x = xq * 4;
     const float* lp = logits + (((long long)b * N) * H + y) * pitch + x;
-    const long long ps = (long long)H * pitch;
-    float m = -INFINITY, z = 0.f, acc = 0.f;
-#pragma unroll 7
+    const float* dl = d_lvl + (size_t)b * N;
+    float m[4], z[4], acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m[k] = -INFINITY; z[k] = 0.f; acc[k] = 0.f; }
+    const bool full = vec4 && x + 3 < W;
+#pragma unroll 4
     for (int n = 0; n < N; ++n) {
-      float ls = __ldg(lp + n * ps) * kLog2e;
-      if (ls > m + kLazy) {
-        float f = ex2f(m - ls);
-        z *= f;
-        acc *= f;
-        m = ls;
+      float v[4];
+      if (full) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(lp + n * ps));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = x + k < W ? __ldg(lp + n * ps + k) : 0.f;
       }
-      float e = ex2f(ls - m);
-      z += e;
-      acc = fmaf(__ldg(d_lvl + b * N + n), e, acc);
+      const float dn = __ldg(dl + n);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float ls = v[k] * kLog2e;
+        if (ls > m[k] + kLazy) {
+          const float f = ex2f(m[k] - ls);
+          z[k] *= f;
+          acc[k] *= f;
+          m[k] = ls;
+        }
+        const float e = ex2f(ls - m[k]);
+        z[k] += e;
+        acc[k] = fmaf(dn, e, acc[k]);
+      }
     }
-    disp[i] = acc / z;
+    float* o = disp + ((long long)b * H + y) * W + x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (x + k < W) o[k] = acc[k] / z[k];
   }
 }
 
-int pick_config(MedParams& p, int n_aux_rows, int* threads, int* smem_bytes) {
+// Measured on B200 (640-px rows): 3 CTAs/SM at 96 registers beats 2 CTAs/SM at 112 registers (0.28 vs 0.33 ms): the
+// kernel is latency- rather than issue-bound, so occupancy wins.  FALN_MED_TUNE_2CTA selects the 112-register variant.
+int pick_config(MedParams& p, int n_aux_rows, int* threads, int* smem_bytes, bool* narrow) {
   const int W = p.W;
   int groups = (W + kPX - 1) / kPX;
   int ncw = (groups + 31) / 32;
   *threads = (ncw + 1) * 32;
-  p.wpad = ((W + 3) & ~3) + 2 * kPad;
-  p.slotf = ((W + 3) & ~3) + 2 * kPad + 8;
-  // ring depth: enough bytes in flight per SM to cover HBM latency (~64 KB/SM), within ~200 KB
-  int per_slot = p.slotf * 4;
-  int fixed = make_layout(0, p.slotf, p.wpad, 3, n_aux_rows).total;
-  int S = 12;
-  while (S > 3 && fixed + S * (per_slot + 16) > 100 * 1024) --S;
-  p.S = S;
-  *smem_bytes = make_layout(S, p.slotf, p.wpad, 3, n_aux_rows).total;
+  const int wr = (W + 3) & ~3;
+  p.wpad = wr + 2 * kPad;
+  p.slotf = wr + 2 * kPad + 8;
+  p.wcopy = wr + 16;
+  // ring: S groups of G plane rows (one barrier hand-shake per group).  Prefer G = 4 with 3 groups in flight; shrink the
+  // group before giving up CTAs per SM.
+  *narrow = *threads <= 288 && (p.flags & 2u);
+  const int per_slot = p.slotf * 4;
+  const int fixed = make_layout(0, 1, p.slotf, p.wpad, p.wcopy, n_aux_rows).total;
+  const int budgets[3] = {(*narrow ? 110 : (W <= 700 ? 72 : (W <= 1400 ? 110 : 220))) * 1024, 110 * 1024, 220 * 1024};
+  p.S = 0;
+  for (int bi = 0; bi < 3 && p.S == 0; ++bi) {
+    for (int G = 4; G >= 1 && p.S == 0; G >>= 1) {
+      for (int S = 3; S >= 2; --S) {
+        if (fixed + S * (G * per_slot + 16) <= budgets[bi]) {
+          p.S = S;
+          p.G = G;
+          break;
+        }
+      }
+    }
+  }
+  if (p.S == 0) { p.S = 2; p.G = 1; }
+  *smem_bytes = make_layout(p.S, p.G, p.slotf, p.wpad, p.wcopy, n_aux_rows).total;
   return 0;
 }
 
@@ -842,8 +1103,10 @@ extern "C" int faln_med_fwd(const float* logits, const float* image, const float
   p.logit_bytes = (((long long)B * N * H - 1) * logit_pitch + W) * 4;
   const bool masks = maskL != nullptr;
   int threads, smem;
-  pick_config(p, masks ? 4 : 0, &threads, &smem);
-  auto kern = masks ? med_fwd_kernel<true> : med_fwd_kernel<false>;
+  bool narrow;
+  pick_config(p, masks ? 4 : 0, &threads, &smem, &narrow);
+  auto kern = narrow ? (masks ? med_fwd_kernel<true, 288, 112> : med_fwd_kernel<false, 288, 112>)
+                     : (masks ? med_fwd_kernel<true, 544, 96> : med_fwd_kernel<false, 544, 96>);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
@@ -872,14 +1135,16 @@ extern "C" int faln_med_bwd(const float* logits, const float* image, const float
   p.B = B; p.N = N; p.H = H; p.W = W; p.pitch = logit_pitch; p.flags = flags;
   p.logit_bytes = (((long long)B * N * H - 1) * logit_pitch + W) * 4;
   int threads, smem;
-  pick_config(p, 6, &threads, &smem);
-  cudaFuncSetAttribute(med_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  bool narrow;
+  pick_config(p, 6, &threads, &smem, &narrow);
+  auto kern = narrow ? med_bwd_kernel<288, 112> : med_bwd_kernel<544, 96>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, med_bwd_kernel, threads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
   if (per_sm < 1) per_sm = 1;
   int grid = sm_count() * per_sm;
   if (grid > B * H) grid = B * H;
-  med_bwd_kernel<<<grid, threads, smem, as_stream(stream)>>>(p);
+  kern<<<grid, threads, smem, as_stream(stream)>>>(p);
   return after_launch("med_bwd_kernel");
 }
 
@@ -887,10 +1152,11 @@ extern "C" int faln_med_disp(const float* logits, const float* d_lvl, float* dis
                              long long logit_pitch, faln_stream_t stream) {
   FALN_REQUIRE(logits && d_lvl && disp, "faln_med_disp: null pointer");
   FALN_REQUIRE(B > 0 && H > 0 && W > 0 && N >= 2, "faln_med_disp: bad shape");
-  long long total = (long long)B * H * W;
+  long long total = (long long)B * H * ((W + 3) / 4);
   int grid = (int)((total + 255) / 256);
   int cap = sm_count() * 16;
   if (grid > cap) grid = cap;
-  med_disp_kernel<<<grid, 256, 0, as_stream(stream)>>>(logits, d_lvl, disp, B, N, H, W, logit_pitch);
+  const int vec4 = (logit_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  med_disp_kernel<<<grid, 256, 0, as_stream(stream)>>>(logits, d_lvl, disp, B, N, H, W, logit_pitch, vec4);
   return after_launch("med_disp_kernel");
 }

@@ -56,6 +56,7 @@ long long faln_launch_count(void);
  * flags: FALN_MED_FORCE_GENERIC forces the per-pixel floor path on every plane (testing).
  */
 #define FALN_MED_FORCE_GENERIC 1u
+#define FALN_MED_TUNE_2CTA 2u /* rows <= 1024 px: 2 CTAs/SM at 112 registers instead of 3 CTAs/SM at 96 (tuning aid) */
 int faln_med_fwd(const float* logits, const float* image, const float* g0x, const float* x_of,
                  const float* d_lvl, float* pan, float* disp, float* maskL, float* maskR, float* lse0,
                  float* lsew, int B, int N, int H, int W, long long logit_pitch, unsigned flags,

@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fal_net_b200 import med  # noqa: E402
 
 
-def bench(B, N, H, W, iters=10, sets=3, peak=6557.8):
+def bench(B, N, H, W, iters=10, sets=3, peak=6557.8, flags=0):
     dev = torch.device("cuda:0")
     gen = torch.Generator(device=dev).manual_seed(7)
     L = [2 * torch.randn(B, N, H, W, generator=gen, device=dev) for _ in range(sets)]
@@ -41,12 +41,12 @@ def bench(B, N, H, W, iters=10, sets=3, peak=6557.8):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters
 
-    t = timeit(lambda s: med.med_forward_raw(L[s], I[s], xo, d, g0x, True, True, False))
+    t = timeit(lambda s: med.med_forward_raw(L[s], I[s], xo, d, g0x, True, True, False, flags))
     out["fwd"] = dict(ms=t, gbs=4 * (N + 7) * px / t / 1e6)
-    t = timeit(lambda s: med.med_forward_raw(L[s], I[s], xo, d, g0x, True, True, True))
+    t = timeit(lambda s: med.med_forward_raw(L[s], I[s], xo, d, g0x, True, True, True, flags))
     out["fwd_masks"] = dict(ms=t, gbs=4 * (N + 9) * px / t / 1e6)
     t = timeit(lambda s: med.med_backward_raw(L[s], I[s], xo, d, g0x, res[s]["pan"], res[s]["disp"], res[s]["lse0"],
-                                              res[s]["lsew"], gp, gd, out=gl))
+                                              res[s]["lsew"], gp, gd, flags, out=gl))
     out["bwd"] = dict(ms=t, gbs=4 * (2 * N + 7) * px / t / 1e6)
     t = timeit(lambda s: med.med_disp_only(L[s], d))
     out["disp_only"] = dict(ms=t, gbs=4 * (N + 1) * px / t / 1e6)
@@ -59,10 +59,11 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--profile", default="", help="B,N,H,W: run each kernel a few times only (for ncu)")
+    ap.add_argument("--flags", type=int, default=0)
     a = ap.parse_args()
     if a.profile:
         B, N, H, W = (int(v) for v in a.profile.split(","))
-        print(json.dumps(bench(B, N, H, W, iters=2, sets=2)))
+        print(json.dumps(bench(B, N, H, W, iters=2, sets=2, flags=a.flags)))
         sys.exit(0)
     peak = 6557.8
     try:
@@ -74,5 +75,5 @@ if __name__ == "__main__":
     if not a.quick:
         cfgs += [(8, 33, 375, 1242), (8, 65, 375, 1242), (2, 33, 1024, 2048), (2, 65, 1024, 2048)]
     for B, N, H, W in cfgs:
-        r = bench(B, N, H, W, peak=peak)
+        r = bench(B, N, H, W, peak=peak, flags=a.flags)
         print(json.dumps(dict(B=B, N=N, H=H, W=W, **{k: {kk: round(vv, 4) for kk, vv in v.items()} for k, v in r.items()})))
