@@ -23,28 +23,28 @@ from . import conv_native as CN
 
 LIBRARY_CALLS = {"conv_backward": 0}
 
-# packed bf16 KRSC weights, keyed by (id(param), param._version, generation): parameters that do not change
-# (frozen Stage-1 model, VGG, inference) are packed once; the trainer bumps GENERATION after each fused-Adam
-# step because the kernel updates the arena behind torch's version counter.
-_PACKED: dict = {}
+# packed bf16 KRSC weights are cached ON the parameter object (attribute ``_faln_packed``), tagged with
+# (param._version, generation, cin): parameters that do not change (frozen Stage-1 model, VGG, inference) are packed
+# once; the trainer bumps GENERATION after each fused-Adam step because the kernel updates the arena behind torch's
+# version counter.  (A dict keyed by id(param) is wrong: ids are recycled when a model is freed.)
 GENERATION = [0]
 
 
 def invalidate_packed_weights():
     GENERATION[0] += 1
-    if len(_PACKED) > 4096:
-        _PACKED.clear()
 
 
 def _packed(weight, cin, tag):
     if weight.grad_fn is not None:                   # derived tensor (the folded logit conv): pack every call
         return CN.pack_weight(weight[:, :cin])
-    key = (id(weight), weight._version, GENERATION[0] if weight.requires_grad else -1, cin, tag)
-    hit = _PACKED.get(key)
-    if hit is None:
-        hit = CN.pack_weight(weight[:, :cin])
-        _PACKED[key] = hit
-    return hit
+    key = (weight._version, GENERATION[0] if weight.requires_grad else -1, cin, tag, weight.data_ptr())
+    cache = getattr(weight, "_faln_packed", None)
+    if cache is None or cache[0] != key:
+        cache = (key, CN.pack_weight(weight[:, :cin]))
+        weight._faln_packed = cache
+    return cache[1]
+
+
 CL = torch.channels_last
 _ACT = CN.ACT
 
