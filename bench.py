@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the training step kernel by kernel instead of replaying its CUDA graph")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
 
@@ -189,8 +190,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from fal_net_b200 import _lib, med, models, steps
     from fal_net_b200 import loss_functions as LF
-    from fal_net_b200.trainer import FlatAdamDDP
+    from fal_net_b200.trainer import FlatAdamDDP, GraphedStep
     from fal_net_b200 import conv as C
+    run_gpu.GraphedStep = GraphedStep
 
     result = run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP, C)
     if world > 1:
@@ -285,11 +287,26 @@ def run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP
 
     frames_per_step = B * world * (2 if wl == "stage2" else 1)
 
+    # training steps replay ONE captured CUDA graph (zero_grad + forward + losses + backward + all-reduce + Adam)
+    graphed = None
+    launches_per_step = lib_convs_per_step = None
+    if wl in ("stage1", "stage2") and not a.no_graph:
+        def loss_fn(left, right):
+            if wl == "stage1":
+                return steps.stage1_loss(model, left, right, mn, mx, a_p=0.0)[0]
+            return steps.stage2_loss(model, fix_model, left, right, mn, mx, a_p=0.01, vgg=vgg)["loss"]
+        graphed = run_gpu.GraphedStep(opt, loss_fn, devb[0][0], devb[0][1], warmup=3)   # 3 eager steps, then capture
+        l0, c0 = _lib.launch_count(), C.LIBRARY_CALLS["conv_backward"]
+        step_dev(*devb[0])                                                              # one eager step: count launches
+        launches_per_step, lib_convs_per_step = _lib.launch_count() - l0, C.LIBRARY_CALLS["conv_backward"] - c0
+
+    def run_step(left, right):
+        return graphed.run(left, right) if graphed is not None else step_dev(left, right)
+
     # ---------------- device-resident timing (value) ----------------
     for i in range(a.warmup):
-        step_dev(*devb[i % nb])
+        run_step(*devb[i % nb])
     sync_all()
-    med.TIMING = []
     lib_conv0 = C.LIBRARY_CALLS["conv_backward"]
     launches0 = _lib.launch_count()
     clocks = ClockSampler(dev.index or 0)
@@ -299,19 +316,26 @@ def run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP
     sync_all()
     e0.record()
     for i in range(a.steps):
-        step_dev(*devb[i % nb])
+        run_step(*devb[i % nb])
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1) / a.steps
     clk = clocks.stop() if rank == 0 else None
-    launches = _lib.launch_count() - launches0
-    lib_convs = C.LIBRARY_CALLS["conv_backward"] - lib_conv0
-    timing, med.TIMING = med.TIMING, None
+    launches = (_lib.launch_count() - launches0) if graphed is None else launches_per_step * a.steps
+    lib_convs = (C.LIBRARY_CALLS["conv_backward"] - lib_conv0) if graphed is None else lib_convs_per_step * a.steps
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
     value = frames_per_step / (ms / 1e3)
+
+    # per-launch CUDA-event timing of the MED kernels (event records cannot live inside a captured graph, so the same
+    # steps are run kernel by kernel once more; these iterations are not part of `value`)
+    med.TIMING = []
+    for i in range(max(3, min(a.steps, 10))):
+        step_dev(*devb[i % nb])
+    sync_all()
+    timing, med.TIMING = med.TIMING, None
 
     # roofline of the MED kernels, from CUDA events around each launch inside the timed region
     kinds = {}
@@ -325,7 +349,7 @@ def run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP
         st = med_stats[dom]
         roofline = {"kernel": dom, "bound": "hbm", "achieved": st["gbs"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": st["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
-                    "avg_launch_ms": st["avg_ms"], "share_of_step": st["avg_ms"] * st["launches"] / a.steps / ms,
+                    "avg_launch_ms": st["avg_ms"], "share_of_step": st["avg_ms"] * (st["launches"] / max(3, min(a.steps, 10))) / ms,
                     "all_med_kernels": med_stats}
 
     # ---------------- end-to-end timing (e2e): pinned host inputs, H2D + D2H inside the timed region ----------------
@@ -335,9 +359,9 @@ def run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP
     out_host = torch.empty(1, pin_memory=True)
     for i in range(a.steps):
         l, r = host[i % nb]
-        ld = l.to(dev, non_blocking=True)
-        rd = r.to(dev, non_blocking=True) if wl in ("stage1", "stage2") else None
-        loss = step_dev(ld, rd)
+        ld = l.to(dev, non_blocking=True) if graphed is None else None
+        rd = r.to(dev, non_blocking=True) if (wl in ("stage1", "stage2") and graphed is None) else None
+        loss = run_step(ld, rd) if graphed is None else graphed.run(l, r)     # graph mode: H2D straight into the static inputs
         out_host.copy_(loss.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()          # the user reads the loss every step
     e1.record()
@@ -355,7 +379,7 @@ def run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP
         "config": cfg, "clocks": clk,
         "e2e": {"value": frames_per_step / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-        "gpu_launches": launches,
+        "gpu_launches": launches, "cuda_graph": graphed is not None,
         "library_conv_backward_calls_in_timed_region": lib_convs,
         "roofline": roofline,
     }

@@ -20,16 +20,30 @@ def pack_weight(w: torch.Tensor, cout_pad: int | None = None) -> torch.Tensor:
     return out
 
 
+_BORDER_MASKS: dict = {}
+
+
+def _border_masks(device) -> torch.Tensor:
+    """[16,3,3] 0/1 masks: which taps of a 3x3 window stay inside the image for border class rc*4+cc
+    (bit0: first tap outside, bit1: last tap outside)."""
+    m = _BORDER_MASKS.get(str(device))
+    if m is None:
+        m = torch.zeros(16, 3, 3)
+        for rc in range(4):
+            for cc in range(4):
+                for kh in range(3):
+                    for kw in range(3):
+                        out = (kh == 0 and rc & 1) or (kh == 2 and rc & 2) or (kw == 0 and cc & 1) or (kw == 2 and cc & 2)
+                        m[rc * 4 + cc, kh, kw] = 0.0 if out else 1.0
+        m = m.to(device)
+        _BORDER_MASKS[str(device)] = m
+    return m
+
+
 def const_channel_table(wf: torch.Tensor, cout_pad=None) -> torch.Tensor:
     """wf [Cout,3,3]: weights of a spatially constant input channel -> [16,Cout] sums over the taps that stay inside
-    the image, per border class rc*4+cc (bit0: first tap outside, bit1: last tap outside)."""
-    rows = []
-    for rc in range(4):
-        kh = [k for k in range(3) if not ((k == 0 and rc & 1) or (k == 2 and rc & 2))]
-        for cc in range(4):
-            kw = [k for k in range(3) if not ((k == 0 and cc & 1) or (k == 2 and cc & 2))]
-            rows.append(wf[:, kh][:, :, kw].sum(dim=(1, 2)))
-    return torch.stack(rows, 0).float().contiguous()
+    the image, per border class (one small matmul on the device; no host-side indexing, so it is graph-capturable)."""
+    return (_border_masks(wf.device).view(16, 9) @ wf.float().reshape(wf.shape[0], 9).t()).contiguous()
 
 
 def _nhwc(t: torch.Tensor) -> torch.Tensor:

@@ -11,7 +11,11 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
                                                    float4* __restrict__ m, float4* __restrict__ v,
                                                    __nv_bfloat162* __restrict__ w16, long long n4, float step_size,
                                                    float beta1, float beta2, float inv_sqrt_bc2, float eps, float wd,
-                                                   float gscale) {
+                                                   float gscale, const float* __restrict__ hp) {
+  if (hp) {  // CUDA-graph mode: step size and bias correction live on the device (written by adam_tick_kernel)
+    step_size = hp[2];
+    inv_sqrt_bc2 = hp[3];
+  }
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     float4 P = p[i], G = g[i], M = m[i], V = v[i];
     float* pp = reinterpret_cast<float*>(&P);
@@ -33,6 +37,17 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
       w16[2 * i] = __floats2bfloat162_rn(pp[0], pp[1]);
       w16[2 * i + 1] = __floats2bfloat162_rn(pp[2], pp[3]);
     }
+  }
+}
+
+// hp = {lr, step (as float), lr / (1 - beta1^step), 1 / sqrt(1 - beta2^step)}: advances the step counter and refreshes
+// the derived factors on the device, so a captured CUDA graph replays a correct Adam update at every step.
+__global__ void adam_tick_kernel(float* hp, float beta1, float beta2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const double t = (double)hp[1] + 1.0;
+    hp[1] = (float)t;
+    hp[2] = (float)((double)hp[0] / (1.0 - pow((double)beta1, t)));
+    hp[3] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, t)));
   }
 }
 
@@ -117,7 +132,24 @@ extern "C" int faln_adam(float* p, const float* g, float* m, float* v, void* w16
   adam_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(
       reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
       reinterpret_cast<float4*>(v), static_cast<__nv_bfloat162*>(w16), n4, (float)(lr / bc1), beta1, beta2,
-      (float)(1.0 / sqrt(bc2)), eps, weight_decay, grad_scale);
+      (float)(1.0 / sqrt(bc2)), eps, weight_decay, grad_scale, nullptr);
+  return after_launch("adam_kernel");
+}
+
+extern "C" int faln_adam_dev(float* p, const float* g, float* m, float* v, void* w16, long long n, float* hp, float beta1,
+                             float beta2, float eps, float weight_decay, float grad_scale, faln_stream_t stream) {
+  FALN_REQUIRE(p && g && m && v && hp && n > 0 && (n & 3) == 0, "faln_adam_dev: n must be a positive multiple of 4");
+  FALN_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                 reinterpret_cast<uintptr_t>(v)) & 15) == 0, "faln_adam_dev: arenas must be 16-byte aligned");
+  adam_tick_kernel<<<1, 32, 0, as_stream(stream)>>>(hp, beta1, beta2);
+  const long long n4 = n / 4;
+  long long grid = (n4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  adam_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+      reinterpret_cast<float4*>(v), static_cast<__nv_bfloat162*>(w16), n4, 0.f, beta1, beta2, 0.f, eps, weight_decay,
+      grad_scale, hp);
   return after_launch("adam_kernel");
 }
 

@@ -15,3 +15,13 @@ def adam_step_(p, g, m, v, w16=None, *, lr, beta1=0.5, beta2=0.999, eps=1e-8, we
                               float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale),
                               _lib.cur_stream())
     _lib.check(rc, "faln_adam")
+
+
+def adam_step_dev_(p, g, m, v, hp, w16=None, *, beta1=0.5, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    """Same update with the learning rate and step counter in device memory (``hp`` = float32[4]: lr, step, and two
+    derived factors the kernel maintains) -- no host scalar changes between steps, so the call can be captured in a
+    CUDA graph and replayed."""
+    rc = _lib.lib().faln_adam_dev(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), _lib.ptr(w16), p.numel(),
+                                  _lib.ptr(hp), float(beta1), float(beta2), float(eps), float(weight_decay),
+                                  float(grad_scale), _lib.cur_stream())
+    _lib.check(rc, "faln_adam_dev")

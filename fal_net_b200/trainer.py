@@ -47,6 +47,9 @@ class FlatAdamDDP:
             p.grad = self.g[off:off + s].view_as(p.data)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.t = 0
+        # device-side copy of (lr, step) for CUDA-graph replay (optim.adam_step_dev_); None on the CPU test path
+        self.hp = torch.tensor([lr, 0.0, 0.0, 0.0], device=dev, dtype=torch.float32) if dev.type == "cuda" else None
+        self.device_hp = False                          # GraphedStep switches this on
         self._update = _update or optim.adam_step_     # tests inject a CPU update to exercise the host logic on gloo
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
@@ -110,7 +113,11 @@ class FlatAdamDDP:
             else:
                 dist.all_reduce(self.g, op=dist.ReduceOp.SUM, group=self.pg)
         self.t += 1
-        self._update(self.p, self.g, self.m, self.v, None, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
+        if self.device_hp:
+            optim.adam_step_dev_(self.p, self.g, self.m, self.v, self.hp, None, beta1=self.betas[0], beta2=self.betas[1],
+                                 eps=self.eps, weight_decay=self.wd, grad_scale=1.0 / self.world)
+        else:
+            self._update(self.p, self.g, self.m, self.v, None, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
                          eps=self.eps, weight_decay=self.wd, step=self.t, grad_scale=1.0 / self.world)
         from . import conv
         conv.invalidate_packed_weights()      # the arena changed behind torch's version counters
@@ -122,3 +129,53 @@ class FlatAdamDDP:
 
     def set_lr(self, lr):
         self.lr = lr
+        if self.hp is not None:
+            self.hp[0:1].fill_(lr)
+
+
+class GraphedStep:
+    """One whole training step (zero_grad, forward, losses, backward, gradient all-reduce, Adam) captured once in a
+    CUDA graph and replayed: the ~1,500 kernel launches of a step cost one ``cudaGraphLaunch`` on the host.
+
+    ``loss_fn(left, right) -> (loss, *aux)`` must be shape-static and free of host synchronisation (the step bodies of
+    fal_net_b200.steps are).  ``run(left, right)`` copies the batch into the static input buffers (device-to-device or
+    pinned-host-to-device, on the current stream), replays the graph and returns the static loss tensor.
+    The Adam step counter / learning rate live on the device (FlatAdamDDP.hp), so replays stay exact."""
+
+    def __init__(self, opt: "FlatAdamDDP", loss_fn, left, right, warmup: int = 3):
+        self.opt, self.loss_fn = opt, loss_fn
+        self.left = torch.empty_like(left, device=opt.p.device)
+        self.right = torch.empty_like(right, device=opt.p.device)
+        self.left.copy_(left)
+        self.right.copy_(right)
+        opt.device_hp = True
+        opt.hp[1:2].fill_(float(opt.t))
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                    # warm-up on a side stream (allocator, lazy inits, NCCL)
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+        self.replays = 0
+
+    def _body(self):
+        self.opt.zero_grad()
+        out = self.loss_fn(self.left, self.right)
+        loss = out[0] if isinstance(out, (tuple, list)) else (out["loss"] if isinstance(out, dict) else out)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def run(self, left=None, right=None):
+        if left is not None:
+            self.left.copy_(left, non_blocking=True)
+        if right is not None:
+            self.right.copy_(right, non_blocking=True)
+        self.graph.replay()
+        self.replays += 1
+        self.opt.t += 1
+        return self.loss

@@ -146,6 +146,10 @@ int faln_occ_mask(const float* a, const float* b, float* out, int B, int H, int 
 int faln_adam(float* p, const float* g, float* m, float* v, void* w16, long long n, float lr, float beta1,
               float beta2, float eps, float weight_decay, int step, float grad_scale,
               faln_stream_t stream);
+/* CUDA-graph-capturable variant: the step counter and learning rate live in device memory, hp = float[4]
+ * {lr, step, (derived) lr/(1-beta1^step), (derived) 1/sqrt(1-beta2^step)}; each call advances hp[1] by one. */
+int faln_adam_dev(float* p, const float* g, float* m, float* v, void* w16, long long n, float* hp, float beta1,
+                  float beta2, float eps, float weight_decay, float grad_scale, faln_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Layout / elementwise helpers of the conv pipeline (bf16 NHWC activations).
