@@ -45,6 +45,10 @@ _SIGNATURES = {
     "faln_nhwc_bf16_to_planar": [_p, _p] + [_i] * 5 + [_ll, _p],
     "faln_planar_to_nhwc_bf16": [_p, _p] + [_i] * 5 + [_ll, _p],
     "faln_conv3x3_fwd": [_p] * 8 + [_i] * 10 + [_ll, _i, _p],
+    "faln_conv3x3_dgrad": [_p] * 5 + [_i] * 12 + [_p],
+    "faln_upsample_nearest_bwd_nhwc": [_p] * 3 + [_i] * 8 + [_p],
+    "faln_maxpool2_bwd_nhwc": [_p] * 3 + [_i] * 5 + [_p],
+    "faln_channel_sum_nhwc": [_p, _p, _ll, _i, _i, _p],
     "faln_stem_conv": [_p] * 4 + [_i] * 6 + [_p],
     "faln_upsample_nearest_nhwc": [_p, _p] + [_i] * 6 + [_p],
     "faln_maxpool2_nhwc": [_p, _p] + [_i] * 4 + [_p],

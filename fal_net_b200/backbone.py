@@ -1,0 +1,247 @@
+"""The FAL_netB encoder-decoder as ONE autograd node with a hand-scheduled backward.
+
+Forward = /root/reference/models/FAL_netB.py:140-176 + the logit 1x1 conv (:190,215), executed layer by layer on the
+tcgen05 kernels (fal_net_b200.conv_native) while a tape keeps the bf16 NHWC activations.
+
+Backward = the exact adjoint of that graph, written out by hand instead of being discovered by autograd:
+
+  * data gradients run on the SAME tcgen05 kernel as the forward (``faln_conv3x3_dgrad``: re-packed weights, stride-2
+    layers as four output-parity classes) and every chain-rule elementwise step is fused into an epilogue --
+    ELU'(saved output), the residual pass-through of the res blocks, the accumulation of the second consumer of a
+    skip tensor, the split of a concatenated input into its two sources (two row ranges of the packed weights);
+  * the nearest-upsample backward is one kernel fused with the producer's ELU';
+  * bias gradients are one channel-sum kernel each;
+  * weight gradients: ``faln_conv3x3_wgrad`` (tcgen05, split-K over pixels) when available, else cuDNN's wgrad
+    (``LIBRARY_CALLS['conv_wgrad']`` counts those for bench.py).
+
+Compared with per-layer autograd.Functions this removes ~700 ATen elementwise / cat / copy / reduce launches per step
+(see profiles/): nothing is concatenated, no gradient is materialised twice, and the schedule is static -- which is what
+lets the whole step live in one CUDA graph.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import conv_native as CN
+from . import layout
+
+CL = torch.channels_last
+LIBRARY_CALLS = {"conv_wgrad": 0}
+
+# (name, cin, cout, stride): encoder stages (/root/reference/models/FAL_netB.py:99-112)
+ENC = (("conv0", 3, 32, 1), ("conv1", 33, 64, 2), ("conv2", 64, 128, 2), ("conv3", 128, 256, 2),
+       ("conv4", 256, 256, 2), ("conv5", 256, 256, 2), ("conv6", 256, 512, 2))
+# (level, up_in, up_out, skip_ch, iconv_out): decoder stages (:116-127); level 1's iconv has no bias / activation
+DEC = ((6, 512, 256, 256, 256), (5, 256, 128, 256, 256), (4, 256, 128, 256, 256), (3, 256, 128, 128, 128),
+       (2, 128, 64, 64, 64), (1, 64, 64, 32, None))
+
+from .conv import GENERATION  # noqa: E402  (shared: bumped by the trainer after each in-place optimiser step)
+
+
+def _cached(weight, tag, fn):
+    """bf16 re-packings of a parameter, cached on the parameter object and refreshed when it changes."""
+    if weight.grad_fn is not None:
+        return fn()
+    key = (weight._version, GENERATION[0] if weight.requires_grad else -1, weight.data_ptr())
+    cache = getattr(weight, "_faln_packs", None)
+    if cache is None or cache.get("key") != key:
+        cache = {"key": key}
+        weight._faln_packs = cache
+    if tag not in cache:
+        cache[tag] = fn()
+    return cache[tag]
+
+
+def _wk(weight, cin=None):
+    cin = cin or weight.shape[1]
+    return _cached(weight, ("fwd", cin), lambda: CN.pack_weight(weight[:, :cin]))
+
+
+def _wd(weight, cin=None):
+    cin = cin or weight.shape[1]
+    return _cached(weight, ("dgrad", cin), lambda: CN.pack_weight_dgrad(weight[:, :cin]))
+
+
+def fold_logit_conv(w_iconv1, w0):
+    """iconv1 (3x3, no bias, no activation; reference :127,174) followed by conv0 (1x1 + bias; :190,215)
+    == one 3x3 conv with W'[o,c,kh,kw] = sum_m W0[o,m] * W_iconv1[m,c,kh,kw]."""
+    return torch.einsum("om,mckl->ockl", w0[:, :, 0, 0], w_iconv1)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def forward(model, image, max_disp, tape=None):
+    """dlog0 [B,N,H,W] fp32 planar (16-byte-multiple row pitch).  ``tape`` (a dict) receives what backward needs."""
+    bb = model.backbone
+    B = image.shape[0]
+    flow_val = (max_disp.reshape(B).float() / 100.0).contiguous()                  # :208-209, constant plane per sample
+    skips = []
+    for i, (name, _, cout, stride) in enumerate(ENC):
+        head = getattr(bb, name)[0]
+        if i == 0:
+            a = CN.stem_conv(image, head.weight, head.bias, 1)                     # reads the fp32 NCHW image directly
+        else:
+            C1 = skips[-1].shape[1]
+            ctab = CN.const_channel_table(head.weight[:, C1].detach()) if i == 1 else None
+            a = CN.conv3x3_fwd(skips[-1], _wk(head.weight, C1), head.bias, stride, 1, cout=cout, ctab=ctab,
+                               cscale=flow_val if i == 1 else None)
+        blk = getattr(bb, name + "_1")
+        r = CN.conv3x3_fwd(a, _wk(blk.conv1.weight), None, 1, 1)
+        s = CN.conv3x3_fwd(r, _wk(blk.conv2.weight), None, 1, 1, residual=a)       # elu(conv2(elu(conv1(x))) + x), :79
+        skips.append(s)
+        if tape is not None:
+            tape[name] = (a, r, s)
+    h = skips[6]
+    for lvl, _, uout, _, iout in DEC:
+        skip = skips[lvl - 1]
+        up = getattr(bb, f"deconv{lvl}")
+        xu = CN.upsample_nearest(h, (skip.shape[2], skip.shape[3]))                # :58
+        u = CN.conv3x3_fwd(xu, _wk(up.conv1.weight), None, 1, 1)                   # :59
+        if iout is not None:
+            ic = getattr(bb, f"iconv{lvl}")[0]
+            hn = CN.conv3x3_fwd(u, _wk(ic.weight), ic.bias, 1, 1, None, skip)      # concat = second TMA source
+            if tape is not None:
+                tape[f"dec{lvl}"] = (h, xu, u, hn)
+            h = hn
+        else:
+            wf = fold_logit_conv(bb.iconv1.weight.detach(), model.conv0.weight.detach())
+            N = wf.shape[0]
+            Bq, _, H, W = u.shape
+            out = layout.alloc_planar(Bq, N, H, W, u.device)
+            CN.conv3x3_fwd(u, CN.pack_weight(wf), model.conv0.bias, 1, 0, None, skip, cout=N, planar_out=out)
+            if tape is not None:
+                tape["dec1"] = (h, xu, u, None)
+                tape["wf"] = wf
+                tape["flow_val"] = flow_val
+                tape["image"] = image
+            return out
+    raise AssertionError("unreachable")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def _wgrad(g_pre, xin, cout, stride=1):
+    """Weight gradient [cout, C(xin), 3, 3] fp32 of a 3x3 conv from the pre-activation gradient and the input."""
+    LIBRARY_CALLS["conv_wgrad"] += 1
+    Cg, C = g_pre.shape[1], xin.shape[1]
+    wshape = torch.empty((Cg, C, 3, 3), device=g_pre.device, dtype=torch.bfloat16).contiguous(memory_format=CL)
+    _, gw, _ = torch.ops.aten.convolution_backward(g_pre, xin, wshape, None, [stride, stride], [1, 1], [1, 1], False,
+                                                   [0, 0], 1, [False, True, False])
+    return gw[:cout].float()
+
+
+def backward(model, tape, g_logits):
+    """Returns {parameter name: fp32 gradient} for every used parameter of the model."""
+    bb = model.backbone
+    grads = {}
+    N = model.no_levels
+    B, _, H, W = g_logits.shape
+    dev = g_logits.device
+
+    def bias_grad(g, C):
+        out = torch.zeros(C, device=dev, dtype=torch.float32)
+        return CN.channel_sum(g, out, C)
+
+    # ---------------------------------------------------------------- folded logits conv (iconv1 o conv0)
+    Np = (N + 31) // 32 * 32
+    g = layout.planar_to_nhwc_bf16(g_logits, Np).permute(0, 3, 1, 2)            # bf16 [B,Np,H,W] channels_last view
+    h2, xu, u, _ = tape["dec1"]
+    s0 = tape["conv0"][2]
+    wf = tape["wf"]
+    grads["conv0.bias"] = bias_grad(g, N)
+    gwf = torch.cat((_wgrad(g, u, N), _wgrad(g, s0, N)), 1)                      # [N,96,3,3]
+    w0 = model.conv0.weight.detach()[:, :, 0, 0]
+    wi1 = bb.iconv1.weight.detach()
+    grads["conv0.weight"] = torch.einsum("ockl,mckl->om", gwf, wi1)[:, :, None, None]
+    grads["backbone.iconv1.weight"] = torch.einsum("om,ockl->mckl", w0, gwf)
+    wd = CN.pack_weight_dgrad(wf)                                                # [96,3,3,Np]
+    C1 = u.shape[1]
+    g_u = CN.conv3x3_dgrad(g, wd, (H, W), rows=(0, C1), dact=1, ysave=u)
+    G_skip = {0: CN.conv3x3_dgrad(g, wd, (H, W), rows=(C1, s0.shape[1]))}        # second consumer arrives in the encoder pass
+    del g
+
+    # ---------------------------------------------------------------- decoder, level 1 .. 6
+    g_h = None
+    for lvl in (1, 2, 3, 4, 5, 6):
+        h_in, xu, u, hn = tape[f"dec{lvl}"]
+        skip = tape[ENC[lvl - 1][0]][2]
+        up = getattr(bb, f"deconv{lvl}")
+        if lvl > 1:
+            ic = getattr(bb, f"iconv{lvl}")[0]
+            cout = ic.weight.shape[0]
+            grads[f"backbone.iconv{lvl}.0.bias"] = bias_grad(g_h, cout)
+            grads[f"backbone.iconv{lvl}.0.weight"] = torch.cat((_wgrad(g_h, u, cout), _wgrad(g_h, skip, cout)), 1)
+            wd = _wd(ic.weight)
+            C1 = u.shape[1]
+            hw = (u.shape[2], u.shape[3])
+            g_u = CN.conv3x3_dgrad(g_h, wd, hw, rows=(0, C1), dact=1, ysave=u)
+            G_skip[lvl - 1] = CN.conv3x3_dgrad(g_h, wd, hw, rows=(C1, skip.shape[1]))
+        grads[f"backbone.deconv{lvl}.conv1.weight"] = _wgrad(g_u, xu, up.conv1.weight.shape[0])
+        g_xu = CN.conv3x3_dgrad(g_u, _wd(up.conv1.weight), (xu.shape[2], xu.shape[3]))
+        # nearest-upsample backward fused with ELU' of the producer (h_{l+1}, or the bottleneck skip s6 for level 6)
+        g_h = CN.upsample_nearest_bwd(g_xu, (h_in.shape[2], h_in.shape[3]), ysave=h_in, dact=1)
+        del g_u, g_xu
+
+    # ---------------------------------------------------------------- encoder, level 6 .. 0
+    g_s = g_h                                                                     # pre-activation gradient of s6
+    for i in (6, 5, 4, 3, 2, 1, 0):
+        name, _, cout, stride = ENC[i]
+        a, r, s = tape[name]
+        head = getattr(bb, name)[0]
+        blk = getattr(bb, name + "_1")
+        hw = (a.shape[2], a.shape[3])
+        grads[f"backbone.{name}_1.conv2.weight"] = _wgrad(g_s, r, cout)
+        g_r = CN.conv3x3_dgrad(g_s, _wd(blk.conv2.weight), hw, dact=1, ysave=r)
+        grads[f"backbone.{name}_1.conv1.weight"] = _wgrad(g_r, a, cout)
+        g_a = CN.conv3x3_dgrad(g_r, _wd(blk.conv1.weight), hw, dact=1, ysave=a, residual=g_s)   # (dgrad + skip path) * ELU'
+        grads[f"backbone.{name}.0.bias"] = bias_grad(g_a, cout)
+        if i == 0:
+            img16 = tape["image"].to(dtype=torch.bfloat16, memory_format=CL)
+            grads["backbone.conv0.0.weight"] = _wgrad(g_a, img16, cout)
+            break
+        prev = tape[ENC[i - 1][0]][2]
+        Cp = prev.shape[1]
+        if i == 1:                                                                # the constant max_disp/100 input plane
+            Bq, _, Hp, Wp = prev.shape
+            plane = tape["flow_val"].to(torch.bfloat16).view(Bq, 1, 1, 1).expand(Bq, 1, Hp, Wp)
+            xin = torch.cat((prev, plane), 1).contiguous(memory_format=CL)
+        else:
+            xin = prev
+        grads[f"backbone.{name}.0.weight"] = _wgrad(g_a, xin, cout, stride)
+        # stride-2 dgrad into the previous skip: add to what the decoder left there, then ELU'(s_{i-1})
+        g_s = CN.conv3x3_dgrad(g_a, _wd(head.weight, Cp), (prev.shape[2], prev.shape[3]), stride=stride,
+                               out=G_skip.pop(i - 1), accum=True, dact=1, ysave=prev)
+        del g_r, g_a
+    return grads
+
+
+class BackboneFn(torch.autograd.Function):
+    """logits = backbone(image); parameters are passed positionally so autograd routes their gradients."""
+
+    @staticmethod
+    def forward(ctx, model, names, image, max_disp, *params):
+        tape = {}
+        out = forward(model, image, max_disp, tape)
+        ctx.model, ctx.names, ctx.tape = model, names, tape
+        return out
+
+    @staticmethod
+    def backward(ctx, g_logits):
+        tape, ctx.tape = ctx.tape, None
+        Bq, Nq, Hq, Wq = g_logits.shape
+        sb, sn, sh, sw = g_logits.stride()
+        if sw != 1 or sn != Hq * sh or sb != Nq * Hq * sh or sh < Wq:            # need a uniformly pitched planar tensor
+            g = layout.alloc_planar(Bq, Nq, Hq, Wq, g_logits.device)
+            g.copy_(g_logits)
+            g_logits = g
+        grads = backward(ctx.model, tape, g_logits)
+        return (None, None, None, None) + tuple(grads.get(n) for n in ctx.names)
+
+
+def logits(model, image, max_disp):
+    """Training-aware entry: tape + hand-scheduled backward when gradients are required, plain forward otherwise."""
+    if not image.is_cuda:
+        raise RuntimeError("fal_net_b200.FAL_netB runs on CUDA (sm_100a) only; there is no CPU path")
+    named = [(n, p) for n, p in model.named_parameters() if "amask_conv" not in n]
+    if torch.is_grad_enabled() and any(p.requires_grad for _, p in named):
+        names = tuple(n for n, _ in named)
+        return BackboneFn.apply(model, names, image, max_disp, *[p for _, p in named])
+    return forward(model, image, max_disp, None)

@@ -116,3 +116,87 @@ def maxpool2(x):
     rc = _lib.lib().faln_maxpool2_nhwc(_lib.ptr(x), _lib.ptr(y), B, Hi, Wi, C, _lib.cur_stream())
     _lib.check(rc, "faln_maxpool2_nhwc")
     return y
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# backward kernels
+# ---------------------------------------------------------------------------------------------------------------
+def pack_weight_dgrad(w: torch.Tensor, cin_pad: int | None = None, cout_pad: int | None = None) -> torch.Tensor:
+    """[Cout,Cin,3,3] -> bf16 [Cin_pad,3,3,Cout_pad]: one row per INPUT channel (the dgrad GEMM's N dimension), the conv's
+    output channels along K (zero-padded to a multiple of 32, matching the zero-padded gradient tensor)."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    cin_pad = cin_pad or (Cin + 31) // 32 * 32
+    cout_pad = cout_pad or (Cout + 31) // 32 * 32
+    out = torch.zeros(cin_pad, 3, 3, cout_pad, device=w.device, dtype=torch.bfloat16)
+    out[:Cin, :, :, :Cout] = w.detach().permute(1, 2, 3, 0).to(torch.bfloat16)
+    return out
+
+
+def conv3x3_dgrad(g, wd, out_hw, stride=1, out=None, rows=None, accum=False, dact=0, ysave=None, residual=None):
+    """Data gradient on the tcgen05 kernel.  g: bf16 [B,Cg,Hg,Wg] channels_last (gradient w.r.t. the conv's pre-activation,
+    Cg = wd.shape[3]); wd from ``pack_weight_dgrad``; ``rows`` = (first, count) selects the input-channel range (one call per
+    concatenated source); result (or ``out``, optionally accumulated into) is bf16 [B,count,H,W] channels_last with the
+    fused epilogue  out = (out_old + dgrad + residual) * act'(ysave)."""
+    g = _nhwc(g)
+    B, Cg, Hg, Wg = g.shape
+    H, W = out_hw
+    assert wd.dtype == torch.bfloat16 and wd.is_contiguous() and wd.shape[3] == Cg, (wd.shape, Cg)
+    first, count = rows if rows is not None else (0, wd.shape[0])
+    assert first % 32 == 0 and count % 32 == 0 and first + count <= wd.shape[0]
+    wslice = wd[first:first + count]
+    if out is None:
+        assert not accum
+        out = torch.empty((B, count, H, W), device=g.device, dtype=torch.bfloat16, memory_format=CL)
+    else:
+        assert out.shape == (B, count, H, W) and out.dtype == torch.bfloat16 and out.is_contiguous(memory_format=CL)
+    if ysave is not None:
+        ysave = _nhwc(ysave)
+        assert ysave.shape == out.shape
+    if residual is not None:
+        residual = _nhwc(residual)
+        assert residual.shape == out.shape
+    assert (Hg, Wg) == ((H - 1) // stride + 1, (W - 1) // stride + 1)
+    rc = _lib.lib().faln_conv3x3_dgrad(_lib.ptr(g), _lib.ptr(wslice), _lib.ptr(out), _lib.ptr(residual), _lib.ptr(ysave),
+                                       B, H, W, Cg, count, count, stride, int(accum), int(dact if ysave is not None else 0),
+                                       count, count, count, _lib.cur_stream())
+    _lib.check(rc, "faln_conv3x3_dgrad")
+    return out
+
+
+def upsample_nearest_bwd(g_hi, lo_hw, ysave=None, dact=0, out=None, accum=False):
+    """Backward of ``upsample_nearest`` fused with act'(ysave): bf16 [B,C,Hh,Wh] -> [B,C,Hl,Wl] (channels_last)."""
+    g_hi = _nhwc(g_hi)
+    B, C, Hh, Wh = g_hi.shape
+    Hl, Wl = lo_hw
+    if out is None:
+        assert not accum
+        out = torch.empty((B, C, Hl, Wl), device=g_hi.device, dtype=torch.bfloat16, memory_format=CL)
+    if ysave is not None:
+        ysave = _nhwc(ysave)
+        assert ysave.shape == out.shape
+    rc = _lib.lib().faln_upsample_nearest_bwd_nhwc(_lib.ptr(g_hi), _lib.ptr(ysave), _lib.ptr(out), B, Hl, Wl, Hh, Wh, C,
+                                                   int(dact if ysave is not None else 0), int(accum), _lib.cur_stream())
+    _lib.check(rc, "faln_upsample_nearest_bwd_nhwc")
+    return out
+
+
+def maxpool2_bwd(x, g_y, dact=0):
+    x, g_y = _nhwc(x), _nhwc(g_y)
+    B, C, Hi, Wi = x.shape
+    assert g_y.shape == (B, C, Hi // 2, Wi // 2)
+    g_x = torch.empty_like(x)
+    rc = _lib.lib().faln_maxpool2_bwd_nhwc(_lib.ptr(x), _lib.ptr(g_y), _lib.ptr(g_x), B, Hi, Wi, C, int(dact), _lib.cur_stream())
+    _lib.check(rc, "faln_maxpool2_bwd_nhwc")
+    return g_x
+
+
+def channel_sum(g, out, C=None):
+    """out[:C] += per-channel sums of the bf16 channels_last gradient g (fp32 accumulate; ``out`` is fp32, typically a
+    bias-gradient view of the flat gradient arena)."""
+    g = _nhwc(g)
+    B, Cs, H, W = g.shape
+    C = C or Cs
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() >= C
+    rc = _lib.lib().faln_channel_sum_nhwc(_lib.ptr(g), _lib.ptr(out), B * H * W, C, Cs, _lib.cur_stream())
+    _lib.check(rc, "faln_channel_sum_nhwc")
+    return out

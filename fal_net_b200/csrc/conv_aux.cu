@@ -111,6 +111,145 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const uint4* __restrict__
   }
 }
 
+// Backward of the nearest upsampling, fused with the producer's activation derivative:
+//   g_lo[b,hl,wl,:] = act'(y_lo[b,hl,wl,:]) * ( [accum: g_lo_old] + sum over the hi-res pixels (h,w) whose nearest source is
+//   (hl,wl) of g_hi[b,h,w,:] ).   The pre-image of a source row is a contiguous run of destination rows; it is found by
+// testing the forward index rule itself on the few candidates, so forward and backward cannot disagree.
+__global__ void __launch_bounds__(256) upsample_nearest_bwd_kernel(const uint4* __restrict__ g_hi, const uint4* __restrict__ y_lo,
+                                                                   uint4* __restrict__ g_lo, int B, int Hl, int Wl, int Hh,
+                                                                   int Wh, int C8, float sh, float sw, int dact, int accum) {
+  const long long n = (long long)B * Hl * Wl * C8;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % C8);
+    long long r = i / C8;
+    const int wl = (int)(r % Wl);
+    r /= Wl;
+    const int hl = (int)(r % Hl);
+    const int b = (int)(r / Hl);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    if (accum) {
+      const uint4 u = g_lo[i];
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h2[e]);
+        acc[2 * e] = f.x;
+        acc[2 * e + 1] = f.y;
+      }
+    }
+    const int h_lo = max(0, (int)floorf((float)hl / sh) - 2), h_hi = min(Hh - 1, (int)ceilf((float)(hl + 1) / sh) + 2);
+    const int w_lo = max(0, (int)floorf((float)wl / sw) - 2), w_hi = min(Wh - 1, (int)ceilf((float)(wl + 1) / sw) + 2);
+    for (int h = h_lo; h <= h_hi; ++h) {
+      if (min((int)floorf(h * sh), Hl - 1) != hl) continue;
+      for (int w = w_lo; w <= w_hi; ++w) {
+        if (min((int)floorf(w * sw), Wl - 1) != wl) continue;
+        const uint4 u = __ldg(g_hi + (((long long)b * Hh + h) * Wh + w) * C8 + c);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(h2[e]);
+          acc[2 * e] += f.x;
+          acc[2 * e + 1] += f.y;
+        }
+      }
+    }
+    if (dact) {
+      const uint4 u = __ldg(y_lo + i);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h2[e]);
+        acc[2 * e] *= f.x > 0.f ? 1.f : (dact == 1 ? f.x + 1.f : 0.f);
+        acc[2 * e + 1] *= f.y > 0.f ? 1.f : (dact == 1 ? f.y + 1.f : 0.f);
+      }
+    }
+    uint4 o;
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+    g_lo[i] = o;
+  }
+}
+
+// Backward of the 2x2 max-pool fused with the ReLU derivative of the pooled-from activation x (VGG slices):
+//   g_x[b,h,w,:] = [x is the (first) maximum of its window] * [x > 0 if dact] * g_y[b,h/2,w/2,:];  odd trailing rows/cols get 0.
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ g_y,
+                                                           uint4* __restrict__ g_x, int B, int Hi, int Wi, int C8, int dact) {
+  const int Ho = Hi / 2, Wo = Wi / 2;
+  const long long n = (long long)B * Hi * Wi * C8;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % C8);
+    long long r = i / C8;
+    const int w = (int)(r % Wi);
+    r /= Wi;
+    const int h = (int)(r % Hi);
+    const int b = (int)(r / Hi);
+    uint4 o = make_uint4(0, 0, 0, 0);
+    const int ho = h >> 1, wo = w >> 1;
+    if (ho < Ho && wo < Wo) {
+      const uint4* p = x + (((long long)b * Hi + 2 * ho) * Wi + 2 * wo) * C8 + c;
+      const uint4 q[4] = {__ldg(p), __ldg(p + C8), __ldg(p + (long long)Wi * C8), __ldg(p + (long long)Wi * C8 + C8)};
+      const uint4 gy = __ldg(g_y + (((long long)b * Ho + ho) * Wo + wo) * C8 + c);
+      const int me = (h & 1) * 2 + (w & 1);
+      const __nv_bfloat16* gv = reinterpret_cast<const __nv_bfloat16*>(&gy);
+      __nv_bfloat16* ov = reinterpret_cast<__nv_bfloat16*>(&o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&q[k])[e]);
+        int arg = 0;  // first maximum in window scan order (matches ATen's max_pool2d_with_indices tie-breaking)
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+          if (v[k] > v[arg]) arg = k;
+        const bool on = arg == me && (!dact || v[me] > 0.f);
+        ov[e] = on ? gv[e] : __float2bfloat16(0.f);
+      }
+    }
+    g_x[i] = o;
+  }
+}
+
+// Per-channel sums of a bf16 NHWC gradient (bias gradients): out[c] += sum over pixels of g[pix, c], fp32.
+// Block = 256 threads = (256 / C8) pixel lanes x C8 channel groups of 8; shared-memory tree over the pixel lanes, then one
+// atomicAdd per channel per block.
+__global__ void __launch_bounds__(256) channel_sum_kernel(const uint4* __restrict__ g, float* __restrict__ out, long long npix,
+                                                          int C8, int Cstride8, int Cout) {
+  __shared__ float sm[256 * 8];
+  const int lanes = 256 / C8;                 // C8 in {4, 8, 16, 32, 64}: divides 256
+  const int cg = threadIdx.x % C8, pl = threadIdx.x / C8;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (long long px = (long long)blockIdx.x * lanes + pl; px < npix; px += (long long)gridDim.x * lanes) {
+    const uint4 u = __ldg(g + px * Cstride8 + cg);
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(h2[e]);
+      acc[2 * e] += f.x;
+      acc[2 * e + 1] += f.y;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sm[threadIdx.x * 8 + e] = acc[e];
+  __syncthreads();
+  for (int s = lanes / 2; s > 0; s >>= 1) {
+    if (pl < s) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sm[threadIdx.x * 8 + e] += sm[(threadIdx.x + s * C8) * 8 + e];
+    }
+    __syncthreads();
+  }
+  if (pl == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (cg * 8 + e < Cout) atomicAdd(out + cg * 8 + e, sm[threadIdx.x * 8 + e]);
+  }
+}
+
 inline int ew_grid(long long n, int threads) {
   long long g = (n + threads - 1) / threads;
   long long cap = (long long)sm_count() * 32;
@@ -153,4 +292,37 @@ extern "C" int faln_maxpool2_nhwc(const void* src, void* dst, int B, int Hi, int
   maxpool2_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), B,
                                                                   Hi, Wi, C / 8);
   return after_launch("maxpool2_kernel");
+}
+
+extern "C" int faln_upsample_nearest_bwd_nhwc(const void* g_hi, const void* y_lo, void* g_lo, int B, int Hl, int Wl, int Hh,
+                                              int Wh, int C, int dact, int accum, faln_stream_t stream) {
+  FALN_REQUIRE(g_hi && g_lo && B > 0 && Hl > 0 && Wl > 0 && Hh > 0 && Wh > 0 && C % 8 == 0,
+               "faln_upsample_nearest_bwd_nhwc: bad argument");
+  FALN_REQUIRE((dact == 0) || y_lo, "faln_upsample_nearest_bwd_nhwc: dact needs the saved activation");
+  const long long n = (long long)B * Hl * Wl * (C / 8);
+  upsample_nearest_bwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(
+      static_cast<const uint4*>(g_hi), static_cast<const uint4*>(y_lo), static_cast<uint4*>(g_lo), B, Hl, Wl, Hh, Wh, C / 8,
+      (float)Hl / (float)Hh, (float)Wl / (float)Wh, dact, accum);
+  return after_launch("upsample_nearest_bwd_kernel");
+}
+
+extern "C" int faln_maxpool2_bwd_nhwc(const void* x, const void* g_y, void* g_x, int B, int Hi, int Wi, int C, int dact,
+                                      faln_stream_t stream) {
+  FALN_REQUIRE(x && g_y && g_x && B > 0 && Hi >= 2 && Wi >= 2 && C % 8 == 0, "faln_maxpool2_bwd_nhwc: bad argument");
+  const long long n = (long long)B * Hi * Wi * (C / 8);
+  maxpool2_bwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(g_y),
+                                                                      static_cast<uint4*>(g_x), B, Hi, Wi, C / 8, dact);
+  return after_launch("maxpool2_bwd_kernel");
+}
+
+extern "C" int faln_channel_sum_nhwc(const void* g, float* out, long long npix, int C, int Cstride, faln_stream_t stream) {
+  FALN_REQUIRE(g && out && npix > 0 && C > 0 && Cstride % 8 == 0 && Cstride >= C, "faln_channel_sum_nhwc: bad argument");
+  const int C8 = Cstride / 8;   // all channel groups of the tensor are walked; channels >= C are dropped at the end
+  FALN_REQUIRE(C8 <= 64 && 256 % C8 == 0, "faln_channel_sum_nhwc: Cstride must be 8/16/32/64/128/256/512 (got %d)", Cstride);
+  const int lanes = 256 / C8;
+  long long grid = (npix + lanes - 1) / lanes;
+  const long long cap = (long long)sm_count() * 4;
+  if (grid > cap) grid = cap;
+  channel_sum_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(g), out, npix, C8, Cstride / 8, C);
+  return after_launch("channel_sum_kernel");
 }

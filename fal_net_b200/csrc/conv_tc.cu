@@ -29,12 +29,28 @@ namespace {
 
 constexpr int kTH = 8, kTW = 16;  // output tile: 8 x 16 pixels = 128 = UMMA_M
 
+// One "tap class": the filter taps that contribute to the output pixels (r * out_mul + oh, c * out_mul + ow).
+//   forward / stride-1 dgrad: one class with 9 taps; stride-2 dgrad: four parity classes with 1, 2, 2, 4 taps.
+// Tap t reads the input tile at offset (dh[t], dw[t]) and the weight columns of filter tap wt[t].
+struct TapClass {
+  int n;
+  signed char dh[9], dw[9], wt[9];
+  signed char oh, ow;
+};
+
 struct ConvParams {
-  int B, H, W, Ho, Wo;
-  int C1, C2, Cin, Cout;
-  int stride, act, planar;
+  int B, H, W, Ho, Wo;     // input dims (TMA coordinates), tile-grid dims (r, c)
+  int C1, C2, Cin, Cout;   // Cin = weight-row length per tap (elements)
+  int stride, act, planar; // stride = element stride of the input box
   int tiles_w, tiles_h;
   int kblocks1, kblocks2;  // BK-channel blocks of source 1 / source 2
+  int ncls;
+  TapClass cls[4];
+  int out_mul, out_H, out_W;  // output pixel = (r * out_mul + oh, c * out_mul + ow) inside an out_H x out_W image
+  int accum;                  // 1: add to what the output tensor already holds (gradient accumulation)
+  int dact;                   // 0 none, 1: multiply by ELU'(ysave), 2: multiply by ReLU'(ysave)  (backward epilogues)
+  const __nv_bfloat16* ysave; // saved activation output the derivative is taken at, NHWC with ysave_c channels
+  int ysave_c, res_c;
   const float* bias;
   const float* ctab;    // [16][Cout] border-class sums of the constant-channel weights, or NULL
   const float* cscale;  // [B] value of the constant channel per sample
@@ -127,7 +143,7 @@ struct SmemLayout {
 };
 
 template <int BK, int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
   using SL = SmemLayout<BK, BN, STAGES>;
@@ -144,7 +160,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
   const int n0 = blockIdx.y * BN;
   const int ho0 = th * kTH, wo0 = tw * kTW;
-  const int ksteps = 9 * (p.kblocks1 + p.kblocks2);
+  const TapClass& tc = p.cls[blockIdx.z];
+  const int ksteps = tc.n * (p.kblocks1 + p.kblocks2);
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA1);
@@ -169,9 +186,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tap = 0; tap < 9; ++tap) {
-        const int kh = tap / 3, kw = tap % 3;
-        const int hi = ho0 * p.stride + kh - 1, wi = wo0 * p.stride + kw - 1;
+      for (int t = 0; t < tc.n; ++t) {
+        const int tap = tc.wt[t];
+        const int hi = ho0 * p.stride + tc.dh[t], wi = wo0 * p.stride + tc.dw[t];
         for (int cb = 0; cb < p.kblocks1 + p.kblocks2; ++cb) {
           mbar_wait(&empty[s], ph ^ 1);
           unsigned char* a_dst = stages + (size_t)s * SL::kStage;
@@ -214,11 +231,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     // ================================================================= epilogue (warps 2..5)
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int m = quad * 32 + lane;       // row of the tile = pixel
-    const int ho = ho0 + m / kTW, wo = wo0 + m % kTW;
-    const bool valid = ho < p.Ho && wo < p.Wo;
+    const int ho = (ho0 + m / kTW) * p.out_mul + tc.oh, wo = (wo0 + m % kTW) * p.out_mul + tc.ow;
+    const bool valid = ho < p.out_H && wo < p.out_W;
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const size_t pix = ((size_t)b * p.Ho + ho) * p.Wo + wo;
+    const size_t pix = ((size_t)b * p.out_H + ho) * p.out_W + wo;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -244,8 +261,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         for (int j = 0; j < 32; ++j)
           if (cg + j < p.Cout) v[j] = fmaf(sc, __ldg(t + j), v[j]);
       }
+      if (p.accum) {
+        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.out) + pix * p.out_c + cg);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u = rp[q];
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 f = __bfloat1622float2(h2[e]);
+            v[q * 8 + 2 * e] += f.x;
+            v[q * 8 + 2 * e + 1] += f.y;
+          }
+        }
+      }
       if (p.residual) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.out_c + cg);
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.res_c + cg);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 u = __ldg(rp + q);
@@ -265,11 +296,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
+      if (p.dact) {
+        // backward epilogue: gradient w.r.t. the pre-activation = gradient * act'(pre), from the SAVED OUTPUT y:
+        // ELU'(pre) = 1 (y > 0) else y + 1;  ReLU'(pre) = [y > 0]
+        const uint4* yp = reinterpret_cast<const uint4*>(p.ysave + pix * p.ysave_c + cg);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u = __ldg(yp + q);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 f = __bfloat1622float2(h2[e]);
+            const float d0 = f.x > 0.f ? 1.f : (p.dact == 1 ? f.x + 1.f : 0.f);
+            const float d1 = f.y > 0.f ? 1.f : (p.dact == 1 ? f.y + 1.f : 0.f);
+            v[q * 8 + 2 * e] *= d0;
+            v[q * 8 + 2 * e + 1] *= d1;
+          }
+        }
+      }
       if (p.planar) {
         float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (cg + j < p.Cout) o[(((size_t)b * p.Cout + cg + j) * p.Ho + ho) * p.out_pitch + wo] = v[j];
+          if (cg + j < p.Cout) o[(((size_t)b * p.Cout + cg + j) * p.out_H + ho) * p.out_pitch + wo] = v[j];
       } else {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_c + cg;
 #pragma unroll
@@ -340,9 +389,30 @@ int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, c
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal);
     attr_set = true;
   }
-  dim3 grid(p.tiles_w * p.tiles_h * p.B, (p.Cout + BN - 1) / BN);
+  dim3 grid(p.tiles_w * p.tiles_h * p.B, (p.Cout + BN - 1) / BN, p.ncls);
   kern<<<grid, 192, SL::kTotal, st>>>(a1, a2, w, p);
   return after_launch("conv3x3_tc_kernel");
+}
+
+// Stage counts: a CTA owns ONE 128-pixel tile and runs only 9 * Cin / BK k-steps, so what hides latency is several CTAs
+// per SM (prologue, TMA latency and epilogue of different tiles overlapping), not a deep ring: 3-4 stages, sized so that
+// 2-5 CTAs fit in shared memory (and their accumulators in the 512 TMEM columns).
+int dispatch(int BK, int BN, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& wm, const ConvParams& p,
+             cudaStream_t st) {
+  if (BK == 64) {
+    switch (BN) {
+      case 256: return launch<64, 256, 4>(a1, a2, wm, p, st);
+      case 128: return launch<64, 128, 3>(a1, a2, wm, p, st);
+      case 64: return launch<64, 64, 3>(a1, a2, wm, p, st);
+      default: return launch<64, 32, 3>(a1, a2, wm, p, st);
+    }
+  }
+  switch (BN) {
+    case 256: return launch<32, 256, 4>(a1, a2, wm, p, st);
+    case 128: return launch<32, 128, 3>(a1, a2, wm, p, st);
+    case 64: return launch<32, 64, 4>(a1, a2, wm, p, st);
+    default: return launch<32, 32, 4>(a1, a2, wm, p, st);
+  }
 }
 
 }  // namespace
@@ -376,6 +446,16 @@ extern "C" int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, co
   p.kblocks1 = C1 / BK; p.kblocks2 = C2 / BK;
   p.bias = bias; p.ctab = ctab; p.cscale = cscale; p.residual = static_cast<const __nv_bfloat16*>(residual); p.out = y;
   p.out_pitch = out_pitch; p.out_c = out_c;
+  p.ncls = 1;
+  p.cls[0].n = 9;
+  for (int t = 0; t < 9; ++t) {
+    p.cls[0].dh[t] = (signed char)(t / 3 - 1);
+    p.cls[0].dw[t] = (signed char)(t % 3 - 1);
+    p.cls[0].wt[t] = (signed char)t;
+  }
+  p.cls[0].oh = p.cls[0].ow = 0;
+  p.out_mul = 1; p.out_H = p.Ho; p.out_W = p.Wo;
+  p.accum = 0; p.dact = 0; p.ysave = nullptr; p.ysave_c = 0; p.res_c = out_c;
   CUtensorMap a1, a2, wm;
   if (!make_act_map(&a1, x, B, H, W, C1, BK, stride) || !make_w_map(&wm, w, Cout_pad, 9 * (C1 + C2), BK, BN) ||
       (x2 && !make_act_map(&a2, x2, B, H, W, C2, BK, stride))) {
@@ -383,20 +463,69 @@ extern "C" int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, co
     return FALN_ERR_LAUNCH;
   }
   if (!x2) a2 = a1;
-  cudaStream_t st = as_stream(stream);
-  if (BK == 64) {
-    switch (BN) {
-      case 256: return launch<64, 256, 4>(a1, a2, wm, p, st);
-      case 128: return launch<64, 128, 6>(a1, a2, wm, p, st);
-      case 64: return launch<64, 64, 8>(a1, a2, wm, p, st);
-      default: return launch<64, 32, 8>(a1, a2, wm, p, st);
+  return dispatch(BK, BN, a1, a2, wm, p, as_stream(stream));
+}
+
+// Data gradient of the 3x3 convolution (pad 1, stride 1 or 2) on the same tcgen05 kernel:
+//   gx[b,h,w,ci] = sum_{kh,kw,co} g[b,(h+1-kh)/s,(w+1-kw)/s,co] * W[co,kh,kw,ci]      (terms with non-integer /s dropped)
+// g  [B,Hg,Wg,Cg] bf16 NHWC: gradient w.r.t. the conv's pre-activation output (Cg = padded Cout, multiple of 32)
+// wd [Cx_pad,3,3,Cg] bf16: the weights re-packed per INPUT channel (rows) -- for a concatenated input the caller passes
+//    the row range of one source and calls once per source
+// gx [B,H,W,gx_c] bf16 NHWC, channels [0,Cx) written (accum: added to); optional fused epilogue
+//    gx = (gx_old + dgrad + residual) * act'(ysave)   -- the chain rule through the producer's ELU / ReLU.
+// Stride 2 runs the four output-parity classes (1, 2, 2, 4 contributing taps) as blockIdx.z of one launch.
+extern "C" int faln_conv3x3_dgrad(const void* g, const void* wd, void* gx, const void* residual, const void* ysave, int B,
+                                  int H, int W, int Cg, int Cx, int Cx_pad, int stride, int accum, int dact, int gx_c,
+                                  int res_c, int ysave_c, faln_stream_t stream) {
+  FALN_REQUIRE(g && wd && gx && B > 0 && H > 0 && W > 0, "faln_conv3x3_dgrad: null pointer / bad shape");
+  FALN_REQUIRE(stride == 1 || stride == 2, "faln_conv3x3_dgrad: stride must be 1 or 2");
+  FALN_REQUIRE(Cg > 0 && Cg % 32 == 0, "faln_conv3x3_dgrad: Cg must be a multiple of 32 (got %d)", Cg);
+  FALN_REQUIRE(Cx > 0 && Cx % 32 == 0 && Cx_pad >= Cx && Cx_pad % 32 == 0 && gx_c >= Cx && gx_c % 8 == 0,
+               "faln_conv3x3_dgrad: Cx must be a multiple of 32 and fit the output tensor");
+  FALN_REQUIRE((dact == 0) == (ysave == nullptr), "faln_conv3x3_dgrad: dact and ysave go together");
+  const int Hg = (H - 1) / stride + 1, Wg = (W - 1) / stride + 1;
+  const int BK = (Cg % 64 == 0) ? 64 : 32;
+  const int BN = Cx_pad % 256 == 0 ? 256 : (Cx_pad % 128 == 0 ? 128 : (Cx_pad % 64 == 0 ? 64 : 32));
+  ConvParams p{};
+  p.B = B; p.H = Hg; p.W = Wg;
+  p.Ho = (H + stride - 1) / stride; p.Wo = (W + stride - 1) / stride;   // tile grid over one parity class
+  p.C1 = Cg; p.C2 = 0; p.Cin = Cg; p.Cout = Cx;
+  p.stride = 1; p.act = 0; p.planar = 0;
+  p.tiles_w = (p.Wo + kTW - 1) / kTW; p.tiles_h = (p.Ho + kTH - 1) / kTH;
+  p.kblocks1 = Cg / BK; p.kblocks2 = 0;
+  p.bias = nullptr; p.ctab = nullptr; p.cscale = nullptr;
+  p.residual = static_cast<const __nv_bfloat16*>(residual); p.out = gx; p.out_pitch = 0; p.out_c = gx_c;
+  p.out_mul = stride; p.out_H = H; p.out_W = W;
+  p.accum = accum; p.dact = dact; p.ysave = static_cast<const __nv_bfloat16*>(ysave); p.ysave_c = ysave_c; p.res_c = res_c;
+  if (stride == 1) {
+    p.ncls = 1;
+    p.cls[0].n = 9;
+    for (int t = 0; t < 9; ++t) {
+      p.cls[0].dh[t] = (signed char)(1 - t / 3);
+      p.cls[0].dw[t] = (signed char)(1 - t % 3);
+      p.cls[0].wt[t] = (signed char)t;
     }
+    p.cls[0].oh = p.cls[0].ow = 0;
   } else {
-    switch (BN) {
-      case 256: return launch<32, 256, 6>(a1, a2, wm, p, st);
-      case 128: return launch<32, 128, 8>(a1, a2, wm, p, st);
-      case 64: return launch<32, 64, 8>(a1, a2, wm, p, st);
-      default: return launch<32, 32, 8>(a1, a2, wm, p, st);
-    }
+    p.ncls = 4;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        TapClass& c = p.cls[ph * 2 + pw];
+        c.n = 0; c.oh = (signed char)ph; c.ow = (signed char)pw;
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw) {
+            if (((ph + 1 - kh) & 1) || ((pw + 1 - kw) & 1)) continue;
+            c.dh[c.n] = (signed char)((ph + 1 - kh) / 2);
+            c.dw[c.n] = (signed char)((pw + 1 - kw) / 2);
+            c.wt[c.n] = (signed char)(kh * 3 + kw);
+            ++c.n;
+          }
+      }
   }
+  CUtensorMap a1, wm;
+  if (!make_act_map(&a1, g, B, Hg, Wg, Cg, BK, 1) || !make_w_map(&wm, wd, Cx_pad, 9 * Cg, BK, BN)) {
+    set_error("faln_conv3x3_dgrad: cuTensorMapEncodeTiled failed (driver entry point missing or bad tensor geometry)");
+    return FALN_ERR_LAUNCH;
+  }
+  return dispatch(BK, BN, a1, a1, wm, p, as_stream(stream));
 }

@@ -20,7 +20,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .. import conv as C
+from .. import backbone
 from .. import med
 
 __all__ = ["FAL_netB"]
@@ -116,37 +116,9 @@ class FAL_net(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def logits(self, input_left, max_disp):
-        """dlog0 [B,N,H,W] fp32, planar with a 16-byte-multiple row pitch (what the MED kernels stream)."""
-        if not input_left.is_cuda:
-            raise RuntimeError("fal_net_b200.FAL_netB runs on CUDA (sm_100a) only; there is no CPU path")
-        bb = self.backbone
-        B, _, H, W = input_left.shape
-        flow_val = (max_disp.reshape(B).float() / 100.0)                       # :208-209, constant plane per sample
-        skips = []
-        h = None
-        for i, (name, _, _, stride) in enumerate(_ENC):
-            head = getattr(bb, name)[0]
-            if i == 0:
-                h = C.stem(input_left, head.weight, head.bias, "elu")          # reads the fp32 NCHW image directly
-            else:
-                h = C.conv3x3(h, head.weight, head.bias, stride=stride, act="elu",
-                              const_channel=flow_val if i == 1 else None)
-            blk = getattr(bb, name + "_1")
-            r = C.conv3x3(h, blk.conv1.weight, None, act="elu")
-            h = C.conv3x3(r, blk.conv2.weight, None, act="elu", residual=h)     # elu(conv2(elu(conv1(x))) + x), :79
-            skips.append(h)
-        h = skips[6]
-        for lvl, _, _, _, iout in _DEC:
-            skip = skips[lvl - 1]
-            up = getattr(bb, f"deconv{lvl}")
-            u = C.conv3x3(h, up.conv1.weight, None, act="elu", upsample_to=(skip.shape[2], skip.shape[3]))   # :58-59
-            if iout is not None:
-                ic = getattr(bb, f"iconv{lvl}")[0]
-                h = C.conv3x3(u, ic.weight, ic.bias, act="elu", concat=skip)
-            else:
-                # iconv1 (:127,174) followed by the 1x1 logit conv (:190,215), folded into one 3x3 conv
-                return C.conv3x3_logits(u, skip, bb.iconv1.weight, self.conv0.weight, self.conv0.bias)
-        raise AssertionError("unreachable")
+        """dlog0 [B,N,H,W] fp32, planar with a 16-byte-multiple row pitch (what the MED kernels stream).  The whole
+        encoder-decoder is one autograd node with a hand-scheduled backward (fal_net_b200.backbone)."""
+        return backbone.logits(self, input_left, max_disp)
 
     def forward(self, input_left, min_disp, max_disp, ret_disp=True, ret_subocc=False, ret_pan=False):
         dlog0 = self.logits(input_left, max_disp)

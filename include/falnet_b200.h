@@ -183,6 +183,23 @@ int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, const float* 
                      const float* cscale, const void* residual, void* y, int B, int H, int W, int C1, int C2, int Cout, int Cout_pad, int stride, int act,
                      int planar, long long out_pitch, int out_c, faln_stream_t stream);
 
+/* Data gradient of the same convolution on the same tcgen05 kernel (replaces cuDNN dgrad behind autograd of
+ * /root/reference/models/FAL_netB.py:35-80): g [B,Hg,Wg,Cg] bf16 NHWC (gradient w.r.t. the conv's pre-activation output),
+ * wd [Cx_pad,3,3,Cg] bf16 (weights re-packed per input channel; one call per concatenated source), gx [B,H,W,gx_c] bf16.
+ * Fused epilogue: gx[..., :Cx] = ([accum] gx_old + dgrad + [residual]) * act'(ysave), dact 0 none / 1 ELU / 2 ReLU.
+ * stride 2 = four output-parity classes in one launch. */
+int faln_conv3x3_dgrad(const void* g, const void* wd, void* gx, const void* residual, const void* ysave, int B, int H,
+                       int W, int Cg, int Cx, int Cx_pad, int stride, int accum, int dact, int gx_c, int res_c,
+                       int ysave_c, faln_stream_t stream);
+/* Backward of F.interpolate(mode='nearest') (reference :58) fused with the producer's activation derivative. */
+int faln_upsample_nearest_bwd_nhwc(const void* g_hi, const void* y_lo, void* g_lo, int B, int Hl, int Wl, int Hh, int Wh,
+                                   int C, int dact, int accum, faln_stream_t stream);
+/* Backward of the VGG 2x2 max-pool (/root/reference/loss_functions.py:21-29) fused with the ReLU derivative. */
+int faln_maxpool2_bwd_nhwc(const void* x, const void* g_y, void* g_x, int B, int Hi, int Wi, int C, int dact,
+                           faln_stream_t stream);
+/* Bias gradient: out[c] += sum over pixels of g[pix, c] (bf16 NHWC with Cstride channels per pixel, fp32 accumulate). */
+int faln_channel_sum_nhwc(const void* g, float* out, long long npix, int C, int Cstride, faln_stream_t stream);
+
 /* Stem convolution for 3-channel fp32 NCHW input (conv0.0 of :99 and VGG conv1_1): reads the image directly
  * (flip_x: x-reversed), w [Cout,3,3,3] fp32 (torch OIHW), Cout 32 or 64, writes bf16 NHWC [B,H,W,Cout]. */
 int faln_stem_conv(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int Cout,

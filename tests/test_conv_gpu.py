@@ -104,3 +104,85 @@ def test_stem_upsample_pool_and_const_channel():
         plane = cval.view(2, 1, 1, 1).expand(2, 1, H, W).to(torch.bfloat16)
         ref = _ref(torch.cat((h, plane), 1), w, b, 2, 1, None)
         assert rel_err(y.float(), ref) < 8e-3
+
+
+def _elu_grad_from_y(y):
+    return torch.where(y > 0, torch.ones_like(y), y + 1)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride,dact,accum,res", [
+    (2, 24, 40, 64, 64, 1, 1, False, False),
+    (2, 47, 156, 32, 32, 1, 1, False, True),       # residual pass-through + ELU' (res block)
+    (1, 19, 33, 128, 128, 1, 2, False, False),     # ReLU' (VGG)
+    (2, 24, 80, 128, 256, 2, 1, True, False),      # stride 2, even sizes, accumulate into an existing gradient
+    (2, 25, 81, 64, 128, 2, 1, False, False),      # stride 2, odd sizes
+    (2, 47, 155, 256, 256, 2, 0, False, False),    # stride 2, mixed parity, no activation
+    (3, 3, 10, 512, 512, 1, 1, False, False),
+    (2, 21, 70, 96, 49, 1, 0, False, False),       # logits conv: Cout 49 padded to 64 on K
+])
+def test_conv3x3_dgrad(B, H, W, Cin, Cout, stride, dact, accum, res):
+    from fal_net_b200 import conv_native as CN
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(H * 1000 + W + Cin + Cout)
+    CL = torch.channels_last
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    Cg = (Cout + 31) // 32 * 32
+    w = (torch.randn(Cout, Cin, 3, 3, generator=gen) * (2.0 / (9 * Cout)) ** 0.5).bfloat16().to(dev)
+    g = torch.zeros(B, Cg, Ho, Wo)
+    g[:, :Cout] = torch.randn(B, Cout, Ho, Wo, generator=gen)
+    g = g.bfloat16().to(dev).contiguous(memory_format=CL)
+    ysave = torch.randn(B, Cin, H, W, generator=gen).bfloat16().to(dev).contiguous(memory_format=CL) if dact else None
+    old = torch.randn(B, Cin, H, W, generator=gen).bfloat16().to(dev).contiguous(memory_format=CL) if accum else None
+    r = torch.randn(B, Cin, H, W, generator=gen).bfloat16().to(dev).contiguous(memory_format=CL) if res else None
+    ref = torch.nn.grad.conv2d_input((B, Cin, H, W), w.float(), g[:, :Cout].float(), stride, 1)
+    if old is not None:
+        ref = ref + old.float()
+    if r is not None:
+        ref = ref + r.float()
+    if dact == 1:
+        ref = ref * _elu_grad_from_y(ysave.float())
+    elif dact == 2:
+        ref = ref * (ysave.float() > 0)
+    out = old.clone(memory_format=CL) if old is not None else None
+    wd = CN.pack_weight_dgrad(w)
+    if Cin % 64 == 0 and not accum and not res and out is None:
+        # two row ranges written into two tensors = the concat split
+        h = Cin // 2
+        a = CN.conv3x3_dgrad(g, wd, (H, W), stride, rows=(0, h), dact=dact, ysave=None if ysave is None else ysave[:, :h])
+        b = CN.conv3x3_dgrad(g, wd, (H, W), stride, rows=(h, h), dact=dact, ysave=None if ysave is None else ysave[:, h:])
+        got = torch.cat((a, b), 1)
+    else:
+        got = CN.conv3x3_dgrad(g, wd, (H, W), stride, out=out, accum=accum, dact=dact, ysave=ysave, residual=r)
+    torch.cuda.synchronize()
+    e = rel_err(got.float(), ref)
+    assert e < 8e-3, e
+
+
+def test_upsample_pool_backward_and_channel_sum():
+    from fal_net_b200 import conv_native as CN
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(11)
+    CL = torch.channels_last
+    for (Hl, Wl), (Hh, Wh) in (((24, 78), (47, 156)), ((3, 10), (6, 20)), ((188, 621), (375, 1242)), ((12, 40), (12, 40))):
+        C = 64 if Hh < 300 else 8
+        x = torch.randn(2, C, Hl, Wl, generator=gen).bfloat16().to(dev).contiguous(memory_format=CL)
+        gh = torch.randn(2, C, Hh, Wh, generator=gen).bfloat16().to(dev).contiguous(memory_format=CL)
+        xr = x.float().requires_grad_(True)
+        F.interpolate(xr, size=(Hh, Wh), mode="nearest").backward(gh.float())
+        ref = xr.grad * _elu_grad_from_y(x.float())
+        got = CN.upsample_nearest_bwd(gh, (Hl, Wl), ysave=x, dact=1)
+        assert rel_err(got.float(), ref) < 8e-3
+    # max-pool backward with ReLU' (distinct values: no ties)
+    x = torch.randn(2, 64, 23, 78, generator=gen).bfloat16().to(dev).contiguous(memory_format=CL)
+    gy = torch.randn(2, 64, 11, 39, generator=gen).bfloat16().to(dev).contiguous(memory_format=CL)
+    xr = x.float().requires_grad_(True)
+    F.max_pool2d(xr, 2, 2).backward(gy.float())
+    ref = xr.grad * (x.float() > 0)
+    assert rel_err(CN.maxpool2_bwd(x, gy, dact=2).float(), ref) < 1e-6
+    # channel sums (bias gradient), accumulating
+    for C, Cs in ((64, 64), (49, 64), (256, 256), (32, 32), (512, 512)):
+        g = torch.randn(2, Cs, 30, 50, generator=gen).bfloat16().to(dev).contiguous(memory_format=CL)
+        out = torch.ones(C, device=dev)
+        CN.channel_sum(g, out, C)
+        ref = 1 + g.float().sum((0, 2, 3))[:C]
+        assert rel_err(out, ref) < 1e-4
