@@ -11,8 +11,9 @@ Backward = the exact adjoint of that graph, written out by hand instead of being
     skip tensor, the split of a concatenated input into its two sources (two row ranges of the packed weights);
   * the nearest-upsample backward is one kernel fused with the producer's ELU';
   * bias gradients are one channel-sum kernel each;
-  * weight gradients: ``faln_conv3x3_wgrad`` (tcgen05, split-K over pixels) when available, else cuDNN's wgrad
-    (``LIBRARY_CALLS['conv_wgrad']`` counts those for bench.py).
+  * weight gradients: ``faln_conv3x3_wgrad`` (tcgen05 with MN-major operands, split-K over pixels) reduces straight
+    into the fp32 gradient arena of the optimiser -- no cuDNN, no cast / add / cat launches around it
+    (``LIBRARY_CALLS['conv_wgrad']`` stays 0; bench.py reports it).
 
 Compared with per-layer autograd.Functions this removes ~700 ATen elementwise / cat / copy / reduce launches per step
 (see profiles/): nothing is concatenated, no gradient is materialised twice, and the schedule is static -- which is what
@@ -118,27 +119,46 @@ def forward(model, image, max_disp, tape=None):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def _wgrad(g_pre, xin, cout, stride=1):
-    """Weight gradient [cout, C(xin), 3, 3] fp32 of a 3x3 conv from the pre-activation gradient and the input."""
-    LIBRARY_CALLS["conv_wgrad"] += 1
-    Cg, C = g_pre.shape[1], xin.shape[1]
-    wshape = torch.empty((Cg, C, 3, 3), device=g_pre.device, dtype=torch.bfloat16).contiguous(memory_format=CL)
-    _, gw, _ = torch.ops.aten.convolution_backward(g_pre, xin, wshape, None, [stride, stride], [1, 1], [1, 1], False,
-                                                   [0, 0], 1, [False, True, False])
-    return gw[:cout].float()
+class _DictSink:
+    """Gradient destination when no flat arena is attached: fresh zeroed fp32 tensors, returned to autograd."""
+
+    def __init__(self, model, device):
+        self.shapes = {n: p.shape for n, p in model.named_parameters()}
+        self.device = device
+        self.grads = {}
+
+    def grad_view(self, name):
+        if name not in self.grads:
+            self.grads[name] = torch.zeros(self.shapes[name], device=self.device, dtype=torch.float32)
+        return self.grads[name]
+
+    def mark_ready(self, name):
+        pass
 
 
-def backward(model, tape, g_logits):
-    """Returns {parameter name: fp32 gradient} for every used parameter of the model."""
+def backward(model, tape, g_logits, sink=None):
+    """Hand-scheduled backward.  Parameter gradients are ACCUMULATED into ``sink.grad_view(name)`` (fp32, the flat gradient
+    arena of trainer.FlatAdamDDP when one is attached to the model -- then ``sink.mark_ready(name)`` releases all-reduce
+    buckets as soon as they are complete); returns the sink."""
     bb = model.backbone
-    grads = {}
     N = model.no_levels
     B, _, H, W = g_logits.shape
     dev = g_logits.device
+    sink = sink or _DictSink(model, dev)
 
-    def bias_grad(g, C):
-        out = torch.zeros(C, device=dev, dtype=torch.float32)
-        return CN.channel_sum(g, out, C)
+    def bias_grad(name, g, C):
+        CN.channel_sum(g, sink.grad_view(name), C)
+        sink.mark_ready(name)
+
+    def wgrad(name, g_pre, sources, cout, stride=1):
+        """sources: the conv's (concatenated) inputs, in channel order."""
+        dW = sink.grad_view(name)
+        off = 0
+        for x in sources:
+            cx = min(x.shape[1], dW.shape[1] - off)
+            CN.conv3x3_wgrad(g_pre, x, dW, cout=cout, cx=cx, ci_off=off, stride=stride)
+            off += cx
+        return dW
 
     # ---------------------------------------------------------------- folded logits conv (iconv1 o conv0)
     Np = (N + 31) // 32 * 32
@@ -146,12 +166,16 @@ def backward(model, tape, g_logits):
     h2, xu, u, _ = tape["dec1"]
     s0 = tape["conv0"][2]
     wf = tape["wf"]
-    grads["conv0.bias"] = bias_grad(g, N)
-    gwf = torch.cat((_wgrad(g, u, N), _wgrad(g, s0, N)), 1)                      # [N,96,3,3]
+    bias_grad("conv0.bias", g, N)
+    gwf = torch.zeros(N, u.shape[1] + s0.shape[1], 3, 3, device=dev, dtype=torch.float32)   # gradient of the folded weight
+    CN.conv3x3_wgrad(g, u, gwf, cout=N, ci_off=0)
+    CN.conv3x3_wgrad(g, s0, gwf, cout=N, ci_off=u.shape[1])
     w0 = model.conv0.weight.detach()[:, :, 0, 0]
     wi1 = bb.iconv1.weight.detach()
-    grads["conv0.weight"] = torch.einsum("ockl,mckl->om", gwf, wi1)[:, :, None, None]
-    grads["backbone.iconv1.weight"] = torch.einsum("om,ockl->mckl", w0, gwf)
+    sink.grad_view("conv0.weight").add_(torch.einsum("ockl,mckl->om", gwf, wi1)[:, :, None, None])
+    sink.mark_ready("conv0.weight")
+    sink.grad_view("backbone.iconv1.weight").add_(torch.einsum("om,ockl->mckl", w0, gwf))
+    sink.mark_ready("backbone.iconv1.weight")
     wd = CN.pack_weight_dgrad(wf)                                                # [96,3,3,Np]
     C1 = u.shape[1]
     g_u = CN.conv3x3_dgrad(g, wd, (H, W), rows=(0, C1), dact=1, ysave=u)
@@ -167,14 +191,16 @@ def backward(model, tape, g_logits):
         if lvl > 1:
             ic = getattr(bb, f"iconv{lvl}")[0]
             cout = ic.weight.shape[0]
-            grads[f"backbone.iconv{lvl}.0.bias"] = bias_grad(g_h, cout)
-            grads[f"backbone.iconv{lvl}.0.weight"] = torch.cat((_wgrad(g_h, u, cout), _wgrad(g_h, skip, cout)), 1)
+            bias_grad(f"backbone.iconv{lvl}.0.bias", g_h, cout)
+            wgrad(f"backbone.iconv{lvl}.0.weight", g_h, (u, skip), cout)
+            sink.mark_ready(f"backbone.iconv{lvl}.0.weight")
             wd = _wd(ic.weight)
             C1 = u.shape[1]
             hw = (u.shape[2], u.shape[3])
             g_u = CN.conv3x3_dgrad(g_h, wd, hw, rows=(0, C1), dact=1, ysave=u)
             G_skip[lvl - 1] = CN.conv3x3_dgrad(g_h, wd, hw, rows=(C1, skip.shape[1]))
-        grads[f"backbone.deconv{lvl}.conv1.weight"] = _wgrad(g_u, xu, up.conv1.weight.shape[0])
+        wgrad(f"backbone.deconv{lvl}.conv1.weight", g_u, (xu,), up.conv1.weight.shape[0])
+        sink.mark_ready(f"backbone.deconv{lvl}.conv1.weight")
         g_xu = CN.conv3x3_dgrad(g_u, _wd(up.conv1.weight), (xu.shape[2], xu.shape[3]))
         # nearest-upsample backward fused with ELU' of the producer (h_{l+1}, or the bottleneck skip s6 for level 6)
         g_h = CN.upsample_nearest_bwd(g_xu, (h_in.shape[2], h_in.shape[3]), ysave=h_in, dact=1)
@@ -188,29 +214,31 @@ def backward(model, tape, g_logits):
         head = getattr(bb, name)[0]
         blk = getattr(bb, name + "_1")
         hw = (a.shape[2], a.shape[3])
-        grads[f"backbone.{name}_1.conv2.weight"] = _wgrad(g_s, r, cout)
+        wgrad(f"backbone.{name}_1.conv2.weight", g_s, (r,), cout)
+        sink.mark_ready(f"backbone.{name}_1.conv2.weight")
         g_r = CN.conv3x3_dgrad(g_s, _wd(blk.conv2.weight), hw, dact=1, ysave=r)
-        grads[f"backbone.{name}_1.conv1.weight"] = _wgrad(g_r, a, cout)
+        wgrad(f"backbone.{name}_1.conv1.weight", g_r, (a,), cout)
+        sink.mark_ready(f"backbone.{name}_1.conv1.weight")
         g_a = CN.conv3x3_dgrad(g_r, _wd(blk.conv1.weight), hw, dact=1, ysave=a, residual=g_s)   # (dgrad + skip path) * ELU'
-        grads[f"backbone.{name}.0.bias"] = bias_grad(g_a, cout)
+        bias_grad(f"backbone.{name}.0.bias", g_a, cout)
+        wname = f"backbone.{name}.0.weight"
         if i == 0:
-            img16 = tape["image"].to(dtype=torch.bfloat16, memory_format=CL)
-            grads["backbone.conv0.0.weight"] = _wgrad(g_a, img16, cout)
+            # the 3-channel image as a 32-channel (zero-padded) bf16 NHWC tensor: same tensor-core path, cx = 3
+            img16 = layout.planar_to_nhwc_bf16(tape["image"].float().contiguous(), 32).permute(0, 3, 1, 2)
+            wgrad(wname, g_a, (img16,), cout)
+            sink.mark_ready(wname)
             break
         prev = tape[ENC[i - 1][0]][2]
         Cp = prev.shape[1]
+        dW = wgrad(wname, g_a, (prev,), cout, stride)
         if i == 1:                                                                # the constant max_disp/100 input plane
-            Bq, _, Hp, Wp = prev.shape
-            plane = tape["flow_val"].to(torch.bfloat16).view(Bq, 1, 1, 1).expand(Bq, 1, Hp, Wp)
-            xin = torch.cat((prev, plane), 1).contiguous(memory_format=CL)
-        else:
-            xin = prev
-        grads[f"backbone.{name}.0.weight"] = _wgrad(g_a, xin, cout, stride)
+            dW[:, Cp].add_(CN.const_channel_wgrad(g_a, tape["flow_val"], (prev.shape[2], prev.shape[3]), stride, cout))
+        sink.mark_ready(wname)
         # stride-2 dgrad into the previous skip: add to what the decoder left there, then ELU'(s_{i-1})
         g_s = CN.conv3x3_dgrad(g_a, _wd(head.weight, Cp), (prev.shape[2], prev.shape[3]), stride=stride,
                                out=G_skip.pop(i - 1), accum=True, dact=1, ysave=prev)
         del g_r, g_a
-    return grads
+    return sink
 
 
 class BackboneFn(torch.autograd.Function):
@@ -221,6 +249,7 @@ class BackboneFn(torch.autograd.Function):
         tape = {}
         out = forward(model, image, max_disp, tape)
         ctx.model, ctx.names, ctx.tape = model, names, tape
+        ctx.sink = getattr(model, "_faln_grad_sink", None)
         return out
 
     @staticmethod
@@ -232,8 +261,11 @@ class BackboneFn(torch.autograd.Function):
             g = layout.alloc_planar(Bq, Nq, Hq, Wq, g_logits.device)
             g.copy_(g_logits)
             g_logits = g
-        grads = backward(ctx.model, tape, g_logits)
-        return (None, None, None, None) + tuple(grads.get(n) for n in ctx.names)
+        sink = ctx.sink if (ctx.sink is not None and ctx.sink.accepts(ctx.model)) else None
+        out = backward(ctx.model, tape, g_logits, sink)
+        if sink is not None:                       # gradients already sit in the flat arena the parameters' .grad alias
+            return (None, None, None, None) + (None,) * len(ctx.names)
+        return (None, None, None, None) + tuple(out.grads.get(n) for n in ctx.names)
 
 
 def logits(model, image, max_disp):

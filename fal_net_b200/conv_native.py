@@ -200,3 +200,63 @@ def channel_sum(g, out, C=None):
     rc = _lib.lib().faln_channel_sum_nhwc(_lib.ptr(g), _lib.ptr(out), B * H * W, C, Cs, _lib.cur_stream())
     _lib.check(rc, "faln_channel_sum_nhwc")
     return out
+
+
+def conv3x3_wgrad(g, x, dW, cout=None, cx=None, ci_off=0, stride=1):
+    """dW[:cout, ci_off:ci_off+cx] += weight gradient of a 3x3 conv (pad 1) on the tcgen05 kernel (csrc/conv_wgrad.cu).
+    g: bf16 [B,Cg,Hg,Wg] channels_last (pre-activation gradient), x: bf16 [B,Cxs,H,W] channels_last (the conv's input, or
+    one source of a concatenated input), dW: fp32 contiguous [Cout,Cin_tot,3,3] (typically a view of the flat gradient
+    arena), accumulated in place with split-K fp32 reductions."""
+    g, x = _nhwc(g), _nhwc(x)
+    B, Cg, Hg, Wg = g.shape
+    _, Cxs, H, W = x.shape
+    assert x.shape[0] == B and (Hg, Wg) == ((H - 1) // stride + 1, (W - 1) // stride + 1), (g.shape, x.shape, stride)
+    assert dW.dtype == torch.float32 and dW.is_contiguous() and dW.dim() == 4 and dW.shape[2:] == (3, 3)
+    cout = cout or dW.shape[0]
+    cx = cx or min(Cxs, dW.shape[1] - ci_off)
+    assert cout <= dW.shape[0] and ci_off + cx <= dW.shape[1]
+    rc = _lib.lib().faln_conv3x3_wgrad(_lib.ptr(g), _lib.ptr(x), _lib.ptr(dW), B, H, W, Cg, Cxs, cout, cx, ci_off,
+                                       dW.shape[1], stride, _lib.cur_stream())
+    _lib.check(rc, "faln_conv3x3_wgrad")
+    return dW
+
+
+def border_sums(g, C=None):
+    """[B,3,3,C] fp32 sums of the bf16 channels_last map g over the 3x3 border classes (first / interior / last row x col)."""
+    g = _nhwc(g)
+    B, Cs, H, W = g.shape
+    C = C or Cs
+    out = torch.zeros(B, 3, 3, C, device=g.device, dtype=torch.float32)
+    rc = _lib.lib().faln_border_sum_nhwc(_lib.ptr(g), _lib.ptr(out), B, H, W, C, Cs, _lib.cur_stream())
+    _lib.check(rc, "faln_border_sum_nhwc")
+    return out
+
+
+_TAP_VALID: dict = {}
+
+
+def _tap_validity(device, last_clipped: bool) -> torch.Tensor:
+    """[3 taps, 3 border classes] 0/1: tap 0 of the first row/col reads index -1; tap 2 of the last row/col reads index
+    n_in when ``last_clipped``.  Cached on the device (no host-to-device copy inside a CUDA-graph capture)."""
+    key = (str(device), bool(last_clipped))
+    m = _TAP_VALID.get(key)
+    if m is None:
+        m = torch.ones(3, 3, device=device)        # built with device-side fills only: legal inside a graph capture
+        m[0, 0].fill_(0.0)
+        if last_clipped:
+            m[2, 2].fill_(0.0)
+        _TAP_VALID[key] = m
+    return m
+
+
+def const_channel_wgrad(g, value, in_hw, stride, cout):
+    """Weight gradient [cout,3,3] of a spatially constant input channel with per-sample value ``value`` [B]: for each tap
+    the sum of g over the output pixels whose tap lands inside the image -- a combination of the nine border-class sums."""
+    B, Cs, Hg, Wg = g.shape
+    H, W = in_hw
+    S = border_sums(g, cout)                                               # [B,3,3,C]
+    S = torch.einsum("b,brcn->rcn", value.float(), S)                      # [3(row class),3(col class),C]
+
+    vh = _tap_validity(g.device, stride * (Hg - 1) + 1 > H - 1)
+    vw = _tap_validity(g.device, stride * (Wg - 1) + 1 > W - 1)
+    return torch.einsum("hr,wc,rcn->nhw", vh, vw, S)

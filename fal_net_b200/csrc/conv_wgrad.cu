@@ -1,0 +1,280 @@
+// conv_wgrad.cu -- weight gradient of the 3x3 convolutions as a tcgen05 / TMEM GEMM over pixels, sm_100a.
+//
+// Replaces the cuDNN wgrad calls autograd issues for nn.Conv2d in /root/reference/models/FAL_netB.py:99-127 (backward of
+// :144-174) and the ~3 ATen cast / add / cat launches around each of them.
+//
+//   dW[co, ci, kh, kw] = sum over (b, ho, wo) of  g[b, ho, wo, co] * x[b, ho*s + kh - 1, wo*s + kw - 1, ci]
+//
+// GEMM view (per filter tap): D[ci, co] = X_tap^T[ci, pixel] * G[pixel, co] -- the reduction dimension K is the PIXEL
+// axis.  Both tensors are NHWC bf16, i.e. the channel (M resp. N) index is the contiguous one: both operands are
+// "MN-major" for tcgen05.mma, which the instruction descriptor supports for 16-bit types (a_major = b_major = 1).
+//
+//   * a CTA owns one filter row kh (3 taps), one block of CB input channels, one block of NB output channels and a
+//     strided subset of the 64-pixel chunks (4 rows x 16 columns of the gradient map) -- split-K over pixels
+//   * per chunk the TMA unit fetches, with the SAME tensor maps geometry the forward uses for its A operand,
+//       g : NB/GC boxes  [GC channels, 16, 4]            (GC = 64, 128B swizzle; 32 -> 64B swizzle)
+//       x : 3 * CB/XC boxes [XC channels, 16*s, 4*s] at the tap's offset, element stride s, out-of-image = 0 = padding
+//     a box lands as 64 pixel rows of 128 (64) bytes = the canonical MN-major swizzled atom sequence: 8 pixel rows x one
+//     swizzle row per atom, atoms 1024 (512) bytes apart along K (descriptor SBO), boxes one after the other along
+//     M / N (descriptor LBO = box bytes)
+//   * the M = 128 rows of one tcgen05.mma are TWO (four) consecutive x boxes -- two taps, or two channel sub-blocks of one
+//     tap -- so small channel counts still fill the instruction; each instruction row owns NB TMEM columns
+//   * the epilogue warps read the accumulators with tcgen05.ld and reduce them into the fp32 gradient tensor
+//     [Cout, Cin_total, 3, 3] (the flat gradient arena the fused Adam reads) with red.global.add.f32: no workspace, no
+//     separate reduction kernel, gradients of a concatenated input are two calls with different column offsets.
+#include "tc_common.cuh"
+
+namespace faln {
+namespace {
+
+constexpr int kCR = 4;            // gradient-map rows per chunk
+constexpr int kP = kCR * kTW;     // 64 pixels per chunk = 4 UMMA K-steps
+
+struct WgradParams {
+  int B, Hg, Wg;            // gradient map
+  int stride;
+  int tiles_w, tiles_h, chunks;
+  int n_cib, n_cob;         // channel blocks
+  int CB, NB;               // channels per block
+  int nb;                   // x boxes per tap (CB / XC)
+  int slots, slots_pad;     // 3 * nb, rounded up to whole instruction rows
+  int irows;                // instruction rows = slots_pad / (128 / XC)
+  int Cx, Cout;             // real channel counts (bounds of what is written)
+  int ci_off, Cin_tot;      // column offset / row length of dW
+  int stages;
+  float* dW;
+};
+
+// MN-major swizzled shared-memory matrix descriptor: start >> 4, LBO >> 4 at [16,30) (distance between the 64- / 32-channel
+// atoms along M/N), SBO >> 4 at [32,46) (distance between 8-pixel atoms along K), version 1 at [46,48), layout type at [61,64)
+// (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).
+template <int ROWB>
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  constexpr uint64_t sbo = 8 * ROWB;
+  constexpr uint64_t layout = (ROWB == 128) ? 2 : 4;
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((sbo >> 4) << 32) | (1ULL << 46) |
+         (layout << 61);
+}
+// instruction descriptor, kind::f16: D fp32, A/B bf16, both MN-major (bits 15, 16), N >> 3 at [17,23), M = 128
+__device__ __forceinline__ uint32_t make_idesc_mn(int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+template <int XROWB, int GROWB>
+__global__ void __launch_bounds__(192)
+conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams p) {
+  constexpr int XC = XROWB / 2, GC = GROWB / 2;       // channels per box
+  constexpr int XBOX = kP * XROWB, GBOX = kP * GROWB;  // bytes per box
+  constexpr int SPR = 128 / XC;                        // x boxes (slots) per instruction row
+  extern __shared__ unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + 8;
+  uint64_t* acc_full = empty + 8;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  unsigned char* stages = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 256 + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = p.slots_pad * XBOX + (p.NB / GC) * GBOX;
+  const int tx_bytes = p.slots * XBOX + (p.NB / GC) * GBOX;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kh = blockIdx.z;
+  const int cib = blockIdx.y % p.n_cib, cob = blockIdx.y / p.n_cib;
+  const int split = blockIdx.x, nsplit = gridDim.x;
+  const int my_chunks = (p.chunks - split + nsplit - 1) / nsplit;  // chunks split, split + nsplit, ...
+  const uint32_t tmem_cols = (uint32_t)(p.irows * p.NB);
+  uint32_t alloc_cols = 32;
+  while (alloc_cols < tmem_cols) alloc_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmG);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, alloc_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================================================= TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_chunks; ++it) {
+        const int c = split + it * nsplit;
+        const int tw = c % p.tiles_w, th = (c / p.tiles_w) % p.tiles_h, b = c / (p.tiles_w * p.tiles_h);
+        const int ho0 = th * kCR, wo0 = tw * kTW;
+        mbar_wait(&empty[s], ph ^ 1);
+        unsigned char* xs = stages + (size_t)s * stage_bytes;
+        unsigned char* gs = xs + p.slots_pad * XBOX;
+        mbar_arrive_expect_tx(&full[s], tx_bytes);
+        for (int q = 0; q < p.NB / GC; ++q) tma_load_4d(gs + q * GBOX, &tmG, cob * p.NB + q * GC, wo0, ho0, b, &full[s]);
+        const int hi = ho0 * p.stride + kh - 1;
+        for (int kw = 0; kw < 3; ++kw) {
+          const int wi = wo0 * p.stride + kw - 1;
+          for (int q = 0; q < p.nb; ++q)
+            tma_load_4d(xs + (kw * p.nb + q) * XBOX, &tmX, cib * p.CB + q * XC, wi, hi, b, &full[s]);
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_mn(p.NB);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_chunks; ++it) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t xs = smem_u32(stages + (size_t)s * stage_bytes);
+        const uint32_t gs = xs + p.slots_pad * XBOX;
+#pragma unroll
+        for (int k = 0; k < kP / 16; ++k) {
+          // 16 pixels further along K = two 8-row atoms = 16 swizzle rows
+          const uint64_t bdesc = make_desc_mn<GROWB>(gs + k * 16 * GROWB, GBOX);
+          for (int j = 0; j < p.irows; ++j) {
+            const uint64_t adesc = make_desc_mn<XROWB>(xs + j * SPR * XBOX + k * 16 * XROWB, XBOX);
+            umma_bf16(tmem_base + j * p.NB, adesc, bdesc, idesc, (it | k) != 0);
+          }
+        }
+        umma_commit(&empty[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+  } else if (my_chunks > 0) {
+    // ================================================================= epilogue (warps 2..5): red.add into dW
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;   // accumulator row inside an instruction row
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    for (int j = 0; j < p.irows; ++j) {
+      const int slot = j * SPR + m / XC;
+      const int kw = slot / p.nb;
+      const int ci = cib * p.CB + (slot % p.nb) * XC + (m % XC);
+      const bool row_ok = slot < p.slots && ci < p.Cx;
+      for (int c0 = 0; c0 < p.NB; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + j * p.NB + c0, r);
+        if (!row_ok) continue;
+        const int co0 = cob * p.NB + c0;
+        float* dst = p.dW + ((size_t)co0 * p.Cin_tot + p.ci_off + ci) * 9 + kh * 3 + kw;
+#pragma unroll
+        for (int n = 0; n < 32; ++n)
+          if (co0 + n < p.Cout) atomicAdd(dst + (size_t)n * p.Cin_tot * 9, __uint_as_float(r[n]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, alloc_cols);
+  }
+}
+
+template <int XROWB, int GROWB>
+int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mg, const WgradParams& p, int splits, int smem, cudaStream_t st) {
+  auto kern = conv3x3_wgrad_kernel<XROWB, GROWB>;
+  static int attr_set = 0;
+  if (attr_set < smem) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_set = smem;
+  }
+  dim3 grid(splits, p.n_cib * p.n_cob, 3);
+  kern<<<grid, 192, smem, st>>>(mx, mg, p);
+  return after_launch("conv3x3_wgrad_kernel");
+}
+
+// per-(sample, border class, channel) sums of an NHWC bf16 map: out[b][rc][cc][c], rc/cc = 0 first row/col, 1 interior,
+// 2 last row/col.  One CTA per (b, row); thread = (column slice, channel), partial sums folded with fp32 atomics.
+__global__ void __launch_bounds__(256) border_sum_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ out, int B,
+                                                         int H, int W, int C, int Cs) {
+  const int row = blockIdx.x;  // b * H + h
+  const int b = row / H, h = row % H;
+  const int rc = h == 0 ? 0 : (h == H - 1 ? 2 : 1);
+  const __nv_bfloat16* src = g + (size_t)row * W * Cs;
+  const int parts = C <= 128 ? 256 / C : 1;  // column slices per channel (C = 32, 64, 128 -> 8, 4, 2)
+  for (int c = threadIdx.x % (256 / parts); c < C; c += 256 / parts) {
+    const int part = threadIdx.x / (256 / parts);
+    float mid = 0.f;
+    for (int w = 1 + part; w < W - 1; w += parts) mid += __bfloat162float(src[(size_t)w * Cs + c]);
+    float* o = out + (((size_t)b * 3 + rc) * 3) * C + c;
+    atomicAdd(o + C, mid);
+    if (part == 0) {
+      atomicAdd(o, __bfloat162float(src[c]));
+      atomicAdd(o + 2 * C, __bfloat162float(src[(size_t)(W - 1) * Cs + c]));
+    }
+  }
+}
+
+}  // namespace
+}  // namespace faln
+
+using namespace faln;
+
+// g  [B,Hg,Wg,Cg] bf16 NHWC: gradient w.r.t. the conv's pre-activation output (Cg % 32 == 0; channels >= Cout are ignored)
+// x  [B,H,W,Cxs]  bf16 NHWC: the conv's input (one source of a concatenated input per call; Cxs % 32 == 0)
+// dW [Cout, Cin_tot, 3, 3] fp32: columns [ci_off, ci_off + Cx) are ACCUMULATED into (caller zeroes them once per step)
+extern "C" int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B, int H, int W, int Cg, int Cxs, int Cout,
+                                  int Cx, int ci_off, int Cin_tot, int stride, faln_stream_t stream) {
+  FALN_REQUIRE(g && x && dW && B > 0 && H > 0 && W > 0, "faln_conv3x3_wgrad: null pointer / bad shape");
+  FALN_REQUIRE(stride == 1 || stride == 2, "faln_conv3x3_wgrad: stride must be 1 or 2");
+  FALN_REQUIRE(Cg % 32 == 0 && Cxs % 32 == 0 && Cg > 0 && Cxs > 0, "faln_conv3x3_wgrad: channel strides must be multiples of 32");
+  FALN_REQUIRE(Cout > 0 && Cout <= Cg && Cx > 0 && Cx <= Cxs && ci_off >= 0 && ci_off + Cx <= Cin_tot,
+               "faln_conv3x3_wgrad: channel ranges out of bounds");
+  const int Hg = (H - 1) / stride + 1, Wg = (W - 1) / stride + 1;
+  const int XC = Cxs % 64 == 0 ? 64 : 32, GC = Cg % 64 == 0 ? 64 : 32;
+  FALN_REQUIRE(XC == 64 || Cxs == 32, "faln_conv3x3_wgrad: input channel count must be 32 or a multiple of 64");
+  FALN_REQUIRE(GC == 64 || Cg == 32, "faln_conv3x3_wgrad: gradient channel count must be 32 or a multiple of 64");
+  WgradParams p{};
+  p.B = B; p.Hg = Hg; p.Wg = Wg; p.stride = stride;
+  p.tiles_w = (Wg + kTW - 1) / kTW; p.tiles_h = (Hg + kCR - 1) / kCR;
+  p.chunks = B * p.tiles_w * p.tiles_h;
+  p.CB = XC == 32 ? 32 : (Cxs % 128 == 0 ? 128 : 64);
+  p.NB = GC == 32 ? 32 : (Cg % 128 == 0 ? 128 : 64);
+  p.n_cib = (Cx + p.CB - 1) / p.CB;       // blocks that contain written channels only
+  p.n_cob = (Cout + p.NB - 1) / p.NB;
+  p.nb = p.CB / XC;
+  p.slots = 3 * p.nb;
+  const int spr = 128 / XC;
+  p.slots_pad = (p.slots + spr - 1) / spr * spr;
+  p.irows = p.slots_pad / spr;
+  p.Cx = Cx; p.Cout = Cout; p.ci_off = ci_off; p.Cin_tot = Cin_tot; p.dW = dW;
+  const int xbox = kP * XC * 2, gbox = kP * GC * 2;
+  const int stage_bytes = p.slots_pad * xbox + (p.NB / GC) * gbox;
+  p.stages = (200 * 1024) / stage_bytes;
+  if (p.stages > 6) p.stages = 6;
+  if (p.stages < 2) p.stages = 2;
+  const int smem = 256 + 1024 + p.stages * stage_bytes;
+  // split-K: about two waves of CTAs over the SMs, never more splits than chunks
+  int splits = (2 * sm_count()) / (3 * p.n_cib * p.n_cob);
+  if (splits > p.chunks) splits = p.chunks;
+  if (splits < 1) splits = 1;
+  CUtensorMap mx, mg;
+  if (!make_act_map(&mx, x, B, H, W, Cxs, XC, stride, kCR) || !make_act_map(&mg, g, B, Hg, Wg, Cg, GC, 1, kCR)) {
+    set_error("faln_conv3x3_wgrad: cuTensorMapEncodeTiled failed (driver entry point missing or bad tensor geometry)");
+    return FALN_ERR_LAUNCH;
+  }
+  cudaStream_t st = as_stream(stream);
+  if (XC == 64 && GC == 64) return launch_wgrad<128, 128>(mx, mg, p, splits, smem, st);
+  if (XC == 32 && GC == 64) return launch_wgrad<64, 128>(mx, mg, p, splits, smem, st);
+  if (XC == 64 && GC == 32) return launch_wgrad<128, 64>(mx, mg, p, splits, smem, st);
+  return launch_wgrad<64, 64>(mx, mg, p, splits, smem, st);
+}
+
+// out [B,3,3,C] fp32 += per-sample sums of g [B,H,W,Cs] (bf16 NHWC, channels [0,C)) over the nine border classes
+// (first / interior / last row x first / interior / last column).  Used for the weight gradient of a spatially constant
+// input channel (the max_disp/100 plane of /root/reference/models/FAL_netB.py:145,208-209).  Needs H, W >= 2.
+extern "C" int faln_border_sum_nhwc(const void* g, float* out, int B, int H, int W, int C, int Cs, faln_stream_t stream) {
+  FALN_REQUIRE(g && out && B > 0 && H >= 2 && W >= 2 && C > 0 && Cs >= C, "faln_border_sum_nhwc: bad arguments");
+  border_sum_kernel<<<B * H, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(g), out, B, H, W, C, Cs);
+  return after_launch("border_sum_kernel");
+}

@@ -74,8 +74,39 @@ class FlatAdamDDP:
             for i, p in enumerate(self.params):
                 p.register_post_accumulate_grad_hook(self._make_hook(i))
         self._reset_counts()
+        # hand-scheduled backward passes (fal_net_b200.backbone) reduce their gradients straight into the arena
+        self._index = {n: i for i, n in enumerate(self.names)}
+        self._model_id = id(model)
+        try:
+            model._faln_grad_sink = self
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------------------------------
+    # gradient-sink protocol used by backbone.backward
+    def accepts(self, model):
+        """True if this arena is where ``model``'s gradients live right now (p.grad aliases the arena)."""
+        if id(model) != self._model_id:
+            return False
+        p, off = self.params[0], self.offsets[0]
+        return p.grad is not None and p.grad.data_ptr() == self.g.data_ptr() + 4 * off
+
+    def grad_view(self, name):
+        i = self._index[name]
+        p = self.params[i]
+        return self.g[self.offsets[i]:self.offsets[i] + p.numel()].view(p.shape)
+
+    def mark_ready(self, name):
+        if self.overlap:
+            self._hook(self._index[name])
+
+    def _hook(self, i):
+        b = self._bucket_of[i]
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            s, e, _ = self.buckets[b]
+            self._works.append(dist.all_reduce(self.g[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
     def _reset_counts(self):
         for b, (_, _, mem) in enumerate(self.buckets):
             self._pending[b] = len(mem)
@@ -83,11 +114,7 @@ class FlatAdamDDP:
 
     def _make_hook(self, i):
         def hook(_p):
-            b = self._bucket_of[i]
-            self._pending[b] -= 1
-            if self._pending[b] == 0:
-                s, e, _ = self.buckets[b]
-                self._works.append(dist.all_reduce(self.g[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+            self._hook(i)
         return hook
 
     def zero_grad(self):

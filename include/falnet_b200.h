@@ -191,6 +191,18 @@ int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, const float* 
 int faln_conv3x3_dgrad(const void* g, const void* wd, void* gx, const void* residual, const void* ysave, int B, int H,
                        int W, int Cg, int Cx, int Cx_pad, int stride, int accum, int dact, int gx_c, int res_c,
                        int ysave_c, faln_stream_t stream);
+/* Weight gradient of the 3x3 convolution (pad 1, stride 1 or 2) on tcgen05 -- replaces the cuDNN wgrad autograd runs for
+ * nn.Conv2d of /root/reference/models/FAL_netB.py:99-127 in loss.backward() (/root/reference/Train_Stage1_K.py:260).
+ *   dW[co, ci_off + ci, kh, kw] += sum_{b,ho,wo} g[b,ho,wo,co] * x[b, ho*s+kh-1, wo*s+kw-1, ci]
+ * g [B,(H-1)/s+1,(W-1)/s+1,Cg] bf16 NHWC (pre-activation gradient), x [B,H,W,Cxs] bf16 NHWC (one source of a concatenated
+ * input per call), dW [Cout,Cin_tot,3,3] fp32, ACCUMULATED with split-K fp32 reductions (zero it once per step).
+ * Cg, Cxs: 32 or multiples of 64; Cout <= Cg and Cx <= Cxs select the channels actually written. */
+int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B, int H, int W, int Cg, int Cxs, int Cout, int Cx,
+                       int ci_off, int Cin_tot, int stride, faln_stream_t stream);
+/* out [B,3,3,C] fp32 += sums of g [B,H,W,Cs] (bf16 NHWC) per sample over the 3x3 border classes (first / interior / last
+ * row x column): the weight gradient of a spatially constant input channel (reference :145,208-209) is a 9-term
+ * combination of these.  H, W >= 2. */
+int faln_border_sum_nhwc(const void* g, float* out, int B, int H, int W, int C, int Cs, faln_stream_t stream);
 /* Backward of F.interpolate(mode='nearest') (reference :58) fused with the producer's activation derivative. */
 int faln_upsample_nearest_bwd_nhwc(const void* g_hi, const void* y_lo, void* g_lo, int B, int Hl, int Wl, int Hh, int Wh,
                                    int C, int dact, int accum, faln_stream_t stream);

@@ -1,0 +1,70 @@
+"""tcgen05 weight-gradient kernel (csrc/conv_wgrad.cu) vs the fp32 wgrad of the same bf16 operands (torch autograd of
+F.conv2d), i.e. the bound is accumulation-order noise only.  Replaces the cuDNN wgrad behind
+/root/reference/models/FAL_netB.py:99-127 in loss.backward()."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CL = torch.channels_last
+
+
+def _ref_wgrad(x16, g16, cout, cin, stride):
+    w = torch.zeros(cout, cin, 3, 3, device=x16.device, dtype=torch.float32, requires_grad=True)
+    y = F.conv2d(x16.float()[:, :cin], w, None, stride, 1)
+    (gw,) = torch.autograd.grad(y, w, g16.float()[:, :cout])
+    return gw
+
+
+CASES = [
+    # B, H, W, Cxs, Cg, cout, cx, stride
+    (2, 12, 40, 64, 64, 64, 64, 1),
+    (2, 12, 40, 32, 32, 32, 32, 1),
+    (2, 12, 40, 32, 64, 49, 32, 1),
+    (2, 12, 40, 64, 32, 32, 64, 1),
+    (1, 7, 23, 128, 64, 64, 128, 1),
+    (2, 9, 20, 64, 128, 128, 64, 1),
+    (1, 6, 20, 256, 256, 256, 256, 1),
+    (2, 3, 10, 512, 512, 512, 512, 1),
+    (2, 13, 41, 32, 64, 64, 32, 2),
+    (2, 12, 40, 64, 128, 128, 64, 2),
+    (1, 6, 20, 256, 512, 512, 256, 2),
+    (8, 48, 160, 64, 64, 64, 64, 1),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cxs,Cg,cout,cx,stride", CASES)
+def test_wgrad_matches_fp32(B, H, W, Cxs, Cg, cout, cx, stride):
+    from fal_net_b200 import conv_native as CN
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(B * 1000 + H * 10 + Cxs + stride)
+    Hg, Wg = (H - 1) // stride + 1, (W - 1) // stride + 1
+    x16 = torch.randn(B, Cxs, H, W, device=dev, generator=g).to(torch.bfloat16).contiguous(memory_format=CL)
+    g16 = torch.randn(B, Cg, Hg, Wg, device=dev, generator=g).to(torch.bfloat16).contiguous(memory_format=CL)
+    ref = _ref_wgrad(x16, g16, cout, cx, stride)
+    # write into columns [8, 8 + cx) of a wider gradient tensor that already holds something (accumulation semantics)
+    dW = torch.full((cout, cx + 16, 3, 3), 0.5, device=dev)
+    CN.conv3x3_wgrad(g16, x16, dW, cout=cout, cx=cx, ci_off=8, stride=stride)
+    torch.cuda.synchronize()
+    got = dW[:, 8:8 + cx] - 0.5
+    scale = ref.abs().max()
+    assert float((got - ref).abs().max() / scale) < 2e-3, float((got - ref).abs().max() / scale)
+    assert float((dW[:, :8] - 0.5).abs().max()) == 0 and float((dW[:, 8 + cx:] - 0.5).abs().max()) == 0
+
+
+@pytest.mark.parametrize("stride,H,W", [(2, 12, 40), (2, 13, 41), (1, 9, 20)])
+def test_const_channel_wgrad(stride, H, W):
+    from fal_net_b200 import conv_native as CN
+    dev = torch.device("cuda:0")
+    B, C = 3, 64
+    gen = torch.Generator(device=dev).manual_seed(5)
+    Hg, Wg = (H - 1) // stride + 1, (W - 1) // stride + 1
+    g16 = torch.randn(B, C, Hg, Wg, device=dev, generator=gen).to(torch.bfloat16).contiguous(memory_format=CL)
+    val = torch.tensor([3.0, 1.5, 2.25], device=dev)
+    plane = val.view(B, 1, 1, 1).expand(B, 1, H, W).contiguous()
+    w = torch.zeros(C, 1, 3, 3, device=dev, requires_grad=True)
+    (ref,) = torch.autograd.grad(F.conv2d(plane, w, None, stride, 1), w, g16.float())
+    got = CN.const_channel_wgrad(g16, val, (H, W), stride, C)
+    assert float((got - ref[:, 0]).abs().max() / ref.abs().max()) < 1e-4

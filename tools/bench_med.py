@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fal_net_b200 import med  # noqa: E402
 
 
-def bench(B, N, H, W, iters=10, sets=3, peak=6557.8, flags=0):
+def bench(B, N, H, W, iters=10, sets=3, peak=6557.8, flags=0, warm=3):
     dev = torch.device("cuda:0")
     gen = torch.Generator(device=dev).manual_seed(7)
     L = [2 * torch.randn(B, N, H, W, generator=gen, device=dev) for _ in range(sets)]
@@ -30,7 +30,7 @@ def bench(B, N, H, W, iters=10, sets=3, peak=6557.8, flags=0):
     gl = torch.empty_like(L[0])
 
     def timeit(fn):
-        for s in range(3):
+        for s in range(warm):
             fn(s % sets)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
@@ -63,7 +63,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.profile:
         B, N, H, W = (int(v) for v in a.profile.split(","))
-        print(json.dumps(bench(B, N, H, W, iters=2, sets=2, flags=a.flags)))
+        print(json.dumps(bench(B, N, H, W, iters=1, sets=2, flags=a.flags, warm=1)))
         sys.exit(0)
     peak = 6557.8
     try:
