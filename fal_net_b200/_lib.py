@@ -46,7 +46,9 @@ _SIGNATURES = {
     "faln_planar_to_nhwc_bf16": [_p, _p] + [_i] * 5 + [_ll, _p],
     "faln_conv3x3_fwd": [_p] * 8 + [_i] * 10 + [_ll, _i, _p],
     "faln_conv3x3_dgrad": [_p] * 5 + [_i] * 12 + [_p],
-    "faln_conv3x3_wgrad": [_p] * 3 + [_i] * 10 + [_p],
+    "faln_conv3x3_wgrad": [_p] * 3 + [_i] * 10 + [_u, _p],
+    "faln_f32_to_bf16": [_p, _p, _ll, _p],
+    "faln_pack_dgrad_batched": [_p, _p, _p, _i, _i, _p],
     "faln_border_sum_nhwc": [_p, _p] + [_i] * 5 + [_p],
     "faln_upsample_nearest_bwd_nhwc": [_p] * 3 + [_i] * 8 + [_p],
     "faln_maxpool2_bwd_nhwc": [_p] * 3 + [_i] * 5 + [_p],

@@ -54,12 +54,25 @@ def _cached(weight, tag, fn):
 
 
 def _wk(weight, cin=None):
+    """Forward (KRSC bf16) weight: a view of the optimiser's bf16 shadow arena when the parameter lives in one (no pack
+    kernels at all), else packed once per parameter version."""
     cin = cin or weight.shape[1]
+    ar = getattr(weight, "_faln_arena", None)
+    if ar is not None and weight.grad_fn is None:
+        w = ar[0].packed_fwd(ar[1], cin)
+        if w is not None:
+            return w
     return _cached(weight, ("fwd", cin), lambda: CN.pack_weight(weight[:, :cin]))
 
 
 def _wd(weight, cin=None):
+    """Data-gradient weight [Cin,3,3,Cout] bf16: the optimiser's batched per-step re-pack, else packed per version."""
     cin = cin or weight.shape[1]
+    ar = getattr(weight, "_faln_arena", None)
+    if ar is not None and weight.grad_fn is None:
+        w = ar[0].packed_dgrad(ar[1], cin)
+        if w is not None:
+            return w
     return _cached(weight, ("dgrad", cin), lambda: CN.pack_weight_dgrad(weight[:, :cin]))
 
 
@@ -129,7 +142,9 @@ class _DictSink:
 
     def grad_view(self, name):
         if name not in self.grads:
-            self.grads[name] = torch.zeros(self.shapes[name], device=self.device, dtype=torch.float32)
+            shp = self.shapes[name]
+            t = torch.zeros(shp, device=self.device, dtype=torch.float32)
+            self.grads[name] = t.contiguous(memory_format=CL) if len(shp) == 4 and shp[2:] == (3, 3) else t
         return self.grads[name]
 
     def mark_ready(self, name):
@@ -167,7 +182,7 @@ def backward(model, tape, g_logits, sink=None):
     s0 = tape["conv0"][2]
     wf = tape["wf"]
     bias_grad("conv0.bias", g, N)
-    gwf = torch.zeros(N, u.shape[1] + s0.shape[1], 3, 3, device=dev, dtype=torch.float32)   # gradient of the folded weight
+    gwf = torch.zeros(N, 3, 3, u.shape[1] + s0.shape[1], device=dev, dtype=torch.float32).permute(0, 3, 1, 2)   # folded weight
     CN.conv3x3_wgrad(g, u, gwf, cout=N, ci_off=0)
     CN.conv3x3_wgrad(g, s0, gwf, cout=N, ci_off=u.shape[1])
     w0 = model.conv0.weight.detach()[:, :, 0, 0]

@@ -3,25 +3,30 @@
 // Replaces the cuDNN wgrad calls autograd issues for nn.Conv2d in /root/reference/models/FAL_netB.py:99-127 (backward of
 // :144-174) and the ~3 ATen cast / add / cat launches around each of them.
 //
-//   dW[co, ci, kh, kw] = sum over (b, ho, wo) of  g[b, ho, wo, co] * x[b, ho*s + kh - 1, wo*s + kw - 1, ci]
+//   dW[co, kh, kw, ci] = sum over (b, ho, wo) of  g[b, ho, wo, co] * x[b, ho*s + kh - 1, wo*s + kw - 1, ci]
 //
 // GEMM view (per filter tap): D[ci, co] = X_tap^T[ci, pixel] * G[pixel, co] -- the reduction dimension K is the PIXEL
 // axis.  Both tensors are NHWC bf16, i.e. the channel (M resp. N) index is the contiguous one: both operands are
 // "MN-major" for tcgen05.mma, which the instruction descriptor supports for 16-bit types (a_major = b_major = 1).
 //
-//   * a CTA owns one filter row kh (3 taps), one block of CB input channels, one block of NB output channels and a
-//     strided subset of the 64-pixel chunks (4 rows x 16 columns of the gradient map) -- split-K over pixels
-//   * per chunk the TMA unit fetches, with the SAME tensor maps geometry the forward uses for its A operand,
-//       g : NB/GC boxes  [GC channels, 16, 4]            (GC = 64, 128B swizzle; 32 -> 64B swizzle)
-//       x : 3 * CB/XC boxes [XC channels, 16*s, 4*s] at the tap's offset, element stride s, out-of-image = 0 = padding
-//     a box lands as 64 pixel rows of 128 (64) bytes = the canonical MN-major swizzled atom sequence: 8 pixel rows x one
-//     swizzle row per atom, atoms 1024 (512) bytes apart along K (descriptor SBO), boxes one after the other along
-//     M / N (descriptor LBO = box bytes)
-//   * the M = 128 rows of one tcgen05.mma are TWO (four) consecutive x boxes -- two taps, or two channel sub-blocks of one
-//     tap -- so small channel counts still fill the instruction; each instruction row owns NB TMEM columns
+//   * a CTA owns ALL NINE taps of one block of XC input channels x NB output channels and a strided subset of the
+//     64-pixel chunks (4 rows x 16 columns of the gradient map) -- split-K over pixels
+//   * per chunk the TMA unit fetches
+//       g : one box [NB channels, 16, 4]                       (64 channels -> 128B swizzle, 32 -> 64B swizzle)
+//       x : stride 1, 64-channel blocks: ONE halo box [64 channels, 18, 6] -- every tap's window is a sub-rectangle of
+//           it, addressed by the start address / LBO of the matrix descriptors.  Measured on B200: the 128B swizzle is a
+//           function of the absolute shared-memory address, so a window may start on any 128-byte row with the
+//           descriptor's base-offset field left 0 (setting it to (start >> 7) & 7 gives wrong results);
+//           otherwise nine boxes [XC channels, 16*s, 4*s] at the taps' offsets with element stride s.
+//           Out-of-image elements are zero-filled by the TMA bounds check = the conv's zero padding
+//     a box lands as pixel rows of 128 (64) bytes = the canonical MN-major swizzled atoms: 8 pixel rows x one swizzle row
+//     per atom, atoms 1024 (512) bytes apart along K (descriptor SBO)
+//   * the M = 128 rows of one tcgen05.mma are TWO (four) taps' windows (descriptor LBO = distance between them), so
+//     64- and 32-channel blocks fill the instruction; each instruction row owns NB TMEM columns (5 x 64 = 320 columns)
 //   * the epilogue warps read the accumulators with tcgen05.ld and reduce them into the fp32 gradient tensor
-//     [Cout, Cin_total, 3, 3] (the flat gradient arena the fused Adam reads) with red.global.add.f32: no workspace, no
-//     separate reduction kernel, gradients of a concatenated input are two calls with different column offsets.
+//     [Cout, 3, 3, Cin_total] (KRSC, the layout of the flat gradient arena the fused Adam reads: lanes = consecutive ci,
+//     so every red.global.add.f32 is a coalesced 128-byte request); gradients of a concatenated input are two calls with
+//     different column offsets.  No workspace, no separate reduction kernel.
 #include "tc_common.cuh"
 
 namespace faln {
@@ -29,16 +34,18 @@ namespace {
 
 constexpr int kCR = 4;            // gradient-map rows per chunk
 constexpr int kP = kCR * kTW;     // 64 pixels per chunk = 4 UMMA K-steps
+constexpr int kHaloW = kTW + 2, kHaloH = kCR + 2;
 
 struct WgradParams {
   int B, Hg, Wg;            // gradient map
   int stride;
   int tiles_w, tiles_h, chunks;
   int n_cib, n_cob;         // channel blocks
-  int CB, NB;               // channels per block
-  int nb;                   // x boxes per tap (CB / XC)
-  int slots, slots_pad;     // 3 * nb, rounded up to whole instruction rows
-  int irows;                // instruction rows = slots_pad / (128 / XC)
+  int NB;                   // output channels per block (= channels of one g box)
+  int irows;                // instruction rows: ceil(9 taps / (128 / XC))
+  int halo;                 // 1: x arrives as one halo box per chunk
+  int x_bytes;              // bytes reserved per stage for x (1024-aligned), tx_x: bytes the TMA delivers
+  int tx_x;
   int Cx, Cout;             // real channel counts (bounds of what is written)
   int ci_off, Cin_tot;      // column offset / row length of dW
   int stages;
@@ -46,14 +53,14 @@ struct WgradParams {
 };
 
 // MN-major swizzled shared-memory matrix descriptor: start >> 4, LBO >> 4 at [16,30) (distance between the 64- / 32-channel
-// atoms along M/N), SBO >> 4 at [32,46) (distance between 8-pixel atoms along K), version 1 at [46,48), layout type at [61,64)
-// (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).
+// atoms along M/N), SBO >> 4 at [32,46) (distance between 8-pixel atoms along K), version 1 at [46,48), base offset at
+// [49,52) (left 0, see above), layout type at [61,64) (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).
 template <int ROWB>
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t base_off = 0) {
   constexpr uint64_t sbo = 8 * ROWB;
   constexpr uint64_t layout = (ROWB == 128) ? 2 : 4;
-  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((sbo >> 4) << 32) | (1ULL << 46) |
-         (layout << 61);
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((sbo >> 4) << 32) |
+         (1ULL << 46) | ((uint64_t)(base_off & 7) << 49) | (layout << 61);
 }
 // instruction descriptor, kind::f16: D fp32, A/B bf16, both MN-major (bits 15, 16), N >> 3 at [17,23), M = 128
 __device__ __forceinline__ uint32_t make_idesc_mn(int N) {
@@ -63,20 +70,19 @@ __device__ __forceinline__ uint32_t make_idesc_mn(int N) {
 template <int XROWB, int GROWB>
 __global__ void __launch_bounds__(192)
 conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams p) {
-  constexpr int XC = XROWB / 2, GC = GROWB / 2;       // channels per box
-  constexpr int XBOX = kP * XROWB, GBOX = kP * GROWB;  // bytes per box
-  constexpr int SPR = 128 / XC;                        // x boxes (slots) per instruction row
+  constexpr int XC = XROWB / 2;                        // channels per x box
+  constexpr int XBOX = kP * XROWB, GBOX = kP * GROWB;  // bytes per (non-halo) box
+  constexpr int SPR = 128 / XC;                        // taps per instruction row
   extern __shared__ unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty = full + 8;
   uint64_t* acc_full = empty + 8;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
   unsigned char* stages = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 256 + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = p.slots_pad * XBOX + (p.NB / GC) * GBOX;
-  const int tx_bytes = p.slots * XBOX + (p.NB / GC) * GBOX;
+  const int stage_bytes = p.x_bytes + GBOX;
+  const int tx_bytes = p.tx_x + GBOX;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kh = blockIdx.z;
   const int cib = blockIdx.y % p.n_cib, cob = blockIdx.y / p.n_cib;
   const int split = blockIdx.x, nsplit = gridDim.x;
   const int my_chunks = (p.chunks - split + nsplit - 1) / nsplit;  // chunks split, split + nsplit, ...
@@ -112,14 +118,14 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const int ho0 = th * kCR, wo0 = tw * kTW;
         mbar_wait(&empty[s], ph ^ 1);
         unsigned char* xs = stages + (size_t)s * stage_bytes;
-        unsigned char* gs = xs + p.slots_pad * XBOX;
+        unsigned char* gs = xs + p.x_bytes;
         mbar_arrive_expect_tx(&full[s], tx_bytes);
-        for (int q = 0; q < p.NB / GC; ++q) tma_load_4d(gs + q * GBOX, &tmG, cob * p.NB + q * GC, wo0, ho0, b, &full[s]);
-        const int hi = ho0 * p.stride + kh - 1;
-        for (int kw = 0; kw < 3; ++kw) {
-          const int wi = wo0 * p.stride + kw - 1;
-          for (int q = 0; q < p.nb; ++q)
-            tma_load_4d(xs + (kw * p.nb + q) * XBOX, &tmX, cib * p.CB + q * XC, wi, hi, b, &full[s]);
+        tma_load_4d(gs, &tmG, cob * p.NB, wo0, ho0, b, &full[s]);
+        if (p.halo) {
+          tma_load_4d(xs, &tmX, cib * XC, wo0 - 1, ho0 - 1, b, &full[s]);
+        } else {
+          for (int t = 0; t < 9; ++t)
+            tma_load_4d(xs + t * XBOX, &tmX, cib * XC, wo0 * p.stride + t % 3 - 1, ho0 * p.stride + t / 3 - 1, b, &full[s]);
         }
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
@@ -134,13 +140,23 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t xs = smem_u32(stages + (size_t)s * stage_bytes);
-        const uint32_t gs = xs + p.slots_pad * XBOX;
+        const uint32_t gs = xs + p.x_bytes;
 #pragma unroll
         for (int k = 0; k < kP / 16; ++k) {
-          // 16 pixels further along K = two 8-row atoms = 16 swizzle rows
+          // K-step k = the 16 pixels of chunk row k: two 8-pixel atoms, 8 swizzle rows apart (SBO)
           const uint64_t bdesc = make_desc_mn<GROWB>(gs + k * 16 * GROWB, GBOX);
           for (int j = 0; j < p.irows; ++j) {
-            const uint64_t adesc = make_desc_mn<XROWB>(xs + j * SPR * XBOX + k * 16 * XROWB, XBOX);
+            uint64_t adesc;
+            if (p.halo) {
+              // instruction row j = taps 2j, 2j+1: windows of the halo tile starting at halo row (k + kh) * 18 + kw
+              const int t0 = 2 * j, t1 = 2 * j + 1;
+              const uint32_t o0 = (uint32_t)(((k + t0 / 3) * kHaloW + t0 % 3) * XROWB);
+              const uint32_t o1 = (uint32_t)(((k + t1 / 3) * kHaloW + t1 % 3) * XROWB);
+              const uint32_t start = xs + o0;
+              adesc = make_desc_mn<XROWB>(start, o1 - o0);
+            } else {
+              adesc = make_desc_mn<XROWB>(xs + j * SPR * XBOX + k * 16 * XROWB, XBOX);
+            }
             umma_bf16(tmem_base + j * p.NB, adesc, bdesc, idesc, (it | k) != 0);
           }
         }
@@ -150,25 +166,24 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       umma_commit(acc_full);
     }
   } else if (my_chunks > 0) {
-    // ================================================================= epilogue (warps 2..5): red.add into dW
+    // ================================================================= epilogue (warps 2..5): red.add into dW (KRSC)
     const int quad = warp & 3;
     const int m = quad * 32 + lane;   // accumulator row inside an instruction row
     mbar_wait(acc_full, 0);
     tc_fence_after();
     for (int j = 0; j < p.irows; ++j) {
-      const int slot = j * SPR + m / XC;
-      const int kw = slot / p.nb;
-      const int ci = cib * p.CB + (slot % p.nb) * XC + (m % XC);
-      const bool row_ok = slot < p.slots && ci < p.Cx;
+      const int tap = j * SPR + m / XC;
+      const int ci = cib * XC + (m % XC);
+      const bool row_ok = tap < 9 && ci < p.Cx;
       for (int c0 = 0; c0 < p.NB; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + j * p.NB + c0, r);
         if (!row_ok) continue;
         const int co0 = cob * p.NB + c0;
-        float* dst = p.dW + ((size_t)co0 * p.Cin_tot + p.ci_off + ci) * 9 + kh * 3 + kw;
+        float* dst = p.dW + ((size_t)co0 * 9 + tap) * p.Cin_tot + p.ci_off + ci;
 #pragma unroll
         for (int n = 0; n < 32; ++n)
-          if (co0 + n < p.Cout) atomicAdd(dst + (size_t)n * p.Cin_tot * 9, __uint_as_float(r[n]));
+          if (co0 + n < p.Cout) atomicAdd(dst + (size_t)n * 9 * p.Cin_tot, __uint_as_float(r[n]));
       }
     }
   }
@@ -188,9 +203,22 @@ int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mg, const WgradParams
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_set = smem;
   }
-  dim3 grid(splits, p.n_cib * p.n_cob, 3);
+  dim3 grid(splits, p.n_cib * p.n_cob, 1);
   kern<<<grid, 192, smem, st>>>(mx, mg, p);
   return after_launch("conv3x3_wgrad_kernel");
+}
+
+// halo tensor map: box [64 channels, 18, 6, 1], 128B swizzle
+bool make_halo_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C) {
+  auto fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)kHaloW, (cuuint32_t)kHaloH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // per-(sample, border class, channel) sums of an NHWC bf16 map: out[b][rc][cc][c], rc/cc = 0 first row/col, 1 interior,
@@ -222,9 +250,10 @@ using namespace faln;
 
 // g  [B,Hg,Wg,Cg] bf16 NHWC: gradient w.r.t. the conv's pre-activation output (Cg % 32 == 0; channels >= Cout are ignored)
 // x  [B,H,W,Cxs]  bf16 NHWC: the conv's input (one source of a concatenated input per call; Cxs % 32 == 0)
-// dW [Cout, Cin_tot, 3, 3] fp32: columns [ci_off, ci_off + Cx) are ACCUMULATED into (caller zeroes them once per step)
+// dW [Cout, 3, 3, Cin_tot] fp32 (KRSC): columns [ci_off, ci_off + Cx) are ACCUMULATED into (caller zeroes them once per step)
+// flags: bit 0 = never use the halo path (validation: nine boxes per chunk instead)
 extern "C" int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B, int H, int W, int Cg, int Cxs, int Cout,
-                                  int Cx, int ci_off, int Cin_tot, int stride, faln_stream_t stream) {
+                                  int Cx, int ci_off, int Cin_tot, int stride, unsigned flags, faln_stream_t stream) {
   FALN_REQUIRE(g && x && dW && B > 0 && H > 0 && W > 0, "faln_conv3x3_wgrad: null pointer / bad shape");
   FALN_REQUIRE(stride == 1 || stride == 2, "faln_conv3x3_wgrad: stride must be 1 or 2");
   FALN_REQUIRE(Cg % 32 == 0 && Cxs % 32 == 0 && Cg > 0 && Cxs > 0, "faln_conv3x3_wgrad: channel strides must be multiples of 32");
@@ -238,28 +267,35 @@ extern "C" int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B
   p.B = B; p.Hg = Hg; p.Wg = Wg; p.stride = stride;
   p.tiles_w = (Wg + kTW - 1) / kTW; p.tiles_h = (Hg + kCR - 1) / kCR;
   p.chunks = B * p.tiles_w * p.tiles_h;
-  p.CB = XC == 32 ? 32 : (Cxs % 128 == 0 ? 128 : 64);
-  p.NB = GC == 32 ? 32 : (Cg % 128 == 0 ? 128 : 64);
-  p.n_cib = (Cx + p.CB - 1) / p.CB;       // blocks that contain written channels only
+  p.NB = GC;
+  p.n_cib = (Cx + XC - 1) / XC;       // blocks that contain written channels only
   p.n_cob = (Cout + p.NB - 1) / p.NB;
-  p.nb = p.CB / XC;
-  p.slots = 3 * p.nb;
   const int spr = 128 / XC;
-  p.slots_pad = (p.slots + spr - 1) / spr * spr;
-  p.irows = p.slots_pad / spr;
-  p.Cx = Cx; p.Cout = Cout; p.ci_off = ci_off; p.Cin_tot = Cin_tot; p.dW = dW;
+  p.irows = (9 + spr - 1) / spr;
+  p.halo = (stride == 1 && XC == 64 && !(flags & 1u)) ? 1 : 0;
   const int xbox = kP * XC * 2, gbox = kP * GC * 2;
-  const int stage_bytes = p.slots_pad * xbox + (p.NB / GC) * gbox;
+  if (p.halo) {
+    p.tx_x = kHaloW * kHaloH * 128;
+    // the dummy tenth tap of the last instruction row reads up to halo row (3 + 3) * 18 + 16: keep it inside the stage
+    p.x_bytes = ((((kCR - 1 + 3) * kHaloW + kTW) * 128) + 1023) / 1024 * 1024;
+  } else {
+    p.tx_x = 9 * xbox;
+    p.x_bytes = p.irows * spr * xbox;
+  }
+  p.Cx = Cx; p.Cout = Cout; p.ci_off = ci_off; p.Cin_tot = Cin_tot; p.dW = dW;
+  const int stage_bytes = p.x_bytes + gbox;
   p.stages = (200 * 1024) / stage_bytes;
-  if (p.stages > 6) p.stages = 6;
+  if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) p.stages = 2;
   const int smem = 256 + 1024 + p.stages * stage_bytes;
-  // split-K: about two waves of CTAs over the SMs, never more splits than chunks
-  int splits = (2 * sm_count()) / (3 * p.n_cib * p.n_cob);
-  if (splits > p.chunks) splits = p.chunks;
+  // split-K: about two CTAs per SM over the whole grid, at least ~4 chunks per CTA (prologue + epilogue amortisation)
+  const int nblk = p.n_cib * p.n_cob;
+  int splits = (2 * sm_count()) / nblk;
+  if (splits > p.chunks / 4) splits = p.chunks / 4;
   if (splits < 1) splits = 1;
   CUtensorMap mx, mg;
-  if (!make_act_map(&mx, x, B, H, W, Cxs, XC, stride, kCR) || !make_act_map(&mg, g, B, Hg, Wg, Cg, GC, 1, kCR)) {
+  const bool ok_x = p.halo ? make_halo_map(&mx, x, B, H, W, Cxs) : make_act_map(&mx, x, B, H, W, Cxs, XC, stride, kCR);
+  if (!ok_x || !make_act_map(&mg, g, B, Hg, Wg, Cg, GC, 1, kCR)) {
     set_error("faln_conv3x3_wgrad: cuTensorMapEncodeTiled failed (driver entry point missing or bad tensor geometry)");
     return FALN_ERR_LAUNCH;
   }

@@ -113,6 +113,46 @@ __global__ void __launch_bounds__(256) nhwc_to_planar_kernel(const __nv_bfloat16
   }
 }
 
+
+// Batched re-packing of the bf16 shadow weights for the data-gradient kernels: for every job (one 3x3 conv weight)
+//   src [Cout][9][Cin_tot]  (KRSC, the layout of the parameter arena)  ->  dst [Cin_used][9][Cout]  (one row per INPUT channel)
+// i.e. nine [Cout x Cin_used] -> [Cin_used x Cout] transposes through a padded 32x32 shared tile.  One launch per step
+// instead of ~4 ATen launches per layer.  jobs[j] = {src_off, dst_off, Cout, Cin_tot, Cin_used, tiles} (elements).
+__global__ void __launch_bounds__(256) pack_dgrad_kernel(const __nv_bfloat16* __restrict__ w16, __nv_bfloat16* __restrict__ wd16,
+                                                         const long long* __restrict__ jobs) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const long long* jb = jobs + (size_t)blockIdx.y * 6;
+  const int Cout = (int)jb[2], Cin_tot = (int)jb[3], Cin_used = (int)jb[4];
+  const int tco = Cout / 32, tci = Cin_used / 32;
+  const int ntiles = 9 * tco * tci;
+  if ((int)blockIdx.x >= ntiles) return;
+  const int t = blockIdx.x / (tco * tci), r = blockIdx.x % (tco * tci);
+  const int co0 = (r / tci) * 32, ci0 = (r % tci) * 32;
+  const __nv_bfloat16* src = w16 + jb[0];
+  __nv_bfloat16* dst = wd16 + jb[1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int co = co0 + ty + 8 * k;
+    tile[ty + 8 * k][tx] = src[((size_t)co * 9 + t) * Cin_tot + ci0 + tx];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ci = ci0 + ty + 8 * k;
+    dst[((size_t)ci * 9 + t) * Cout + co0 + tx] = tile[tx][ty + 8 * k];
+  }
+}
+
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4* __restrict__ src, __nv_bfloat162* __restrict__ dst,
+                                                          long long n4) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 v = src[i];
+    dst[2 * i] = __floats2bfloat162_rn(v.x, v.y);
+    dst[2 * i + 1] = __floats2bfloat162_rn(v.z, v.w);
+  }
+}
+
 }  // namespace
 }  // namespace faln
 
@@ -182,4 +222,26 @@ extern "C" int faln_nhwc_bf16_to_planar(const void* src, float* dst, int B, int 
   nhwc_to_planar_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(src), dst, C, H, W, Cp,
                                                              pitch);
   return after_launch("nhwc_to_planar_kernel");
+}
+
+extern "C" int faln_pack_dgrad_batched(const void* w16, void* wd16, const long long* jobs, int njobs, int max_tiles,
+                                       faln_stream_t stream) {
+  FALN_REQUIRE(w16 && wd16 && jobs && njobs > 0 && max_tiles > 0 && njobs <= 65535, "faln_pack_dgrad_batched: bad arguments");
+  dim3 grid(max_tiles, njobs);
+  pack_dgrad_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(w16),
+                                                          static_cast<__nv_bfloat16*>(wd16), jobs);
+  return after_launch("pack_dgrad_kernel");
+}
+
+extern "C" int faln_f32_to_bf16(const float* src, void* dst, long long n, faln_stream_t stream) {
+  FALN_REQUIRE(src && dst && n > 0 && (n & 3) == 0, "faln_f32_to_bf16: n must be a positive multiple of 4");
+  FALN_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0,
+               "faln_f32_to_bf16: buffers must be 16-byte aligned");
+  const long long n4 = n / 4;
+  long long grid = (n4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  f32_to_bf16_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(src),
+                                                               static_cast<__nv_bfloat162*>(dst), n4);
+  return after_launch("f32_to_bf16_kernel");
 }

@@ -37,14 +37,38 @@ class FlatAdamDDP:
             o += (s + 3) // 4 * 4                       # keep every tensor 16-byte aligned inside the arena
         self.n = (o + 3) // 4 * 4
         self.offsets = offs
+        self.shapes = [tuple(p.shape) for p in self.params]
         self.p = torch.zeros(self.n, device=dev, dtype=torch.float32)
         self.g = torch.zeros(self.n, device=dev, dtype=torch.float32)
         self.m = torch.zeros(self.n, device=dev, dtype=torch.float32)
         self.v = torch.zeros(self.n, device=dev, dtype=torch.float32)
-        for p, off, s in zip(self.params, offs, sizes):
-            self.p[off:off + s].copy_(p.data.reshape(-1))
-            p.data = self.p[off:off + s].view_as(p.data)
-            p.grad = self.g[off:off + s].view_as(p.data)
+        for i, p in enumerate(self.params):
+            view = self._view(self.p, i)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self._view(self.g, i)
+            p._faln_arena = (self, i)
+        # ---- bf16 shadow of the arena (kept current by the Adam kernel) and the per-step dgrad re-packing: 3x3 conv weights
+        # live in the arena in KRSC order, so the shadow IS the packed forward weight and the weight gradient is written
+        # coalesced; the [Cin,3,3,Cout] packs of the data-gradient kernels come from one batched transpose launch
+        self.w16 = self.wd16 = self._jobs = None
+        self._dgrad_off = {}
+        self._versions = [p._version for p in self.params]
+        if dev.type == "cuda":
+            self.w16 = torch.zeros(self.n, device=dev, dtype=torch.bfloat16)
+            jobs, o, max_tiles = [], 0, 1
+            for i, shp in enumerate(self.shapes):
+                if len(shp) == 4 and shp[2:] == (3, 3) and shp[0] % 32 == 0 and shp[1] >= 32:
+                    cout, cin = shp[0], shp[1]
+                    used = cin // 32 * 32
+                    jobs.append([offs[i], o, cout, cin, used, 0])
+                    self._dgrad_off[i] = (o, used)
+                    o += used * 9 * cout
+                    max_tiles = max(max_tiles, 9 * (cout // 32) * (used // 32))
+            self.wd16 = torch.zeros(max(o, 8), device=dev, dtype=torch.bfloat16)
+            self._jobs = torch.tensor(jobs, dtype=torch.int64, device=dev) if jobs else None
+            self._max_tiles = max_tiles
+            self.sync_shadow()
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.t = 0
         # device-side copy of (lr, step) for CUDA-graph replay (optim.adam_step_dev_); None on the CPU test path
@@ -83,6 +107,59 @@ class FlatAdamDDP:
             pass
 
     # ------------------------------------------------------------------------------------------
+    def _view(self, arena, i):
+        """Logical-shape view of parameter i inside ``arena``; 3x3 conv weights are stored KRSC (= torch.channels_last)."""
+        shp, off = self.shapes[i], self.offsets[i]
+        n = 1
+        for d in shp:
+            n *= d
+        flat = arena[off:off + n]
+        if len(shp) == 4 and shp[2:] == (3, 3):
+            return flat.view(shp[0], 3, 3, shp[1]).permute(0, 3, 1, 2)
+        return flat.view(shp)
+
+    def sync_shadow(self):
+        """Refresh the bf16 shadow and the dgrad packs from the fp32 arena (after anything but our Adam changed it)."""
+        if self.w16 is None:
+            return
+        from . import _lib
+        _lib.check(_lib.lib().faln_f32_to_bf16(_lib.ptr(self.p), _lib.ptr(self.w16), self.n, _lib.cur_stream()),
+                   "faln_f32_to_bf16")
+        self._repack_dgrad()
+        self._versions = [p._version for p in self.params]
+
+    def _repack_dgrad(self):
+        if self._jobs is None:
+            return
+        from . import _lib
+        _lib.check(_lib.lib().faln_pack_dgrad_batched(_lib.ptr(self.w16), _lib.ptr(self.wd16), _lib.ptr(self._jobs),
+                                                      self._jobs.shape[0], self._max_tiles, _lib.cur_stream()),
+                   "faln_pack_dgrad_batched")
+
+    def _fresh(self, i):
+        if self.params[i]._version != self._versions[i]:      # someone wrote the parameter through torch: re-derive
+            self.sync_shadow()
+
+    def packed_fwd(self, i, cin):
+        """bf16 [Cout,3,3,Cin] forward weight of parameter i straight out of the shadow arena, or None if the layer needs
+        an explicit pack (partial input-channel range, Cout not a multiple of 32)."""
+        shp = self.shapes[i]
+        if self.w16 is None or len(shp) != 4 or shp[2:] != (3, 3) or cin != shp[1] or shp[0] % 32 or shp[1] % 8:
+            return None
+        self._fresh(i)
+        off = self.offsets[i]
+        return self.w16[off:off + shp[0] * 9 * shp[1]].view(shp[0], 3, 3, shp[1])
+
+    def packed_dgrad(self, i, cin):
+        """bf16 [Cin_used,3,3,Cout] data-gradient weight of parameter i (refreshed once per step), or None."""
+        ent = self._dgrad_off.get(i)
+        if ent is None or ent[1] != cin:
+            return None
+        self._fresh(i)
+        o, used = ent
+        cout = self.shapes[i][0]
+        return self.wd16[o:o + used * 9 * cout].view(used, 3, 3, cout)
+
     # gradient-sink protocol used by backbone.backward
     def accepts(self, model):
         """True if this arena is where ``model``'s gradients live right now (p.grad aliases the arena)."""
@@ -92,9 +169,7 @@ class FlatAdamDDP:
         return p.grad is not None and p.grad.data_ptr() == self.g.data_ptr() + 4 * off
 
     def grad_view(self, name):
-        i = self._index[name]
-        p = self.params[i]
-        return self.g[self.offsets[i]:self.offsets[i] + p.numel()].view(p.shape)
+        return self._view(self.g, self._index[name])
 
     def mark_ready(self, name):
         if self.overlap:
@@ -119,14 +194,15 @@ class FlatAdamDDP:
 
     def zero_grad(self):
         self.g.zero_()
-        for p, off in zip(self.params, self.offsets):      # autograd may have replaced .grad; re-point it
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):      # autograd may have replaced .grad; re-point it
             if p.grad is None or p.grad.data_ptr() != self.g.data_ptr() + 4 * off:
-                p.grad = self.g[off:off + p.numel()].view_as(p.data)
+                p.grad = self._view(self.g, i)
         self._reset_counts()
 
     def broadcast_parameters(self, src=0):
         if self.world > 1:
             dist.broadcast(self.p, src=src, group=self.pg)
+            self.sync_shadow()
 
     def step(self):
         if self.world > 1:
@@ -141,11 +217,12 @@ class FlatAdamDDP:
                 dist.all_reduce(self.g, op=dist.ReduceOp.SUM, group=self.pg)
         self.t += 1
         if self.device_hp:
-            optim.adam_step_dev_(self.p, self.g, self.m, self.v, self.hp, None, beta1=self.betas[0], beta2=self.betas[1],
+            optim.adam_step_dev_(self.p, self.g, self.m, self.v, self.hp, self.w16, beta1=self.betas[0], beta2=self.betas[1],
                                  eps=self.eps, weight_decay=self.wd, grad_scale=1.0 / self.world)
         else:
-            self._update(self.p, self.g, self.m, self.v, None, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
+            self._update(self.p, self.g, self.m, self.v, self.w16, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
                          eps=self.eps, weight_decay=self.wd, step=self.t, grad_scale=1.0 / self.world)
+        self._repack_dgrad()
         from . import conv
         conv.invalidate_packed_weights()      # the arena changed behind torch's version counters
 

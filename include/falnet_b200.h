@@ -191,14 +191,24 @@ int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, const float* 
 int faln_conv3x3_dgrad(const void* g, const void* wd, void* gx, const void* residual, const void* ysave, int B, int H,
                        int W, int Cg, int Cx, int Cx_pad, int stride, int accum, int dact, int gx_c, int res_c,
                        int ysave_c, faln_stream_t stream);
+/* bf16 shadow of the flat fp32 parameter arena (what faln_adam keeps up to date): plain conversion, n % 4 == 0. */
+int faln_f32_to_bf16(const float* src, void* dst, long long n, faln_stream_t stream);
+/* Re-pack every 3x3 conv weight of the bf16 shadow arena for faln_conv3x3_dgrad in ONE launch:
+ * per job j, jobs[6j..] = {src_off, dst_off, Cout, Cin_tot, Cin_used, 0} (element offsets; Cout, Cin_used % 32 == 0):
+ *   w16 + src_off: [Cout][3][3][Cin_tot] (KRSC)  ->  wd16 + dst_off: [Cin_used][3][3][Cout].
+ * max_tiles >= max_j 9 * (Cout/32) * (Cin_used/32).  `jobs` is device memory. */
+int faln_pack_dgrad_batched(const void* w16, void* wd16, const long long* jobs, int njobs, int max_tiles,
+                            faln_stream_t stream);
 /* Weight gradient of the 3x3 convolution (pad 1, stride 1 or 2) on tcgen05 -- replaces the cuDNN wgrad autograd runs for
  * nn.Conv2d of /root/reference/models/FAL_netB.py:99-127 in loss.backward() (/root/reference/Train_Stage1_K.py:260).
- *   dW[co, ci_off + ci, kh, kw] += sum_{b,ho,wo} g[b,ho,wo,co] * x[b, ho*s+kh-1, wo*s+kw-1, ci]
+ *   dW[co, kh, kw, ci_off + ci] += sum_{b,ho,wo} g[b,ho,wo,co] * x[b, ho*s+kh-1, wo*s+kw-1, ci]
  * g [B,(H-1)/s+1,(W-1)/s+1,Cg] bf16 NHWC (pre-activation gradient), x [B,H,W,Cxs] bf16 NHWC (one source of a concatenated
- * input per call), dW [Cout,Cin_tot,3,3] fp32, ACCUMULATED with split-K fp32 reductions (zero it once per step).
- * Cg, Cxs: 32 or multiples of 64; Cout <= Cg and Cx <= Cxs select the channels actually written. */
+ * input per call), dW [Cout,3,3,Cin_tot] fp32 -- the KRSC memory of a torch.channels_last [Cout,Cin_tot,3,3] tensor --
+ * ACCUMULATED with split-K fp32 reductions (zero it once per step).
+ * Cg, Cxs: 32 or multiples of 64; Cout <= Cg and Cx <= Cxs select the channels actually written.
+ * flags: 0 normally; bit 0 disables the halo-tile path (validation only). */
 int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B, int H, int W, int Cg, int Cxs, int Cout, int Cx,
-                       int ci_off, int Cin_tot, int stride, faln_stream_t stream);
+                       int ci_off, int Cin_tot, int stride, unsigned flags, faln_stream_t stream);
 /* out [B,3,3,C] fp32 += sums of g [B,H,W,Cs] (bf16 NHWC) per sample over the 3x3 border classes (first / interior / last
  * row x column): the weight gradient of a spatially constant input channel (reference :145,208-209) is a 9-term
  * combination of these.  H, W >= 2. */

@@ -34,8 +34,10 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("flags", [0, 1])
 @pytest.mark.parametrize("B,H,W,Cxs,Cg,cout,cx,stride", CASES)
-def test_wgrad_matches_fp32(B, H, W, Cxs, Cg, cout, cx, stride):
+def test_wgrad_matches_fp32(B, H, W, Cxs, Cg, cout, cx, stride, flags):
+    """flags 0: production path (halo tile for stride-1 64-channel blocks); 1: nine boxes per chunk everywhere."""
     from fal_net_b200 import conv_native as CN
     torch.backends.cudnn.allow_tf32 = False
     dev = torch.device("cuda:0")
@@ -45,8 +47,8 @@ def test_wgrad_matches_fp32(B, H, W, Cxs, Cg, cout, cx, stride):
     g16 = torch.randn(B, Cg, Hg, Wg, device=dev, generator=g).to(torch.bfloat16).contiguous(memory_format=CL)
     ref = _ref_wgrad(x16, g16, cout, cx, stride)
     # write into columns [8, 8 + cx) of a wider gradient tensor that already holds something (accumulation semantics)
-    dW = torch.full((cout, cx + 16, 3, 3), 0.5, device=dev)
-    CN.conv3x3_wgrad(g16, x16, dW, cout=cout, cx=cx, ci_off=8, stride=stride)
+    dW = torch.full((cout, cx + 16, 3, 3), 0.5, device=dev).contiguous(memory_format=CL)
+    CN.conv3x3_wgrad(g16, x16, dW, cout=cout, cx=cx, ci_off=8, stride=stride, flags=flags)
     torch.cuda.synchronize()
     got = dW[:, 8:8 + cx] - 0.5
     scale = ref.abs().max()
