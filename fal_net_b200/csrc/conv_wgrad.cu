@@ -67,12 +67,14 @@ __device__ __forceinline__ uint32_t make_idesc_mn(int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-template <int XROWB, int GROWB>
+template <int XROWB, int GROWB, bool HALO>
 __global__ void __launch_bounds__(192)
 conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams p) {
   constexpr int XC = XROWB / 2;                        // channels per x box
+  constexpr int NB = GROWB / 2;                        // output channels per block = channels of the g box
   constexpr int XBOX = kP * XROWB, GBOX = kP * GROWB;  // bytes per (non-halo) box
   constexpr int SPR = 128 / XC;                        // taps per instruction row
+  constexpr int IROWS = (9 + SPR - 1) / SPR;           // instruction rows (5 for 64-channel blocks, 3 for 32-channel ones)
   extern __shared__ unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty = full + 8;
@@ -86,9 +88,8 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const int cib = blockIdx.y % p.n_cib, cob = blockIdx.y / p.n_cib;
   const int split = blockIdx.x, nsplit = gridDim.x;
   const int my_chunks = (p.chunks - split + nsplit - 1) / nsplit;  // chunks split, split + nsplit, ...
-  const uint32_t tmem_cols = (uint32_t)(p.irows * p.NB);
-  uint32_t alloc_cols = 32;
-  while (alloc_cols < tmem_cols) alloc_cols <<= 1;
+  constexpr uint32_t tmem_cols = IROWS * NB;
+  constexpr uint32_t alloc_cols = tmem_cols <= 32 ? 32 : tmem_cols <= 64 ? 64 : tmem_cols <= 128 ? 128 : tmem_cols <= 256 ? 256 : 512;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmX);
@@ -120,12 +121,13 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         unsigned char* xs = stages + (size_t)s * stage_bytes;
         unsigned char* gs = xs + p.x_bytes;
         mbar_arrive_expect_tx(&full[s], tx_bytes);
-        tma_load_4d(gs, &tmG, cob * p.NB, wo0, ho0, b, &full[s]);
-        if (p.halo) {
+        tma_load_4d(gs, &tmG, cob * NB, wo0, ho0, b, &full[s]);
+        if (HALO) {
           tma_load_4d(xs, &tmX, cib * XC, wo0 - 1, ho0 - 1, b, &full[s]);
         } else {
-          for (int t = 0; t < 9; ++t)
-            tma_load_4d(xs + t * XBOX, &tmX, cib * XC, wo0 * p.stride + t % 3 - 1, ho0 * p.stride + t / 3 - 1, b, &full[s]);
+          const int wi = wo0 * p.stride - 1, hi = ho0 * p.stride - 1;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) tma_load_4d(xs + t * XBOX, &tmX, cib * XC, wi + t % 3, hi + t / 3, b, &full[s]);
         }
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
@@ -133,31 +135,34 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   } else if (warp == 1) {
     // ================================================================= MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_mn(p.NB);
+      const uint32_t idesc = make_idesc_mn(NB);
+      // everything but the stage base address is a compile-time constant: descriptors are (template + base >> 4)
+      const uint64_t b_tmpl = make_desc_mn<GROWB>(0, GBOX);
+      const uint64_t a_tmpl_box = make_desc_mn<XROWB>(0, XBOX);
       int s = 0;
       uint32_t ph = 0;
       for (int it = 0; it < my_chunks; ++it) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t xs = smem_u32(stages + (size_t)s * stage_bytes);
-        const uint32_t gs = xs + p.x_bytes;
+        const uint64_t xs16 = (uint64_t)(xs >> 4), gs16 = (uint64_t)((xs + p.x_bytes) >> 4);
 #pragma unroll
         for (int k = 0; k < kP / 16; ++k) {
           // K-step k = the 16 pixels of chunk row k: two 8-pixel atoms, 8 swizzle rows apart (SBO)
-          const uint64_t bdesc = make_desc_mn<GROWB>(gs + k * 16 * GROWB, GBOX);
-          for (int j = 0; j < p.irows; ++j) {
+          const uint64_t bdesc = b_tmpl + gs16 + (uint64_t)(k * 16 * GROWB / 16);
+#pragma unroll
+          for (int j = 0; j < IROWS; ++j) {
             uint64_t adesc;
-            if (p.halo) {
+            if (HALO) {
               // instruction row j = taps 2j, 2j+1: windows of the halo tile starting at halo row (k + kh) * 18 + kw
               const int t0 = 2 * j, t1 = 2 * j + 1;
               const uint32_t o0 = (uint32_t)(((k + t0 / 3) * kHaloW + t0 % 3) * XROWB);
               const uint32_t o1 = (uint32_t)(((k + t1 / 3) * kHaloW + t1 % 3) * XROWB);
-              const uint32_t start = xs + o0;
-              adesc = make_desc_mn<XROWB>(start, o1 - o0);
+              adesc = make_desc_mn<XROWB>(0, o1 - o0) + xs16 + (uint64_t)(o0 >> 4);
             } else {
-              adesc = make_desc_mn<XROWB>(xs + j * SPR * XBOX + k * 16 * XROWB, XBOX);
+              adesc = a_tmpl_box + xs16 + (uint64_t)((j * SPR * XBOX + k * 16 * XROWB) >> 4);
             }
-            umma_bf16(tmem_base + j * p.NB, adesc, bdesc, idesc, (it | k) != 0);
+            umma_bf16(tmem_base + j * NB, adesc, bdesc, idesc, (it | k) != 0);
           }
         }
         umma_commit(&empty[s]);
@@ -171,15 +176,20 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int m = quad * 32 + lane;   // accumulator row inside an instruction row
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    for (int j = 0; j < p.irows; ++j) {
+    // CTAs of the same channel block reduce into the same addresses: start each split at a different (row, column
+    // group) so they do not sweep the output in lock-step
+    constexpr int kSteps = IROWS * (NB / 32);
+    for (int q = 0; q < kSteps; ++q) {
+      const int step = (q + split) % kSteps;
+      const int j = step / (NB / 32), c0 = (step % (NB / 32)) * 32;
       const int tap = j * SPR + m / XC;
       const int ci = cib * XC + (m % XC);
       const bool row_ok = tap < 9 && ci < p.Cx;
-      for (int c0 = 0; c0 < p.NB; c0 += 32) {
+      {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + j * p.NB + c0, r);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + j * NB + c0, r);
         if (!row_ok) continue;
-        const int co0 = cob * p.NB + c0;
+        const int co0 = cob * NB + c0;
         float* dst = p.dW + ((size_t)co0 * 9 + tap) * p.Cin_tot + p.ci_off + ci;
 #pragma unroll
         for (int n = 0; n < 32; ++n)
@@ -195,9 +205,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   }
 }
 
-template <int XROWB, int GROWB>
+template <int XROWB, int GROWB, bool HALO>
 int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mg, const WgradParams& p, int splits, int smem, cudaStream_t st) {
-  auto kern = conv3x3_wgrad_kernel<XROWB, GROWB>;
+  auto kern = conv3x3_wgrad_kernel<XROWB, GROWB, HALO>;
   static int attr_set = 0;
   if (attr_set < smem) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -300,10 +310,12 @@ extern "C" int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B
     return FALN_ERR_LAUNCH;
   }
   cudaStream_t st = as_stream(stream);
-  if (XC == 64 && GC == 64) return launch_wgrad<128, 128>(mx, mg, p, splits, smem, st);
-  if (XC == 32 && GC == 64) return launch_wgrad<64, 128>(mx, mg, p, splits, smem, st);
-  if (XC == 64 && GC == 32) return launch_wgrad<128, 64>(mx, mg, p, splits, smem, st);
-  return launch_wgrad<64, 64>(mx, mg, p, splits, smem, st);
+  if (XC == 64 && GC == 64)
+    return p.halo ? launch_wgrad<128, 128, true>(mx, mg, p, splits, smem, st) : launch_wgrad<128, 128, false>(mx, mg, p, splits, smem, st);
+  if (XC == 64 && GC == 32)
+    return p.halo ? launch_wgrad<128, 64, true>(mx, mg, p, splits, smem, st) : launch_wgrad<128, 64, false>(mx, mg, p, splits, smem, st);
+  if (XC == 32 && GC == 64) return launch_wgrad<64, 128, false>(mx, mg, p, splits, smem, st);
+  return launch_wgrad<64, 64, false>(mx, mg, p, splits, smem, st);
 }
 
 // out [B,3,3,C] fp32 += per-sample sums of g [B,H,W,Cs] (bf16 NHWC, channels [0,C)) over the nine border classes
