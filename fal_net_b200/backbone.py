@@ -132,6 +132,17 @@ def forward(model, image, max_disp, tape=None):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(dev):
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return st
+
+
 class _DictSink:
     """Gradient destination when no flat arena is attached: fresh zeroed fp32 tensors, returned to autograd."""
 
@@ -161,19 +172,41 @@ def backward(model, tape, g_logits, sink=None):
     dev = g_logits.device
     sink = sink or _DictSink(model, dev)
 
-    def bias_grad(name, g, C):
-        CN.channel_sum(g, sink.grad_view(name), C)
-        sink.mark_ready(name)
+    # Parameter gradients are off the critical path (only the data-gradient chain feeds the next layer): they run on a
+    # side stream, ordered after their producer by an event, and are joined before returning.  Inside a CUDA-graph capture
+    # this becomes a parallel branch of the graph, so the latency-bound small layers of both chains overlap.
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    keep = []                                                  # tensors the side stream reads stay alive until the join
 
-    def wgrad(name, g_pre, sources, cout, stride=1):
-        """sources: the conv's (concatenated) inputs, in channel order."""
-        dW = sink.grad_view(name)
-        off = 0
-        for x in sources:
-            cx = min(x.shape[1], dW.shape[1] - off)
-            CN.conv3x3_wgrad(g_pre, x, dW, cout=cout, cx=cx, ci_off=off, stride=stride)
-            off += cx
-        return dW
+    def on_side(fn, *tensors):
+        keep.extend(tensors)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            fn()
+
+    def bias_grad(name, g, C):
+        def run():
+            CN.channel_sum(g, sink.grad_view(name), C)
+            sink.mark_ready(name)
+        on_side(run, g)
+
+    def wgrad(name, g_pre, sources, cout, stride=1, const=None):
+        """sources: the conv's (concatenated) inputs, in channel order; const = (value[B], in_hw) of a trailing constant
+        input plane."""
+        def run():
+            dW = sink.grad_view(name)
+            off = 0
+            for x in sources:
+                cx = min(x.shape[1], dW.shape[1] - off)
+                CN.conv3x3_wgrad(g_pre, x, dW, cout=cout, cx=cx, ci_off=off, stride=stride)
+                off += cx
+            if const is not None:
+                dW[:, off].add_(CN.const_channel_wgrad(g_pre, const[0], const[1], stride, cout))
+            sink.mark_ready(name)
+        on_side(run, g_pre, *sources)
 
     # ---------------------------------------------------------------- folded logits conv (iconv1 o conv0)
     Np = (N + 31) // 32 * 32
@@ -182,15 +215,18 @@ def backward(model, tape, g_logits, sink=None):
     s0 = tape["conv0"][2]
     wf = tape["wf"]
     bias_grad("conv0.bias", g, N)
-    gwf = torch.zeros(N, 3, 3, u.shape[1] + s0.shape[1], device=dev, dtype=torch.float32).permute(0, 3, 1, 2)   # folded weight
-    CN.conv3x3_wgrad(g, u, gwf, cout=N, ci_off=0)
-    CN.conv3x3_wgrad(g, s0, gwf, cout=N, ci_off=u.shape[1])
-    w0 = model.conv0.weight.detach()[:, :, 0, 0]
-    wi1 = bb.iconv1.weight.detach()
-    sink.grad_view("conv0.weight").add_(torch.einsum("ockl,mckl->om", gwf, wi1)[:, :, None, None])
-    sink.mark_ready("conv0.weight")
-    sink.grad_view("backbone.iconv1.weight").add_(torch.einsum("om,ockl->mckl", w0, gwf))
-    sink.mark_ready("backbone.iconv1.weight")
+
+    def folded():
+        gwf = torch.zeros(N, 3, 3, u.shape[1] + s0.shape[1], device=dev, dtype=torch.float32).permute(0, 3, 1, 2)
+        CN.conv3x3_wgrad(g, u, gwf, cout=N, ci_off=0)
+        CN.conv3x3_wgrad(g, s0, gwf, cout=N, ci_off=u.shape[1])
+        w0 = model.conv0.weight.detach()[:, :, 0, 0]
+        wi1 = bb.iconv1.weight.detach()
+        sink.grad_view("conv0.weight").add_(torch.einsum("ockl,mckl->om", gwf, wi1)[:, :, None, None])
+        sink.mark_ready("conv0.weight")
+        sink.grad_view("backbone.iconv1.weight").add_(torch.einsum("om,ockl->mckl", w0, gwf))
+        sink.mark_ready("backbone.iconv1.weight")
+    on_side(folded, g, u, s0)
     wd = CN.pack_weight_dgrad(wf)                                                # [96,3,3,Np]
     C1 = u.shape[1]
     g_u = CN.conv3x3_dgrad(g, wd, (H, W), rows=(0, C1), dact=1, ysave=u)
@@ -208,14 +244,12 @@ def backward(model, tape, g_logits, sink=None):
             cout = ic.weight.shape[0]
             bias_grad(f"backbone.iconv{lvl}.0.bias", g_h, cout)
             wgrad(f"backbone.iconv{lvl}.0.weight", g_h, (u, skip), cout)
-            sink.mark_ready(f"backbone.iconv{lvl}.0.weight")
             wd = _wd(ic.weight)
             C1 = u.shape[1]
             hw = (u.shape[2], u.shape[3])
             g_u = CN.conv3x3_dgrad(g_h, wd, hw, rows=(0, C1), dact=1, ysave=u)
             G_skip[lvl - 1] = CN.conv3x3_dgrad(g_h, wd, hw, rows=(C1, skip.shape[1]))
         wgrad(f"backbone.deconv{lvl}.conv1.weight", g_u, (xu,), up.conv1.weight.shape[0])
-        sink.mark_ready(f"backbone.deconv{lvl}.conv1.weight")
         g_xu = CN.conv3x3_dgrad(g_u, _wd(up.conv1.weight), (xu.shape[2], xu.shape[3]))
         # nearest-upsample backward fused with ELU' of the producer (h_{l+1}, or the bottleneck skip s6 for level 6)
         g_h = CN.upsample_nearest_bwd(g_xu, (h_in.shape[2], h_in.shape[3]), ysave=h_in, dact=1)
@@ -230,10 +264,8 @@ def backward(model, tape, g_logits, sink=None):
         blk = getattr(bb, name + "_1")
         hw = (a.shape[2], a.shape[3])
         wgrad(f"backbone.{name}_1.conv2.weight", g_s, (r,), cout)
-        sink.mark_ready(f"backbone.{name}_1.conv2.weight")
         g_r = CN.conv3x3_dgrad(g_s, _wd(blk.conv2.weight), hw, dact=1, ysave=r)
         wgrad(f"backbone.{name}_1.conv1.weight", g_r, (a,), cout)
-        sink.mark_ready(f"backbone.{name}_1.conv1.weight")
         g_a = CN.conv3x3_dgrad(g_r, _wd(blk.conv1.weight), hw, dact=1, ysave=a, residual=g_s)   # (dgrad + skip path) * ELU'
         bias_grad(f"backbone.{name}.0.bias", g_a, cout)
         wname = f"backbone.{name}.0.weight"
@@ -241,18 +273,18 @@ def backward(model, tape, g_logits, sink=None):
             # the 3-channel image as a 32-channel (zero-padded) bf16 NHWC tensor: same tensor-core path, cx = 3
             img16 = layout.planar_to_nhwc_bf16(tape["image"].float().contiguous(), 32).permute(0, 3, 1, 2)
             wgrad(wname, g_a, (img16,), cout)
-            sink.mark_ready(wname)
             break
         prev = tape[ENC[i - 1][0]][2]
         Cp = prev.shape[1]
-        dW = wgrad(wname, g_a, (prev,), cout, stride)
-        if i == 1:                                                                # the constant max_disp/100 input plane
-            dW[:, Cp].add_(CN.const_channel_wgrad(g_a, tape["flow_val"], (prev.shape[2], prev.shape[3]), stride, cout))
-        sink.mark_ready(wname)
+        # conv1.0's 33rd input is the constant max_disp/100 plane
+        wgrad(wname, g_a, (prev,), cout, stride,
+              const=(tape["flow_val"], (prev.shape[2], prev.shape[3])) if i == 1 else None)
         # stride-2 dgrad into the previous skip: add to what the decoder left there, then ELU'(s_{i-1})
         g_s = CN.conv3x3_dgrad(g_a, _wd(head.weight, Cp), (prev.shape[2], prev.shape[3]), stride=stride,
                                out=G_skip.pop(i - 1), accum=True, dact=1, ysave=prev)
         del g_r, g_a
+    main.wait_stream(side)                                                        # join: gradients complete, `keep` may go
+    del keep
     return sink
 
 
