@@ -1,196 +1,35 @@
-"""Convolution front-end of the encoder-decoder and the VGG perceptual slices.
+"""VGG19 perceptual slices (/root/reference/loss_functions.py:7-44) on the tcgen05 convolution kernels.
 
-Activations are bf16 tensors of logical shape [B,C,H,W] in ``torch.channels_last`` memory format, i.e. NHWC
-in memory -- the layout the tcgen05 implicit-GEMM kernels (csrc/conv_tc.cu) consume through TMA.
+Activations are bf16 tensors of logical shape [B,C,H,W] in ``torch.channels_last`` memory format, i.e. NHWC in memory --
+the layout the implicit-GEMM kernels (csrc/conv_tc.cu) consume through TMA.
 
-FORWARD is always the hand-written sm_100a path: the stem kernel for the 3-channel image, tcgen05/TMEM
-implicit GEMM for every other 3x3 conv with bias / ELU / ReLU / residual fused in the epilogue, the skip
-concatenation expressed as a second TMA source (no torch.cat), the constant max_disp/100 plane folded into
-a border-class bias table, and the logit 1x1 conv folded into the last 3x3 conv whose epilogue writes fp32
-planar logits.
-
-BACKWARD (round 1 status): data- and weight-gradients of the convolutions are still computed with
-``aten.convolution_backward`` (cuDNN, bf16) -- counted in ``LIBRARY_CALLS`` so bench.py reports how much of
-the step is library code.  Native tcgen05 dgrad / wgrad kernels are the next milestone.  Nothing here
-runs without CUDA.
+The three slices are ONE autograd node with a hand-scheduled backward (like fal_net_b200.backbone): the network is
+frozen (reference :33-34), so backward is the data-gradient chain only -- ``faln_conv3x3_dgrad`` with the ReLU
+derivative, the pool-output gradients of the shallower slices and the max-pool routing fused into epilogues / one small
+kernel each -- down to the fp32 gradient of the input image.  No cuDNN, no ATen elementwise glue.  Nothing here runs
+without CUDA.
 """
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 from . import conv_native as CN
+from . import layout
 
-LIBRARY_CALLS = {"conv_backward": 0}
-
-# packed bf16 KRSC weights are cached ON the parameter object (attribute ``_faln_packed``), tagged with
-# (param._version, generation, cin): parameters that do not change (frozen Stage-1 model, VGG, inference) are packed
-# once; the trainer bumps GENERATION after each fused-Adam step because the kernel updates the arena behind torch's
-# version counter.  (A dict keyed by id(param) is wrong: ids are recycled when a model is freed.)
+# Re-packed bf16 weights are cached ON the parameter object, tagged with (param._version, generation): parameters that do
+# not change (frozen Stage-1 model, VGG, inference) are packed once; the trainer bumps GENERATION after each fused-Adam
+# step because that kernel updates the arena behind torch's version counter.  (A dict keyed by id(param) is wrong: ids
+# are recycled when a model is freed.)
 GENERATION = [0]
+LIBRARY_CALLS = {"conv_backward": 0}     # stays 0: kept so bench.py can report that no library convolution ran
 
 
 def invalidate_packed_weights():
     GENERATION[0] += 1
 
 
-def _packed(weight, cin, tag):
-    if weight.grad_fn is not None:                   # derived tensor (the folded logit conv): pack every call
-        return CN.pack_weight(weight[:, :cin])
-    key = (weight._version, GENERATION[0] if weight.requires_grad else -1, cin, tag, weight.data_ptr())
-    cache = getattr(weight, "_faln_packed", None)
-    if cache is None or cache[0] != key:
-        cache = (key, CN.pack_weight(weight[:, :cin]))
-        weight._faln_packed = cache
-    return cache[1]
-
-
 CL = torch.channels_last
 _ACT = CN.ACT
-
-
-def input_to_nhwc(x: torch.Tensor) -> torch.Tensor:
-    """fp32 NCHW image -> bf16 NHWC activation (only used where the stem kernel is not)."""
-    return x.to(dtype=torch.bfloat16, memory_format=CL)
-
-
-def _act_grad(g, y, act):
-    """gradient w.r.t. the pre-activation, from the (saved) activation output y."""
-    if act == 1:                                   # ELU: d/dx = 1 (x>0) else exp(x) = y + 1
-        return g * torch.where(y > 0, torch.ones_like(y), y + 1)
-    if act == 2:
-        return g * (y > 0).to(g.dtype)
-    return g
-
-
-def _conv_backward(g_pre, xin, w16, want_x, want_w, want_b, stride):
-    LIBRARY_CALLS["conv_backward"] += 1
-    return torch.ops.aten.convolution_backward(g_pre, xin, w16, [w16.shape[0]] if want_b else None, [stride, stride],
-                                               [1, 1], [1, 1], False, [0, 0], 1, [want_x, want_w, want_b])
-
-
-class _Conv3x3(torch.autograd.Function):
-    """y = act(conv3x3(cat(up(x), x2, const)) + bias + residual); forward native, backward see module docstring."""
-
-    @staticmethod
-    def forward(ctx, x, x2, residual, weight, bias, const_val, stride, act, up_to, planar):
-        xu = CN.upsample_nearest(x, up_to) if up_to is not None else x.contiguous(memory_format=CL)
-        C1 = xu.shape[1]
-        C2 = x2.shape[1] if x2 is not None else 0
-        ctab = None
-        if const_val is not None:
-            ctab = CN.const_channel_table(weight[:, C1 + C2].detach())
-            const_val = const_val.detach().float().contiguous()
-        wk = _packed(weight, C1 + C2, "w")
-        if planar:
-            from . import layout
-            B, _, H, W = xu.shape
-            out = layout.alloc_planar(B, weight.shape[0], H, W, xu.device)
-            y = CN.conv3x3_fwd(xu, wk, bias, stride, act, None, x2, cout=weight.shape[0], planar_out=out)
-        else:
-            y = CN.conv3x3_fwd(xu, wk, bias, stride, act, residual, x2, cout=weight.shape[0], ctab=ctab, cscale=const_val)
-        ctx.save_for_backward(x, xu if up_to is not None else None, x2, weight, const_val, y if act else None)
-        ctx.cfg = (stride, act, up_to, bias is not None, residual is not None, planar)
-        return y
-
-    @staticmethod
-    def backward(ctx, g):
-        x, xu, x2, weight, const_val, y = ctx.saved_tensors
-        stride, act, up_to, has_bias, has_res, planar = ctx.cfg
-        if planar:
-            g = g.to(dtype=torch.bfloat16, memory_format=CL)
-        else:
-            g = g.contiguous(memory_format=CL)
-        g_pre = _act_grad(g, y, act).contiguous(memory_format=CL)
-        src = xu if xu is not None else x
-        parts = [src.contiguous(memory_format=CL)]
-        if x2 is not None:
-            parts.append(x2)
-        if const_val is not None:
-            B, _, H, W = src.shape
-            parts.append(const_val.to(src.dtype).view(B, 1, 1, 1).expand(B, 1, H, W))
-        xin = parts[0] if len(parts) == 1 else torch.cat(parts, 1).contiguous(memory_format=CL)
-        need_x = ctx.needs_input_grad[0] or (x2 is not None and ctx.needs_input_grad[1])
-        gx, gw, gb = _conv_backward(g_pre, xin, weight.to(torch.bfloat16), need_x, ctx.needs_input_grad[3],
-                                    has_bias and ctx.needs_input_grad[4], stride)
-        g_x = g_x2 = None
-        if need_x:
-            C1 = src.shape[1]
-            g_src = gx[:, :C1]
-            if x2 is not None and ctx.needs_input_grad[1]:
-                g_x2 = gx[:, C1:C1 + x2.shape[1]]
-            if ctx.needs_input_grad[0]:
-                if up_to is not None and tuple(x.shape[2:]) != tuple(up_to):
-                    g_x = torch.ops.aten.upsample_nearest2d_backward(g_src.contiguous(memory_format=CL), list(up_to),
-                                                                     list(x.shape), None, None)
-                else:
-                    g_x = g_src
-        g_res = g_pre if (has_res and ctx.needs_input_grad[2]) else None
-        return (g_x, g_x2, g_res, None if gw is None else gw.float(), None if gb is None else gb.float(), None, None,
-                None, None, None)
-
-
-class _Stem(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, weight, bias, act):
-        y = CN.stem_conv(x, weight, bias, act)
-        ctx.save_for_backward(x, weight, y if act else None)
-        ctx.cfg = (act, bias is not None)
-        return y
-
-    @staticmethod
-    def backward(ctx, g):
-        x, weight, y = ctx.saved_tensors
-        act, has_bias = ctx.cfg
-        g_pre = _act_grad(g.contiguous(memory_format=CL), y, act).contiguous(memory_format=CL)
-        gx, gw, gb = _conv_backward(g_pre, input_to_nhwc(x), weight.to(torch.bfloat16), ctx.needs_input_grad[0],
-                                    ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2], 1)
-        return (None if gx is None else gx.float().contiguous(), None if gw is None else gw.float(),
-                None if gb is None else gb.float(), None)
-
-
-class _MaxPool2(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x):
-        y = CN.maxpool2(x)
-        ctx.save_for_backward(x)
-        return y
-
-    @staticmethod
-    def backward(ctx, g):
-        (x,) = ctx.saved_tensors
-        with torch.enable_grad():
-            xr = x.detach().requires_grad_(True)
-            F.max_pool2d(xr, 2, 2).backward(g)
-        return xr.grad
-
-
-def stem(x, weight, bias, act="elu"):
-    """First layer on the fp32 NCHW image (reads it directly, writes bf16 NHWC)."""
-    return _Stem.apply(x, weight, bias, _ACT[act])
-
-
-def conv3x3(x, weight, bias=None, stride=1, act=None, residual=None, const_channel=None, upsample_to=None, concat=None):
-    """y = act(conv3x3(gather(x)) + bias [+ residual]), pad 1.
-
-    gather(x) = nearest-upsample to ``upsample_to`` (reference deconv, models/FAL_netB.py:58), channel concat with
-    ``concat`` (skip connection, :153-173) and/or with a per-sample constant plane ``const_channel`` [B] (the
-    max_disp/100 "flow" channel, :145,208-209)."""
-    return _Conv3x3.apply(x, concat, residual, weight, bias, const_channel, stride, _ACT[act], upsample_to, False)
-
-
-def fold_logit_conv(w_iconv1, w0, b0):
-    """iconv1 (3x3, no bias, no activation; reference :127,174) followed by conv0 (1x1 + bias; :190,215)
-    == one 3x3 conv with W'[o,c,kh,kw] = sum_m W0[o,m] * W_iconv1[m,c,kh,kw] and bias b0."""
-    return torch.einsum("om,mckl->ockl", w0[:, :, 0, 0], w_iconv1), b0
-
-
-def conv3x3_logits(u, skip, w_iconv1, w0, b0):
-    """Last layer: (u, skip) as two TMA sources -> folded 3x3 conv -> fp32 planar logits [B,N,H,W] (row pitch a
-    multiple of 16 bytes), written straight from the fp32 accumulator."""
-    w, b = fold_logit_conv(w_iconv1, w0, b0)
-    return _Conv3x3.apply(u, skip, None, w, b, None, 1, 0, None, True)
-
 
 # ------------------------------------------------------------------------------------------------
 # VGG19 features[0:19] (the three pooled activations of /root/reference/loss_functions.py:21-29,36-44)
@@ -198,15 +37,92 @@ def conv3x3_logits(u, skip, w_iconv1, w0, b0):
 VGG_CFG = (64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M")
 
 
-def vgg_features(ws, x):
-    """ws: list of (weight fp32 [Co,Ci,3,3], bias fp32 [Co]) for the 8 convs; x fp32 NCHW image [B,3,H,W]."""
+def _vgg_pack(w, tag, fn):
+    key = (w._version, w.data_ptr(), tag)
+    cache = getattr(w, "_faln_packs", None)
+    if cache is None:
+        cache = w._faln_packs = {}
+    if cache.get("key_" + tag) != key:
+        cache["key_" + tag] = key
+        cache[tag] = fn()
+    return cache[tag]
+
+
+def _vgg_forward(ws, x, tape=None):
     outs, i = [], 0
     for v in VGG_CFG:
         if v == "M":
-            x = _MaxPool2.apply(x)
+            y = CN.maxpool2(x)
+            if tape is not None:
+                tape.append(("pool", x))
+            x = y
             outs.append(x)
         else:
             w, b = ws[i]
-            x = stem(x, w, b, "relu") if i == 0 else conv3x3(x, w, b, act="relu")
+            if i == 0:
+                y = CN.stem_conv(x, w, b, _ACT["relu"])
+            else:
+                y = CN.conv3x3_fwd(x, _vgg_pack(w, "fwd", lambda: CN.pack_weight(w)), b, 1, _ACT["relu"])
+            if tape is not None:
+                tape.append(("conv", i, y))
+            x = y
             i += 1
     return outs
+
+
+class _VggFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, *flat_ws):
+        ws = list(zip(flat_ws[0::2], flat_ws[1::2]))
+        tape = []
+        outs = _vgg_forward(ws, x, tape)
+        ctx.tape, ctx.ws, ctx.in_shape = tape, ws, x.shape
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *g_outs):
+        tape, ws = ctx.tape, ctx.ws
+        ctx.tape = None
+        g_outs = [None if t is None else t.to(torch.bfloat16).contiguous(memory_format=CL) for t in g_outs]
+        g = None                                     # gradient w.r.t. the tensor produced by the tape entry being visited
+        for k in range(len(tape) - 1, -1, -1):
+            ent = tape[k]
+            if ent[0] == "pool":
+                x = ent[1]                           # the pool's input = ReLU output of the previous conv
+                if g is None:                        # deepest slice: only its own output gradient arrives here
+                    g = g_outs.pop()
+                    if g is None:
+                        g = torch.zeros((x.shape[0], x.shape[1], x.shape[2] // 2, x.shape[3] // 2), device=x.device,
+                                        dtype=torch.bfloat16).contiguous(memory_format=CL)
+                # max-pool routing fused with ReLU'(x): g becomes the gradient w.r.t. the previous conv's PRE-activation
+                g = CN.maxpool2_bwd(x, g, dact=2)
+            else:
+                _, i, y = ent
+                hw = (y.shape[2], y.shape[3])
+                if i == 0:
+                    # stem (3 -> 64): data gradient on the tensor-core path with the 3 input channels padded to 32
+                    w = ws[0][0]
+                    wd = _vgg_pack(w, "dgrad", lambda: CN.pack_weight_dgrad(w, cin_pad=32))
+                    gx = CN.conv3x3_dgrad(g, wd, hw)
+                    gx = layout.nhwc_bf16_to_planar(gx.permute(0, 2, 3, 1), 3, pitch=hw[1])
+                    return (gx.contiguous(),) + (None,) * (2 * len(ws))
+                w = ws[i][0]
+                wd = _vgg_pack(w, "dgrad", lambda: CN.pack_weight_dgrad(w))
+                prev = tape[k - 1]
+                if prev[0] == "conv":                # producer is conv + ReLU: fuse ReLU'(its saved output)
+                    g = CN.conv3x3_dgrad(g, wd, hw, dact=2, ysave=prev[2])
+                else:                                # producer is a pool, whose output is also a slice output: the
+                    g_own = g_outs.pop() if g_outs else None               # epilogue adds that slice's own gradient
+                    g = CN.conv3x3_dgrad(g, wd, hw, residual=g_own)
+        raise AssertionError("unreachable")
+
+
+def vgg_features(ws, x):
+    """ws: list of (weight fp32 [Co,Ci,3,3], bias fp32 [Co]) for the 8 convs; x fp32 NCHW image [B,3,H,W].
+    Returns the three pooled activations (bf16 channels_last)."""
+    if not x.is_cuda:
+        raise RuntimeError("fal_net_b200 VGG features run on CUDA (sm_100a) only; there is no CPU path")
+    if torch.is_grad_enabled() and x.requires_grad:
+        flat = [t for wb in ws for t in wb]
+        return list(_VggFn.apply(x, *flat))
+    return _vgg_forward(ws, x)
