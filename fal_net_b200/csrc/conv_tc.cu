@@ -16,6 +16,9 @@
 //   * a second (concatenated) source is just more K steps with its own tensor map: torch.cat never happens
 //   * epilogue warps read TMEM with tcgen05.ld, add bias / residual, apply ELU / ReLU, and write either bf16
 //     NHWC or fp32 planar (the logits layout the MED kernels stream).
+#include <cstdio>
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace faln {
@@ -38,7 +41,7 @@ struct ConvParams {
   int stride, act, planar; // stride = element stride of the input box
   int tiles_w, tiles_h;
   int kblocks1, kblocks2;  // BK-channel blocks of source 1 / source 2
-  int ncls;
+  int ncls, nblk;         // tap classes, N blocks of BN output channels
   TapClass cls[4];
   int out_mul, out_H, out_W;  // output pixel = (r * out_mul + oh, c * out_mul + ow) inside an out_H x out_W image
   int accum;                  // 1: add to what the output tensor already holds (gradient accumulation)
@@ -82,26 +85,127 @@ struct SmemLayout {
   static constexpr int kTotal = kBars + STAGES * kStage + 1024 /* alignment slack */;
 };
 
+// Epilogue of CW (32 or 16) consecutive output channels of one pixel: accumulator registers r -> bias / constant-channel
+// table / accumulate / residual / activation / activation derivative -> bf16 NHWC or fp32 planar store.
+template <int CW>
+__device__ __forceinline__ void epilogue_store(const ConvParams& p, const uint32_t (&r)[CW], int cg, size_t pix, int b, int ho,
+                                               int wo) {
+    float v[CW];
+#pragma unroll
+    for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < CW; ++j)
+        if (cg + j < p.Cout) v[j] += __ldg(p.bias + cg + j);
+    }
+    if (p.ctab) {
+      // a spatially constant extra input channel (the max_disp/100 plane of reference :145,208-209) contributes
+      // value * (sum of its weights over the taps that fall inside the image): a per-border-class bias
+      const int rc = (ho == 0 ? 1 : 0) | (p.stride * ho + 1 > p.H - 1 ? 2 : 0);
+      const int cc = (wo == 0 ? 1 : 0) | (p.stride * wo + 1 > p.W - 1 ? 2 : 0);
+      const float* t = p.ctab + (size_t)(rc * 4 + cc) * p.Cout + cg;
+      const float sc = __ldg(p.cscale + b);
+#pragma unroll
+      for (int j = 0; j < CW; ++j)
+        if (cg + j < p.Cout) v[j] = fmaf(sc, __ldg(t + j), v[j]);
+    }
+    if (p.accum) {
+      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.out) + pix * p.out_c + cg);
+#pragma unroll
+      for (int q = 0; q < CW / 8; ++q) {
+        uint4 u = rp[q];
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __bfloat1622float2(h2[e]);
+          v[q * 8 + 2 * e] += f.x;
+          v[q * 8 + 2 * e + 1] += f.y;
+        }
+      }
+    }
+    if (p.residual) {
+      const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.res_c + cg);
+#pragma unroll
+      for (int q = 0; q < CW / 8; ++q) {
+        uint4 u = __ldg(rp + q);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __bfloat1622float2(h2[e]);
+          v[q * 8 + 2 * e] += f.x;
+          v[q * 8 + 2 * e + 1] += f.y;
+        }
+      }
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) v[j] = elu1(v[j]);
+    } else if (p.act == 2) {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.dact) {
+      // backward epilogue: gradient w.r.t. the pre-activation = gradient * act'(pre), from the SAVED OUTPUT y:
+      // ELU'(pre) = 1 (y > 0) else y + 1;  ReLU'(pre) = [y > 0]
+      const uint4* yp = reinterpret_cast<const uint4*>(p.ysave + pix * p.ysave_c + cg);
+#pragma unroll
+      for (int q = 0; q < CW / 8; ++q) {
+        uint4 u = __ldg(yp + q);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __bfloat1622float2(h2[e]);
+          const float d0 = f.x > 0.f ? 1.f : (p.dact == 1 ? f.x + 1.f : 0.f);
+          const float d1 = f.y > 0.f ? 1.f : (p.dact == 1 ? f.y + 1.f : 0.f);
+          v[q * 8 + 2 * e] *= d0;
+          v[q * 8 + 2 * e + 1] *= d1;
+        }
+      }
+    }
+    if (p.planar) {
+      float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+      for (int j = 0; j < CW; ++j)
+        if (cg + j < p.Cout) o[(((size_t)b * p.Cout + cg + j) * p.out_H + ho) * p.out_pitch + wo] = v[j];
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_c + cg;
+#pragma unroll
+      for (int q = 0; q < CW / 8; ++q) {
+        uint4 u;
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+        *reinterpret_cast<uint4*>(o + q * 8) = u;
+      }
+    }
+}
+
+// Persistent, warp-specialised kernel: a CTA walks work items (tap class, N block, 128-pixel tile) with stride gridDim.x.
+//   warp 0      TMA producer: runs ahead across tiles through the STAGES-deep smem ring
+//   warp 1      MMA issuer: accumulates tile i into TMEM buffer i % 2 while ...
+//   warps 2-5   ... the epilogue warps drain buffer (i - 1) % 2 (tcgen05.ld, bias / residual / activation, stores)
+// so neither the TMA latency nor the epilogue of a tile is exposed (measured on the one-tile-per-CTA version: ~6 us of
+// serial latency per tile against 0.6 us of tensor work).
 template <int BK, int BN, int STAGES>
 __global__ void __launch_bounds__(192)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
   using SL = SmemLayout<BK, BN, STAGES>;
+  constexpr int kAcc = 2;                                   // TMEM accumulator buffers
+  constexpr uint32_t kTmemCols = (kAcc * BN) < 32 ? 32 : (kAcc * BN);
   extern __shared__ unsigned char smem_raw[];
   // barriers first, then 1024B-aligned operand stages
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_empty = acc_full + kAcc;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + kAcc);
   unsigned char* stages = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + SL::kBars + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
-  const int n0 = blockIdx.y * BN;
-  const int ho0 = th * kTH, wo0 = tw * kTW;
-  const TapClass& tc = p.cls[blockIdx.z];
-  const int ksteps = tc.n * (p.kblocks1 + p.kblocks2);
+  const int tiles = p.tiles_w * p.tiles_h * p.B;
+  const int total = tiles * p.nblk * p.ncls;                // work item w = (cls * tiles + tile) * nblk + nb
+  const int kb = p.kblocks1 + p.kblocks2;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA1);
@@ -111,11 +215,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(acc_full, 1);
+    for (int a = 0; a < kAcc; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);                          // one arrival per epilogue warp
+    }
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, BN < 32 ? 32 : BN);
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -126,22 +233,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = 0; t < tc.n; ++t) {
-        const int tap = tc.wt[t];
-        const int hi = ho0 * p.stride + tc.dh[t], wi = wo0 * p.stride + tc.dw[t];
-        for (int cb = 0; cb < p.kblocks1 + p.kblocks2; ++cb) {
-          mbar_wait(&empty[s], ph ^ 1);
-          unsigned char* a_dst = stages + (size_t)s * SL::kStage;
-          unsigned char* b_dst = a_dst + SL::kA;
-          mbar_arrive_expect_tx(&full[s], SL::kStage);
-          if (cb < p.kblocks1) {
-            tma_load_4d(a_dst, &tmA1, cb * BK, wi, hi, b, &full[s]);
-            tma_load_2d(b_dst, &tmW, tap * p.Cin + cb * BK, n0, &full[s]);
-          } else {
-            tma_load_4d(a_dst, &tmA2, (cb - p.kblocks1) * BK, wi, hi, b, &full[s]);
-            tma_load_2d(b_dst, &tmW, tap * p.Cin + p.C1 + (cb - p.kblocks1) * BK, n0, &full[s]);
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int nb = w % p.nblk, tile = (w / p.nblk) % tiles;
+        const TapClass& tc = p.cls[w / (p.nblk * tiles)];
+        const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
+        const int n0 = nb * BN;
+        for (int t = 0; t < tc.n; ++t) {
+          const int tap = tc.wt[t];
+          const int hi = th * kTH * p.stride + tc.dh[t], wi = tw * kTW * p.stride + tc.dw[t];
+          for (int cb = 0; cb < kb; ++cb) {
+            mbar_wait(&empty[s], ph ^ 1);
+            unsigned char* a_dst = stages + (size_t)s * SL::kStage;
+            unsigned char* b_dst = a_dst + SL::kA;
+            mbar_arrive_expect_tx(&full[s], SL::kStage);
+            if (cb < p.kblocks1) {
+              tma_load_4d(a_dst, &tmA1, cb * BK, wi, hi, b, &full[s]);
+              tma_load_2d(b_dst, &tmW, tap * p.Cin + cb * BK, n0, &full[s]);
+            } else {
+              tma_load_4d(a_dst, &tmA2, (cb - p.kblocks1) * BK, wi, hi, b, &full[s]);
+              tma_load_2d(b_dst, &tmW, tap * p.Cin + p.C1 + (cb - p.kblocks1) * BK, n0, &full[s]);
+            }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
           }
-          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -151,132 +264,225 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       constexpr uint32_t idesc = make_idesc<BN>();
       int s = 0;
       uint32_t ph = 0;
-      for (int k = 0; k < ksteps; ++k) {
-        mbar_wait(&full[s], ph);
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int ksteps = p.cls[w / (p.nblk * tiles)].n * kb;
+        const int a = it & 1;
+        mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(stages + (size_t)s * SL::kStage);
-        const uint64_t adesc = make_desc<BK>(a_addr);
-        const uint64_t bdesc = make_desc<BK>(a_addr + SL::kA);
+        const uint32_t tacc = tmem_base + (uint32_t)(a * BN);
+        for (int k = 0; k < ksteps; ++k) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(stages + (size_t)s * SL::kStage);
+          const uint64_t adesc = make_desc<BK>(a_addr);
+          const uint64_t bdesc = make_desc<BK>(a_addr + SL::kA);
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the (addr >> 4) field
+            umma_bf16(tacc, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
+          }
+          umma_commit(&empty[s]);  // frees the smem stage when these MMAs have read it
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&empty[s]);  // frees the smem stage when these MMAs have read it
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+        umma_commit(&acc_full[a]);  // accumulator complete
       }
-      umma_commit(acc_full);  // accumulator complete
     }
   } else {
     // ================================================================= epilogue (warps 2..5)
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int m = quad * 32 + lane;       // row of the tile = pixel
-    const int ho = (ho0 + m / kTW) * p.out_mul + tc.oh, wo = (wo0 + m % kTW) * p.out_mul + tc.ow;
-    const bool valid = ho < p.out_H && wo < p.out_W;
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const size_t pix = ((size_t)b * p.out_H + ho) * p.out_W + wo;
+    int it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const int nb = w % p.nblk, tile = (w / p.nblk) % tiles;
+      const TapClass& tc = p.cls[w / (p.nblk * tiles)];
+      const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
+      const int n0 = nb * BN;
+      const int ho = (th * kTH + m / kTW) * p.out_mul + tc.oh, wo = (tw * kTW + m % kTW) * p.out_mul + tc.ow;
+      const bool valid = ho < p.out_H && wo < p.out_W;
+      const size_t pix = ((size_t)b * p.out_H + ho) * p.out_W + wo;
+      const int a = it & 1;
+      mbar_wait(&acc_full[a], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + c0, r);
-      const int cg = n0 + c0;  // first global output channel of this chunk
-      if (!valid || cg >= p.Cout) continue;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (cg + j < p.Cout) v[j] += __ldg(p.bias + cg + j);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tacc + c0, r);
+        const int cg = n0 + c0;  // first global output channel of this chunk
+        if (!valid || cg >= p.Cout) continue;
+        epilogue_store<32>(p, r, cg, pix, b, ho, wo);
       }
-      if (p.ctab) {
-        // a spatially constant extra input channel (the max_disp/100 plane of reference :145,208-209) contributes
-        // value * (sum of its weights over the taps that fall inside the image): a per-border-class bias
-        const int rc = (ho == 0 ? 1 : 0) | (p.stride * ho + 1 > p.H - 1 ? 2 : 0);
-        const int cc = (wo == 0 ? 1 : 0) | (p.stride * wo + 1 > p.W - 1 ? 2 : 0);
-        const float* t = p.ctab + (size_t)(rc * 4 + cc) * p.Cout + cg;
-        const float sc = __ldg(p.cscale + b);
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (cg + j < p.Cout) v[j] = fmaf(sc, __ldg(t + j), v[j]);
-      }
-      if (p.accum) {
-        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.out) + pix * p.out_c + cg);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u = rp[q];
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float2 f = __bfloat1622float2(h2[e]);
-            v[q * 8 + 2 * e] += f.x;
-            v[q * 8 + 2 * e + 1] += f.y;
-          }
-        }
-      }
-      if (p.residual) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.res_c + cg);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u = __ldg(rp + q);
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float2 f = __bfloat1622float2(h2[e]);
-            v[q * 8 + 2 * e] += f.x;
-            v[q * 8 + 2 * e + 1] += f.y;
-          }
-        }
-      }
-      if (p.act == 1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = elu1(v[j]);
-      } else if (p.act == 2) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-      if (p.dact) {
-        // backward epilogue: gradient w.r.t. the pre-activation = gradient * act'(pre), from the SAVED OUTPUT y:
-        // ELU'(pre) = 1 (y > 0) else y + 1;  ReLU'(pre) = [y > 0]
-        const uint4* yp = reinterpret_cast<const uint4*>(p.ysave + pix * p.ysave_c + cg);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u = __ldg(yp + q);
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float2 f = __bfloat1622float2(h2[e]);
-            const float d0 = f.x > 0.f ? 1.f : (p.dact == 1 ? f.x + 1.f : 0.f);
-            const float d1 = f.y > 0.f ? 1.f : (p.dact == 1 ? f.y + 1.f : 0.f);
-            v[q * 8 + 2 * e] *= d0;
-            v[q * 8 + 2 * e + 1] *= d1;
-          }
-        }
-      }
-      if (p.planar) {
-        float* o = reinterpret_cast<float*>(p.out);
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (cg + j < p.Cout) o[(((size_t)b * p.Cout + cg + j) * p.out_H + ho) * p.out_pitch + wo] = v[j];
-      } else {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_c + cg;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
-          *reinterpret_cast<uint4*>(o + q * 8) = u;
-        }
-      }
+      // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld inside tmem_ld32): hand it back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[a]);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ row-tile kernel
+// Wide, few-channel layers (full and half resolution) are bound by L2 -> SM traffic in the tile kernel above: every 128-pixel
+// tile re-fetches its input patch once per filter tap (9 x 16 KB) plus the weights (9 x 8 KB), ~8.9 TB/s measured against
+// the ~12 TB/s L2 cap.  Here a tile is ONE output row x 128 pixels, so that
+//   * the input arrives as ONE halo box per channel block: [BK, 130, 3] (rows h-1..h+1, columns w0-1..w0+128); the A
+//     operand of tap (dh, dw) is the window starting at halo row (dh+1)*130 + (dw+1) -- 128 consecutive shared-memory rows,
+//     a legal K-major operand with the usual SBO (the 128B/64B swizzle is a function of the shared address, so a window
+//     may start on any row)
+//   * the weights of all nine taps stay resident in shared memory for the life of the (persistent) CTA
+//   * the output row segment is contiguous in NHWC memory.
+// Per 128 pixels the SM now pulls 50 KB (3x the algorithmic input, the overlap served by L2) instead of 216 KB.
+// Eight epilogue warps (two per TMEM lane quadrant, half of the columns each) drain the double-buffered accumulator.
+constexpr int kRowW = 128, kHaloCols = kRowW + 2, kHaloRows = 3;
+
+template <int BK, int BN, int STAGES>
+struct RowSmem {
+  static constexpr int kHalo = (kHaloCols * kHaloRows * BK * 2 + 1023) / 1024 * 1024;
+  static constexpr int kW = BN * BK * 2;                       // one (tap, channel block) weight tile
+  static constexpr int kBars = 1024;
+  static int total(int kb) { return kBars + 1024 + 9 * kb * kW + STAGES * kHalo; }
+};
+
+template <int BK, int BN, int STAGES>
+__global__ void __launch_bounds__(320)
+conv3x3_row_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                   const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+  using SL = RowSmem<BK, BN, STAGES>;
+  constexpr int kAcc = 2;
+  constexpr uint32_t kTmemCols = (kAcc * BN) < 32 ? 32 : (kAcc * BN);
+  constexpr int CW = BN / 2;                                   // columns per epilogue warp
+  extern __shared__ unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint64_t* acc_empty = acc_full + kAcc;
+  uint64_t* wfull = acc_empty + kAcc;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wfull + 1);
+  unsigned char* wsm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + SL::kBars + 1023) & ~uintptr_t(1023));
+  const int kb = p.kblocks1 + p.kblocks2;
+  unsigned char* stages = wsm + (size_t)9 * kb * SL::kW;      // kW is a multiple of 1024 (BN * BK * 2 >= 2048)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = p.tiles_w * p.H * p.B;                    // work item = (b, h, 128-pixel segment)
+  const TapClass& tc = p.cls[0];
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmW);
+    if (p.kblocks2) prefetch_tmap(&tmA2);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < kAcc; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 8);                            // one arrival per epilogue warp
+    }
+    mbar_init(wfull, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================================================= TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wfull, 9 * kb * SL::kW);
+      for (int t = 0; t < 9; ++t)
+        for (int cb = 0; cb < kb; ++cb) {
+          const int col = tc.wt[t] * p.Cin + (cb < p.kblocks1 ? cb * BK : p.C1 + (cb - p.kblocks1) * BK);
+          tma_load_2d(wsm + (size_t)(t * kb + cb) * SL::kW, &tmW, col, 0, wfull);
+        }
+      int s = 0;
+      uint32_t ph = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int tw = w % p.tiles_w, h = (w / p.tiles_w) % p.H, b = w / (p.tiles_w * p.H);
+        for (int cb = 0; cb < kb; ++cb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], kHaloCols * kHaloRows * BK * 2);
+          unsigned char* dst = stages + (size_t)s * SL::kHalo;
+          if (cb < p.kblocks1) tma_load_4d(dst, &tmA1, cb * BK, tw * kRowW - 1, h - 1, b, &full[s]);
+          else tma_load_4d(dst, &tmA2, (cb - p.kblocks1) * BK, tw * kRowW - 1, h - 1, b, &full[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      uint32_t aoff[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) aoff[t] = (uint32_t)(((tc.dh[t] + 1) * kHaloCols + (tc.dw[t] + 1)) * BK * 2) >> 4;
+      const uint64_t wdesc0 = make_desc<BK>(smem_u32(wsm));
+      mbar_wait(wfull, 0);
+      tc_fence_after();
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int a = it & 1;
+        mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(a * BN);
+        for (int cb = 0; cb < kb; ++cb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t hdesc = make_desc<BK>(smem_u32(stages + (size_t)s * SL::kHalo));
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const uint64_t adesc = hdesc + aoff[t];
+            const uint64_t bdesc = wdesc0 + (uint64_t)(((t * kb + cb) * SL::kW) >> 4);
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) umma_bf16(tacc, adesc + 2 * kk, bdesc + 2 * kk, idesc, (cb | t | kk) != 0);
+          }
+          umma_commit(&empty[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&acc_full[a]);
+      }
+    }
+  } else {
+    // ================================================================= epilogue (warps 2..9)
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int m = quad * 32 + lane;
+    int it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const int tw = w % p.tiles_w, h = (w / p.tiles_w) % p.H, b = w / (p.tiles_w * p.H);
+      const int wo = tw * kRowW + m;
+      const bool valid = wo < p.W;
+      const size_t pix = ((size_t)b * p.H + h) * p.W + wo;
+      const int a = it & 1;
+      mbar_wait(&acc_full[a], (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[CW];
+      const uint32_t taddr = tmem_base + (uint32_t)(a * BN + half * CW) + ((uint32_t)(quad * 32) << 16);
+      if (CW == 32) tmem_ld32(taddr, reinterpret_cast<uint32_t(&)[32]>(r));
+      else tmem_ld16(taddr, reinterpret_cast<uint32_t(&)[16]>(r));
+      // registers hold the data: the accumulator buffer can be refilled while this warp does the arithmetic and stores
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[a]);
+      const int cg = half * CW;
+      if (valid && cg < p.Cout) epilogue_store<CW>(p, r, cg, pix, b, h, wo);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -295,37 +501,117 @@ bool make_w_map(CUtensorMap* m, const void* ptr, int rows, int K, int BK, int BN
 }
 
 template <int BK, int BN, int STAGES>
-int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const ConvParams& p, cudaStream_t st) {
+int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, ConvParams p, cudaStream_t st) {
   using SL = SmemLayout<BK, BN, STAGES>;
   auto kern = conv3x3_tc_kernel<BK, BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int per_sm = 0;
+  if (per_sm == 0) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal);
-    attr_set = true;
+    // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for every kernel that contains tcgen05.alloc (it cannot know
+    // the column count), so the co-residency is computed here: shared memory (228 KB per SM, 1 KB reserved per CTA),
+    // TMEM columns (512 per SM) and registers (64 K per SM, __launch_bounds__(192)).
+    int n = (228 * 1024) / (SL::kTotal + 1024);
+    const int tmem_cols = 2 * BN < 32 ? 32 : 2 * BN;
+    if (n > 512 / tmem_cols) n = 512 / tmem_cols;          // co-resident CTAs must all get their TMEM columns
+    if (n > 6) n = 6;
+    if (getenv("FALN_DEBUG")) fprintf(stderr, "conv3x3_tc_kernel<%d,%d,%d>: smem %d, %d CTAs/SM\n", BK, BN, STAGES, SL::kTotal, n);
+    per_sm = n < 1 ? 1 : n;
   }
-  dim3 grid(p.tiles_w * p.tiles_h * p.B, (p.Cout + BN - 1) / BN, p.ncls);
-  kern<<<grid, 192, SL::kTotal, st>>>(a1, a2, w, p);
+  p.nblk = (p.Cout + BN - 1) / BN;
+  const long long total = (long long)p.tiles_w * p.tiles_h * p.B * p.nblk * p.ncls;
+  long long grid = (long long)sm_count() * per_sm;
+  if (grid > total) grid = total;
+  kern<<<(int)grid, 192, SL::kTotal, st>>>(a1, a2, w, p);
   return after_launch("conv3x3_tc_kernel");
 }
 
-// Stage counts: a CTA owns ONE 128-pixel tile and runs only 9 * Cin / BK k-steps, so what hides latency is several CTAs
-// per SM (prologue, TMA latency and epilogue of different tiles overlapping), not a deep ring: 3-4 stages, sized so that
-// 2-5 CTAs fit in shared memory (and their accumulators in the 512 TMEM columns).
+bool make_row_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int BK) {
+  auto fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)kHaloCols, (cuuint32_t)kHaloRows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BK, int BN, int STAGES>
+int launch_row(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, ConvParams p, cudaStream_t st) {
+  using SL = RowSmem<BK, BN, STAGES>;
+  auto kern = conv3x3_row_kernel<BK, BN, STAGES>;
+  const int smem = SL::total(p.kblocks1 + p.kblocks2);
+  static int attr = 0;
+  if (attr < smem) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = smem;
+  }
+  int per_sm = (228 * 1024) / (smem + 1024);      // see launch(): the occupancy API answers 1 for tcgen05.alloc kernels
+  const int tmem_cols = 2 * BN < 32 ? 32 : 2 * BN;
+  if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
+  if (per_sm > 3) per_sm = 3;
+  if (per_sm < 1) per_sm = 1;
+  p.tiles_w = (p.W + kRowW - 1) / kRowW;
+  p.nblk = 1;
+  const long long total = (long long)p.tiles_w * p.H * p.B;
+  long long grid = (long long)sm_count() * per_sm;
+  if (grid > total) grid = total;
+  kern<<<(int)grid, 320, smem, st>>>(a1, a2, w, p);
+  return after_launch("conv3x3_row_kernel");
+}
+
+// Stride-1 layers with one N block (Cout_pad <= 64) on wide maps whose nine-tap weights fit in shared memory beside two
+// halo stages.  Returns 1 if the layer was launched here, 0 if the caller should use the tile kernel, < 0 on error.
+int try_row_kernel(const void* x, const void* x2, const void* wptr, int wrows, ConvParams& p, int BK, int C2, cudaStream_t st) {
+  static const bool disabled = getenv("FALN_CONV_NO_ROW") != nullptr;
+  if (disabled || p.stride != 1 || p.ncls != 1 || p.cls[0].n != 9 || p.out_mul != 1) return 0;
+  if (wrows != 32 && wrows != 64) return 0;
+  if (p.W < 192) return 0;
+  const int kb = p.kblocks1 + p.kblocks2;
+  const int halo = (kHaloCols * kHaloRows * BK * 2 + 1023) / 1024 * 1024;
+  if (2048 + 9 * kb * wrows * BK * 2 + 2 * halo > 225 * 1024) return 0;
+  CUtensorMap a1, a2, wm;
+  if (!make_row_map(&a1, x, p.B, p.H, p.W, p.C1, BK) || !make_w_map(&wm, wptr, wrows, 9 * p.Cin, BK, wrows) ||
+      (x2 && !make_row_map(&a2, x2, p.B, p.H, p.W, C2, BK))) {
+    set_error("conv3x3 row kernel: cuTensorMapEncodeTiled failed");
+    return FALN_ERR_LAUNCH;
+  }
+  if (!x2) a2 = a1;
+  int rc;
+  if (BK == 64) rc = wrows == 64 ? launch_row<64, 64, 2>(a1, a2, wm, p, st) : launch_row<64, 32, 2>(a1, a2, wm, p, st);
+  else rc = wrows == 64 ? launch_row<32, 64, 3>(a1, a2, wm, p, st) : launch_row<32, 32, 3>(a1, a2, wm, p, st);
+  return rc == 0 ? 1 : rc;
+}
+
+// Small feature maps give few 128-pixel tiles: a wide N tile then leaves most SMs idle while a handful of CTAs walk a
+// long K loop alone (measured: 16 CTAs, 22-45 us for the 3x10 bottleneck layers).  Narrow the N tile until the grid
+// covers the SMs; the A tile is re-read by the extra CTAs out of L2.
+int narrow_bn(int BN, int tiles, int cout_pad, int ncls) {
+  while (BN > 64 && tiles * (cout_pad / BN) * ncls < sm_count()) BN >>= 1;
+  return BN;
+}
+
+// Ring depth: the producer runs ahead across tiles, so 3-4 stages with two CTAs per SM keep the HBM stream busy on the
+// large maps; when the whole layer is at most two work items per SM (small maps, long K loops) a deeper ring with one
+// CTA per SM hides the per-step TMA latency instead.
 int dispatch(int BK, int BN, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& wm, const ConvParams& p,
              cudaStream_t st) {
+  const long long total = (long long)p.tiles_w * p.tiles_h * p.B * ((p.Cout + BN - 1) / BN) * p.ncls;
+  const bool deep = total <= 2LL * sm_count();
   if (BK == 64) {
     switch (BN) {
       case 256: return launch<64, 256, 4>(a1, a2, wm, p, st);
-      case 128: return launch<64, 128, 3>(a1, a2, wm, p, st);
-      case 64: return launch<64, 64, 3>(a1, a2, wm, p, st);
-      default: return launch<64, 32, 3>(a1, a2, wm, p, st);
+      case 128: return deep ? launch<64, 128, 6>(a1, a2, wm, p, st) : launch<64, 128, 3>(a1, a2, wm, p, st);
+      case 64: return deep ? launch<64, 64, 8>(a1, a2, wm, p, st) : launch<64, 64, 2>(a1, a2, wm, p, st);
+      default: return launch<64, 32, 2>(a1, a2, wm, p, st);
     }
   }
   switch (BN) {
     case 256: return launch<32, 256, 4>(a1, a2, wm, p, st);
-    case 128: return launch<32, 128, 3>(a1, a2, wm, p, st);
-    case 64: return launch<32, 64, 4>(a1, a2, wm, p, st);
-    default: return launch<32, 32, 4>(a1, a2, wm, p, st);
+    case 128: return launch<32, 128, 4>(a1, a2, wm, p, st);
+    case 64: return launch<32, 64, 3>(a1, a2, wm, p, st);
+    default: return launch<32, 32, 3>(a1, a2, wm, p, st);
   }
 }
 
@@ -354,6 +640,7 @@ extern "C" int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, co
   ConvParams p{};
   p.B = B; p.H = H; p.W = W;
   p.Ho = (H - 1) / stride + 1; p.Wo = (W - 1) / stride + 1;
+  BN = narrow_bn(BN, B * ((p.Wo + kTW - 1) / kTW) * ((p.Ho + kTH - 1) / kTH), Cout_pad, 1);
   p.C1 = C1; p.C2 = C2; p.Cin = C1 + C2; p.Cout = Cout;
   p.stride = stride; p.act = act; p.planar = planar;
   p.tiles_w = (p.Wo + kTW - 1) / kTW; p.tiles_h = (p.Ho + kTH - 1) / kTH;
@@ -370,6 +657,10 @@ extern "C" int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, co
   p.cls[0].oh = p.cls[0].ow = 0;
   p.out_mul = 1; p.out_H = p.Ho; p.out_W = p.Wo;
   p.accum = 0; p.dact = 0; p.ysave = nullptr; p.ysave_c = 0; p.res_c = out_c;
+  {
+    const int rr = try_row_kernel(x, x2, w, Cout_pad, p, BK, C2, as_stream(stream));
+    if (rr != 0) return rr > 0 ? 0 : rr;
+  }
   CUtensorMap a1, a2, wm;
   if (!make_act_map(&a1, x, B, H, W, C1, BK, stride) || !make_w_map(&wm, w, Cout_pad, 9 * (C1 + C2), BK, BN) ||
       (x2 && !make_act_map(&a2, x2, B, H, W, C2, BK, stride))) {
@@ -399,10 +690,11 @@ extern "C" int faln_conv3x3_dgrad(const void* g, const void* wd, void* gx, const
   FALN_REQUIRE((dact == 0) == (ysave == nullptr), "faln_conv3x3_dgrad: dact and ysave go together");
   const int Hg = (H - 1) / stride + 1, Wg = (W - 1) / stride + 1;
   const int BK = (Cg % 64 == 0) ? 64 : 32;
-  const int BN = Cx_pad % 256 == 0 ? 256 : (Cx_pad % 128 == 0 ? 128 : (Cx_pad % 64 == 0 ? 64 : 32));
+  int BN = Cx_pad % 256 == 0 ? 256 : (Cx_pad % 128 == 0 ? 128 : (Cx_pad % 64 == 0 ? 64 : 32));
   ConvParams p{};
   p.B = B; p.H = Hg; p.W = Wg;
   p.Ho = (H + stride - 1) / stride; p.Wo = (W + stride - 1) / stride;   // tile grid over one parity class
+  BN = narrow_bn(BN, B * ((p.Wo + kTW - 1) / kTW) * ((p.Ho + kTH - 1) / kTH), Cx_pad, stride == 2 ? 4 : 1);
   p.C1 = Cg; p.C2 = 0; p.Cin = Cg; p.Cout = Cx;
   p.stride = 1; p.act = 0; p.planar = 0;
   p.tiles_w = (p.Wo + kTW - 1) / kTW; p.tiles_h = (p.Ho + kTH - 1) / kTH;
@@ -435,6 +727,10 @@ extern "C" int faln_conv3x3_dgrad(const void* g, const void* wd, void* gx, const
             ++c.n;
           }
       }
+  }
+  {
+    const int rr = try_row_kernel(g, nullptr, wd, Cx_pad, p, BK, 0, as_stream(stream));
+    if (rr != 0) return rr > 0 ? 0 : rr;
   }
   CUtensorMap a1, wm;
   if (!make_act_map(&a1, g, B, Hg, Wg, Cg, BK, 1) || !make_w_map(&wm, wd, Cx_pad, 9 * Cg, BK, BN)) {

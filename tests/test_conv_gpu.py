@@ -30,6 +30,12 @@ def _ref(x, w, b, stride, act, res):
     (3, 3, 10, 512, 0, 512, 1, 1, False, True),      # bottleneck map smaller than one tile
     (2, 375 // 8, 1242 // 8, 256, 0, 256, 2, 1, True, False),
     (1, 6, 20, 256, 0, 512, 2, 1, True, False),
+    # wide maps, one N block: the row-tile kernel (one halo load per 128-pixel row segment, resident weights)
+    (2, 9, 640, 64, 0, 64, 1, 1, True, False),       # exact 5 segments per row
+    (1, 11, 300, 64, 0, 64, 1, 1, False, True),      # ragged last segment + residual
+    (2, 7, 333, 32, 0, 32, 1, 1, False, True),       # BK=32 (64B swizzle), 16 columns per epilogue warp
+    (1, 5, 257, 64, 64, 64, 1, 1, True, False),      # two sources
+    (1, 6, 200, 128, 0, 64, 1, 2, True, False),      # two K blocks of one source, ReLU
 ])
 def test_conv3x3_bf16_nhwc(B, H, W, C1, C2, Cout, stride, act, bias, res):
     from fal_net_b200 import conv_native as CN
@@ -70,6 +76,14 @@ def test_conv3x3_planar_fp32_logits():
     torch.cuda.synchronize()
     ref = _ref(torch.cat((u, s), 1), w, b, 1, 0, None)
     assert rel_err(out, ref) < 1e-3          # fp32 straight from the accumulator: only operand rounding is shared
+    # the same layer on a wide map goes through the row-tile kernel (BK = 32, three channel blocks, planar stores)
+    B, H, W = 1, 6, 270
+    u = torch.randn(B, 64, H, W, generator=g).bfloat16().to(dev).contiguous(memory_format=CL)
+    s = torch.randn(B, 32, H, W, generator=g).bfloat16().to(dev).contiguous(memory_format=CL)
+    out = layout.alloc_planar(B, N, H, W, dev)
+    CN.conv3x3_fwd(u, CN.pack_weight(w, 64), b, 1, 0, None, s, cout=N, planar_out=out)
+    torch.cuda.synchronize()
+    assert rel_err(out, _ref(torch.cat((u, s), 1), w, b, 1, 0, None)) < 1e-3
 
 
 def test_stem_upsample_pool_and_const_channel():
@@ -119,6 +133,9 @@ def _elu_grad_from_y(y):
     (2, 47, 155, 256, 256, 2, 0, False, False),    # stride 2, mixed parity, no activation
     (3, 3, 10, 512, 512, 1, 1, False, False),
     (2, 21, 70, 96, 49, 1, 0, False, False),       # logits conv: Cout 49 padded to 64 on K
+    (2, 9, 640, 64, 64, 1, 1, False, False),       # row-tile kernel (wide map, one N block)
+    (1, 7, 333, 32, 32, 1, 1, False, True),
+    (1, 6, 260, 64, 49, 1, 0, False, False),
 ])
 def test_conv3x3_dgrad(B, H, W, Cin, Cout, stride, dact, accum, res):
     from fal_net_b200 import conv_native as CN
