@@ -28,12 +28,13 @@ MEAN = (0.411, 0.432, 0.45)
 
 
 def peaks():
+    """(HBM GB/s, sustained bf16 TFLOP/s, source): the driver's measurements on this pool's B200s, else the recipe's fallback."""
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -227,7 +228,7 @@ def run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP
     wl = a.workload
     cfg = workload_config(wl, world)
     B, H, W = cfg["per_gpu_batch"], cfg["H"], cfg["W"]
-    hbm_peak, peak_src = peaks()
+    hbm_peak, tf_peak, peak_src = peaks()
 
     torch.manual_seed(0)
     model = models.FAL_netB(no_levels=N).to(dev)
@@ -329,28 +330,63 @@ def run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP
     ms = float(t[0])
     value = frames_per_step / (ms / 1e3)
 
-    # per-launch CUDA-event timing of the MED kernels (event records cannot live inside a captured graph, so the same
-    # steps are run kernel by kernel once more; these iterations are not part of `value`)
-    med.TIMING = []
-    for i in range(max(3, min(a.steps, 10))):
+    # per-launch CUDA-event timing of our kernels (event records cannot live inside a captured graph, so the same steps
+    # are run kernel by kernel once more, on ONE stream so that every kernel is timed alone; these iterations are not
+    # part of `value`)
+    from fal_net_b200 import backbone as BB, conv_native as CNV
+    n_prof = max(3, min(a.steps, 10))
+    BB.USE_SIDE_STREAM = False
+    step_dev(*devb[0])                                               # settle allocator / caches in this mode
+    med.TIMING, CNV.TIMING = [], []
+    for i in range(n_prof):
         step_dev(*devb[i % nb])
     sync_all()
     timing, med.TIMING = med.TIMING, None
+    ctiming, CNV.TIMING = CNV.TIMING, None
+    BB.USE_SIDE_STREAM = True
 
-    # roofline of the MED kernels, from CUDA events around each launch inside the timed region
+    # MED kernels: HBM roofline from the algorithmic bytes of SURVEY.md 8(d)
     kinds = {}
     for kind, s0, s1, nbytes in timing:
         kinds.setdefault(kind, []).append((s0.elapsed_time(s1), nbytes))
-    med_stats = {k: {"launches": len(v), "avg_ms": sum(x for x, _ in v) / len(v),
-                     "gbs": sum(nb_ for _, nb_ in v) / sum(x for x, _ in v) / 1e6} for k, v in kinds.items()}
-    dom = max(med_stats.items(), key=lambda kv: kv[1]["avg_ms"] * kv[1]["launches"])[0] if med_stats else None
+    med_stats = {k: {"launches_per_step": len(v) / n_prof, "avg_ms": sum(x for x, _ in v) / len(v),
+                     "gbs": sum(nb_ for _, nb_ in v) / sum(x for x, _ in v) / 1e6,
+                     "frac": sum(nb_ for _, nb_ in v) / sum(x for x, _ in v) / 1e6 / hbm_peak,
+                     "share_of_step": sum(x for x, _ in v) / n_prof / ms} for k, v in kinds.items()}
+    # convolution kernels (tcgen05 tile / row / wgrad): tensor roofline from the algorithmic FLOPs; layer by layer the
+    # bound is max(flops / tensor peak, bytes / HBM peak) because the <= 96-channel layers sit below the bf16 ridge
+    fam = {}
+    for kind, s0, s1, fl, nbytes in ctiming:
+        f = fam.setdefault(kind, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "bound_ms": 0.0, "n": 0})
+        f["ms"] += s0.elapsed_time(s1)
+        f["flops"] += fl
+        f["bytes"] += nbytes
+        f["bound_ms"] += max(fl / (tf_peak * 1e9), nbytes / (hbm_peak * 1e6))
+        f["n"] += 1
+    conv_stats = {k: {"launches_per_step": f["n"] / n_prof, "ms_per_step": f["ms"] / n_prof,
+                      "tflops": f["flops"] / f["ms"] / 1e9, "frac_of_tensor_peak": f["flops"] / f["ms"] / 1e9 / tf_peak,
+                      "frac_of_layerwise_roofline": f["bound_ms"] / f["ms"], "share_of_step": f["ms"] / n_prof / ms}
+                  for k, f in fam.items() if f["ms"] > 0}
     roofline = None
-    if dom:
+    if conv_stats:
+        tot_ms = sum(f["ms"] for f in fam.values())
+        tot_fl = sum(f["flops"] for f in fam.values())
+        tot_bound = sum(f["bound_ms"] for f in fam.values())
+        roofline = {"kernel": "conv3x3 family (tcgen05 tile/row kernels: forward + dgrad, MN-major wgrad)", "bound": "tensor",
+                    "achieved": tot_fl / tot_ms / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": tot_fl / tot_ms / 1e9 / tf_peak, "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained",
+                    "frac_of_layerwise_roofline": tot_bound / tot_ms,
+                    "launches_per_step": sum(f["n"] for f in fam.values()) / n_prof, "ms_per_step": tot_ms / n_prof,
+                    "share_of_step": tot_ms / n_prof / ms, "by_kernel": conv_stats}
+    roofline_med = None
+    if med_stats:
+        dom = max(med_stats.items(), key=lambda kv: kv[1]["avg_ms"] * kv[1]["launches_per_step"])[0]
         st = med_stats[dom]
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": st["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": st["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
-                    "avg_launch_ms": st["avg_ms"], "share_of_step": st["avg_ms"] * (st["launches"] / max(3, min(a.steps, 10))) / ms,
-                    "all_med_kernels": med_stats}
+        roofline_med = {"kernel": dom, "bound": "hbm", "achieved": st["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                        "frac": st["frac"], "traffic": None, "peak_source": peak_src + " hbm_gbs",
+                        "avg_launch_ms": st["avg_ms"], "share_of_step": st["share_of_step"], "all_med_kernels": med_stats}
+        if roofline is None:
+            roofline, roofline_med = roofline_med, None
 
     # ---------------- end-to-end timing (e2e): pinned host inputs, H2D + D2H inside the timed region ----------------
     h2d = 2 * B * 3 * H * W * 4 if wl in ("stage1", "stage2") else B * 3 * H * W * 4
@@ -380,9 +416,11 @@ def run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP
         "e2e": {"value": frames_per_step / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "cuda_graph": graphed is not None,
-        "library_conv_backward_calls_in_timed_region": lib_convs,
+        "library_conv_calls_in_timed_region": lib_convs,
         "roofline": roofline,
     }
+    if roofline_med is not None:
+        res["roofline_med"] = roofline_med
     if rank == 0 and not a.no_cpu_baseline and world == 1:
         val, unit, cores, sample, cms = cpu_reference(wl if wl != "med" else "stage1", 3, 1, budget_s=20.0)
         res["cpu_baseline"] = {"value": val, "unit": unit, "cores": cores, "kind": "port", "sample": sample,

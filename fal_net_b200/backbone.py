@@ -133,6 +133,7 @@ def forward(model, image, max_disp, tape=None):
 
 # ------------------------------------------------------------------------------------------------------------------
 _SIDE_STREAMS: dict = {}
+USE_SIDE_STREAM = True      # bench.py switches this off for its per-kernel timing pass (kernels then run one at a time)
 
 
 def _side_stream(dev):
@@ -180,6 +181,9 @@ def backward(model, tape, g_logits, sink=None):
     keep = []                                                  # tensors the side stream reads stay alive until the join
 
     def on_side(fn, *tensors):
+        if not USE_SIDE_STREAM:
+            fn()
+            return
         keep.extend(tensors)
         ev = torch.cuda.Event()
         ev.record(main)

@@ -10,6 +10,18 @@ from . import _lib
 CL = torch.channels_last
 ACT = {None: 0, "none": 0, "elu": 1, "relu": 2}
 
+# bench.py sets this to a list to collect (kind, start_event, end_event, algorithmic_flops, algorithmic_bytes) per conv launch
+TIMING = None
+
+
+def _timed(kind, flops, nbytes):
+    if TIMING is None:
+        return None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    TIMING.append((kind, e0, e1, flops, nbytes))
+    e0.record()
+    return e1
+
 
 def pack_weight(w: torch.Tensor, cout_pad: int | None = None) -> torch.Tensor:
     """[Cout,Cin,3,3] (any float dtype) -> bf16 KRSC [Cout_pad,3,3,Cin], zero rows beyond Cout."""
@@ -77,10 +89,14 @@ def conv3x3_fwd(x, w_krsc, bias=None, stride=1, act=0, residual=None, x2=None, c
     else:
         y = torch.empty((B, cout, Ho, Wo), device=x.device, dtype=torch.bfloat16, memory_format=CL)
         planar, pitch, out_c = 0, 0, cout
+    ev = _timed("conv_fwd", 2 * 9 * (C1 + C2) * cout * B * Ho * Wo,
+                2 * B * H * W * (C1 + C2) + (4 if planar else 2) * B * Ho * Wo * cout + 2 * 9 * (C1 + C2) * cout)
     rc = _lib.lib().faln_conv3x3_fwd(_lib.ptr(x), _lib.ptr(x2), _lib.ptr(w_krsc), _lib.ptr(bias), _lib.ptr(ctab),
                                      _lib.ptr(cscale), _lib.ptr(residual), _lib.ptr(y), B, H, W, C1, C2, cout, cout_pad,
                                      stride, int(act), planar, pitch, out_c, _lib.cur_stream())
     _lib.check(rc, "faln_conv3x3_fwd")
+    if ev is not None:
+        ev.record()
     return y
 
 
@@ -156,10 +172,13 @@ def conv3x3_dgrad(g, wd, out_hw, stride=1, out=None, rows=None, accum=False, dac
         residual = _nhwc(residual)
         assert residual.shape == out.shape
     assert (Hg, Wg) == ((H - 1) // stride + 1, (W - 1) // stride + 1)
+    ev = _timed("conv_dgrad", 2 * 9 * Cg * count * B * Hg * Wg, 2 * B * Hg * Wg * Cg + 2 * B * H * W * count + 2 * 9 * Cg * count)
     rc = _lib.lib().faln_conv3x3_dgrad(_lib.ptr(g), _lib.ptr(wslice), _lib.ptr(out), _lib.ptr(residual), _lib.ptr(ysave),
                                        B, H, W, Cg, count, count, stride, int(accum), int(dact if ysave is not None else 0),
                                        count, count, count, _lib.cur_stream())
     _lib.check(rc, "faln_conv3x3_dgrad")
+    if ev is not None:
+        ev.record()
     return out
 
 
@@ -216,9 +235,12 @@ def conv3x3_wgrad(g, x, dW, cout=None, cx=None, ci_off=0, stride=1, flags=0):
     cout = cout or dW.shape[0]
     cx = cx or min(Cxs, dW.shape[1] - ci_off)
     assert cout <= dW.shape[0] and ci_off + cx <= dW.shape[1]
+    ev = _timed("conv_wgrad", 2 * 9 * cx * cout * B * Hg * Wg, 2 * B * Hg * Wg * Cg + 2 * B * H * W * Cxs + 4 * 9 * cx * cout)
     rc = _lib.lib().faln_conv3x3_wgrad(_lib.ptr(g), _lib.ptr(x), _lib.ptr(dW), B, H, W, Cg, Cxs, cout, cx, ci_off,
                                        dW.shape[1], stride, int(flags), _lib.cur_stream())
     _lib.check(rc, "faln_conv3x3_wgrad")
+    if ev is not None:
+        ev.record()
     return dW
 
 
