@@ -1047,6 +1047,341 @@ __global__ void __launch_bounds__(256) med_disp_kernel(const float* __restrict__
   }
 }
 
+// =============================================================================================
+// Forward, fast path (no masks): rows 16-byte aligned, pitch % 4 == 0, pad columns [W, ceil4(W)) zero.
+//
+// ncu on the kernel above (profiles/r1d_med_full_*): 209 warp instructions per plane-iteration of which ~65 are the
+// arithmetic / loads the algorithm needs; the rest is control flow of the per-plane alignment switches, bounds logic,
+// address arithmetic and parameter re-loads.  This variant removes them:
+//   * the online softmax is order-independent, so each row's planes are visited grouped by the alignment class
+//     R = k0 & 3 of their integer shift; the loop body is instantiated per R and every tap window is two aligned
+//     128-bit shared loads whose lanes are named at compile time (no switch, no moves)
+//   * every ring slot keeps an all-zero tail and the rows' pad columns are zero, so a window that leaves the row reads
+//     zeros: one index clamp replaces the interior / edge branches
+//   * per-plane constants, ring pointers and loop state live in registers; the producer walks the same permuted order.
+// Planes whose shift is within rounding distance of an integer ("special") are visited last on the generic path.
+// =============================================================================================
+struct FastAcc {
+  float2 nm0[2], z0[2], dacc[2], nmw[2], zw[2], pacc[3][2];
+};
+
+__device__ __forceinline__ void lazy_rescale(FastAcc& A, float2 (&arg0)[2], float2 (&argw)[2], const float2 (&l2)[2],
+                                             const float2 (&wl)[2]) {
+  if (fmaxf(max4(arg0[0], arg0[1]), max4(argw[0], argw[1])) > kLazy) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float& a0 = e ? arg0[h].y : arg0[h].x;
+        if (a0 > kLazy) {
+          float& nm = e ? A.nm0[h].y : A.nm0[h].x;
+          const float f = rescale_factor(nm, (e ? l2[h].y : l2[h].x) * kLog2e);
+          (e ? A.z0[h].y : A.z0[h].x) *= f;
+          (e ? A.dacc[h].y : A.dacc[h].x) *= f;
+          a0 = 0.f;
+        }
+        float& aw = e ? argw[h].y : argw[h].x;
+        if (aw > kLazy) {
+          float& nm = e ? A.nmw[h].y : A.nmw[h].x;
+          const float f = rescale_factor(nm, (e ? wl[h].y : wl[h].x) * kLog2e);
+          (e ? A.zw[h].y : A.zw[h].x) *= f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) (e ? A.pacc[c][h].y : A.pacc[c][h].x) *= f;
+          aw = 0.f;
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void accumulate_plane(FastAcc& A, float dn, const float2 (&arg0)[2], const float2 (&argw)[2],
+                                                 const float2 (&a)[2], const float2 (&sc0)[3][2], const float2 (&sc1)[3][2]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float2 e0 = ex2_2(arg0[h]);
+    A.z0[h] = add2(A.z0[h], e0);
+    A.dacc[h] = fma2(splat(dn), e0, A.dacc[h]);
+    const float2 ew = ex2_2(argw[h]);
+    A.zw[h] = add2(A.zw[h], ew);
+    const float2 w1 = mul2(ew, a[h]);
+    const float2 w0 = fma2(w1, splat(-1.0f), ew);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      A.pacc[c][h] = fma2(w0, sc0[c][h], A.pacc[c][h]);
+      A.pacc[c][h] = fma2(w1, sc1[c][h], A.pacc[c][h]);
+    }
+  }
+}
+
+// One plane whose integer shift k0 has (k0 & 3) == R.  `row` points at element 0 of the staged plane row (16B aligned).
+template <int R>
+__device__ __forceinline__ void fast_plane(FastAcc& A, const float* row, const float* img, const PlaneInfo& pi, int xb,
+                                           int wr, int wz, int wcopy, float cW, const float2 (&g0p)[2],
+                                           const float2 (&nxf)[2]) {
+  const float4 L = *reinterpret_cast<const float4*>(row + xb);
+  // tap window: elements xb + k0 .. xb + k0 + 4 = lanes R .. R + 4 of the two aligned quads at xb + k0 - R; a window that
+  // starts beyond the row is redirected to the zero tail
+  const int b0 = min(xb + pi.k0 - R, wr);
+  const float4 w0 = *reinterpret_cast<const float4*>(row + b0);
+  const float4 w1 = *reinterpret_cast<const float4*>(row + b0 + 4);
+  const float q[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+  float2 a[2], wl[2];
+  a[0] = frac2(g0p[0], nxf[0], pi.xof, cW, pi.nk0f);
+  a[1] = frac2(g0p[1], nxf[1], pi.xof, cW, pi.nk0f);
+  wl[0] = make_float2(fmaf(a[0].x, q[R + 1] - q[R], q[R]), fmaf(a[0].y, q[R + 2] - q[R + 1], q[R + 1]));
+  wl[1] = make_float2(fmaf(a[1].x, q[R + 3] - q[R + 2], q[R + 2]), fmaf(a[1].y, q[R + 4] - q[R + 3], q[R + 3]));
+  // image taps out of the phase copies: A = taps 0..3 (copy R), B = taps 1..4 (copy R + 1, or copy 0 shifted by one quad)
+  const int i0 = min(xb + (pi.k0 - R), wz);
+  const float* pa = img + (R * 3) * wcopy + i0;
+  const float* pb = img + (R < 3 ? (R + 1) * 3 * wcopy : 4) + i0;
+  float2 sc0[3][2], sc1[3][2];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float4 Aq = *reinterpret_cast<const float4*>(pa + c * wcopy);
+    const float4 Bq = *reinterpret_cast<const float4*>(pb + c * wcopy);
+    sc0[c][0] = make_float2(Aq.x, Aq.y);
+    sc0[c][1] = make_float2(Aq.z, Aq.w);
+    sc1[c][0] = make_float2(Bq.x, Bq.y);
+    sc1[c][1] = make_float2(Bq.z, Bq.w);
+  }
+  const float2 l2[2] = {make_float2(L.x, L.y), make_float2(L.z, L.w)};
+  float2 arg0[2], argw[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    arg0[h] = fma2(l2[h], splat(kLog2e), A.nm0[h]);
+    argw[h] = fma2(wl[h], splat(kLog2e), A.nmw[h]);
+  }
+  lazy_rescale(A, arg0, argw, l2, wl);
+  accumulate_plane(A, pi.d, arg0, argw, a, sc0, sc1);
+}
+
+// generic per-pixel path (shift within rounding distance of an integer)
+__device__ __forceinline__ void special_plane(FastAcc& A, const float* row, const float* img, const PlaneInfo& pi, int xb,
+                                              int W, int wcopy, float cW, const float (&g0)[kPX]) {
+  const float4 L = *reinterpret_cast<const float4*>(row + xb);
+  float2 a[2], wl[2], sc0[3][2], sc1[3][2];
+  float wlv[kPX], av[kPX];
+#pragma unroll
+  for (int i = 0; i < kPX; ++i) {
+    const float t = coord_plus(g0[i], pi.xof, cW);
+    const float x0f = floorf(t);
+    av[i] = t - x0f;
+    const int x0 = (int)x0f;
+    const float f0 = tap(row, x0, W), f1 = tap(row, x0 + 1, W);
+    wlv[i] = fmaf(av[i], f1 - f0, f0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* ir = img + c * wcopy;  // phase-0 copy = the row itself
+      const float i0 = tap(ir, x0, W), i1 = tap(ir, x0 + 1, W);
+      if (i & 1) { sc0[c][i >> 1].y = i0; sc1[c][i >> 1].y = i1; }
+      else { sc0[c][i >> 1].x = i0; sc1[c][i >> 1].x = i1; }
+    }
+  }
+  a[0] = make_float2(av[0], av[1]);
+  a[1] = make_float2(av[2], av[3]);
+  wl[0] = make_float2(wlv[0], wlv[1]);
+  wl[1] = make_float2(wlv[2], wlv[3]);
+  const float2 l2[2] = {make_float2(L.x, L.y), make_float2(L.z, L.w)};
+  float2 arg0[2], argw[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    arg0[h] = fma2(l2[h], splat(kLog2e), A.nm0[h]);
+    argw[h] = fma2(wl[h], splat(kLog2e), A.nmw[h]);
+  }
+  lazy_rescale(A, arg0, argw, l2, wl);
+  accumulate_plane(A, pi.d, arg0, argw, a, sc0, sc1);
+}
+
+// Plane visiting order of sample b: classes R = 0..3 of the ordinary planes, then the special ones.  Both the producer
+// and the consumers derive it from the same table, so the ring carries the planes in exactly the order they are consumed.
+__device__ __forceinline__ void build_order(const PlaneInfo* T, int N, unsigned char* ord, int* cnt) {
+  int o = 0;
+  for (int cls = 0; cls < 5; ++cls) {
+    int c = 0;
+    for (int n = 0; n < N; ++n) {
+      const int k = T[n].special ? 4 : (T[n].k0 & 3);
+      if (k == cls) { ord[o++] = (unsigned char)n; ++c; }
+    }
+    cnt[cls] = c;
+  }
+}
+
+template <int kMaxThreads, int kMaxRegs>
+__global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med_fwd_fast_kernel(const MedParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Layout L = make_layout(p.S, p.G, p.slotf, p.wpad, p.wcopy, 0);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_full);
+  uint64_t* empty = reinterpret_cast<uint64_t*>(smem + L.off_empty);
+  float* img = reinterpret_cast<float*>(smem + L.off_img);
+  float* ring = reinterpret_cast<float*>(smem + L.off_ring);
+  unsigned char* ord = smem + L.off_aux;                    // [kMaxN] consumer copy, [kMaxN] producer copy
+  int* cnt = reinterpret_cast<int*>(smem + L.off_aux + 2 * kMaxN);
+  const PlaneTab T = tab_ptrs(smem, L);
+  PlaneInfo* Tp = reinterpret_cast<PlaneInfo*>(smem + L.off_aux + 2 * kMaxN + 64);   // producer's own table
+
+  const int ncons = blockDim.x - 32;
+  const int tid = threadIdx.x;
+  const int rows = p.B * p.H;
+  const int W = p.W, N = p.N;
+  const int wr = (W + 3) & ~3;
+  const int G = p.G, S = p.S, slotf = p.slotf;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], ncons / 32);
+    }
+    fence_barrier_init();
+  }
+  // zero the ring once: the front pad and the tail of every slot are never written again (bulk copies cover exactly
+  // [kPad, kPad + wr) of a slot), so windows that leave the row read zeros
+  for (int i = tid; i < S * G * slotf; i += blockDim.x) ring[i] = 0.f;
+  fence_proxy_async();
+  __syncthreads();
+
+  if (tid >= ncons) {
+    // ------------------------------------------------------------------ producer warp
+    if (tid == ncons) {
+      unsigned char* ordp = ord + kMaxN;
+      int cntp[5];
+      int slot = 0, cur_b = -1;
+      uint32_t par = 0;
+      const long long plane = (long long)p.H * p.pitch;
+      for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int b = row / p.H, y = row % p.H;
+        if (b != cur_b) {
+          fill_tab(p, Tp, b, 0, 1);
+          build_order(Tp, N, ordp, cntp);
+          cur_b = b;
+        }
+        const float* src0 = p.logits + ((long long)b * N * p.H + y) * p.pitch;
+        for (int i0 = 0; i0 < N; i0 += G) {
+          const int c = min(G, N - i0);
+          while (!mbar_try_wait(&empty[slot], par ^ 1)) __nanosleep(32);
+          mbar_arrive_expect_tx(&full[slot], (uint32_t)(c * wr * 4));
+          for (int q = 0; q < c; ++q)
+            bulk_g2s(ring + ((size_t)slot * G + q) * slotf + kPad, src0 + ordp[i0 + q] * plane, (uint32_t)(wr * 4), &full[slot]);
+          if (++slot == S) { slot = 0; par ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers
+  const int xb = tid * kPX;
+  const bool active = xb < W;
+  const float cW = 0.5f * (float)(W - 1);
+  const int lane = tid & 31;
+  const int wz = ((W + 3) & ~3) + 4;
+  const int wcopy = p.wcopy;
+  float g0[kPX];
+#pragma unroll
+  for (int i = 0; i < kPX; ++i) g0[i] = __ldg(p.g0x + min(xb + i, W - 1));
+  const float2 g0p[2] = {make_float2(g0[0], g0[1]), make_float2(g0[2], g0[3])};
+  const float2 nxf[2] = {make_float2(-(float)xb, -(float)(xb + 1)), make_float2(-(float)(xb + 2), -(float)(xb + 3))};
+  int slot = 0, q = 0, cur_b = -1;
+  uint32_t par = 0;
+
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = row / p.H, y = row % p.H;
+    named_bar_sync(1, ncons);  // previous row fully consumed: tables / image rows may be overwritten
+    if (b != cur_b) {
+      fill_tab(p, T, b, tid, ncons);
+      named_bar_sync(1, ncons);
+      if (tid == 0) build_order(T, N, ord, cnt);
+      cur_b = b;
+    }
+    stage_image(img, p.image + (size_t)b * 3 * p.H * W, y, p.H, W, p.wcopy, tid, ncons);
+    named_bar_sync(1, ncons);
+
+    FastAcc A;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      A.nm0[h] = A.nmw[h] = splat(INFINITY);
+      A.z0[h] = A.dacc[h] = A.zw[h] = splat(0.f);
+      A.pacc[0][h] = A.pacc[1][h] = A.pacc[2][h] = splat(0.f);
+    }
+
+    int i = 0;
+    // one step of the ring: returns the staged row of the i-th plane in visiting order (element 0), after the barrier
+    // wait of its group; `release` hands a finished group back to the producer
+    auto acquire = [&]() -> const float* {
+      if (q == 0) mbar_wait(&full[slot], par);
+      return ring + ((size_t)slot * G + q) * slotf + kPad;
+    };
+    auto release = [&]() {
+      ++i;
+      if (++q == G || i == N) {
+        q = 0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+        if (++slot == S) { slot = 0; par ^= 1; }
+      }
+    };
+    const int c0 = cnt[0], c1 = cnt[1], c2 = cnt[2], c3 = cnt[3], c4 = cnt[4];
+    for (int c = 0; c < c0; ++c) {
+      const float* rowp = acquire();
+      if (active) fast_plane<0>(A, rowp, img, T[ord[i]], xb, wr, wz, wcopy, cW, g0p, nxf);
+      release();
+    }
+    for (int c = 0; c < c1; ++c) {
+      const float* rowp = acquire();
+      if (active) fast_plane<1>(A, rowp, img, T[ord[i]], xb, wr, wz, wcopy, cW, g0p, nxf);
+      release();
+    }
+    for (int c = 0; c < c2; ++c) {
+      const float* rowp = acquire();
+      if (active) fast_plane<2>(A, rowp, img, T[ord[i]], xb, wr, wz, wcopy, cW, g0p, nxf);
+      release();
+    }
+    for (int c = 0; c < c3; ++c) {
+      const float* rowp = acquire();
+      if (active) fast_plane<3>(A, rowp, img, T[ord[i]], xb, wr, wz, wcopy, cW, g0p, nxf);
+      release();
+    }
+    for (int c = 0; c < c4; ++c) {
+      const float* rowp = acquire();
+      if (active) special_plane(A, rowp, img, T[ord[i]], xb, W, wcopy, cW, g0);
+      release();
+    }
+
+    if (active) {
+      float o[kPX];
+      const size_t r1 = ((size_t)b * p.H + y) * W;
+      const float m0v[4] = {-A.nm0[0].x, -A.nm0[0].y, -A.nm0[1].x, -A.nm0[1].y};
+      const float mwv[4] = {-A.nmw[0].x, -A.nmw[0].y, -A.nmw[1].x, -A.nmw[1].y};
+      const float z0v[4] = {A.z0[0].x, A.z0[0].y, A.z0[1].x, A.z0[1].y};
+      const float zwv[4] = {A.zw[0].x, A.zw[0].y, A.zw[1].x, A.zw[1].y};
+      if (p.disp) {
+        const float dv[4] = {A.dacc[0].x, A.dacc[0].y, A.dacc[1].x, A.dacc[1].y};
+#pragma unroll
+        for (int k = 0; k < kPX; ++k) o[k] = dv[k] / z0v[k];
+        store_row4(p.disp + r1, xb, o, W);
+      }
+      if (p.pan) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float pv[4] = {A.pacc[c][0].x, A.pacc[c][0].y, A.pacc[c][1].x, A.pacc[c][1].y};
+#pragma unroll
+          for (int k = 0; k < kPX; ++k) o[k] = pv[k] / zwv[k];
+          store_row4(p.pan + (((size_t)b * 3 + c) * p.H + y) * W, xb, o, W);
+        }
+      }
+      if (p.lse0) {
+#pragma unroll
+        for (int k = 0; k < kPX; ++k) o[k] = (m0v[k] + lg2f(z0v[k])) * kLn2;
+        store_row4(p.lse0 + r1, xb, o, W);
+      }
+      if (p.lsew) {
+#pragma unroll
+        for (int k = 0; k < kPX; ++k) o[k] = (mwv[k] + lg2f(zwv[k])) * kLn2;
+        store_row4(p.lsew + r1, xb, o, W);
+      }
+    }
+  }
+}
+
 // Measured on B200 (640-px rows): 3 CTAs/SM at 96 registers beats 2 CTAs/SM at 112 registers (0.28 vs 0.33 ms): the
 // kernel is latency- rather than issue-bound, so occupancy wins.  FALN_MED_TUNE_2CTA selects the 112-register variant.
 int pick_config(MedParams& p, int n_aux_rows, int* threads, int* smem_bytes, bool* narrow) {
@@ -1104,7 +1439,26 @@ extern "C" int faln_med_fwd(const float* logits, const float* image, const float
   const bool masks = maskL != nullptr;
   int threads, smem;
   bool narrow;
+  // fast path: no masks, 16-byte aligned rows whose pad columns [W, ceil4(W)) are zero (FALN_MED_ZERO_PAD promise, or
+  // W % 4 == 0), N <= 128
+  if (!masks && !(flags & (FALN_MED_FORCE_GENERIC | FALN_MED_NO_FAST)) && logit_pitch % 4 == 0 &&
+      (W % 4 == 0 || (flags & FALN_MED_ZERO_PAD))) {
+    // aux region: two order lists + counts + the producer's own plane table (320 + kMaxN * 32 bytes)
+    const int aux_need = 320 + kMaxN * 32, aux_row = (((W + 3) & ~3) + 2 * kPad) * 4;
+    pick_config(p, (aux_need + aux_row - 1) / aux_row, &threads, &smem, &narrow);
+    auto kern = threads <= 352 ? med_fwd_fast_kernel<352, 96> : med_fwd_fast_kernel<544, 96>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    if (per_sm < 1) per_sm = 1;
+    int grid = sm_count() * per_sm;
+    if (grid > B * H) grid = B * H;
+    kern<<<grid, threads, smem, as_stream(stream)>>>(p);
+    return after_launch("med_fwd_fast_kernel");
+  }
   pick_config(p, masks ? 4 : 0, &threads, &smem, &narrow);
+  // (Measured: capping 1242-px rows -- 352 threads -- at 88 registers so that two CTAs fit an SM is SLOWER, 0.70 vs 0.67 ms:
+  // the spills cost more than the extra warps bring.)
   auto kern = narrow ? (masks ? med_fwd_kernel<true, 288, 112> : med_fwd_kernel<false, 288, 112>)
                      : (masks ? med_fwd_kernel<true, 544, 96> : med_fwd_kernel<false, 544, 96>);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -33,7 +33,10 @@ def planar_to_nhwc_bf16(x, Cp):
 def alloc_planar(B, C, H, W, device, pitch=None):
     """fp32 [B,C,H,W] view with a 16-byte-multiple row pitch (TMA-friendly rows for the MED kernels)."""
     pitch = pitch or ((W + 3) // 4) * 4
-    return torch.empty(B, C, H, pitch, device=device, dtype=torch.float32)[..., :W]
+    buf = torch.empty(B, C, H, pitch, device=device, dtype=torch.float32)
+    if pitch != W:
+        buf[..., W:].zero_()          # the MED fast kernels read the pad columns as zeros (FALN_MED_ZERO_PAD)
+    return buf[..., :W]
 
 
 def nhwc_bf16_to_planar(x, C, pitch=None):

@@ -136,8 +136,9 @@ class MedSynthesis(torch.autograd.Function):
     /root/reference/models/FAL_netB.py:256-273; the image is a leaf without grad)."""
 
     @staticmethod
-    def forward(ctx, logits, image, x_of, d_lvl, g0x, want_masks):
-        r = med_forward_raw(logits, image, x_of, d_lvl, g0x, True, True, want_masks)
+    def forward(ctx, logits, image, x_of, d_lvl, g0x, want_masks, flags=0):
+        r = med_forward_raw(logits, image, x_of, d_lvl, g0x, True, True, want_masks, flags)
+        ctx.flags = flags
         ctx.save_for_backward(logits, image, x_of, d_lvl, g0x, r["pan"], r["disp"], r["lse0"], r["lsew"])
         outs = (r["pan"], r["disp"])
         if want_masks:
@@ -148,23 +149,29 @@ class MedSynthesis(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_pan, g_disp, *_):
         logits, image, x_of, d_lvl, g0x, pan, disp, lse0, lsew = ctx.saved_tensors
-        g = med_backward_raw(logits, image, x_of, d_lvl, g0x, pan, disp, lse0, lsew, g_pan, g_disp)
-        return g, None, None, None, None, None
+        g = med_backward_raw(logits, image, x_of, d_lvl, g0x, pan, disp, lse0, lsew, g_pan, g_disp, ctx.flags)
+        return g, None, None, None, None, None, None
 
 
-def med_section(dlog0, image, min_disp, max_disp, ret_disp=True, ret_subocc=False, ret_pan=False):
+FLAG_ZERO_PAD = 8     # FALN_MED_ZERO_PAD
+FLAG_NO_FAST = 16     # FALN_MED_NO_FAST
+
+
+def med_section(dlog0, image, min_disp, max_disp, ret_disp=True, ret_subocc=False, ret_pan=False, zero_pad=False):
     """FAL_net.forward from ``dlog0`` on, same return convention as the reference
     (/root/reference/models/FAL_netB.py:228-229,285-297): a bare tensor when only the disparity is asked
-    for, else a list ordered [pan?, disp?, maskL?, maskR?]."""
+    for, else a list ordered [pan?, disp?, maskL?, maskR?].  ``zero_pad``: the caller guarantees that ``dlog0`` comes from
+    ``layout.alloc_planar`` (16-byte aligned rows, zeroed pad columns), which enables the fast kernels for W % 4 != 0."""
     B, N, H, W = dlog0.shape
+    flags = FLAG_ZERO_PAD if zero_pad else 0
     d_lvl, x_of = level_tables(min_disp, max_disp, N, W)
     if ret_disp and not ret_subocc and not ret_pan:
         if dlog0.requires_grad and torch.is_grad_enabled():
             g0x = grid_row(W, dlog0.device)
-            return MedSynthesis.apply(dlog0, image, x_of, d_lvl, g0x, False)[1]
+            return MedSynthesis.apply(dlog0, image, x_of, d_lvl, g0x, False, flags)[1]
         return med_disp_only(dlog0, d_lvl)
     g0x = grid_row(W, dlog0.device)
-    res = MedSynthesis.apply(dlog0, image, x_of, d_lvl, g0x, bool(ret_subocc))
+    res = MedSynthesis.apply(dlog0, image, x_of, d_lvl, g0x, bool(ret_subocc), flags)
     out = []
     if ret_pan:
         out.append(res[0])

@@ -122,4 +122,4 @@ class FAL_net(nn.Module):
 
     def forward(self, input_left, min_disp, max_disp, ret_disp=True, ret_subocc=False, ret_pan=False):
         dlog0 = self.logits(input_left, max_disp)
-        return med.med_section(dlog0, input_left, min_disp, max_disp, ret_disp, ret_subocc, ret_pan)
+        return med.med_section(dlog0, input_left, min_disp, max_disp, ret_disp, ret_subocc, ret_pan, zero_pad=True)

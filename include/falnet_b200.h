@@ -57,6 +57,10 @@ long long faln_launch_count(void);
  */
 #define FALN_MED_FORCE_GENERIC 1u
 #define FALN_MED_TUNE_2CTA 2u /* rows <= 1024 px: 2 CTAs/SM at 112 registers instead of 3 CTAs/SM at 96 (tuning aid) */
+#define FALN_MED_ZERO_PAD 8u  /* caller's promise: logit rows are 16-byte aligned, logit_pitch % 4 == 0 and the pad columns
+                               * [W, logit_pitch) hold zeros (what fal_net_b200.layout.alloc_planar produces): enables the
+                               * branch-free fast kernels for W % 4 != 0 (rows with W % 4 == 0 qualify without it) */
+#define FALN_MED_NO_FAST 16u  /* never take the fast kernels (validation of one path against the other) */
 int faln_med_fwd(const float* logits, const float* image, const float* g0x, const float* x_of,
                  const float* d_lvl, float* pan, float* disp, float* maskL, float* maskR, float* lse0,
                  float* lsew, int B, int N, int H, int W, long long logit_pitch, unsigned flags,

@@ -196,3 +196,24 @@ def test_integer_and_near_integer_shifts():
     for nm in ("pan", "disp", "maskL", "maskR", "glogits"):
         e = rel_err(r[nm], ref[nm])
         assert e < TOL, (nm, e)
+
+
+@pytest.mark.parametrize("B,N,H,W", [(2, 49, 5, 1242), (1, 33, 4, 621), (2, 49, 6, 640), (1, 65, 3, 2048), (1, 9, 5, 40)])
+def test_fast_forward_matches_reference_kernel(B, N, H, W):
+    """The branch-free fast forward (planes visited by alignment class, zero-tail ring; FALN_MED_ZERO_PAD layout) against
+    the general kernel on the same padded logits: same math, different summation order over planes -> 1e-5."""
+    from fal_net_b200 import layout, med
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(W + N)
+    logits = layout.alloc_planar(B, N, H, W, dev)
+    logits.copy_((2 * torch.randn(B, N, H, W, generator=g)).to(dev))
+    img = (torch.rand(B, 3, H, W, generator=g) - 0.43).to(dev)
+    mx = torch.full((B, 1, 1), 300.0 if W >= 600 else 0.45 * W, device=dev)
+    mn = mx * 2 / 300
+    d, xo = med.level_tables(mn, mx, N, W)
+    g0x = med.grid_row(W, dev)
+    fast = med.med_forward_raw(logits, img, xo, d, g0x, True, True, False, med.FLAG_ZERO_PAD)
+    slow = med.med_forward_raw(logits, img, xo, d, g0x, True, True, False, med.FLAG_NO_FAST)
+    for k in ("pan", "disp", "lse0", "lsew"):
+        err = float((fast[k] - slow[k]).abs().max() / slow[k].abs().max())
+        assert err < 1e-5, (k, err)

@@ -10,13 +10,19 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fal_net_b200 import med  # noqa: E402
+from fal_net_b200 import layout, med  # noqa: E402
 
 
 def bench(B, N, H, W, iters=10, sets=3, peak=6557.8, flags=0, warm=3):
     dev = torch.device("cuda:0")
     gen = torch.Generator(device=dev).manual_seed(7)
-    L = [2 * torch.randn(B, N, H, W, generator=gen, device=dev) for _ in range(sets)]
+    # logits in the layout the network's last conv writes: 16-byte-multiple row pitch, zeroed pad columns
+    L = []
+    for _ in range(sets):
+        t = layout.alloc_planar(B, N, H, W, dev)
+        t.copy_(2 * torch.randn(B, N, H, W, generator=gen, device=dev))
+        L.append(t)
+    flags |= med.FLAG_ZERO_PAD
     I = [torch.rand(B, 3, H, W, generator=gen, device=dev) - 0.43 for _ in range(sets)]
     gp = torch.randn(B, 3, H, W, generator=gen, device=dev)
     gd = torch.randn(B, 1, H, W, generator=gen, device=dev)
@@ -27,7 +33,7 @@ def bench(B, N, H, W, iters=10, sets=3, peak=6557.8, flags=0, warm=3):
     px = B * H * W
     out = {}
     res = [med.med_forward_raw(L[s], I[s], xo, d, g0x, True, True, True) for s in range(sets)]
-    gl = torch.empty_like(L[0])
+    gl = layout.alloc_planar(B, N, H, W, dev)
 
     def timeit(fn):
         for s in range(warm):
