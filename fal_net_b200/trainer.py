@@ -265,6 +265,12 @@ class GraphedStep:
         with torch.cuda.graph(self.graph):
             self.loss = self._body()
         self.replays = 0
+        # input prefetch: the NEXT batch's host->device copy runs on a copy stream while the current step executes
+        self._copy_stream = torch.cuda.Stream()
+        self._stage = None
+        self._staged = None                              # event: staged batch has landed on the device
+        self._consumed = torch.cuda.Event()              # event: staged batch has been moved into the graph's inputs
+        self._consumed.record()
 
     def _body(self):
         self.opt.zero_grad()
@@ -274,7 +280,28 @@ class GraphedStep:
         self.opt.step()
         return loss.detach()
 
+    def prefetch(self, left, right):
+        """Start copying the next batch (pinned host or device tensors) into a staging buffer on the copy stream; the next
+        ``run()`` without arguments consumes it.  Lets the H2D transfer of step i+1 overlap the kernels of step i."""
+        if self._stage is None:
+            self._stage = (torch.empty_like(self.left), torch.empty_like(self.right))
+        cs = self._copy_stream
+        cs.wait_event(self._consumed)                    # the staging buffers are free again
+        with torch.cuda.stream(cs):
+            self._stage[0].copy_(left, non_blocking=True)
+            self._stage[1].copy_(right, non_blocking=True)
+            self._staged = torch.cuda.Event()
+            self._staged.record(cs)
+
     def run(self, left=None, right=None):
+        if left is None and right is None and self._staged is not None:
+            main = torch.cuda.current_stream()
+            main.wait_event(self._staged)
+            self.left.copy_(self._stage[0], non_blocking=True)     # device-to-device, ~10 us
+            self.right.copy_(self._stage[1], non_blocking=True)
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(main)
+            self._staged = None
         if left is not None:
             self.left.copy_(left, non_blocking=True)
         if right is not None:
