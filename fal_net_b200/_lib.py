@@ -45,6 +45,7 @@ _SIGNATURES = {
     "faln_nhwc_bf16_to_planar": [_p, _p] + [_i] * 5 + [_ll, _p],
     "faln_planar_to_nhwc_bf16": [_p, _p] + [_i] * 5 + [_ll, _p],
     "faln_conv3x3_fwd": [_p] * 8 + [_i] * 10 + [_ll, _i, _p],
+    "faln_conv3x3_logits_disp": [_p] * 6 + [_i] * 7 + [_p],
     "faln_conv3x3_dgrad": [_p] * 5 + [_i] * 12 + [_p],
     "faln_conv3x3_wgrad": [_p] * 3 + [_i] * 10 + [_u, _p],
     "faln_f32_to_bf16": [_p, _p, _ll, _p],

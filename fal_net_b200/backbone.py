@@ -83,8 +83,10 @@ def fold_logit_conv(w_iconv1, w0):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def forward(model, image, max_disp, tape=None):
-    """dlog0 [B,N,H,W] fp32 planar (16-byte-multiple row pitch).  ``tape`` (a dict) receives what backward needs."""
+def forward(model, image, max_disp, tape=None, disp_lvl=None):
+    """dlog0 [B,N,H,W] fp32 planar (16-byte-multiple row pitch).  ``tape`` (a dict) receives what backward needs.
+    With ``disp_lvl`` [B,N] (inference, no tape) the last layer's epilogue takes the softmax-expectation itself and the
+    function returns the disparity [B,1,H,W]: the logits never reach HBM."""
     bb = model.backbone
     B = image.shape[0]
     flow_val = (max_disp.reshape(B).float() / 100.0).contiguous()                  # :208-209, constant plane per sample
@@ -120,6 +122,8 @@ def forward(model, image, max_disp, tape=None):
             wf = fold_logit_conv(bb.iconv1.weight.detach(), model.conv0.weight.detach())
             N = wf.shape[0]
             Bq, _, H, W = u.shape
+            if disp_lvl is not None and tape is None and CN.logits_disp_supported(W, N):
+                return CN.conv3x3_logits_disp(u, skip, CN.pack_weight(wf, 64), model.conv0.bias, disp_lvl)
             out = layout.alloc_planar(Bq, N, H, W, u.device)
             CN.conv3x3_fwd(u, CN.pack_weight(wf), model.conv0.bias, 1, 0, None, skip, cout=N, planar_out=out)
             if tape is not None:
@@ -129,6 +133,19 @@ def forward(model, image, max_disp, tape=None):
                 tape["image"] = image
             return out
     raise AssertionError("unreachable")
+
+
+def disparity(model, image, min_disp, max_disp):
+    """Inference path (/root/reference/models/FAL_netB.py:228-229, Test_KITTI.py:196): disparity only, no autograd."""
+    from . import med
+    if not image.is_cuda:
+        raise RuntimeError("fal_net_b200.FAL_netB runs on CUDA (sm_100a) only; there is no CPU path")
+    N = model.no_levels
+    d_lvl, _ = med.level_tables(min_disp, max_disp, N, image.shape[3])
+    out = forward(model, image, max_disp, None, disp_lvl=d_lvl)
+    if out.shape[1] == 1 and N != 1:
+        return out
+    return med.med_disp_only(out, d_lvl)
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -100,6 +100,34 @@ def conv3x3_fwd(x, w_krsc, bias=None, stride=1, act=0, residual=None, x2=None, c
     return y
 
 
+def logits_disp_supported(W, n_levels):
+    """The fused logits -> disparity epilogue lives in the row-tile kernel: wide maps, at most 64 levels."""
+    return W >= 192 and n_levels <= 64
+
+
+def conv3x3_logits_disp(x, x2, w_krsc, bias, d_lvl):
+    """Inference form of the last layer: disparity [B,1,H,W] fp32 = sum_n d_lvl[b,n] * softmax_n(conv3x3(cat(x, x2)) + bias),
+    with the N logit planes kept on chip (csrc/conv_tc.cu, row-tile kernel)."""
+    x, x2 = _nhwc(x), _nhwc(x2)
+    B, C1, H, W = x.shape
+    C2 = x2.shape[1]
+    N = d_lvl.shape[1]
+    assert w_krsc.shape == (64, 3, 3, C1 + C2) and w_krsc.dtype == torch.bfloat16 and w_krsc.is_contiguous()
+    assert d_lvl.shape == (B, N) and N <= 64
+    d64 = torch.zeros(B, 64, device=x.device, dtype=torch.float32)          # levels beyond N: weight 0 ...
+    d64[:, :N] = d_lvl
+    b64 = torch.full((64,), float("-inf"), device=x.device, dtype=torch.float32)   # ... and logit -inf
+    b64[:N] = bias.detach().float()
+    disp = torch.empty(B, 1, H, W, device=x.device, dtype=torch.float32)
+    ev = _timed("conv_fwd", 2 * 9 * (C1 + C2) * N * B * H * W, 2 * B * H * W * (C1 + C2) + 4 * B * H * W)
+    rc = _lib.lib().faln_conv3x3_logits_disp(_lib.ptr(x), _lib.ptr(x2), _lib.ptr(w_krsc), _lib.ptr(b64), _lib.ptr(d64),
+                                             _lib.ptr(disp), B, H, W, C1, C2, N, 64, _lib.cur_stream())
+    _lib.check(rc, "faln_conv3x3_logits_disp")
+    if ev is not None:
+        ev.record()
+    return disp
+
+
 def stem_conv(x, w, bias, act, flip_x=False):
     """fp32 NCHW image [B,3,H,W] -> bf16 channels_last [B,Cout,H,W]; w [Cout,3,3,3] fp32."""
     x = _lib.f32c(x)

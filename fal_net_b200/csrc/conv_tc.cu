@@ -55,6 +55,9 @@ struct ConvParams {
   void* out;
   long long out_pitch;
   int out_c;  // channel count (stride) of the NHWC output tensor
+  // inference epilogue of the logits layer (row kernel only): disp = sum_n d_lvl[b,n] * softmax_n(logits + bias)
+  const float* disp_lvl;  // [B, Cout] disparity of each level
+  float* disp_out;        // [B, 1, H, W] fp32; when set nothing else is written (the logits never reach HBM)
 };
 
 // K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -345,7 +348,7 @@ template <int BK, int BN, int STAGES>
 struct RowSmem {
   static constexpr int kHalo = (kHaloCols * kHaloRows * BK * 2 + 1023) / 1024 * 1024;
   static constexpr int kW = BN * BK * 2;                       // one (tap, channel block) weight tile
-  static constexpr int kBars = 1024;
+  static constexpr int kBars = 4096;                           // barriers (first 1 KB) + disparity-epilogue exchange (3 KB)
   static int total(int kb) { return kBars + 1024 + 9 * kb * kW + STAGES * kHalo; }
 };
 
@@ -364,6 +367,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
   uint64_t* acc_empty = acc_full + kAcc;
   uint64_t* wfull = acc_empty + kAcc;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wfull + 1);
+  float* exch = reinterpret_cast<float*>(smem_raw + 1024);    // [2][128][3]: partial softmax sums of the second column half
   unsigned char* wsm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + SL::kBars + 1023) & ~uintptr_t(1023));
   const int kb = p.kblocks1 + p.kblocks2;
   unsigned char* stages = wsm + (size_t)9 * kb * SL::kW;      // kW is a multiple of 1024 (BN * BK * 2 >= 2048)
@@ -466,6 +470,51 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
       const int a = it & 1;
       mbar_wait(&acc_full[a], (it >> 1) & 1);
       tc_fence_after();
+      if (BN == 64 && p.disp_out != nullptr) {
+        // fused softmax-expectation (reference :216-229).  The two warps of a lane quadrant each reduce 32 planes
+        // (bias padded with -inf and d_lvl with 0 beyond N, so no per-plane predicates), exchange their partial
+        // (max, sum, weighted sum) through shared memory and the first one writes the disparity.
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (uint32_t)(a * BN + half * 32) + ((uint32_t)(quad * 32) << 16), r);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[a]);
+        const float4* bp = reinterpret_cast<const float4*>(p.bias) + half * 8;
+        const float4* dp = reinterpret_cast<const float4*>(p.disp_lvl + (size_t)b * 64) + half * 8;
+        float v[32];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bq = __ldg(bp + q);
+          v[4 * q] = __uint_as_float(r[4 * q]) + bq.x;
+          v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bq.y;
+          v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bq.z;
+          v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bq.w;
+          mx = fmaxf(fmaxf(fmaxf(mx, v[4 * q]), fmaxf(v[4 * q + 1], v[4 * q + 2])), v[4 * q + 3]);
+        }
+        const float nm = -mx * 1.4426950408889634f;
+        float z = 0.f, acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 dq = __ldg(dp + q);
+          const float e0 = ex2f(fmaf(v[4 * q], 1.4426950408889634f, nm)), e1 = ex2f(fmaf(v[4 * q + 1], 1.4426950408889634f, nm));
+          const float e2 = ex2f(fmaf(v[4 * q + 2], 1.4426950408889634f, nm)), e3 = ex2f(fmaf(v[4 * q + 3], 1.4426950408889634f, nm));
+          z += (e0 + e1) + (e2 + e3);
+          acc = fmaf(dq.x, e0, fmaf(dq.y, e1, fmaf(dq.z, e2, fmaf(dq.w, e3, acc))));
+        }
+        float* ex = exch + ((it & 1) * 128 + m) * 3;
+        if (half == 1) {
+          ex[0] = mx; ex[1] = z; ex[2] = acc;
+        }
+        named_bar_sync(2 + quad, 64);
+        if (half == 0 && valid) {
+          const float m1 = ex[0], z1 = ex[1], a1 = ex[2];
+          const float mm = fmaxf(mx, m1);                     // half 0 always holds real planes: mm is finite
+          const float f0 = ex2f((mx - mm) * 1.4426950408889634f), f1 = ex2f((m1 - mm) * 1.4426950408889634f);
+          p.disp_out[pix] = (acc * f0 + a1 * f1) / (z * f0 + z1 * f1);
+        }
+        continue;
+      }
       uint32_t r[CW];
       const uint32_t taddr = tmem_base + (uint32_t)(a * BN + half * CW) + ((uint32_t)(quad * 32) << 16);
       if (CW == 32) tmem_ld32(taddr, reinterpret_cast<uint32_t(&)[32]>(r));
@@ -567,6 +616,7 @@ int try_row_kernel(const void* x, const void* x2, const void* wptr, int wrows, C
   static const bool disabled = getenv("FALN_CONV_NO_ROW") != nullptr;
   if (disabled || p.stride != 1 || p.ncls != 1 || p.cls[0].n != 9 || p.out_mul != 1) return 0;
   if (wrows != 32 && wrows != 64) return 0;
+  if (p.disp_out && wrows != 64) return 0;
   if (p.W < 192) return 0;
   const int kb = p.kblocks1 + p.kblocks2;
   const int halo = (kHaloCols * kHaloRows * BK * 2 + 1023) / 1024 * 1024;
@@ -623,10 +673,11 @@ using namespace faln;
 // x [B,H,W,C1] bf16 NHWC, x2 [B,H,W,C2] or NULL (channel-concatenated after x), w [Cout_pad, 3, 3, C1+C2] bf16 (KRSC, rows
 // beyond Cout zero), bias [Cout] fp32 or NULL, residual [B,Ho,Wo,out_c] bf16 or NULL.
 // y: bf16 NHWC [B,Ho,Wo,out_c] (planar = 0) or fp32 planar [B,Cout,Ho,out_pitch] (planar = 1).
-extern "C" int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, const float* bias, const float* ctab,
-                                const float* cscale, const void* residual, void* y, int B, int H, int W, int C1, int C2, int Cout, int Cout_pad, int stride, int act,
-                                int planar, long long out_pitch, int out_c, faln_stream_t stream) {
-  FALN_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0, "faln_conv3x3_fwd: null pointer / bad shape");
+static int conv3x3_fwd_impl(const void* x, const void* x2, const void* w, const float* bias, const float* ctab,
+                            const float* cscale, const void* residual, void* y, int B, int H, int W, int C1, int C2, int Cout,
+                            int Cout_pad, int stride, int act, int planar, long long out_pitch, int out_c,
+                            const float* disp_lvl, float* disp_out, faln_stream_t stream) {
+  FALN_REQUIRE(x && w && (y || disp_out) && B > 0 && H > 0 && W > 0, "faln_conv3x3_fwd: null pointer / bad shape");
   FALN_REQUIRE(stride == 1 || stride == 2, "faln_conv3x3_fwd: stride must be 1 or 2");
   FALN_REQUIRE((ctab == nullptr) == (cscale == nullptr), "faln_conv3x3_fwd: ctab and cscale go together");
   FALN_REQUIRE(C1 % 32 == 0 && C2 % 32 == 0 && C1 > 0 && (x2 != nullptr) == (C2 > 0),
@@ -657,9 +708,14 @@ extern "C" int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, co
   p.cls[0].oh = p.cls[0].ow = 0;
   p.out_mul = 1; p.out_H = p.Ho; p.out_W = p.Wo;
   p.accum = 0; p.dact = 0; p.ysave = nullptr; p.ysave_c = 0; p.res_c = out_c;
+  p.disp_lvl = disp_lvl; p.disp_out = disp_out;
   {
     const int rr = try_row_kernel(x, x2, w, Cout_pad, p, BK, C2, as_stream(stream));
     if (rr != 0) return rr > 0 ? 0 : rr;
+  }
+  if (disp_out) {
+    set_error("faln_conv3x3_logits_disp: layer not eligible for the row-tile kernel (needs stride 1, W >= 192, Cout_pad == 64)");
+    return FALN_ERR_ARG;
   }
   CUtensorMap a1, a2, wm;
   if (!make_act_map(&a1, x, B, H, W, C1, BK, stride) || !make_w_map(&wm, w, Cout_pad, 9 * (C1 + C2), BK, BN) ||
@@ -669,6 +725,28 @@ extern "C" int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, co
   }
   if (!x2) a2 = a1;
   return dispatch(BK, BN, a1, a2, wm, p, as_stream(stream));
+}
+
+extern "C" int faln_conv3x3_fwd(const void* x, const void* x2, const void* w, const float* bias, const float* ctab,
+                                const float* cscale, const void* residual, void* y, int B, int H, int W, int C1, int C2, int Cout, int Cout_pad, int stride, int act,
+                                int planar, long long out_pitch, int out_c, faln_stream_t stream) {
+  return conv3x3_fwd_impl(x, x2, w, bias, ctab, cscale, residual, y, B, H, W, C1, C2, Cout, Cout_pad, stride, act, planar,
+                          out_pitch, out_c, nullptr, nullptr, stream);
+}
+
+// Inference form of the logits layer: disp[b,0,h,w] = sum_n d_lvl[b,n] * softmax_n(conv3x3(cat(x, x2)) + bias)_n, fused into
+// the epilogue of the row-tile kernel so that the N logit planes are never written (reference: conv :174,215 + softmax and
+// expectation :216-229).  bias is [64] padded with -inf beyond N, d_lvl is [B,64] padded with 0 (so the epilogue needs no
+// per-plane predicates).  Needs W >= 192 and N <= 64; returns FALN_ERR_ARG otherwise (the caller then writes the logits
+// and calls faln_med_disp).
+extern "C" int faln_conv3x3_logits_disp(const void* x, const void* x2, const void* w, const float* bias, const float* d_lvl,
+                                        float* disp, int B, int H, int W, int C1, int C2, int N, int Cout_pad,
+                                        faln_stream_t stream) {
+  FALN_REQUIRE(d_lvl && disp && bias && N > 0 && N <= 64 && Cout_pad == 64, "faln_conv3x3_logits_disp: need N <= 64 padded to 64 rows");
+  FALN_REQUIRE(((reinterpret_cast<uintptr_t>(d_lvl) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0,
+               "faln_conv3x3_logits_disp: bias [64] and d_lvl [B,64] must be 16-byte aligned");
+  return conv3x3_fwd_impl(x, x2, w, bias, nullptr, nullptr, nullptr, nullptr, B, H, W, C1, C2, N, Cout_pad, 1, 0, 1, W, N,
+                          d_lvl, disp, stream);
 }
 
 // Data gradient of the 3x3 convolution (pad 1, stride 1 or 2) on the same tcgen05 kernel:

@@ -121,5 +121,8 @@ class FAL_net(nn.Module):
         return backbone.logits(self, input_left, max_disp)
 
     def forward(self, input_left, min_disp, max_disp, ret_disp=True, ret_subocc=False, ret_pan=False):
+        if ret_disp and not ret_subocc and not ret_pan and not (
+                torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+            return backbone.disparity(self, input_left, min_disp, max_disp)      # inference: fused disparity epilogue
         dlog0 = self.logits(input_left, max_disp)
         return med.med_section(dlog0, input_left, min_disp, max_disp, ret_disp, ret_subocc, ret_pan, zero_pad=True)

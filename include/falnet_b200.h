@@ -203,6 +203,13 @@ int faln_f32_to_bf16(const float* src, void* dst, long long n, faln_stream_t str
  * max_tiles >= max_j 9 * (Cout/32) * (Cin_used/32).  `jobs` is device memory. */
 int faln_pack_dgrad_batched(const void* w16, void* wd16, const long long* jobs, int njobs, int max_tiles,
                             faln_stream_t stream);
+/* Inference form of the last layer (reference models/FAL_netB.py:174,215-229; Test_KITTI.py:196): the folded logits conv
+ * with the softmax-expectation over the N disparity levels fused into its epilogue, disp [B,1,H,W] fp32 =
+ * sum_n d_lvl[b,n] * softmax_n(conv3x3(cat(x, x2)) + bias).  The logit planes never reach HBM.  Stride 1, W >= 192,
+ * N <= 64 with the weight padded to 64 rows, bias [64] padded with -inf and d_lvl [B,64] padded with 0 (both 16-byte
+ * aligned); otherwise FALN_ERR_ARG (write the logits and call faln_med_disp). */
+int faln_conv3x3_logits_disp(const void* x, const void* x2, const void* w, const float* bias, const float* d_lvl,
+                             float* disp, int B, int H, int W, int C1, int C2, int N, int Cout_pad, faln_stream_t stream);
 /* Weight gradient of the 3x3 convolution (pad 1, stride 1 or 2) on tcgen05 -- replaces the cuDNN wgrad autograd runs for
  * nn.Conv2d of /root/reference/models/FAL_netB.py:99-127 in loss.backward() (/root/reference/Train_Stage1_K.py:260).
  *   dW[co, kh, kw, ci_off + ci] += sum_{b,ho,wo} g[b,ho,wo,co] * x[b, ho*s+kh-1, wo*s+kw-1, ci]

@@ -185,3 +185,21 @@ def test_graphed_step_matches_eager():
     for a, b in zip(le, lg):
         assert abs(a - b) <= 5e-3 * abs(a), (le, lg)         # wgrad split-K order differs run to run (fp32 red.add)
     assert rel_l2(pg, pe) < 1e-3
+
+
+def test_fused_disparity_epilogue_matches_unfused():
+    """Inference: the logits layer with the softmax-expectation fused into its epilogue (the N planes never reach HBM)
+    against the same layer writing fp32 logits followed by the disparity kernel (reference :215-229)."""
+    from fal_net_b200 import backbone, med
+    dev = _dev()
+    m, _ = _model()
+    B, H, W = 2, 37, 333
+    img = images(B, H, W, 5).to(dev)
+    mn, mx = (t.to(dev) for t in disp_range(B))
+    with torch.no_grad():
+        fused = m(img, mn, mx, ret_disp=True, ret_subocc=False, ret_pan=False)
+        d_lvl, _ = med.level_tables(mn, mx, m.no_levels, W)
+        logits = backbone.forward(m, img, mx, None)
+        unfused = med.med_disp_only(logits, d_lvl)
+    assert fused.shape == unfused.shape == (B, 1, H, W)
+    assert float((fused - unfused).abs().max() / unfused.abs().max()) < 1e-4
