@@ -24,6 +24,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "med3.h"
 
 namespace faln {
 namespace {
@@ -293,6 +294,36 @@ __device__ __forceinline__ void fill_tab(const MedParams& p, PlaneTab t, int b, 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Clean-up mode (FALN_MED_CLEANUP_, internal): the third-generation forward (med3.cu) accumulates the softmax sums
+// without a running maximum and leaves the rows whose sums left the safe range to the forward kernel of this file,
+// marked by lse0[b, 0, y, 0] = NaN.  In clean-up mode a CTA first builds the list of its rows that need work and exits
+// at once when there is none (the normal case: one global-load latency).
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned FALN_MED_CLEANUP_ = 0x100u;
+constexpr int kTodoWords = 32;                       // up to 1024 rows per CTA
+
+// All threads of the CTA.  Returns false when the CTA has nothing to do.  todo: bit i = i-th row of this CTA
+// (row = blockIdx.x + i * gridDim.x) needs work.
+__device__ __forceinline__ bool build_todo(const MedParams& p, const float* lse0, unsigned* todo) {
+  const int rows = p.B * p.H;
+  if (threadIdx.x < kTodoWords) todo[threadIdx.x] = 0u;
+  __syncthreads();
+  bool mine = false;
+  for (int i = threadIdx.x; blockIdx.x + (long long)i * gridDim.x < rows; i += blockDim.x) {
+    const int row = blockIdx.x + i * gridDim.x;
+    const float v = __ldcg(lse0 + (size_t)row * p.W);
+    const bool need = v != v;
+    if (need) {
+      atomicOr(&todo[i >> 5], 1u << (i & 31));
+      mine = true;
+    }
+  }
+  return __syncthreads_or(mine) != 0;
+}
+__device__ __forceinline__ bool todo_bit(const unsigned* todo, int i) { return (todo[i >> 5] >> (i & 31)) & 1u; }
+
 // Producer: stream `sweeps` x N plane rows of image row (b, y) through the ring, G rows per mbarrier group.
 __device__ __forceinline__ void produce_row(const MedParams& p, unsigned char* smem, const Layout& L, int b, int y,
                                             int sweeps, int& slot, uint32_t& par) {
@@ -401,6 +432,9 @@ __global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med_fwd_ker
   const int tid = threadIdx.x;
   const int rows = p.B * p.H;
   const int W = p.W, N = p.N;
+  __shared__ unsigned todo[kTodoWords];
+  const bool cleanup = (p.flags & FALN_MED_CLEANUP_) != 0;
+  if (cleanup && !build_todo(p, p.lse0, todo)) return;
 
   if (tid == 0) {
     for (int s = 0; s < p.S; ++s) {
@@ -417,8 +451,10 @@ __global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med_fwd_ker
     if (tid == ncons) {
       int slot = 0;
       uint32_t par = 0;
-      for (int row = blockIdx.x; row < rows; row += gridDim.x)
+      for (int row = blockIdx.x, it = 0; row < rows; row += gridDim.x, ++it) {
+        if (cleanup && !todo_bit(todo, it)) continue;
         produce_row(p, smem, L, row / p.H, row % p.H, kMasks ? 2 : 1, slot, par);
+      }
     }
     return;
   }
@@ -446,7 +482,8 @@ __global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med_fwd_ker
   int cur_b = -1;
   const int plane_head_step = (int)(((long long)p.H * p.pitch) & 3);
 
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+  for (int row = blockIdx.x, it = 0; row < rows; row += gridDim.x, ++it) {
+    if (cleanup && !todo_bit(todo, it)) continue;
     const int b = row / p.H, y = row % p.H;
     named_bar_sync(1, ncons);  // previous row fully consumed: tables / image rows may be overwritten
     if (b != cur_b) {
@@ -1439,10 +1476,33 @@ extern "C" int faln_med_fwd(const float* logits, const float* image, const float
   const bool masks = maskL != nullptr;
   int threads, smem;
   bool narrow;
+  const bool aligned_rows = logit_pitch % 4 == 0 && (W % 4 == 0 || (flags & FALN_MED_ZERO_PAD));
+  // third generation (med3.cu): barrier-free register gathers, max-free softmax sums; needs the lse outputs (they carry the
+  // "recompute this row" mark) and is followed by a clean-up launch of the robust kernel of this file
+  if (!(flags & (FALN_MED_FORCE_GENERIC | FALN_MED_NO_FAST | FALN_MED_NO_V3)) && aligned_rows && lse0 && lsew &&
+      (long long)B * H <= (long long)sm_count() * 32 * kTodoWords) {
+    m3::M3Params q{};
+    q.force_generic = (flags & FALN_MED_V3_GENERIC) ? 1 : 0;
+    q.logits = logits; q.image = image; q.g0x = g0x; q.x_of = x_of; q.d_lvl = d_lvl;
+    q.pan = pan; q.disp = disp; q.maskL = maskL; q.maskR = maskR; q.lse0 = lse0; q.lsew = lsew;
+    q.B = B; q.N = N; q.H = H; q.W = W; q.pitch = logit_pitch;
+    const int rc = m3::med3_launch_fwd(q, masks, as_stream(stream));
+    if (rc < 0) return rc;
+    if (rc == 1) {
+      p.flags |= FALN_MED_CLEANUP_;
+      pick_config(p, masks ? 4 : 0, &threads, &smem, &narrow);
+      auto kern = narrow ? (masks ? med_fwd_kernel<true, 288, 112> : med_fwd_kernel<false, 288, 112>)
+                         : (masks ? med_fwd_kernel<true, 544, 96> : med_fwd_kernel<false, 544, 96>);
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      int grid = sm_count();
+      if (grid > B * H) grid = B * H;
+      kern<<<grid, threads, smem, as_stream(stream)>>>(p);
+      return after_launch("med_fwd_kernel<cleanup>");
+    }
+  }
   // fast path: no masks, 16-byte aligned rows whose pad columns [W, ceil4(W)) are zero (FALN_MED_ZERO_PAD promise, or
   // W % 4 == 0), N <= 128
-  if (!masks && !(flags & (FALN_MED_FORCE_GENERIC | FALN_MED_NO_FAST)) && logit_pitch % 4 == 0 &&
-      (W % 4 == 0 || (flags & FALN_MED_ZERO_PAD))) {
+  if (!masks && !(flags & (FALN_MED_FORCE_GENERIC | FALN_MED_NO_FAST)) && aligned_rows) {
     // aux region: two order lists + counts + the producer's own plane table (320 + kMaxN * 32 bytes)
     const int aux_need = 320 + kMaxN * 32, aux_row = (((W + 3) & ~3) + 2 * kPad) * 4;
     pick_config(p, (aux_need + aux_row - 1) / aux_row, &threads, &smem, &narrow);
@@ -1490,6 +1550,17 @@ extern "C" int faln_med_bwd(const float* logits, const float* image, const float
   p.logit_bytes = (((long long)B * N * H - 1) * logit_pitch + W) * 4;
   int threads, smem;
   bool narrow;
+  const bool aligned_rows = logit_pitch % 4 == 0 && (W % 4 == 0 || (flags & FALN_MED_ZERO_PAD));
+  if (!(flags & (FALN_MED_FORCE_GENERIC | FALN_MED_NO_FAST | FALN_MED_NO_V3)) && aligned_rows) {
+    m3::M3Params q{};
+    q.force_generic = (flags & FALN_MED_V3_GENERIC) ? 1 : 0;
+    q.logits = logits; q.image = image; q.g0x = g0x; q.x_of = x_of; q.d_lvl = d_lvl;
+    q.pan_in = pan; q.disp_in = disp; q.lse0_in = lse0; q.lsew_in = lsew;
+    q.g_pan = g_pan; q.g_disp = g_disp; q.g_logits = g_logits; q.g_pitch = g_pitch;
+    q.B = B; q.N = N; q.H = H; q.W = W; q.pitch = logit_pitch;
+    const int rc = m3::med3_launch_bwd(q, as_stream(stream));
+    if (rc != 0) return rc < 0 ? rc : FALN_OK;
+  }
   pick_config(p, 6, &threads, &smem, &narrow);
   auto kern = narrow ? med_bwd_kernel<288, 112> : med_bwd_kernel<544, 96>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -61,6 +61,9 @@ long long faln_launch_count(void);
                                * [W, logit_pitch) hold zeros (what fal_net_b200.layout.alloc_planar produces): enables the
                                * branch-free fast kernels for W % 4 != 0 (rows with W % 4 == 0 qualify without it) */
 #define FALN_MED_NO_FAST 16u  /* never take the fast kernels (validation of one path against the other) */
+#define FALN_MED_NO_V3 32u    /* skip the third-generation kernels (csrc/med3.cu: barrier-free gathers, max-free softmax
+                               * sums + clean-up launch) and use the second-generation ones (A/B comparison) */
+#define FALN_MED_V3_GENERIC 64u /* third generation: every plane on its per-pixel generic code (testing) */
 int faln_med_fwd(const float* logits, const float* image, const float* g0x, const float* x_of,
                  const float* d_lvl, float* pan, float* disp, float* maskL, float* maskR, float* lse0,
                  float* lsew, int B, int N, int H, int W, long long logit_pitch, unsigned flags,
