@@ -499,27 +499,31 @@ int env_int(const char* name, int dflt) {
 }
 
 // Threads, ring shape and CTAs/SM for a row width.  Returns the dynamic shared-memory size, or 0 when nothing fits.
-int configure(M3Params& p, int n_rows, bool with_img, int* threads, int* ctas) {
+// want_small: CTAs/SM to aim for on rows of <= 640 px (192 threads); 1242-px rows (352 threads) aim for 2, wider rows 1.
+// Ring shapes are tried in order of plane rows in flight, (S - 1) * G: the stream must cover the HBM latency
+// (~35 KB per SM at 6.5 TB/s) while one group is being consumed.
+int configure(M3Params& p, int n_rows, bool with_img, int want_small, int* threads, int* ctas) {
   const int groups = (p.W + kPX - 1) / kPX;
   const int ncw = (groups + 31) / 32;
   *threads = (ncw + 1) * 32;
-  int want = *threads <= 192 ? 4 : (*threads <= 352 ? 2 : 1);
+  int want = *threads <= 192 ? want_small : (*threads <= 352 ? 2 : 1);
   want = env_int("FALN_MED3_CTAS", want);
+  if (want < 1) want = 1;
   if (*threads > 352) want = 1;
   else if (*threads > 192 && want > 2) want = 2;
+  else if (want > 4) want = 4;
+  static const int shapes[][2] = {{4, 4}, {4, 3}, {2, 5}, {2, 4}, {4, 2}, {2, 3}, {1, 5}, {2, 2}, {1, 3}, {1, 2}};   // {G, S}
   const int envS = env_int("FALN_MED3_S", 0), envG = env_int("FALN_MED3_G", 0);
   for (int ct = want; ct >= 1; --ct) {
     const int budget = (228 * 1024) / ct - 1024 - 64;
-    // prefer groups of 4 planes with 3 groups in flight; shrink the group before giving up a CTA per SM
-    for (int G = envG ? envG : 4; G >= 1; G = (envG ? 0 : G >> 1)) {
-      for (int S = envS ? envS : 3; S >= 2; S = (envS ? 0 : S - 1)) {
-        const int need = make_smem(p.W, S, G, n_rows, with_img).total;
-        if (need <= budget && need <= 227 * 1024) {
-          p.S = S;
-          p.G = G;
-          *ctas = ct;
-          return need;
-        }
+    for (const auto& sh : shapes) {
+      const int G = envG > 0 ? envG : sh[0], S = envS > 1 ? (envS > 14 ? 14 : envS) : sh[1];
+      const int need = make_smem(p.W, S, G, n_rows, with_img).total;
+      if (need <= budget && need <= 227 * 1024) {
+        p.S = S;
+        p.G = G;
+        *ctas = ct;
+        return need;
       }
     }
   }
@@ -531,7 +535,7 @@ int configure(M3Params& p, int n_rows, bool with_img, int* threads, int* ctas) {
 // Returns 1 when the launch was made, 0 when the shape is not eligible (caller falls back), <0 on error.
 int med3_launch_fwd(M3Params p, bool masks, cudaStream_t stream) {
   int threads = 0, ctas = 1;
-  const int smem = configure(p, masks ? 3 : 0, true, &threads, &ctas);
+  const int smem = configure(p, masks ? 3 : 0, true, masks ? 3 : 4, &threads, &ctas);
   if (!smem) return 0;
   int grid = sm_count() * ctas;
   if (grid > p.B * p.H) grid = p.B * p.H;
@@ -552,7 +556,7 @@ int med3_launch_fwd(M3Params p, bool masks, cudaStream_t stream) {
 
 int med3_launch_bwd(M3Params p, cudaStream_t stream) {
   int threads = 0, ctas = 1;
-  const int smem = configure(p, 6, false, &threads, &ctas);
+  const int smem = configure(p, 6, false, 3, &threads, &ctas);
   if (!smem) return 0;
   int grid = sm_count() * ctas;
   if (grid > p.B * p.H) grid = p.B * p.H;

@@ -155,6 +155,8 @@ class MedSynthesis(torch.autograd.Function):
 
 FLAG_ZERO_PAD = 8     # FALN_MED_ZERO_PAD
 FLAG_NO_FAST = 16     # FALN_MED_NO_FAST
+FLAG_NO_V3 = 32       # FALN_MED_NO_V3: second-generation kernels (A/B comparison)
+FLAG_V3_GENERIC = 64  # FALN_MED_V3_GENERIC: third generation, every plane on the per-pixel generic code (testing)
 
 
 def med_section(dlog0, image, min_disp, max_disp, ret_disp=True, ret_subocc=False, ret_pan=False, zero_pad=False):

@@ -130,17 +130,21 @@ def test_no_mask_variant_and_autograd_wrapper():
 def test_full_size_rows_and_linearity(B, N, H, W):
     """BASELINE.json config #5 / #3 sizes: oracle on random rows + linearity of pan in the image."""
     from fal_net_b200 import med
+    from fal_net_b200 import layout
     dev = _dev()
     gen = torch.Generator(device=dev).manual_seed(7)
-    logits = 2 * torch.randn(B, N, H, W, generator=gen, device=dev)
+    # the layout the network's last conv writes (16-byte row pitch, zero pad columns): third-generation kernels
+    logits = layout.alloc_planar(B, N, H, W, dev)
+    logits.copy_(2 * torch.randn(B, N, H, W, generator=gen, device=dev))
+    ZP = med.FLAG_ZERO_PAD
     img = torch.rand(B, 3, H, W, generator=gen, device=dev) - 0.43
     gp = torch.randn(B, 3, H, W, generator=gen, device=dev)
     gd = torch.randn(B, 1, H, W, generator=gen, device=dev)
     mn, mx = disp_range(B)
     d, xo = O.level_tables(mn, mx, N, W)
     g0x = O.identity_grid(1, 1, 2, W)[0, 0, :, 0].contiguous().to(dev)
-    r = med.med_forward_raw(logits, img, xo.to(dev), d.to(dev), g0x, True, True, True)
-    gl = med.med_backward_raw(logits, img, xo.to(dev), d.to(dev), g0x, r["pan"], r["disp"], r["lse0"], r["lsew"], gp, gd)
+    r = med.med_forward_raw(logits, img, xo.to(dev), d.to(dev), g0x, True, True, True, ZP)
+    gl = med.med_backward_raw(logits, img, xo.to(dev), d.to(dev), g0x, r["pan"], r["disp"], r["lse0"], r["lsew"], gp, gd, ZP)
     rows = [(0, 0), (B - 1, H - 1), (B // 2, H // 2), (B - 1, 1), (0, H - 2), (B // 3, (2 * H) // 3)]
     for b, y in rows:
         lo = logits[b:b + 1, :, y:y + 1].cpu()
@@ -154,8 +158,8 @@ def test_full_size_rows_and_linearity(B, N, H, W):
         assert e < TOL, (b, y, "glogits", e)
     # linearity in the image (same logits): pan(I1 + I2) == pan(I1) + pan(I2)
     img2 = torch.rand(B, 3, H, W, generator=gen, device=dev) - 0.5
-    p2 = med.med_forward_raw(logits, img2, xo.to(dev), d.to(dev), g0x, True, False, False)["pan"]
-    p12 = med.med_forward_raw(logits, img + img2, xo.to(dev), d.to(dev), g0x, True, False, False)["pan"]
+    p2 = med.med_forward_raw(logits, img2, xo.to(dev), d.to(dev), g0x, True, False, False, ZP)["pan"]
+    p12 = med.med_forward_raw(logits, img + img2, xo.to(dev), d.to(dev), g0x, True, False, False, ZP)["pan"]
     assert rel_err(p12, r["pan"] + p2) < 2e-5
     # masks are clamped, disparity stays inside [min_disp, max_disp]
     assert float(r["maskL"].max()) <= 1.0 and float(r["maskR"].max()) <= 1.0
@@ -217,3 +221,61 @@ def test_fast_forward_matches_reference_kernel(B, N, H, W):
     for k in ("pan", "disp", "lse0", "lsew"):
         err = float((fast[k] - slow[k]).abs().max() / slow[k].abs().max())
         assert err < 1e-5, (k, err)
+
+
+def _planar_case(B, N, H, W, seed, maxd=None):
+    from fal_net_b200 import layout, med
+    dev = _dev()
+    g = torch.Generator().manual_seed(seed)
+    logits = layout.alloc_planar(B, N, H, W, dev)
+    logits.copy_((2 * torch.randn(B, N, H, W, generator=g)).to(dev))
+    img = (torch.rand(B, 3, H, W, generator=g) - 0.43).to(dev)
+    gp, gd = torch.randn(B, 3, H, W, generator=g).to(dev), torch.randn(B, 1, H, W, generator=g).to(dev)
+    mx = torch.full((B, 1, 1), maxd if maxd else (300.0 if W >= 600 else 0.45 * W), device=dev)
+    mn = mx * 2 / 300
+    d, xo = med.level_tables(mn, mx, N, W)
+    return logits, img, gp, gd, d, xo, med.grid_row(W, dev)
+
+
+def _all_outputs(logits, img, gp, gd, d, xo, g0x, flags):
+    from fal_net_b200 import layout, med
+    B, N, H, W = logits.shape
+    r = med.med_forward_raw(logits, img, xo, d, g0x, True, True, True, flags)
+    out = layout.alloc_planar(B, N, H, W, logits.device)
+    r["glogits"] = med.med_backward_raw(logits, img, xo, d, g0x, r["pan"], r["disp"], r["lse0"], r["lsew"], gp, gd, flags, out=out)
+    return r
+
+
+@pytest.mark.parametrize("B,N,H,W", [(2, 49, 5, 1242), (1, 33, 4, 621), (3, 49, 7, 640), (1, 65, 3, 2048), (1, 9, 5, 40),
+                                     (2, 49, 300, 1242)])
+def test_third_generation_matches_second(B, N, H, W):
+    """med3.cu (barrier-free register gathers, max-free sums) against the second-generation kernels of med.cu on the
+    production layout: forward with masks, backward; and the third generation's own per-pixel generic code against its
+    class-specialised windows.  Same math, different association -> 2e-5."""
+    from fal_net_b200 import med
+    case = _planar_case(B, N, H, W, W + N)
+    v3 = _all_outputs(*case, med.FLAG_ZERO_PAD)
+    v2 = _all_outputs(*case, med.FLAG_ZERO_PAD | med.FLAG_NO_V3)
+    for k in ("pan", "disp", "maskL", "maskR", "lse0", "lsew", "glogits"):
+        err = float((v3[k] - v2[k]).abs().max() / v2[k].abs().max())
+        assert err < 2e-5, (k, err)
+    if H <= 8:
+        vg = _all_outputs(*case, med.FLAG_ZERO_PAD | med.FLAG_V3_GENERIC)
+        for k in ("pan", "disp", "maskL", "maskR", "glogits"):
+            err = float((vg[k] - v3[k]).abs().max() / v3[k].abs().max())
+            assert err < 2e-5, (k, err)
+
+
+def test_third_generation_overflow_rows_are_recomputed():
+    """Logits beyond the range of the max-free softmax sums: the third-generation forward marks the row and the clean-up
+    launch of the robust kernel recomputes it; results equal the second generation's, untouched rows included."""
+    from fal_net_b200 import med
+    logits, img, gp, gd, d, xo, g0x = _planar_case(2, 49, 6, 640, 77)
+    logits[1, 7, 2, 100] = 300.0          # exp(300) overflows fp32
+    logits[0, :, 4, 321] = -200.0         # every plane underflows at one pixel
+    v3 = _all_outputs(logits, img, gp, gd, d, xo, g0x, med.FLAG_ZERO_PAD)
+    v2 = _all_outputs(logits, img, gp, gd, d, xo, g0x, med.FLAG_ZERO_PAD | med.FLAG_NO_V3)
+    for k in ("pan", "disp", "maskL", "maskR", "lse0", "lsew", "glogits"):
+        assert torch.isfinite(v3[k]).all(), k
+        err = float((v3[k] - v2[k]).abs().max() / v2[k].abs().max())
+        assert err < 2e-5, (k, err)
