@@ -9,7 +9,7 @@
 //   * no running maximum in the softmax sums; forward rows whose sums leave the safe range are left to the robust
 //     second-generation kernel, launched right after in clean-up mode (it exits at once when there is nothing to do).
 //     The signal is in the output itself: lse0[b, 0, y, 0] = NaN marks a row to recompute.
-//   * register caps sized so that 1242-px rows run two CTAs per SM and 640-px rows four.
+//   * register caps sized against the per-sub-partition register file so that 1242-px and 640-px rows run two CTAs per SM.
 // Eligibility (checked on the host, med.cu): 16-byte aligned logit rows, pitch % 4 == 0, zero pad columns, lse outputs
 // present.  Everything else stays on the second-generation kernels.
 #include <math.h>
@@ -175,15 +175,34 @@ struct Ring {
   int S, G, slotf, lane;
   int slot;
   uint32_t par;
+  bool ready;          // the full barrier of the current slot was already seen complete (early try_wait)
+  bool last_row;       // the CTA is on its last row
+  int left;            // groups left in the current row (all sweeps)
 };
 
+// Groups per sweep of a row: every class is cut into groups of up to G planes (same rule as the producer).
+__device__ __forceinline__ int groups_per_sweep(const int* cnt, int G) {
+  int g = 0;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) g += (cnt[k] + G - 1) / G;
+  return g;
+}
+
 // All planes of one alignment class: groups of up to G planes share one mbarrier hand-shake; the inner loop is free of
-// pipeline logic.  f(row, ent) processes one plane.
+// pipeline logic.  f(row, ent) processes one plane.  mbarrier.try_wait costs ~90 cycles even on a completed phase
+// (B300_MICROARCH.md), so the test of the NEXT group's barrier is issued before this group's planes are processed and
+// only its result is consumed afterwards.
 template <int kUnroll, class F>
 __device__ __forceinline__ void class_run(Ring& rg, const Ent*& ent, int count, bool active, F f) {
   for (int g0 = 0; g0 < count; g0 += rg.G) {
     const int c = min(rg.G, count - g0);
-    mbar_wait(&rg.full[rg.slot], rg.par);
+    if (!rg.ready) mbar_wait(&rg.full[rg.slot], rg.par);
+    int ns = rg.slot + 1;
+    uint32_t np = rg.par;
+    if (ns == rg.S) { ns = 0; np ^= 1; }
+    const bool has_next = !(rg.last_row && rg.left == 1);
+    --rg.left;
+    rg.ready = has_next ? mbar_try_wait(&rg.full[ns], np) : false;
     if (active) {
       const float* rowp = rg.ring + (size_t)rg.slot * rg.G * rg.slotf;
 #pragma unroll kUnroll
@@ -192,9 +211,12 @@ __device__ __forceinline__ void class_run(Ring& rg, const Ent*& ent, int count, 
     ent += c;
     __syncwarp();
     if (rg.lane == 0) mbar_arrive(&rg.empty[rg.slot]);
-    if (++rg.slot == rg.S) { rg.slot = 0; rg.par ^= 1; }
+    rg.slot = ns;
+    rg.par = np;
   }
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Stage the three image rows of (b, y) into the image records; each thread handles its own quad.
 __device__ __forceinline__ void stage_image(float* img, const float* img_b, int y, int H, int W, int xb) {
@@ -292,7 +314,7 @@ __global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med3_fwd_ke
   const float* g0row = rows_s + kPad;
   float* nl0row = rows_s + rowf + kPad;
   float* nlwrow = rows_s + 2 * rowf + kPad;
-  Ring rg{ring + kPad, P.full, P.empty, tab, p.S, p.G, slot_floats(W), tid & 31, 0, 0u};
+  Ring rg{ring + kPad, P.full, P.empty, tab, p.S, p.G, slot_floats(W), tid & 31, 0, 0u, false, false, 0};
   int cur_b = -1;
   uint32_t tf = 0;
 
@@ -307,9 +329,16 @@ __global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med3_fwd_ke
       tf ^= 1;
       cur_b = b;
     }
+    rg.left = groups_per_sweep(cnt, p.G) * (kMasks ? 2 : 1);
+    rg.last_row = row == r1 - 1;
     named_bar_sync(1, ncons);   // previous row fully consumed: image copies / row arrays may be overwritten
     if (active) stage_image(img, p.image + (size_t)b * 3 * H * W, y, H, W, c.xb);
     named_bar_sync(1, ncons);
+    if (active && row + 1 < r1) {   // next row's image quads: in L2 by the time they are staged
+      const int bn = (row + 1) / H, yn = (row + 1) % H;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) prefetch_l2(p.image + (((size_t)bn * 3 + ch) * H + yn) * W + min(c.xb, W - 1));
+    }
 
     // ---------------------------------------------------------------- sweep A
     FwdAcc A;
@@ -410,7 +439,7 @@ __global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med3_bwd_ke
   float* nlwrow = rows_s + rowf + kPad;
   float* dotrow = rows_s + 2 * rowf + kPad;
   float* gprow = rows_s + 3 * rowf + kPad;
-  Ring rg{ring + kPad, P.full, P.empty, tab, p.S, p.G, slot_floats(W), tid & 31, 0, 0u};
+  Ring rg{ring + kPad, P.full, P.empty, tab, p.S, p.G, slot_floats(W), tid & 31, 0, 0u, false, false, 0};
   int cur_b = -1;
   uint32_t tf = 0;
 
@@ -429,6 +458,8 @@ __global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med3_bwd_ke
     // ---- per-row constants: own-pixel registers and the staged rows of the whole row
     BwdCtx t;
     const size_t r1o = ((size_t)b * H + y) * W;
+    rg.left = groups_per_sweep(cnt, p.G);
+    rg.last_row = row == r1 - 1;
     named_bar_sync(1, ncons);   // previous row fully consumed
     if (active) {
       float dot[4] = {0.f, 0.f, 0.f, 0.f};
@@ -466,6 +497,22 @@ __global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med3_bwd_ke
     }
     named_bar_sync(1, ncons);
 
+    if (active && row + 1 < r1) {   // next row's per-pixel inputs: in L2 by the time they are loaded
+      const int bn = (row + 1) / H, yn = (row + 1) % H;
+      const int xq = min(c.xb, W - 1);
+      const size_t rn = ((size_t)bn * H + yn) * W + xq;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const size_t rc = (((size_t)bn * 3 + ch) * H + yn) * W + xq;
+        if (p.g_pan) prefetch_l2(p.g_pan + rc);
+        prefetch_l2(p.pan_in + rc);
+        prefetch_l2(p.image + rc);
+      }
+      prefetch_l2(p.lsew_in + rn);
+      prefetch_l2(p.lse0_in + rn);
+      prefetch_l2(p.disp_in + rn);
+      if (p.g_disp) prefetch_l2(p.g_disp + rn);
+    }
     const long long obase = ((long long)b * N * H + y) * p.g_pitch;
     const long long oplane = (long long)H * p.g_pitch;
     float* const obase_p = p.g_logits + obase + c.xb;
@@ -511,7 +558,7 @@ int configure(M3Params& p, int n_rows, bool with_img, int want_small, int* threa
   if (want < 1) want = 1;
   if (*threads > 352) want = 1;
   else if (*threads > 192 && want > 2) want = 2;
-  else if (want > 4) want = 4;
+  else if (want > 3) want = 3;
   static const int shapes[][2] = {{4, 4}, {4, 3}, {2, 5}, {2, 4}, {4, 2}, {2, 3}, {1, 5}, {2, 2}, {1, 3}, {1, 2}};   // {G, S}
   const int envS = env_int("FALN_MED3_S", 0), envG = env_int("FALN_MED3_G", 0);
   for (int ct = want; ct >= 1; --ct) {
@@ -535,7 +582,7 @@ int configure(M3Params& p, int n_rows, bool with_img, int want_small, int* threa
 // Returns 1 when the launch was made, 0 when the shape is not eligible (caller falls back), <0 on error.
 int med3_launch_fwd(M3Params p, bool masks, cudaStream_t stream) {
   int threads = 0, ctas = 1;
-  const int smem = configure(p, masks ? 3 : 0, true, masks ? 3 : 4, &threads, &ctas);
+  const int smem = configure(p, masks ? 3 : 0, true, 2, &threads, &ctas);
   if (!smem) return 0;
   int grid = sm_count() * ctas;
   if (grid > p.B * p.H) grid = p.B * p.H;
@@ -545,10 +592,14 @@ int med3_launch_fwd(M3Params p, bool masks, cudaStream_t stream) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                   \
     kern<<<grid, threads, smem, stream>>>(p);                                                        \
   } while (0)
-  if (threads <= 192 && ctas >= 4) M3_LAUNCH_FWD(192, 80);
-  else if (threads <= 192) M3_LAUNCH_FWD(192, 104);
-  else if (threads <= 352 && ctas >= 2) M3_LAUNCH_FWD(352, 88);
-  else M3_LAUNCH_FWD(544, 112);
+  // Register caps follow the PER-SUB-PARTITION register file (16,384 registers, warp w of a CTA on sub-partition w % 4):
+  // k CTAs of nw warps put k * ceil(nw / 4) warps on sub-partition 0, so regs/thread <= 512 / (k * ceil(nw / 4)).
+  // 6 warps (640 px): 3 CTAs -> 80, 2 -> 128; 11 warps (1242 px): 2 CTAs -> 80, 1 -> 128; 17 warps (2048 px): 96.
+  if (threads <= 192 && ctas >= 3) M3_LAUNCH_FWD(192, 80);
+  else if (threads <= 192) M3_LAUNCH_FWD(192, 128);
+  else if (threads <= 352 && ctas >= 2) M3_LAUNCH_FWD(352, 80);
+  else if (threads <= 352) M3_LAUNCH_FWD(352, 128);
+  else M3_LAUNCH_FWD(544, 96);
 #undef M3_LAUNCH_FWD
   const int rc = after_launch(masks ? "med3_fwd_kernel<masks>" : "med3_fwd_kernel");
   return rc == FALN_OK ? 1 : rc;
@@ -556,7 +607,7 @@ int med3_launch_fwd(M3Params p, bool masks, cudaStream_t stream) {
 
 int med3_launch_bwd(M3Params p, cudaStream_t stream) {
   int threads = 0, ctas = 1;
-  const int smem = configure(p, 6, false, 3, &threads, &ctas);
+  const int smem = configure(p, 6, false, 2, &threads, &ctas);
   if (!smem) return 0;
   int grid = sm_count() * ctas;
   if (grid > p.B * p.H) grid = p.B * p.H;
@@ -566,10 +617,11 @@ int med3_launch_bwd(M3Params p, cudaStream_t stream) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                   \
     kern<<<grid, threads, smem, stream>>>(p);                                                        \
   } while (0)
-  if (threads <= 192 && ctas >= 4) M3_LAUNCH_BWD(192, 80);
-  else if (threads <= 192) M3_LAUNCH_BWD(192, 104);
-  else if (threads <= 352 && ctas >= 2) M3_LAUNCH_BWD(352, 88);
-  else M3_LAUNCH_BWD(544, 112);
+  if (threads <= 192 && ctas >= 3) M3_LAUNCH_BWD(192, 80);
+  else if (threads <= 192) M3_LAUNCH_BWD(192, 128);
+  else if (threads <= 352 && ctas >= 2) M3_LAUNCH_BWD(352, 80);
+  else if (threads <= 352) M3_LAUNCH_BWD(352, 128);
+  else M3_LAUNCH_BWD(544, 96);
 #undef M3_LAUNCH_BWD
   const int rc = after_launch("med3_bwd_kernel");
   return rc == FALN_OK ? 1 : rc;
