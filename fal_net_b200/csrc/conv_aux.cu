@@ -223,8 +223,11 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const uint4* __restric
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (long long px = (long long)blockIdx.x * lanes + pl; px < npix; px += (long long)gridDim.x * lanes) {
-    const uint4 u = __ldg(g + px * Cstride8 + cg);
+  // four independent 16-byte loads in flight per thread (the single-load loop left the HBM pipe at ~1/3: 31 us per launch
+  // in profiles/r1d_launches_stage1.txt)
+  const long long step = (long long)gridDim.x * lanes;
+  long long px = (long long)blockIdx.x * lanes + pl;
+  auto add8 = [&](const uint4& u) {
     const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -232,7 +235,18 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const uint4* __restric
       acc[2 * e] += f.x;
       acc[2 * e + 1] += f.y;
     }
+  };
+  for (; px + 3 * step < npix; px += 4 * step) {
+    const uint4 u0 = __ldg(g + px * Cstride8 + cg);
+    const uint4 u1 = __ldg(g + (px + step) * Cstride8 + cg);
+    const uint4 u2 = __ldg(g + (px + 2 * step) * Cstride8 + cg);
+    const uint4 u3 = __ldg(g + (px + 3 * step) * Cstride8 + cg);
+    add8(u0);
+    add8(u1);
+    add8(u2);
+    add8(u3);
   }
+  for (; px < npix; px += step) add8(__ldg(g + px * Cstride8 + cg));
 #pragma unroll
   for (int e = 0; e < 8; ++e) sm[threadIdx.x * 8 + e] = acc[e];
   __syncthreads();
@@ -321,7 +335,7 @@ extern "C" int faln_channel_sum_nhwc(const void* g, float* out, long long npix, 
   FALN_REQUIRE(C8 <= 64 && 256 % C8 == 0, "faln_channel_sum_nhwc: Cstride must be 8/16/32/64/128/256/512 (got %d)", Cstride);
   const int lanes = 256 / C8;
   long long grid = (npix + lanes - 1) / lanes;
-  const long long cap = (long long)sm_count() * 4;
+  const long long cap = (long long)sm_count() * 8;
   if (grid > cap) grid = cap;
   channel_sum_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(g), out, npix, C8, Cstride / 8, C);
   return after_launch("channel_sum_kernel");

@@ -546,14 +546,16 @@ int env_int(const char* name, int dflt) {
 }
 
 // Threads, ring shape and CTAs/SM for a row width.  Returns the dynamic shared-memory size, or 0 when nothing fits.
-// want_small: CTAs/SM to aim for on rows of <= 640 px (192 threads); 1242-px rows (352 threads) aim for 2, wider rows 1.
+// want_small: CTAs/SM to aim for on rows of <= 640 px (192 threads).  Wider rows run one CTA per SM at up to 128
+// registers: measured on B200 at 1242 px, two CTAs at the 80 registers the sub-partition register file then allows spill
+// into local memory and lose (fwd 0.400 vs 0.373 ms, masks 0.788 vs 0.678, bwd 0.702 vs 0.574; gpurun_out/s2_*).
 // Ring shapes are tried in order of plane rows in flight, (S - 1) * G: the stream must cover the HBM latency
 // (~35 KB per SM at 6.5 TB/s) while one group is being consumed.
 int configure(M3Params& p, int n_rows, bool with_img, int want_small, int* threads, int* ctas) {
   const int groups = (p.W + kPX - 1) / kPX;
   const int ncw = (groups + 31) / 32;
   *threads = (ncw + 1) * 32;
-  int want = *threads <= 192 ? want_small : (*threads <= 352 ? 2 : 1);
+  int want = *threads <= 192 ? want_small : 1;
   want = env_int("FALN_MED3_CTAS", want);
   if (want < 1) want = 1;
   if (*threads > 352) want = 1;
