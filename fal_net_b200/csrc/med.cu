@@ -298,7 +298,7 @@ __device__ __forceinline__ void fill_tab(const MedParams& p, PlaneTab t, int b, 
 // ---------------------------------------------------------------------------------------------
 // Clean-up mode (FALN_MED_CLEANUP_, internal): the third-generation forward (med3.cu) accumulates the softmax sums
 // without a running maximum and leaves the rows whose sums left the safe range to the forward kernel of this file,
-// marked by lse0[b, 0, y, 0] = NaN.  In clean-up mode a CTA first builds the list of its rows that need work and exits
+// marked by a NaN in lse0[b, 0, y, 128 w] (one mark per warp of 128 pixels).  In clean-up mode a CTA first builds the list of its rows that need work and exits
 // at once when there is none (the normal case: one global-load latency).
 // ---------------------------------------------------------------------------------------------
 constexpr unsigned FALN_MED_CLEANUP_ = 0x100u;
@@ -313,8 +313,12 @@ __device__ __forceinline__ bool build_todo(const MedParams& p, const float* lse0
   bool mine = false;
   for (int i = threadIdx.x; blockIdx.x + (long long)i * gridDim.x < rows; i += blockDim.x) {
     const int row = blockIdx.x + i * gridDim.x;
-    const float v = __ldcg(lse0 + (size_t)row * p.W);
-    const bool need = v != v;
+    // the third-generation forward marks a row per warp: NaN over lse0 of the warp's first pixel (every 128th)
+    bool need = false;
+    for (int x = 0; x < p.W; x += 128) {
+      const float v = __ldcg(lse0 + (size_t)row * p.W + x);
+      need = need || (v != v);
+    }
     if (need) {
       atomicOr(&todo[i >> 5], 1u << (i & 31));
       mine = true;

@@ -29,6 +29,7 @@ struct M3Params {
   long long pitch;   // logits row pitch, elements (multiple of 4)
   int B, N, H, W;
   int S, G;          // ring: S groups of G plane rows (filled in by the launcher)
+  int nbuf;          // per-row staging buffers (1 or 2; filled in by the launcher)
   int force_generic; // every plane on the per-pixel generic code (testing)
 };
 

@@ -26,13 +26,20 @@
 //     pixels it needs from the un-shifted logit window it owns and the staged normaliser rows, so the plane loops contain
 //     no CTA barrier and no shared-memory exchange (the second-generation kernels synchronised the CTA once per plane)
 //   * the softmax sums are accumulated WITHOUT a running maximum (plain exp2 of the logit): a row whose sums leave
-//     [2^-100, 2^120] is flagged and recomputed by the robust second-generation kernel (med.cu, cleanup launch)
+//     [2^-100, 2^120] is flagged (per warp of 128 pixels) and recomputed by the robust second-generation kernel
+//     (med.cu, clean-up launch)
 #pragma once
 
 #if defined(__CUDACC__)
 #include "common.cuh"
 #define M3_FN __device__ __forceinline__
 #define M3_HD __host__ __device__ inline
+// 1 / x to 1 ulp (MUFU.RCP); the sums it divides are in [2^-100, 2^120]
+__device__ __forceinline__ float m3_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 #else
 // ------------------------------------------------------------------------------------------ host shims
 #include <math.h>
@@ -55,6 +62,7 @@ namespace faln {
 static inline float ex2f(float x) { return exp2f(x); }
 static inline float lg2f(float x) { return log2f(x); }
 }  // namespace faln
+static inline float m3_rcp(float x) { return 1.0f / x; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 #endif
@@ -261,6 +269,7 @@ M3_FN bool fwd_finish(const FwdAcc& A, int xb, int W, float disp[4], float pan[3
   const float zwv[4] = {A.zw[0].x, A.zw[0].y, A.zw[1].x, A.zw[1].y};
   const float dv[4] = {A.dacc[0].x, A.dacc[0].y, A.dacc[1].x, A.dacc[1].y};
   bool bad = false;
+  float rzw[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const bool in = xb + i < W;
@@ -271,13 +280,14 @@ M3_FN bool fwd_finish(const FwdAcc& A, int xb, int W, float disp[4], float pan[3
     nlw[i] = in ? -lw : -INFINITY;
     lse0[i] = l0 * kLn2;
     lsew[i] = lw * kLn2;
-    disp[i] = dv[i] / z0v[i];
+    disp[i] = dv[i] * m3_rcp(z0v[i]);
+    rzw[i] = m3_rcp(zwv[i]);
   }
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
     const float pv[4] = {A.pacc[ch][0].x, A.pacc[ch][0].y, A.pacc[ch][1].x, A.pacc[ch][1].y};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pan[ch][i] = pv[i] / zwv[i];
+    for (int i = 0; i < 4; ++i) pan[ch][i] = pv[i] * rzw[i];
   }
   return bad;
 }

@@ -115,7 +115,7 @@ extern "C" int emu_med3_fwd(const float* logits, const float* image, const float
           stage_quad(img.data(), ch, xb, load_row4(image + (((size_t)b * 3 + ch) * H + y) * W, xb, W));
       }
       const size_t r1o = ((size_t)b * H + y) * W;
-      bool any_bad = false;
+      std::vector<char> warp_bad(ncons / 32, 0);   // the kernel votes per warp (128 pixels) and marks lse0 of its first pixel
       for (int tid = 0; tid < ncons; ++tid) {
         PxCtx c = make_ctx(tid, W, g0x);
         if (c.xb >= W) continue;
@@ -132,7 +132,7 @@ extern "C" int emu_med3_fwd(const float* logits, const float* image, const float
           }
         }
         float dv[4], pv[3][4], l0[4], lw[4], nl0[4], nlw[4];
-        any_bad = fwd_finish(A, c.xb, W, dv, pv, l0, lw, nl0, nlw) || any_bad;
+        if (fwd_finish(A, c.xb, W, dv, pv, l0, lw, nl0, nlw)) warp_bad[tid / 32] = 1;
         store_row4(disp + r1o, c.xb, dv, W);
         for (int ch = 0; ch < 3; ++ch) store_row4(pan + (((size_t)b * 3 + ch) * H + y) * W, c.xb, pv[ch], W);
         store_row4(lse0 + r1o, c.xb, l0, W);
@@ -140,10 +140,13 @@ extern "C" int emu_med3_fwd(const float* logits, const float* image, const float
         st4(nl0row + c.xb, make_float4(nl0[0], nl0[1], nl0[2], nl0[3]));
         st4(nlwrow + c.xb, make_float4(nlw[0], nlw[1], nlw[2], nlw[3]));
       }
-      if (any_bad) {
-        lse0[r1o] = NAN;
-        ++flagged;
-      }
+      bool any_bad = false;
+      for (int w = 0; w < ncons / 32; ++w)
+        if (warp_bad[w]) {
+          lse0[r1o + 128 * w] = NAN;
+          any_bad = true;
+        }
+      if (any_bad) ++flagged;
       if (!masks) continue;
       for (int tid = 0; tid < ncons; ++tid) {
         PxCtx c = make_ctx(tid, W, g0x);

@@ -127,3 +127,13 @@ def test_overflow_rows_are_flagged(emu):
     big[0, 2, 1, 10] = 200.0            # exp(200) overflows fp32 without a running maximum
     out, flagged = _run(emu, big, img, d, xo, gp, gd)
     assert flagged == 1 and torch.isnan(out["lse0"][0, 0, 1, 0]) and not torch.isnan(out["lse0"][0, 0, 0, 0])
+    # wider row: the mark sits on the first pixel of the warp (128 pixels) that saw the overflow
+    B, N, H, W = 1, 5, 1, 300
+    logits = 2 * torch.randn(B, N, H, W, generator=g)
+    logits[0, 1, 0, 200] = 250.0
+    img = images(B, H, W, 6)
+    gp, gd = torch.randn(B, 3, H, W, generator=g), torch.randn(B, 1, H, W, generator=g)
+    d, xo = O.level_tables(*disp_range(B, 20.0, 1.0), N, W)
+    out, flagged = _run(emu, logits, img, d, xo, gp, gd)
+    marks = torch.isnan(out["lse0"][0, 0, 0]).nonzero().flatten().tolist()
+    assert flagged == 1 and 128 in marks and all(m % 128 == 0 for m in marks)
