@@ -135,54 +135,6 @@ __device__ __forceinline__ void build_table(const M3Params& p, int b, int lane, 
   __syncwarp();
 }
 
-// Producer warp, forward: the image records of row (b, y), one quad per lane and step.
-__device__ __forceinline__ void stage_image_row(const M3Params& p, float* img, int b, int y, int lane) {
-  const int W = p.W, H = p.H, nq = ceil4(W) / 4;
-  const float* img_b = p.image + (size_t)b * 3 * H * W;
-  for (int q = lane; q < nq; q += 32) {
-    float4 v[3];
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) v[ch] = load_row4(img_b + ((size_t)ch * H + y) * W, 4 * q, W);
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) stage_quad(img, ch, 4 * q, v[ch]);
-  }
-}
-
-// Backward row arrays of one buffer (offsets in units of row_floats):
-constexpr int kBwNlw = 0, kBwDot = 1, kBwGp = 2, kBwNl0 = 5, kBwGd = 6, kBwNdsp = 7, kBwImg = 8, kBwRows = 11;
-// Producer warp, backward: everything the consumers need per pixel of row (b, y).
-__device__ __forceinline__ void stage_bwd_row(const M3Params& p, float* rows, int rowf, int b, int y, int lane) {
-  const int W = p.W, H = p.H, nq = ceil4(W) / 4;
-  const size_t r1o = ((size_t)b * H + y) * W;
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int q = lane; q < nq; q += 32) {
-    const int xb = 4 * q;
-    float dot[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      const size_t rc = (((size_t)b * 3 + ch) * H + y) * W;
-      const float4 gq = p.g_pan ? load_row4(p.g_pan + rc, xb, W) : z4;
-      const float4 pq = load_row4(p.pan_in + rc, xb, W);
-      dot[0] = fmaf(gq.x, pq.x, dot[0]);
-      dot[1] = fmaf(gq.y, pq.y, dot[1]);
-      dot[2] = fmaf(gq.z, pq.z, dot[2]);
-      dot[3] = fmaf(gq.w, pq.w, dot[3]);
-      st4(rows + (kBwGp + ch) * rowf + xb, gq);
-      st4(rows + (kBwImg + ch) * rowf + xb, load_row4(p.image + rc, xb, W));
-    }
-    st4(rows + kBwDot * rowf + xb, make_float4(dot[0], dot[1], dot[2], dot[3]));
-    const float4 lw = load_row4(p.lsew_in + r1o, xb, W);
-    const float4 l0 = load_row4(p.lse0_in + r1o, xb, W);
-    const float4 gd = p.g_disp ? load_row4(p.g_disp + r1o, xb, W) : z4;
-    const float4 dp = load_row4(p.disp_in + r1o, xb, W);
-    st4(rows + kBwNlw * rowf + xb, make_float4(xb < W ? -lw.x * kLog2e : -INFINITY, xb + 1 < W ? -lw.y * kLog2e : -INFINITY,
-                                              xb + 2 < W ? -lw.z * kLog2e : -INFINITY, xb + 3 < W ? -lw.w * kLog2e : -INFINITY));
-    st4(rows + kBwNl0 * rowf + xb, make_float4(-l0.x * kLog2e, -l0.y * kLog2e, -l0.z * kLog2e, -l0.w * kLog2e));
-    st4(rows + kBwGd * rowf + xb, gd);
-    st4(rows + kBwNdsp * rowf + xb, make_float4(-dp.x, -dp.y, -dp.z, -dp.w));
-  }
-}
-
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Copy warp: rows [r0, r1) of the flattened (b, y) index, `sweeps` passes over the planes of every row.  Builds the plane
@@ -229,44 +181,46 @@ __device__ __forceinline__ void copy_warp(const M3Params& p, const Pipe& P, floa
   }
 }
 
-// Staging warp: the per-row inputs of rows [r0, r1) into the nbuf staging buffers (image records for the forward, the row
-// arrays for the backward), one buffer per row, handed over through aux_full / aux_empty.  With two buffers row r+1 is
-// staged while row r is consumed; with one (2048-px rows) staging still overlaps the consumers' epilogue / mask sweep.
-template <bool kBwd>
-__device__ __forceinline__ void stage_warp(const M3Params& p, const Pipe& P, float* aux, int aux_stride, int r0, int r1,
-                                           int lane) {
-  const int nbuf = p.nbuf, rowf = row_floats(p.W), W = p.W, H = p.H;
+// Staging warp (forward): the image records of rows [r0, r1) into the nbuf record buffers, one buffer per row, handed
+// over through aux_full / aux_empty.  With two buffers row r+1 is staged while row r is consumed; with one, staging
+// overlaps the consumers' epilogue / mask sweep.  Four quads per lane are loaded before the first is stored, so a row
+// costs a few load latencies, not one per quad.
+__device__ __forceinline__ void stage_warp(const M3Params& p, const Pipe& P, float* img0, int imgf, int r0, int r1, int lane) {
+  const int nbuf = p.nbuf, W = p.W, H = p.H;
   const int nq = ceil4(W) / 4;
   uint32_t ae = 0;   // bit buf = parity of the next aux_empty phase of that buffer
   for (int row = r0, it = 0; row < r1; ++row, ++it) {
     const int b = row / H, y = row % H;
     const int buf = it % nbuf;
-    // pull the row's inputs into L2 while the buffer is still in use
+    const float* img_b = p.image + ((size_t)b * 3 * H + y) * W;
+    // pull the row into L2 while the buffer is still in use
     for (int q = lane; q < nq; q += 32) {
-      const int xq = min(4 * q, W - 1);
-      const size_t r1o = ((size_t)b * H + y) * W + xq;
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        const size_t rc = (((size_t)b * 3 + ch) * H + y) * W + xq;
-        prefetch_l2(p.image + rc);
-        if (kBwd) {
-          if (p.g_pan) prefetch_l2(p.g_pan + rc);
-          prefetch_l2(p.pan_in + rc);
-        }
-      }
-      if (kBwd) {
-        prefetch_l2(p.lsew_in + r1o);
-        prefetch_l2(p.lse0_in + r1o);
-        prefetch_l2(p.disp_in + r1o);
-        if (p.g_disp) prefetch_l2(p.g_disp + r1o);
-      }
+      for (int ch = 0; ch < 3; ++ch) prefetch_l2(img_b + (size_t)ch * H * W + min(4 * q, W - 1));
     }
     if (it >= nbuf) {   // the buffer holds row it - nbuf until every consumer warp released it
       mbar_wait_sleep(&P.aux_empty[buf], (ae >> buf) & 1u);
       ae ^= 1u << buf;
     }
-    if (kBwd) stage_bwd_row(p, aux + (size_t)buf * aux_stride + kPad, rowf, b, y, lane);
-    else stage_image_row(p, aux + (size_t)buf * aux_stride, b, y, lane);
+    float* img = img0 + (size_t)buf * imgf;
+    for (int q0 = lane; q0 < nq; q0 += 128) {
+      float4 v[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = q0 + 32 * u;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+          v[u][ch] = q < nq ? load_row4(img_b + (size_t)ch * H * W, 4 * q, W) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = q0 + 32 * u;
+        if (q < nq) {
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) stage_quad(img, ch, 4 * q, v[u][ch]);
+        }
+      }
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&P.aux_full[buf]);
   }
@@ -403,7 +357,7 @@ __global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med3_fwd_ke
 
   if (tid >= ncons) {
     if (tid < ncons + 32) copy_warp(p, P, ring, tab, cls, cnt, r0, r1, kMasks ? 2 : 1, tid & 31);
-    else stage_warp<false>(p, P, img0, imgf, r0, r1, tid & 31);
+    else stage_warp(p, P, img0, imgf, r0, r1, tid & 31);
     return;
   }
 
@@ -504,14 +458,16 @@ __global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med3_fwd_ke
 }
 
 // =============================================================================================
-// Backward.  No CTA-wide barrier on the consumer side: the per-pixel inputs of a row (g_pan, <g_pan, pan>, the
-// normalisers, g_disp, disp, the image) are staged by the producer warp into one of two row-array buffers.
+// Backward.  The per-pixel inputs of a row (g_pan, <g_pan, pan>, the normalisers, g_disp, disp, the image window) are
+// loaded by the consumer threads themselves, one quad each -- 19 independent loads, one memory latency per row -- and
+// published through four row arrays between two CTA barriers.  (Measured on B200: staging these thirteen input rows with
+// one extra warp instead loses 25 % at 1242 px and 2x at 2048 px -- a single warp serialises ~10 load latencies per row.)
 // =============================================================================================
 template <int kMaxThreads, int kMaxRegs>
 __global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med3_bwd_kernel(const M3Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int n_rows = 1 + kBwRows * p.nbuf;   // g0row + nbuf x the backward row arrays
-  const Smem L = make_smem(p.W, p.S, p.G, n_rows, 0);
+  constexpr int kRows = 6;   // g0row, nlwrow, dotrow, gprow[3]
+  const Smem L = make_smem(p.W, p.S, p.G, kRows, 0);
   int* cnt = reinterpret_cast<int*>(smem + L.off_cnt);
   unsigned char* cls = smem + L.off_cls;
   Ent* tab = reinterpret_cast<Ent*>(smem + L.off_tab);
@@ -519,19 +475,16 @@ __global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med3_bwd_ke
   float* ring = reinterpret_cast<float*>(smem + L.off_ring);
   const Pipe P = make_pipe(smem, L, p.S);
 
-  const int ncons = blockDim.x - 64;   // consumer threads; then the copy warp and the staging warp
+  const int ncons = blockDim.x - 32;   // consumer threads; then the copy warp
   const int tid = threadIdx.x;
   const int W = p.W, H = p.H, N = p.N;
   const int rowf = row_floats(W);
-  // -inf arrays: the nlw row of each buffer (array 1 + buf * kBwRows)
-  prologue(p, smem, L, (1u << (1 + kBwNlw)) | (p.nbuf > 1 ? 1u << (1 + kBwRows + kBwNlw) : 0u), n_rows, 0, ncons);
+  prologue(p, smem, L, 1u << 1, kRows, 0, ncons);
   int r0, r1;
   row_range(p.B * H, r0, r1);
-  float* const rows0 = rows_s + rowf;   // first buffer (after the affine-grid row)
 
   if (tid >= ncons) {
-    if (tid < ncons + 32) copy_warp(p, P, ring, tab, cls, cnt, r0, r1, 1, tid & 31);
-    else stage_warp<true>(p, P, rows0, kBwRows * rowf, r0, r1, tid & 31);
+    copy_warp(p, P, ring, tab, cls, cnt, r0, r1, 1, tid & 31);
     return;
   }
 
@@ -542,35 +495,76 @@ __global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med3_bwd_ke
   const bool active = c.xb < W;
   const float nxm1 = -(float)(c.xb - 1);
   const float* g0row = rows_s + kPad;
+  float* nlwrow = rows_s + rowf + kPad;
+  float* dotrow = rows_s + 2 * rowf + kPad;
+  float* gprow = rows_s + 3 * rowf + kPad;
   const int lane = tid & 31;
   Ring rg{ring + kPad, P.full, P.empty, p.S, p.G, slot_floats(W), lane, 0, 0u, false, false, 0};
   int cur_b = -1;
-  uint32_t tf = 0, af = 0;
+  uint32_t tf = 0;
 
-  for (int row = r0, it = 0; row < r1; ++row, ++it) {
+  for (int row = r0; row < r1; ++row) {
     const int b = row / H, y = row % H;
     next_sample(P, b, cur_b, tf, lane);
+
+    // ---- per-row constants: own-pixel registers and the staged rows of the whole row
+    BwdCtx t;
+    const size_t r1o = ((size_t)b * H + y) * W;
     rg.left = groups_per_sweep(cnt, p.G);
     rg.last_row = row == r1 - 1;
-    const int buf = it % p.nbuf;
-    const float* rb = rows0 + (size_t)buf * kBwRows * rowf + kPad;
-    const float* nlwrow = rb + kBwNlw * rowf;
-    const float* dotrow = rb + kBwDot * rowf;
-    const float* gprow = rb + kBwGp * rowf;
-    mbar_wait(&P.aux_full[buf], (af >> buf) & 1u);
-    af ^= 1u << buf;
-
-    // ---- own-pixel constants out of the staged rows
-    BwdCtx t;
+    named_bar_sync(1, ncons);   // previous row fully consumed
     if (active) {
-      const float4 n0 = ld4(rb + kBwNl0 * rowf + c.xb), gd = ld4(rb + kBwGd * rowf + c.xb), nd = ld4(rb + kBwNdsp * rowf + c.xb);
-      t.nl0[0] = n0.x; t.nl0[1] = n0.y; t.nl0[2] = n0.z; t.nl0[3] = n0.w;
-      t.gd[0] = gd.x; t.gd[1] = gd.y; t.gd[2] = gd.z; t.gd[3] = gd.w;
-      t.ndsp[0] = nd.x; t.ndsp[1] = nd.y; t.ndsp[2] = nd.z; t.ndsp[3] = nd.w;
+      float dot[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) win6(rb + (kBwImg + ch) * rowf, c.xb, t.iw[ch]);
+      for (int ch = 0; ch < 3; ++ch) {
+        const size_t rc = (((size_t)b * 3 + ch) * H + y) * W;
+        const float4 gq = p.g_pan ? load_row4(p.g_pan + rc, c.xb, W) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 pq = load_row4(p.pan_in + rc, c.xb, W);
+        dot[0] = fmaf(gq.x, pq.x, dot[0]);
+        dot[1] = fmaf(gq.y, pq.y, dot[1]);
+        dot[2] = fmaf(gq.z, pq.z, dot[2]);
+        dot[3] = fmaf(gq.w, pq.w, dot[3]);
+        st4(gprow + ch * rowf + c.xb, gq);
+        const float4 iq = load_row4(p.image + rc, c.xb, W);
+        t.iw[ch][0] = c.xb > 0 ? __ldg(p.image + rc + c.xb - 1) : 0.f;
+        t.iw[ch][1] = iq.x; t.iw[ch][2] = iq.y; t.iw[ch][3] = iq.z; t.iw[ch][4] = iq.w;
+        t.iw[ch][5] = c.xb + 4 < W ? __ldg(p.image + rc + c.xb + 4) : 0.f;
+      }
+      st4(dotrow + c.xb, make_float4(dot[0], dot[1], dot[2], dot[3]));
+      const float4 lw = load_row4(p.lsew_in + r1o, c.xb, W);
+      const float4 l0 = load_row4(p.lse0_in + r1o, c.xb, W);
+      const float4 gd = p.g_disp ? load_row4(p.g_disp + r1o, c.xb, W) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 dp = load_row4(p.disp_in + r1o, c.xb, W);
+      const float lwv[4] = {lw.x, lw.y, lw.z, lw.w}, l0v[4] = {l0.x, l0.y, l0.z, l0.w};
+      const float gdv[4] = {gd.x, gd.y, gd.z, gd.w}, dpv[4] = {dp.x, dp.y, dp.z, dp.w};
+      float nl[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        nl[i] = c.xb + i < W ? -lwv[i] * kLog2e : -INFINITY;
+        t.nl0[i] = -l0v[i] * kLog2e;
+        t.gd[i] = gdv[i];
+        t.ndsp[i] = -dpv[i];
+      }
+      st4(nlwrow + c.xb, make_float4(nl[0], nl[1], nl[2], nl[3]));
     }
+    named_bar_sync(1, ncons);
 
+    if (active && row + 1 < r1) {   // next row's per-pixel inputs: in L2 by the time they are loaded
+      const int bn = (row + 1) / H, yn = (row + 1) % H;
+      const int xq = min(c.xb, W - 1);
+      const size_t rn = ((size_t)bn * H + yn) * W + xq;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const size_t rc = (((size_t)bn * 3 + ch) * H + yn) * W + xq;
+        if (p.g_pan) prefetch_l2(p.g_pan + rc);
+        prefetch_l2(p.pan_in + rc);
+        prefetch_l2(p.image + rc);
+      }
+      prefetch_l2(p.lsew_in + rn);
+      prefetch_l2(p.lse0_in + rn);
+      prefetch_l2(p.disp_in + rn);
+      if (p.g_disp) prefetch_l2(p.g_disp + rn);
+    }
     const long long obase = ((long long)b * N * H + y) * p.g_pitch;
     const long long oplane = (long long)H * p.g_pitch;
     float* const obase_p = p.g_logits + obase;
@@ -594,8 +588,6 @@ __global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med3_bwd_ke
         store_row4(obase_p + e.src * oplane, c.xb, g, W);
       });
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&P.aux_empty[buf]);   // this warp is done with the row arrays
   }
 }
 
@@ -609,14 +601,13 @@ int env_int(const char* name, int dflt) {
 // nothing fits.  want_small: CTAs/SM to aim for on rows of <= 640 px (192 threads).  Wider rows run one CTA per SM at up to
 // 128 registers: measured on B200 at 1242 px, two CTAs at the 80 registers the sub-partition register file then allows
 // spill into local memory and lose (fwd 0.400 vs 0.373 ms, masks 0.788 vs 0.678, bwd 0.702 vs 0.574; gpurun_out/s2_*).
-// Shared memory per CTA = fixed + nbuf staging buffers (img_per_buf image-record buffers / rows_per_buf row arrays each)
-// + rows_fixed row arrays + the ring.  Two staging buffers are preferred (the producer warp stages row r+1 while row r is
+// Shared memory per CTA = fixed + nbuf image-record buffers (forward) + rows_fixed row arrays + the ring.  Two staging buffers are preferred (the producer warp stages row r+1 while row r is
 // consumed); ring shapes are tried in order of plane rows in flight, (S - 1) * G: the stream must cover the HBM latency
 // (~35 KB per SM at 6.5 TB/s) while one group is being consumed.
-int configure(M3Params& p, int rows_fixed, int rows_per_buf, int img_per_buf, int want_small, int* threads, int* ctas) {
+int configure(M3Params& p, int rows_fixed, int img_per_buf, int max_buf, int n_prod, int want_small, int* threads, int* ctas) {
   const int groups = (p.W + kPX - 1) / kPX;
   const int ncw = (groups + 31) / 32;
-  *threads = (ncw + 2) * 32;   // consumers + copy warp + staging warp
+  *threads = (ncw + n_prod) * 32;   // consumers + copy warp (+ staging warp)
   int want = *threads <= 224 ? want_small : 1;
   want = env_int("FALN_MED3_CTAS", want);
   if (want < 1) want = 1;
@@ -627,11 +618,11 @@ int configure(M3Params& p, int rows_fixed, int rows_per_buf, int img_per_buf, in
   const int envS = env_int("FALN_MED3_S", 0), envG = env_int("FALN_MED3_G", 0), envB = env_int("FALN_MED3_NBUF", 0);
   for (int ct = want; ct >= 1; --ct) {
     const int budget = (228 * 1024) / ct - 1024 - 64;
-    for (int nbuf = (envB == 1 ? 1 : 2); nbuf >= (envB == 2 ? 2 : 1); --nbuf) {
+    for (int nbuf = (envB == 1 ? 1 : max_buf); nbuf >= (envB == 2 ? max_buf : 1); --nbuf) {
       int best = -1, best_need = 0;
       for (int k = 0; k < (int)(sizeof(shapes) / sizeof(shapes[0])); ++k) {
         const int G = envG > 0 ? envG : shapes[k][0], S = envS > 1 ? (envS > 13 ? 13 : envS) : shapes[k][1];
-        const int need = make_smem(p.W, S, G, rows_fixed + nbuf * rows_per_buf, nbuf * img_per_buf).total;
+        const int need = make_smem(p.W, S, G, rows_fixed, nbuf * img_per_buf).total;
         if (need <= budget && need <= 227 * 1024) {
           best = k;
           best_need = need;
@@ -640,8 +631,8 @@ int configure(M3Params& p, int rows_fixed, int rows_per_buf, int img_per_buf, in
           break;
         }
       }
-      // two staging buffers only if they still leave a ring of at least 6 plane rows in flight
-      if (best >= 0 && (nbuf == 1 || (p.S - 1) * p.G >= 6 || envB == 2)) {
+      // two staging buffers only if they still leave a ring of at least 8 plane rows in flight, in groups of four
+      if (best >= 0 && (nbuf == 1 || ((p.S - 1) * p.G >= 8 && p.G >= 4) || envB == 2)) {
         p.nbuf = nbuf;
         *ctas = ct;
         return best_need;
@@ -656,7 +647,8 @@ int configure(M3Params& p, int rows_fixed, int rows_per_buf, int img_per_buf, in
 // Returns 1 when the launch was made, 0 when the shape is not eligible (caller falls back), <0 on error.
 int med3_launch_fwd(M3Params p, bool masks, cudaStream_t stream) {
   int threads = 0, ctas = 1;
-  const int smem = configure(p, masks ? 5 : 0, 0, 1, 2, &threads, &ctas);
+  // masks: one record buffer (the mask sweep leaves the staging warp a whole sweep to refill it; measured better)
+  const int smem = configure(p, masks ? 5 : 0, 1, masks ? 1 : 2, 2, 2, &threads, &ctas);
   if (!smem) return 0;
   int grid = sm_count() * ctas;
   if (grid > p.B * p.H) grid = p.B * p.H;
@@ -681,7 +673,7 @@ int med3_launch_fwd(M3Params p, bool masks, cudaStream_t stream) {
 
 int med3_launch_bwd(M3Params p, cudaStream_t stream) {
   int threads = 0, ctas = 1;
-  const int smem = configure(p, 1, kBwRows, 0, 2, &threads, &ctas);
+  const int smem = configure(p, 6, 0, 1, 1, 2, &threads, &ctas);
   if (!smem) return 0;
   int grid = sm_count() * ctas;
   if (grid > p.B * p.H) grid = p.B * p.H;
@@ -691,11 +683,11 @@ int med3_launch_bwd(M3Params p, cudaStream_t stream) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                   \
     kern<<<grid, threads, smem, stream>>>(p);                                                        \
   } while (0)
-  if (threads <= 224 && ctas >= 3) M3_LAUNCH_BWD(224, 80);
-  else if (threads <= 224) M3_LAUNCH_BWD(224, 128);
-  else if (threads <= 384 && ctas >= 2) M3_LAUNCH_BWD(384, 80);
-  else if (threads <= 384) M3_LAUNCH_BWD(384, 128);
-  else M3_LAUNCH_BWD(576, 96);
+  if (threads <= 192 && ctas >= 3) M3_LAUNCH_BWD(192, 80);
+  else if (threads <= 192) M3_LAUNCH_BWD(192, 128);
+  else if (threads <= 352 && ctas >= 2) M3_LAUNCH_BWD(352, 80);
+  else if (threads <= 352) M3_LAUNCH_BWD(352, 128);
+  else M3_LAUNCH_BWD(544, 96);
 #undef M3_LAUNCH_BWD
   const int rc = after_launch("med3_bwd_kernel");
   return rc == FALN_OK ? 1 : rc;

@@ -8,7 +8,7 @@ TAG=${1:-s}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
 echo "== med tests"; timeout 400 python -m pytest tests/test_med_gpu.py -q > gpurun_out/${TAG}_medtests.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/${TAG}_medtests.log
 echo "== bench_med v3";  timeout 200 python tools/bench_med.py --quick > gpurun_out/${TAG}_med_v3.jsonl 2> gpurun_out/${TAG}_med_v3.err; echo "rc=$?"; cat gpurun_out/${TAG}_med_v3.jsonl
-for cfg in "CTAS=1" "CTAS=3" "G=2 S=5"; do
+for cfg in "CTAS=1" "NBUF=1"; do
   envs=""; for kv in $cfg; do envs="$envs FALN_MED3_$kv"; done
   f="gpurun_out/${TAG}_med_sweep_$(echo $cfg | tr ' =' '__').jsonl"
   echo "== sweep $cfg"; env $envs timeout 120 python tools/bench_med.py --quick > "$f" 2>&1; cat "$f" | cut -c1-420
