@@ -21,6 +21,8 @@ lets the whole step live in one CUDA graph.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import conv_native as CN
@@ -151,13 +153,17 @@ def disparity(model, image, min_disp, max_disp):
 # ------------------------------------------------------------------------------------------------------------------
 _SIDE_STREAMS: dict = {}
 USE_SIDE_STREAM = True      # bench.py switches this off for its per-kernel timing pass (kernels then run one at a time)
+# Parameter-gradient tasks (weight gradients, bias sums) of different layers are independent: they are dealt round-robin
+# onto this many side streams, so the latency-bound kernels of the small layers overlap each other as well as the
+# data-gradient chain.  FALN_SIDE_STREAMS overrides (1 = the single side stream of the earlier design).
+N_SIDE_STREAMS = max(1, int(os.environ.get("FALN_SIDE_STREAMS", "2")))
 
 
-def _side_stream(dev):
+def _side_streams(dev):
     key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
     st = _SIDE_STREAMS.get(key)
-    if st is None:
-        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    if st is None or len(st) != N_SIDE_STREAMS:
+        st = _SIDE_STREAMS[key] = [torch.cuda.Stream(device=key) for _ in range(N_SIDE_STREAMS)]
     return st
 
 
@@ -194,24 +200,39 @@ def backward(model, tape, g_logits, sink=None):
     # side stream, ordered after their producer by an event, and are joined before returning.  Inside a CUDA-graph capture
     # this becomes a parallel branch of the graph, so the latency-bound small layers of both chains overlap.
     main = torch.cuda.current_stream(dev)
-    side = _side_stream(dev)
-    keep = []                                                  # tensors the side stream reads stay alive until the join
+    sides = _side_streams(dev)
+    keep = []                                                  # tensors the side streams read stay alive until the join
+    turn = [0]
 
     def on_side(fn, *tensors):
         if not USE_SIDE_STREAM:
             fn()
             return
         keep.extend(tensors)
+        side = sides[turn[0] % len(sides)]
+        turn[0] += 1
         ev = torch.cuda.Event()
         ev.record(main)
         side.wait_event(ev)
         with torch.cuda.stream(side):
             fn()
 
+    def ready(name):
+        """Release ``name`` to the gradient sink.  When this completes an all-reduce bucket, the collective is issued from
+        the current side stream, so that stream first waits for the gradients its siblings are still producing."""
+        if USE_SIDE_STREAM and len(sides) > 1 and getattr(sink, "completes_bucket", lambda n: False)(name):
+            cur = torch.cuda.current_stream(dev)
+            for other in sides:
+                if other is not cur:
+                    ev = torch.cuda.Event()
+                    ev.record(other)
+                    cur.wait_event(ev)
+        sink.mark_ready(name)
+
     def bias_grad(name, g, C):
         def run():
             CN.channel_sum(g, sink.grad_view(name), C)
-            sink.mark_ready(name)
+            ready(name)
         on_side(run, g)
 
     def wgrad(name, g_pre, sources, cout, stride=1, const=None):
@@ -226,7 +247,7 @@ def backward(model, tape, g_logits, sink=None):
                 off += cx
             if const is not None:
                 dW[:, off].add_(CN.const_channel_wgrad(g_pre, const[0], const[1], stride, cout))
-            sink.mark_ready(name)
+            ready(name)
         on_side(run, g_pre, *sources)
 
     # ---------------------------------------------------------------- folded logits conv (iconv1 o conv0)
@@ -244,9 +265,9 @@ def backward(model, tape, g_logits, sink=None):
         w0 = model.conv0.weight.detach()[:, :, 0, 0]
         wi1 = bb.iconv1.weight.detach()
         sink.grad_view("conv0.weight").add_(torch.einsum("ockl,mckl->om", gwf, wi1)[:, :, None, None])
-        sink.mark_ready("conv0.weight")
+        ready("conv0.weight")
         sink.grad_view("backbone.iconv1.weight").add_(torch.einsum("om,ockl->mckl", w0, gwf))
-        sink.mark_ready("backbone.iconv1.weight")
+        ready("backbone.iconv1.weight")
     on_side(folded, g, u, s0)
     wd = CN.pack_weight_dgrad(wf)                                                # [96,3,3,Np]
     C1 = u.shape[1]
@@ -304,7 +325,8 @@ def backward(model, tape, g_logits, sink=None):
         g_s = CN.conv3x3_dgrad(g_a, _wd(head.weight, Cp), (prev.shape[2], prev.shape[3]), stride=stride,
                                out=G_skip.pop(i - 1), accum=True, dact=1, ysave=prev)
         del g_r, g_a
-    main.wait_stream(side)                                                        # join: gradients complete, `keep` may go
+    for side in sides:                                                            # join: gradients complete, `keep` may go
+        main.wait_stream(side)
     del keep
     return sink
 

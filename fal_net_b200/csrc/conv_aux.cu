@@ -1,6 +1,8 @@
 // conv_aux.cu -- the small CUDA-core kernels around the tcgen05 convolution: the 3-channel stem convolution
 // (K = 27 is too thin for a tensor-core tile and its input is the fp32 NCHW image itself), nearest upsampling,
 // 2x2 max-pooling, all on bf16 NHWC activations.  All are HBM-bound streaming kernels.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace faln {
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const uint4* __restri
 // Per-channel sums of a bf16 NHWC gradient (bias gradients): out[c] += sum over pixels of g[pix, c], fp32.
 // Block = 256 threads = (256 / C8) pixel lanes x C8 channel groups of 8; shared-memory tree over the pixel lanes, then one
 // atomicAdd per channel per block.
+template <bool kUnroll>
 __global__ void __launch_bounds__(256) channel_sum_kernel(const uint4* __restrict__ g, float* __restrict__ out, long long npix,
                                                           int C8, int Cstride8, int Cout) {
   __shared__ float sm[256 * 8];
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const uint4* __restric
       acc[2 * e + 1] += f.y;
     }
   };
-  for (; px + 3 * step < npix; px += 4 * step) {
+  for (; kUnroll && px + 3 * step < npix; px += 4 * step) {
     const uint4 u0 = __ldg(g + px * Cstride8 + cg);
     const uint4 u1 = __ldg(g + (px + step) * Cstride8 + cg);
     const uint4 u2 = __ldg(g + (px + 2 * step) * Cstride8 + cg);
@@ -335,8 +338,17 @@ extern "C" int faln_channel_sum_nhwc(const void* g, float* out, long long npix, 
   FALN_REQUIRE(C8 <= 64 && 256 % C8 == 0, "faln_channel_sum_nhwc: Cstride must be 8/16/32/64/128/256/512 (got %d)", Cstride);
   const int lanes = 256 / C8;
   long long grid = (npix + lanes - 1) / lanes;
-  const long long cap = (long long)sm_count() * 8;
+  // Tuning aids (the kernel runs on the gradient side stream, concurrently with the data-gradient chain, so its
+  // footprint matters as much as its own speed): FALN_CHSUM_CAP = blocks per SM, FALN_CHSUM_UNROLL = 0/1.
+  // Measured on B200 (Stage-1 step, gpurun_out/s5_*): 8 blocks/SM 5.36 ms, 4 blocks/SM 5.16 ms, 2 blocks/SM with four
+  // loads in flight 5.05 ms -- a small footprint leaves the SMs to the data-gradient chain.
+  static const int cap_per_sm = getenv("FALN_CHSUM_CAP") ? atoi(getenv("FALN_CHSUM_CAP")) : 2;
+  static const int unroll = getenv("FALN_CHSUM_UNROLL") ? atoi(getenv("FALN_CHSUM_UNROLL")) : 1;
+  const long long cap = (long long)sm_count() * (cap_per_sm > 0 ? cap_per_sm : 2);
   if (grid > cap) grid = cap;
-  channel_sum_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(g), out, npix, C8, Cstride / 8, C);
+  if (unroll)
+    channel_sum_kernel<true><<<(int)grid, 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(g), out, npix, C8, Cstride / 8, C);
+  else
+    channel_sum_kernel<false><<<(int)grid, 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(g), out, npix, C8, Cstride / 8, C);
   return after_launch("channel_sum_kernel");
 }

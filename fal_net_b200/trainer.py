@@ -175,6 +175,10 @@ class FlatAdamDDP:
         if self.overlap:
             self._hook(self._index[name])
 
+    def completes_bucket(self, name):
+        """True if marking ``name`` ready will complete (and launch the all-reduce of) its bucket."""
+        return bool(self.overlap) and self._pending[self._bucket_of[self._index[name]]] == 1
+
     def _hook(self, i):
         b = self._bucket_of[i]
         self._pending[b] -= 1
