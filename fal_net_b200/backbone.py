@@ -153,10 +153,11 @@ def disparity(model, image, min_disp, max_disp):
 # ------------------------------------------------------------------------------------------------------------------
 _SIDE_STREAMS: dict = {}
 USE_SIDE_STREAM = True      # bench.py switches this off for its per-kernel timing pass (kernels then run one at a time)
-# Parameter-gradient tasks (weight gradients, bias sums) of different layers are independent: they are dealt round-robin
-# onto this many side streams, so the latency-bound kernels of the small layers overlap each other as well as the
-# data-gradient chain.  FALN_SIDE_STREAMS overrides (1 = the single side stream of the earlier design).
-N_SIDE_STREAMS = max(1, int(os.environ.get("FALN_SIDE_STREAMS", "2")))
+# Parameter-gradient tasks (weight gradients, bias sums) of different layers are independent and can be dealt round-robin
+# onto several side streams (FALN_SIDE_STREAMS).  Measured on B200 (gpurun_out/s6_*): the data-gradient chain on the main
+# stream is the critical path and more concurrency beside it only takes SMs away from it -- Stage-1 step 5.04 ms with one
+# side stream, 5.26 ms with two to four; Stage-2 15.67 vs 15.97 ms.  Default: one.
+N_SIDE_STREAMS = max(1, int(os.environ.get("FALN_SIDE_STREAMS", "1")))
 
 
 def _side_streams(dev):

@@ -27,6 +27,8 @@
 //     [Cout, 3, 3, Cin_total] (KRSC, the layout of the flat gradient arena the fused Adam reads: lanes = consecutive ci,
 //     so every red.global.add.f32 is a coalesced 128-byte request); gradients of a concatenated input are two calls with
 //     different column offsets.  No workspace, no separate reduction kernel.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace faln {
@@ -300,7 +302,11 @@ extern "C" int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B
   const int smem = 256 + 1024 + p.stages * stage_bytes;
   // split-K: about two CTAs per SM over the whole grid, at least ~4 chunks per CTA (prologue + epilogue amortisation)
   const int nblk = p.n_cib * p.n_cob;
-  int splits = (2 * sm_count()) / nblk;
+  // FALN_WGRAD_FILL_PCT: CTAs the split-K aims for, in percent of the SM count.  The kernel runs on the gradient side
+  // stream next to the data-gradient chain, which is the critical path of the step: measured on B200 (Stage-1 step,
+  // gpurun_out/s7_*) 300 % -> 5.33 ms, 200 % -> 5.07 ms, 100 % -> 4.75 ms.
+  static const int fill_pct = getenv("FALN_WGRAD_FILL_PCT") ? atoi(getenv("FALN_WGRAD_FILL_PCT")) : 100;
+  int splits = ((fill_pct > 0 ? fill_pct : 100) * sm_count() / 100) / nblk;
   if (splits > p.chunks / 4) splits = p.chunks / 4;
   if (splits < 1) splits = 1;
   CUtensorMap mx, mg;

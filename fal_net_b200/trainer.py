@@ -12,6 +12,8 @@
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -266,7 +268,11 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # FALN_MAIN_PRIORITY=1: capture on a high-priority stream, so the kernels of the critical (forward / data-gradient)
+        # chain are scheduled ahead of the parameter-gradient work on the default-priority side stream
+        prio = int(os.environ.get("FALN_MAIN_PRIORITY", "0"))
+        cap_stream = torch.cuda.Stream(priority=-1) if prio else None
+        with torch.cuda.graph(self.graph, stream=cap_stream):
             self.loss = self._body()
         self.replays = 0
         # input prefetch: the NEXT batch's host->device copy runs on a copy stream while the current step executes

@@ -1,18 +1,22 @@
 #!/bin/bash
-# gpurun session for step-level numbers: side-stream / channel_sum variants, full GPU suite.
+# gpurun session for step-level numbers: stream priority / footprint variants of the gradient side work.
 set -u
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 TAG=${1:-t}
-echo "== model tests"; timeout 600 python -m pytest tests/test_model_gpu.py tests/test_conv_gpu.py -q > gpurun_out/${TAG}_modeltests.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/${TAG}_modeltests.log
-for cfg in "2 2" "1 2" "3 2" "4 2" "2 1" "3 1"; do
-  set -- $cfg
-  echo "== bench stage1 side_streams=$1 chsum_cap=$2"
-  FALN_SIDE_STREAMS=$1 FALN_CHSUM_CAP=$2 timeout 300 python bench.py > gpurun_out/${TAG}_bench_ss_$1_$2.json 2> gpurun_out/${TAG}_bench_ss_$1_$2.err
-  python -c "import json;d=json.load(open('gpurun_out/${TAG}_bench_ss_$1_$2.json'));print(d['ms_per_step'],d['value'],d['e2e']['value'])"
+run() {  # name, env...
+  local name=$1; shift
+  echo "== bench stage1 $name"
+  env "$@" timeout 300 python bench.py > gpurun_out/${TAG}_bench_$name.json 2> gpurun_out/${TAG}_bench_$name.err
+  python -c "import json;d=json.load(open('gpurun_out/${TAG}_bench_$name.json'));print(d['ms_per_step'],d['value'],d['e2e']['value'])"
+}
+run p100 FALN_WGRAD_FILL_PCT=100
+run p75 FALN_WGRAD_FILL_PCT=75
+run p50 FALN_WGRAD_FILL_PCT=50
+run p33 FALN_WGRAD_FILL_PCT=33
+run p50_cs1 FALN_WGRAD_FILL_PCT=50 FALN_CHSUM_CAP=1
+run p200 FALN_WGRAD_FILL_PCT=200
+for pct in 100 50; do
+echo "== stage2 pct=$pct"; FALN_WGRAD_FILL_PCT=$pct timeout 400 python bench.py --workload stage2 > gpurun_out/${TAG}_bench_stage2_p$pct.json 2> gpurun_out/${TAG}_bench_stage2_p$pct.err
+python -c "import json;d=json.load(open('gpurun_out/${TAG}_bench_stage2_p$pct.json'));print(d['ms_per_step'],d['value'],d['e2e']['value'])"
 done
-for ss in 1 2 3; do
-  echo "== stage2 side_streams=$ss"; FALN_SIDE_STREAMS=$ss timeout 400 python bench.py --workload stage2 > gpurun_out/${TAG}_bench_stage2_ss$ss.json 2> gpurun_out/${TAG}_bench_stage2_ss$ss.err
-  python -c "import json;d=json.load(open('gpurun_out/${TAG}_bench_stage2_ss$ss.json'));print(d['ms_per_step'],d['value'],d['e2e']['value'])"
-done
-echo "== full gpu suite"; timeout 900 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_gputests.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/${TAG}_gputests.log
