@@ -11,61 +11,91 @@ namespace {
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : (__expf(v) - 1.0f); }
 
 // Stem: y[b,h,w,:] = act(bias + sum_{c<3,kh,kw} w[co,c,kh,kw] * x[b,c,h+kh-1,w+kw-1]), x fp32 NCHW (optionally read
-// x-reversed), y bf16 NHWC.  One thread per output pixel, COUT accumulators in registers, weights broadcast from
-// shared memory.  Replaces conv0.0 (/root/reference/models/FAL_netB.py:99) and VGG conv1_1.
+// x-reversed), y bf16 NHWC.  Replaces conv0.0 (/root/reference/models/FAL_netB.py:99) and VGG conv1_1.
+// A thread owns TWO horizontally adjacent pixels x 32 output channels: the 3 x 4 input window is loaded once for both, and
+// every broadcast 128-bit weight load feeds four packed FFMA2 (two channel pairs x two pixels), so the kernel issues
+// ~540 instructions per pixel and 32 channels instead of ~1,080 (one pixel x COUT channels per thread, scalar FFMA; ncu
+// launch lists profiles/r1e_*: 88 us per Stage-1 launch against a 24 us FMA-pipe floor).  fp32 accumulation in the same
+// (c, kh, kw) order as before.
 template <int COUT>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                                                         int B, int H, int W, int act, int flip_x) {
-  __shared__ float ws[27 * COUT];  // [tap][c][co] -> index (c*9 + kh*3 + kw) * COUT + co
-  __shared__ float bs[COUT];
+  constexpr int G = COUT / 32;                        // channel groups of 32
+  __shared__ __align__(16) float ws[27 * COUT];       // [tap][co], tap = c*9 + kh*3 + kw
+  __shared__ __align__(16) float bs[COUT];
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
-    const int co = i % COUT, t = i / COUT;  // t = c*9 + kh*3 + kw
+    const int co = i % COUT, t = i / COUT;
     ws[i] = __ldg(w + co * 27 + t);
   }
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = bias ? __ldg(bias + i) : 0.f;
   __syncthreads();
-  const long long npx = (long long)B * H * W;
+  const int pw = (W + 1) / 2;                          // pixel pairs per row
+  const long long units = (long long)B * H * pw * G;
   const long long hw = (long long)H * W;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
-    const int xw = (int)(i % W);
-    const int yh = (int)((i / W) % H);
-    const long long b = i / hw;
-    float acc[COUT];
+  for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < units; u += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(u % G);
+    long long r = u / G;
+    const int xw = (int)(r % pw) * 2;
+    r /= pw;
+    const int yh = (int)(r % H);
+    const long long b = r / H;
+    float2 acc0[16], acc1[16];
+    {
+      const float2* bp = reinterpret_cast<const float2*>(bs + cg * 32);
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = bs[co];
+      for (int j = 0; j < 16; ++j) acc0[j] = acc1[j] = bp[j];
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const int yy = yh + kh - 1;
+        float v[4];
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int xx = xw + kw - 1;
-          float v = 0.f;
+        for (int k = 0; k < 4; ++k) {
+          const int xx = xw + k - 1;
+          v[k] = 0.f;
           if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
             const int xs = flip_x ? W - 1 - xx : xx;
-            v = __ldg(x + (b * 3 + c) * hw + (long long)yy * W + xs);
+            v[k] = __ldg(x + (b * 3 + c) * hw + (long long)yy * W + xs);
           }
-          const float* wp = ws + (c * 9 + kh * 3 + kw) * COUT;
+        }
 #pragma unroll
-          for (int co = 0; co < COUT; ++co) acc[co] = fmaf(v, wp[co], acc[co]);
+        for (int kw = 0; kw < 3; ++kw) {
+          const float4* wp = reinterpret_cast<const float4*>(ws + (c * 9 + kh * 3 + kw) * COUT + cg * 32);
+          const float2 a0 = make_float2(v[kw], v[kw]), a1 = make_float2(v[kw + 1], v[kw + 1]);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 w4 = wp[q];
+            const float2 wl = make_float2(w4.x, w4.y), wh = make_float2(w4.z, w4.w);
+            acc0[2 * q] = __ffma2_rn(a0, wl, acc0[2 * q]);
+            acc0[2 * q + 1] = __ffma2_rn(a0, wh, acc0[2 * q + 1]);
+            acc1[2 * q] = __ffma2_rn(a1, wl, acc1[2 * q]);
+            acc1[2 * q + 1] = __ffma2_rn(a1, wh, acc1[2 * q + 1]);
+          }
         }
       }
     }
-    uint4* dst = reinterpret_cast<uint4*>(y + i * COUT);
 #pragma unroll
-    for (int q = 0; q < COUT / 8; ++q) {
-      uint4 u;
-      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+    for (int px = 0; px < 2; ++px) {
+      if (xw + px >= W) break;
+      const long long pix = (b * H + yh) * W + xw + px;
+      uint4* dst = reinterpret_cast<uint4*>(y + pix * COUT + cg * 32);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float a0 = acc[q * 8 + 2 * e], a1 = acc[q * 8 + 2 * e + 1];
-        if (act == 1) { a0 = elu1(a0); a1 = elu1(a1); }
-        else if (act == 2) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-        h2[e] = __floats2bfloat162_rn(a0, a1);
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = px ? acc1[q * 4 + e] : acc0[q * 4 + e];
+          float a0 = a.x, a1 = a.y;
+          if (act == 1) { a0 = elu1(a0); a1 = elu1(a1); }
+          else if (act == 2) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+          h2[e] = __floats2bfloat162_rn(a0, a1);
+        }
+        dst[q] = o;
       }
-      dst[q] = u;
     }
   }
 }
@@ -284,12 +314,11 @@ extern "C" int faln_stem_conv(const float* x, const float* w, const float* bias,
                               int act, int flip_x, faln_stream_t stream) {
   FALN_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0, "faln_stem_conv: bad argument");
   FALN_REQUIRE(Cout == 32 || Cout == 64, "faln_stem_conv: Cout must be 32 or 64 (got %d)", Cout);
-  const long long npx = (long long)B * H * W;
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(y);
   if (Cout == 32)
-    stem_conv_kernel<32><<<ew_grid(npx, 128), 128, 0, as_stream(stream)>>>(x, w, bias, out, B, H, W, act, flip_x);
+    stem_conv_kernel<32><<<ew_grid((long long)B * H * ((W + 1) / 2), 128), 128, 0, as_stream(stream)>>>(x, w, bias, out, B, H, W, act, flip_x);
   else
-    stem_conv_kernel<64><<<ew_grid(npx, 128), 128, 0, as_stream(stream)>>>(x, w, bias, out, B, H, W, act, flip_x);
+    stem_conv_kernel<64><<<ew_grid((long long)B * H * ((W + 1) / 2) * 2, 128), 128, 0, as_stream(stream)>>>(x, w, bias, out, B, H, W, act, flip_x);
   return after_launch("stem_conv_kernel");
 }
 
