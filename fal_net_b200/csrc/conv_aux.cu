@@ -17,10 +17,10 @@ __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : (__expf(v)
 // ~540 instructions per pixel and 32 channels instead of ~1,080 (one pixel x COUT channels per thread, scalar FFMA; ncu
 // launch lists profiles/r1e_*: 88 us per Stage-1 launch against a 24 us FMA-pipe floor).  fp32 accumulation in the same
 // (c, kh, kw) order as before.
-template <int COUT>
+template <int COUT, int ACT>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
-                                                        int B, int H, int W, int act, int flip_x) {
+                                                        int B, int H, int W, int flip_x) {
   constexpr int G = COUT / 32;                        // channel groups of 32
   __shared__ __align__(16) float ws[27 * COUT];       // [tap][co], tap = c*9 + kh*3 + kw
   __shared__ __align__(16) float bs[COUT];
@@ -31,39 +31,45 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = bias ? __ldg(bias + i) : 0.f;
   __syncthreads();
   const int pw = (W + 1) / 2;                          // pixel pairs per row
-  const long long units = (long long)B * H * pw * G;
-  const long long hw = (long long)H * W;
-  for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < units; u += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(u % G);
-    long long r = u / G;
-    const int xw = (int)(r % pw) * 2;
+  const int units = B * H * pw * G;                    // < 2^31 (checked on the host)
+  const int hw = H * W;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < units; u += gridDim.x * blockDim.x) {
+    const int cg = u % G;
+    int r = u / G;
+    const int xw = (r % pw) * 2;
     r /= pw;
-    const int yh = (int)(r % H);
-    const long long b = r / H;
+    const int yh = r % H;
+    const int b = r / H;
+    // column offsets / validity of the four window columns and row validity of the three window rows: once per unit
+    int xo[4];
+    bool xv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int xx = xw + k - 1;
+      xv[k] = xx >= 0 && xx < W;
+      xo[k] = flip_x ? W - 1 - xx : xx;
+    }
     float2 acc0[16], acc1[16];
     {
       const float2* bp = reinterpret_cast<const float2*>(bs + cg * 32);
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc0[j] = acc1[j] = bp[j];
     }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
+    const float* xb = x + (size_t)b * 3 * hw + (size_t)yh * W;
+    const float* wp0 = ws + cg * 32;
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {      // rolled: keeps the loop body (288 FFMA2) inside the instruction cache
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const int yy = yh + kh - 1;
+        const bool yv = yy >= 0 && yy < H;
+        const float* xr = xb + (kh - 1) * W;
         float v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int xx = xw + k - 1;
-          v[k] = 0.f;
-          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-            const int xs = flip_x ? W - 1 - xx : xx;
-            v[k] = __ldg(x + (b * 3 + c) * hw + (long long)yy * W + xs);
-          }
-        }
+        for (int k = 0; k < 4; ++k) v[k] = (yv && xv[k]) ? __ldg(xr + xo[k]) : 0.f;
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const float4* wp = reinterpret_cast<const float4*>(ws + (c * 9 + kh * 3 + kw) * COUT + cg * 32);
+          const float4* wp = reinterpret_cast<const float4*>(wp0 + (kh * 3 + kw) * COUT);
           const float2 a0 = make_float2(v[kw], v[kw]), a1 = make_float2(v[kw + 1], v[kw + 1]);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -76,12 +82,14 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
           }
         }
       }
+      xb += hw;
+      wp0 += 9 * COUT;
     }
+    const size_t pix = ((size_t)b * H + yh) * W + xw;
 #pragma unroll
     for (int px = 0; px < 2; ++px) {
       if (xw + px >= W) break;
-      const long long pix = (b * H + yh) * W + xw + px;
-      uint4* dst = reinterpret_cast<uint4*>(y + pix * COUT + cg * 32);
+      uint4* dst = reinterpret_cast<uint4*>(y + (pix + px) * COUT + cg * 32);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 o;
@@ -90,8 +98,8 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
         for (int e = 0; e < 4; ++e) {
           const float2 a = px ? acc1[q * 4 + e] : acc0[q * 4 + e];
           float a0 = a.x, a1 = a.y;
-          if (act == 1) { a0 = elu1(a0); a1 = elu1(a1); }
-          else if (act == 2) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+          if (ACT == 1) { a0 = elu1(a0); a1 = elu1(a1); }
+          else if (ACT == 2) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
           h2[e] = __floats2bfloat162_rn(a0, a1);
         }
         dst[q] = o;
@@ -314,11 +322,19 @@ extern "C" int faln_stem_conv(const float* x, const float* w, const float* bias,
                               int act, int flip_x, faln_stream_t stream) {
   FALN_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0, "faln_stem_conv: bad argument");
   FALN_REQUIRE(Cout == 32 || Cout == 64, "faln_stem_conv: Cout must be 32 or 64 (got %d)", Cout);
+  FALN_REQUIRE(act >= 0 && act <= 2, "faln_stem_conv: act must be 0 (none), 1 (ELU) or 2 (ReLU)");
+  const long long units = (long long)B * H * ((W + 1) / 2) * (Cout / 32);
+  FALN_REQUIRE(units < (1LL << 31) && (long long)B * 3 * H * W < (1LL << 31), "faln_stem_conv: tensor too large");
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(y);
-  if (Cout == 32)
-    stem_conv_kernel<32><<<ew_grid((long long)B * H * ((W + 1) / 2), 128), 128, 0, as_stream(stream)>>>(x, w, bias, out, B, H, W, act, flip_x);
-  else
-    stem_conv_kernel<64><<<ew_grid((long long)B * H * ((W + 1) / 2) * 2, 128), 128, 0, as_stream(stream)>>>(x, w, bias, out, B, H, W, act, flip_x);
+  const int grid = ew_grid(units, 128);
+  cudaStream_t st = as_stream(stream);
+#define FALN_STEM(C, A) stem_conv_kernel<C, A><<<grid, 128, 0, st>>>(x, w, bias, out, B, H, W, flip_x)
+  if (Cout == 32) {
+    if (act == 0) FALN_STEM(32, 0); else if (act == 1) FALN_STEM(32, 1); else FALN_STEM(32, 2);
+  } else {
+    if (act == 0) FALN_STEM(64, 0); else if (act == 1) FALN_STEM(64, 1); else FALN_STEM(64, 2);
+  }
+#undef FALN_STEM
   return after_launch("stem_conv_kernel");
 }
 
