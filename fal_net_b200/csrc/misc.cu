@@ -91,6 +91,56 @@ __global__ void __launch_bounds__(256) planar_to_nhwc_kernel(const float* __rest
   }
 }
 
+// Wide variant for Cp <= 64, 16-byte aligned planar rows: a block owns 128 pixels of one row and all channels.  Every
+// thread issues its 8 (Cp = 64) 128-bit loads before the one barrier, then writes 16-byte chunks of 8 bf16 channels; a
+// warp's store covers 4 pixels x 128 bytes contiguously.  (The 32-pixel kernel above keeps 4 scalar loads in flight per
+// thread and synchronises twice per 32 channels: 93 us for the 8x49x192x640 gradient, against ~55 us of DRAM time.)
+template <int CP>
+__global__ void __launch_bounds__(256) planar_to_nhwc_wide_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                                  int C, int H, int W, long long pitch) {
+  constexpr int kPX = 128, kStride = kPX + 4;            // +4 floats: 16-byte aligned rows, chunk reads 2-way conflicted at most
+  __shared__ __align__(16) float tile[CP * kStride];
+  const int xt = blockIdx.x * kPX;
+  const int y = blockIdx.y, b = blockIdx.z;
+  constexpr int kLoads = CP * (kPX / 4) / 256;           // float4 loads per thread
+  float4 v[kLoads];
+#pragma unroll
+  for (int k = 0; k < kLoads; ++k) {
+    const int i = threadIdx.x + 256 * k;
+    const int c = i / (kPX / 4), x = xt + 4 * (i % (kPX / 4));
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C && x < W) {
+      const float* sp = src + (((long long)b * C + c) * H + y) * pitch + x;
+      if (x + 3 < W) {
+        v[k] = __ldg(reinterpret_cast<const float4*>(sp));
+      } else {
+        v[k].x = __ldg(sp);
+        if (x + 1 < W) v[k].y = __ldg(sp + 1);
+        if (x + 2 < W) v[k].z = __ldg(sp + 2);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kLoads; ++k) {
+    const int i = threadIdx.x + 256 * k;
+    *reinterpret_cast<float4*>(tile + (i / (kPX / 4)) * kStride + 4 * (i % (kPX / 4))) = v[k];
+  }
+  __syncthreads();
+  constexpr int kChunks = CP / 8;                         // 16-byte chunks per pixel
+#pragma unroll
+  for (int k = 0; k < kPX * kChunks / 256; ++k) {
+    const int i = threadIdx.x + 256 * k;
+    const int ch = i % kChunks, px = i / kChunks, x = xt + px;
+    if (x >= W) continue;
+    uint4 o;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      h2[e] = __floats2bfloat162_rn(tile[(ch * 8 + 2 * e) * kStride + px], tile[(ch * 8 + 2 * e + 1) * kStride + px]);
+    *reinterpret_cast<uint4*>(dst + (((long long)b * H + y) * W + x) * CP + ch * 8) = o;
+  }
+}
+
 __global__ void __launch_bounds__(256) nhwc_to_planar_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
                                                              int C, int H, int W, int Cp, long long pitch) {
   __shared__ float tile[32][33];
@@ -209,6 +259,14 @@ extern "C" int faln_planar_to_nhwc_bf16(const float* src, void* dst, int B, int 
                                         faln_stream_t stream) {
   FALN_REQUIRE(src && dst && B > 0 && C > 0 && Cp >= C && pitch >= W && H <= 65535 && B <= 65535,
                "faln_planar_to_nhwc_bf16: bad argument");
+  if ((Cp == 64 || Cp == 32) && pitch % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    dim3 gridw((W + 127) / 128, H, B);
+    if (Cp == 64)
+      planar_to_nhwc_wide_kernel<64><<<gridw, 256, 0, as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), C, H, W, pitch);
+    else
+      planar_to_nhwc_wide_kernel<32><<<gridw, 256, 0, as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), C, H, W, pitch);
+    return after_launch("planar_to_nhwc_wide_kernel");
+  }
   dim3 grid((W + 31) / 32, H, B);
   planar_to_nhwc_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), C, H, W, Cp, pitch);
   return after_launch("planar_to_nhwc_kernel");

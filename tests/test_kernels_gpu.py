@@ -146,3 +146,13 @@ def test_layout_kernels():
     back = layout.nhwc_bf16_to_planar(zn, 49, pitch=72)
     assert back.shape == (2, 49, 5, 70) and back.stride(2) == 72
     assert torch.equal(back.cpu(), z.bfloat16().float())
+    # 16-byte aligned planar rows (the layout of the logits / their gradient): wide transpose kernel, incl. a ragged last
+    # quad (W % 4 != 0), more than one 128-pixel block per row, and Cp = 32
+    for C, Cp, W in ((49, 64, 70), (49, 64, 301), (17, 32, 130), (64, 64, 128)):
+        zz = torch.randn(2, C, 3, W, generator=g)
+        zp = layout.alloc_planar(2, C, 3, W, dev)
+        zp.copy_(zz.to(dev))
+        out = layout.planar_to_nhwc_bf16(zp, Cp)
+        ref = torch.zeros(2, 3, W, Cp)
+        ref[..., :C] = zz.permute(0, 2, 3, 1)
+        assert torch.equal(out.cpu().float(), ref.bfloat16().float()), (C, Cp, W)
