@@ -35,7 +35,7 @@ def launches(src, dst):
         agg[name][0] += 1
         agg[name][1] += v
         tot += v
-    ours = sum(t for k, (n, t) in agg.items() if "faln::" in k)
+    ours = sum(t for k, (n, t) in agg.items() if "faln::" in k or "m3::" in k)
     with open(dst, "w") as f:
         f.write(f"# source: {src} (ncu --metrics gpu__time_duration.sum --clock-control none; cold-cache, serialised)\n")
         f.write(f"# total {tot:.1f} us over {sum(n for n, _ in agg.values())} launches; libfalnet kernels {ours:.1f} us ({100 * ours / tot:.1f}%)\n")
