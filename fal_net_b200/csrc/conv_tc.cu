@@ -638,7 +638,10 @@ int try_row_kernel(const void* x, const void* x2, const void* wptr, int wrows, C
 // long K loop alone (measured: 16 CTAs, 22-45 us for the 3x10 bottleneck layers).  Narrow the N tile until the grid
 // covers the SMs; the A tile is re-read by the extra CTAs out of L2.
 int narrow_bn(int BN, int tiles, int cout_pad, int ncls) {
-  while (BN > 64 && tiles * (cout_pad / BN) * ncls < sm_count()) BN >>= 1;
+  // FALN_CONV_NARROW_PCT: work items (in % of the SM count) below which the N tile is halved.  Measured on the Stage-1 step
+  // (gpurun_out/s16_*): 200 % -> 4.655 ms, 100 % -> 4.657 ms, 50 % -> 4.606 ms.
+  static const int pct = getenv("FALN_CONV_NARROW_PCT") ? atoi(getenv("FALN_CONV_NARROW_PCT")) : 50;
+  while (BN > 64 && tiles * (cout_pad / BN) * ncls < sm_count() * pct / 100) BN >>= 1;
   return BN;
 }
 
@@ -648,7 +651,9 @@ int narrow_bn(int BN, int tiles, int cout_pad, int ncls) {
 int dispatch(int BK, int BN, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& wm, const ConvParams& p,
              cudaStream_t st) {
   const long long total = (long long)p.tiles_w * p.tiles_h * p.B * ((p.Cout + BN - 1) / BN) * p.ncls;
-  const bool deep = total <= 2LL * sm_count();
+  // FALN_CONV_DEEP_PCT: work items (in % of the SM count) up to which the deep-ring / one-CTA-per-SM variants are used
+  static const int deep_pct = getenv("FALN_CONV_DEEP_PCT") ? atoi(getenv("FALN_CONV_DEEP_PCT")) : 200;
+  const bool deep = total <= (long long)sm_count() * deep_pct / 100;
   if (BK == 64) {
     switch (BN) {
       case 256: return launch<64, 256, 4>(a1, a2, wm, p, st);

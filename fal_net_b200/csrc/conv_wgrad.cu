@@ -296,7 +296,10 @@ extern "C" int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B
   }
   p.Cx = Cx; p.Cout = Cout; p.ci_off = ci_off; p.Cin_tot = Cin_tot; p.dW = dW;
   const int stage_bytes = p.x_bytes + gbox;
-  p.stages = (200 * 1024) / stage_bytes;
+  // FALN_WGRAD_SMEM_KB: shared memory the operand ring may take (tuning aid).  The kernel runs beside the data-gradient chain;
+  // a CTA that fills the SM's shared memory keeps that chain's CTAs off the SM for as long as it runs.
+  static const int ring_kb = getenv("FALN_WGRAD_SMEM_KB") ? atoi(getenv("FALN_WGRAD_SMEM_KB")) : 200;
+  p.stages = ((ring_kb > 0 ? ring_kb : 200) * 1024) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) p.stages = 2;
   const int smem = 256 + 1024 + p.stages * stage_bytes;
