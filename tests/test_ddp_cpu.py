@@ -50,6 +50,19 @@ def _worker(rank, world, port, out):
     opt = FlatAdamDDP(model, lr=1e-2, bucket_mb=1e-4, _update=_cpu_update)     # tiny buckets -> several all-reduces
     assert len(opt.buckets) >= 2
     opt.broadcast_parameters()
+    # gradient-sink protocol of the hand-scheduled backward: marking the last member of a bucket launches its all-reduce
+    # (the backward then makes its side stream wait for the sibling streams first, backbone.backward.ready)
+    opt.zero_grad()
+    b0 = opt._bucket_of[0]
+    members = [n for n in opt.names if opt._bucket_of[opt._index[n]] == b0]
+    for n in members[:-1]:
+        assert not opt.completes_bucket(n)
+        opt.mark_ready(n)
+    assert opt.completes_bucket(members[-1])
+    opt.mark_ready(members[-1])
+    assert len(opt._works) == 1
+    for w in opt._works:
+        w.wait()
     g = torch.Generator().manual_seed(100 + rank)                               # rank-offset data
     for _ in range(3):
         x = torch.randn(4, 7, generator=g)

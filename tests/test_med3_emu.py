@@ -77,6 +77,25 @@ def test_emulated_kernels_match_oracle(emu, B, N, H, W, maxd, mind):
         assert e < TOL, (nm, e)
 
 
+def test_per_sample_level_tables(emu):
+    """Every sample with its own disparity range (its own class-sorted plane table in the kernels), N = 65."""
+    B, N, H, W = 3, 65, 2, 322
+    g = torch.Generator().manual_seed(21)
+    logits = 2 * torch.randn(B, N, H, W, generator=g)
+    img = images(B, H, W, 8)
+    gp, gd = torch.randn(B, 3, H, W, generator=g), torch.randn(B, 1, H, W, generator=g)
+    mx = torch.tensor([300.0, 120.0, 33.3]).view(B, 1, 1)
+    mn = torch.tensor([2.0, 0.7, 1.1]).view(B, 1, 1)
+    d, xo = O.level_tables(mn, mx, N, W)
+    ref = O.med_forward_closed(logits, img, d, xo)
+    ref["glogits"] = O.med_backward_closed(logits, img, d, xo, gp, gd)
+    out, flagged = _run(emu, logits, img, d, xo, gp, gd)
+    assert flagged == 0
+    for nm in ("pan", "disp", "maskL", "maskR", "lse0", "lsew", "glogits"):
+        e = rel_err(out[nm], ref[nm])
+        assert e < TOL, (nm, e)
+
+
 def test_generic_code_matches_fast_code(emu):
     """Every plane forced onto the per-pixel generic functions: same results as the class-specialised windows."""
     B, N, H, W = 1, 21, 2, 322
