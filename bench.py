@@ -382,8 +382,15 @@ def run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP
     if med_stats:
         dom = max(med_stats.items(), key=lambda kv: kv[1]["avg_ms"] * kv[1]["launches_per_step"])[0]
         st = med_stats[dom]
+        # `traffic` stays null (no ncu capture of THIS batch shape); `traffic_ncu` quotes dram__bytes_read.sum +
+        # dram__bytes_write.sum per launch of the committed `ncu --set full` captures (profiles/r1e_med3_full_*) beside the
+        # algorithmic bytes of the captured shape: DRAM traffic ~ algorithmic bytes, i.e. no wasted re-reads
+        ncu_traffic = {"med_fwd": {"shape": "16x49x192x640", "dram_mb": 447.7, "algorithmic_mb": 440.4},
+                       "med_fwd_masks": {"shape": "16x49x192x640", "dram_mb": 468.3, "algorithmic_mb": 456.1},
+                       "med_bwd": {"shape": "8x49x375x1242", "dram_mb": 1888.7, "algorithmic_mb": 1564.9}}
         roofline_med = {"kernel": dom, "bound": "hbm", "achieved": st["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                        "frac": st["frac"], "traffic": None, "peak_source": peak_src + " hbm_gbs",
+                        "frac": st["frac"], "traffic": None, "traffic_ncu": ncu_traffic.get(dom),
+                        "peak_source": peak_src + " hbm_gbs",
                         "avg_launch_ms": st["avg_ms"], "share_of_step": st["share_of_step"], "all_med_kernels": med_stats}
         if roofline is None:
             roofline, roofline_med = roofline_med, None
