@@ -14,17 +14,32 @@ from fal_net_b200.entry_common import SyntheticStereo, init_distributed
 
 parser = argparse.ArgumentParser(description="Testing pan generation (B200-native hot path)",
                                  formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+def _flag(v):
+    """The reference declares its switches as plain valued options (``-fpp True``); accept that form and the bare switch."""
+    return str(v).lower() not in ("0", "false", "no", "none", "")
+
+
 parser.add_argument("-d", "--data", default="")
 parser.add_argument("-tn", "--tdataName", default="Kitti_eigen_test_improved")
 parser.add_argument("-relbase", "--rel_baselne", type=float, default=1)
 parser.add_argument("-mdisp", "--max_disp", type=float, default=300)
 parser.add_argument("-mindisp", "--min_disp", type=float, default=2)
-parser.add_argument("-b", "--batch_size", type=int, default=8)
+parser.add_argument("-b", "--batch_size", type=int, default=8, help="reference default: 1 (its loader is b1, :113)")
 parser.add_argument("-m", "--model", default="FAL_netB")
 parser.add_argument("-no_levels", "--no_levels", type=int, default=49)
 parser.add_argument("--checkpoint", default=None, help="checkpoint.pth.tar of the reference or of this repo")
-parser.add_argument("-fpp", "--f_post_process", action="store_true")
-parser.add_argument("-mspp", "--ms_post_process", action="store_true")
+parser.add_argument("-fpp", "--f_post_process", nargs="?", const=True, default=False, type=_flag)
+parser.add_argument("-mspp", "--ms_post_process", nargs="?", const=True, default=True, type=_flag,
+                    help="multi-scale post-processing (the reference's shipped default, :57-58); -fpp takes precedence")
+# accepted for command-line compatibility with the reference (:34-60); data loading, metric tables and PNG / PLY dumps are
+# out of scope (SURVEY.md 2.1), the values are not used
+for _opts, _dflt in ((("-eval", "--evaluate"), True), (("-save", "--save"), False), (("-save_pc", "--save_pc"), False),
+                     (("-save_pan", "--save_pan"), False), (("-save_input", "--save_input"), False),
+                     (("-w", "--workers"), 4), (("--print-freq", "-p"), 10), (("-gpu_no", "--gpu_no"), "0"),
+                     (("-dt", "--dataset"), "Kitti_stage2"), (("-ts", "--time_stamp"), ""), (("-dtl", "--details"), ""),
+                     (("-median", "--median"), False)):
+    parser.add_argument(*_opts, default=_dflt, help="accepted, unused")
+parser.add_argument("--sparse", action="store_true", default=False, help="accepted, unused")
 parser.add_argument("--images", type=int, default=64, help="number of synthetic 375x1242 images (Eigen-split shaped)")
 
 

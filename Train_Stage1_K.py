@@ -43,6 +43,12 @@ parser.add_argument("--epoch_size", type=int, default=0)
 parser.add_argument("--print-freq", "-p", type=int, default=100)
 parser.add_argument("--start-epoch", type=int, default=0)
 parser.add_argument("--pretrained", default=None, help="checkpoint to resume from")
+# accepted for command-line compatibility with the reference (data loading / validation split are out of scope,
+# SURVEY.md 2.1): the values are not used
+for _opts, _dflt in ((("-train_split", "--train_split"), "eigen_train_split"), (("-vdn", "--vdataName"), "Kitti2015"),
+                     (("-relbase_test", "--rel_baset"), 1), (("-w", "--workers"), 4), (("-tbs", "--tbatch_size"), 1)):
+    parser.add_argument(*_opts, default=_dflt, help="accepted, unused")
+parser.add_argument("--sparse", action="store_true", default=True, help="accepted, unused")
 parser.add_argument("--synthetic", type=int, default=50, help="synthetic batches per epoch (no dataset on the box)")
 parser.add_argument("--save_path", default="Kitti_stage1")
 

@@ -13,7 +13,8 @@ from fal_net_b200.entry_common import AverageMeter, SyntheticStereo, init_distri
 from fal_net_b200.trainer import FlatAdamDDP
 
 parser = S1.parser
-parser.set_defaults(lr=0.00005, a_sm=0.4 * 2 / 512, save_path="Kitti_stage2")
+# defaults of /root/reference/Train_Stage2_K.py:44-60 where they differ from Stage 1
+parser.set_defaults(lr=0.00005, a_sm=0.4 * 2 / 512, batch_size=4, milestones=[5, 10], epochs=20, save_path="Kitti_stage2")
 parser.add_argument("-mirror_loss", "--a_mr", type=float, default=1, help="Mirror loss weight")
 parser.add_argument("--fix_model", default=None, help="Stage-1 checkpoint for the frozen model (random init if absent)")
 
