@@ -8,6 +8,7 @@ import subprocess
 
 import pytest
 import torch
+from hypothesis import given, settings, strategies as st
 
 from oracle import falnet_oracle as O
 from tests.helpers import disp_range, images, rel_err
@@ -156,3 +157,25 @@ def test_overflow_rows_are_flagged(emu):
     out, flagged = _run(emu, logits, img, d, xo, gp, gd)
     marks = torch.isnan(out["lse0"][0, 0, 0]).nonzero().flatten().tolist()
     assert flagged == 1 and 128 in marks and all(m % 128 == 0 for m in marks)
+
+
+@settings(max_examples=12, deadline=None)
+@given(W=st.integers(8, 200), N=st.integers(2, 24), maxd=st.floats(1.0, 260.0), ratio=st.floats(1.5, 200.0),
+       seed=st.integers(0, 10_000))
+def test_random_shapes_and_disparity_ranges(emu, W, N, maxd, ratio, seed):
+    """Property test: arbitrary widths (every W % 4, rows shorter than a warp, shifts beyond the row), plane counts and
+    disparity ranges -- the emulated kernels agree with the oracle, and with their own generic per-pixel code."""
+    B, H = 2, 1
+    g = torch.Generator().manual_seed(seed)
+    logits = 2 * torch.randn(B, N, H, W, generator=g)
+    img = images(B, H, W, seed + 1)
+    gp, gd = torch.randn(B, 3, H, W, generator=g), torch.randn(B, 1, H, W, generator=g)
+    mn, mx = disp_range(B, maxd, maxd / ratio)
+    d, xo = O.level_tables(mn, mx, N, W)
+    ref = O.med_forward_closed(logits, img, d, xo)
+    ref["glogits"] = O.med_backward_closed(logits, img, d, xo, gp, gd)
+    out, flagged = _run(emu, logits, img, d, xo, gp, gd)
+    assert flagged == 0
+    for nm in ("pan", "disp", "maskL", "maskR", "glogits"):
+        e = rel_err(out[nm], ref[nm])
+        assert e < TOL, (nm, e, W, N, maxd, ratio, seed)
