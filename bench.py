@@ -3,10 +3,22 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload stage1|stage2|test|med] [--impl reference]
 
-One JSON line on stdout (rank 0).  Default workload = BASELINE.json configs[1]: a Stage-1 training step
+One JSON line on stdout (rank 0).  Headline workload at every N = BASELINE.json configs[1]: a Stage-1 training step
 (reconstruction + smoothness loss, Adam included), batch 8 per GPU, 640x192 crops, N = 49, synthetic
 KITTI-shaped stereo pairs, random-init weights (models.FAL_netB under torch.manual_seed(0)).
 A "step" = forward + losses + backward + gradient all-reduce (N > 1) + Adam on one batch.
+
+The same line carries, under "extras", driver-run sub-lines measured in the same process with the same timing rules:
+  * "stage2" (every N): BASELINE configs[2], the Stage-2 step the >= 7x scaling target is stated on -- per-N values
+    make the Stage-2 weak-scaling series (the headline stays ONE workload across N so the driver's own
+    value_N / (N * value_1) is meaningful);
+  * "test" (every N): configs[3], Test_KITTI flip post-processing, image-sharded, no collective;
+  * "med" (N = 1): configs[4], the six MED microbench shapes, fwd / fwd+masks / bwd, each with its HBM roofline;
+  * "reference_gpu" (N = 1): the UNMODIFIED reference (baseline/_ref) on the same B200 -- Stage-1 step B = 8 and
+    inference b1 -- the practical bar (SURVEY.md 8d);
+  * "conv_layers" (N = 1): every distinct FAL_netB layer shape, our kernel vs cuDNN bf16 channels_last (fwd, dgrad, wgrad).
+`--impl reference` times the reference's own code (baseline/_ref) on the host cores; `cpu_baseline` is the same thing
+on a bounded sample, run in a subprocess.
 """
 from __future__ import annotations
 
@@ -86,18 +98,91 @@ def synth_batch(B, H, W, seed, device="cpu", pin=False):
 
 
 # --------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port on the host cores
+# reference arm / cpu_baseline: the reference's own code (baseline/_ref) on the host cores; oracle port as fall-back
 # --------------------------------------------------------------------------------------------------
-def cpu_reference(workload, steps, warmup, sample_b=None, budget_s=25.0):
-    """Times oracle/falnet_oracle.py (the CPU restatement of the reference, bit-identical to it on CPU) on a
-    bounded sample of the workload.  Returns (value, unit, cores, sample_description, ms_per_step)."""
-    from oracle import falnet_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+def _reference_step_fn(device, workload, B, seed_off=0):
+    """Builds the reference model + optimiser exactly as the reference's entry points do (Train_Stage1_K.py:171-181,
+    Train_Stage2_K.py:172-190, Test_KITTI.py:123-124,196-203) and returns (step_fn, frames_per_step, description)."""
+    from baseline import ref_loader
+    cpu = device == "cpu"
+    RM, RL = ref_loader.load(cpu=cpu, want_losses=workload != "test")
     N = 49
+    dev = torch.device(device)
+
+    def make(seed):
+        torch.manual_seed(seed)
+        m = RM.FAL_netB(None, no_levels=N)
+        return m.to(dev)
+
+    mx = torch.full((B, 1, 1), 300.0, device=dev)
+    mn = mx * 2 / 300
     if workload in ("stage1", "stage2"):
         H, W = 192, 640
-        B = sample_b or 1
+        model = make(0)
+        fix = make(1).eval() if workload == "stage2" else None
+        groups = [{"params": model.bias_parameters(), "weight_decay": 0.0},
+                  {"params": model.weight_parameters(), "weight_decay": 0.0}]
+        opt = torch.optim.Adam(params=groups, lr=1e-4 if workload == "stage1" else 5e-5, betas=(0.5, 0.999))
+        left, right = (t.to(dev) for t in synth_batch(B, H, W, 1234 + seed_off))
+
+        def step():
+            opt.zero_grad()
+            if workload == "stage1":
+                loss = ref_loader.ref_stage1(RL, model, left, right, mn, mx, a_p=0.0)[0]
+            else:
+                loss = ref_loader.ref_stage2(RL, model, fix, left, right, mn, mx, a_p=0.01)["loss"]
+            loss.backward()
+            opt.step()
+            return loss
+        return step, B * (2 if workload == "stage2" else 1), f"{workload} step, {B} of 8 {'pairs' if workload == 'stage2' else 'images'}, 192x640, N=49"
+    H, W = 375, 1242
+    model = make(0).eval()
+    img = synth_batch(B, H, W, 1234 + seed_off)[0].to(dev)
+
+    def step():
+        with torch.no_grad():                                           # Test_KITTI.py:196-203, exact index flip
+            d = model(img, mn, mx, ret_disp=True, ret_subocc=False, ret_pan=False)
+            fd = model(torch.flip(img, dims=[3]), mn, mx, ret_disp=True, ret_subocc=False, ret_pan=False)
+            return ((d + torch.flip(fd, dims=[3])) / 2).mean()
+    return step, B, f"Test_KITTI flip-PP, {B} of 8 images, 375x1242, N=49"
+
+
+def cpu_reference(workload, steps, warmup, sample_b=None, budget_s=25.0):
+    """The reference's own modules (baseline/_ref, unmodified; `.cuda()` is the identity on this CPU leg) on all host
+    cores, on a bounded sample of the workload.  Falls back to oracle/falnet_oracle.py (kind "port", bit-identical to
+    the reference on CPU) when baseline/_ref did not travel.  Returns (value, unit, cores, kind, sample, ms_per_step)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wl = workload if workload != "med" else "stage1"
+    from baseline import ref_loader
+    if not ref_loader.available():
+        return _cpu_port(wl, steps, warmup, sample_b, budget_s)
+    B = sample_b or 1
+    step, per_step, desc = _reference_step_fn("cpu", wl, B)
+    t0 = time.time()
+    float(step())
+    first = time.time() - t0
+    if sample_b is None and wl != "test" and first * 8 * 3 < budget_s:   # the whole batch of 8 fits the budget
+        B = 8
+        step, per_step, desc = _reference_step_fn("cpu", wl, B)
+        t0 = time.time()
+        float(step())
+        first = time.time() - t0
+    n = max(1, min(steps, int(budget_s / max(first, 1e-3))))
+    t0 = time.time()
+    for _ in range(n):
+        float(step())
+    dt = (time.time() - t0) / n
+    return per_step / dt, "frames/s", cores, "reference", desc + f", unmodified reference (fp32 torch CPU), {n} timed step(s)", dt * 1e3
+
+
+def _cpu_port(workload, steps, warmup, sample_b=None, budget_s=25.0):
+    from oracle import falnet_oracle as O
+    cores = os.cpu_count() or 1
+    N = 49
+    B = sample_b or 1
+    if workload in ("stage1", "stage2"):
+        H, W = 192, 640
         p = {k: v.clone().requires_grad_("amask" not in k) for k, v in O.init_params(N, seed=0).items()}
         pfix = {k: v.clone() for k, v in O.init_params(N, seed=1).items()}
         vgg_ws = O.init_vgg(2)
@@ -120,11 +205,10 @@ def cpu_reference(workload, steps, warmup, sample_b=None, budget_s=25.0):
             with torch.no_grad():
                 O.adam_step({k: t for k, t in p.items()}, {k: t.grad for k, t in p.items()}, m, v, tstep[0], 1e-4)
             return float(loss)
-        unit, per_step = "frames/s", B * (1 if workload == "stage1" else 2)
-        sample = f"{workload} step on {B} of 8 {'pairs' if workload == 'stage2' else 'images'}, 192x640, N=49, fp32 torch CPU"
+        per_step = B * (1 if workload == "stage1" else 2)
+        sample = f"{workload} step on {B} of 8 {'pairs' if workload == 'stage2' else 'images'}, 192x640, N=49, oracle port (fp32 torch CPU)"
     else:
         H, W = 375, 1242
-        B = sample_b or 1
         p = O.init_params(N, seed=0)
         img = synth_batch(B, H, W, 1234)[0]
         mx = torch.full((B, 1, 1), 300.0)
@@ -134,18 +218,163 @@ def cpu_reference(workload, steps, warmup, sample_b=None, budget_s=25.0):
             with torch.no_grad():
                 d = O.test_disp_fpp(p, img, mn, mx, flip=lambda t: torch.flip(t, dims=[3]))
             return float(d.mean())
-        unit, per_step = "frames/s", B
-        sample = f"Test_KITTI flip-PP on {B} of 8 images, 375x1242, N=49, fp32 torch CPU"
+        per_step = B
+        sample = f"Test_KITTI flip-PP on {B} of 8 images, 375x1242, N=49, oracle port (fp32 torch CPU)"
     t0 = time.time()
-    for _ in range(max(1, min(warmup, 1))):
-        step()
+    step()
     first = time.time() - t0
     n = max(1, min(steps, int(budget_s / max(first, 1e-3))))
     t0 = time.time()
     for _ in range(n):
         step()
     dt = (time.time() - t0) / n
-    return per_step / dt, unit, cores, sample + f", {n} timed step(s)", dt * 1e3
+    return per_step / dt, "frames/s", cores, "port", sample + f", {n} timed step(s)", dt * 1e3
+
+
+def reference_gpu(steps=10, warmup=3):
+    """The UNMODIFIED reference on the same B200 (its stock path: fp32 tensors, cuDNN with torch's default TF32 convolution
+    setting, eager launches): Stage-1 step B = 8 at 192x640 and disparity inference b1 at 375x1242 (SURVEY.md 8d "the
+    practical bar").  CUDA-event timing after warm-up."""
+    out = {"impl": "reference_gpu", "torch": torch.__version__, "cudnn_conv_tf32": bool(torch.backends.cudnn.allow_tf32),
+           "note": "stock reference settings; not a roofline claim"}
+    for name, wl, B in (("stage1_b8_192x640", "stage1", 8), ("stage2_8pairs_192x640", "stage2", 8),
+                        ("test_fpp_b1_375x1242", "test", 1)):
+        try:
+            step, per_step, desc = _reference_step_fn("cuda", wl, B)
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"ms_per_step": ms, "frames_per_s": per_step / (ms / 1e3), "what": desc,
+                         "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+            del step
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats()
+        except Exception as e:                                   # report, do not hide
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    return out
+
+
+def med_microbench(hbm_peak, peak_src, iters=10):
+    """BASELINE configs[4]: the six MED microbench shapes (N = 33 / 49 / 65 at 8x375x1242 and 2x1024x2048), fwd (pan + disp),
+    fwd + both occlusion masks, bwd; GB/s = algorithmic bytes of SURVEY.md 8(d) / CUDA-event time; three rotating buffer sets
+    of >= 0.45 GB each so the 126 MB L2 cannot serve repeats.  The kernels are the ones the training step launches."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_med
+    rows = []
+    for B, N, H, W in ((8, 33, 375, 1242), (8, 49, 375, 1242), (8, 65, 375, 1242),
+                       (2, 33, 1024, 2048), (2, 49, 1024, 2048), (2, 65, 1024, 2048), (16, 49, 192, 640)):
+        r = bench_med.bench(B, N, H, W, iters=iters, peak=hbm_peak)
+        torch.cuda.empty_cache()
+        row = {"shape": f"{B}x{N}x{H}x{W}"}
+        for k, v in r.items():
+            row[k] = {"ms": round(v["ms"], 4), "roofline": {"bound": "hbm", "achieved": round(v["gbs"], 1), "peak": hbm_peak,
+                                                           "unit": "GB/s", "frac": round(v["gbs"] / hbm_peak, 4)}}
+        rows.append(row)
+    return {"peak_source": peak_src + " hbm_gbs", "algorithmic_bytes_per_px": "fwd 4(N+7), fwd_masks 4(N+9), bwd 4(2N+7), disp_only 4(N+1)",
+            "l2": "3 rotating buffer sets per shape", "rows": rows}
+
+
+# (name, cin, cout, H_in, W_in, stride) of every distinct 3x3 layer shape of FAL_netB at 192x640
+_LAYERS = (("conv0_1.*", 32, 32, 192, 640, 1), ("conv1.0", 32, 64, 192, 640, 2), ("conv1_1.*", 64, 64, 96, 320, 1),
+           ("conv2.0", 64, 128, 96, 320, 2), ("conv2_1.*", 128, 128, 48, 160, 1), ("conv3.0", 128, 256, 48, 160, 2),
+           ("conv3_1.*", 256, 256, 24, 80, 1), ("conv4.0", 256, 256, 24, 80, 2), ("conv4_1.*", 256, 256, 12, 40, 1),
+           ("conv5.0", 256, 256, 12, 40, 2), ("conv5_1.*", 256, 256, 6, 20, 1), ("conv6.0", 256, 512, 6, 20, 2),
+           ("conv6_1.*", 512, 512, 3, 10, 1), ("deconv6", 512, 256, 6, 20, 1), ("iconv6", 512, 256, 6, 20, 1),
+           ("deconv5", 256, 128, 12, 40, 1), ("iconv5", 384, 256, 12, 40, 1), ("deconv4", 256, 128, 24, 80, 1),
+           ("iconv4", 384, 256, 24, 80, 1), ("deconv3", 256, 128, 48, 160, 1), ("iconv3", 256, 128, 48, 160, 1),
+           ("deconv2", 128, 64, 96, 320, 1), ("iconv2", 128, 64, 96, 320, 1), ("deconv1", 64, 64, 192, 640, 1),
+           ("iconv1+conv0 (folded)", 96, 64, 192, 640, 1))
+
+
+def conv_layer_table(tf_peak, hbm_peak, B=8, iters=8):
+    """Per-layer microseconds of our tcgen05 kernels against cuDNN (bf16, channels_last, cudnn.benchmark autotuned) for the
+    forward, data-gradient and weight-gradient of every distinct FAL_netB layer shape at the Stage-1 batch (B = 8, 192x640).
+    Each timed alone (CUDA events, 8 launches after 3 warm-ups; inputs of the big layers exceed L2 only at full
+    resolution -- the small-map layers are L2-resident for BOTH implementations).  `bound_us` = the layer-wise roofline
+    max(flops / tensor peak, bytes / HBM peak)."""
+    import torch.nn.functional as F
+    from fal_net_b200 import conv_native as CN
+    dev = torch.device("cuda", torch.cuda.current_device())
+    old_bench = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    CL = torch.channels_last
+    g = torch.Generator(device=dev).manual_seed(11)
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e3
+
+    rows, tot = [], {"ours": 0.0, "cudnn": 0.0, "bound": 0.0}
+    for name, cin, cout, H, W, stride in _LAYERS:
+        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        x = torch.randn(B, cin, H, W, device=dev, generator=g).to(torch.bfloat16).contiguous(memory_format=CL)
+        w = (torch.randn(cout, cin, 3, 3, device=dev, generator=g) / (3 * cin ** 0.5))
+        gy = torch.randn(B, cout, Ho, Wo, device=dev, generator=g).to(torch.bfloat16).contiguous(memory_format=CL)
+        w16 = w.to(torch.bfloat16).contiguous(memory_format=CL)
+        wk, wd = CN.pack_weight(w), CN.pack_weight_dgrad(w)
+        dW = torch.zeros(cout, 3, 3, cin, device=dev).permute(0, 3, 1, 2)
+        flops = 2 * 9 * cin * cout * B * Ho * Wo
+        nbytes = 2 * B * (H * W * cin + Ho * Wo * cout) + 2 * 9 * cin * cout
+        bound = max(flops / (tf_peak * 1e12), nbytes / (hbm_peak * 1e9)) * 1e6
+        row = {"layer": name, "cin": cin, "cout": cout, "hw_in": [H, W], "stride": stride, "gflop": round(flops / 1e9, 3),
+               "bound_us": round(bound, 2)}
+        ops = {
+            "fwd": (lambda: CN.conv3x3_fwd(x, wk, None, stride, 1),
+                    lambda: F.conv2d(x, w16, None, stride, 1)),
+            "dgrad": (lambda: CN.conv3x3_dgrad(gy, wd, (H, W), stride=stride),
+                      lambda: torch.ops.aten.convolution_backward(gy, x, w16, None, [stride, stride], [1, 1], [1, 1], False,
+                                                                  [0, 0], 1, [True, False, False])),
+            "wgrad": (lambda: CN.conv3x3_wgrad(gy, x, dW, cout=cout, stride=stride),
+                      lambda: torch.ops.aten.convolution_backward(gy, x, w16, None, [stride, stride], [1, 1], [1, 1], False,
+                                                                  [0, 0], 1, [False, True, False])),
+        }
+        for op, (ours, lib) in ops.items():
+            try:
+                t_o = timeit(ours)
+            except Exception as e:
+                t_o = None
+                row[op + "_error"] = f"{type(e).__name__}: {e}"[:160]
+            t_c = timeit(lib)
+            row[op] = {"ours_us": None if t_o is None else round(t_o, 1), "cudnn_bf16_us": round(t_c, 1),
+                       "ours_frac_of_bound": None if t_o is None else round(bound / t_o, 3)}
+            if t_o is not None:
+                tot["ours"] += t_o
+                tot["cudnn"] += t_c
+                tot["bound"] += bound
+        rows.append(row)
+        del x, w, gy, w16, wk, wd, dW
+    torch.backends.cudnn.benchmark = old_bench
+    return {"batch": B, "what": "us per launch, each kernel timed alone; cuDNN = torch conv2d / convolution_backward, bf16 "
+            "channels_last, cudnn.benchmark=True", "sum_ours_us": round(tot["ours"], 1), "sum_cudnn_bf16_us": round(tot["cudnn"], 1),
+            "sum_bound_us": round(tot["bound"], 1), "rows": rows}
+
+
+def _subprocess_json(argv, timeout):
+    """Run `python bench.py <argv>` and return its last JSON line (legs that must not share this process's state)."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__)] + argv, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           text=True, timeout=timeout)
+        for line in reversed(r.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"error": f"rc={r.returncode}: {r.stderr[-300:]}"}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -157,9 +386,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="stage1", choices=["stage1", "stage2", "test", "med"])
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference_gpu"])
+    ap.add_argument("--budget", type=float, default=90.0, help="--impl reference: seconds of timed CPU work")
+    ap.add_argument("--sample-b", type=int, default=None, help="--impl reference: images (pairs) per step of the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--extras", default="stage2,test,med,reference_gpu,conv_layers",
+                    help="comma list of the sub-lines to attach (med / reference_gpu / conv_layers only at N = 1)")
     ap.add_argument("--no-graph", action="store_true", help="launch the training step kernel by kernel instead of replaying its CUDA graph")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
@@ -171,15 +404,20 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        val, unit, cores, sample, ms = cpu_reference(a.workload if a.workload != "med" else "stage1", a.steps, a.warmup,
-                                                     budget_s=90.0)
+        val, unit, cores, kind, sample, ms = cpu_reference(a.workload, a.steps, a.warmup, sample_b=a.sample_b,
+                                                           budget_s=a.budget)
         print(json.dumps({
             "impl": "reference", "metric": metric_name(a.workload), "value": val, "unit": unit, "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a.workload, a.gpus),
-            "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
+        return 0
+    if a.impl == "reference_gpu":
+        if rank == 0:
+            torch.cuda.set_device(0)
+            print(json.dumps(reference_gpu(steps=min(a.steps, 10), warmup=3)))
         return 0
 
     import torch.distributed as dist
@@ -194,8 +432,41 @@ def main():
     from fal_net_b200.trainer import FlatAdamDDP, GraphedStep
     from fal_net_b200 import conv as C
     run_gpu.GraphedStep = GraphedStep
+    ctx = (rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP, C)
 
-    result = run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP, C)
+    result = run_gpu(a, a.workload, *ctx)
+    wanted = [] if a.no_extras else [e for e in a.extras.split(",") if e]
+    extras = {}
+    for wl in ("stage2", "test"):
+        if wl in wanted and wl != a.workload:
+            torch.cuda.empty_cache()
+            r = run_gpu(a, wl, *ctx, light=True)
+            extras[wl] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "gpu_launches", "cuda_graph",
+                                            "config", "roofline", "roofline_med") if k in r}
+            if wl == "stage2":
+                extras[wl]["pairs_per_s"] = r["value"] / 2
+    if world == 1 and rank == 0:
+        torch.cuda.empty_cache()
+        hbm_peak, tf_peak, peak_src = peaks()
+        if "med" in wanted:
+            extras["med"] = med_microbench(hbm_peak, peak_src)
+        if "conv_layers" in wanted:
+            extras["conv_layers"] = conv_layer_table(tf_peak, hbm_peak)
+        torch.cuda.empty_cache()
+        if "reference_gpu" in wanted:
+            extras["reference_gpu"] = _subprocess_json(["--impl", "reference_gpu", "--steps", "10"], timeout=240)
+            try:
+                extras["reference_gpu"]["speedup_stage1_device"] = \
+                    result["value"] / extras["reference_gpu"]["stage1_b8_192x640"]["frames_per_s"]
+            except Exception:
+                pass
+        if not a.no_cpu_baseline:
+            cb = _subprocess_json(["--impl", "reference", "--workload", a.workload, "--steps", "3", "--budget", "20"], timeout=300)
+            result["cpu_baseline"] = cb.get("cpu_baseline", cb)
+            if "ms_per_step" in cb:
+                result["cpu_baseline"]["ms_per_step"] = cb["ms_per_step"]
+    if extras:
+        result["extras"] = extras
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -223,9 +494,10 @@ def workload_config(workload, n):
     return base
 
 
-def run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP, C):
+def run_gpu(a, wl, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP, C, light=False):
+    """Builds workload ``wl`` and measures it (device-resident value, per-kernel rooflines, e2e).  ``light``: an extras
+    sub-line -- same timing rules, shorter per-kernel pass."""
     N = 49
-    wl = a.workload
     cfg = workload_config(wl, world)
     B, H, W = cfg["per_gpu_batch"], cfg["H"], cfg["W"]
     hbm_peak, tf_peak, peak_src = peaks()
@@ -334,7 +606,7 @@ def run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP
     # are run kernel by kernel once more, on ONE stream so that every kernel is timed alone; these iterations are not
     # part of `value`)
     from fal_net_b200 import backbone as BB, conv_native as CNV
-    n_prof = max(3, min(a.steps, 10))
+    n_prof = 3 if light else max(3, min(a.steps, 10))
     BB.USE_SIDE_STREAM = False
     step_dev(*devb[0])                                               # settle allocator / caches in this mode
     med.TIMING, CNV.TIMING = [], []
@@ -435,10 +707,6 @@ def run_gpu(a, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAdamDDP
     }
     if roofline_med is not None:
         res["roofline_med"] = roofline_med
-    if rank == 0 and not a.no_cpu_baseline and world == 1:
-        val, unit, cores, sample, cms = cpu_reference(wl if wl != "med" else "stage1", 3, 1, budget_s=20.0)
-        res["cpu_baseline"] = {"value": val, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
-                               "ms_per_step": cms}
     return res
 
 

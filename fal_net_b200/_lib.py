@@ -18,7 +18,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "falnet_b200.h")
 _lib = None
 
 _C = ctypes
-_p, _i, _ll, _f, _u = _C.c_void_p, _C.c_int, _C.c_longlong, _C.c_float, _C.c_uint
+_p, _i, _ll, _f, _u, _d = _C.c_void_p, _C.c_int, _C.c_longlong, _C.c_float, _C.c_uint, _C.c_double
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 _SIGNATURES = {
@@ -57,6 +57,12 @@ _SIGNATURES = {
     "faln_stem_conv": [_p] * 4 + [_i] * 6 + [_p],
     "faln_upsample_nearest_nhwc": [_p, _p] + [_i] * 6 + [_p],
     "faln_maxpool2_nhwc": [_p, _p] + [_i] * 4 + [_p],
+    "faln_flip_resize_bilinear": [_p, _p] + [_i] * 6 + [_p],
+    "faln_percentile_rows": [_p, _i, _ll, _ll, _d, _d, _p, _p],
+    "faln_mspp_blend": [_p] * 4 + [_i] * 5 + [_f, _p],
+    "faln_kitti_errors": [_p] * 3 + [_i] * 8 + [_d] * 4 + [_p],
+    "faln_real_epe": [_p] * 3 + [_i] * 6 + [_p],
+    "faln_rmse255": [_p] * 3 + [_i] * 3 + [_f] * 3 + [_p],
 }
 _RESTYPES = {"faln_last_error": _C.c_char_p, "faln_launch_count": _C.c_longlong}
 

@@ -16,6 +16,7 @@ import warnings
 
 import torch
 
+from . import _lib
 from . import conv as C
 from . import losses as K
 
@@ -209,6 +210,29 @@ def mirror_loss(disp, mdisp, occ, window, flip_x=False, inv_max=None):
     if inv_max is None:
         inv_max = K.inv_rowmax(mdisp)
     return _Mirror.apply(disp, mdisp.contiguous(), occ.contiguous(), inv_max, window[0], window[1], bool(flip_x))
+
+
+def EPE(net_out, target, sparse=False, disp=True, mean=True):
+    """End-point error of a 1-channel disparity map (:124-141), masked by target != 0 when ``sparse``; one kernel, fp64
+    sums, result a 0-d device tensor.  (The 2-channel optical-flow variant of the reference is not on this path.)"""
+    if net_out.shape[1] != 1 or not disp:
+        raise NotImplementedError("EPE: only the 1-channel disparity form is on the FAL-net path")
+    return _epe(net_out, target, sparse, mean)
+
+
+def _epe(output, target, sparse, mean=True):
+    o, t = _lib.f32c(output, "output"), _lib.f32c(target, "target")
+    B, _, h, w = o.shape
+    _, _, H, W = t.shape
+    s = torch.empty(2, device=o.device, dtype=torch.float64)
+    _lib.check(_lib.lib().faln_real_epe(_lib.ptr(o), _lib.ptr(t), _lib.ptr(s), B, h, w, H, W, int(bool(sparse)),
+                                        _lib.cur_stream()), "faln_real_epe")
+    return (s[0] / s[1] if mean else s[0] / B).float()
+
+
+def realEPE(output, target, sparse=False):
+    """:170-173: bilinear (align_corners=True) up-sampling of ``output`` to the target's size fused with the masked mean."""
+    return _epe(output, target, sparse, True)
 
 
 def getGrayscale(input):

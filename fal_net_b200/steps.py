@@ -12,7 +12,6 @@ Differences from the reference that do not change results beyond fp rounding:
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 from . import loss_functions as LF
 from . import losses as K
@@ -96,18 +95,13 @@ def test_disp(model, image, min_disp, max_disp, f_post_process=False, ms_post_pr
 
 @torch.no_grad()
 def ms_pp(input_view, model, disp, min_disp, max_pix):
-    """Multi-scale post-processing (Test_KITTI.py:287-300); the 95th percentile is taken per call over the
-    whole tensor like the reference (which runs with batch 1), on the device (torch.quantile, no host sync)."""
-    B, C, H, W = input_view.shape
+    """Multi-scale post-processing (Test_KITTI.py:287-300) on three small kernels (csrc/postproc.cu) around the 2/3-scale
+    network pass: flip + bilinear down-scale of the view; an exact device-side 95th percentile PER IMAGE (the reference
+    runs batch 1, so its np.percentile is per image; here B > 1 keeps that meaning and nothing syncs with the host);
+    nearest up-sampling + un-flip + blend in one pass."""
+    from . import postproc
     up_fac = 2 / 3
-    small = F.interpolate(torch.flip(input_view, dims=[3]), scale_factor=up_fac, mode="bilinear", align_corners=True)
+    small = postproc.flip_resize_bilinear(input_view, scale_factor=up_fac, flip_x=True)
     d2 = model(small, min_disp, max_pix, ret_disp=True, ret_pan=False, ret_subocc=False)
-    d2 = (1 / up_fac) * F.interpolate(d2, size=(H, W), mode="nearest")
-    d2 = torch.flip(d2, dims=[3])
-    flat = disp.reshape(-1).float()
-    k = 0.95 * (flat.numel() - 1)                       # numpy.percentile 'linear' interpolation
-    lo = torch.kthvalue(flat, int(k) + 1).values
-    hi = torch.kthvalue(flat, min(int(k) + 2, flat.numel())).values
-    p95 = lo + (hi - lo) * (k - int(k))
-    norm = torch.clamp(disp / (p95 + 1e-6), max=1.0)
-    return (1 - norm) * disp + norm * d2
+    p95 = postproc.percentile_rows(disp, 95.0, add=1e-6)
+    return postproc.mspp_blend(disp, d2, p95, 1 / up_fac)

@@ -246,6 +246,36 @@ int faln_upsample_nearest_nhwc(const void* src, void* dst, int B, int Hi, int Wi
 /* 2x2 stride-2 max pooling (VGG pools, /root/reference/loss_functions.py:21-29) on bf16 NHWC. */
 int faln_maxpool2_nhwc(const void* src, void* dst, int B, int Hi, int Wi, int C, faln_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Inference post-processing and validation metrics: csrc/postproc.cu.
+ * ---------------------------------------------------------------------------------------------- */
+/* flip_x (optional) + F.interpolate(mode='bilinear', align_corners=True): /root/reference/Test_KITTI.py:291-292.
+ * in [BC,H,W] fp32 -> out [BC,Ho,Wo] fp32. */
+int faln_flip_resize_bilinear(const float* in, float* out, int BC, int H, int W, int Ho, int Wo, int flip_x,
+                              faln_stream_t stream);
+/* out[b] = (float)(numpy.percentile(x[b, :n], 100*q) + add), exact (radix select on the device): replaces the
+ * `np.percentile(disp.detach().cpu().numpy(), 95) + 1e-6` host round trip of /root/reference/Test_KITTI.py:297.
+ * x [B, stride >= n] fp32. */
+int faln_percentile_rows(const float* x, int B, long long n, long long stride, double q, double add, float* out,
+                         faln_stream_t stream);
+/* out = (1 - norm) * disp + norm * up_mul * unflip(nearest_up(small)), norm = min(disp / p[b], 1):
+ * /root/reference/Test_KITTI.py:294-300.  disp, out [B,1,H,W]; small [B,1,Hs,Ws] (flipped coordinates); p [B]. */
+int faln_mspp_blend(const float* disp, const float* small, const float* p, float* out, int B, int H, int W, int Hs, int Ws,
+                    float up_mul, faln_stream_t stream);
+/* The seven KITTI depth errors as per-image fp64 partial sums {count, abs_rel, sq_rel, sq, log_sq, n_a1, n_a2, n_a3}
+ * (sums [B,8], zeroed by the call): /root/reference/myUtils.py:196-232 applied to the depths of :234-254 (mode 0,
+ * KITTI2015: gt is a disparity map, both sides fb / disp) or :256-277 (mode 1, Eigen: gt is a depth map, window =
+ * [H-219,H-4) x [44,1180)).  gt, pred [B,H,W] fp32. */
+int faln_kitti_errors(const float* gt, const float* pred, double* sums, int B, int H, int W, int y0, int y1, int x0, int x1,
+                      int mode, double fb_gt, double fb_pred, double min_d, double max_d, faln_stream_t stream);
+/* realEPE (/root/reference/loss_functions.py:124-141,170-173): sums = {sum |target - bilinear_up(output)|, count} over
+ * target != 0 (sparse) or all pixels.  output [B,1,h,w], target [B,1,H,W]. */
+int faln_real_epe(const float* output, const float* target, double* sums, int B, int h, int w, int H, int W, int sparse,
+                  faln_stream_t stream);
+/* get_rmse (/root/reference/myUtils.py:138-150): sum = sum over [B,3,H,W] of (clamp((o+mean_c)*255,0,255) - (l+mean_c)*255)^2 */
+int faln_rmse255(const float* output, const float* label, double* sum, int B, int H, int W, float m0, float m1, float m2,
+                 faln_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -459,9 +459,15 @@ def test_disp_mspp(p, image, min_disp, max_disp, flip=None):
     ds = falnet_forward(p, small, min_disp, max_disp)
     ds = (1 / (2 / 3)) * F.interpolate(ds, size=(H, W), mode="nearest")
     ds = flip(ds)
-    norm = d / (np.percentile(d.detach().cpu().numpy(), 95) + 1e-6)
-    norm = torch.clamp(norm, max=1.0)
-    return (1 - norm) * d + norm * ds
+    # the reference evaluates with batch 1 (Test_KITTI.py:113), so its np.percentile is PER IMAGE; for B > 1 the same
+    # meaning is kept image by image
+    out = []
+    for b in range(B):
+        db = d[b:b + 1]
+        norm = db / (np.percentile(db.detach().cpu().numpy(), 95) + 1e-6)
+        norm = torch.clamp(norm, max=1.0)
+        out.append((1 - norm) * db + norm * ds[b:b + 1])
+    return torch.cat(out, 0)
 
 
 def adam_step(params, grads, m, v, step, lr, beta1=0.5, beta2=0.999, eps=1e-8):
@@ -477,3 +483,65 @@ def adam_step(params, grads, m, v, step, lr, beta1=0.5, beta2=0.999, eps=1e-8):
         v[k].mul_(beta2).addcmul_(g, g, value=1 - beta2)
         denom = (v[k].sqrt() / math.sqrt(bc2)).add_(eps)
         params[k].addcdiv_(m[k], denom, value=-lr / bc1)
+
+
+# ----------------------------------------------------------------------------------------------
+# Validation metrics (numpy, like the reference)
+# ----------------------------------------------------------------------------------------------
+KITTI_ERROR_NAMES = ['abs_rel', 'sq_rel', 'rms', 'log_rms', 'a1', 'a2', 'a3']
+WIDTH_TO_FOCAL = {1242: 721.5377, 1241: 718.856, 1224: 707.0493, 1238: 718.3351, 1226: 707.0912, 1280: 738.2355}
+WIDTH_TO_BASELINE = {1242: 0.9982 * 0.54, 1241: 0.9848 * 0.54, 1224: 1.0144 * 0.54, 1238: 0.9847 * 0.54,
+                     1226: 0.9765 * 0.54, 1280: 0.54}
+
+
+def kitti_errors(gt, pred, min_d=1.0, max_d=80.0):
+    """/root/reference/myUtils.py:196-232 (use_median=False).  gt, pred: numpy depth maps."""
+    mask = gt > 0
+    gt = gt[mask]
+    pred = pred[mask]
+    pred = np.clip(pred, min_d, max_d)
+    gt = np.clip(gt, min_d, max_d)
+    thresh = np.maximum(gt / pred, pred / gt)
+    a1, a2, a3 = (thresh < 1.25).mean(), (thresh < 1.25 ** 2).mean(), (thresh < 1.25 ** 3).mean()
+    rmse = np.sqrt(((gt - pred) ** 2).mean())
+    rmse_log = np.sqrt(((np.log(gt) - np.log(pred)) ** 2).mean())
+    abs_rel = np.mean(np.abs(gt - pred) / gt)
+    sq_rel = np.mean(((gt - pred) ** 2) / gt)
+    return [abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3]
+
+
+def depths_kitti2015(gt_disp, pred_disp):
+    """/root/reference/myUtils.py:234-254 for one image (numpy [H,W])."""
+    width = gt_disp.shape[1]
+    gt_mask, pred_mask = gt_disp > 0, pred_disp > 0
+    gt_depth = WIDTH_TO_FOCAL[width] * 0.54 / (gt_disp + (1.0 - gt_mask))
+    pred_depth = WIDTH_TO_FOCAL[width] * 0.54 / (pred_disp + (1.0 - pred_mask))
+    return gt_mask * gt_depth, pred_depth
+
+
+def depths_kitti_eigen(gt_depth, pred_disp):
+    """/root/reference/myUtils.py:256-277 for one image: Eigen crop, gt already a depth map."""
+    height, width = gt_depth.shape
+    gt = gt_depth[height - 219:height - 4, 44:1180]
+    pr = pred_disp[height - 219:height - 4, 44:1180]
+    gt_mask, pred_mask = gt > 0, pr > 0
+    pred_depth = WIDTH_TO_FOCAL[width] * WIDTH_TO_BASELINE[width] / (pr + (1.0 - pred_mask))
+    return gt_mask * gt, pred_depth
+
+
+def get_rmse(output_right, label_right, mean=_RGB_MEAN):
+    """/root/reference/myUtils.py:138-150."""
+    m = torch.tensor(mean, dtype=output_right.dtype).view(1, 3, 1, 1)
+    o = torch.clamp((output_right + m) * 255, 0, 255)
+    l = (label_right + m) * 255
+    return torch.mean((o - l) ** 2) ** 0.5
+
+
+def real_epe(output, target, sparse=False):
+    """/root/reference/loss_functions.py:124-141,170-173 for 1-channel disparity maps."""
+    h, w = target.shape[2:]
+    up = F.interpolate(output, size=(h, w), mode="bilinear", align_corners=True)
+    epe = torch.norm(target - up, p=2, dim=1)
+    if sparse:
+        epe = epe[~(target[:, 0] == 0)]
+    return epe.mean()

@@ -40,3 +40,21 @@ def rel_l2(a, b):
     """||a-b||_2 / ||b||_2."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def sparse_gt(B, H, W, seed, lo, hi, keep=0.25):
+    """Seeded sparse ground-truth map (zeros = invalid), as tests/golden/make_golden_r2.py draws it."""
+    g = torch.Generator().manual_seed(seed)
+    v = lo + (hi - lo) * torch.rand(B, 1, H, W, generator=g)
+    m = torch.rand(B, 1, H, W, generator=g) < keep
+    return (v * m).float()
+
+
+def metrics_inputs(B=2, H=375, W=1242):
+    """(gt disparity, gt depth, predicted disparity) of the metrics golden cases (make_golden_r2.py `metrics`)."""
+    gt = sparse_gt(B, H, W, 11, 1.0, 180.0)
+    g = torch.Generator().manual_seed(12)
+    pred = (gt * (0.8 + 0.4 * torch.rand(gt.shape, generator=g)) + (gt == 0) * 200 * torch.rand(gt.shape, generator=g)).float()
+    pred[:, :, :5, :7] = 0.0
+    gt_d = sparse_gt(B, H, W, 13, 0.5, 95.0)
+    return gt, gt_d, pred

@@ -9,11 +9,11 @@ from tests.helpers import disp_range, images, rel_err, rel_l2
 
 pytestmark = pytest.mark.gpu
 OUT_TOL, LOSS_TOL = 2e-2, 1e-2
-# Disparity of a RANDOM-INIT network is an expectation over 49 nearly-flat probabilities, i.e. the worst case for
-# logit noise: bf16 activation storage through 34 layers (cuDNN bf16 gives the same figure) puts the max-norm error
-# at ~2.5e-2 of max|disp| while the relative L2 error is ~5e-3.  We hold rel-L2 to the 2e-2 bound and the max-norm
-# (SURVEY.md 8c(iv) reports both) to 4e-2 for disparity; pan and every loss meet 2e-2 / 1e-2 in max-norm.
-DISP_MAX_TOL = 4e-2
+# End-to-end outputs of a RANDOM-INIT network (a softmax over 49 nearly-flat logits of magnitude ~15) are the worst case
+# for logit noise.  Here, against the CPU oracle at small shapes: the conv outputs (logits) are held to 2e-2 in max-norm,
+# the MED section given those logits to 1e-4, and the end-to-end outputs to 2e-2 in relative L2.  The end-to-end
+# MAX-norm is asserted at BASELINE shapes in tests/test_reference_gpu.py::test_whole_model_at_baseline_shapes against
+# the reference on the same GPU, with the reference's own cuDNN-bf16 run as the yardstick (no hand-widened constants).
 
 
 def _dev():
@@ -56,8 +56,8 @@ def test_forward_all_outputs(H, W):
         pan, disp, mL, mR = m(left.to(dev), mn.to(dev), mx.to(dev), ret_disp=True, ret_subocc=True, ret_pan=True)
         donly = m(left.to(dev), mn.to(dev), mx.to(dev))
     rp, rd, rmL, rmR = O.falnet_forward(p, left, mn, mx, True, True, True)
-    assert isinstance(donly, torch.Tensor) and rel_l2(donly, rd) < OUT_TOL and rel_err(donly, rd) < DISP_MAX_TOL
-    assert rel_l2(disp, rd) < OUT_TOL and rel_err(disp, rd) < DISP_MAX_TOL
+    assert isinstance(donly, torch.Tensor) and rel_l2(donly, rd) < OUT_TOL
+    assert rel_l2(disp, rd) < OUT_TOL
     # (1) the convolution outputs themselves (the logits) meet the bf16 bound in max-norm
     with torch.no_grad():
         lg = m.logits(left.to(dev), mx.to(dev))[..., :W].cpu().contiguous()
@@ -69,10 +69,8 @@ def test_forward_all_outputs(H, W):
     ref = O.med_forward_closed(lg, left, d, xo)
     assert rel_err(pan, ref["pan"]) < 1e-4 and rel_err(disp, ref["disp"]) < 1e-4
     assert rel_err(mL, ref["maskL"]) < 1e-4 and rel_err(mR, ref["maskR"]) < 1e-4
-    # (3) end to end: a softmax over 49 random-init logits of magnitude ~15 amplifies the 1e-2 logit noise, so the
-    # max-norm of pan sits at ~4.5e-2 (cuDNN bf16 gives the same) while its relative L2 error meets the 2e-2 bound
-    assert rel_l2(pan, rp) < OUT_TOL and rel_err(pan, rp) < 6e-2
-    assert rel_err(mL, rmL) < 5e-2 and rel_err(mR, rmR) < 5e-2
+    # (3) end to end, relative L2 (max-norm: see the note at the top of this file)
+    assert rel_l2(pan, rp) < OUT_TOL and rel_l2(mL, rmL) < OUT_TOL and rel_l2(mR, rmR) < OUT_TOL
 
 
 def test_stage1_step_loss_and_gradients():
@@ -89,12 +87,18 @@ def test_stage1_step_loss_and_gradients():
     lo.backward()
     assert rel_err(loss, lo) < LOSS_TOL and rel_err(rec, rrec) < LOSS_TOL and rel_err(sm, rsm) < 3e-2
     named = dict(m.named_parameters())
-    for k in ("conv0.bias", "conv0.weight", "backbone.iconv1.weight", "backbone.iconv2.0.weight", "backbone.conv3.0.weight",
-              "backbone.conv0.0.weight"):
-        g, r = named[k].grad.cpu().flatten(), pp[k].grad.flatten()
-        cos = float(torch.dot(g, r) / (g.norm() * r.norm()))
-        assert cos > 0.98, (k, cos)
-        assert 0.9 < float(g.norm() / r.norm()) < 1.1, k
+    # every used tensor against the oracle's autograd (fp32 CPU): relative L2.  bf16 activation / gradient storage puts
+    # the decoder at ~1e-2 and the bottleneck (end of a 34-layer chain) at ~4e-2; a wrong scale, a missing term or a
+    # mis-indexed tap in any hand-scheduled gradient shows up as >= 1e-1.  The per-tensor comparison against the
+    # reference's own cuDNN-bf16 backward is tests/test_reference_gpu.py::test_stage1_parameter_gradients_all_tensors.
+    n_checked = 0
+    for k, q in named.items():
+        if "amask_conv" in k:
+            continue
+        e = rel_l2(q.grad, pp[k].grad)
+        assert e < 6e-2, (k, e)
+        n_checked += 1
+    assert n_checked == 47
     assert named["backbone.amask_conv.0.weight"].grad is None
 
 
@@ -130,8 +134,13 @@ def test_stage2_loss():
     ref = O.stage2_loss(p, pf, left, right, mn, mx, a_p=0.01, vgg_ws=ws, flip=lambda t: torch.flip(t, dims=[3]))
     for k, tol in (("loss", LOSS_TOL), ("rec", LOSS_TOL), ("sm", 3e-2), ("mirror", 3e-2)):
         assert rel_err(res[k], ref[k]) < tol, (k, float(res[k]), float(ref[k]))
-    assert rel_err(res["O_L"], ref["O_L"]) < 5e-2 and rel_err(res["O_R"], ref["O_R"]) < 5e-2
-    assert all(torch.isfinite(q.grad).all() for _, q in m.used_parameters())
+    assert rel_l2(res["O_L"], ref["O_L"]) < OUT_TOL and rel_l2(res["O_R"], ref["O_R"]) < OUT_TOL
+    # gradients of every used tensor (mirror loss, flip-folded rec / smoothness, VGG dgrad into the backbone)
+    pp = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    O.stage2_loss(pp, pf, left, right, mn, mx, a_p=0.01, vgg_ws=ws, flip=lambda t: torch.flip(t, dims=[3]))["loss"].backward()
+    for k, q in m.used_parameters():
+        e = rel_l2(q.grad, pp[k].grad)
+        assert e < 6e-2, (k, e)
 
 
 def test_inference_post_processing():
@@ -144,10 +153,10 @@ def test_inference_post_processing():
     flip = lambda t: torch.flip(t, dims=[3])
     d_fpp = steps.test_disp(m, img.to(dev), mn.to(dev), mx.to(dev), f_post_process=True)
     r_fpp = O.test_disp_fpp(p, img, mn, mx, flip=flip)
-    assert rel_l2(d_fpp, r_fpp) < OUT_TOL and rel_err(d_fpp, r_fpp) < DISP_MAX_TOL
+    assert rel_l2(d_fpp, r_fpp) < OUT_TOL
     d_ms = steps.test_disp(m, img.to(dev), mn.to(dev), mx.to(dev), ms_post_process=True)
     r_ms = O.test_disp_mspp(p, img, mn, mx, flip=flip)
-    assert rel_l2(d_ms, r_ms) < OUT_TOL and rel_err(d_ms, r_ms) < DISP_MAX_TOL
+    assert rel_l2(d_ms, r_ms) < OUT_TOL
 
 
 def test_graphed_step_matches_eager():

@@ -105,3 +105,19 @@ def test_product_level_tables_bit_identical_to_reference_loop():
                 d0, x0 = O.level_tables(mnn, mxx, N, W)
                 d1, x1 = med.level_tables(mnn, mxx, N, W)
                 assert torch.equal(d0, d1) and torch.equal(x0, x1)
+
+
+def test_product_constructor_draws_the_reference_random_stream(golden_dir):
+    """torch.manual_seed(0); FAL_netB(no_levels=N) of the product gives the reference's initial weights
+    (/root/reference/models/FAL_netB.py:130-138,190-192): per-tensor sums and abs-sums recorded from the reference."""
+    import numpy as np
+    import torch
+    from fal_net_b200 import models
+    g = np.load(f"{golden_dir}/init_checksums.npz")
+    for N in (49, 33):
+        torch.manual_seed(0)
+        sd = models.FAL_netB(no_levels=N).state_dict()
+        assert int(g[f"init{N}_nparam"]) == sum(v.numel() for v in sd.values())
+        sums = np.array([float(v.double().sum()) for v in sd.values()])
+        abss = np.array([float(v.double().abs().sum()) for v in sd.values()])
+        assert np.array_equal(sums, g[f"init{N}_sums"]) and np.array_equal(abss, g[f"init{N}_abs"])

@@ -1,0 +1,262 @@
+"""GPU: the product against the UNMODIFIED reference executed on the same B200 (baseline/_ref, cuDNN fp32 'ieee').
+
+VERDICT r1 "next #1": (a) MED with the product's own device-built level tables <= 1e-4 against
+/root/reference/models/FAL_netB.py:200-297 run on CUDA, at BASELINE shapes; (b) the whole model at 8x192x640 and
+1x375x1242, with the reference under bf16 autocast (cuDNN bf16) as the yardstick for what bf16 activation storage
+costs; (c) Stage-1 and Stage-2 parameter gradients, every used tensor, against reference autograd.
+
+Every test appends its measured errors to gpurun_out/parity_r2.jsonl (when that directory exists) so the table in
+DESIGN.md is a copy of what ran.
+"""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn as nn
+
+from baseline import ref_loader
+from tests.helpers import disp_range, images, rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _log(rec):
+    d = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_r2.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not ref_loader.available():
+        pytest.skip("baseline/_ref not installed (tools/install_reference.py needs /root/reference)")
+    assert torch.cuda.is_available()
+    torch.backends.cudnn.allow_tf32 = False                     # fp32 mode = IEEE convolutions
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.backends.cudnn.conv.fp32_precision = "ieee"
+    except Exception:
+        pass
+    return ref_loader.load()
+
+
+class _Bf16Backbone:
+    """Yardstick: the reference with ONLY its encoder-decoder under torch.autocast(bf16) -- cuDNN bf16 convolutions with
+    bf16 activation storage, the logit 1x1 conv and everything after it in fp32.  (Autocasting the whole forward also
+    rounds the 49 logits to bf16, which ruins the synthesis: recorded as ``cudnn_bf16_all`` for information only.)
+    Patches the INSTANCE's backbone.forward; the reference source is untouched."""
+
+    def __init__(self, rm):
+        self.rm = rm
+
+    def __enter__(self):
+        orig = self.rm.backbone.forward
+
+        def fwd(*a, **k):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = orig(*a, **k)
+            return out.float()
+        self.rm.backbone.forward = fwd
+
+    def __exit__(self, *exc):
+        del self.rm.backbone.forward
+
+
+class _Const(nn.Module):
+    def __init__(self, t):
+        super().__init__()
+        self.t = t
+
+    def forward(self, *a):
+        return self.t
+
+
+# ------------------------------------------------------------------------------------------------------ (a) MED
+@pytest.mark.parametrize("B,N,H,W,planar", [(8, 49, 192, 640, True), (1, 49, 375, 1242, True), (2, 33, 64, 322, False),
+                                            (1, 65, 48, 2048, True)])
+def test_med_device_tables_vs_reference_on_cuda(ref, B, N, H, W, planar):
+    """Identical logits on both sides; the product builds its level tables on the device (CUDA libm), the reference
+    runs its own grid_sample path on the same device.  Bound: 1e-4 max-abs/max-abs on pan, disp, both masks and the
+    logit gradient (north_star, fp32 mode)."""
+    from fal_net_b200 import layout, med
+    ref_models, _ = ref
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(B * 1000 + N * 10 + W)
+    vals = 2 * torch.randn(B, N, H, W, generator=gen, device=dev)
+    img = images(B, H, W, 1234 + W).to(dev)
+    gp = torch.randn(B, 3, H, W, generator=gen, device=dev)
+    gd = torch.randn(B, 1, H, W, generator=gen, device=dev)
+    mn, mx = (t.to(dev) for t in disp_range(B))
+
+    rl = vals.clone().requires_grad_(True)
+    torch.manual_seed(0)
+    m = ref_models.FAL_netB(no_levels=N).cuda()
+    m.backbone = _Const(rl)
+    m.conv0 = nn.Identity()
+    rp, rd, rmL, rmR = m(img, mn, mx, ret_disp=True, ret_subocc=True, ret_pan=True)
+    (rg,) = torch.autograd.grad((rp * gp).sum() + (rd * gd).sum(), rl)
+
+    if planar:                                   # the layout the product's last conv writes: third-generation kernels
+        ol = layout.alloc_planar(B, N, H, W, dev)
+        ol.copy_(vals)
+    else:
+        ol = vals.clone()
+    ol.requires_grad_(True)
+    pan, disp, mL, mR = med.med_section(ol, img, mn, mx, ret_disp=True, ret_subocc=True, ret_pan=True, zero_pad=planar)
+    (og,) = torch.autograd.grad((pan * gp).sum() + (disp * gd).sum(), ol)
+    errs = {"pan": rel_err(pan, rp), "disp": rel_err(disp, rd), "maskL": rel_err(mL, rmL), "maskR": rel_err(mR, rmR),
+            "g_logits": rel_err(og[..., :W], rg)}
+    _log({"test": "med_device_tables_vs_reference_cuda", "shape": [B, N, H, W], "errs": errs})
+    assert all(v < 1e-4 for v in errs.values()), errs
+
+
+# ------------------------------------------------------------------------------------------------ (b) whole model
+def _pair(ref_models, seed=0, N=49):
+    from fal_net_b200 import models
+    torch.manual_seed(seed)
+    rm = ref_models.FAL_netB(no_levels=N).cuda()
+    om = models.FAL_netB({"state_dict": rm.state_dict()}, no_levels=N).cuda()
+    return rm, om
+
+
+@pytest.mark.parametrize("B,H,W", [(8, 192, 640), (1, 375, 1242)])
+def test_whole_model_at_baseline_shapes(ref, B, H, W):
+    """All four outputs of FAL_netB.forward at BASELINE configs[1] / configs[0] shapes.  Bound per output, for both the
+    max-norm and the relative L2 error: 2e-2 (north_star), or -- where bf16 activation storage through 34 layers makes
+    that unreachable for ANY bf16 implementation (a softmax over 49 random-init logits of magnitude ~15 amplifies the
+    logit noise) -- no worse than 1.2x what the reference itself shows on the same GPU when cuDNN runs its
+    encoder-decoder in bf16 (``_Bf16Backbone``), measured in the same test."""
+    ref_models, _ = ref
+    dev = torch.device("cuda:0")
+    rm, om = _pair(ref_models)
+    left = images(B, H, W, 1234).to(dev)
+    mn, mx = (t.to(dev) for t in disp_range(B))
+    names = ("pan", "disp", "maskL", "maskR")
+    with torch.no_grad():
+        r32 = rm(left, mn, mx, ret_disp=True, ret_subocc=True, ret_pan=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            rall = rm(left, mn, mx, ret_disp=True, ret_subocc=True, ret_pan=True)
+        with _Bf16Backbone(rm):
+            r16 = rm(left, mn, mx, ret_disp=True, ret_subocc=True, ret_pan=True)
+        ours = om(left, mn, mx, ret_disp=True, ret_subocc=True, ret_pan=True)
+        d_only = om(left, mn, mx)
+    rec = {"test": "whole_model", "shape": [B, H, W]}
+    for k, a, c, ca, r in zip(names, ours, r16, rall, r32):
+        rec[k] = {"ours_max": rel_err(a, r), "ours_l2": rel_l2(a, r), "cudnn_bf16_max": rel_err(c.float(), r),
+                  "cudnn_bf16_l2": rel_l2(c.float(), r), "cudnn_bf16_all_max": rel_err(ca.float(), r),
+                  "cudnn_bf16_all_l2": rel_l2(ca.float(), r)}
+    rec["disp_only"] = {"ours_max": rel_err(d_only, r32[1]), "ours_l2": rel_l2(d_only, r32[1])}
+    _log(rec)
+    for k in names:
+        e = rec[k]
+        assert e["ours_l2"] < max(2e-2, 1.2 * e["cudnn_bf16_l2"]), (k, rec)
+        assert e["ours_max"] < max(2e-2, 1.2 * e["cudnn_bf16_max"]), (k, rec)
+    assert rec["disp_only"]["ours_l2"] < 2e-2 and \
+        rec["disp_only"]["ours_max"] < max(2e-2, 1.2 * rec["disp"]["cudnn_bf16_max"]), rec
+
+
+# ------------------------------------------------------------------------------------------------ (c) gradients
+def _grad_table(om, rm, r16_grads):
+    named_o = dict(om.named_parameters())
+    rows = {}
+    for n, p in rm.named_parameters():
+        if "amask_conv" in n:
+            assert p.grad is None and named_o[n].grad is None
+            continue
+        g, r = named_o[n].grad, p.grad
+        rows[n] = (rel_l2(g, r), rel_l2(r16_grads[n], r))
+    return rows
+
+
+def _check_grads(tag, rows, shape):
+    worst = max(rows.items(), key=lambda kv: kv[1][0])
+    _log({"test": tag, "shape": shape, "n_tensors": len(rows), "worst": [worst[0], *worst[1]],
+          "median_ours": sorted(v[0] for v in rows.values())[len(rows) // 2],
+          "median_cudnn_bf16": sorted(v[1] for v in rows.values())[len(rows) // 2],
+          "rows": {k: [round(v[0], 5), round(v[1], 5)] for k, v in rows.items()}})
+    assert len(rows) == 47
+    bad = {k: v for k, v in rows.items() if not v[0] < max(2e-2, 1.5 * v[1])}
+    assert not bad, bad
+
+
+def test_stage1_parameter_gradients_all_tensors(ref):
+    """Every used parameter tensor of a Stage-1 step (perceptual term on) against reference autograd in fp32:
+    per-tensor rel-L2 <= 2e-2, or <= 1.5x the error the reference's own backward shows for that tensor with cuDNN bf16 in
+    its encoder-decoder (``_Bf16Backbone``)."""
+    from fal_net_b200 import loss_functions as LF, steps
+    ref_models, RL = ref
+    dev = torch.device("cuda:0")
+    B, H, W = 2, 128, 384
+    rm, om = _pair(ref_models)
+    left, right = images(B, H, W, 1234).to(dev), images(B, H, W, 1235).to(dev)
+    mn, mx = (t.to(dev) for t in disp_range(B))
+    a_p = 0.01
+    r_loss = ref_loader.ref_stage1(RL, rm, left, right, mn, mx, a_p=a_p)[0]
+    r_loss.backward()
+    g32 = {n: p.grad.clone() for n, p in rm.named_parameters() if p.grad is not None}
+    rm.zero_grad(set_to_none=True)
+    with _Bf16Backbone(rm):
+        l16 = ref_loader.ref_stage1(RL, rm, left, right, mn, mx, a_p=a_p)[0]
+    l16.backward()
+    g16 = {n: p.grad.clone() for n, p in rm.named_parameters() if p.grad is not None}
+    for n, p in rm.named_parameters():
+        p.grad = g32.get(n)
+    vgg = LF.Vgg19_pc().to(dev)
+    loss = steps.stage1_loss(om, left, right, mn, mx, a_p=a_p, vgg=vgg)[0]
+    loss.backward()
+    assert rel_err(loss, r_loss) < 1e-2, (float(loss), float(r_loss))
+    _check_grads("stage1_grads", _grad_table(om, rm, g16), [B, H, W])
+
+
+def test_stage2_parameter_gradients_all_tensors(ref):
+    """Same for the Stage-2 step (masks, mirror loss, flip-folded losses, VGG dgrad); exact index flips on both sides."""
+    from fal_net_b200 import loss_functions as LF, steps
+    ref_models, RL = ref
+    dev = torch.device("cuda:0")
+    B, H, W = 2, 128, 384
+    rm, om = _pair(ref_models, 0)
+    rf, of = _pair(ref_models, 1)
+    left, right = images(B, H, W, 1234).to(dev), images(B, H, W, 1235).to(dev)
+    mn, mx = (t.to(dev) for t in disp_range(B))
+    flip = lambda t: torch.flip(t, dims=[3])
+    res_r = ref_loader.ref_stage2(RL, rm, rf, left, right, mn, mx, a_p=0.01, flip=flip)
+    res_r["loss"].backward()
+    g32 = {n: p.grad.clone() for n, p in rm.named_parameters() if p.grad is not None}
+    rm.zero_grad(set_to_none=True)
+    with _Bf16Backbone(rm):
+        l16 = ref_loader.ref_stage2(RL, rm, rf, left, right, mn, mx, a_p=0.01, flip=flip)["loss"]
+    l16.backward()
+    g16 = {n: p.grad.clone() for n, p in rm.named_parameters() if p.grad is not None}
+    for n, p in rm.named_parameters():
+        p.grad = g32.get(n)
+    vgg = LF.Vgg19_pc().to(dev)
+    res = steps.stage2_loss(om, of, left, right, mn, mx, a_p=0.01, vgg=vgg)
+    res["loss"].backward()
+    for k in ("loss", "rec", "sm", "mirror"):
+        assert rel_err(res[k], res_r[k]) < (1e-2 if k in ("loss", "rec") else 3e-2), (k, float(res[k]), float(res_r[k]))
+    _check_grads("stage2_grads", _grad_table(om, rm, g16), [B, H, W])
+
+
+def test_losses_vs_reference_on_cuda(ref):
+    """rec_loss_fnc / smoothness of the product against the reference's loss_functions.py executed on CUDA."""
+    from fal_net_b200 import loss_functions as LF
+    _, RL = ref
+    dev = torch.device("cuda:0")
+    B, H, W = 4, 96, 320
+    g = torch.Generator(device=dev).manual_seed(3)
+    synth = (torch.rand(B, 3, H, W, generator=g, device=dev) - 0.43)
+    label = images(B, H, W, 9).to(dev)
+    mask = torch.rand(B, 1, H, W, generator=g, device=dev)
+    disp = 50 * torch.rand(B, 1, H, W, generator=g, device=dev)
+    for m_r, m_o in ((1, 1), (mask, mask)):
+        with torch.no_grad():
+            r = RL.rec_loss_fnc(m_r, synth, label, RL.vgg(label), 0.01)
+            o = LF.rec_loss_fnc(m_o, synth, label, LF.vgg(label), 0.01)
+        assert rel_err(o, r) < 1e-2, (float(o), float(r))
+    c0 = int(0.2 * W)
+    r = RL.smoothness(label[:, :, :, c0:], disp[:, :, :, c0:], gamma=2)
+    o = LF.smoothness(label[:, :, :, c0:], disp[:, :, :, c0:], gamma=2)
+    assert rel_err(o, r) < 1e-4, (float(o), float(r))
