@@ -333,13 +333,25 @@ def conv_layer_table(tf_peak, hbm_peak, B=8, iters=8):
         bound = max(flops / (tf_peak * 1e12), nbytes / (hbm_peak * 1e9)) * 1e6
         row = {"layer": name, "cin": cin, "cout": cout, "hw_in": [H, W], "stride": stride, "gflop": round(flops / 1e9, 3),
                "bound_us": round(bound, 2)}
+        # a 96-channel input is two sources in the network (64-channel deconv output + 32-channel skip): the data and
+        # weight gradients run per source, exactly as fal_net_b200.backbone schedules them
+        parts = [(0, cin)] if (cin == 32 or cin % 64 == 0) else [(0, cin // 64 * 64), (cin // 64 * 64, cin % 64)]
+        xs = [x[:, o:o + c].contiguous(memory_format=CL) for o, c in parts] if len(parts) > 1 else [x]
+
+        def ours_dgrad():
+            for o, c in parts:
+                CN.conv3x3_dgrad(gy, wd, (H, W), stride=stride, rows=(o, c))
+
+        def ours_wgrad():
+            for (o, c), xp in zip(parts, xs):
+                CN.conv3x3_wgrad(gy, xp, dW, cout=cout, cx=c, ci_off=o, stride=stride)
         ops = {
             "fwd": (lambda: CN.conv3x3_fwd(x, wk, None, stride, 1),
                     lambda: F.conv2d(x, w16, None, stride, 1)),
-            "dgrad": (lambda: CN.conv3x3_dgrad(gy, wd, (H, W), stride=stride),
+            "dgrad": (ours_dgrad,
                       lambda: torch.ops.aten.convolution_backward(gy, x, w16, None, [stride, stride], [1, 1], [1, 1], False,
                                                                   [0, 0], 1, [True, False, False])),
-            "wgrad": (lambda: CN.conv3x3_wgrad(gy, x, dW, cout=cout, stride=stride),
+            "wgrad": (ours_wgrad,
                       lambda: torch.ops.aten.convolution_backward(gy, x, w16, None, [stride, stride], [1, 1], [1, 1], False,
                                                                   [0, 0], 1, [False, True, False])),
         }

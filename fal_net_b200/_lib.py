@@ -63,6 +63,10 @@ _SIGNATURES = {
     "faln_kitti_errors": [_p] * 3 + [_i] * 8 + [_d] * 4 + [_p],
     "faln_real_epe": [_p] * 3 + [_i] * 6 + [_p],
     "faln_rmse255": [_p] * 3 + [_i] * 3 + [_f] * 3 + [_p],
+    "faln_maskr_noalign": [_p] * 6 + [_i] * 4 + [_ll, _p],
+    "faln_pil_bicubic_ksize": [_i, _i],
+    "faln_pil_bicubic_coeffs": [_i, _i, _i, _i, _p, _p],
+    "faln_augment_crops_u8": [_p, _i, _p, _p, _p, _ll, _i, _p, _i, _i, _p],
 }
 _RESTYPES = {"faln_last_error": _C.c_char_p, "faln_launch_count": _C.c_longlong}
 

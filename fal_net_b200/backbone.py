@@ -31,12 +31,9 @@ from . import layout
 CL = torch.channels_last
 LIBRARY_CALLS = {"conv_wgrad": 0}
 
-# (name, cin, cout, stride): encoder stages (/root/reference/models/FAL_netB.py:99-112)
-ENC = (("conv0", 3, 32, 1), ("conv1", 33, 64, 2), ("conv2", 64, 128, 2), ("conv3", 128, 256, 2),
-       ("conv4", 256, 256, 2), ("conv5", 256, 256, 2), ("conv6", 256, 512, 2))
-# (level, up_in, up_out, skip_ch, iconv_out): decoder stages (:116-127); level 1's iconv has no bias / activation
-DEC = ((6, 512, 256, 256, 256), (5, 256, 128, 256, 256), (4, 256, 128, 256, 256), (3, 256, 128, 128, 128),
-       (2, 128, 64, 64, 64), (1, 64, 64, 32, None))
+# The encoder / decoder stage tables ((name, cin, cout, stride) and (level, up_in, up_out, skip_ch, iconv_out)) come from
+# the model's ``_spec`` (fal_net_b200.models._falnet: FAL_netA / B / C differ only in those tables, in the attribute name
+# of the encoder-decoder and in A's separable residual kernels).
 
 from .conv import GENERATION  # noqa: E402  (shared: bumped by the trainer after each in-place optimiser step)
 
@@ -55,6 +52,21 @@ def _cached(weight, tag, fn):
     return cache[tag]
 
 
+def _embed3(w):
+    """A 3x1 / 1x3 kernel (FAL_netA's residual blocks, /root/reference/models/FAL_netA.py:73-76) as the 3x3 kernel with the
+    absent taps zero -- exact, and it lets every layer run on the same tcgen05 3x3 kernels."""
+    if w.shape[2:] == (3, 3):
+        return w
+    w3 = torch.zeros(w.shape[0], w.shape[1], 3, 3, device=w.device, dtype=w.dtype)
+    if w.shape[2:] == (3, 1):
+        w3[:, :, :, 1] = w[:, :, :, 0]
+    elif w.shape[2:] == (1, 3):
+        w3[:, :, 1, :] = w[:, :, 0, :]
+    else:
+        raise RuntimeError(f"unsupported conv kernel shape {tuple(w.shape)}")
+    return w3
+
+
 def _wk(weight, cin=None):
     """Forward (KRSC bf16) weight: a view of the optimiser's bf16 shadow arena when the parameter lives in one (no pack
     kernels at all), else packed once per parameter version."""
@@ -64,7 +76,7 @@ def _wk(weight, cin=None):
         w = ar[0].packed_fwd(ar[1], cin)
         if w is not None:
             return w
-    return _cached(weight, ("fwd", cin), lambda: CN.pack_weight(weight[:, :cin]))
+    return _cached(weight, ("fwd", cin), lambda: CN.pack_weight(_embed3(weight.detach())[:, :cin]))
 
 
 def _wd(weight, cin=None):
@@ -75,7 +87,7 @@ def _wd(weight, cin=None):
         w = ar[0].packed_dgrad(ar[1], cin)
         if w is not None:
             return w
-    return _cached(weight, ("dgrad", cin), lambda: CN.pack_weight_dgrad(weight[:, :cin]))
+    return _cached(weight, ("dgrad", cin), lambda: CN.pack_weight_dgrad(_embed3(weight.detach())[:, :cin]))
 
 
 def fold_logit_conv(w_iconv1, w0):
@@ -89,7 +101,8 @@ def forward(model, image, max_disp, tape=None, disp_lvl=None):
     """dlog0 [B,N,H,W] fp32 planar (16-byte-multiple row pitch).  ``tape`` (a dict) receives what backward needs.
     With ``disp_lvl`` [B,N] (inference, no tape) the last layer's epilogue takes the softmax-expectation itself and the
     function returns the disparity [B,1,H,W]: the logits never reach HBM."""
-    bb = model.backbone
+    bb = model.bb
+    ENC, DEC = model._spec.enc, model._spec.dec
     B = image.shape[0]
     flow_val = (max_disp.reshape(B).float() / 100.0).contiguous()                  # :208-209, constant plane per sample
     skips = []
@@ -191,7 +204,9 @@ def backward(model, tape, g_logits, sink=None):
     """Hand-scheduled backward.  Parameter gradients are ACCUMULATED into ``sink.grad_view(name)`` (fp32, the flat gradient
     arena of trainer.FlatAdamDDP when one is attached to the model -- then ``sink.mark_ready(name)`` releases all-reduce
     buckets as soon as they are complete); returns the sink."""
-    bb = model.backbone
+    bb = model.bb
+    ENC, DEC = model._spec.enc, model._spec.dec
+    pfx = model._spec.bb_attr + "."
     N = model.no_levels
     B, _, H, W = g_logits.shape
     dev = g_logits.device
@@ -240,12 +255,16 @@ def backward(model, tape, g_logits, sink=None):
         """sources: the conv's (concatenated) inputs, in channel order; const = (value[B], in_hw) of a trailing constant
         input plane."""
         def run():
-            dW = sink.grad_view(name)
+            dW = dst = sink.grad_view(name)
+            if dW.shape[2:] != (3, 3):          # separable kernel: full 3x3 gradient into scratch, keep the taps that exist
+                dW = torch.zeros(dW.shape[0], 3, 3, dW.shape[1], device=dev, dtype=torch.float32).permute(0, 3, 1, 2)
             off = 0
             for x in sources:
                 cx = min(x.shape[1], dW.shape[1] - off)
                 CN.conv3x3_wgrad(g_pre, x, dW, cout=cout, cx=cx, ci_off=off, stride=stride)
                 off += cx
+            if dW is not dst:
+                dst.add_(dW[:, :, :, 1:2] if dst.shape[2:] == (3, 1) else dW[:, :, 1:2, :])
             if const is not None:
                 dW[:, off].add_(CN.const_channel_wgrad(g_pre, const[0], const[1], stride, cout))
             ready(name)
@@ -267,8 +286,8 @@ def backward(model, tape, g_logits, sink=None):
         wi1 = bb.iconv1.weight.detach()
         sink.grad_view("conv0.weight").add_(torch.einsum("ockl,mckl->om", gwf, wi1)[:, :, None, None])
         ready("conv0.weight")
-        sink.grad_view("backbone.iconv1.weight").add_(torch.einsum("om,ockl->mckl", w0, gwf))
-        ready("backbone.iconv1.weight")
+        sink.grad_view(pfx + "iconv1.weight").add_(torch.einsum("om,ockl->mckl", w0, gwf))
+        ready(pfx + "iconv1.weight")
     on_side(folded, g, u, s0)
     wd = CN.pack_weight_dgrad(wf)                                                # [96,3,3,Np]
     C1 = u.shape[1]
@@ -285,14 +304,14 @@ def backward(model, tape, g_logits, sink=None):
         if lvl > 1:
             ic = getattr(bb, f"iconv{lvl}")[0]
             cout = ic.weight.shape[0]
-            bias_grad(f"backbone.iconv{lvl}.0.bias", g_h, cout)
-            wgrad(f"backbone.iconv{lvl}.0.weight", g_h, (u, skip), cout)
+            bias_grad(pfx + f"iconv{lvl}.0.bias", g_h, cout)
+            wgrad(pfx + f"iconv{lvl}.0.weight", g_h, (u, skip), cout)
             wd = _wd(ic.weight)
             C1 = u.shape[1]
             hw = (u.shape[2], u.shape[3])
             g_u = CN.conv3x3_dgrad(g_h, wd, hw, rows=(0, C1), dact=1, ysave=u)
             G_skip[lvl - 1] = CN.conv3x3_dgrad(g_h, wd, hw, rows=(C1, skip.shape[1]))
-        wgrad(f"backbone.deconv{lvl}.conv1.weight", g_u, (xu,), up.conv1.weight.shape[0])
+        wgrad(pfx + f"deconv{lvl}.conv1.weight", g_u, (xu,), up.conv1.weight.shape[0])
         g_xu = CN.conv3x3_dgrad(g_u, _wd(up.conv1.weight), (xu.shape[2], xu.shape[3]))
         # nearest-upsample backward fused with ELU' of the producer (h_{l+1}, or the bottleneck skip s6 for level 6)
         g_h = CN.upsample_nearest_bwd(g_xu, (h_in.shape[2], h_in.shape[3]), ysave=h_in, dact=1)
@@ -306,12 +325,12 @@ def backward(model, tape, g_logits, sink=None):
         head = getattr(bb, name)[0]
         blk = getattr(bb, name + "_1")
         hw = (a.shape[2], a.shape[3])
-        wgrad(f"backbone.{name}_1.conv2.weight", g_s, (r,), cout)
+        wgrad(pfx + f"{name}_1.conv2.weight", g_s, (r,), cout)
         g_r = CN.conv3x3_dgrad(g_s, _wd(blk.conv2.weight), hw, dact=1, ysave=r)
-        wgrad(f"backbone.{name}_1.conv1.weight", g_r, (a,), cout)
+        wgrad(pfx + f"{name}_1.conv1.weight", g_r, (a,), cout)
         g_a = CN.conv3x3_dgrad(g_r, _wd(blk.conv1.weight), hw, dact=1, ysave=a, residual=g_s)   # (dgrad + skip path) * ELU'
-        bias_grad(f"backbone.{name}.0.bias", g_a, cout)
-        wname = f"backbone.{name}.0.weight"
+        bias_grad(pfx + f"{name}.0.bias", g_a, cout)
+        wname = pfx + f"{name}.0.weight"
         if i == 0:
             # the 3-channel image as a 32-channel (zero-padded) bf16 NHWC tensor: same tensor-core path, cx = 3
             img16 = layout.planar_to_nhwc_bf16(tape["image"].float().contiguous(), 32).permute(0, 3, 1, 2)

@@ -275,6 +275,52 @@ __global__ void __launch_bounds__(256) rmse255_kernel(const float* __restrict__ 
   if ((threadIdx.x & 31) == 0) atomicAdd(sum, s);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// FAL_netA's maskR (/root/reference/models/FAL_netA.py:264): sum_n grid_sample(softmax(dlog0)_n, grid + x_of_n) with the
+// grid built for align_corners=True (:231-234) but sampled with grid_sample's DEFAULT align_corners=False -- a true 2-D
+// bilinear resampling (ix = ((gx + 1) * W - 1) / 2, iy = ((gy + 1) * H - 1) / 2, zero padding), clamped to <= 1.
+// ATen's fp32 op order is replayed (grid_sampler_unnormalize, floor, corner weights).  Only FAL_netA with ret_subocc
+// reaches this kernel; it gathers from global memory (not a roofline kernel).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maskr_noalign_kernel(const float* __restrict__ logits, const float* __restrict__ lse0,
+                                                            const float* __restrict__ g0x, const float* __restrict__ g0y,
+                                                            const float* __restrict__ x_of, float* __restrict__ out, int B,
+                                                            int N, int H, int W, long long pitch) {
+  const long long n_px = (long long)B * H * W;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n_px; i += (long long)gridDim.x * 256) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const int b = (int)(i / ((long long)W * H));
+    const float gy = __ldg(g0y + y);
+    const float iy = __fdiv_rn(__fadd_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)H), -1.f), 2.f);
+    const float iy0f = floorf(iy);
+    const int iy0 = (int)iy0f, iy1 = iy0 + 1;
+    const float wy0 = __fadd_rn(__fadd_rn(iy0f, 1.f), -iy), wy1 = __fadd_rn(iy, -iy0f);
+    const float gx0 = __ldg(g0x + x);
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const float gx = __fadd_rn(gx0, __ldg(x_of + b * N + n));
+      const float ix = __fdiv_rn(__fadd_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)W), -1.f), 2.f);
+      const float ix0f = floorf(ix);
+      const int ix0 = (int)ix0f, ix1 = ix0 + 1;
+      const float wx0 = __fadd_rn(__fadd_rn(ix0f, 1.f), -ix), wx1 = __fadd_rn(ix, -ix0f);
+      const float* L = logits + ((long long)b * N + n) * H * pitch;
+      const float* S = lse0 + (long long)b * H * W;
+      float v = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int yy = (t & 2) ? iy1 : iy0, xx = (t & 1) ? ix1 : ix0;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          const float p = __expf(__ldg(L + (long long)yy * pitch + xx) - __ldg(S + (long long)yy * W + xx));
+          const float w = __fmul_rn((t & 1) ? wx1 : wx0, (t & 2) ? wy1 : wy0);
+          v = __fadd_rn(v, __fmul_rn(p, w));
+        }
+      }
+      acc += v;
+    }
+    out[i] = acc > 1.f ? 1.f : acc;
+  }
+}
+
 int grid_for(long long n) {
   long long g = (n + 255) / 256;
   const long long cap = (long long)sm_count() * 8;
@@ -343,4 +389,13 @@ extern "C" int faln_rmse255(const float* output, const float* label, double* sum
   const long long n = (long long)B * 3 * H * W;
   rmse255_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(output, label, sum, n, (long long)H * W, m0, m1, m2);
   return after_launch("rmse255_kernel");
+}
+
+extern "C" int faln_maskr_noalign(const float* logits, const float* lse0, const float* g0x, const float* g0y, const float* x_of,
+                                  float* maskR, int B, int N, int H, int W, long long logit_pitch, faln_stream_t stream) {
+  FALN_REQUIRE(logits && lse0 && g0x && g0y && x_of && maskR && B > 0 && N > 0 && H > 0 && W > 0 && logit_pitch >= W,
+               "faln_maskr_noalign: bad argument");
+  maskr_noalign_kernel<<<grid_for((long long)B * H * W), 256, 0, as_stream(stream)>>>(logits, lse0, g0x, g0y, x_of, maskR, B, N,
+                                                                                     H, W, logit_pitch);
+  return after_launch("maskr_noalign_kernel");
 }

@@ -142,8 +142,8 @@ class MedSynthesis(torch.autograd.Function):
         ctx.save_for_backward(logits, image, x_of, d_lvl, g0x, r["pan"], r["disp"], r["lse0"], r["lsew"])
         outs = (r["pan"], r["disp"])
         if want_masks:
-            ctx.mark_non_differentiable(r["maskL"], r["maskR"])
-            outs = outs + (r["maskL"], r["maskR"])
+            ctx.mark_non_differentiable(r["maskL"], r["maskR"], r["lse0"])
+            outs = outs + (r["maskL"], r["maskR"], r["lse0"])
         return outs
 
     @staticmethod
@@ -159,7 +159,19 @@ FLAG_NO_V3 = 32       # FALN_MED_NO_V3: second-generation kernels (A/B compariso
 FLAG_V3_GENERIC = 64  # FALN_MED_V3_GENERIC: third generation, every plane on the per-pixel generic code (testing)
 
 
-def med_section(dlog0, image, min_disp, max_disp, ret_disp=True, ret_subocc=False, ret_pan=False, zero_pad=False):
+def maskr_noalign(logits, lse0, x_of):
+    """FAL_netA's maskR (/root/reference/models/FAL_netA.py:264: grid_sample with its default align_corners=False)."""
+    B, N, H, W = logits.shape
+    out = torch.empty(B, 1, H, W, device=logits.device, dtype=torch.float32)
+    rc = _lib.lib().faln_maskr_noalign(_lib.ptr(logits), _lib.ptr(lse0), _lib.ptr(grid_row(W, logits.device)),
+                                       _lib.ptr(grid_row(H, logits.device)), _lib.ptr(x_of), _lib.ptr(out), B, N, H, W,
+                                       _pitch_of(logits), _lib.cur_stream())
+    _lib.check(rc, "faln_maskr_noalign")
+    return out
+
+
+def med_section(dlog0, image, min_disp, max_disp, ret_disp=True, ret_subocc=False, ret_pan=False, zero_pad=False,
+                maskr_align_corners=True):
     """FAL_net.forward from ``dlog0`` on, same return convention as the reference
     (/root/reference/models/FAL_netB.py:228-229,285-297): a bare tensor when only the disparity is asked
     for, else a list ordered [pan?, disp?, maskL?, maskR?].  ``zero_pad``: the caller guarantees that ``dlog0`` comes from
@@ -174,6 +186,10 @@ def med_section(dlog0, image, min_disp, max_disp, ret_disp=True, ret_subocc=Fals
         return med_disp_only(dlog0, d_lvl)
     g0x = grid_row(W, dlog0.device)
     res = MedSynthesis.apply(dlog0, image, x_of, d_lvl, g0x, bool(ret_subocc), flags)
+    if ret_subocc and not maskr_align_corners:
+        # FAL_netA: maskR is re-sampled with align_corners=False; the fused kernel's pan / disp / maskL stand
+        with torch.no_grad():
+            res = res[:3] + (maskr_noalign(dlog0.detach(), res[4], x_of),)
     out = []
     if ret_pan:
         out.append(res[0])

@@ -2,6 +2,7 @@
 
   stage1_loss  <- /root/reference/Train_Stage1_K.py:236-258
   stage2_loss  <- /root/reference/Train_Stage2_K.py:247-327
+  stage1_slow_loss <- /root/reference/Train_Stage1_Kslow.py:236-278
   test_disp    <- /root/reference/Test_KITTI.py:196-205, 287-300
 
 Differences from the reference that do not change results beyond fp rounding:
@@ -79,6 +80,30 @@ def stage2_loss(model, fix_model, left, right, min_disp, max_disp, a_p=0.01, a_s
     loss = rec + a_sm * sm + a_mr * mirror
     return dict(loss=loss, rec=rec, sm=sm, mirror=mirror, rpan=rpan, lpan_f=lpan_f, ldisp=ldisp, rdisp_f=rdisp_f,
                 O_L=O_L, O_R=O_R)
+
+
+def stage1_slow_loss(model, left, right, min_disp, max_disp, a_p=0.01, a_sm=0.2 * 2 / 512, vgg=None):
+    """Step body of /root/reference/Train_Stage1_Kslow.py:236-278: both views through the network as one batch
+    ([left, flip(right)]), reconstruction + smoothness on both, no occlusion masks, no mirror loss.  Returns dict."""
+    B, _, H, W = left.shape
+    c20, c80 = int(0.20 * W), int(0.80 * W)
+    mn2, mx2 = torch.cat((min_disp, min_disp), 0), torch.cat((max_disp, max_disp), 0)
+    vgg = vgg or LF.vgg
+    pan, disp = model(torch.cat((left, torch.flip(right, dims=[3])), 0), mn2, mx2, ret_disp=True, ret_pan=True,
+                      ret_subocc=False)
+    rpan, lpan_f = pan[:B], pan[B:]                      # second half lives in flipped coordinates (un-flip folded below)
+    ldisp, rdisp_f = disp[:B], disp[B:]
+    vgg_right = vgg_left = None
+    if a_p > 0:
+        with torch.no_grad():
+            vgg_right, vgg_left = vgg(right), vgg(left)
+    rec = (LF.rec_loss_fnc(1, rpan, right, vgg_right, a_p) + LF.rec_loss_fnc(1, lpan_f, left, vgg_left, a_p, flip_x=True)) / 2
+    sm = 0
+    if a_sm > 0:
+        sm = (LF.smoothness(left, ldisp, gamma=2, window=(c20, W)) +
+              LF.smoothness(right, rdisp_f, gamma=2, window=(0, c80), flip_x=True)) / 2
+    loss = rec + a_sm * sm
+    return dict(loss=loss, rec=rec, sm=sm, rpan=rpan, lpan_f=lpan_f, ldisp=ldisp, rdisp_f=rdisp_f)
 
 
 @torch.no_grad()

@@ -276,6 +276,41 @@ int faln_real_epe(const float* output, const float* target, double* sums, int B,
 int faln_rmse255(const float* output, const float* label, double* sum, int B, int H, int W, float m0, float m1, float m2,
                  faln_stream_t stream);
 
+/* FAL_netA's maskR only (/root/reference/models/FAL_netA.py:264): the right-from-left occlusion mask sampled with
+ * grid_sample's default align_corners=False on the align_corners=True grid (a 2-D bilinear resampling), from the logits
+ * and the saved log-sum-exp of the un-warped logits.  g0x [W], g0y [H]: rows of the identity affine grid. */
+int faln_maskr_noalign(const float* logits, const float* lse0, const float* g0x, const float* g0y, const float* x_of,
+                       float* maskR, int B, int N, int H, int W, long long logit_pitch, faln_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training input pipeline on the device: csrc/input_pipe.cu.
+ * Replaces /root/reference/data_transforms.py:46-157 + the input transform of /root/reference/Train_Stage1_K.py:124-128
+ * (4 DataLoader workers running PIL / numpy per sample): decoded uint8 HWC images in, normalised fp32 NCHW crops out,
+ * bit-exact with the reference (integer resampling; value chain as a 3x256 table per image).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* src; /* device pointer: uint8 [H,W,3] (HWC, like the numpy array the reference's loader returns) */
+  int H, W;        /* source size */
+  int row0, rows;  /* source rows the crop needs: [row0, row0+rows) */
+  int x_tab, y_tab;/* offsets (ints) into `tabs`: bounds[2*t] then coeffs[t*ks], for the crop's columns / rows */
+  int ksx, ksy;    /* taps per output pixel (faln_pil_bicubic_ksize) */
+  int flip;        /* 1: mirror the crop horizontally (RandomHorizontalFlip, data_transforms.py:96-116) */
+  int dst;         /* image slot in the output tensor */
+  int lut;         /* offset (floats) into `luts`: 3 x 256 values, uint8 -> normalised fp32 */
+  int pad_;
+} faln_aug_desc;
+
+/* HOST functions (no CUDA): Pillow's bicubic resampling tables (Resample.c precompute_coeffs + normalize_coeffs_8bpc)
+ * for output pixels [out_lo, out_lo+out_n) of an in_size -> out_size resize; what `Image.resize(..., Image.BICUBIC)`
+ * at data_transforms.py:67 computes internally.  bounds [2*out_n], coeffs [out_n * ksize]. */
+int faln_pil_bicubic_ksize(int in_size, int out_size);
+int faln_pil_bicubic_coeffs(int in_size, int out_size, int out_lo, int out_n, int* bounds, int* coeffs);
+/* Two batched launches (horizontal pass into `inter`, vertical pass + value table + mirror into `out`).
+ * descs [n_img], tabs, luts: device; inter: n_img * inter_stride bytes of scratch (>= max_rows*tw*3 each);
+ * out [n_slots,3,th,tw] fp32. */
+int faln_augment_crops_u8(const faln_aug_desc* descs, int n_img, const int* tabs, const float* luts, unsigned char* inter,
+                          long long inter_stride, int max_rows, float* out, int th, int tw, faln_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,27 +51,57 @@ DECODER = [(6, 512, 256, 256 + 256, 256), (5, 256, 128, 128 + 256, 256), (4, 256
            (3, 256, 128, 128 + 128, 128), (2, 128, 64, 64 + 64, 64), (1, 64, 64, 32 + 64, None)]
 
 
-def param_shapes(no_levels: int = 49) -> "OrderedDict[str, tuple]":
-    """state_dict keys and shapes of FAL_netB in registration order."""
+# Variants.  FAL_netC (/root/reference/models/FAL_netC.py:110-120,185): wider bottleneck, encoder-decoder
+# registered as ``synth``.  FAL_netA (/root/reference/models/FAL_netA.py:73-76,99-126,183,264): narrower, 3x1 / 1x3 residual
+# kernels, no amask_conv, registered as ``BackBone``, maskR sampled with grid_sample's default align_corners=False.
+VARIANTS = {
+    "FAL_netB": dict(prefix="backbone", enc=ENCODER, dec=DECODER, separable=False, amask=True, maskr_align=True),
+    "FAL_netC": dict(prefix="synth",
+                     enc=[("conv0", 3, 32, 1), ("conv1", 33, 64, 2), ("conv2", 64, 128, 2), ("conv3", 128, 256, 2),
+                          ("conv4", 256, 256, 2), ("conv5", 256, 512, 2), ("conv6", 512, 512, 2)],
+                     dec=[(6, 512, 256, 256 + 512, 512), (5, 512, 256, 256 + 256, 256), (4, 256, 128, 128 + 256, 256),
+                          (3, 256, 128, 128 + 128, 128), (2, 128, 64, 64 + 64, 64), (1, 64, 64, 32 + 64, None)],
+                     separable=False, amask=True, maskr_align=True),
+    "FAL_netA": dict(prefix="BackBone",
+                     enc=[("conv0", 3, 32, 1), ("conv1", 33, 64, 2), ("conv2", 64, 128, 2), ("conv3", 128, 128, 2),
+                          ("conv4", 128, 256, 2), ("conv5", 256, 256, 2), ("conv6", 256, 256, 2)],
+                     dec=[(6, 256, 128, 128 + 256, 256), (5, 256, 128, 128 + 256, 256), (4, 256, 128, 128 + 128, 128),
+                          (3, 128, 64, 128 + 64, 128), (2, 128, 64, 64 + 64, 64), (1, 64, 64, 32 + 64, None)],
+                     separable=True, amask=False, maskr_align=False),
+}
+
+
+def param_shapes(no_levels: int = 49, variant: str = "FAL_netB") -> "OrderedDict[str, tuple]":
+    """state_dict keys and shapes in registration order."""
+    v = VARIANTS[variant]
+    pf = v["prefix"]
+    k1, k2 = ((3, 1), (1, 3)) if v["separable"] else ((3, 3), (3, 3))
     sh = OrderedDict()
-    for name, cin, cout, _ in ENCODER:
-        sh[f"backbone.{name}.0.weight"] = (cout, cin, 3, 3)
-        sh[f"backbone.{name}.0.bias"] = (cout,)
-        sh[f"backbone.{name}_1.conv1.weight"] = (cout, cout, 3, 3)
-        sh[f"backbone.{name}_1.conv2.weight"] = (cout, cout, 3, 3)
-    for lvl, din, dout, iin, iout in DECODER:
-        sh[f"backbone.deconv{lvl}.conv1.weight"] = (dout, din, 3, 3)
+    for name, cin, cout, _ in v["enc"]:
+        sh[f"{pf}.{name}.0.weight"] = (cout, cin, 3, 3)
+        sh[f"{pf}.{name}.0.bias"] = (cout,)
+        sh[f"{pf}.{name}_1.conv1.weight"] = (cout, cout) + k1
+        sh[f"{pf}.{name}_1.conv2.weight"] = (cout, cout) + k2
+    for lvl, din, dout, iin, iout in v["dec"]:
+        sh[f"{pf}.deconv{lvl}.conv1.weight"] = (dout, din, 3, 3)
         if iout is not None:
-            sh[f"backbone.iconv{lvl}.0.weight"] = (iout, iin, 3, 3)
-            sh[f"backbone.iconv{lvl}.0.bias"] = (iout,)
+            sh[f"{pf}.iconv{lvl}.0.weight"] = (iout, iin, 3, 3)
+            sh[f"{pf}.iconv{lvl}.0.bias"] = (iout,)
         else:
-            sh["backbone.iconv1.weight"] = (no_levels, iin, 3, 3)
-    sh["backbone.amask_conv.0.weight"] = (48, 96, 3, 3)
-    sh["backbone.amask_conv.0.bias"] = (48,)
-    sh["backbone.amask_conv.2.weight"] = (1, 48, 3, 3)
+            sh[f"{pf}.iconv1.weight"] = (no_levels, iin, 3, 3)
+    if v["amask"]:
+        sh[f"{pf}.amask_conv.0.weight"] = (48, 96, 3, 3)
+        sh[f"{pf}.amask_conv.0.bias"] = (48,)
+        sh[f"{pf}.amask_conv.2.weight"] = (1, 48, 3, 3)
     sh["conv0.weight"] = (no_levels, no_levels, 1, 1)
     sh["conv0.bias"] = (no_levels,)
     return sh
+
+
+def variant_of(p) -> str:
+    """Which variant a parameter dict belongs to (from its key prefix)."""
+    k = next(iter(p.keys()))
+    return {"backbone": "FAL_netB", "synth": "FAL_netC", "BackBone": "FAL_netA"}[k.split(".")[0]]
 
 
 def init_params(no_levels: int = 49, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
@@ -94,35 +124,42 @@ def init_params(no_levels: int = 49, seed: int = 0) -> "OrderedDict[str, torch.T
 # Backbone  (/root/reference/models/FAL_netB.py:140-176)
 # ----------------------------------------------------------------------------------------------
 
+def _pad_of(w):
+    return ((w.shape[2] - 1) // 2, (w.shape[3] - 1) // 2)
+
+
 def _res_block(p, prefix, x):
-    # /root/reference/models/FAL_netB.py:78-80
-    y = F.elu(F.conv2d(x, p[prefix + ".conv1.weight"], None, 1, 1))
-    y = F.conv2d(y, p[prefix + ".conv2.weight"], None, 1, 1)
+    # /root/reference/models/FAL_netB.py:78-80 (3x3 kernels); FAL_netA.py:73-80 (3x1 then 1x3, "same" padding)
+    w1, w2 = p[prefix + ".conv1.weight"], p[prefix + ".conv2.weight"]
+    y = F.elu(F.conv2d(x, w1, None, 1, _pad_of(w1)))
+    y = F.conv2d(y, w2, None, 1, _pad_of(w2))
     return F.elu(y + x)
 
 
 def backbone_forward(p, x, flow, collect=None):
     """x [B,3,H,W], flow [B,1,H,W] -> dlog [B,N,H,W]."""
+    v = VARIANTS[variant_of(p)]
+    pf = v["prefix"]
     skips = []
     h = x
-    for i, (name, _, _, stride) in enumerate(ENCODER):
+    for i, (name, _, _, stride) in enumerate(v["enc"]):
         if i == 1:
             h = torch.cat((h, flow), 1)                                       # :145
-        h = F.elu(F.conv2d(h, p[f"backbone.{name}.0.weight"], p[f"backbone.{name}.0.bias"], stride, 1))
-        h = _res_block(p, f"backbone.{name}_1", h)
+        h = F.elu(F.conv2d(h, p[f"{pf}.{name}.0.weight"], p[f"{pf}.{name}.0.bias"], stride, 1))
+        h = _res_block(p, f"{pf}.{name}_1", h)
         skips.append(h)
         if collect is not None:
             collect[name] = h
     h = skips[6]
-    for lvl, _, _, _, iout in DECODER:
+    for lvl, _, _, _, iout in v["dec"]:
         skip = skips[lvl - 1]
         u = F.interpolate(h, size=(skip.shape[2], skip.shape[3]), mode="nearest")   # :58
-        u = F.elu(F.conv2d(u, p[f"backbone.deconv{lvl}.conv1.weight"], None, 1, 1))  # :59
+        u = F.elu(F.conv2d(u, p[f"{pf}.deconv{lvl}.conv1.weight"], None, 1, 1))      # :59
         c = torch.cat((u, skip), 1)
         if iout is not None:
-            h = F.elu(F.conv2d(c, p[f"backbone.iconv{lvl}.0.weight"], p[f"backbone.iconv{lvl}.0.bias"], 1, 1))
+            h = F.elu(F.conv2d(c, p[f"{pf}.iconv{lvl}.0.weight"], p[f"{pf}.iconv{lvl}.0.bias"], 1, 1))
         else:
-            h = F.conv2d(c, p["backbone.iconv1.weight"], None, 1, 1)            # :127,174 no activation
+            h = F.conv2d(c, p[f"{pf}.iconv1.weight"], None, 1, 1)               # :127,174 no activation
         if collect is not None:
             collect[f"iconv{lvl}"] = h
     return h
@@ -154,7 +191,8 @@ def identity_grid(B, C, H, W, device=None, align_corners=True):
     return F.affine_grid(th, [B, C, H, W], align_corners=align_corners)
 
 
-def med_forward_ops(dlog0, image, min_disp, max_disp, ret_disp=True, ret_subocc=False, ret_pan=False):
+def med_forward_ops(dlog0, image, min_disp, max_disp, ret_disp=True, ret_subocc=False, ret_pan=False,
+                    maskr_align=True):
     """The reference's op sequence on (dlog0, image): /root/reference/models/FAL_netB.py:216-297.
     Returns the same thing as FAL_net.forward (a tensor when only ret_disp, else a list ordered
     [pan?, disp?, maskL?, maskR?])."""
@@ -191,7 +229,8 @@ def med_forward_ops(dlog0, image, min_disp, max_disp, ret_disp=True, ret_subocc=
         g = shifted(n, +1)
         if ret_subocc:
             with torch.no_grad():
-                maskR = maskR + F.grid_sample(sm0[:, n].unsqueeze(1).detach(), g, align_corners=True)
+                # FAL_netA.py:264 calls grid_sample WITHOUT align_corners for maskR (default False); B / C pass True
+                maskR = maskR + F.grid_sample(sm0[:, n].unsqueeze(1).detach(), g, align_corners=bool(maskr_align))
                 maskL = maskL + F.grid_sample(Dprob[:, n].unsqueeze(1).detach(), shifted(n, -1),
                                               align_corners=True)
         if ret_pan:
@@ -293,7 +332,8 @@ def falnet_forward(p, image, min_disp, max_disp, ret_disp=True, ret_subocc=False
     flow[:, 0] = max_disp * flow[:, 0] / 100                                     # :208-209
     dlog = backbone_forward(p, image, flow)
     dlog0 = F.conv2d(dlog, p["conv0.weight"], p["conv0.bias"])                   # :215
-    return med_forward_ops(dlog0, image, min_disp, max_disp, ret_disp, ret_subocc, ret_pan)
+    return med_forward_ops(dlog0, image, min_disp, max_disp, ret_disp, ret_subocc, ret_pan,
+                           maskr_align=VARIANTS[variant_of(p)]["maskr_align"])
 
 
 # ----------------------------------------------------------------------------------------------
@@ -439,6 +479,24 @@ def stage2_loss(p, p_fix, left, right, min_disp, max_disp, a_p=0.01, a_sm=0.4 * 
     loss = rec + a_sm * sm + a_mr * mirror
     return dict(loss=loss, rec=rec, sm=sm, mirror=mirror, rpan=rpan, lpan=lpan, ldisp=ldisp, rdisp=rdisp,
                 O_L=O_L, O_R=O_R)
+
+
+def stage1_slow_loss(p, left, right, min_disp, max_disp, a_p=0.01, a_sm=0.2 * 2 / 512, vgg_ws=None, flip=grid_flip):
+    """/root/reference/Train_Stage1_Kslow.py:236-278: Stage-2's two-view batch without masks / mirror loss."""
+    B, C, H, W = left.shape
+    mn2, mx2 = torch.cat((min_disp, min_disp), 0), torch.cat((max_disp, max_disp), 0)
+    pan, disp = falnet_forward(p, torch.cat((left, flip(right)), 0), mn2, mx2, ret_disp=True, ret_pan=True)
+    rpan, lpan = pan[:B], flip(pan[B:])
+    ldisp, rdisp = disp[:B], flip(disp[B:])
+    vgg_right = vgg_features(vgg_ws, right) if a_p > 0 else None
+    vgg_left = vgg_features(vgg_ws, left) if a_p > 0 else None
+    rec = (rec_loss(1, rpan, right, vgg_right, a_p, vgg_ws) + rec_loss(1, lpan, left, vgg_left, a_p, vgg_ws)) / 2
+    c20, c80 = int(0.20 * W), int(0.80 * W)
+    sm = 0
+    if a_sm > 0:
+        sm = (smoothness(left[..., c20:], ldisp[..., c20:], gamma=2) +
+              smoothness(right[..., :c80], rdisp[..., :c80], gamma=2)) / 2
+    return dict(loss=rec + a_sm * sm, rec=rec, sm=sm, rpan=rpan, lpan=lpan, ldisp=ldisp, rdisp=rdisp)
 
 
 def test_disp_fpp(p, image, min_disp, max_disp, flip=None):

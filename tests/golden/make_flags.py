@@ -32,6 +32,6 @@ def flags_of(path):
 
 
 if __name__ == "__main__":
-    res = {name: flags_of(os.path.join(REF, name + ".py")) for name in ("Train_Stage1_K", "Train_Stage2_K", "Test_KITTI")}
+    res = {name: flags_of(os.path.join(REF, name + ".py")) for name in ("Train_Stage1_K", "Train_Stage1_Kslow", "Train_Stage2_K", "Test_KITTI")}
     json.dump(res, open(OUT, "w"), indent=1, sort_keys=True)
     print({k: len(v) for k, v in res.items()}, "->", OUT)
