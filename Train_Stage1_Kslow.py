@@ -59,6 +59,7 @@ def train(train_loader, m_model, g_optimizer, epoch, args, device):
     epoch_size = len(train_loader) if args.epoch_size == 0 else min(len(train_loader), args.epoch_size)
     m_model.train()
     end = time.time()
+    loss_sum, n_steps = None, 0                         # every step's loss, accumulated on the device: one sync per epoch
     for i, ((left_view, right_view), max_disp) in enumerate(train_loader):
         left_view = left_view.to(device, non_blocking=True)
         right_view = right_view.to(device, non_blocking=True)
@@ -69,6 +70,8 @@ def train(train_loader, m_model, g_optimizer, epoch, args, device):
         loss, rec_loss = res["loss"], res["rec"]
         loss.backward()
         g_optimizer.step()
+        loss_sum = loss.detach() if loss_sum is None else loss_sum + loss.detach()
+        n_steps += 1
         if i % args.print_freq == 0:                       # the only host sync, every print_freq steps
             losses.update(loss.item(), args.batch_size)
             rec_losses.update(rec_loss.item(), args.batch_size)
@@ -77,7 +80,7 @@ def train(train_loader, m_model, g_optimizer, epoch, args, device):
         end = time.time()
         if i >= epoch_size:
             break
-    return losses.avg
+    return float(loss_sum) / max(n_steps, 1) if loss_sum is not None else 0.0
 
 
 def main(argv=None):

@@ -16,7 +16,10 @@ parser = S1.parser
 # defaults of /root/reference/Train_Stage2_K.py:44-60 where they differ from Stage 1
 parser.set_defaults(lr=0.00005, a_sm=0.4 * 2 / 512, batch_size=4, milestones=[5, 10], epochs=20, save_path="Kitti_stage2")
 parser.add_argument("-mirror_loss", "--a_mr", type=float, default=1, help="Mirror loss weight")
-parser.add_argument("--fix_model", default=None, help="Stage-1 checkpoint for the frozen model (random init if absent)")
+parser.add_argument("--fix_model", default=None, help="Stage-1 checkpoint of the frozen teacher (reference default: a run "
+                    "directory, Train_Stage2_K.py:63-65); required when the mirror loss is on")
+parser.add_argument("--random-teacher", action="store_true",
+                    help="benchmarking only: allow a random-init frozen model when --fix_model is absent and a_mr > 0")
 
 
 def train(train_loader, m_model, fix_model, g_optimizer, epoch, args, device):
@@ -25,6 +28,7 @@ def train(train_loader, m_model, fix_model, g_optimizer, epoch, args, device):
     epoch_size = len(train_loader) if args.epoch_size == 0 else min(len(train_loader), args.epoch_size)
     m_model.train()
     end = time.time()
+    loss_sum, n_steps = None, 0                         # every step's loss, accumulated on the device: one sync per epoch
     for i, ((left_view, right_view), max_disp) in enumerate(train_loader):
         left_view = left_view.to(device, non_blocking=True)
         right_view = right_view.to(device, non_blocking=True)
@@ -35,23 +39,33 @@ def train(train_loader, m_model, fix_model, g_optimizer, epoch, args, device):
                                 a_sm=args.a_sm, a_mr=args.a_mr)
         res["loss"].backward()
         g_optimizer.step()
-        if i % args.print_freq == 0:
+        loss_sum = res["loss"].detach() if loss_sum is None else loss_sum + res["loss"].detach()
+        n_steps += 1
+        if i % args.print_freq == 0:                    # the only host sync inside the epoch
             losses.update(res["loss"].item(), args.batch_size)
             batch_time.update(time.time() - end)
             print(f"Epoch: [{epoch}][{i}/{epoch_size}] Time {batch_time}  Loss {losses}")
         end = time.time()
         if i >= epoch_size:
             break
-    return losses.avg
+    return float(loss_sum) / max(n_steps, 1) if loss_sum is not None else 0.0
 
 
 def main(argv=None):
     args = parser.parse_args(argv)
     rank, world, device = init_distributed()
     network_data = torch.load(args.pretrained, map_location="cpu") if args.pretrained else None
+    if network_data:
+        args.m_model = network_data["m_model"]                                   # reference :166
     m_model = models.__dict__[args.m_model](network_data, no_levels=args.no_levels).to(device)
+    if args.a_mr > 0 and not args.fix_model and not args.random_teacher:
+        # the reference defaults --fix_model to a Stage-1 checkpoint and fails without it (:63-65,176-183); a random frozen
+        # teacher would make the mirror loss meaningless, so it has to be asked for explicitly
+        raise SystemExit("Train_Stage2_K: --fix_model <stage-1 checkpoint> is required when a_mr > 0 "
+                         "(pass --random-teacher for a synthetic benchmark run)")
     fix_data = torch.load(args.fix_model, map_location="cpu") if args.fix_model else None
-    fix_model = models.__dict__[args.m_model](fix_data, no_levels=args.no_levels).to(device).eval()
+    fix_name = fix_data["m_model"] if fix_data and "m_model" in fix_data else args.m_model   # reference :178-180
+    fix_model = models.__dict__[fix_name](fix_data, no_levels=args.no_levels).to(device).eval()
     for p in fix_model.parameters():
         p.requires_grad_(False)
     g_optimizer = FlatAdamDDP(m_model, lr=args.lr, betas=(args.momentum, args.beta), weight_decay=args.weight_decay,

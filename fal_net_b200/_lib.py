@@ -57,6 +57,13 @@ _SIGNATURES = {
     "faln_stem_conv": [_p] * 4 + [_i] * 6 + [_p],
     "faln_upsample_nearest_nhwc": [_p, _p] + [_i] * 6 + [_p],
     "faln_maxpool2_nhwc": [_p, _p] + [_i] * 4 + [_p],
+    "faln_level_tables": [_p] * 4 + [_i] * 3 + [_p],
+    "faln_fold_logit_conv": [_p, _p] + [_ll] * 4 + [_p, _p] + [_i] * 4 + [_p],
+    "faln_fold_logit_conv_bwd": [_p] * 3 + [_ll] * 4 + [_p] + [_ll] * 4 + [_p, _i, _i, _p],
+    "faln_const_channel_table": [_p] + [_ll] * 4 + [_i, _p, _i, _p],
+    "faln_const_channel_wgrad": [_p, _p, _p] + [_ll] * 4 + [_i] * 5 + [_p],
+    "faln_scalar_combine": [_p, _p, _i, _p, _p],
+    "faln_scalar_scale": [_p, _p, _i, _p, _p],
     "faln_flip_resize_bilinear": [_p, _p] + [_i] * 6 + [_p],
     "faln_percentile_rows": [_p, _i, _ll, _ll, _d, _d, _p, _p],
     "faln_mspp_blend": [_p] * 4 + [_i] * 5 + [_f, _p],

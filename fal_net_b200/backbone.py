@@ -92,8 +92,22 @@ def _wd(weight, cin=None):
 
 def fold_logit_conv(w_iconv1, w0):
     """iconv1 (3x3, no bias, no activation; reference :127,174) followed by conv0 (1x1 + bias; :190,215)
-    == one 3x3 conv with W'[o,c,kh,kw] = sum_m W0[o,m] * W_iconv1[m,c,kh,kw]."""
+    == one 3x3 conv with W'[o,c,kh,kw] = sum_m W0[o,m] * W_iconv1[m,c,kh,kw].  (torch form: tests / documentation; the
+    product path is CN.fold_logit_conv, one kernel that writes the bf16 packs directly.)"""
     return torch.einsum("om,mckl->ockl", w0[:, :, 0, 0], w_iconv1)
+
+
+def _folded_packs(model, rows_pad):
+    """(forward pack, dgrad pack) of the folded logits layer; recomputed when either parameter changed (training: once per
+    step, one launch), cached otherwise (frozen model, inference)."""
+    wi, w0 = model.bb.iconv1.weight, model.conv0.weight
+    key = (wi._version, w0._version, wi.data_ptr(), w0.data_ptr(), rows_pad,
+           GENERATION[0] if (wi.requires_grad or w0.requires_grad) else -1)
+    cache = getattr(model, "_faln_fold", None)
+    if cache is None or cache[0] != key:
+        cache = (key, CN.fold_logit_conv(wi, w0, rows_pad))
+        model._faln_fold = cache
+    return cache[1]
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -112,7 +126,7 @@ def forward(model, image, max_disp, tape=None, disp_lvl=None):
             a = CN.stem_conv(image, head.weight, head.bias, 1)                     # reads the fp32 NCHW image directly
         else:
             C1 = skips[-1].shape[1]
-            ctab = CN.const_channel_table(head.weight[:, C1].detach()) if i == 1 else None
+            ctab = CN.const_channel_table_of(head.weight, C1) if i == 1 else None
             a = CN.conv3x3_fwd(skips[-1], _wk(head.weight, C1), head.bias, stride, 1, cout=cout, ctab=ctab,
                                cscale=flow_val if i == 1 else None)
         blk = getattr(bb, name + "_1")
@@ -134,16 +148,18 @@ def forward(model, image, max_disp, tape=None, disp_lvl=None):
                 tape[f"dec{lvl}"] = (h, xu, u, hn)
             h = hn
         else:
-            wf = fold_logit_conv(bb.iconv1.weight.detach(), model.conv0.weight.detach())
-            N = wf.shape[0]
+            N = model.no_levels
             Bq, _, H, W = u.shape
-            if disp_lvl is not None and tape is None and CN.logits_disp_supported(W, N):
-                return CN.conv3x3_logits_disp(u, skip, CN.pack_weight(wf, 64), model.conv0.bias, disp_lvl)
+            fused = disp_lvl is not None and tape is None and CN.logits_disp_supported(W, N)
+            # W' = conv0 . iconv1 as the forward pack and the data-gradient pack, one launch; frozen weights: cached
+            wfk, wfd = _folded_packs(model, 64 if fused else None)
+            if fused:
+                return CN.conv3x3_logits_disp(u, skip, wfk, model.conv0.bias, disp_lvl)
             out = layout.alloc_planar(Bq, N, H, W, u.device)
-            CN.conv3x3_fwd(u, CN.pack_weight(wf), model.conv0.bias, 1, 0, None, skip, cout=N, planar_out=out)
+            CN.conv3x3_fwd(u, wfk, model.conv0.bias, 1, 0, None, skip, cout=N, planar_out=out)
             if tape is not None:
                 tape["dec1"] = (h, xu, u, None)
-                tape["wf"] = wf
+                tape["wfd"] = wfd
                 tape["flow_val"] = flow_val
                 tape["image"] = image
             return out
@@ -266,7 +282,7 @@ def backward(model, tape, g_logits, sink=None):
             if dW is not dst:
                 dst.add_(dW[:, :, :, 1:2] if dst.shape[2:] == (3, 1) else dW[:, :, 1:2, :])
             if const is not None:
-                dW[:, off].add_(CN.const_channel_wgrad(g_pre, const[0], const[1], stride, cout))
+                CN.const_channel_wgrad_into(g_pre, const[0], const[1], stride, cout, dW, off)
             ready(name)
         on_side(run, g_pre, *sources)
 
@@ -275,21 +291,19 @@ def backward(model, tape, g_logits, sink=None):
     g = layout.planar_to_nhwc_bf16(g_logits, Np).permute(0, 3, 1, 2)            # bf16 [B,Np,H,W] channels_last view
     h2, xu, u, _ = tape["dec1"]
     s0 = tape["conv0"][2]
-    wf = tape["wf"]
     bias_grad("conv0.bias", g, N)
 
     def folded():
         gwf = torch.zeros(N, 3, 3, u.shape[1] + s0.shape[1], device=dev, dtype=torch.float32).permute(0, 3, 1, 2)
         CN.conv3x3_wgrad(g, u, gwf, cout=N, ci_off=0)
         CN.conv3x3_wgrad(g, s0, gwf, cout=N, ci_off=u.shape[1])
-        w0 = model.conv0.weight.detach()[:, :, 0, 0]
-        wi1 = bb.iconv1.weight.detach()
-        sink.grad_view("conv0.weight").add_(torch.einsum("ockl,mckl->om", gwf, wi1)[:, :, None, None])
+        # adjoint of the fold, one launch: dW0 = <gW', W_iconv1>, dW_iconv1 = W0^T gW'
+        CN.fold_logit_conv_bwd(gwf, bb.iconv1.weight, model.conv0.weight, sink.grad_view(pfx + "iconv1.weight"),
+                               sink.grad_view("conv0.weight"))
         ready("conv0.weight")
-        sink.grad_view(pfx + "iconv1.weight").add_(torch.einsum("om,ockl->mckl", w0, gwf))
         ready(pfx + "iconv1.weight")
     on_side(folded, g, u, s0)
-    wd = CN.pack_weight_dgrad(wf)                                                # [96,3,3,Np]
+    wd = tape["wfd"]                                                             # [96,3,3,Np], written by the fold kernel
     C1 = u.shape[1]
     g_u = CN.conv3x3_dgrad(g, wd, (H, W), rows=(0, C1), dact=1, ysave=u)
     G_skip = {0: CN.conv3x3_dgrad(g, wd, (H, W), rows=(C1, s0.shape[1]))}        # second consumer arrives in the encoder pass

@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "csrc", "_obj")
 LIB = os.path.join(PKG, "libfalnet_sm100.so")
-SOURCES = ["lib.cu", "med.cu", "med3.cu", "losses.cu", "misc.cu", "conv_tc.cu", "conv_aux.cu", "conv_wgrad.cu", "postproc.cu", "input_pipe.cu"]
+SOURCES = ["lib.cu", "med.cu", "med3.cu", "losses.cu", "misc.cu", "conv_tc.cu", "conv_aux.cu", "conv_wgrad.cu", "postproc.cu", "input_pipe.cu", "small_ops.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

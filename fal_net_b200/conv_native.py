@@ -58,6 +58,62 @@ def const_channel_table(wf: torch.Tensor, cout_pad=None) -> torch.Tensor:
     return (_border_masks(wf.device).view(16, 9) @ wf.float().reshape(wf.shape[0], 9).t()).contiguous()
 
 
+def const_channel_table_of(weight: torch.Tensor, channel: int) -> torch.Tensor:
+    """[16,Cout] border-class sums of input channel ``channel`` of a (possibly KRSC-strided) [Cout,Cin,3,3] fp32 weight:
+    one launch (csrc/small_ops.cu), no slicing / matmul."""
+    w = weight.detach()
+    assert w.dtype == torch.float32 and w.dim() == 4 and w.shape[2:] == (3, 3)
+    ctab = torch.empty(16, w.shape[0], device=w.device, dtype=torch.float32)
+    so, sc, sh, sw = w.stride()
+    _lib.check(_lib.lib().faln_const_channel_table(_lib.ptr(w), so, sc, sh, sw, int(channel), _lib.ptr(ctab), w.shape[0],
+                                                   _lib.cur_stream()), "faln_const_channel_table")
+    return ctab
+
+
+def fold_logit_conv(w_iconv1: torch.Tensor, w0: torch.Tensor, rows_pad=None):
+    """iconv1 (3x3, no bias, no activation; reference :127,174) followed by conv0 (1x1 + bias; :190,215) == one 3x3 conv
+    with W'[o,c,kh,kw] = sum_m W0[o,m] * W_iconv1[m,c,kh,kw].  Returns (forward pack [Np,3,3,C] bf16, data-gradient pack
+    [Cp,3,3,Np] bf16) straight from one kernel (csrc/small_ops.cu)."""
+    wi, w0 = w_iconv1.detach(), w0.detach()
+    N, C = wi.shape[0], wi.shape[1]
+    Np = rows_pad or (N + 31) // 32 * 32
+    Cp = (C + 31) // 32 * 32
+    fwd = torch.empty(Np, 3, 3, C, device=wi.device, dtype=torch.bfloat16)
+    dg = torch.empty(Cp, 3, 3, Np, device=wi.device, dtype=torch.bfloat16)
+    so, sc, sh, sw = wi.stride()
+    w0m = w0.reshape(N, N)
+    assert w0m.is_contiguous() and wi.dtype == torch.float32 and w0m.dtype == torch.float32
+    _lib.check(_lib.lib().faln_fold_logit_conv(_lib.ptr(w0m), _lib.ptr(wi), so, sc, sh, sw, _lib.ptr(fwd), _lib.ptr(dg), N, C,
+                                               Np, Cp, _lib.cur_stream()), "faln_fold_logit_conv")
+    return fwd, dg
+
+
+def fold_logit_conv_bwd(gwf, w_iconv1, w0, g_w_iconv1, g_w0):
+    """Adjoint of ``fold_logit_conv``: accumulates into the gradient views g_w_iconv1 (strided) and g_w0 ([N,N,1,1])."""
+    wi, w0 = w_iconv1.detach(), w0.detach()
+    N, C = wi.shape[0], wi.shape[1]
+    gk = gwf.permute(0, 2, 3, 1)
+    assert gk.is_contiguous() and gk.shape == (N, 3, 3, C) and g_w0.is_contiguous()
+    so, sc, sh, sw = wi.stride()
+    gso, gsc, gsh, gsw = g_w_iconv1.stride()
+    _lib.check(_lib.lib().faln_fold_logit_conv_bwd(_lib.ptr(gk), _lib.ptr(w0.reshape(N, N)), _lib.ptr(wi), so, sc, sh, sw,
+                                                   _lib.ptr(g_w_iconv1), gso, gsc, gsh, gsw, _lib.ptr(g_w0), N, C,
+                                                   _lib.cur_stream()), "faln_fold_logit_conv_bwd")
+
+
+def const_channel_wgrad_into(g, value, in_hw, stride, cout, dW, channel):
+    """dW[:, channel] += weight gradient of a spatially constant input channel with per-sample value ``value`` [B]: the
+    nine border-class sums of the output gradient (one kernel) combined per tap (one kernel)."""
+    B, Cs, Hg, Wg = g.shape
+    H, W = in_hw
+    S = border_sums(g, cout)                                               # [B,3,3,C]
+    so, sc, sh, sw = dW.stride()
+    val = value.float().contiguous()
+    _lib.check(_lib.lib().faln_const_channel_wgrad(_lib.ptr(S), _lib.ptr(val), _lib.ptr(dW), so, sc, sh, sw, int(channel), B,
+                                                   cout, int(stride * (Hg - 1) + 1 > H - 1), int(stride * (Wg - 1) + 1 > W - 1),
+                                                   _lib.cur_stream()), "faln_const_channel_wgrad")
+
+
 def _nhwc(t: torch.Tensor) -> torch.Tensor:
     assert t.dtype == torch.bfloat16 and t.is_cuda
     return t.contiguous(memory_format=CL)

@@ -58,6 +58,7 @@ struct ConvParams {
   // inference epilogue of the logits layer (row kernel only): disp = sum_n d_lvl[b,n] * softmax_n(logits + bias)
   const float* disp_lvl;  // [B, Cout] disparity of each level
   float* disp_out;        // [B, 1, H, W] fp32; when set nothing else is written (the logits never reach HBM)
+  int tma_out;            // row kernel: bf16 NHWC output staged in shared memory and written by TMA (tensor map tmY)
 };
 
 // K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -90,13 +91,18 @@ struct SmemLayout {
 
 // Epilogue of CW (32 or 16) consecutive output channels of one pixel: accumulator registers r -> bias / constant-channel
 // table / accumulate / residual / activation / activation derivative -> bf16 NHWC or fp32 planar store.
+// breg: the CW bias values of this thread's channel chunk held in registers (row kernel: the chunk never changes during the
+// life of the CTA, so they are loaded once instead of CW scalar loads per tile -- measured: 121 -> see profiles/r2_*), or
+// nullptr to read p.bias per call (tile kernel: the N block changes from work item to work item).
 template <int CW>
-__device__ __forceinline__ void epilogue_store(const ConvParams& p, const uint32_t (&r)[CW], int cg, size_t pix, int b, int ho,
-                                               int wo) {
-    float v[CW];
+__device__ __forceinline__ void epilogue_values(const ConvParams& p, const uint32_t (&r)[CW], const float* breg, int cg,
+                                                size_t pix, int b, int ho, int wo, float (&v)[CW]) {
 #pragma unroll
     for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
-    if (p.bias) {
+    if (breg) {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) v[j] += breg[j];
+    } else if (p.bias) {
 #pragma unroll
       for (int j = 0; j < CW; ++j)
         if (cg + j < p.Cout) v[j] += __ldg(p.bias + cg + j);
@@ -165,6 +171,11 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, const uint32
         }
       }
     }
+}
+
+template <int CW>
+__device__ __forceinline__ void store_direct(const ConvParams& p, const float (&v)[CW], int cg, size_t pix, int b, int ho,
+                                             int wo) {
     if (p.planar) {
       float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
@@ -182,6 +193,41 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, const uint32
       }
     }
 }
+
+template <int CW>
+__device__ __forceinline__ void epilogue_store(const ConvParams& p, const uint32_t (&r)[CW], int cg, size_t pix, int b, int ho,
+                                               int wo) {
+  float v[CW];
+  epilogue_values<CW>(p, r, nullptr, cg, pix, b, ho, wo, v);
+  store_direct<CW>(p, v, cg, pix, b, ho, wo);
+}
+
+// bf16 NHWC output staged through shared memory and written by the TMA unit (row kernel).  A thread owns pixel row m of the
+// [128 px][BN ch] tile and CW consecutive channels starting at c0; the 16-byte chunks go where the tensor map's swizzle
+// (128B for 128-byte rows, 64B for 64-byte rows; a function of the shared address, tile base 1024-byte aligned) expects them,
+// which also makes the 32 lanes of a warp hit 32 different bank groups.
+template <int BN, int CW>
+__device__ __forceinline__ void stage_tile_row(unsigned char* tile, int m, int c0, const float (&v)[CW]) {
+  constexpr int kRowBytes = BN * 2;
+#pragma unroll
+  for (int q = 0; q < CW / 8; ++q) {
+    uint4 u;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+    const int chunk = c0 / 8 + q;
+    const int phys = kRowBytes == 128 ? (chunk ^ (m & 7)) : (chunk ^ ((m >> 1) & 3));
+    *reinterpret_cast<uint4*>(tile + (size_t)m * kRowBytes + phys * 16) = u;
+  }
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // Persistent, warp-specialised kernel: a CTA walks work items (tap class, N block, 128-pixel tile) with stride gridDim.x.
 //   warp 0      TMA producer: runs ahead across tiles through the STAGES-deep smem ring
@@ -349,13 +395,14 @@ struct RowSmem {
   static constexpr int kHalo = (kHaloCols * kHaloRows * BK * 2 + 1023) / 1024 * 1024;
   static constexpr int kW = BN * BK * 2;                       // one (tap, channel block) weight tile
   static constexpr int kBars = 4096;                           // barriers (first 1 KB) + disparity-epilogue exchange (3 KB)
-  static int total(int kb) { return kBars + 1024 + 9 * kb * kW + STAGES * kHalo; }
+  static constexpr int kOut = 128 * BN * 2;                    // one staged output tile [128 px][BN ch] bf16 (x2: double buffer)
+  static int total(int kb) { return kBars + 1024 + 9 * kb * kW + STAGES * kHalo + 2 * kOut; }
 };
 
 template <int BK, int BN, int STAGES>
 __global__ void __launch_bounds__(320)
 conv3x3_row_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                   const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY, const ConvParams p) {
   using SL = RowSmem<BK, BN, STAGES>;
   constexpr int kAcc = 2;
   constexpr uint32_t kTmemCols = (kAcc * BN) < 32 ? 32 : (kAcc * BN);
@@ -371,6 +418,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
   unsigned char* wsm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + SL::kBars + 1023) & ~uintptr_t(1023));
   const int kb = p.kblocks1 + p.kblocks2;
   unsigned char* stages = wsm + (size_t)9 * kb * SL::kW;      // kW is a multiple of 1024 (BN * BK * 2 >= 2048)
+  unsigned char* otile = stages + (size_t)STAGES * SL::kHalo; // 2 x kOut, 1024-byte aligned (kHalo is a multiple of 1024)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = p.tiles_w * p.H * p.B;                    // work item = (b, h, 128-pixel segment)
@@ -380,6 +428,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
     prefetch_tmap(&tmA1);
     prefetch_tmap(&tmW);
     if (p.kblocks2) prefetch_tmap(&tmA2);
+    if (p.tma_out) prefetch_tmap(&tmY);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -461,6 +510,11 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     const int m = quad * 32 + lane;
+    const bool issuer = warp == 2 && lane == 0;                 // issues the TMA stores of the staged output tiles
+    // this thread's CW output channels never change: keep their bias in registers for the life of the CTA
+    float breg[CW];
+#pragma unroll
+    for (int j = 0; j < CW; ++j) breg[j] = (p.bias && p.disp_out == nullptr && half * CW + j < p.Cout) ? __ldg(p.bias + half * CW + j) : 0.f;
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
       const int tw = w % p.tiles_w, h = (w / p.tiles_w) % p.H, b = w / (p.tiles_w * p.H);
@@ -524,8 +578,27 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[a]);
       const int cg = half * CW;
-      if (valid && cg < p.Cout) epilogue_store<CW>(p, r, cg, pix, b, h, wo);
+      if (p.tma_out) {
+        // every thread owns a row of the staged tile (rows beyond the image are clipped by the tensor map on the way out)
+        float v[CW];
+        if (valid) epilogue_values<CW>(p, r, breg, cg, pix, b, h, wo, v);
+        else {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) v[j] = 0.f;
+        }
+        unsigned char* tile = otile + (size_t)(it & 1) * SL::kOut;
+        stage_tile_row<BN, CW>(tile, m, cg, v);
+        fence_proxy_async();                                  // generic-proxy writes -> visible to the TMA (async proxy)
+        if (issuer) tma_store_wait_read0();                   // the store issued one tile ago has finished reading smem
+        named_bar_sync(1, 256);                               // (so the OTHER buffer is free for the next tile's writes)
+        if (issuer) tma_store_3d(&tmY, tile, 0, tw * kRowW, b * p.H + h);
+      } else if (valid && cg < p.Cout) {
+        float v[CW];
+        epilogue_values<CW>(p, r, breg, cg, pix, b, h, wo, v);
+        store_direct<CW>(p, v, cg, pix, b, h, wo);
+      }
     }
+    if (issuer) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -586,8 +659,22 @@ bool make_row_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, i
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// bf16 NHWC output [B*H rows][W][out_c] with a [1][128][BN] store box (rows = 128 consecutive pixels of one image row)
+bool make_out_map(CUtensorMap* m, const void* ptr, long long rows, int W, int out_c, int BN) {
+  auto fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)out_c, (cuuint64_t)W, (cuuint64_t)rows};
+  cuuint64_t strides[2] = {(cuuint64_t)out_c * 2, (cuuint64_t)W * out_c * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BN, (cuuint32_t)kRowW, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, BN == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BK, int BN, int STAGES>
-int launch_row(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, ConvParams p, cudaStream_t st) {
+int launch_row(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const CUtensorMap& ym, ConvParams p,
+               cudaStream_t st) {
   using SL = RowSmem<BK, BN, STAGES>;
   auto kern = conv3x3_row_kernel<BK, BN, STAGES>;
   const int smem = SL::total(p.kblocks1 + p.kblocks2);
@@ -606,7 +693,7 @@ int launch_row(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& 
   const long long total = (long long)p.tiles_w * p.H * p.B;
   long long grid = (long long)sm_count() * per_sm;
   if (grid > total) grid = total;
-  kern<<<(int)grid, 320, smem, st>>>(a1, a2, w, p);
+  kern<<<(int)grid, 320, smem, st>>>(a1, a2, w, ym, p);
   return after_launch("conv3x3_row_kernel");
 }
 
@@ -620,17 +707,24 @@ int try_row_kernel(const void* x, const void* x2, const void* wptr, int wrows, C
   if (p.W < 192) return 0;
   const int kb = p.kblocks1 + p.kblocks2;
   const int halo = (kHaloCols * kHaloRows * BK * 2 + 1023) / 1024 * 1024;
-  if (2048 + 9 * kb * wrows * BK * 2 + 2 * halo > 225 * 1024) return 0;
-  CUtensorMap a1, a2, wm;
+  if (2048 + 4096 + 9 * kb * wrows * BK * 2 + (BK == 64 ? 2 : 3) * halo + 2 * 128 * wrows * 2 > 226 * 1024) return 0;
+  CUtensorMap a1, a2, wm, ym;
   if (!make_row_map(&a1, x, p.B, p.H, p.W, p.C1, BK) || !make_w_map(&wm, wptr, wrows, 9 * p.Cin, BK, wrows) ||
       (x2 && !make_row_map(&a2, x2, p.B, p.H, p.W, C2, BK))) {
     set_error("conv3x3 row kernel: cuTensorMapEncodeTiled failed");
     return FALN_ERR_LAUNCH;
   }
   if (!x2) a2 = a1;
+  // staged TMA store of the bf16 NHWC output: whole-chunk writes only (Cout == the N tile), 16-byte aligned rows
+  static const bool no_tma_out = getenv("FALN_CONV_NO_TMA_OUT") != nullptr;
+  p.tma_out = 0;
+  ym = a1;
+  if (!no_tma_out && !p.planar && !p.disp_out && p.Cout == wrows && p.out_c % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && make_out_map(&ym, p.out, (long long)p.B * p.H, p.W, p.out_c, wrows))
+    p.tma_out = 1;
   int rc;
-  if (BK == 64) rc = wrows == 64 ? launch_row<64, 64, 2>(a1, a2, wm, p, st) : launch_row<64, 32, 2>(a1, a2, wm, p, st);
-  else rc = wrows == 64 ? launch_row<32, 64, 3>(a1, a2, wm, p, st) : launch_row<32, 32, 3>(a1, a2, wm, p, st);
+  if (BK == 64) rc = wrows == 64 ? launch_row<64, 64, 2>(a1, a2, wm, ym, p, st) : launch_row<64, 32, 2>(a1, a2, wm, ym, p, st);
+  else rc = wrows == 64 ? launch_row<32, 64, 3>(a1, a2, wm, ym, p, st) : launch_row<32, 32, 2>(a1, a2, wm, ym, p, st);
   return rc == 0 ? 1 : rc;
 }
 

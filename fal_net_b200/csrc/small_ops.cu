@@ -1,0 +1,233 @@
+// small_ops.cu -- the small device-side helpers that keep library (ATen / cuBLAS) launches out of a training step.
+//
+// Round 1's launch list (profiles/r1e_launches_stage1.txt) showed ~75 ATen launches per Stage-1 step (258 per Stage-2
+// step): exp / log / linspace of the level tables recomputed every forward, the logit-fold einsums on cuBLAS / cutlass SIMT
+// sgemm + magma, zero-fills, strided copies and a dozen one-element multiplies / adds of the loss arithmetic.  Each is a
+// few microseconds of a serial launch chain.  The kernels here replace them one for one:
+//
+//   level_tables_kernel      d_n, x_of_n of /root/reference/models/FAL_netB.py:204-205,224-225,241 (same fp32 op order)
+//   fold_logit_conv_kernel   W' = W0 . W_iconv1 (:174,190,215 are linear with nothing between them), written directly as the
+//                            bf16 forward pack [Np,3,3,C] and the data-gradient pack [C,3,3,Np]
+//   fold_grad_kernel         the adjoint: dW0 = <gW', W_iconv1>, dW_iconv1 = W0^T gW', accumulated into the gradient arena
+//   const_table_kernel       border-class sums of the constant max_disp/100 channel's weights (:145,208-209)
+//   const_wgrad_kernel       weight gradient of that channel from the nine border-class sums of the output gradient
+//   scalar_combine / scale   loss = sum_i w_i * term_i and its adjoint (Train_Stage1_K.py:258, Train_Stage2_K.py:309-327)
+#include "common.cuh"
+
+namespace faln {
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Level tables.  The reference evaluates, per level n (c = n / (N - 1), a Python double; c - 1 reaches the fp32 kernel
+// rounded to fp32):  d = max_disp * exp(log(max_disp / min_disp) * (c - 1)),
+//                    x_of = x_pix_max * exp(log(x_pix_max / x_pix_min) * (c - 1)),  x_pix_* = 2 * *_disp / W
+// as separate fp32 ATen kernels, i.e. every operation rounds to fp32: replayed here with explicit _rn intrinsics (no FMA
+// contraction) and the same libm entry points ATen's CUDA kernels call (expf / logf, not the fast intrinsics).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void level_tables_kernel(const float* __restrict__ min_disp, const float* __restrict__ max_disp,
+                                    float* __restrict__ d, float* __restrict__ xo, int B, int N, float Wf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N) return;
+  const int b = i / N, n = i % N;
+  const float cm1 = (float)((double)n / (double)(N - 1) - 1.0);
+  const float mn = min_disp[b], mx = max_disp[b];
+  const float xmin = __fdiv_rn(__fmul_rn(2.f, mn), Wf), xmax = __fdiv_rn(__fmul_rn(2.f, mx), Wf);
+  d[i] = __fmul_rn(mx, expf(__fmul_rn(logf(__fdiv_rn(mx, mn)), cm1)));
+  xo[i] = __fmul_rn(xmax, expf(__fmul_rn(logf(__fdiv_rn(xmax, xmin)), cm1)));
+}
+
+// element (o, c, kh, kw) of a 4-D weight given its four strides (the optimiser arena stores 3x3 weights KRSC, plain
+// parameters are NCHW-contiguous: both are strided views of the same logical tensor)
+struct W4 {
+  long long so, sc, sh, sw;
+  __device__ __forceinline__ long long at(int o, int c, int kh, int kw) const { return o * so + c * sc + kh * sh + kw * sw; }
+};
+
+// W'[o, c, t] = sum_m W0[o, m] * Wi1[m, c, t];  fwd pack [Np, 9, C] bf16 (rows >= N zero), dgrad pack [Cp, 9, Np] bf16
+// (rows >= C zero; columns >= N zero), plus the fp32 folded weight [N, C, 9] (tape, for the backward's algebra).
+// One thread per (c, t) column; the N x N matrix W0 is staged in shared memory.
+__global__ void __launch_bounds__(128) fold_logit_conv_kernel(const float* __restrict__ w0, const float* __restrict__ wi1, W4 s,
+                                                              __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dg,
+                                                              int N, int C, int Np, int Cp) {
+  extern __shared__ float sw0[];   // [N][N]
+  for (int i = threadIdx.x; i < N * N; i += blockDim.x) sw0[i] = w0[i];
+  __syncthreads();
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;   // c * 9 + t
+  if (col >= Cp * 9) return;
+  const int c = col / 9, t = col % 9, kh = t / 3, kw = t % 3;
+  if (c >= C) {
+    for (int o = 0; o < Np; ++o) dg[((long long)c * 9 + t) * Np + o] = __float2bfloat16(0.f);
+    return;
+  }
+  for (int o = 0; o < Np; ++o) {
+    float acc = 0.f;
+    if (o < N)
+      for (int m = 0; m < N; ++m) acc = fmaf(sw0[o * N + m], __ldg(wi1 + s.at(m, c, kh, kw)), acc);
+    const __nv_bfloat16 h = __float2bfloat16(acc);
+    fwd[((long long)o * 9 + t) * C + c] = h;
+    dg[((long long)c * 9 + t) * Np + o] = h;
+  }
+}
+
+// gwf [N, 9, C] fp32 (KRSC, what the weight-gradient kernel wrote for the folded layer).
+//   blocks [0, nA):   dWi1[m, c, t] += sum_o W0[o, m] * gwf[o, t, c]        (one thread per (c, t) column)
+//   blocks [nA, ..):  dW0[o, m]    += sum_{c,t} gwf[o, t, c] * Wi1[m, c, t]  (one warp per (o, m) pair)
+__global__ void __launch_bounds__(128) fold_grad_kernel(const float* __restrict__ gwf, const float* __restrict__ w0,
+                                                        const float* __restrict__ wi1, W4 s, float* __restrict__ g_wi1, W4 gs,
+                                                        float* __restrict__ g_w0, int N, int C, int nA) {
+  if ((int)blockIdx.x < nA) {
+    extern __shared__ float sw0[];
+    for (int i = threadIdx.x; i < N * N; i += blockDim.x) sw0[i] = w0[i];
+    __syncthreads();
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= C * 9) return;
+    const int c = col / 9, t = col % 9, kh = t / 3, kw = t % 3;
+    for (int m = 0; m < N; ++m) {
+      float acc = 0.f;
+      for (int o = 0; o < N; ++o) acc = fmaf(sw0[o * N + m], __ldg(gwf + ((long long)o * 9 + t) * C + c), acc);
+      g_wi1[gs.at(m, c, kh, kw)] += acc;
+    }
+    return;
+  }
+  const int pair = (blockIdx.x - nA) * 4 + (threadIdx.x >> 5);
+  if (pair >= N * N) return;
+  const int o = pair / N, m = pair % N, lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int i = lane; i < 9 * C; i += 32) {
+    const int t = i / C, c = i % C;
+    acc = fmaf(__ldg(gwf + (long long)o * 9 * C + i), __ldg(wi1 + s.at(m, c, t / 3, t % 3)), acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) g_w0[pair] += acc;
+}
+
+// ctab[cls, o] = sum over the taps of border class cls = rc * 4 + cc (bit0: first tap outside, bit1: last tap outside) that
+// stay inside the image of w[o, ch, kh, kw]
+__global__ void const_table_kernel(const float* __restrict__ w, W4 s, int ch, float* __restrict__ ctab, int Cout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 16 * Cout) return;
+  const int cls = i / Cout, o = i % Cout, rc = cls >> 2, cc = cls & 3;
+  float acc = 0.f;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      const bool out = (kh == 0 && (rc & 1)) || (kh == 2 && (rc & 2)) || (kw == 0 && (cc & 1)) || (kw == 2 && (cc & 2));
+      if (!out) acc += __ldg(w + s.at(o, ch, kh, kw));
+    }
+  ctab[i] = acc;
+}
+
+// dW[o, ch, kh, kw] += sum_b value[b] * sum over the border classes (r, c) whose tap (kh, kw) lands inside the image of
+// S[b, r, c, o]   (S = nine border-class sums of the output gradient, csrc/conv_aux.cu border_sum_kernel)
+__global__ void const_wgrad_kernel(const float* __restrict__ S, const float* __restrict__ value, float* __restrict__ dW, W4 gs,
+                                   int ch, int B, int Cout, int last_row_clipped, int last_col_clipped) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * 9) return;
+  const int o = i / 9, kh = (i % 9) / 3, kw = i % 3;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float sb = 0.f;
+    for (int r = 0; r < 3; ++r) {
+      const bool vr = !(kh == 0 && r == 0) && !(kh == 2 && r == 2 && last_row_clipped);
+      if (!vr) continue;
+      for (int c = 0; c < 3; ++c) {
+        const bool vc = !(kw == 0 && c == 0) && !(kw == 2 && c == 2 && last_col_clipped);
+        if (vc) sb += __ldg(S + (((long long)b * 3 + r) * 3 + c) * Cout + o);
+      }
+    }
+    acc = fmaf(__ldg(value + b), sb, acc);
+  }
+  dW[gs.at(o, ch, kh, kw)] += acc;
+}
+
+struct Terms {
+  const float* p[8];
+  float w[8];
+  int n;
+};
+__global__ void scalar_combine_kernel(Terms t, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float acc = 0.f;
+    for (int i = 0; i < t.n; ++i) acc = fmaf(t.w[i], *t.p[i], acc);
+    *out = acc;
+  }
+}
+__global__ void scalar_scale_kernel(const float* __restrict__ g, Terms t, float* __restrict__ out) {
+  if (threadIdx.x < t.n && blockIdx.x == 0) out[threadIdx.x] = t.w[threadIdx.x] * (*g);
+}
+
+}  // namespace
+}  // namespace faln
+
+using namespace faln;
+
+extern "C" int faln_level_tables(const float* min_disp, const float* max_disp, float* d_lvl, float* x_of, int B, int N, int W,
+                                 faln_stream_t stream) {
+  FALN_REQUIRE(min_disp && max_disp && d_lvl && x_of && B > 0 && N >= 2 && W > 0, "faln_level_tables: bad argument");
+  level_tables_kernel<<<(B * N + 127) / 128, 128, 0, as_stream(stream)>>>(min_disp, max_disp, d_lvl, x_of, B, N, (float)W);
+  return after_launch("level_tables_kernel");
+}
+
+extern "C" int faln_fold_logit_conv(const float* w0, const float* w_iconv1, long long so, long long sc, long long sh,
+                                    long long sw, void* fwd_pack, void* dgrad_pack, int N, int C, int Np, int Cp,
+                                    faln_stream_t stream) {
+  FALN_REQUIRE(w0 && w_iconv1 && fwd_pack && dgrad_pack && N > 0 && N <= 104 && C > 0 && Np >= N && Cp >= C,
+               "faln_fold_logit_conv: bad argument (N <= 104)");
+  // zero rows [N, Np) of the forward pack
+  if (Np > N)
+    FALN_REQUIRE(cudaMemsetAsync(static_cast<__nv_bfloat16*>(fwd_pack) + (size_t)N * 9 * C, 0, (size_t)(Np - N) * 9 * C * 2,
+                                 as_stream(stream)) == cudaSuccess, "faln_fold_logit_conv: memset failed");
+  const W4 s{so, sc, sh, sw};
+  fold_logit_conv_kernel<<<(Cp * 9 + 127) / 128, 128, (size_t)N * N * 4, as_stream(stream)>>>(
+      w0, w_iconv1, s, static_cast<__nv_bfloat16*>(fwd_pack), static_cast<__nv_bfloat16*>(dgrad_pack), N, C, Np, Cp);
+  return after_launch("fold_logit_conv_kernel");
+}
+
+extern "C" int faln_fold_logit_conv_bwd(const float* gwf, const float* w0, const float* w_iconv1, long long so, long long sc,
+                                        long long sh, long long sw, float* g_w_iconv1, long long gso, long long gsc,
+                                        long long gsh, long long gsw, float* g_w0, int N, int C, faln_stream_t stream) {
+  FALN_REQUIRE(gwf && w0 && w_iconv1 && g_w_iconv1 && g_w0 && N > 0 && N <= 104 && C > 0, "faln_fold_logit_conv_bwd: bad argument");
+  const W4 s{so, sc, sh, sw}, gs{gso, gsc, gsh, gsw};
+  const int nA = (C * 9 + 127) / 128, nB = (N * N + 3) / 4;
+  fold_grad_kernel<<<nA + nB, 128, (size_t)N * N * 4, as_stream(stream)>>>(gwf, w0, w_iconv1, s, g_w_iconv1, gs, g_w0, N, C, nA);
+  return after_launch("fold_grad_kernel");
+}
+
+extern "C" int faln_const_channel_table(const float* w, long long so, long long sc, long long sh, long long sw, int channel,
+                                        float* ctab, int Cout, faln_stream_t stream) {
+  FALN_REQUIRE(w && ctab && Cout > 0 && channel >= 0, "faln_const_channel_table: bad argument");
+  const W4 s{so, sc, sh, sw};
+  const_table_kernel<<<(16 * Cout + 127) / 128, 128, 0, as_stream(stream)>>>(w, s, channel, ctab, Cout);
+  return after_launch("const_table_kernel");
+}
+
+extern "C" int faln_const_channel_wgrad(const float* border_sums, const float* value, float* dW, long long so, long long sc,
+                                        long long sh, long long sw, int channel, int B, int Cout, int last_row_clipped,
+                                        int last_col_clipped, faln_stream_t stream) {
+  FALN_REQUIRE(border_sums && value && dW && B > 0 && Cout > 0 && channel >= 0, "faln_const_channel_wgrad: bad argument");
+  const W4 gs{so, sc, sh, sw};
+  const_wgrad_kernel<<<(Cout * 9 + 127) / 128, 128, 0, as_stream(stream)>>>(border_sums, value, dW, gs, channel, B, Cout,
+                                                                           last_row_clipped, last_col_clipped);
+  return after_launch("const_wgrad_kernel");
+}
+
+extern "C" int faln_scalar_combine(const float* const* terms, const float* weights, int n, float* out, faln_stream_t stream) {
+  FALN_REQUIRE(terms && weights && out && n > 0 && n <= 8, "faln_scalar_combine: 1..8 terms");
+  Terms t{};
+  t.n = n;
+  for (int i = 0; i < n; ++i) {
+    FALN_REQUIRE(terms[i] != nullptr, "faln_scalar_combine: null term");
+    t.p[i] = terms[i];
+    t.w[i] = weights[i];
+  }
+  scalar_combine_kernel<<<1, 32, 0, as_stream(stream)>>>(t, out);
+  return after_launch("scalar_combine_kernel");
+}
+
+extern "C" int faln_scalar_scale(const float* g, const float* weights, int n, float* out, faln_stream_t stream) {
+  FALN_REQUIRE(g && weights && out && n > 0 && n <= 8, "faln_scalar_scale: 1..8 terms");
+  Terms t{};
+  t.n = n;
+  for (int i = 0; i < n; ++i) t.w[i] = weights[i];
+  scalar_scale_kernel<<<1, 32, 0, as_stream(stream)>>>(g, t, out);
+  return after_launch("scalar_scale_kernel");
+}

@@ -109,6 +109,47 @@ class GpuStereoAugment:
     def sample(self, h, w, rng=_random, nprng=np.random):
         return sample_params(h, w, self.size, rng=rng, nprng=nprng, **self.cfg)
 
+    def plan(self, shapes, params, ptrs=None):
+        """Host half of a batch: per-image descriptors, the packed coefficient tables and value tables.
+        shapes: [(h, w)] per pair; params: [AugParams]; ptrs: [(left_ptr, right_ptr)] device addresses (0 when only
+        planning).  Returns dict(descs, tabs int32, luts float32 [n,3,256], max_rows, n_img)."""
+        th, tw = self.size
+        B = len(params)
+        descs = (_Desc * (2 * B))()
+        tabs, luts = [], []
+        t_off = l_off = 0
+        max_rows = 1
+        for i, p in enumerate(params):
+            h, w = shapes[i]
+            rw, rh = int(w * p.factor), int(h * p.factor)
+            bx, kx = pil_bicubic_tables(w, rw, p.x1, tw)
+            by, ky = pil_bicubic_tables(h, rh, p.y1, th)
+            row0 = int(by[:, 0].min())
+            rows = int((by[:, 0] + by[:, 1]).max()) - row0
+            max_rows = max(max_rows, rows)
+            x_tab = t_off
+            tabs += [bx.reshape(-1), kx.reshape(-1)]
+            t_off += bx.size + kx.size
+            y_tab = t_off
+            tabs += [by.reshape(-1), ky.reshape(-1)]
+            t_off += by.size + ky.size
+            for v in range(2):
+                src_view = (1 - v) if p.swap_lr else v               # listdataset_train.py:75-82: random view order
+                # RandomHorizontalFlip mirrors both views AND swaps them (data_transforms.py:100-101): view v -> slot 1-v;
+                # the per-channel brightness factors are drawn per OUTPUT slot, after the swap (:157-160)
+                slot = (1 - v) if p.flip else v
+                d = descs[2 * i + v]
+                d.src = 0 if ptrs is None else int(ptrs[i][src_view])
+                d.H, d.W, d.row0, d.rows = h, w, row0, rows
+                d.x_tab, d.ksx, d.y_tab, d.ksy = x_tab, kx.shape[1], y_tab, ky.shape[1]
+                d.flip = int(p.flip)
+                d.dst = slot * B + i
+                d.lut = l_off
+                luts.append(value_table(p.gamma, p.bright, None if p.cbright is None else p.cbright[slot], self.mean))
+                l_off += 768
+        return dict(descs=descs, tabs=np.concatenate(tabs).astype(np.int32), luts=torch.stack(luts), max_rows=max_rows,
+                    n_img=2 * B)
+
     def __call__(self, lefts, rights, params=None, rng=_random, nprng=np.random):
         """lefts / rights: sequences of uint8 [H,W,3] CUDA tensors (decoded images).  Returns (left, right) fp32
         [B,3,th,tw] and the parameters used.  ``params``: explicit list of AugParams (else drawn per pair)."""
@@ -117,47 +158,18 @@ class GpuStereoAugment:
         dev = lefts[0].device
         if not lefts[0].is_cuda:
             raise RuntimeError("GpuStereoAugment needs CUDA tensors (no CPU pixel path)")
+        for a, b in zip(lefts, rights):
+            assert a.dtype == b.dtype == torch.uint8 and a.dim() == 3 and a.shape == b.shape and a.shape[2] == 3
+            assert a.is_contiguous() and b.is_contiguous()
         if params is None:
             params = [self.sample(lefts[i].shape[0], lefts[i].shape[1], rng, nprng) for i in range(B)]
-        descs = (_Desc * (2 * B))()
-        tabs, luts, keep = [], [], []
-        t_off = l_off = 0
-        max_rows = 1
-        for i, p in enumerate(params):
-            views = [lefts[i], rights[i]]
-            if p.swap_lr:
-                views = views[::-1]
-            for v, img in enumerate(views):
-                assert img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 3 and img.is_contiguous()
-                h, w = img.shape[0], img.shape[1]
-                rw, rh = int(w * p.factor), int(h * p.factor)
-                bx, kx = pil_bicubic_tables(w, rw, p.x1, tw)
-                by, ky = pil_bicubic_tables(h, rh, p.y1, th)
-                row0 = int(by[:, 0].min())
-                rows = int((by[:, 0] + by[:, 1]).max()) - row0
-                max_rows = max(max_rows, rows)
-                d = descs[2 * i + v]
-                d.src, d.H, d.W, d.row0, d.rows = img.data_ptr(), h, w, row0, rows
-                d.x_tab, d.ksx = t_off, kx.shape[1]
-                tabs += [bx.reshape(-1), kx.reshape(-1)]
-                t_off += bx.size + kx.size
-                d.y_tab, d.ksy = t_off, ky.shape[1]
-                tabs += [by.reshape(-1), ky.reshape(-1)]
-                t_off += by.size + ky.size
-                d.flip = int(p.flip)
-                # after a flip the reference also swaps the views (data_transforms.py:100-101): view v lands in slot 1-v
-                slot = (1 - v) if p.flip else v
-                d.dst = slot * B + i
-                d.lut = l_off
-                luts.append(value_table(p.gamma, p.bright, None if p.cbright is None else p.cbright[v], self.mean))
-                l_off += 768
-                keep.append(img)
-        tab_np = np.concatenate(tabs).astype(np.int32)
-        lut_t = torch.stack(luts).reshape(-1)
-        desc_t = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8)
-        tab_d = torch.from_numpy(tab_np).pin_memory().to(dev, non_blocking=True)
-        lut_d = lut_t.pin_memory().to(dev, non_blocking=True)
+        pl = self.plan([(t.shape[0], t.shape[1]) for t in lefts], params,
+                       [(lefts[i].data_ptr(), rights[i].data_ptr()) for i in range(B)])
+        desc_t = torch.frombuffer(bytearray(bytes(pl["descs"])), dtype=torch.uint8)
+        tab_d = torch.from_numpy(pl["tabs"]).pin_memory().to(dev, non_blocking=True)
+        lut_d = pl["luts"].reshape(-1).pin_memory().to(dev, non_blocking=True)
         desc_d = desc_t.pin_memory().to(dev, non_blocking=True)
+        max_rows = pl["max_rows"]
         stride = max_rows * tw * 3
         inter = torch.empty(2 * B * stride, device=dev, dtype=torch.uint8)
         out = torch.empty(2 * B, 3, th, tw, device=dev, dtype=torch.float32)

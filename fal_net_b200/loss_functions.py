@@ -173,13 +173,46 @@ vgg = _LazyVgg()
 # ------------------------------------------------------------------------------------------------
 # public loss functions (reference names)
 # ------------------------------------------------------------------------------------------------
+class _Combine(torch.autograd.Function):
+    """sum_i w_i * term_i over 0-d device scalars in ONE launch (and one for the adjoint) instead of a chain of one-element
+    ATen multiplies / adds -- the loss arithmetic of Train_Stage1_K.py:258 / Train_Stage2_K.py:309-327."""
+
+    @staticmethod
+    def forward(ctx, weights, *terms):
+        import ctypes
+        n = len(terms)
+        ctx.weights = weights
+        ts = [t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous() for t in terms]
+        out = torch.empty((), device=ts[0].device, dtype=torch.float32)
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])
+        ws = (ctypes.c_float * n)(*weights)
+        _lib.check(_lib.lib().faln_scalar_combine(ptrs, ws, n, _lib.ptr(out), _lib.cur_stream()), "faln_scalar_combine")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes
+        n = len(ctx.weights)
+        buf = torch.empty(n, device=g.device, dtype=torch.float32)
+        ws = (ctypes.c_float * n)(*ctx.weights)
+        _lib.check(_lib.lib().faln_scalar_scale(_lib.ptr(g.contiguous().float()), ws, n, _lib.ptr(buf), _lib.cur_stream()),
+                   "faln_scalar_scale")
+        return (None,) + tuple(buf[i] for i in range(n))
+
+
+def combine(pairs):
+    """sum of weight * term over ``pairs`` = [(weight, 0-d CUDA tensor or Python number)]; numbers fold into... nothing:
+    a numeric term must be 0 (an absent loss) and is skipped."""
+    live = [(float(w), t) for w, t in pairs if torch.is_tensor(t)]
+    assert all((not torch.is_tensor(t)) and t == 0 for _, t in pairs if not torch.is_tensor(t)), "numeric terms must be 0"
+    assert 1 <= len(live) <= 8
+    return _Combine.apply(tuple(w for w, _ in live), *[t for _, t in live])
+
+
 def perceptual_loss(out_vgg, label_vgg, layer=None):
     if layer is not None:
         return _MseBf16.apply(out_vgg[layer], label_vgg[layer])
-    l_p = 0
-    for i in range(3):
-        l_p = l_p + _MseBf16.apply(out_vgg[i], label_vgg[i])
-    return l_p
+    return combine([(1.0, _MseBf16.apply(out_vgg[i], label_vgg[i])) for i in range(3)])
 
 
 def rec_loss_fnc(mask, synth, label, vgg_label, a_p, flip_x=False):
@@ -188,7 +221,8 @@ def rec_loss_fnc(mask, synth, label, vgg_label, a_p, flip_x=False):
     want_blend = a_p > 0 and vgg_label is not None
     val, blend = _RecL1.apply(synth, label, m, want_blend, bool(flip_x))
     if want_blend:
-        val = val + a_p * perceptual_loss(vgg(blend), vgg_label)
+        out_vgg = vgg(blend)
+        val = combine([(1.0, val)] + [(a_p, _MseBf16.apply(out_vgg[i], vgg_label[i])) for i in range(3)])
     return val
 
 

@@ -12,23 +12,26 @@ import torch.nn.functional as F
 from . import _lib
 
 
-_CM1_CACHE: dict = {}
-
-
 def level_tables(min_disp: torch.Tensor, max_disp: torch.Tensor, no_levels: int, W: int):
-    """d [B,N] (pixels) and x_of [B,N] (normalised grid units) of the exponential disparity levels.
+    """d [B,N] (pixels) and x_of [B,N] (normalised grid units) of the exponential disparity levels: the fp32 expressions of
+    /root/reference/models/FAL_netB.py:204-205,224-225,241 for all levels in ONE launch (``faln_level_tables`` replays the
+    reference's op order with every operation rounded to fp32; the reference launches ~6 tiny ATen kernels per level per
+    loop, ~300 per forward).  Bit-compared with the torch expressions on the device in tests/test_med_gpu.py."""
+    B = min_disp.shape[0]
+    mn = _lib.f32c(min_disp.reshape(B), "min_disp")
+    mx = _lib.f32c(max_disp.reshape(B), "max_disp")
+    d = torch.empty(B, no_levels, device=mn.device, dtype=torch.float32)
+    xo = torch.empty(B, no_levels, device=mn.device, dtype=torch.float32)
+    _lib.check(_lib.lib().faln_level_tables(_lib.ptr(mn), _lib.ptr(mx), _lib.ptr(d), _lib.ptr(xo), B, no_levels, W,
+                                            _lib.cur_stream()), "faln_level_tables")
+    return d, xo
 
-    Same fp32 expressions as /root/reference/models/FAL_netB.py:204-205,224-225,241, evaluated for all levels
-    at once (the reference launches ~6 tiny kernels per level per loop: ~300 launches per forward).  The
-    per-level factor (c - 1), a Python double in the reference, reaches the fp32 kernel rounded to fp32 --
-    which is what the cached fp32 vector below holds, so the tables are bit-identical to the per-level loop
-    (checked on CPU against the oracle in tests/test_oracle_golden.py and on the GPU in tests/test_med_gpu.py)."""
-    key = (no_levels, str(min_disp.device))
-    cm1 = _CM1_CACHE.get(key)
-    if cm1 is None:
-        cm1 = torch.tensor([n / (no_levels - 1) - 1 for n in range(no_levels)], dtype=torch.float64).to(torch.float32)
-        cm1 = cm1.to(min_disp.device)
-        _CM1_CACHE[key] = cm1
+
+def level_tables_torch(min_disp: torch.Tensor, max_disp: torch.Tensor, no_levels: int, W: int):
+    """The same tables with the reference's own torch expressions, vectorised over the levels (the per-level factor (c - 1),
+    a Python double in the reference, reaches the fp32 kernel rounded to fp32).  Test reference for ``level_tables``."""
+    cm1 = torch.tensor([n / (no_levels - 1) - 1 for n in range(no_levels)], dtype=torch.float64).to(torch.float32)
+    cm1 = cm1.to(min_disp.device)
     x_pix_min = 2 * min_disp / W
     x_pix_max = 2 * max_disp / W
     d = max_disp * torch.exp(torch.log(max_disp / min_disp) * cm1)

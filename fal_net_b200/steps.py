@@ -31,7 +31,7 @@ def stage1_loss(model, left, right, min_disp, max_disp, a_p=0.01, a_sm=0.2 * 2 /
     if a_sm > 0:
         # the 20 % left dis-occluded band has no supervision (Train_Stage1_K.py:254-255)
         sm = LF.smoothness(left, ldisp, gamma=2, window=(int(0.20 * W), W))
-    loss = rec + a_sm * sm
+    loss = LF.combine([(1.0, rec), (a_sm, sm)])
     return loss, rec, sm, rpan, ldisp
 
 
@@ -67,17 +67,17 @@ def stage2_loss(model, fix_model, left, right, min_disp, max_disp, a_p=0.01, a_s
     else:
         O_L = O_R = 1
 
-    rec = (LF.rec_loss_fnc(O_R, rpan, right, vgg_right, a_p) +
-           LF.rec_loss_fnc(O_L, lpan_f, left, vgg_left, a_p, flip_x=True)) / 2
+    rec = LF.combine([(0.5, LF.rec_loss_fnc(O_R, rpan, right, vgg_right, a_p)),
+                      (0.5, LF.rec_loss_fnc(O_L, lpan_f, left, vgg_left, a_p, flip_x=True))])
     sm = 0
     if a_sm > 0:
-        sm = (LF.smoothness(left, ldisp, gamma=2, window=(c20, W)) +
-              LF.smoothness(right, rdisp_f, gamma=2, window=(0, c80), flip_x=True)) / 2
+        sm = LF.combine([(0.5, LF.smoothness(left, ldisp, gamma=2, window=(c20, W))),
+                         (0.5, LF.smoothness(right, rdisp_f, gamma=2, window=(0, c80), flip_x=True))])
     mirror = 0
     if a_mr > 0:
-        mirror = (LF.mirror_loss(ldisp, mldisp, O_L, (c20, W)) +
-                  LF.mirror_loss(rdisp_f, mrdisp, O_R, (0, c80), flip_x=True)) / 2
-    loss = rec + a_sm * sm + a_mr * mirror
+        mirror = LF.combine([(0.5, LF.mirror_loss(ldisp, mldisp, O_L, (c20, W))),
+                             (0.5, LF.mirror_loss(rdisp_f, mrdisp, O_R, (0, c80), flip_x=True))])
+    loss = LF.combine([(1.0, rec), (a_sm, sm), (a_mr, mirror)])
     return dict(loss=loss, rec=rec, sm=sm, mirror=mirror, rpan=rpan, lpan_f=lpan_f, ldisp=ldisp, rdisp_f=rdisp_f,
                 O_L=O_L, O_R=O_R)
 
@@ -97,12 +97,13 @@ def stage1_slow_loss(model, left, right, min_disp, max_disp, a_p=0.01, a_sm=0.2 
     if a_p > 0:
         with torch.no_grad():
             vgg_right, vgg_left = vgg(right), vgg(left)
-    rec = (LF.rec_loss_fnc(1, rpan, right, vgg_right, a_p) + LF.rec_loss_fnc(1, lpan_f, left, vgg_left, a_p, flip_x=True)) / 2
+    rec = LF.combine([(0.5, LF.rec_loss_fnc(1, rpan, right, vgg_right, a_p)),
+                      (0.5, LF.rec_loss_fnc(1, lpan_f, left, vgg_left, a_p, flip_x=True))])
     sm = 0
     if a_sm > 0:
-        sm = (LF.smoothness(left, ldisp, gamma=2, window=(c20, W)) +
-              LF.smoothness(right, rdisp_f, gamma=2, window=(0, c80), flip_x=True)) / 2
-    loss = rec + a_sm * sm
+        sm = LF.combine([(0.5, LF.smoothness(left, ldisp, gamma=2, window=(c20, W))),
+                         (0.5, LF.smoothness(right, rdisp_f, gamma=2, window=(0, c80), flip_x=True))])
+    loss = LF.combine([(1.0, rec), (a_sm, sm)])
     return dict(loss=loss, rec=rec, sm=sm, rpan=rpan, lpan_f=lpan_f, ldisp=ldisp, rdisp_f=rdisp_f)
 
 

@@ -23,8 +23,6 @@ from . import optim
 class FlatAdamDDP:
     def __init__(self, model, lr, betas=(0.5, 0.999), eps=1e-8, weight_decay=0.0, bias_decay=0.0,
                  bucket_mb: float = 16.0, process_group=None, overlap=True, _update=None):
-        if weight_decay != bias_decay:
-            raise NotImplementedError("weight_decay != bias_decay is not supported by the flat arena (both default to 0)")
         named = model.used_parameters() if hasattr(model, "used_parameters") else list(model.named_parameters())
         named = [(n, p) for n, p in named if p.requires_grad]
         # arena order = reverse registration order ~ the order in which backward produces gradients
@@ -72,6 +70,18 @@ class FlatAdamDDP:
             self._max_tiles = max_tiles
             self.sync_shadow()
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        # The reference's two Adam param groups (Train_Stage1_K.py:177-181: bias_parameters with bias_decay, weight_parameters
+        # with weight_decay).  Equal decays (the default, both 0) ride in the fused kernel's scalar; distinct decays use a
+        # per-element decay arena folded into the gradient before the kernel (g += wd_elem * p, Adam's L2 form).
+        self.wdv = None
+        if weight_decay != bias_decay:
+            self.wd = 0.0
+            self.wdv = torch.zeros(self.n, device=dev, dtype=torch.float32)
+            for i, nme in enumerate(self.names):
+                n_i = 1
+                for d_ in self.shapes[i]:
+                    n_i *= d_
+                self.wdv[offs[i]:offs[i] + n_i] = bias_decay if "bias" in nme else weight_decay
         self.t = 0
         # device-side copy of (lr, step) for CUDA-graph replay (optim.adam_step_dev_); None on the CPU test path
         self.hp = torch.tensor([lr, 0.0, 0.0, 0.0], device=dev, dtype=torch.float32) if dev.type == "cuda" else None
@@ -129,6 +139,8 @@ class FlatAdamDDP:
                    "faln_f32_to_bf16")
         self._repack_dgrad()
         self._versions = [p._version for p in self.params]
+        from . import conv
+        conv.invalidate_packed_weights()               # per-parameter packs cached by backbone._cached are stale now
 
     def _repack_dgrad(self):
         if self._jobs is None:
@@ -222,6 +234,8 @@ class FlatAdamDDP:
             else:
                 dist.all_reduce(self.g, op=dist.ReduceOp.SUM, group=self.pg)
         self.t += 1
+        if self.wdv is not None:                       # distinct decays: the kernel scales g by 1/world afterwards
+            self.g.addcmul_(self.wdv, self.p, value=float(self.world))
         if self.device_hp:
             optim.adam_step_dev_(self.p, self.g, self.m, self.v, self.hp, self.w16, beta1=self.betas[0], beta2=self.betas[1],
                                  eps=self.eps, weight_decay=self.wd, grad_scale=1.0 / self.world)
@@ -260,20 +274,32 @@ class GraphedStep:
         self.right.copy_(right)
         opt.device_hp = True
         opt.hp[1:2].fill_(float(opt.t))
+        # Warm-up (allocator, lazy inits, NCCL) runs real steps: snapshot the optimiser state and put it back afterwards, so
+        # capturing a graph does not train the model (three silent Adam updates on the first batch).
+        snap = [t.clone() for t in (opt.p, opt.m, opt.v, opt.hp)] if warmup > 0 else None
+        t0 = opt.t
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):                    # warm-up on a side stream (allocator, lazy inits, NCCL)
+        with torch.cuda.stream(side):                    # warm-up on a side stream
             for _ in range(warmup):
                 self._body()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if snap is not None:
+            for dst, src in zip((opt.p, opt.m, opt.v, opt.hp), snap):
+                dst.copy_(src)
+            opt.t = t0
+            opt.sync_shadow()
+            torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         # FALN_MAIN_PRIORITY=1: capture on a high-priority stream, so the kernels of the critical (forward / data-gradient)
         # chain are scheduled ahead of the parameter-gradient work on the default-priority side stream
         prio = int(os.environ.get("FALN_MAIN_PRIORITY", "0"))
         cap_stream = torch.cuda.Stream(priority=-1) if prio else None
+        t_cap = opt.t
         with torch.cuda.graph(self.graph, stream=cap_stream):
             self.loss = self._body()
+        opt.t = t_cap                                    # capturing executed nothing: the host step counter must not move
         self.replays = 0
         # input prefetch: the NEXT batch's host->device copy runs on a copy stream while the current step executes
         self._copy_stream = torch.cuda.Stream()

@@ -247,6 +247,37 @@ int faln_upsample_nearest_nhwc(const void* src, void* dst, int B, int Hi, int Wi
 int faln_maxpool2_nhwc(const void* src, void* dst, int B, int Hi, int Wi, int C, faln_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Small device-side helpers that keep ATen / cuBLAS launches out of a training step: csrc/small_ops.cu.
+ * ---------------------------------------------------------------------------------------------- */
+/* d_lvl[b,n], x_of[b,n] of /root/reference/models/FAL_netB.py:204-205,224-225,241 in ONE launch, same fp32 op order as the
+ * reference's per-level ATen kernels (every operation rounded to fp32; expf / logf).  min_disp, max_disp [B]. */
+int faln_level_tables(const float* min_disp, const float* max_disp, float* d_lvl, float* x_of, int B, int N, int W,
+                      faln_stream_t stream);
+/* Folded logits layer W' = W0 . W_iconv1 (/root/reference/models/FAL_netB.py:174,190,215: a 3x3 conv without bias or
+ * activation followed by a 1x1 conv).  w0 [N,N] fp32; w_iconv1 logical [N,C,3,3] fp32 with element strides (so,sc,sh,sw);
+ * fwd_pack [Np,3,3,C] bf16 (rows >= N zero), dgrad_pack [Cp,3,3,Np] bf16 (zero padded). */
+int faln_fold_logit_conv(const float* w0, const float* w_iconv1, long long so, long long sc, long long sh, long long sw,
+                         void* fwd_pack, void* dgrad_pack, int N, int C, int Np, int Cp, faln_stream_t stream);
+/* Adjoint of the fold: gwf [N,3,3,C] fp32 (gradient of W', KRSC) -> g_w0 [N,N] += <gwf, W_iconv1>,
+ * g_w_iconv1 (strided like the parameter's gradient view) += W0^T gwf. */
+int faln_fold_logit_conv_bwd(const float* gwf, const float* w0, const float* w_iconv1, long long so, long long sc, long long sh,
+                             long long sw, float* g_w_iconv1, long long gso, long long gsc, long long gsh, long long gsw,
+                             float* g_w0, int N, int C, faln_stream_t stream);
+/* Border-class sums [16,Cout] of the weights of input channel `channel` (the constant max_disp/100 plane,
+ * /root/reference/models/FAL_netB.py:145,208-209) of a strided [Cout,Cin,3,3] weight. */
+int faln_const_channel_table(const float* w, long long so, long long sc, long long sh, long long sw, int channel, float* ctab,
+                             int Cout, faln_stream_t stream);
+/* dW[:, channel, :, :] += weight gradient of that constant channel from the nine border-class sums of the output gradient
+ * (border_sums [B,3,3,Cout], faln_border_sum_nhwc) and the per-sample value [B]. */
+int faln_const_channel_wgrad(const float* border_sums, const float* value, float* dW, long long so, long long sc, long long sh,
+                             long long sw, int channel, int B, int Cout, int last_row_clipped, int last_col_clipped,
+                             faln_stream_t stream);
+/* out = sum_i weights[i] * *terms[i]  (n <= 8 device scalars; `terms` and `weights` are HOST arrays): the loss arithmetic of
+ * /root/reference/Train_Stage1_K.py:258 / Train_Stage2_K.py:309-327 in one launch; and its adjoint out[i] = weights[i] * *g. */
+int faln_scalar_combine(const float* const* terms, const float* weights, int n, float* out, faln_stream_t stream);
+int faln_scalar_scale(const float* g, const float* weights, int n, float* out, faln_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Inference post-processing and validation metrics: csrc/postproc.cu.
  * ---------------------------------------------------------------------------------------------- */
 /* flip_x (optional) + F.interpolate(mode='bilinear', align_corners=True): /root/reference/Test_KITTI.py:291-292.

@@ -183,6 +183,14 @@ def test_device_tables_match_cpu_tables():
         d1, x1 = med.level_tables(mn.to(dev), mx.to(dev), 49, W)
         d0, x0 = O.level_tables(mn, mx, 49, W)
         assert rel_err(d1, d0) < 1e-6 and rel_err(x1, x0) < 1e-6
+        # the one-launch table kernel is BIT-identical to the reference's torch expressions evaluated on the same device
+        for N in (33, 49, 65):
+            for mxv, mnv in ((300.0, 2.0), (60.0, 0.75), (192.3, 1.7)):
+                mxx = torch.tensor([mxv, mxv * 0.7], device=dev).view(2, 1, 1)
+                mnn = torch.tensor([mnv, mnv * 1.3], device=dev).view(2, 1, 1)
+                dk, xk = med.level_tables(mnn, mxx, N, W)
+                dt, xt = med.level_tables_torch(mnn, mxx, N, W)
+                assert torch.equal(dk, dt) and torch.equal(xk, xt), (W, N, mxv)
 
 
 def test_integer_and_near_integer_shifts():

@@ -95,7 +95,8 @@ def test_adam_matches_torch():
 
 
 def test_product_level_tables_bit_identical_to_reference_loop():
-    """fal_net_b200.med.level_tables (vectorised) == the reference's per-level expressions, bit for bit (CPU)."""
+    """fal_net_b200.med.level_tables_torch (the vectorised torch form the device kernel is checked against on the GPU,
+    tests/test_med_gpu.py) == the reference's per-level expressions, bit for bit (CPU)."""
     from fal_net_b200 import med
     for N in (9, 33, 49, 65):
         for W in (160, 640, 1242, 2048):
@@ -103,7 +104,7 @@ def test_product_level_tables_bit_identical_to_reference_loop():
                 mxx = torch.tensor([mx, mx * 0.7]).view(2, 1, 1)
                 mnn = torch.tensor([mn, mn * 1.3]).view(2, 1, 1)
                 d0, x0 = O.level_tables(mnn, mxx, N, W)
-                d1, x1 = med.level_tables(mnn, mxx, N, W)
+                d1, x1 = med.level_tables_torch(mnn, mxx, N, W)
                 assert torch.equal(d0, d1) and torch.equal(x0, x1)
 
 
