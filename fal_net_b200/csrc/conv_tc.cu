@@ -276,6 +276,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                 // everything above overlapped the previous kernel's tail; its results are visible from here on
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ================================================================= TMA producer
@@ -446,6 +448,8 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                 // everything above overlapped the previous kernel's tail; its results are visible from here on
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ================================================================= TMA producer
@@ -643,7 +647,7 @@ int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, C
   const long long total = (long long)p.tiles_w * p.tiles_h * p.B * p.nblk * p.ncls;
   long long grid = (long long)sm_count() * per_sm;
   if (grid > total) grid = total;
-  kern<<<(int)grid, 192, SL::kTotal, st>>>(a1, a2, w, p);
+  launch_pdl(kern, dim3((unsigned)grid), dim3(192), (size_t)SL::kTotal, st, a1, a2, w, p);
   return after_launch("conv3x3_tc_kernel");
 }
 
@@ -693,7 +697,7 @@ int launch_row(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& 
   const long long total = (long long)p.tiles_w * p.H * p.B;
   long long grid = (long long)sm_count() * per_sm;
   if (grid > total) grid = total;
-  kern<<<(int)grid, 320, smem, st>>>(a1, a2, w, ym, p);
+  launch_pdl(kern, dim3((unsigned)grid), dim3(320), (size_t)smem, st, a1, a2, w, ym, p);
   return after_launch("conv3x3_row_kernel");
 }
 

@@ -109,6 +109,8 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                 // prologue overlapped the previous kernel's tail (common.cuh: programmatic dependent launch)
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ================================================================= TMA producer
@@ -216,7 +218,7 @@ int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mg, const WgradParams
     attr_set = smem;
   }
   dim3 grid(splits, p.n_cib * p.n_cob, 1);
-  kern<<<grid, 192, smem, st>>>(mx, mg, p);
+  launch_pdl(kern, grid, dim3(192), (size_t)smem, st, mx, mg, p);
   return after_launch("conv3x3_wgrad_kernel");
 }
 

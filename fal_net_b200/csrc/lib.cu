@@ -1,6 +1,7 @@
 // lib.cu -- library-level plumbing of libfalnet_sm100.so: error state, launch accounting.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -24,6 +25,14 @@ int after_launch(const char* what) {
     return FALN_ERR_LAUNCH;
   }
   return FALN_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("FALN_PDL");
+    return v != nullptr && v[0] != '0';
+  }();
+  return on;
 }
 
 int sm_count() {

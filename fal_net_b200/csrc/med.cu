@@ -1037,9 +1037,14 @@ __global__ void __launch_bounds__(kMaxThreads) __maxnreg__(kMaxRegs) med_bwd_ker
 // Disparity-only epilogue (inference): pure streaming, no staging needed.  4 pixels per thread,
 // all planes of a pixel quad in flight (MLP), float4 loads when the pitch allows.
 // =============================================================================================
+// Streaming form (round 2): the round-1 kernel visited one plane at a time with a data-dependent rescale branch, which kept
+// only ~4 loads in flight per thread (0.47-0.57 of the HBM peak).  Here a thread owns a pixel quad and walks the planes in
+// chunks of eight: the eight 128-bit loads are issued back to back, the running maximum moves at most once per chunk
+// (one rescale per eight planes) and every plane costs one exp2 -- the kernel is a pure HBM stream of 4 (N + 1) B/px.
 __global__ void __launch_bounds__(256) med_disp_kernel(const float* __restrict__ logits, const float* __restrict__ d_lvl,
                                                        float* __restrict__ disp, int B, int N, int H, int W,
                                                        long long pitch, int vec4) {
+  constexpr int kChunk = 8;
   const int wq = (W + 3) / 4;
   const long long total = (long long)B * H * wq;
   const long long ps = (long long)H * pitch;
@@ -1056,35 +1061,55 @@ __global__ void __launch_bounds__(256) med_disp_kernel(const float* __restrict__
 #pragma unroll
     for (int k = 0; k < 4; ++k) { m[k] = -INFINITY; z[k] = 0.f; acc[k] = 0.f; }
     const bool full = vec4 && x + 3 < W;
-#pragma unroll 4
-    for (int n = 0; n < N; ++n) {
-      float v[4];
-      if (full) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(lp + n * ps));
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-      } else {
+    for (int n0 = 0; n0 < N; n0 += kChunk) {
+      float v[kChunk][4];
+      float dn[kChunk];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = x + k < W ? __ldg(lp + n * ps + k) : 0.f;
+      for (int j = 0; j < kChunk; ++j) {
+        const int n = n0 + j;
+        if (n < N) {
+          if (full) {
+            const float4 q = __ldcs(reinterpret_cast<const float4*>(lp + n * ps));   // streamed once: evict first
+            v[j][0] = q.x; v[j][1] = q.y; v[j][2] = q.z; v[j][3] = q.w;
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[j][k] = x + k < W ? __ldg(lp + n * ps + k) : 0.f;
+          }
+          dn[j] = __ldg(dl + n);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[j][k] = -INFINITY;
+          dn[j] = 0.f;
+        }
       }
-      const float dn = __ldg(dl + n);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float ls = v[k] * kLog2e;
-        if (ls > m[k] + kLazy) {
-          const float f = ex2f(m[k] - ls);
+        float cm = v[0][k];
+#pragma unroll
+        for (int j = 1; j < kChunk; ++j) cm = fmaxf(cm, v[j][k]);
+        cm *= kLog2e;
+        if (cm > m[k]) {                       // at most once per chunk
+          const float f = ex2f(m[k] - cm);     // exp2(-inf) = 0 on the first chunk
           z[k] *= f;
           acc[k] *= f;
-          m[k] = ls;
+          m[k] = cm;
         }
-        const float e = ex2f(ls - m[k]);
-        z[k] += e;
-        acc[k] = fmaf(dn, e, acc[k]);
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) {
+          const float e = ex2f(fmaf(v[j][k], kLog2e, -m[k]));
+          z[k] += e;
+          acc[k] = fmaf(dn[j], e, acc[k]);
+        }
       }
     }
     float* o = disp + ((long long)b * H + y) * W + x;
+    if (x + 3 < W && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+      __stcs(reinterpret_cast<float4*>(o), make_float4(acc[0] / z[0], acc[1] / z[1], acc[2] / z[2], acc[3] / z[3]));
+    } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (x + k < W) o[k] = acc[k] / z[k];
+      for (int k = 0; k < 4; ++k)
+        if (x + k < W) o[k] = acc[k] / z[k];
+    }
   }
 }
 

@@ -182,7 +182,10 @@ M3_FN void win5(const float* base, float v[5]) {
 #pragma unroll
   for (int i = 0; i < 5; ++i) v[i] = q[R + i];
 }
-// un-shifted six-tap window of the own quad: row[xb-1 .. xb+4]
+// un-shifted six-tap window of the own quad: row[xb-1 .. xb+4].  (Round 2 measured the two outer taps as warp shuffles of
+// the neighbouring lanes' inner taps instead of the two scalar loads, whose 16-byte lane stride is a 4-way bank conflict:
+// fwd+masks 0.366 -> 0.393 ms and bwd 0.278 -> 0.303 ms at 16x49x192x640 -- SLOWER; SHFL + activemask bookkeeping cost
+// more issue slots than the conflicts cost wavefronts.  Loads kept.)
 M3_FN void win6(const float* row, int xb, float v[6]) {
   const float4 a = ld4(row + xb);
   v[0] = row[xb - 1];

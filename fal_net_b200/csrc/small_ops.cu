@@ -31,7 +31,10 @@ __global__ void level_tables_kernel(const float* __restrict__ min_disp, const fl
   const int b = i / N, n = i % N;
   const float cm1 = (float)((double)n / (double)(N - 1) - 1.0);
   const float mn = min_disp[b], mx = max_disp[b];
-  const float xmin = __fdiv_rn(__fmul_rn(2.f, mn), Wf), xmax = __fdiv_rn(__fmul_rn(2.f, mx), Wf);
+  // `tensor / python_scalar` on CUDA is a multiplication by the fp32 reciprocal of the scalar (ATen div_true_kernel_cuda's
+  // CPU-scalar fast path), not a division: replayed as such
+  const float inv_w = __frcp_rn(Wf);
+  const float xmin = __fmul_rn(__fmul_rn(2.f, mn), inv_w), xmax = __fmul_rn(__fmul_rn(2.f, mx), inv_w);
   d[i] = __fmul_rn(mx, expf(__fmul_rn(logf(__fdiv_rn(mx, mn)), cm1)));
   xo[i] = __fmul_rn(xmax, expf(__fmul_rn(logf(__fdiv_rn(xmax, xmin)), cm1)));
 }
@@ -44,61 +47,78 @@ struct W4 {
 };
 
 // W'[o, c, t] = sum_m W0[o, m] * Wi1[m, c, t];  fwd pack [Np, 9, C] bf16 (rows >= N zero), dgrad pack [Cp, 9, Np] bf16
-// (rows >= C zero; columns >= N zero), plus the fp32 folded weight [N, C, 9] (tape, for the backward's algebra).
-// One thread per (c, t) column; the N x N matrix W0 is staged in shared memory.
-__global__ void __launch_bounds__(128) fold_logit_conv_kernel(const float* __restrict__ w0, const float* __restrict__ wi1, W4 s,
+// (rows >= C zero; columns >= N zero).  A 49 x 49 x 864 matmul: a block owns kFoldCols (c, t) columns, stages W0 and its slice
+// of W_iconv1 in shared memory, and 256 threads produce the Np x kFoldCols outputs.
+constexpr int kFoldCols = 32;
+__global__ void __launch_bounds__(256) fold_logit_conv_kernel(const float* __restrict__ w0, const float* __restrict__ wi1, W4 s,
                                                               __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dg,
                                                               int N, int C, int Np, int Cp) {
-  extern __shared__ float sw0[];   // [N][N]
-  for (int i = threadIdx.x; i < N * N; i += blockDim.x) sw0[i] = w0[i];
-  __syncthreads();
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;   // c * 9 + t
-  if (col >= Cp * 9) return;
-  const int c = col / 9, t = col % 9, kh = t / 3, kw = t % 3;
-  if (c >= C) {
-    for (int o = 0; o < Np; ++o) dg[((long long)c * 9 + t) * Np + o] = __float2bfloat16(0.f);
-    return;
+  extern __shared__ float sm[];
+  float* sw0 = sm;                 // [N][N]
+  float* swi = sm + N * N;         // [N][kFoldCols]
+  const int col0 = blockIdx.x * kFoldCols;
+  for (int i = threadIdx.x; i < N * N; i += 256) sw0[i] = w0[i];
+  for (int i = threadIdx.x; i < N * kFoldCols; i += 256) {
+    const int m = i / kFoldCols, col = col0 + i % kFoldCols;
+    const int c = col / 9, t = col % 9;
+    swi[i] = (c < C) ? __ldg(wi1 + s.at(m, c, t / 3, t % 3)) : 0.f;
   }
-  for (int o = 0; o < Np; ++o) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < Np * kFoldCols; i += 256) {
+    const int o = i / kFoldCols, j = i % kFoldCols, col = col0 + j;
+    const int c = col / 9, t = col % 9;
+    if (c >= Cp) continue;
     float acc = 0.f;
-    if (o < N)
-      for (int m = 0; m < N; ++m) acc = fmaf(sw0[o * N + m], __ldg(wi1 + s.at(m, c, kh, kw)), acc);
+    if (o < N && c < C)
+      for (int m = 0; m < N; ++m) acc = fmaf(sw0[o * N + m], swi[m * kFoldCols + j], acc);
     const __nv_bfloat16 h = __float2bfloat16(acc);
-    fwd[((long long)o * 9 + t) * C + c] = h;
+    if (c < C) fwd[((long long)o * 9 + t) * C + c] = h;
     dg[((long long)c * 9 + t) * Np + o] = h;
   }
 }
 
 // gwf [N, 9, C] fp32 (KRSC, what the weight-gradient kernel wrote for the folded layer).
-//   blocks [0, nA):   dWi1[m, c, t] += sum_o W0[o, m] * gwf[o, t, c]        (one thread per (c, t) column)
-//   blocks [nA, ..):  dW0[o, m]    += sum_{c,t} gwf[o, t, c] * Wi1[m, c, t]  (one warp per (o, m) pair)
-__global__ void __launch_bounds__(128) fold_grad_kernel(const float* __restrict__ gwf, const float* __restrict__ w0,
+//   blocks [0, nA):      dWi1[m, c, t] += sum_o W0[o, m] * gwf[o, t, c]         (a block owns kFoldCols columns)
+//   blocks [nA, nA+N):   dW0[o, m]     += sum_{c,t} gwf[o, t, c] * Wi1[m, c, t]  (a block owns row o: gwf[o] staged, one warp per m)
+__global__ void __launch_bounds__(256) fold_grad_kernel(const float* __restrict__ gwf, const float* __restrict__ w0,
                                                         const float* __restrict__ wi1, W4 s, float* __restrict__ g_wi1, W4 gs,
                                                         float* __restrict__ g_w0, int N, int C, int nA) {
+  extern __shared__ float sm[];
   if ((int)blockIdx.x < nA) {
-    extern __shared__ float sw0[];
-    for (int i = threadIdx.x; i < N * N; i += blockDim.x) sw0[i] = w0[i];
+    float* sw0 = sm;               // [N][N]
+    float* sg = sm + N * N;        // [N][kFoldCols]
+    const int col0 = blockIdx.x * kFoldCols;
+    for (int i = threadIdx.x; i < N * N; i += 256) sw0[i] = w0[i];
+    for (int i = threadIdx.x; i < N * kFoldCols; i += 256) {
+      const int o = i / kFoldCols, col = col0 + i % kFoldCols;
+      const int c = col / 9, t = col % 9;
+      sg[i] = (c < C) ? __ldg(gwf + ((long long)o * 9 + t) * C + c) : 0.f;
+    }
     __syncthreads();
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= C * 9) return;
-    const int c = col / 9, t = col % 9, kh = t / 3, kw = t % 3;
-    for (int m = 0; m < N; ++m) {
+    for (int i = threadIdx.x; i < N * kFoldCols; i += 256) {
+      const int m = i / kFoldCols, j = i % kFoldCols, col = col0 + j;
+      const int c = col / 9, t = col % 9;
+      if (c >= C) continue;
       float acc = 0.f;
-      for (int o = 0; o < N; ++o) acc = fmaf(sw0[o * N + m], __ldg(gwf + ((long long)o * 9 + t) * C + c), acc);
-      g_wi1[gs.at(m, c, kh, kw)] += acc;
+      for (int o = 0; o < N; ++o) acc = fmaf(sw0[o * N + m], sg[o * kFoldCols + j], acc);
+      g_wi1[gs.at(m, c, t / 3, t % 3)] += acc;
     }
     return;
   }
-  const int pair = (blockIdx.x - nA) * 4 + (threadIdx.x >> 5);
-  if (pair >= N * N) return;
-  const int o = pair / N, m = pair % N, lane = threadIdx.x & 31;
-  float acc = 0.f;
-  for (int i = lane; i < 9 * C; i += 32) {
-    const int t = i / C, c = i % C;
-    acc = fmaf(__ldg(gwf + (long long)o * 9 * C + i), __ldg(wi1 + s.at(m, c, t / 3, t % 3)), acc);
+  const int o = blockIdx.x - nA;
+  float* sgo = sm;                 // [9 * C]: gwf[o, :, :]
+  for (int i = threadIdx.x; i < 9 * C; i += 256) sgo[i] = __ldg(gwf + (long long)o * 9 * C + i);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int m = warp; m < N; m += 8) {
+    float acc = 0.f;
+    for (int i = lane; i < 9 * C; i += 32) {
+      const int t = i / C, c = i % C;
+      acc = fmaf(sgo[i], __ldg(wi1 + s.at(m, c, t / 3, t % 3)), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) g_w0[o * N + m] += acc;
   }
-  acc = warp_sum(acc);
-  if (lane == 0) g_w0[pair] += acc;
 }
 
 // ctab[cls, o] = sum over the taps of border class cls = rc * 4 + cc (bit0: first tap outside, bit1: last tap outside) that
@@ -170,14 +190,14 @@ extern "C" int faln_level_tables(const float* min_disp, const float* max_disp, f
 extern "C" int faln_fold_logit_conv(const float* w0, const float* w_iconv1, long long so, long long sc, long long sh,
                                     long long sw, void* fwd_pack, void* dgrad_pack, int N, int C, int Np, int Cp,
                                     faln_stream_t stream) {
-  FALN_REQUIRE(w0 && w_iconv1 && fwd_pack && dgrad_pack && N > 0 && N <= 104 && C > 0 && Np >= N && Cp >= C,
-               "faln_fold_logit_conv: bad argument (N <= 104)");
+  FALN_REQUIRE(w0 && w_iconv1 && fwd_pack && dgrad_pack && N > 0 && N <= 96 && C > 0 && Np >= N && Cp >= C,
+               "faln_fold_logit_conv: bad argument (N <= 96)");
   // zero rows [N, Np) of the forward pack
   if (Np > N)
     FALN_REQUIRE(cudaMemsetAsync(static_cast<__nv_bfloat16*>(fwd_pack) + (size_t)N * 9 * C, 0, (size_t)(Np - N) * 9 * C * 2,
                                  as_stream(stream)) == cudaSuccess, "faln_fold_logit_conv: memset failed");
   const W4 s{so, sc, sh, sw};
-  fold_logit_conv_kernel<<<(Cp * 9 + 127) / 128, 128, (size_t)N * N * 4, as_stream(stream)>>>(
+  fold_logit_conv_kernel<<<(Cp * 9 + kFoldCols - 1) / kFoldCols, 256, (size_t)(N * N + N * kFoldCols) * 4, as_stream(stream)>>>(
       w0, w_iconv1, s, static_cast<__nv_bfloat16*>(fwd_pack), static_cast<__nv_bfloat16*>(dgrad_pack), N, C, Np, Cp);
   return after_launch("fold_logit_conv_kernel");
 }
@@ -185,10 +205,13 @@ extern "C" int faln_fold_logit_conv(const float* w0, const float* w_iconv1, long
 extern "C" int faln_fold_logit_conv_bwd(const float* gwf, const float* w0, const float* w_iconv1, long long so, long long sc,
                                         long long sh, long long sw, float* g_w_iconv1, long long gso, long long gsc,
                                         long long gsh, long long gsw, float* g_w0, int N, int C, faln_stream_t stream) {
-  FALN_REQUIRE(gwf && w0 && w_iconv1 && g_w_iconv1 && g_w0 && N > 0 && N <= 104 && C > 0, "faln_fold_logit_conv_bwd: bad argument");
+  FALN_REQUIRE(gwf && w0 && w_iconv1 && g_w_iconv1 && g_w0 && N > 0 && N <= 96 && C > 0, "faln_fold_logit_conv_bwd: bad argument");
   const W4 s{so, sc, sh, sw}, gs{gso, gsc, gsh, gsw};
-  const int nA = (C * 9 + 127) / 128, nB = (N * N + 3) / 4;
-  fold_grad_kernel<<<nA + nB, 128, (size_t)N * N * 4, as_stream(stream)>>>(gwf, w0, w_iconv1, s, g_w_iconv1, gs, g_w0, N, C, nA);
+  const int nA = (C * 9 + kFoldCols - 1) / kFoldCols;
+  size_t smem = (size_t)(N * N + N * kFoldCols) * 4;
+  if (smem < (size_t)9 * C * 4) smem = (size_t)9 * C * 4;
+  FALN_REQUIRE(smem <= 48 * 1024, "faln_fold_logit_conv_bwd: layer too wide for the staging buffers");
+  fold_grad_kernel<<<nA + N, 256, smem, as_stream(stream)>>>(gwf, w0, w_iconv1, s, g_w_iconv1, gs, g_w0, N, C, nA);
   return after_launch("fold_grad_kernel");
 }
 

@@ -31,6 +31,45 @@ class SyntheticStereo:
                    right.pin_memory() if torch.cuda.is_available() else right), torch.full((self.B,), float(self.max_disp))
 
 
+class SyntheticValidation:
+    """Iterable of ((left, right), sparse disparity target) batches shaped like the reference's KITTI2015 validation loader
+    output (Datasets/Kitti2015.py; Train_Stage1_K.py:293-297): 375x1242 views and a ~25 %-dense disparity map, zeros =
+    invalid."""
+
+    def __init__(self, n_batches, batch=1, H=375, W=1242, seed=7):
+        self.n, self.B, self.H, self.W, self.seed = n_batches, batch, H, W, seed
+
+    def __len__(self):
+        return self.n
+
+    def __iter__(self):
+        g = torch.Generator().manual_seed(self.seed)
+        mean = torch.tensor(MEAN).view(1, 3, 1, 1)
+        for _ in range(self.n):
+            left = torch.rand(self.B, 3, self.H, self.W, generator=g) - mean
+            right = torch.rand(self.B, 3, self.H, self.W, generator=g) - mean
+            disp = 1.0 + 150.0 * torch.rand(self.B, 1, self.H, self.W, generator=g)
+            keep = torch.rand(self.B, 1, self.H, self.W, generator=g) < 0.25
+            yield (left, right), disp * keep
+
+
+class SyntheticRawStereo:
+    """Decoded uint8 stereo pairs [H,W,3] as the reference's image loader hands them to the co-transforms
+    (Datasets/listdataset_train.py:77-80), for the device input pipeline (fal_net_b200.input_pipeline)."""
+
+    def __init__(self, n_batches, batch, H=375, W=1242, seed=0):
+        self.n, self.B, self.H, self.W, self.seed = n_batches, batch, H, W, seed
+
+    def __len__(self):
+        return self.n
+
+    def __iter__(self):
+        g = torch.Generator().manual_seed(self.seed)
+        for _ in range(self.n):
+            yield ([torch.randint(0, 256, (self.H, self.W, 3), generator=g, dtype=torch.uint8) for _ in range(self.B)],
+                   [torch.randint(0, 256, (self.H, self.W, 3), generator=g, dtype=torch.uint8) for _ in range(self.B)])
+
+
 class AverageMeter:
     def __init__(self):
         self.sum, self.count, self.val = 0.0, 0, 0.0
