@@ -67,6 +67,17 @@ def _embed3(w):
     return w3
 
 
+# Nearest 2x up-sampling folded into the deconv convolution (CN.conv3x3_up2_fwd / _dgrad: four taps per output parity class
+# instead of nine, no up-sampled tensor).  Exact-2x levels only (every level of the 192x640 training crops); other sizes --
+# KITTI full resolution has odd levels -- keep the explicit up-sample.  FALN_NO_UP2=1 switches it off (A/B measurements).
+USE_UP2 = os.environ.get("FALN_NO_UP2", "0") in ("", "0")
+
+
+def _up2_packs(weight):
+    """(forward, dgrad) folded packs of a deconv weight: one launch, refreshed once per optimiser step."""
+    return _cached(weight, ("up2",), lambda: CN.pack_up2_weights(weight))
+
+
 def _wk(weight, cin=None):
     """Forward (KRSC bf16) weight: a view of the optimiser's bf16 shadow arena when the parameter lives in one (no pack
     kernels at all), else packed once per parameter version."""
@@ -139,8 +150,12 @@ def forward(model, image, max_disp, tape=None, disp_lvl=None):
     for lvl, _, uout, _, iout in DEC:
         skip = skips[lvl - 1]
         up = getattr(bb, f"deconv{lvl}")
-        xu = CN.upsample_nearest(h, (skip.shape[2], skip.shape[3]))                # :58
-        u = CN.conv3x3_fwd(xu, _wk(up.conv1.weight), None, 1, 1)                   # :59
+        if USE_UP2 and skip.shape[2] == 2 * h.shape[2] and skip.shape[3] == 2 * h.shape[3] and h.shape[1] % 32 == 0:
+            xu = None                                                              # :58-59 as ONE kernel, xu never exists
+            u = CN.conv3x3_up2_fwd(h, _up2_packs(up.conv1.weight)[0], None, 1)
+        else:
+            xu = CN.upsample_nearest(h, (skip.shape[2], skip.shape[3]))            # :58
+            u = CN.conv3x3_fwd(xu, _wk(up.conv1.weight), None, 1, 1)               # :59
         if iout is not None:
             ic = getattr(bb, f"iconv{lvl}")[0]
             hn = CN.conv3x3_fwd(u, _wk(ic.weight), ic.bias, 1, 1, None, skip)      # concat = second TMA source
@@ -276,6 +291,7 @@ def backward(model, tape, g_logits, sink=None):
                 dW = torch.zeros(dW.shape[0], 3, 3, dW.shape[1], device=dev, dtype=torch.float32).permute(0, 3, 1, 2)
             off = 0
             for x in sources:
+                x = x() if callable(x) else x                  # lazily built input (the up-sampled map of a folded deconv)
                 cx = min(x.shape[1], dW.shape[1] - off)
                 CN.conv3x3_wgrad(g_pre, x, dW, cout=cout, cx=cx, ci_off=off, stride=stride)
                 off += cx
@@ -284,7 +300,7 @@ def backward(model, tape, g_logits, sink=None):
             if const is not None:
                 CN.const_channel_wgrad_into(g_pre, const[0], const[1], stride, cout, dW, off)
             ready(name)
-        on_side(run, g_pre, *sources)
+        on_side(run, g_pre, *[x for x in sources if not callable(x)])
 
     # ---------------------------------------------------------------- folded logits conv (iconv1 o conv0)
     Np = (N + 31) // 32 * 32
@@ -325,11 +341,22 @@ def backward(model, tape, g_logits, sink=None):
             hw = (u.shape[2], u.shape[3])
             g_u = CN.conv3x3_dgrad(g_h, wd, hw, rows=(0, C1), dact=1, ysave=u)
             G_skip[lvl - 1] = CN.conv3x3_dgrad(g_h, wd, hw, rows=(C1, skip.shape[1]))
-        wgrad(pfx + f"deconv{lvl}.conv1.weight", g_u, (xu,), up.conv1.weight.shape[0])
-        g_xu = CN.conv3x3_dgrad(g_u, _wd(up.conv1.weight), (xu.shape[2], xu.shape[3]))
-        # nearest-upsample backward fused with ELU' of the producer (h_{l+1}, or the bottleneck skip s6 for level 6)
-        g_h = CN.upsample_nearest_bwd(g_xu, (h_in.shape[2], h_in.shape[3]), ysave=h_in, dact=1)
-        del g_u, g_xu
+        if xu is None:
+            # folded level: the weight gradient still wants the up-sampled input -- rebuilt on the SIDE stream, off the
+            # critical path -- while the data gradient goes straight to the low-resolution tensor (up-sample backward,
+            # 3x3 data gradient and ELU' of the producer in one kernel)
+            hw_up = (u.shape[2], u.shape[3])
+            keep.append(h_in)
+            wgrad(pfx + f"deconv{lvl}.conv1.weight", g_u, (lambda h_=h_in, hw_=hw_up: CN.upsample_nearest(h_, hw_),),
+                  up.conv1.weight.shape[0])
+            g_h = CN.conv3x3_up2_dgrad(g_u, _up2_packs(up.conv1.weight)[1], dact=1, ysave=h_in)
+            del g_u
+        else:
+            wgrad(pfx + f"deconv{lvl}.conv1.weight", g_u, (xu,), up.conv1.weight.shape[0])
+            g_xu = CN.conv3x3_dgrad(g_u, _wd(up.conv1.weight), (xu.shape[2], xu.shape[3]))
+            # nearest-upsample backward fused with ELU' of the producer (h_{l+1}, or the bottleneck skip s6 for level 6)
+            g_h = CN.upsample_nearest_bwd(g_xu, (h_in.shape[2], h_in.shape[3]), ysave=h_in, dact=1)
+            del g_u, g_xu
 
     # ---------------------------------------------------------------- encoder, level 6 .. 0
     g_s = g_h                                                                     # pre-activation gradient of s6

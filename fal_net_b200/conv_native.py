@@ -14,11 +14,11 @@ ACT = {None: 0, "none": 0, "elu": 1, "relu": 2}
 TIMING = None
 
 
-def _timed(kind, flops, nbytes):
+def _timed(kind, flops, nbytes, gemm_n=64):
     if TIMING is None:
         return None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    TIMING.append((kind, e0, e1, flops, nbytes))
+    TIMING.append((kind, e0, e1, flops, nbytes, gemm_n))
     e0.record()
     return e1
 
@@ -146,7 +146,7 @@ def conv3x3_fwd(x, w_krsc, bias=None, stride=1, act=0, residual=None, x2=None, c
         y = torch.empty((B, cout, Ho, Wo), device=x.device, dtype=torch.bfloat16, memory_format=CL)
         planar, pitch, out_c = 0, 0, cout
     ev = _timed("conv_fwd", 2 * 9 * (C1 + C2) * cout * B * Ho * Wo,
-                2 * B * H * W * (C1 + C2) + (4 if planar else 2) * B * Ho * Wo * cout + 2 * 9 * (C1 + C2) * cout)
+                2 * B * H * W * (C1 + C2) + (4 if planar else 2) * B * Ho * Wo * cout + 2 * 9 * (C1 + C2) * cout, cout_pad)
     rc = _lib.lib().faln_conv3x3_fwd(_lib.ptr(x), _lib.ptr(x2), _lib.ptr(w_krsc), _lib.ptr(bias), _lib.ptr(ctab),
                                      _lib.ptr(cscale), _lib.ptr(residual), _lib.ptr(y), B, H, W, C1, C2, cout, cout_pad,
                                      stride, int(act), planar, pitch, out_c, _lib.cur_stream())
@@ -175,13 +175,73 @@ def conv3x3_logits_disp(x, x2, w_krsc, bias, d_lvl):
     b64 = torch.full((64,), float("-inf"), device=x.device, dtype=torch.float32)   # ... and logit -inf
     b64[:N] = bias.detach().float()
     disp = torch.empty(B, 1, H, W, device=x.device, dtype=torch.float32)
-    ev = _timed("conv_fwd", 2 * 9 * (C1 + C2) * N * B * H * W, 2 * B * H * W * (C1 + C2) + 4 * B * H * W)
+    ev = _timed("conv_fwd", 2 * 9 * (C1 + C2) * N * B * H * W, 2 * B * H * W * (C1 + C2) + 4 * B * H * W, 64)
     rc = _lib.lib().faln_conv3x3_logits_disp(_lib.ptr(x), _lib.ptr(x2), _lib.ptr(w_krsc), _lib.ptr(b64), _lib.ptr(d64),
                                              _lib.ptr(disp), B, H, W, C1, C2, N, 64, _lib.cur_stream())
     _lib.check(rc, "faln_conv3x3_logits_disp")
     if ev is not None:
         ev.record()
     return disp
+
+
+def pack_up2_weights(weight: torch.Tensor):
+    """(forward pack [Cout_pad,16,Cin] bf16, dgrad pack [Cin_pad,16,Cout_pad] bf16) of an up-sample + conv block's folded
+    weights (csrc/small_ops.cu pack_up2_kernel), from the fp32 [Cout,Cin,3,3] weight in whatever layout it lives."""
+    w = weight.detach()
+    assert w.dtype == torch.float32 and w.dim() == 4 and w.shape[2:] == (3, 3)
+    Cout, Cin = w.shape[0], w.shape[1]
+    Cout_pad, Cin_pad = (Cout + 31) // 32 * 32, (Cin + 31) // 32 * 32
+    assert Cin % 32 == 0
+    fwd = torch.empty(Cout_pad, 16, Cin, device=w.device, dtype=torch.bfloat16)
+    dg = torch.empty(Cin_pad, 16, Cout_pad, device=w.device, dtype=torch.bfloat16)
+    so, sc, sh, sw = w.stride()
+    _lib.check(_lib.lib().faln_pack_up2_weights(_lib.ptr(w), so, sc, sh, sw, _lib.ptr(fwd), _lib.ptr(dg), Cout, Cin, Cout_pad,
+                                                Cin_pad, _lib.cur_stream()), "faln_pack_up2_weights")
+    return fwd, dg
+
+
+def conv3x3_up2_fwd(x, w_fold, bias=None, act=0, cout=None):
+    """act(conv3x3(upsample_nearest_2x(x))) without the up-sampled tensor: x bf16 [B,C,H,W] channels_last (low resolution),
+    w_fold from ``pack_up2_weights``; returns bf16 [B,Cout,2H,2W] channels_last."""
+    x = _nhwc(x)
+    B, C1, H, W = x.shape
+    cout_pad = w_fold.shape[0]
+    cout = cout or cout_pad
+    assert w_fold.shape[1:] == (16, C1) and w_fold.dtype == torch.bfloat16 and w_fold.is_contiguous()
+    y = torch.empty((B, cout, 2 * H, 2 * W), device=x.device, dtype=torch.bfloat16, memory_format=CL)
+    if bias is not None:
+        bias = bias.detach().float().contiguous()
+    # algorithmic FLOPs of the REFERENCE formulation (nine taps on the up-sampled map) so that rooflines stay comparable
+    ev = _timed("conv_fwd", 2 * 9 * C1 * cout * B * 4 * H * W, 2 * B * H * W * C1 + 2 * B * 4 * H * W * cout + 2 * 9 * C1 * cout,
+                cout_pad)
+    rc = _lib.lib().faln_conv3x3_up2_fwd(_lib.ptr(x), _lib.ptr(w_fold), _lib.ptr(bias), _lib.ptr(y), B, H, W, C1, cout, cout_pad,
+                                         int(act), cout, _lib.cur_stream())
+    _lib.check(rc, "faln_conv3x3_up2_fwd")
+    if ev is not None:
+        ev.record()
+    return y
+
+
+def conv3x3_up2_dgrad(g, wd_fold, dact=0, ysave=None):
+    """Gradient w.r.t. the LOW-resolution input of an up-sample + conv block, times act'(ysave) of the producer:
+    g bf16 [B,Cg,2H,2W] channels_last -> bf16 [B,Cx,H,W] channels_last."""
+    g = _nhwc(g)
+    B, Cg, H2, W2 = g.shape
+    assert H2 % 2 == 0 and W2 % 2 == 0
+    H, W = H2 // 2, W2 // 2
+    Cx = wd_fold.shape[0]
+    assert wd_fold.shape[1:] == (16, Cg) and wd_fold.dtype == torch.bfloat16 and wd_fold.is_contiguous()
+    out = torch.empty((B, Cx, H, W), device=g.device, dtype=torch.bfloat16, memory_format=CL)
+    if ysave is not None:
+        ysave = _nhwc(ysave)
+        assert ysave.shape == out.shape
+    ev = _timed("conv_dgrad", 2 * 9 * Cg * Cx * B * H2 * W2, 2 * B * H2 * W2 * Cg + 2 * B * H * W * Cx + 2 * 9 * Cg * Cx, Cx)
+    rc = _lib.lib().faln_conv3x3_up2_dgrad(_lib.ptr(g), _lib.ptr(wd_fold), _lib.ptr(out), _lib.ptr(ysave), B, H, W, Cg, Cx,
+                                           int(dact if ysave is not None else 0), Cx, Cx, _lib.cur_stream())
+    _lib.check(rc, "faln_conv3x3_up2_dgrad")
+    if ev is not None:
+        ev.record()
+    return out
 
 
 def stem_conv(x, w, bias, act, flip_x=False):
@@ -256,7 +316,7 @@ def conv3x3_dgrad(g, wd, out_hw, stride=1, out=None, rows=None, accum=False, dac
         residual = _nhwc(residual)
         assert residual.shape == out.shape
     assert (Hg, Wg) == ((H - 1) // stride + 1, (W - 1) // stride + 1)
-    ev = _timed("conv_dgrad", 2 * 9 * Cg * count * B * Hg * Wg, 2 * B * Hg * Wg * Cg + 2 * B * H * W * count + 2 * 9 * Cg * count)
+    ev = _timed("conv_dgrad", 2 * 9 * Cg * count * B * Hg * Wg, 2 * B * Hg * Wg * Cg + 2 * B * H * W * count + 2 * 9 * Cg * count, count)
     rc = _lib.lib().faln_conv3x3_dgrad(_lib.ptr(g), _lib.ptr(wslice), _lib.ptr(out), _lib.ptr(residual), _lib.ptr(ysave),
                                        B, H, W, Cg, count, count, stride, int(accum), int(dact if ysave is not None else 0),
                                        count, count, count, _lib.cur_stream())
@@ -319,7 +379,7 @@ def conv3x3_wgrad(g, x, dW, cout=None, cx=None, ci_off=0, stride=1, flags=0):
     cout = cout or dW.shape[0]
     cx = cx or min(Cxs, dW.shape[1] - ci_off)
     assert cout <= dW.shape[0] and ci_off + cx <= dW.shape[1]
-    ev = _timed("conv_wgrad", 2 * 9 * cx * cout * B * Hg * Wg, 2 * B * Hg * Wg * Cg + 2 * B * H * W * Cxs + 4 * 9 * cx * cout)
+    ev = _timed("conv_wgrad", 2 * 9 * cx * cout * B * Hg * Wg, 2 * B * Hg * Wg * Cg + 2 * B * H * W * Cxs + 4 * 9 * cx * cout, 64)
     rc = _lib.lib().faln_conv3x3_wgrad(_lib.ptr(g), _lib.ptr(x), _lib.ptr(dW), B, H, W, Cg, Cxs, cout, cx, ci_off,
                                        dW.shape[1], stride, int(flags), _lib.cur_stream())
     _lib.check(rc, "faln_conv3x3_wgrad")

@@ -31,7 +31,7 @@ constexpr int kTH = 8;  // output tile: kTH x kTW = 8 x 16 pixels = 128 = UMMA_M
 // Tap t reads the input tile at offset (dh[t], dw[t]) and the weight columns of filter tap wt[t].
 struct TapClass {
   int n;
-  signed char dh[9], dw[9], wt[9];
+  signed char dh[16], dw[16], wt[16];   // up to 16 taps: the 4x4 gather of the upsample-folded data gradient
   signed char oh, ow;
 };
 
@@ -916,6 +916,95 @@ extern "C" int faln_conv3x3_dgrad(const void* g, const void* wd, void* gx, const
   CUtensorMap a1, wm;
   if (!make_act_map(&a1, g, B, Hg, Wg, Cg, BK, 1) || !make_w_map(&wm, wd, Cx_pad, 9 * Cg, BK, BN)) {
     set_error("faln_conv3x3_dgrad: cuTensorMapEncodeTiled failed (driver entry point missing or bad tensor geometry)");
+    return FALN_ERR_LAUNCH;
+  }
+  return dispatch(BK, BN, a1, a1, wm, p, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Nearest-neighbour 2x up-sampling folded INTO the 3x3 convolution that follows it (the reference's ``deconv`` block,
+// /root/reference/models/FAL_netB.py:51-60: F.interpolate(nearest) then conv3x3).  For an exact 2x size the up-sampled
+// image repeats every source pixel 2x2, so output pixel (2i+ph, 2j+pw) sees only a 2x2 neighbourhood of SOURCE pixels and the
+// nine taps collapse into four per output parity class:
+//     y[2i+ph, 2j+pw] = sum_{a,b in {0,1}} Wf[ph,pw][a][b] . x[i + a + ph - 1, j + b + pw - 1],
+//     Wf[ph,pw][a][b] = sum_{kh in G(ph,a)} sum_{kw in G(pw,b)} W[kh][kw],  G(0,0)={0}, G(0,1)={1,2}, G(1,0)={0,1}, G(1,1)={2}
+// (zero padding of the up-sampled image == zero fill of the source box).  2.25x fewer MMAs, the up-sampled tensor is never
+// written or read, and the launch runs as four tap classes of the tile kernel (like the stride-2 data gradient).
+// w: [Cout_pad][16][C1] bf16, virtual tap (ph*2+pw)*4 + a*2+b (faln_pack_up2_weights).  y: bf16 NHWC [B,2H,2W,out_c].
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int faln_conv3x3_up2_fwd(const void* x, const void* w, const float* bias, void* y, int B, int H, int W, int C1,
+                                    int Cout, int Cout_pad, int act, int out_c, faln_stream_t stream) {
+  FALN_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0, "faln_conv3x3_up2_fwd: null pointer / bad shape");
+  FALN_REQUIRE(C1 > 0 && C1 % 32 == 0 && Cout > 0 && Cout % 32 == 0 && Cout_pad >= Cout && Cout_pad % 32 == 0 && out_c >= Cout &&
+                   out_c % 8 == 0, "faln_conv3x3_up2_fwd: channel counts must be multiples of 32");
+  const int BK = (C1 % 64 == 0) ? 64 : 32;
+  int BN = Cout_pad % 256 == 0 ? 256 : (Cout_pad % 128 == 0 ? 128 : (Cout_pad % 64 == 0 ? 64 : 32));
+  ConvParams p{};
+  p.B = B; p.H = H; p.W = W;
+  p.Ho = H; p.Wo = W;                                     // tile grid over the SOURCE pixels (one parity class at a time)
+  BN = narrow_bn(BN, B * ((W + kTW - 1) / kTW) * ((H + kTH - 1) / kTH), Cout_pad, 4);
+  p.C1 = C1; p.C2 = 0; p.Cin = C1; p.Cout = Cout;
+  p.stride = 1; p.act = act; p.planar = 0;
+  p.tiles_w = (W + kTW - 1) / kTW; p.tiles_h = (H + kTH - 1) / kTH;
+  p.kblocks1 = C1 / BK; p.kblocks2 = 0;
+  p.bias = bias; p.out = y; p.out_c = out_c; p.res_c = out_c;
+  p.out_mul = 2; p.out_H = 2 * H; p.out_W = 2 * W;
+  p.ncls = 4;
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      TapClass& c = p.cls[ph * 2 + pw];
+      c.n = 4; c.oh = (signed char)ph; c.ow = (signed char)pw;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          c.dh[a * 2 + b] = (signed char)(a + ph - 1);
+          c.dw[a * 2 + b] = (signed char)(b + pw - 1);
+          c.wt[a * 2 + b] = (signed char)((ph * 2 + pw) * 4 + a * 2 + b);
+        }
+    }
+  CUtensorMap a1, wm;
+  if (!make_act_map(&a1, x, B, H, W, C1, BK, 1) || !make_w_map(&wm, w, Cout_pad, 16 * C1, BK, BN)) {
+    set_error("faln_conv3x3_up2_fwd: cuTensorMapEncodeTiled failed");
+    return FALN_ERR_LAUNCH;
+  }
+  return dispatch(BK, BN, a1, a1, wm, p, as_stream(stream));
+}
+
+// Data gradient of the folded block: gradient w.r.t. the LOW-resolution input directly (the nearest-upsample backward --
+// a 2x2 sum -- and the 3x3 data gradient fused):
+//     gx[i, j] = sum_{r,c in {-1,0,1,2}} V[r][c]^T . g[2i + r, 2j + c],   V[r][c] = sum_{kh in Gr(r)} sum_{kw in Gr(c)} W[kh][kw],
+//     Gr(-1) = {2}, Gr(0) = {1,2}, Gr(1) = {0,1}, Gr(2) = {0}
+// i.e. a stride-2 gather over the high-resolution gradient with a 4x4 window (one tap class of 16 taps, box element
+// stride 2).  wd: [Cx_pad][16][Cg] bf16, virtual tap (r+1)*4 + (c+1).  Epilogue as faln_conv3x3_dgrad.
+extern "C" int faln_conv3x3_up2_dgrad(const void* g, const void* wd, void* gx, const void* ysave, int B, int H, int W, int Cg,
+                                      int Cx, int dact, int gx_c, int ysave_c, faln_stream_t stream) {
+  FALN_REQUIRE(g && wd && gx && B > 0 && H > 0 && W > 0, "faln_conv3x3_up2_dgrad: null pointer / bad shape");
+  FALN_REQUIRE(Cg > 0 && Cg % 32 == 0 && Cx > 0 && Cx % 32 == 0 && gx_c >= Cx && gx_c % 8 == 0,
+               "faln_conv3x3_up2_dgrad: channel counts must be multiples of 32");
+  FALN_REQUIRE((dact == 0) == (ysave == nullptr), "faln_conv3x3_up2_dgrad: dact and ysave go together");
+  const int BK = (Cg % 64 == 0) ? 64 : 32;
+  int BN = Cx % 256 == 0 ? 256 : (Cx % 128 == 0 ? 128 : (Cx % 64 == 0 ? 64 : 32));
+  ConvParams p{};
+  p.B = B; p.H = 2 * H; p.W = 2 * W;                      // the tensor the TMA reads: the high-resolution gradient
+  p.Ho = H; p.Wo = W;
+  BN = narrow_bn(BN, B * ((W + kTW - 1) / kTW) * ((H + kTH - 1) / kTH), Cx, 1);
+  p.C1 = Cg; p.C2 = 0; p.Cin = Cg; p.Cout = Cx;
+  p.stride = 2; p.act = 0; p.planar = 0;
+  p.tiles_w = (W + kTW - 1) / kTW; p.tiles_h = (H + kTH - 1) / kTH;
+  p.kblocks1 = Cg / BK; p.kblocks2 = 0;
+  p.out = gx; p.out_c = gx_c; p.res_c = gx_c;
+  p.out_mul = 1; p.out_H = H; p.out_W = W;
+  p.dact = dact; p.ysave = static_cast<const __nv_bfloat16*>(ysave); p.ysave_c = ysave_c;
+  p.ncls = 1;
+  p.cls[0].n = 16; p.cls[0].oh = p.cls[0].ow = 0;
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      p.cls[0].dh[r * 4 + c] = (signed char)(r - 1);
+      p.cls[0].dw[r * 4 + c] = (signed char)(c - 1);
+      p.cls[0].wt[r * 4 + c] = (signed char)(r * 4 + c);
+    }
+  CUtensorMap a1, wm;
+  if (!make_act_map(&a1, g, B, 2 * H, 2 * W, Cg, BK, 2) || !make_w_map(&wm, wd, Cx, 16 * Cg, BK, BN)) {
+    set_error("faln_conv3x3_up2_dgrad: cuTensorMapEncodeTiled failed");
     return FALN_ERR_LAUNCH;
   }
   return dispatch(BK, BN, a1, a1, wm, p, as_stream(stream));

@@ -159,6 +159,59 @@ __global__ void const_wgrad_kernel(const float* __restrict__ S, const float* __r
   dW[gs.at(o, ch, kh, kw)] += acc;
 }
 
+// Folded weights of an up-sample + conv block (csrc/conv_tc.cu, faln_conv3x3_up2_fwd / _dgrad): sums of the original taps in
+// fp32, rounded once to bf16.  fwd [Cout_pad][16][Cin]: tap (ph*2+pw)*4 + a*2+b = sum over G(ph,a) x G(pw,b);
+// dgrad [Cin_pad][16][Cout_pad]: tap (r+1)*4 + (c+1) = sum over Gr(r) x Gr(c).  One thread per (co, ci).
+__device__ __forceinline__ void up2_group(int idx, int& lo, int& hi) {   // G / Gr sets as [lo, hi] tap ranges
+  // idx 0: {0}, 1: {1,2}, 2: {0,1}, 3: {2}
+  lo = (idx == 1) ? 1 : (idx == 3 ? 2 : 0);
+  hi = (idx == 0) ? 0 : (idx == 2 ? 1 : 2);
+}
+__global__ void __launch_bounds__(256) pack_up2_kernel(const float* __restrict__ w, W4 s, __nv_bfloat16* __restrict__ fwd,
+                                                       __nv_bfloat16* __restrict__ dg, int Cout, int Cin, int Cout_pad, int Cin_pad) {
+  const long long i = blockIdx.x * 256LL + threadIdx.x;
+  if (i >= (long long)Cout_pad * Cin_pad) return;
+  const int ci = (int)(i % Cin_pad), co = (int)(i / Cin_pad);
+  float k[3][3];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) k[kh][kw] = (co < Cout && ci < Cin) ? __ldg(w + s.at(co, ci, kh, kw)) : 0.f;
+  // forward: classes (ph, pw), taps (a, b): row group index = ph*2 + a -> {0}, {1,2}, {0,1}, {2}
+  if (ci < Cin) {
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            int r0, r1, c0, c1;
+            up2_group(ph * 2 + a, r0, r1);
+            up2_group(pw * 2 + b, c0, c1);
+            float acc = 0.f;
+            for (int kh = r0; kh <= r1; ++kh)
+              for (int kw = c0; kw <= c1; ++kw) acc += k[kh][kw];
+            fwd[((long long)co * 16 + (ph * 2 + pw) * 4 + a * 2 + b) * Cin + ci] = __float2bfloat16(acc);
+          }
+  }
+  // data gradient: window offsets r, c in {-1, 0, 1, 2} -> Gr(-1) = {2}, Gr(0) = {1,2}, Gr(1) = {0,1}, Gr(2) = {0}
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int gmap[4] = {3, 1, 2, 0};   // offset -1 -> {2}, 0 -> {1,2}, +1 -> {0,1}, +2 -> {0}
+      int r0, r1, c0, c1;
+      up2_group(gmap[r], r0, r1);
+      up2_group(gmap[c], c0, c1);
+      float acc = 0.f;
+      for (int kh = r0; kh <= r1; ++kh)
+        for (int kw = c0; kw <= c1; ++kw) acc += k[kh][kw];
+      dg[((long long)ci * 16 + r * 4 + c) * Cout_pad + co] = __float2bfloat16(acc);
+    }
+}
+
 struct Terms {
   const float* p[8];
   float w[8];
@@ -253,4 +306,16 @@ extern "C" int faln_scalar_scale(const float* g, const float* weights, int n, fl
   for (int i = 0; i < n; ++i) t.w[i] = weights[i];
   scalar_scale_kernel<<<1, 32, 0, as_stream(stream)>>>(g, t, out);
   return after_launch("scalar_scale_kernel");
+}
+
+extern "C" int faln_pack_up2_weights(const float* w, long long so, long long sc, long long sh, long long sw, void* fwd_pack,
+                                     void* dgrad_pack, int Cout, int Cin, int Cout_pad, int Cin_pad, faln_stream_t stream) {
+  FALN_REQUIRE(w && fwd_pack && dgrad_pack && Cout > 0 && Cin > 0 && Cout_pad >= Cout && Cin_pad >= Cin,
+               "faln_pack_up2_weights: bad argument");
+  const W4 s{so, sc, sh, sw};
+  const long long n = (long long)Cout_pad * Cin_pad;
+  pack_up2_kernel<<<(int)((n + 255) / 256), 256, 0, as_stream(stream)>>>(w, s, static_cast<__nv_bfloat16*>(fwd_pack),
+                                                                        static_cast<__nv_bfloat16*>(dgrad_pack), Cout, Cin,
+                                                                        Cout_pad, Cin_pad);
+  return after_launch("pack_up2_kernel");
 }

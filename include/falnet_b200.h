@@ -246,6 +246,22 @@ int faln_upsample_nearest_nhwc(const void* src, void* dst, int B, int Hi, int Wi
 /* 2x2 stride-2 max pooling (VGG pools, /root/reference/loss_functions.py:21-29) on bf16 NHWC. */
 int faln_maxpool2_nhwc(const void* src, void* dst, int B, int Hi, int Wi, int C, faln_stream_t stream);
 
+/* Nearest 2x up-sampling folded into the 3x3 convolution that follows it (the reference's deconv block,
+ * /root/reference/models/FAL_netB.py:51-60: F.interpolate(nearest) :58 + conv3x3 + ELU :59), exact-2x sizes only: four taps per
+ * output parity class instead of nine, the up-sampled tensor never exists.  x [B,H,W,C1] bf16 NHWC (LOW resolution);
+ * w [Cout_pad][16][C1] bf16 from faln_pack_up2_weights; y [B,2H,2W,out_c] bf16 NHWC. */
+int faln_conv3x3_up2_fwd(const void* x, const void* w, const float* bias, void* y, int B, int H, int W, int C1, int Cout,
+                         int Cout_pad, int act, int out_c, faln_stream_t stream);
+/* Its data gradient w.r.t. the LOW-resolution input: nearest-upsample backward (2x2 sum) + 3x3 data gradient as one 4x4
+ * stride-2 gather, with the producer's activation derivative fused (dact / ysave as in faln_conv3x3_dgrad).
+ * g [B,2H,2W,Cg] bf16; wd [Cx][16][Cg] bf16 from faln_pack_up2_weights; gx [B,H,W,gx_c]. */
+int faln_conv3x3_up2_dgrad(const void* g, const void* wd, void* gx, const void* ysave, int B, int H, int W, int Cg, int Cx,
+                           int dact, int gx_c, int ysave_c, faln_stream_t stream);
+/* Folded weights of such a block from the fp32 [Cout,Cin,3,3] weight (element strides so,sc,sh,sw): sums of the original taps
+ * in fp32, rounded once to bf16.  fwd_pack [Cout_pad][16][Cin], dgrad_pack [Cin_pad][16][Cout_pad]. */
+int faln_pack_up2_weights(const float* w, long long so, long long sc, long long sh, long long sw, void* fwd_pack,
+                          void* dgrad_pack, int Cout, int Cin, int Cout_pad, int Cin_pad, faln_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Small device-side helpers that keep ATen / cuBLAS launches out of a training step: csrc/small_ops.cu.
  * ---------------------------------------------------------------------------------------------- */

@@ -240,3 +240,38 @@ def test_vgg_slices_forward_and_input_gradient():
         assert float((o.float() - r).abs().max() / r.abs().max()) < 2e-2
     assert gx.shape == gr.shape and gx.dtype == torch.float32
     assert float((gx - gr).norm() / gr.norm()) < 3e-2, float((gx - gr).norm() / gr.norm())
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 64, 64, 24, 40), (1, 256, 128, 6, 10), (2, 128, 64, 13, 21), (1, 512, 256, 3, 10),
+                                            (2, 64, 64, 96, 320)])
+def test_upsample_folded_conv_forward_and_data_gradient(B, Cin, Cout, H, W):
+    """deconv block (nearest 2x up-sampling + conv3x3 + ELU, reference :51-60) as ONE kernel with folded weights: forward
+    against fp32 F.interpolate + conv2d on the same bf16 operands, data gradient (w.r.t. the LOW-resolution input, times the
+    producer's ELU') against fp32 autograd; and both against the explicit two-kernel path of the product."""
+    import torch.nn.functional as F
+    from fal_net_b200 import conv_native as CN
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(B * 100 + Cin + H)
+    x = torch.randn(B, Cin, H, W, generator=g, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g, device=dev) / (3 * Cin ** 0.5))
+    wf, wd = CN.pack_up2_weights(w)
+    y = CN.conv3x3_up2_fwd(x, wf, None, 1)
+    xr = x.float().requires_grad_(True)
+    w16 = w.to(torch.bfloat16).float()
+    yr = F.elu(F.conv2d(F.interpolate(xr, scale_factor=2, mode="nearest"), w16, None, 1, 1))
+    assert y.shape == yr.shape
+    # folded weights are bf16(sum of fp32 taps), the reference multiplies bf16-rounded taps: within the bf16 bound
+    assert float((y.float() - yr).abs().max() / yr.abs().max()) < 2e-2
+    y2 = CN.conv3x3_fwd(CN.upsample_nearest(x, (2 * H, 2 * W)), CN.pack_weight(w), None, 1, 1)
+    assert float((y.float() - y2.float()).abs().max() / y2.float().abs().max()) < 2e-2
+    # data gradient with the producer's ELU' (ysave = an ELU output, i.e. > -1)
+    gy = torch.randn(B, Cout, 2 * H, 2 * W, generator=g, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    pre = torch.randn(B, Cin, H, W, generator=g, device=dev)
+    ys = F.elu(pre).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    gx = CN.conv3x3_up2_dgrad(gy, wd, dact=1, ysave=ys)
+    lin = F.conv2d(F.interpolate(xr, scale_factor=2, mode="nearest"), w16, None, 1, 1)
+    (gr,) = torch.autograd.grad((lin * gy.float()).sum(), xr)
+    ysf = ys.float()
+    gr = gr * torch.where(ysf > 0, torch.ones_like(ysf), ysf + 1)
+    assert gx.shape == gr.shape
+    assert float((gx.float() - gr).abs().max() / gr.abs().max()) < 2e-2
