@@ -391,6 +391,18 @@ def conv_layer_table(tf_peak, hbm_peak, B=8, iters=8):
                 tot["ours"] += t_o
                 tot["cudnn"] += t_c
                 tot["bound"] += bound
+        if name.startswith("deconv") and H % 2 == 0 and W % 2 == 0 and stride == 1:
+            # the reference's deconv block = nearest 2x up-sampling + this conv: ours runs it as ONE folded kernel on the
+            # low-resolution input (and one folded data-gradient kernel); the library needs interpolate + conv (+ its backward)
+            xl = x[:, :, ::2, ::2].contiguous(memory_format=CL)
+            wf_up, wd_up = CN.pack_up2_weights(w)
+            xl32 = xl.float().contiguous(memory_format=CL)
+            t_o = timeit(lambda: CN.conv3x3_up2_fwd(xl, wf_up, None, 1))
+            t_c = timeit(lambda: F.elu(F.conv2d(F.interpolate(xl, scale_factor=2, mode="nearest"), w16, None, 1, 1)))
+            t_od = timeit(lambda: CN.conv3x3_up2_dgrad(gy, wd_up))
+            row["block_fwd"] = {"ours_folded_us": round(t_o, 1), "cudnn_interpolate_conv_elu_us": round(t_c, 1)}
+            row["block_dgrad"] = {"ours_folded_us": round(t_od, 1)}
+            del xl, xl32, wf_up, wd_up
         rows.append(row)
         del x, w, gy, w16, wk, wd, dW
     torch.backends.cudnn.benchmark = old_bench

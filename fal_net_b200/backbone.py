@@ -129,6 +129,9 @@ def forward(model, image, max_disp, tape=None, disp_lvl=None):
     bb = model.bb
     ENC, DEC = model._spec.enc, model._spec.dec
     B = image.shape[0]
+    sink = getattr(model, "_faln_grad_sink", None)
+    if tape is not None and sink is not None and hasattr(sink, "start_repack"):
+        sink.start_repack(_side_streams(image.device)[0])      # data-gradient weight packs: overlapped with this forward
     flow_val = (max_disp.reshape(B).float() / 100.0).contiguous()                  # :208-209, constant plane per sample
     skips = []
     for i, (name, _, cout, stride) in enumerate(ENC):
