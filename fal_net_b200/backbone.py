@@ -205,13 +205,18 @@ USE_SIDE_STREAM = True      # bench.py switches this off for its per-kernel timi
 # stream is the critical path and more concurrency beside it only takes SMs away from it -- Stage-1 step 5.04 ms with one
 # side stream, 5.26 ms with two to four; Stage-2 15.67 vs 15.97 ms.  Default: one.
 N_SIDE_STREAMS = max(1, int(os.environ.get("FALN_SIDE_STREAMS", "1")))
+# The bias-gradient sums are deliberately small-footprint, long-latency kernels (two blocks per SM): on the weight-gradient
+# stream they add ~0.28 ms of serial latency to a side chain that is now as long as the data-gradient chain.  FALN_BIAS_STREAM=1
+# gives them a stream of their own (same footprint, no serialisation with the weight gradients).
+BIAS_STREAM = os.environ.get("FALN_BIAS_STREAM", "1") not in ("", "0")
 
 
 def _side_streams(dev):
     key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
     st = _SIDE_STREAMS.get(key)
-    if st is None or len(st) != N_SIDE_STREAMS:
-        st = _SIDE_STREAMS[key] = [torch.cuda.Stream(device=key) for _ in range(N_SIDE_STREAMS)]
+    n = N_SIDE_STREAMS + (1 if BIAS_STREAM else 0)
+    if st is None or len(st) != n:
+        st = _SIDE_STREAMS[key] = [torch.cuda.Stream(device=key) for _ in range(n)]
     return st
 
 
@@ -254,13 +259,16 @@ def backward(model, tape, g_logits, sink=None):
     keep = []                                                  # tensors the side streams read stay alive until the join
     turn = [0]
 
-    def on_side(fn, *tensors):
+    def on_side(fn, *tensors, bias=False):
         if not USE_SIDE_STREAM:
             fn()
             return
         keep.extend(tensors)
-        side = sides[turn[0] % len(sides)]
-        turn[0] += 1
+        if bias and BIAS_STREAM:
+            side = sides[-1]                                   # the bias-sum stream
+        else:
+            side = sides[turn[0] % N_SIDE_STREAMS]
+            turn[0] += 1
         ev = torch.cuda.Event()
         ev.record(main)
         side.wait_event(ev)
@@ -283,7 +291,7 @@ def backward(model, tape, g_logits, sink=None):
         def run():
             CN.channel_sum(g, sink.grad_view(name), C)
             ready(name)
-        on_side(run, g)
+        on_side(run, g, bias=True)
 
     def wgrad(name, g_pre, sources, cout, stride=1, const=None):
         """sources: the conv's (concatenated) inputs, in channel order; const = (value[B], in_hw) of a trailing constant

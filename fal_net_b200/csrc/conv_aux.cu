@@ -387,9 +387,9 @@ extern "C" int faln_channel_sum_nhwc(const void* g, float* out, long long npix, 
   // footprint matters as much as its own speed): FALN_CHSUM_CAP = blocks per SM, FALN_CHSUM_UNROLL = 0/1.
   // Measured on B200 (Stage-1 step, gpurun_out/s5_*): 8 blocks/SM 5.36 ms, 4 blocks/SM 5.16 ms, 2 blocks/SM with four
   // loads in flight 5.05 ms -- a small footprint leaves the SMs to the data-gradient chain.
-  static const int cap_per_sm = getenv("FALN_CHSUM_CAP") ? atoi(getenv("FALN_CHSUM_CAP")) : 2;
+  static const int cap_per_sm = getenv("FALN_CHSUM_CAP") ? atoi(getenv("FALN_CHSUM_CAP")) : 1;  // round 2: 1 (own stream, FALN_BIAS_STREAM): 4.37 -> 4.34 ms
   static const int unroll = getenv("FALN_CHSUM_UNROLL") ? atoi(getenv("FALN_CHSUM_UNROLL")) : 1;
-  const long long cap = (long long)sm_count() * (cap_per_sm > 0 ? cap_per_sm : 2);
+  const long long cap = (long long)sm_count() * (cap_per_sm > 0 ? cap_per_sm : 1);
   if (grid > cap) grid = cap;
   if (unroll)
     channel_sum_kernel<true><<<(int)grid, 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(g), out, npix, C8, Cstride / 8, C);

@@ -14,8 +14,21 @@ from __future__ import annotations
 
 import torch
 
+import os
+
 from . import loss_functions as LF
 from . import losses as K
+
+_OVERLAP = os.environ.get("FALN_STAGE2_OVERLAP", "1") not in ("", "0")
+_AUX_STREAMS: dict = {}
+
+
+def _aux_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _AUX_STREAMS.get(key)
+    if st is None:
+        st = _AUX_STREAMS[key] = torch.cuda.Stream(device=key)
+    return st
 
 
 def stage1_loss(model, left, right, min_disp, max_disp, a_p=0.01, a_sm=0.2 * 2 / 512, vgg=None):
@@ -43,12 +56,29 @@ def stage2_loss(model, fix_model, left, right, min_disp, max_disp, a_p=0.01, a_s
     left_f, right_f = torch.flip(left, dims=[3]), torch.flip(right, dims=[3])
     vgg = vgg or LF.vgg
 
-    mldisp = mrdisp = None
-    if a_mr > 0:
-        with torch.no_grad():                                            # :255-264
-            dfix = fix_model(torch.cat((left_f, right), 0), mn2, mx2, ret_disp=True, ret_pan=False, ret_subocc=False)
-            mldisp = torch.flip(dfix[:B], dims=[3]).contiguous()
-            mrdisp = dfix[B:].contiguous()
+    # The frozen model's pass and the VGG features of the two label views depend on the inputs only: they run on a side
+    # stream beside the trainable forward (a parallel branch of the captured step graph), so that one chain's large layers
+    # fill the SMs the other chain's small-map layers leave idle.  FALN_STAGE2_OVERLAP=0 runs them in line.
+    mldisp = mrdisp = vgg_right = vgg_left = None
+    side = _aux_stream(left.device) if _OVERLAP else None
+    main = torch.cuda.current_stream(left.device)
+
+    def frozen_work():
+        nonlocal mldisp, mrdisp, vgg_right, vgg_left
+        with torch.no_grad():
+            if a_mr > 0:                                                 # :255-264
+                dfix = fix_model(torch.cat((left_f, right), 0), mn2, mx2, ret_disp=True, ret_pan=False, ret_subocc=False)
+                mldisp = torch.flip(dfix[:B], dims=[3]).contiguous()
+                mrdisp = dfix[B:].contiguous()
+            if a_p > 0:
+                vgg_right, vgg_left = vgg(right), vgg(left)
+
+    if side is not None:
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            frozen_work()
+    else:
+        frozen_work()
 
     pan, disp, mask0, mask1 = model(torch.cat((left, right_f), 0), mn2, mx2,
                                     ret_disp=True, ret_pan=True, ret_subocc=True)        # :267-271
@@ -56,10 +86,11 @@ def stage2_loss(model, fix_model, left, right, min_disp, max_disp, a_p=0.01, a_s
     rpan, lpan_f = pan[:B], pan[B:]
     ldisp, rdisp_f = disp[:B], disp[B:]
 
-    vgg_right = vgg_left = None
-    if a_p > 0:
-        with torch.no_grad():
-            vgg_right, vgg_left = vgg(right), vgg(left)
+    if side is not None:
+        main.wait_stream(side)
+        for t in (mldisp, mrdisp) + tuple(vgg_right or ()) + tuple(vgg_left or ()):
+            if t is not None:
+                t.record_stream(main)                                    # allocated on the side stream, consumed here
 
     if a_mr > 0:                                                         # :295-299
         O_L = K.occ_mask(mask0[:B], mask1[B:], False, True, 0, c20)      # lmask * unflip(lrmask); first 20 % := 1
