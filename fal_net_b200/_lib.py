@@ -57,6 +57,7 @@ _SIGNATURES = {
     "faln_stem_conv": [_p] * 4 + [_i] * 6 + [_p],
     "faln_upsample_nearest_nhwc": [_p, _p] + [_i] * 6 + [_p],
     "faln_maxpool2_nhwc": [_p, _p] + [_i] * 4 + [_p],
+    "faln_stem_conv_tc": [_p] * 6 + [_i] * 6 + [_p],
     "faln_conv3x3_up2_fwd": [_p] * 4 + [_i] * 8 + [_p],
     "faln_conv3x3_up2_dgrad": [_p] * 4 + [_i] * 8 + [_p],
     "faln_pack_up2_weights": [_p] + [_ll] * 4 + [_p, _p] + [_i] * 4 + [_p],

@@ -244,15 +244,33 @@ def conv3x3_up2_dgrad(g, wd_fold, dact=0, ysave=None):
     return out
 
 
+# FALN_STEM_TC=1: tensor-core stem (one im2col pass to a 32-wide bf16 K vector + a K = 32 tcgen05 GEMM) instead of the
+# fp32-FMA stem kernel.  Measured on B200 (round 2): Stage-1 step 4.345 vs 4.340 ms, Stage-2 13.95 vs 14.11 ms (the
+# 64-channel VGG stem gains), Test flip-PP 7.73 vs 7.65 ms (loses) -- the extra pass over a 64 B/px patch tensor and the tile
+# kernel's per-pixel stores eat what the FMA pipe saves, and it rounds the input image to bf16.  Default: off.
+STEM_TC = __import__("os").environ.get("FALN_STEM_TC", "0") not in ("", "0")
+
+
 def stem_conv(x, w, bias, act, flip_x=False):
-    """fp32 NCHW image [B,3,H,W] -> bf16 channels_last [B,Cout,H,W]; w [Cout,3,3,3] fp32."""
+    """fp32 NCHW image [B,3,H,W] -> bf16 channels_last [B,Cout,H,W]; w [Cout,3,3,3] fp32 (fp32-FMA kernel; see STEM_TC)."""
     x = _lib.f32c(x)
     B, _, H, W = x.shape
     Cout = w.shape[0]
     y = torch.empty((B, Cout, H, W), device=x.device, dtype=torch.bfloat16, memory_format=CL)
-    rc = _lib.lib().faln_stem_conv(_lib.ptr(x), _lib.ptr(w.detach().float().contiguous()),
-                                   _lib.ptr(None if bias is None else bias.detach().float().contiguous()), _lib.ptr(y), B, H,
-                                   W, Cout, int(act), int(flip_x), _lib.cur_stream())
+    wc = w.detach().float().contiguous()
+    bc = None if bias is None else bias.detach().float().contiguous()
+    if STEM_TC:
+        col = torch.empty((B, H, W, 32), device=x.device, dtype=torch.bfloat16)
+        wpack = torch.empty((Cout, 32), device=x.device, dtype=torch.bfloat16)
+        ev = _timed("conv_fwd", 2 * 27 * Cout * B * H * W, 12 * B * H * W + 2 * B * H * W * Cout, Cout)
+        rc = _lib.lib().faln_stem_conv_tc(_lib.ptr(x), _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(y), _lib.ptr(col), _lib.ptr(wpack),
+                                          B, H, W, Cout, int(act), int(flip_x), _lib.cur_stream())
+        _lib.check(rc, "faln_stem_conv_tc")
+        if ev is not None:
+            ev.record()
+        return y
+    rc = _lib.lib().faln_stem_conv(_lib.ptr(x), _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(y), B, H, W, Cout, int(act), int(flip_x),
+                                   _lib.cur_stream())
     _lib.check(rc, "faln_stem_conv")
     return y
 

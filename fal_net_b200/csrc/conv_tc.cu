@@ -1009,3 +1009,86 @@ extern "C" int faln_conv3x3_up2_dgrad(const void* g, const void* wd, void* gx, c
   }
   return dispatch(BK, BN, a1, a1, wm, p, as_stream(stream));
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tensor-core stem (round 2).  The first layer of the encoder (3 -> 32, ELU; /root/reference/models/FAL_netB.py:99) and of
+// VGG19 (3 -> 64, ReLU; /root/reference/loss_functions.py:21) read the fp32 NCHW image.  The fp32-FMA stem kernel
+// (conv_aux.cu) is FMA-bound: 27 x Cout FMAs per pixel, 139 us per 16 images at 64 channels against a ~45 us store floor.
+// Here the 3x3x3 patch of every pixel becomes a 32-wide bf16 K vector (27 taps + 5 zeros; zero padding at the borders;
+// optional horizontal flip) in ONE pass over the image, and the layer is a K = 32 GEMM on the tile kernel (one tap class
+// with a single centre tap), bias / activation in its epilogue.  An extra block of the im2col launch packs the weights.
+// ------------------------------------------------------------------------------------------------------------------
+namespace faln {
+namespace {
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          __nv_bfloat16* __restrict__ col, __nv_bfloat16* __restrict__ wpack,
+                                                          int B, int H, int W, int Cout, int Cout_pad, int flip_x) {
+  if (blockIdx.x == gridDim.x - 1) {               // weight pack: [Cout_pad][32], k = (kh*3 + kw)*3 + c
+    for (int i = threadIdx.x; i < Cout_pad * 32; i += 256) {
+      const int co = i / 32, k = i % 32;
+      float v = 0.f;
+      if (co < Cout && k < 27) {
+        const int c = k % 3, t = k / 3;
+        v = __ldg(w + (co * 3 + c) * 9 + t);
+      }
+      wpack[i] = __float2bfloat16(v);
+    }
+    return;
+  }
+  const long long npx = (long long)B * H * W, hw = (long long)H * W;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < npx; i += (long long)(gridDim.x - 1) * 256) {
+    const int xo = (int)(i % W), y = (int)((i / W) % H);
+    const long long b = i / hw;
+    const float* p = x + b * 3 * hw;
+    __align__(16) __nv_bfloat16 v[32];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = xo + t % 3 - 1;
+      const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      const int xs = flip_x ? W - 1 - xx : xx;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[t * 3 + c] = __float2bfloat16(in ? __ldg(p + c * hw + (long long)yy * W + xs) : 0.f);
+    }
+#pragma unroll
+    for (int k = 27; k < 32; ++k) v[k] = __float2bfloat16(0.f);
+    uint4* o = reinterpret_cast<uint4*>(col + i * 32);
+    const uint4* src = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = src[q];
+  }
+}
+}  // namespace
+}  // namespace faln
+
+// x [B,3,H,W] fp32 NCHW, w [Cout,3,3,3] fp32, bias [Cout] or NULL -> y [B,H,W,Cout] bf16 NHWC (Cout = 32 or 64).
+// col: scratch [B,H,W,32] bf16; wpack: scratch [Cout,32] bf16 (both written by this call).
+extern "C" int faln_stem_conv_tc(const float* x, const float* w, const float* bias, void* y, void* col, void* wpack, int B,
+                                 int H, int W, int Cout, int act, int flip_x, faln_stream_t stream) {
+  FALN_REQUIRE(x && w && y && col && wpack && B > 0 && H > 0 && W > 0, "faln_stem_conv_tc: bad argument");
+  FALN_REQUIRE(Cout == 32 || Cout == 64, "faln_stem_conv_tc: Cout must be 32 or 64 (got %d)", Cout);
+  FALN_REQUIRE(act >= 0 && act <= 2, "faln_stem_conv_tc: act must be 0 (none), 1 (ELU) or 2 (ReLU)");
+  const long long npx = (long long)B * H * W;
+  long long grid = (npx + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  stem_im2col_kernel<<<(int)grid + 1, 256, 0, as_stream(stream)>>>(x, w, static_cast<__nv_bfloat16*>(col),
+                                                                 static_cast<__nv_bfloat16*>(wpack), B, H, W, Cout, Cout, flip_x);
+  int rc = after_launch("stem_im2col_kernel");
+  if (rc != FALN_OK) return rc;
+  ConvParams p{};
+  p.B = B; p.H = H; p.W = W; p.Ho = H; p.Wo = W;
+  p.C1 = 32; p.C2 = 0; p.Cin = 32; p.Cout = Cout;
+  p.stride = 1; p.act = act; p.planar = 0;
+  p.tiles_w = (W + kTW - 1) / kTW; p.tiles_h = (H + kTH - 1) / kTH;
+  p.kblocks1 = 1; p.kblocks2 = 0;
+  p.bias = bias; p.out = y; p.out_c = Cout; p.res_c = Cout;
+  p.out_mul = 1; p.out_H = H; p.out_W = W;
+  p.ncls = 1;
+  p.cls[0].n = 1; p.cls[0].dh[0] = 0; p.cls[0].dw[0] = 0; p.cls[0].wt[0] = 0; p.cls[0].oh = p.cls[0].ow = 0;
+  CUtensorMap a1, wm;
+  if (!make_act_map(&a1, col, B, H, W, 32, 32, 1) || !make_w_map(&wm, wpack, Cout, 32, 32, Cout)) {
+    set_error("faln_stem_conv_tc: cuTensorMapEncodeTiled failed");
+    return FALN_ERR_LAUNCH;
+  }
+  return dispatch(32, Cout, a1, a1, wm, p, as_stream(stream));
+}

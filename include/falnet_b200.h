@@ -246,6 +246,11 @@ int faln_upsample_nearest_nhwc(const void* src, void* dst, int B, int Hi, int Wi
 /* 2x2 stride-2 max pooling (VGG pools, /root/reference/loss_functions.py:21-29) on bf16 NHWC. */
 int faln_maxpool2_nhwc(const void* src, void* dst, int B, int Hi, int Wi, int C, faln_stream_t stream);
 
+/* Tensor-core form of faln_stem_conv: the 3x3x3 patch of every pixel as a 32-wide bf16 K vector (one pass over the image,
+ * zero padding, optional flip) + a K = 32 GEMM on the tcgen05 tile kernel with bias / activation in the epilogue.
+ * col: scratch [B,H,W,32] bf16, wpack: scratch [Cout,32] bf16 (both written by the call).  Same operands / result otherwise. */
+int faln_stem_conv_tc(const float* x, const float* w, const float* bias, void* y, void* col, void* wpack, int B, int H, int W,
+                      int Cout, int act, int flip_x, faln_stream_t stream);
 /* Nearest 2x up-sampling folded into the 3x3 convolution that follows it (the reference's deconv block,
  * /root/reference/models/FAL_netB.py:51-60: F.interpolate(nearest) :58 + conv3x3 + ELU :59), exact-2x sizes only: four taps per
  * output parity class instead of nine, the up-sampled tensor never exists.  x [B,H,W,C1] bf16 NHWC (LOW resolution);

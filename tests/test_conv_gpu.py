@@ -98,6 +98,16 @@ def test_stem_upsample_pool_and_const_channel():
         y = CN.stem_conv(x, w, b, act)
         ref = _ref(x, w, b, 1, act, None)
         assert rel_err(y.float(), ref) < 8e-3
+        # the tensor-core form (FALN_STEM_TC=1): image patch and weights are bf16 operands like every other layer
+        CN.STEM_TC = True
+        try:
+            yt = CN.stem_conv(x, w, b, act)
+            yf = CN.stem_conv(x, w, b, act, flip_x=True)
+        finally:
+            CN.STEM_TC = False
+        ref16 = _ref(x.bfloat16().float(), w.bfloat16().float(), b, 1, act, None)
+        assert rel_err(yt.float(), ref16) < 8e-3 and rel_err(yt.float(), ref) < 2e-2
+        assert rel_err(yf.float(), _ref(torch.flip(x, dims=[3]).bfloat16().float(), w.bfloat16().float(), b, 1, act, None)) < 8e-3
     # nearest upsample, non-integer ratios like the 375x1242 pyramid (24 -> 47, 78 -> 156)
     a = torch.randn(2, 64, 24, 78, generator=g).bfloat16().to(dev).contiguous(memory_format=CL)
     up = CN.upsample_nearest(a, (47, 156))
