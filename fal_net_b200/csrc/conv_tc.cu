@@ -232,11 +232,17 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // Persistent, warp-specialised kernel: a CTA walks work items (tap class, N block, 128-pixel tile) with stride gridDim.x.
 //   warp 0      TMA producer: runs ahead across tiles through the STAGES-deep smem ring
 //   warp 1      MMA issuer: accumulates tile i into TMEM buffer i % 2 while ...
-//   warps 2-5   ... the epilogue warps drain buffer (i - 1) % 2 (tcgen05.ld, bias / residual / activation, stores)
+//   warps 2-9   ... the eight epilogue warps (two per TMEM lane quadrant, alternating 32-column chunks) drain buffer
+//               (i - 1) % 2 (tcgen05.ld, bias / residual / activation, stores).  Round 2: eight instead of four -- on the
+//               layers that give a CTA a single work item the epilogue is not overlapped with anything, and four warps
+//               (one per sub-partition, latency-bound) took ~6 us for a 128 x 256 tile
 // so neither the TMA latency nor the epilogue of a tile is exposed (measured on the one-tile-per-CTA version: ~6 us of
 // serial latency per tile against 0.6 us of tensor work).
+template <int BN>
+constexpr int tc_epi_warps() { return BN >= 128 ? 8 : 4; }   // wide N tiles: two epilogue warps per TMEM lane quadrant
+
 template <int BK, int BN, int STAGES>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(64 + 32 * tc_epi_warps<BN>())
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
   using SL = SmemLayout<BK, BN, STAGES>;
@@ -266,7 +272,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     }
     for (int a = 0; a < kAcc; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);                          // one arrival per epilogue warp
+      mbar_init(&acc_empty[a], tc_epi_warps<BN>());         // one arrival per epilogue warp
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -340,8 +346,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       }
     }
   } else {
-    // ================================================================= epilogue (warps 2..5)
+    // ================================================================= epilogue (warps 2..9)
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    constexpr int kChunkStep = 32 * (tc_epi_warps<BN>() / 4);
+    const int half = (warp - 2) >> 2;     // which warp of the quadrant (0 when there is one): even / odd 32-column chunks
     const int m = quad * 32 + lane;       // row of the tile = pixel
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
@@ -357,7 +365,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * 32; c0 < BN; c0 += kChunkStep) {
         uint32_t r[32];
         tmem_ld32(tacc + c0, r);
         const int cg = n0 + c0;  // first global output channel of this chunk
@@ -635,11 +643,12 @@ int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, C
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::kTotal);
     // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for every kernel that contains tcgen05.alloc (it cannot know
     // the column count), so the co-residency is computed here: shared memory (228 KB per SM, 1 KB reserved per CTA),
-    // TMEM columns (512 per SM) and registers (64 K per SM, __launch_bounds__(192)).
+    // TMEM columns (512 per SM) and registers (64 K per SM, __launch_bounds__(320)).
     int n = (228 * 1024) / (SL::kTotal + 1024);
     const int tmem_cols = 2 * BN < 32 ? 32 : 2 * BN;
     if (n > 512 / tmem_cols) n = 512 / tmem_cols;          // co-resident CTAs must all get their TMEM columns
     if (n > 6) n = 6;
+    if (tc_epi_warps<BN>() == 8 && n > 2) n = 2;            // 320 threads x ~72 registers: two CTAs per SM fit the register file
     if (getenv("FALN_DEBUG")) fprintf(stderr, "conv3x3_tc_kernel<%d,%d,%d>: smem %d, %d CTAs/SM\n", BK, BN, STAGES, SL::kTotal, n);
     per_sm = n < 1 ? 1 : n;
   }
@@ -647,7 +656,7 @@ int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, C
   const long long total = (long long)p.tiles_w * p.tiles_h * p.B * p.nblk * p.ncls;
   long long grid = (long long)sm_count() * per_sm;
   if (grid > total) grid = total;
-  launch_pdl(kern, dim3((unsigned)grid), dim3(192), (size_t)SL::kTotal, st, a1, a2, w, p);
+  launch_pdl(kern, dim3((unsigned)grid), dim3(64 + 32 * tc_epi_warps<BN>()), (size_t)SL::kTotal, st, a1, a2, w, p);
   return after_launch("conv3x3_tc_kernel");
 }
 

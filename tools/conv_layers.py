@@ -20,6 +20,7 @@ ap.add_argument("--ops", default="fwd,dgrad,wgrad")
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--time", action="store_true")
+ap.add_argument("--graph", action="store_true", help="time a CUDA-graph replay of the launches (no host launch overhead)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 CL = torch.channels_last
@@ -51,7 +52,23 @@ for name, cin, cout, H, W, stride in bench._LAYERS:
             CN.conv3x3_wgrad(gy, xp, dW, cout=cout, cx=c, ci_off=o, stride=stride)
     for op in a.ops.split(","):
         fn = {"fwd": fwd, "dgrad": dgrad, "wgrad": wgrad}[op]
-        if a.time:
+        if a.time and a.graph:
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                for _ in range(a.iters):
+                    fn()
+            gr.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gr.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            print(f"{name:24s} {op:6s} {e0.elapsed_time(e1) / a.iters * 1e3:8.1f} us (graph)")
+        elif a.time:
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
