@@ -103,9 +103,18 @@ __device__ __forceinline__ void epilogue_values(const ConvParams& p, const uint3
 #pragma unroll
       for (int j = 0; j < CW; ++j) v[j] += breg[j];
     } else if (p.bias) {
+      if (cg + CW <= p.Cout && (reinterpret_cast<uintptr_t>(p.bias + cg) & 15) == 0) {   // whole chunk: 128-bit loads
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + cg);
 #pragma unroll
-      for (int j = 0; j < CW; ++j)
-        if (cg + j < p.Cout) v[j] += __ldg(p.bias + cg + j);
+        for (int q = 0; q < CW / 4; ++q) {
+          const float4 bq = __ldg(bp + q);
+          v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CW; ++j)
+          if (cg + j < p.Cout) v[j] += __ldg(p.bias + cg + j);
+      }
     }
     if (p.ctab) {
       // a spatially constant extra input channel (the max_disp/100 plane of reference :145,208-209) contributes
@@ -239,7 +248,7 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // so neither the TMA latency nor the epilogue of a tile is exposed (measured on the one-tile-per-CTA version: ~6 us of
 // serial latency per tile against 0.6 us of tensor work).
 template <int BN>
-constexpr int tc_epi_warps() { return BN >= 128 ? 8 : 4; }   // wide N tiles: two epilogue warps per TMEM lane quadrant
+constexpr int tc_epi_warps() { return BN >= 256 ? 16 : (BN >= 128 ? 8 : 4); }   // wide N tiles: 2 / 4 epilogue warps per TMEM lane quadrant
 
 template <int BK, int BN, int STAGES>
 __global__ void __launch_bounds__(64 + 32 * tc_epi_warps<BN>())
@@ -649,6 +658,7 @@ int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, C
     if (n > 512 / tmem_cols) n = 512 / tmem_cols;          // co-resident CTAs must all get their TMEM columns
     if (n > 6) n = 6;
     if (tc_epi_warps<BN>() == 8 && n > 2) n = 2;            // 320 threads x ~72 registers: two CTAs per SM fit the register file
+    if (tc_epi_warps<BN>() == 16 && n > 1) n = 1;           // 576 threads
     if (getenv("FALN_DEBUG")) fprintf(stderr, "conv3x3_tc_kernel<%d,%d,%d>: smem %d, %d CTAs/SM\n", BK, BN, STAGES, SL::kTotal, n);
     per_sm = n < 1 ? 1 : n;
   }
