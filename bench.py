@@ -317,8 +317,9 @@ _LAYERS = (("conv0_1.*", 32, 32, 192, 640, 1), ("conv1.0", 32, 64, 192, 640, 2),
 def conv_layer_table(tf_peak, hbm_peak, B=8, iters=8):
     """Per-layer microseconds of our tcgen05 kernels against cuDNN (bf16, channels_last, cudnn.benchmark autotuned) for the
     forward, data-gradient and weight-gradient of every distinct FAL_netB layer shape at the Stage-1 batch (B = 8, 192x640).
-    Each timed alone (CUDA events, 8 launches after 3 warm-ups; inputs of the big layers exceed L2 only at full
-    resolution -- the small-map layers are L2-resident for BOTH implementations).  `bound_us` = the layer-wise roofline
+    Each timed alone as a CUDA-graph replay of 8 back-to-back launches after 3 warm-ups (no host launch overhead on either
+    side); inputs of the big layers exceed L2 only at full resolution -- the small-map layers are L2-resident for BOTH
+    implementations.  `bound_us` = the layer-wise roofline
     max(flops / tensor peak, bytes / HBM peak); `bound_ss_us` adds the shared-memory operand port of SS-mode tcgen05.mma
     (smem_port_gbs) as a third bound."""
     import torch.nn.functional as F
@@ -330,14 +331,28 @@ def conv_layer_table(tf_peak, hbm_peak, B=8, iters=8):
     g = torch.Generator(device=dev).manual_seed(11)
 
     def timeit(fn):
+        """us per launch of a CUDA-graph replay of `iters` back-to-back launches (no host launch overhead on either side:
+        an eager loop is host-bound below ~25 us per call); eager fallback if the capture fails."""
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
+        try:
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                for _ in range(iters):
+                    fn()
+            gr.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            gr.replay()
+            e1.record()
+        except Exception:
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters * 1e3
 
@@ -406,7 +421,7 @@ def conv_layer_table(tf_peak, hbm_peak, B=8, iters=8):
         rows.append(row)
         del x, w, gy, w16, wk, wd, dW
     torch.backends.cudnn.benchmark = old_bench
-    return {"batch": B, "what": "us per launch, each kernel timed alone; cuDNN = torch conv2d / convolution_backward, bf16 "
+    return {"batch": B, "what": "us per launch (CUDA-graph replay), each kernel timed alone; cuDNN = torch conv2d / convolution_backward, bf16 "
             "channels_last, cudnn.benchmark=True", "sum_ours_us": round(tot["ours"], 1), "sum_cudnn_bf16_us": round(tot["cudnn"], 1),
             "sum_bound_us": round(tot["bound"], 1), "rows": rows}
 
