@@ -128,6 +128,7 @@ class Vgg19_pc(torch.nn.Module):
     BASELINE.json's "random-init weights" benchmark configuration uses."""
 
     _CONV_IDX = (0, 2, 5, 7, 10, 12, 14, 16)
+    _CONV_IDX4 = (19, 21, 23, 25)                      # slice4 (reference :30-32): conv4_1 .. conv4_4, then pool4
 
     def __init__(self, requires_grad=False, seed=2):
         super().__init__()
@@ -145,11 +146,22 @@ class Vgg19_pc(torch.nn.Module):
             [torch.nn.Parameter(sd[f"features.{i}.weight"].clone(), requires_grad=requires_grad) for i in self._CONV_IDX])
         self.biases = torch.nn.ParameterList(
             [torch.nn.Parameter(sd[f"features.{i}.bias"].clone(), requires_grad=requires_grad) for i in self._CONV_IDX])
+        self.weights4 = torch.nn.ParameterList(
+            [torch.nn.Parameter(sd[f"features.{i}.weight"].clone(), requires_grad=False) for i in self._CONV_IDX4])
+        self.biases4 = torch.nn.ParameterList(
+            [torch.nn.Parameter(sd[f"features.{i}.bias"].clone(), requires_grad=False) for i in self._CONV_IDX4])
 
     def forward(self, x, full=False):
-        if full:
-            raise NotImplementedError("slice4 (pool4) is never used on the hot path (reference :36-44)")
-        return tuple(C.vgg_features(list(zip(self.weights, self.biases)), x.float()))
+        outs = tuple(C.vgg_features(list(zip(self.weights, self.biases)), x.float()))
+        if not full:
+            return outs
+        # slice4 (reference :41-43; never used by the losses): forward only -- its output carries no gradient
+        with torch.no_grad():
+            h = outs[2].detach()
+            for w, b in zip(self.weights4, self.biases4):
+                h = C.CN.conv3x3_fwd(h, C._vgg_pack(w, "fwd", lambda w=w: C.CN.pack_weight(w)), b, 1, C._ACT["relu"])
+            h = C.CN.maxpool2(h)
+        return outs + (h,)
 
 
 class _LazyVgg:

@@ -285,3 +285,41 @@ def test_upsample_folded_conv_forward_and_data_gradient(B, Cin, Cout, H, W):
     gr = gr * torch.where(ysf > 0, torch.ones_like(ysf), ysf + 1)
     assert gx.shape == gr.shape
     assert float((gx.float() - gr).abs().max() / gr.abs().max()) < 2e-2
+
+
+def test_vgg_full_returns_the_fourth_slice():
+    """Vgg19_pc(x, full=True) (reference loss_functions.py:36-44): four pooled activations, the fourth after conv4_1..4_4."""
+    from fal_net_b200 import loss_functions as LF
+    dev = torch.device("cuda:0")
+    vgg = LF.Vgg19_pc().to(dev)
+    x = (torch.rand(2, 3, 64, 96, generator=torch.Generator().manual_seed(3)) - 0.43).to(dev)
+    with torch.no_grad():
+        outs = vgg(x, full=True)
+    assert len(outs) == 4 and tuple(outs[3].shape) == (2, 512, 4, 6)
+    h = outs[2].float()
+    for w, b in zip(vgg.weights4, vgg.biases4):
+        h = F.relu(F.conv2d(h.bfloat16().float(), w.bfloat16().float(), b, 1, 1))
+    ref = F.max_pool2d(h, 2, 2)
+    assert rel_err(outs[3].float(), ref) < 2e-2
+
+
+@pytest.mark.parametrize("H,W,stride", [(24, 40, 2), (25, 41, 2), (24, 40, 1), (13, 21, 1)])
+def test_const_channel_weight_gradient_against_autograd(H, W, stride):
+    """the weight gradient of the spatially constant max_disp/100 input plane (border-class sums, one kernel to
+    combine them) against autograd of a conv over an EXPLICIT constant plane -- stride 2 with even and odd sizes, stride 1."""
+    from fal_net_b200 import conv_native as CN
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(H * 7 + W)
+    B, Cout = 3, 64
+    Hg, Wg = (H - 1) // stride + 1, (W - 1) // stride + 1
+    gy = torch.randn(B, Cout, Hg, Wg, generator=g, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    val = torch.tensor([3.0, 1.25, 0.5], device=dev)
+    w = torch.zeros(Cout, 1, 3, 3, device=dev, requires_grad=True)
+    plane = val.view(B, 1, 1, 1).expand(B, 1, H, W).contiguous()
+    y = F.conv2d(plane, w, None, stride, 1)
+    (ref,) = torch.autograd.grad((y * gy.float()).sum(), w)
+    for krsc in (False, True):                                 # plain NCHW gradient tensor and the arena's KRSC layout
+        dW = torch.zeros(Cout, 3, 3, 33, device=dev).permute(0, 3, 1, 2) if krsc else torch.zeros(Cout, 33, 3, 3, device=dev)
+        CN.const_channel_wgrad_into(gy, val, (H, W), stride, Cout, dW, 32)
+        assert rel_err(dW[:, 32], ref[:, 0]) < 1e-5
+        assert float(dW[:, :32].abs().max()) == 0.0

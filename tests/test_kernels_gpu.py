@@ -156,3 +156,28 @@ def test_layout_kernels():
         ref = torch.zeros(2, 3, W, Cp)
         ref[..., :C] = zz.permute(0, 2, 3, 1)
         assert torch.equal(out.cpu().float(), ref.bfloat16().float()), (C, Cp, W)
+
+
+def test_flat_adam_two_param_groups_like_the_reference():
+    """The reference builds Adam with two param groups -- bias_parameters with bias_decay, weight_parameters with weight_decay
+    (Train_Stage1_K.py:177-181).  FlatAdamDDP with distinct decays against torch.optim.Adam on the same parameters / grads."""
+    from fal_net_b200 import models
+    from fal_net_b200.trainer import FlatAdamDDP
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    m = models.FAL_netB(no_levels=9).to(dev)
+    ref = {n: p.detach().clone().requires_grad_(True) for n, p in m.used_parameters()}
+    opt = FlatAdamDDP(m, lr=1e-3, betas=(0.5, 0.999), weight_decay=1e-2, bias_decay=0.0)
+    topt = torch.optim.Adam([{"params": [p for n, p in ref.items() if "bias" in n], "weight_decay": 0.0},
+                             {"params": [p for n, p in ref.items() if "weight" in n], "weight_decay": 1e-2}],
+                            lr=1e-3, betas=(0.5, 0.999))
+    g = torch.Generator(device=dev).manual_seed(1)
+    for _ in range(3):
+        opt.zero_grad()
+        opt.g.copy_(torch.randn(opt.g.shape, generator=g, device=dev) * 1e-2)
+        for n, p in m.used_parameters():
+            ref[n].grad = p.grad.detach().clone().contiguous()
+        opt.step()
+        topt.step()
+    for n, p in m.used_parameters():
+        assert float((p.detach() - ref[n].detach()).abs().max()) < 2e-6, n
