@@ -282,6 +282,174 @@ def reference_gpu(steps=10, warmup=3):
     return out
 
 
+def _dev_ms(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def next_rows_bench(dev, models, steps, LF, FlatAdamDDP, GraphedStep):
+    """SURVEY.md 8(f) rows, measured with the same rules (CUDA events, warm-up, inputs > L2 or rotating):
+    f1 Test_KITTI multi-scale post-processing, f2 validate() metrics, f3 input pipeline, f4 FAL_netA / FAL_netC /
+    Train_Stage1_Kslow steps.  Where the reference's own module for the row imports here (baseline/_ref myUtils.py,
+    data_transforms.py: host code by construction) it is timed beside ours on one host core, as its DataLoader worker /
+    validate() loop would run it."""
+    import importlib.util
+    import random as _random
+    import time as _time
+    import numpy as np
+    from fal_net_b200 import input_pipeline as IP, myUtils as MU, postproc
+    out = {}
+    N = 49
+    mx8 = torch.full((8, 1, 1), 300.0, device=dev)
+    mn8 = mx8 * 2 / 300
+
+    def ref_module(name):
+        p = os.path.join(ROOT, "baseline", "_ref", name + ".py")
+        if not os.path.exists(p):
+            return None
+        spec = importlib.util.spec_from_file_location("falnet_ref_" + name, p)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+
+    # ---- f1: multi-scale post-processing (Test_KITTI.py:287-300), 8 images at 375x1242 ----
+    try:
+        torch.manual_seed(0)
+        model = models.FAL_netB(no_levels=N).to(dev).eval()
+        imgs = [synth_batch(8, 375, 1242, 77 + i)[0].to(dev) for i in range(3)]
+        it = [0]
+
+        def f_mspp():
+            it[0] += 1
+            return steps.test_disp(model, imgs[it[0] % 3], mn8, mx8, ms_post_process=True)
+
+        def f_plain():
+            it[0] += 1
+            return steps.test_disp(model, imgs[it[0] % 3], mn8, mx8)
+        ms_m, ms_p = _dev_ms(f_mspp), _dev_ms(f_plain)
+        disp = f_plain()
+        small = postproc.flip_resize_bilinear(imgs[0], scale_factor=2 / 3, flip_x=True)
+        d2 = model(small, mn8, mx8, ret_disp=True, ret_pan=False, ret_subocc=False)
+        p95 = postproc.percentile_rows(disp, 95.0, add=1e-6)
+        out["f1_ms_pp"] = {"ms_per_8_images": ms_m, "frames_per_s": 8 / (ms_m / 1e3), "plain_pass_ms": ms_p,
+                           "kernels_us": {"flip_resize_bilinear": 1e3 * _dev_ms(lambda: postproc.flip_resize_bilinear(imgs[0], scale_factor=2 / 3, flip_x=True)),
+                                          "percentile_rows": 1e3 * _dev_ms(lambda: postproc.percentile_rows(disp, 95.0, add=1e-6)),
+                                          "mspp_blend": 1e3 * _dev_ms(lambda: postproc.mspp_blend(disp, d2, p95, 1.5))},
+                           "what": "disparity pass + 2/3-scale flipped pass + per-image 95th percentile + blend, B=8 375x1242"}
+        del model, imgs, disp, small, d2
+    except Exception as e:
+        out["f1_ms_pp"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    torch.cuda.empty_cache()
+
+    # ---- f2: validate() metrics (Train_Stage1_K.py:279-347), one batch of 8 at 375x1242 ----
+    try:
+        g = torch.Generator(device=dev).manual_seed(5)
+        disp = 2 + 60 * torch.rand(8, 1, 375, 1242, device=dev, generator=g)
+        tgt = (2 + 60 * torch.rand(8, 1, 375, 1242, device=dev, generator=g)) * (torch.rand(8, 1, 375, 1242, device=dev, generator=g) < 0.25)
+        a_ = torch.rand(8, 3, 375, 1242, device=dev, generator=g) - 0.4
+        b_ = torch.rand(8, 3, 375, 1242, device=dev, generator=g) - 0.4
+
+        def f_ours():
+            return MU.kitti_errors_batch(tgt, disp, "Kitti2015"), LF.realEPE(disp, tgt, sparse=True), MU.get_rmse(a_, b_)
+        ms_o = _dev_ms(f_ours)
+        row = {"ours_ms_per_batch8": ms_o, "what": "7 KITTI errors + EPE + RMSE for 8 images 375x1242, device-resident, no host sync"}
+        RU = ref_module("myUtils")
+        if RU is not None:
+            def f_ref():
+                td, pd_ = tgt.squeeze(1).cpu().numpy(), disp.squeeze(1).cpu().numpy()
+                gt_d, pr_d = RU.disps_to_depths_kitti2015(td, pd_)
+                return [RU.compute_kitti_errors(gt_d[i], pr_d[i]) for i in range(len(gt_d))], RU.get_rmse(a_, b_)
+            f_ref()
+            torch.cuda.synchronize()
+            t0 = _time.perf_counter()
+            for _ in range(3):
+                f_ref()
+            torch.cuda.synchronize()
+            row["reference_ms_per_batch8"] = (_time.perf_counter() - t0) / 3 * 1e3
+            row["reference_what"] = "reference myUtils.py as validate() calls it (.cpu().numpy() + numpy per image), wall clock"
+        out["f2_metrics"] = row
+        del disp, tgt, a_, b_
+    except Exception as e:
+        out["f2_metrics"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    torch.cuda.empty_cache()
+
+    # ---- f3: input pipeline (data_transforms.py + Train_Stage1_K.py:115-128), 8 pairs 375x1242 -> 192x640 ----
+    try:
+        r = np.random.RandomState(3)
+        raw = [(r.randint(0, 256, (375, 1242, 3)).astype(np.uint8), r.randint(0, 256, (375, 1242, 3)).astype(np.uint8))
+               for _ in range(8)]
+        lefts = [torch.from_numpy(a).to(dev) for a, _ in raw]
+        rights = [torch.from_numpy(b).to(dev) for _, b in raw]
+        aug = IP.GpuStereoAugment((192, 640))
+        _random.seed(0)
+        np.random.seed(0)
+        params = [aug.sample(375, 1242) for _ in range(8)]
+        ms_dev = _dev_ms(lambda: aug(lefts, rights, params=params))
+        torch.cuda.synchronize()
+        t0 = _time.perf_counter()
+        for _ in range(5):
+            aug(lefts, rights, params=params)
+        torch.cuda.synchronize()
+        ms_wall = (_time.perf_counter() - t0) / 5 * 1e3
+        row = {"ours_ms_per_8_pairs_device_stream": ms_dev, "ours_ms_per_8_pairs_wall_incl_host_tables": ms_wall,
+               "pairs_per_s_wall": 8 / (ms_wall / 1e3),
+               "what": "decoded uint8 pairs resident on the device -> normalised fp32 crops; host half = Pillow-exact coefficient / value tables"}
+        DT = ref_module("data_transforms")
+        if DT is not None:
+            import torchvision.transforms as T
+            co = DT.Compose([DT.RandomResizeCrop((192, 640), down=0.75, up=1.5), DT.RandomHorizontalFlip(),
+                             DT.RandomGamma(min=0.8, max=1.2), DT.RandomBrightness(min=0.5, max=2.0),
+                             DT.RandomCBrightness(min=0.8, max=1.2)])
+            tf = T.Compose([DT.ArrayToTensor(), T.Normalize(mean=[0, 0, 0], std=[255, 255, 255]),
+                            T.Normalize(mean=[0.411, 0.432, 0.45], std=[1, 1, 1])])
+            _random.seed(0)
+            np.random.seed(0)
+            t0 = _time.perf_counter()
+            for a, b in raw:
+                inputs, _ = co([a.copy(), b.copy()], None)
+                _ = [tf(x) for x in inputs]
+            ms_ref = (_time.perf_counter() - t0) * 1e3
+            row["reference_ms_per_8_pairs_one_worker"] = ms_ref
+            row["reference_pairs_per_s_4_workers"] = 4 * 8 / (ms_ref / 1e3)
+            row["reference_what"] = "reference co-transforms + input transform on one host core (its DataLoader runs 4 such workers)"
+        out["f3_input_pipeline"] = row
+        del lefts, rights
+    except Exception as e:
+        out["f3_input_pipeline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    torch.cuda.empty_cache()
+
+    # ---- f4: FAL_netA / FAL_netC Stage-1 steps and the Train_Stage1_Kslow step (B = 8, 192x640, N = 49, graph replay) ----
+    left, right = [t.to(dev) for t in synth_batch(8, 192, 640, 99)]
+    for name, ctor, slow in (("FAL_netA", "FAL_netA", False), ("FAL_netC", "FAL_netC", False), ("Kslow_FAL_netB", "FAL_netB", True)):
+        try:
+            torch.manual_seed(0)
+            model = getattr(models, ctor)(no_levels=N).to(dev)
+            opt = FlatAdamDDP(model, lr=1e-4)
+            vgg = LF.vgg if slow else None
+
+            def loss_fn(l, r_, model=model, slow=slow, vgg=vgg):
+                if slow:
+                    return steps.stage1_slow_loss(model, l, r_, mn8, mx8, a_p=0.01, vgg=vgg)["loss"]
+                return steps.stage1_loss(model, l, r_, mn8, mx8, a_p=0.0)[0]
+            gs = GraphedStep(opt, loss_fn, left, right, warmup=3)
+            ms = _dev_ms(lambda: gs.run(left, right), iters=20)
+            out["f4_" + name] = {"ms_per_step": ms, "frames_per_s": 8 / (ms / 1e3),
+                                 "params_m": sum(p.numel() for p in model.parameters()) / 1e6}
+            del gs, opt, model
+        except Exception as e:
+            out["f4_" + name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+    return out
+
+
 def med_microbench(hbm_peak, peak_src, iters=10):
     """BASELINE configs[4]: the six MED microbench shapes (N = 33 / 49 / 65 at 8x375x1242 and 2x1024x2048), fwd (pan + disp),
     fwd + both occlusion masks, bwd; GB/s = algorithmic bytes of SURVEY.md 8(d) / CUDA-event time; three rotating buffer sets
@@ -453,7 +621,7 @@ def main():
     ap.add_argument("--sample-b", type=int, default=None, help="--impl reference: images (pairs) per step of the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--extras", default="stage2,test,med,reference_gpu,conv_layers",
+    ap.add_argument("--extras", default="stage2,test,med,reference_gpu,conv_layers,next_rows",
                     help="comma list of the sub-lines to attach (med / reference_gpu / conv_layers only at N = 1)")
     ap.add_argument("--no-graph", action="store_true", help="launch the training step kernel by kernel instead of replaying its CUDA graph")
     a = ap.parse_args()
@@ -514,6 +682,8 @@ def main():
             extras["med"] = med_microbench(hbm_peak, peak_src)
         if "conv_layers" in wanted:
             extras["conv_layers"] = conv_layer_table(tf_peak, hbm_peak)
+        if "next_rows" in wanted:
+            extras["next_rows"] = next_rows_bench(dev, models, steps, LF, FlatAdamDDP, GraphedStep)
         torch.cuda.empty_cache()
         if "reference_gpu" in wanted:
             extras["reference_gpu"] = _subprocess_json(["--impl", "reference_gpu", "--steps", "10"], timeout=240)
