@@ -59,6 +59,8 @@ struct ConvParams {
   const float* disp_lvl;  // [B, Cout] disparity of each level
   float* disp_out;        // [B, 1, H, W] fp32; when set nothing else is written (the logits never reach HBM)
   int tma_out;            // row kernel: bf16 NHWC output staged in shared memory and written by TMA (tensor map tmY)
+  int tile_h, tile_b;     // split-K kernel: the 128-pixel tile is tile_b images x tile_h rows x 16 columns (tile_b * tile_h = 8)
+  int tiles_b;            // split-K kernel: ceil(B / tile_b)
 };
 
 // K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -385,6 +387,203 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[a]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ split-K cluster kernel
+// Small feature maps (3x10 ... 12x40 at the KITTI crop) give the tile kernel at most a few dozen 128-pixel tiles with K loops
+// of 36 ... 72 steps: every CTA pulls its 16 KB + BN * 128 B per step through ONE SM's L2 port (~64 B/clk measured), 14 - 24 us
+// per layer where cuDNN needs 7 - 10 (per-layer table).  Here ONE work item (tap class, N block, tile) belongs to
+// a thread-block CLUSTER of SPLIT CTAs:
+//   * CTA `rank` runs K steps [rank * ksteps / SPLIT, (rank + 1) * ksteps / SPLIT) of the same (tap, channel block) loop
+//     into its own TMEM accumulator -- SPLIT SMs' worth of L2 ports and tensor pipes per tile, wide N tiles stay affordable
+//   * the partial accumulators are reduce-scattered over DISTRIBUTED SHARED MEMORY in 16-column chunks: chunk c belongs to
+//     rank (c / kSub) % SPLIT; a CTA sends the chunks it does not own straight from TMEM registers into the owner's staging
+//     buffer (st.shared::cluster), one cluster barrier, then every CTA finishes its own columns (bias, residual,
+//     activation ... the same epilogue_values as everywhere) -- no atomics, no second kernel, fixed summation order
+//   * the tile itself spans images when the map is shorter than 8 rows (tile_b x tile_h x 16 pixels, a 4-D TMA box with a
+//     batch extent), so a 3x10 map fills 60 of the 128 MMA rows instead of 30.
+// One work item per cluster, no persistence (these layers have fewer items than SMs); warp roles as in the tile kernel.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int BN, int SPLIT>
+struct SplitCfg {
+  static constexpr int kChunks = BN / 16;                              // 16-column chunks of the tile
+  static constexpr int kOwn = kChunks / SPLIT;                         // chunks a CTA finishes
+  static constexpr int kSub = kOwn >= 2 ? 2 : 1;                       // epilogue warps per TMEM lane quadrant
+  static constexpr int kThreads = 64 + 128 * kSub;
+  static constexpr int kStaging = (SPLIT - 1) * kOwn * 4 * 128 * 16;   // [sender slot][own chunk][float4 q][row] float4
+  static constexpr int kStage = 128 * 64 * 2 + BN * 64 * 2;            // BK = 64
+  static constexpr int kStagesFit = (218 * 1024 - kStaging) / kStage;
+  static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
+  static constexpr int kTotal = 1024 + kStages * kStage + kStaging + 1024;
+  static_assert(kChunks % SPLIT == 0 && kOwn % kSub == 0 && kStages >= 2, "unsupported split-K shape");
+};
+
+template <int BN, int SPLIT>
+__global__ void __launch_bounds__(SplitCfg<BN, SPLIT>::kThreads)
+conv3x3_splitk_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                      const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+  using CF = SplitCfg<BN, SPLIT>;
+  constexpr int BK = 64, STAGES = CF::kStages, kSub = CF::kSub;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  extern __shared__ unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  unsigned char* stages = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1024 + 1023) & ~uintptr_t(1023));
+  unsigned char* staging = stages + (size_t)STAGES * CF::kStage;      // same offset in every CTA of the cluster
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int w = blockIdx.x / SPLIT;                                   // work item = (cls * tiles + tile) * nblk + nb
+  const int tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+  const int kb = p.kblocks1 + p.kblocks2;
+  const int nb = w % p.nblk, tile = (w / p.nblk) % tiles;
+  const TapClass& tc = p.cls[w / (p.nblk * tiles)];
+  const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tb = tile / (p.tiles_w * p.tiles_h);
+  const int n0 = nb * BN;
+  const int ksteps = tc.n * kb;
+  const int k_lo = rank * ksteps / SPLIT, k_hi = (rank + 1) * ksteps / SPLIT;   // the host guarantees ksteps >= SPLIT
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmW);
+    if (p.kblocks2) prefetch_tmap(&tmA2);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  cluster_arrive();   // #1: "this CTA runs, its shared memory exists" -- waited for before the first remote store
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int k = k_lo; k < k_hi; ++k) {
+        const int t = k / kb, cb = k - t * kb;
+        const int tap = tc.wt[t];
+        const int hi = th * p.tile_h * p.stride + tc.dh[t], wi = tw * kTW * p.stride + tc.dw[t];
+        mbar_wait(&empty[s], ph ^ 1);
+        unsigned char* a_dst = stages + (size_t)s * CF::kStage;
+        unsigned char* b_dst = a_dst + 128 * BK * 2;
+        mbar_arrive_expect_tx(&full[s], CF::kStage);
+        if (cb < p.kblocks1) {
+          tma_load_4d(a_dst, &tmA1, cb * BK, wi, hi, tb * p.tile_b, &full[s]);
+          tma_load_2d(b_dst, &tmW, tap * p.Cin + cb * BK, n0, &full[s]);
+        } else {
+          tma_load_4d(a_dst, &tmA2, (cb - p.kblocks1) * BK, wi, hi, tb * p.tile_b, &full[s]);
+          tma_load_2d(b_dst, &tmW, tap * p.Cin + p.C1 + (cb - p.kblocks1) * BK, n0, &full[s]);
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int k = k_lo; k < k_hi; ++k) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(stages + (size_t)s * CF::kStage);
+        const uint64_t adesc = make_desc<BK>(a_addr);
+        const uint64_t bdesc = make_desc<BK>(a_addr + 128 * BK * 2);
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) umma_bf16(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k != k_lo) || kk != 0);
+        umma_commit(&empty[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+  }
+  __syncwarp();
+  cluster_wait();     // #1
+
+  // ---- epilogue warps 2 .. 2 + 4 * kSub: quadrant = warp & 3 (the TMEM lanes a warp may read), sub = which of the quadrant's warps
+  const int quad = warp & 3, sub = (warp - 2) >> 2;
+  const int m = quad * 32 + lane;                                     // tile row = pixel (bb, hh, ww)
+  const int per_img = p.tile_h * kTW;
+  const int bb = m / per_img, hh = (m / kTW) % p.tile_h, ww = m % kTW;
+  const int b = tb * p.tile_b + bb;
+  const int ho = (th * p.tile_h + hh) * p.out_mul + tc.oh, wo = (tw * kTW + ww) * p.out_mul + tc.ow;
+  const bool valid = b < p.B && ho < p.out_H && wo < p.out_W;
+  const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16);
+  const uint32_t stg = smem_u32(staging);
+  if (warp >= 2) {
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = sub; c < CF::kChunks; c += kSub) {                   // send the chunks other ranks own
+      const int owner = (c / kSub) % SPLIT;
+      if (owner == rank) continue;
+      uint32_t r[16];
+      tmem_ld16(tacc + c * 16, r);
+      if (!valid) continue;
+      const int slot = (rank - owner + SPLIT) % SPLIT - 1;
+      const int lc = (c / (kSub * SPLIT)) * kSub + sub;                // index among the owner's chunks
+      const uint32_t dst = mapa_u32(stg + (uint32_t)(((slot * CF::kOwn + lc) * 4) * 128 + m) * 16, (uint32_t)owner);
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) st_cluster_v4(dst + qd * 128 * 16, r[4 * qd], r[4 * qd + 1], r[4 * qd + 2], r[4 * qd + 3]);
+    }
+  }
+  __syncwarp();
+  cluster_arrive();   // #2: release the partial sums ...
+  cluster_wait();     //     ... and acquire the ones sent to this CTA
+  if (warp >= 2) {
+    const size_t pix = ((size_t)b * p.out_H + ho) * p.out_W + wo;
+#pragma unroll 1
+    for (int c = sub; c < CF::kChunks; c += kSub) {
+      if ((c / kSub) % SPLIT != rank) continue;
+      uint32_t r[16];
+      tmem_ld16(tacc + c * 16, r);
+      const int cg = n0 + c * 16;
+      if (!valid || cg >= p.Cout) continue;
+      const int lc = (c / (kSub * SPLIT)) * kSub + sub;
+#pragma unroll
+      for (int slot = 0; slot < SPLIT - 1; ++slot) {
+        const float4* src = reinterpret_cast<const float4*>(staging) + ((slot * CF::kOwn + lc) * 4) * 128 + m;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const float4 a = src[qd * 128];
+          r[4 * qd] = __float_as_uint(__uint_as_float(r[4 * qd]) + a.x);
+          r[4 * qd + 1] = __float_as_uint(__uint_as_float(r[4 * qd + 1]) + a.y);
+          r[4 * qd + 2] = __float_as_uint(__uint_as_float(r[4 * qd + 2]) + a.z);
+          r[4 * qd + 3] = __float_as_uint(__uint_as_float(r[4 * qd + 3]) + a.w);
+        }
+      }
+      epilogue_store<16>(p, r, cg, pix, b, ho, wo);
     }
   }
   tc_fence_before();
@@ -787,6 +986,113 @@ int dispatch(int BK, int BN, const CUtensorMap& a1, const CUtensorMap& a2, const
   }
 }
 
+// ---- split-K cluster kernel: host side -------------------------------------------------------------------------
+template <int BN, int SPLIT>
+int launch_split(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const ConvParams& p, long long items,
+                 cudaStream_t st, int* max_clusters) {
+  using CF = SplitCfg<BN, SPLIT>;
+  auto kern = conv3x3_splitk_kernel<BN, SPLIT>;
+  static int resident = 0;   // clusters the device can hold at once (GPC topology x one CTA per SM at this shared-memory size)
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(items > 0 ? items * SPLIT : SPLIT));
+  cfg.blockDim = dim3(CF::kThreads);
+  cfg.dynamicSmemBytes = CF::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = SPLIT;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (resident == 0) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::kTotal);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = (sm_count() * 7 / 8) / SPLIT;   // conservative: GPCs are not all the same size
+    }
+    resident = n;
+    if (getenv("FALN_DEBUG")) fprintf(stderr, "conv3x3_splitk_kernel<%d,%d>: smem %d, %d stages, %d resident clusters\n", BN, SPLIT, CF::kTotal, CF::kStages, n);
+  }
+  if (max_clusters) {        // query only
+    *max_clusters = resident;
+    return 0;
+  }
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a1, a2, w, p);
+  if (e != cudaSuccess) {
+    set_error("conv3x3_splitk_kernel launch failed: %s", cudaGetErrorString(e));
+    return FALN_ERR_LAUNCH;
+  }
+  return after_launch("conv3x3_splitk_kernel");
+}
+
+int split_call(int BN, int SPLIT, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const ConvParams& p,
+               long long items, cudaStream_t st, int* max_clusters) {
+  if (BN == 128) {
+    if (SPLIT == 8) return launch_split<128, 8>(a1, a2, w, p, items, st, max_clusters);
+    if (SPLIT == 4) return launch_split<128, 4>(a1, a2, w, p, items, st, max_clusters);
+    if (SPLIT == 2) return launch_split<128, 2>(a1, a2, w, p, items, st, max_clusters);
+  } else if (BN == 64) {
+    if (SPLIT == 4) return launch_split<64, 4>(a1, a2, w, p, items, st, max_clusters);
+    if (SPLIT == 2) return launch_split<64, 2>(a1, a2, w, p, items, st, max_clusters);
+  }
+  return FALN_ERR_ARG;
+}
+
+// Decides between the tile kernel (BN_cur as narrowed by the caller) and the split-K cluster kernel with a cost model in
+// "KB through one SM's L2 port" (the measured bound of these layers): K steps per CTA x (A tile + B tile) + the partial sums
+// exchanged over DSMEM.  Only layers whose work items fit one wave are considered.  Returns 1 if launched, 0 if the caller
+// should go on with the tile kernel, < 0 on error.  FALN_CONV_SPLITK=0 disables; FALN_CONV_SPLITK_PCT = cost ratio (%) below
+// which the split kernel is taken.
+int try_splitk(const void* x, const void* x2, int C2, const void* wptr, int wrows, int wcols, ConvParams p, int BK, int BN_cur,
+               cudaStream_t st) {
+  static const int enabled = getenv("FALN_CONV_SPLITK") ? atoi(getenv("FALN_CONV_SPLITK")) : 1;
+  static const int pct = getenv("FALN_CONV_SPLITK_PCT") ? atoi(getenv("FALN_CONV_SPLITK_PCT")) : 75;
+  if (!enabled || BK != 64 || p.disp_out) return 0;
+  const int kb = p.kblocks1 + p.kblocks2;
+  int min_steps = 1 << 30, max_steps = 0;
+  for (int c = 0; c < p.ncls; ++c) {
+    min_steps = p.cls[c].n * kb < min_steps ? p.cls[c].n * kb : min_steps;
+    max_steps = p.cls[c].n * kb > max_steps ? p.cls[c].n * kb : max_steps;
+  }
+  const long long cur_items = (long long)p.tiles_w * p.tiles_h * p.B * ((p.Cout + BN_cur - 1) / BN_cur) * p.ncls;
+  if (cur_items > sm_count()) return 0;
+  const double cost_cur = (double)max_steps * (16 + BN_cur / 8);
+  const int th = p.Ho >= 5 ? 8 : (p.Ho >= 3 ? 4 : 2), tb = 8 / th;
+  const int tiles_h = (p.Ho + th - 1) / th, tiles_b = (p.B + tb - 1) / tb;
+  const long long tiles = (long long)p.tiles_w * tiles_h * tiles_b;
+  static const int cand[5][2] = {{128, 8}, {128, 4}, {128, 2}, {64, 4}, {64, 2}};
+  int best = -1;
+  double best_cost = cost_cur * pct / 100.0;
+  for (int i = 0; i < 5; ++i) {
+    const int BN = cand[i][0], S = cand[i][1];
+    if (wrows % BN != 0 || min_steps < S) continue;
+    const long long items = tiles * ((p.Cout + BN - 1) / BN) * p.ncls;
+    int resident = 0;
+    CUtensorMap dummy{};
+    if (split_call(BN, S, dummy, dummy, dummy, p, 0, st, &resident) != 0 || items > resident) continue;
+    const double cost = (double)((max_steps + S - 1) / S) * (16 + BN / 8) + 2.0 * (BN / 2) * (S - 1) / S;
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = i;
+    }
+  }
+  if (best < 0) return 0;
+  const int BN = cand[best][0], S = cand[best][1];
+  p.tile_h = th; p.tile_b = tb; p.tiles_h = tiles_h; p.tiles_b = tiles_b;
+  p.nblk = (p.Cout + BN - 1) / BN;
+  CUtensorMap a1, a2, wm;
+  if (!make_act_map(&a1, x, p.B, p.H, p.W, p.C1, BK, p.stride, th, tb) || !make_w_map(&wm, wptr, wrows, wcols, BK, BN) ||
+      (x2 && !make_act_map(&a2, x2, p.B, p.H, p.W, C2, BK, p.stride, th, tb))) {
+    set_error("conv3x3 split-K kernel: cuTensorMapEncodeTiled failed");
+    return FALN_ERR_LAUNCH;
+  }
+  if (!x2) a2 = a1;
+  const int rc = split_call(BN, S, a1, a2, wm, p, tiles * p.nblk * p.ncls, st, nullptr);
+  return rc == 0 ? 1 : rc;
+}
+
 }  // namespace
 }  // namespace faln
 
@@ -838,6 +1144,10 @@ static int conv3x3_fwd_impl(const void* x, const void* x2, const void* w, const 
   if (disp_out) {
     set_error("faln_conv3x3_logits_disp: layer not eligible for the row-tile kernel (needs stride 1, W >= 192, Cout_pad == 64)");
     return FALN_ERR_ARG;
+  }
+  {
+    const int rr = try_splitk(x, x2, C2, w, Cout_pad, 9 * (C1 + C2), p, BK, BN, as_stream(stream));
+    if (rr != 0) return rr > 0 ? 0 : rr;
   }
   CUtensorMap a1, a2, wm;
   if (!make_act_map(&a1, x, B, H, W, C1, BK, stride) || !make_w_map(&wm, w, Cout_pad, 9 * (C1 + C2), BK, BN) ||
@@ -932,6 +1242,10 @@ extern "C" int faln_conv3x3_dgrad(const void* g, const void* wd, void* gx, const
     const int rr = try_row_kernel(g, nullptr, wd, Cx_pad, p, BK, 0, as_stream(stream));
     if (rr != 0) return rr > 0 ? 0 : rr;
   }
+  {
+    const int rr = try_splitk(g, nullptr, 0, wd, Cx_pad, 9 * Cg, p, BK, BN, as_stream(stream));
+    if (rr != 0) return rr > 0 ? 0 : rr;
+  }
   CUtensorMap a1, wm;
   if (!make_act_map(&a1, g, B, Hg, Wg, Cg, BK, 1) || !make_w_map(&wm, wd, Cx_pad, 9 * Cg, BK, BN)) {
     set_error("faln_conv3x3_dgrad: cuTensorMapEncodeTiled failed (driver entry point missing or bad tensor geometry)");
@@ -980,6 +1294,10 @@ extern "C" int faln_conv3x3_up2_fwd(const void* x, const void* w, const float* b
           c.wt[a * 2 + b] = (signed char)((ph * 2 + pw) * 4 + a * 2 + b);
         }
     }
+  {
+    const int rr = try_splitk(x, nullptr, 0, w, Cout_pad, 16 * C1, p, BK, BN, as_stream(stream));
+    if (rr != 0) return rr > 0 ? 0 : rr;
+  }
   CUtensorMap a1, wm;
   if (!make_act_map(&a1, x, B, H, W, C1, BK, 1) || !make_w_map(&wm, w, Cout_pad, 16 * C1, BK, BN)) {
     set_error("faln_conv3x3_up2_fwd: cuTensorMapEncodeTiled failed");
@@ -1021,6 +1339,10 @@ extern "C" int faln_conv3x3_up2_dgrad(const void* g, const void* wd, void* gx, c
       p.cls[0].dw[r * 4 + c] = (signed char)(c - 1);
       p.cls[0].wt[r * 4 + c] = (signed char)(r * 4 + c);
     }
+  {
+    const int rr = try_splitk(g, nullptr, 0, wd, Cx, 16 * Cg, p, BK, BN, as_stream(stream));
+    if (rr != 0) return rr > 0 ? 0 : rr;
+  }
   CUtensorMap a1, wm;
   if (!make_act_map(&a1, g, B, 2 * H, 2 * W, Cg, BK, 2) || !make_w_map(&wm, wd, Cx, 16 * Cg, BK, BN)) {
     set_error("faln_conv3x3_up2_dgrad: cuTensorMapEncodeTiled failed");

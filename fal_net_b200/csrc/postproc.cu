@@ -8,6 +8,8 @@
 //
 // Everything here is HBM / latency bound and tiny next to the network passes; the point is that nothing forces a
 // device-to-host synchronisation inside the evaluation loop.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace faln {
@@ -45,7 +47,12 @@ __global__ void __launch_bounds__(256) flip_resize_bilinear_kernel(const float* 
 // ---------------------------------------------------------------------------------------------------------------
 // q-th percentile of every row of x [B, n] (numpy.percentile, method 'linear'), exact: three radix-select passes over the
 // order-preserving integer image of the floats (11 + 11 + 10 bits) give the k-th order statistic, a fourth pass the
-// next larger value when the (k+1)-th differs.  One CTA per row; shared-memory histograms.
+// next larger value when the (k+1)-th differs.
+// A row is one thread-block CLUSTER of kPctCluster CTAs (round 2: one CTA per row took 226 us for 8 x 466 k values -- a
+// single SM's load bandwidth plus 32-way same-address shared atomics, disparities fall into a few dozen of the 2048 first-pass
+// bins): every CTA histograms its interleaved slice into its own shared memory with warp-aggregated atomics, the
+// histograms are summed over distributed shared memory by every CTA (identical result everywhere, so no broadcast), and
+// the bin search runs redundantly per CTA.
 // out[b] = (float)(p + add), p computed in fp64 like numpy's lerp on its float64 virtual index.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned f2ord(float f) {
@@ -88,12 +95,21 @@ __device__ void pick_bin(const unsigned* hist, int nb, unsigned long long r, uns
   }
 }
 
-__global__ void __launch_bounds__(1024) percentile_rows_kernel(const float* __restrict__ x, long long n, long long stride,
-                                                               double q, double add, float* __restrict__ out) {
-  __shared__ unsigned hist[2048];
+constexpr int kPctCluster = 8;
+
+__global__ void __cluster_dims__(kPctCluster, 1, 1) __launch_bounds__(1024)
+percentile_rows_kernel(const float* __restrict__ x, long long n, long long stride, double q, double add,
+                       float* __restrict__ out) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ unsigned hist[2048];    // this CTA's slice (read by the other CTAs of the cluster)
+  __shared__ unsigned merged[2048];  // the row's histogram
   __shared__ unsigned s_bin, s_cnt, s_min;
   __shared__ unsigned long long s_r;
-  const float* row = x + (long long)blockIdx.x * stride;
+  const int rank = (int)cluster.block_rank();
+  const int row_id = blockIdx.x / kPctCluster;
+  const float* row = x + (long long)row_id * stride;
+  const long long first = (long long)rank * 1024 + threadIdx.x, step = 1024LL * kPctCluster;
   const double vi = q * (double)(n - 1);
   unsigned long long k = (unsigned long long)floor(vi);
   const double t = vi - (double)k;
@@ -106,12 +122,23 @@ __global__ void __launch_bounds__(1024) percentile_rows_kernel(const float* __re
     const unsigned himask = pass == 0 ? 0u : (pass == 1 ? 0xffe00000u : 0xfffffc00u);
     for (int i = threadIdx.x; i < nb; i += 1024) hist[i] = 0;
     __syncthreads();
-    for (long long i = threadIdx.x; i < n; i += 1024) {
-      const unsigned o = f2ord(row[i]);
-      if ((o & himask) == prefix) atomicAdd(&hist[(o >> shift) & (nb - 1)], 1u);
+    for (long long i = first; i < n; i += step) {
+      const unsigned o = f2ord(__ldg(row + i));
+      if ((o & himask) == prefix) {
+        const unsigned bin = (o >> shift) & (nb - 1);
+        const unsigned peers = __match_any_sync(__activemask(), bin);     // one atomic per distinct bin of the warp
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+      }
     }
-    __syncthreads();
-    pick_bin(hist, nb, r, &s_bin, &s_r, &s_cnt);
+    cluster.sync();                                  // every slice histogram is complete and visible
+    for (int i = threadIdx.x; i < nb; i += 1024) {
+      unsigned sum = 0;
+#pragma unroll
+      for (int c = 0; c < kPctCluster; ++c) sum += cluster.map_shared_rank(hist, c)[i];
+      merged[i] = sum;
+    }
+    cluster.sync();                                  // all remote reads of hist done before anyone zeroes it again
+    pick_bin(merged, nb, r, &s_bin, &s_r, &s_cnt);
     __syncthreads();
     prefix |= s_bin << shift;
     r = s_r;
@@ -120,27 +147,33 @@ __global__ void __launch_bounds__(1024) percentile_rows_kernel(const float* __re
   }
   const unsigned uk = prefix;  // exact k-th order statistic; r = its rank among the cnt_last copies of that value
   unsigned uk1 = uk;
-  if (t > 0.0 && r + 1 >= cnt_last) {  // the (k+1)-th is the smallest value greater than uk
+  const bool need_next = t > 0.0 && r + 1 >= cnt_last;  // the (k+1)-th is the smallest value greater than uk (uniform over the cluster)
+  if (need_next) {
     if (threadIdx.x == 0) s_min = 0xffffffffu;
     __syncthreads();
     unsigned m = 0xffffffffu;
-    for (long long i = threadIdx.x; i < n; i += 1024) {
-      const unsigned o = f2ord(row[i]);
+    for (long long i = first; i < n; i += step) {
+      const unsigned o = f2ord(__ldg(row + i));
       if (o > uk && o < m) m = o;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMin(&s_min, m);
-    __syncthreads();
-    uk1 = s_min == 0xffffffffu ? uk : s_min;
+    cluster.sync();
+    if (rank == 0 && threadIdx.x == 0) {
+      unsigned mm = 0xffffffffu;
+      for (int c = 0; c < kPctCluster; ++c) mm = min(mm, *cluster.map_shared_rank(&s_min, c));
+      uk1 = mm == 0xffffffffu ? uk : mm;
+    }
   }
-  if (threadIdx.x == 0) {
+  if (rank == 0 && threadIdx.x == 0) {
     const double a = (double)ord2f(uk), b = (double)ord2f(uk1);
     // numpy _lerp: a + (b - a) * t, switched to b - (b - a) * (1 - t) for t >= 0.5
     const double d = b - a;
     const double p = t >= 0.5 ? b - d * (1.0 - t) : a + d * t;
-    out[blockIdx.x] = (float)(p + add);
+    out[row_id] = (float)(p + add);
   }
+  cluster.sync();   // no CTA leaves while its shared memory may still be read by rank 0
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -345,7 +378,7 @@ extern "C" int faln_flip_resize_bilinear(const float* in, float* out, int BC, in
 extern "C" int faln_percentile_rows(const float* x, int B, long long n, long long stride, double q, double add, float* out,
                                     faln_stream_t stream) {
   FALN_REQUIRE(x && out && B > 0 && n > 0 && stride >= n && q >= 0.0 && q <= 1.0, "faln_percentile_rows: bad argument");
-  percentile_rows_kernel<<<B, 1024, 0, as_stream(stream)>>>(x, n, stride, q, add, out);
+  percentile_rows_kernel<<<B * kPctCluster, 1024, 0, as_stream(stream)>>>(x, n, stride, q, add, out);
   return after_launch("percentile_rows_kernel");
 }
 

@@ -92,12 +92,13 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   return fn;
 }
 
-bool make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int BK, int stride, int rows = 8) {
+bool make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int BK, int stride, int rows = 8,
+                  int images = 1) {
   auto fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(kTW * stride), (cuuint32_t)(rows * stride), 1};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(kTW * stride), (cuuint32_t)(rows * stride), (cuuint32_t)images};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,

@@ -36,6 +36,14 @@ def _ref(x, w, b, stride, act, res):
     (2, 7, 333, 32, 0, 32, 1, 1, False, True),       # BK=32 (64B swizzle), 16 columns per epilogue warp
     (1, 5, 257, 64, 64, 64, 1, 1, True, False),      # two sources
     (1, 6, 200, 128, 0, 64, 1, 2, True, False),      # two K blocks of one source, ReLU
+    # small maps at the training batch: the split-K cluster kernel (K loop shared by 2 / 4 / 8 CTAs, DSMEM reduce-scatter)
+    (8, 6, 20, 256, 0, 256, 1, 1, True, True),       # conv5_1: BN 128 x 4 CTAs
+    (8, 3, 10, 512, 0, 512, 1, 1, True, False),      # conv6_1: tiles of 2 images x 4 rows, 8 CTAs per tile
+    (5, 2, 7, 256, 0, 256, 1, 0, False, False),      # tiles of 4 images x 2 rows, ragged batch
+    (8, 12, 40, 256, 0, 256, 2, 1, True, False),     # conv5.0: stride 2 into a 6x20 map
+    (8, 6, 20, 256, 256, 256, 1, 1, True, False),    # iconv6: two sources
+    (3, 1, 5, 128, 0, 128, 1, 2, True, False),       # one-row map
+    (8, 6, 20, 256, 0, 64, 1, 0, True, False),       # one N block of 64
 ])
 def test_conv3x3_bf16_nhwc(B, H, W, C1, C2, Cout, stride, act, bias, res):
     from fal_net_b200 import conv_native as CN
@@ -146,6 +154,12 @@ def _elu_grad_from_y(y):
     (2, 9, 640, 64, 64, 1, 1, False, False),       # row-tile kernel (wide map, one N block)
     (1, 7, 333, 32, 32, 1, 1, False, True),
     (1, 6, 260, 64, 49, 1, 0, False, False),
+    # split-K cluster kernel
+    (8, 6, 20, 256, 256, 1, 1, False, True),
+    (8, 12, 40, 256, 256, 2, 1, True, False),      # stride 2 (four tap classes of 1 / 2 / 2 / 4 taps), accumulate
+    (5, 3, 10, 512, 512, 1, 1, False, False),
+    (8, 11, 39, 256, 256, 2, 0, False, False),     # stride 2, odd sizes
+    (8, 6, 20, 512, 256, 1, 0, False, False),      # concat split: two row ranges of the re-packed weights
 ])
 def test_conv3x3_dgrad(B, H, W, Cin, Cout, stride, dact, accum, res):
     from fal_net_b200 import conv_native as CN
@@ -249,11 +263,29 @@ def test_vgg_slices_forward_and_input_gradient():
     for o, r in zip(outs, refs):
         assert float((o.float() - r).abs().max() / r.abs().max()) < 2e-2
     assert gx.shape == gr.shape and gx.dtype == torch.float32
-    assert float((gx - gr).norm() / gr.norm()) < 3e-2, float((gx - gr).norm() / gr.norm())
+    # yardstick: the same slices through cuDNN's bf16 convolutions (torch autocast).  A ReLU / arg-max decision taken on an
+    # activation one bf16 ulp away re-routes a gradient discretely, so the error of ANY bf16 implementation against the fp32
+    # chain is a few 1e-2 here and moves with the summation order; the rule is the one of tests/test_reference_gpu.py:
+    # ours <= max(2e-2, 1.5 x cuDNN-bf16).
+    xa = x.detach().clone().requires_grad_(True)
+    h, i, outs_a = xa, 0, []
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        for v in VGG_CFG:
+            if v == "M":
+                h = F.max_pool2d(h, 2, 2)
+                outs_a.append(h)
+            else:
+                h = F.relu(F.conv2d(h, vgg.weights[i], vgg.biases[i], 1, 1))
+                i += 1
+    (ga,) = torch.autograd.grad(sum((o.float() * c).sum() for o, c in zip(outs_a, cots)), xa)
+    yard = float((ga - gr).norm() / gr.norm())
+    e = float((gx - gr).norm() / gr.norm())
+    assert e < max(2e-2, 1.5 * yard), (e, yard)
 
 
 @pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 64, 64, 24, 40), (1, 256, 128, 6, 10), (2, 128, 64, 13, 21), (1, 512, 256, 3, 10),
-                                            (2, 64, 64, 96, 320)])
+                                            (2, 64, 64, 96, 320),
+                                            (8, 512, 256, 3, 10), (8, 256, 128, 6, 20), (3, 256, 128, 5, 9)])  # split-K cluster kernel
 def test_upsample_folded_conv_forward_and_data_gradient(B, Cin, Cout, H, W):
     """deconv block (nearest 2x up-sampling + conv3x3 + ELU, reference :51-60) as ONE kernel with folded weights: forward
     against fp32 F.interpolate + conv2d on the same bf16 operands, data gradient (w.r.t. the LOW-resolution input, times the

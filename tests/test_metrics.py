@@ -110,17 +110,25 @@ def test_device_flip_resize_and_blend_match_aten(B, H, W):
 
 @pytest.mark.gpu
 def test_ms_pp_per_image_semantics_batch_vs_single():
-    """with B > 1, ms_pp of the batch equals ms_pp of each image alone (the percentile is per image)."""
+    """with B > 1, ms_pp of the batch equals ms_pp of each image alone (the percentile is per image).  The three
+    images get disparity ranges 1 : 0.3 : 0.6, so a percentile taken over the batch would move the blend weights of the
+    second image by a factor ~3.  Tolerance: the convolution kernels are planned per launch shape (a batch of 3 and a batch
+    of 1 use different tilings / K splits, like cuDNN's per-shape algorithm choice), so the two runs are two bf16 evaluations
+    of the network: the 2e-2 of BASELINE's north_star, not bit equality."""
     from fal_net_b200 import models, steps
-    from tests.helpers import disp_range
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     m = models.FAL_netB(no_levels=49).to(dev)
     B, H, W = 3, 96, 320
     img = images(B, H, W, 21).to(dev)
-    img[1] *= 0.3                                                # different disparity distributions per image
-    mn, mx = (t.to(dev) for t in disp_range(B))
+    mx = torch.tensor([300.0, 90.0, 180.0], device=dev).view(B, 1, 1)
+    mn = mx * 2 / 300
     whole = steps.test_disp(m, img, mn, mx, ms_post_process=True)
+    plain = steps.test_disp(m, img, mn, mx)
+    p_all = float(np.percentile(plain.cpu().numpy(), 95))
     for b in range(B):
         one = steps.test_disp(m, img[b:b + 1], mn[b:b + 1], mx[b:b + 1], ms_post_process=True)
-        assert rel_err(whole[b:b + 1], one) < 1e-4, b
+        assert rel_err(whole[b:b + 1], one) < 2e-2, b
+    # the discriminating power of the check: image 1's own percentile is far from the batch's
+    p_1 = float(np.percentile(plain[1:2].cpu().numpy(), 95))
+    assert p_1 < 0.6 * p_all, (p_1, p_all)
