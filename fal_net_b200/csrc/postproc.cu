@@ -96,6 +96,7 @@ __device__ void pick_bin(const unsigned* hist, int nb, unsigned long long r, uns
 }
 
 constexpr int kPctCluster = 8;
+constexpr int kPctUnroll = 8;
 
 __global__ void __cluster_dims__(kPctCluster, 1, 1) __launch_bounds__(1024)
 percentile_rows_kernel(const float* __restrict__ x, long long n, long long stride, double q, double add,
@@ -122,12 +123,18 @@ percentile_rows_kernel(const float* __restrict__ x, long long n, long long strid
     const unsigned himask = pass == 0 ? 0u : (pass == 1 ? 0xffe00000u : 0xfffffc00u);
     for (int i = threadIdx.x; i < nb; i += 1024) hist[i] = 0;
     __syncthreads();
-    for (long long i = first; i < n; i += step) {
-      const unsigned o = f2ord(__ldg(row + i));
-      if ((o & himask) == prefix) {
-        const unsigned bin = (o >> shift) & (nb - 1);
-        const unsigned peers = __match_any_sync(__activemask(), bin);     // one atomic per distinct bin of the warp
-        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+    for (long long i0 = first; i0 < n; i0 += step * kPctUnroll) {          // kPctUnroll independent loads in flight per thread
+      float v[kPctUnroll];
+#pragma unroll
+      for (int u = 0; u < kPctUnroll; ++u) v[u] = i0 + u * step < n ? __ldg(row + i0 + u * step) : 0.f;
+#pragma unroll
+      for (int u = 0; u < kPctUnroll; ++u) {
+        const unsigned o = f2ord(v[u]);
+        if (i0 + u * step < n && (o & himask) == prefix) {
+          const unsigned bin = (o >> shift) & (nb - 1);
+          const unsigned peers = __match_any_sync(__activemask(), bin);   // one atomic per distinct bin of the warp
+          if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+        }
       }
     }
     cluster.sync();                                  // every slice histogram is complete and visible
@@ -152,9 +159,15 @@ percentile_rows_kernel(const float* __restrict__ x, long long n, long long strid
     if (threadIdx.x == 0) s_min = 0xffffffffu;
     __syncthreads();
     unsigned m = 0xffffffffu;
-    for (long long i = first; i < n; i += step) {
-      const unsigned o = f2ord(__ldg(row + i));
-      if (o > uk && o < m) m = o;
+    for (long long i0 = first; i0 < n; i0 += step * kPctUnroll) {
+      float v[kPctUnroll];
+#pragma unroll
+      for (int u = 0; u < kPctUnroll; ++u) v[u] = i0 + u * step < n ? __ldg(row + i0 + u * step) : 0.f;
+#pragma unroll
+      for (int u = 0; u < kPctUnroll; ++u) {
+        const unsigned o = f2ord(v[u]);
+        if (i0 + u * step < n && o > uk && o < m) m = o;
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
