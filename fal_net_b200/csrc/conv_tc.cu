@@ -80,7 +80,9 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : (__expf(v) - 1.0f); }
+// ELU with the flush-to-zero hardware exponential (MUFU.EX2 without the denormal range fix-up __expf compiles to: 5 instead
+// of 10 instructions per value in the epilogues, which are issue-bound -- DESIGN.md 5)
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : (ex2f(v * 1.4426950408889634f) - 1.0f); }
 
 template <int BK, int BN, int STAGES>
 struct SmemLayout {
@@ -98,13 +100,13 @@ struct SmemLayout {
 // nullptr to read p.bias per call (tile kernel: the N block changes from work item to work item).
 template <int CW>
 __device__ __forceinline__ void epilogue_values(const ConvParams& p, const uint32_t (&r)[CW], const float* breg, int cg,
-                                                size_t pix, int b, int ho, int wo, float (&v)[CW]) {
+                                                size_t pix, int b, int ho, int wo, float (&v)[CW], bool bias_done = false) {
 #pragma unroll
     for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
     if (breg) {
 #pragma unroll
       for (int j = 0; j < CW; ++j) v[j] += breg[j];
-    } else if (p.bias) {
+    } else if (p.bias && !bias_done) {
       if (cg + CW <= p.Cout && (reinterpret_cast<uintptr_t>(p.bias + cg) & 15) == 0) {   // whole chunk: 128-bit loads
         const float4* bp = reinterpret_cast<const float4*>(p.bias + cg);
 #pragma unroll
@@ -238,6 +240,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // Persistent, warp-specialised kernel: a CTA walks work items (tap class, N block, 128-pixel tile) with stride gridDim.x.
@@ -828,6 +831,359 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------ column-walk kernel
+// The row kernel above still reads the A operand once per tap: 9 x (4 KB A + CO * 32 B of B) per 128-pixel K16 step, 192 B per
+// tensor clock at CO = 64 against the SM's 128 B/clk shared-memory port ("what bounds the convolutions").  Here a
+// CTA walks DOWN a 128-pixel column strip and turns the three vertical taps into extra N columns instead of extra A reads:
+// input row r contributes to the output rows r, r + 1 and r - 1 (vertical tap offsets 0, -1, +1), so ONE instruction with
+// N = 3 * CO multiplies the row's window by the three taps' weights [B0 | B1 | B2] and accumulates into three TMEM
+// accumulators that live in slots (output row mod 3) of a 3 * CO-column bank; the horizontal taps stay shifted windows of
+// the row.  Per K16 step and horizontal tap the port now moves 4 KB of A + 3 * CO * 32 B of B for 3x the MACs: 104 B per
+// tensor clock at CO = 64 (tensor-bound), and every input row is fetched ONCE (a [BK, 130, 1] box) instead of three times.
+//   * slot order: the three slots hold (B0,B1,B2), (B2,B0,B1) or (B1,B2,B0) for r mod 3 = 0, 1, 2; blocks that are adjacent
+//     both in the weight tile and in TMEM go out as one instruction (N = 3 CO, or 2 CO + CO)
+//   * the block of the NEW output row r + 1 starts its accumulator (accumulate flag off at the row's first K step, which is
+//     therefore issued block by block); output row q is complete after input row q + 1 and is drained by the epilogue warps
+//     while the tensor pipe works on the CTA's SECOND strip: two banks (2 x 3 x CO TMEM columns), row-steps alternate
+//   * work = the flattened (image, column strip, row) sequence cut into 2 x gridDim.x chains; a chain restarts (one extra,
+//     one-block row-step above and below) where it crosses into another strip; rows -1 and H are zero boxes (TMA bounds).
+// Epilogue arithmetic, weight residency and the TMA-staged output are the row kernel's (the store is issued by a dedicated
+// warp here).  fwd and stride-1 dgrad differ only in TapClass.
+// STATUS (round 2, measured on B200; opt-in with FALN_CONV_COL=1, off by default): parity-green on every row-kernel test
+// shape plus six of its own (tests/test_conv_gpu.py), but not yet faster than the row kernel: 64 -> 64 at 8x192x640 94 us vs
+// 81 us, 32 -> 32 47 vs 38 us, 96 -> 64 138 vs 126 us.  clock64() timelines of one CTA (recorded while developing it) show
+// where the time goes: the tensor side needs ~1,600 clk per row-step (12 - 24 instructions; the row kernel needs ~2,180 clk
+// for its 36) but the eight epilogue warps need ~2,350 clk per drained row (bias + ELU ~1,190 clk -- MUFU-bound at 512 --,
+// staging ~380, TMEM read / zero / barriers ~450) and with ONE CTA per SM (384 TMEM columns) nothing else overlaps them, whereas
+// the row kernel's epilogue (~1,800 clk per tile) hides under its longer MMA phase.  What would make it pay: sixteen epilogue
+// warps (16 columns each) and a packed-half exponential, or two CTAs per SM with the weights shared through a cluster.
+// Lessons already folded in: a single copy of each role's loop body (two unrolled copies overflowed the instruction cache: 30 % of
+// the stall samples were no_inst), 32-bit descriptor arithmetic and no per-instruction predicates in the issuing thread (the first
+// version spent ~1,100 instructions per row-step there), TMEM zeroing by the epilogue warps instead of accumulate-flag logic.
+struct ColWalker {
+  int t, t1, H, tiles_w;
+  int b, tw, h0, h1, r;
+  bool in_run;
+  __device__ __forceinline__ void init(long long t0_, long long t1_, int H_, int tiles_w_) {
+    t = (int)t0_; t1 = (int)t1_; H = H_; tiles_w = tiles_w_; in_run = false;
+    b = tw = h0 = h1 = r = 0;
+  }
+  // next row-step (input row r of the run of output rows [h0, h1] in strip (b, tw)); false when the chain is exhausted
+  __device__ __forceinline__ bool next() {
+    if (in_run && r <= h1) { ++r; return true; }
+    if (in_run) { t += h1 - h0 + 1; in_run = false; }
+    if (t >= t1) return false;
+    h0 = t % H;
+    const int col = t / H;
+    tw = col % tiles_w; b = col / tiles_w;
+    h1 = h0 + (t1 - t) - 1;
+    if (h1 > H - 1) h1 = H - 1;
+    r = h0 - 1;
+    in_run = true;
+    return true;
+  }
+};
+
+template <int BK, int CO>
+struct ColSmem {
+  static constexpr int kRow = (kHaloCols * BK * 2 + 1023) / 1024 * 1024;   // one input row [130 px][BK] (swizzled rows)
+  static constexpr int kW = CO * BK * 2;                                  // one (tap, channel block) weight tile
+  static constexpr int kBars = 1024;
+  static constexpr int kOut = 128 * CO * 2;
+  static int total(int kb, int stages) { return kBars + 1024 + 9 * kb * kW + stages * kRow + 2 * kOut; }
+};
+
+template <int BK, int CO>
+__global__ void __launch_bounds__(352)
+conv3x3_col_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY, const ConvParams p,
+                   const int nstages) {
+  using SL = ColSmem<BK, CO>;
+  constexpr int kMaxStages = 12;
+  constexpr uint32_t kTmemCols = 6 * CO <= 256 ? 256 : 512;
+  constexpr int kBank = kTmemCols / 2;                          // TMEM columns between the two banks (3 * CO used)
+  constexpr int CW = CO / 2;
+  extern __shared__ unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* acc_full = empty + kMaxStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* wfull = acc_empty + 2;
+  uint64_t* out_full = wfull + 1;                              // staged output tile complete (8 epilogue warps)
+  uint64_t* out_empty = out_full + 2;                          // ... and read out by the TMA store (store warp)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(out_empty + 2);
+  float* sbias = reinterpret_cast<float*>(smem_raw + 512);     // [CO] bias (zeros when the layer has none)
+  unsigned char* wsm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + SL::kBars + 1023) & ~uintptr_t(1023));
+  const int kb = p.kblocks1 + p.kblocks2;
+  unsigned char* stages = wsm + (size_t)9 * kb * SL::kW;
+  unsigned char* otile = stages + (size_t)nstages * SL::kRow;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long T = (long long)p.tiles_w * p.H * p.B;
+  const TapClass& tc = p.cls[0];
+  // the CTA's two chains; every role walks them alternately with ONE copy of its loop body (`cur` / `oth` swap each turn:
+  // two unrolled copies of the epilogue overflowed the instruction cache -- 30 % of all stall samples were no_inst)
+  ColWalker cur, oth;
+  {
+    const long long c = 2LL * blockIdx.x, nch = 2LL * gridDim.x;
+    cur.init(c * T / nch, (c + 1) * T / nch, p.H, p.tiles_w);
+    oth.init((c + 1) * T / nch, (c + 2) * T / nch, p.H, p.tiles_w);
+  }
+  bool alive_cur = cur.next(), alive_oth = oth.next();
+  int be = 0;                                                   // bank of `cur`
+  auto swap_chains = [&]() {
+    const ColWalker tmp = cur; cur = oth; oth = tmp;
+    const bool ta = alive_cur; alive_cur = alive_oth; alive_oth = ta;
+    be ^= 1;
+  };
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmW);
+    if (p.kblocks2) prefetch_tmap(&tmA2);
+    if (p.tma_out) prefetch_tmap(&tmY);
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 8);
+    }
+    mbar_init(wfull, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&out_full[a], 8);
+      mbar_init(&out_empty[a], 1);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + CO) sbias[threadIdx.x - 64] = (p.bias && (int)threadIdx.x - 64 < p.Cout) ? __ldg(p.bias + threadIdx.x - 64) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ================================================================= TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wfull, 9 * kb * SL::kW);
+      for (int t = 0; t < 9; ++t) {
+        const int dwi = tc.dw[t] + 1, j = tc.dh[t] == 0 ? 0 : (tc.dh[t] < 0 ? 1 : 2);
+        for (int cb = 0; cb < kb; ++cb) {
+          const int col = tc.wt[t] * p.Cin + (cb < p.kblocks1 ? cb * BK : p.C1 + (cb - p.kblocks1) * BK);
+          tma_load_2d(wsm + (size_t)((cb * 3 + dwi) * 3 + j) * SL::kW, &tmW, col, 0, wfull);
+        }
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      while (alive_cur || alive_oth) {
+        if (alive_cur) {
+          const ColWalker& k = cur;
+          for (int cb = 0; cb < kb; ++cb) {
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], kHaloCols * BK * 2);
+            unsigned char* dst = stages + (size_t)s * SL::kRow;
+            if (cb < p.kblocks1) tma_load_4d(dst, &tmA1, cb * BK, k.tw * kRowW - 1, k.r, k.b, &full[s]);
+            else tma_load_4d(dst, &tmA2, (cb - p.kblocks1) * BK, k.tw * kRowW - 1, k.r, k.b, &full[s]);
+            if (++s == nstages) { s = 0; ph ^= 1; }
+          }
+          alive_cur = cur.next();
+        }
+        swap_chains();
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    if (lane == 0) {
+      // Every row-step issues ALL three blocks with the accumulate flag on -- the accumulators are zeroed by the epilogue
+      // warps (tcgen05.st after a slot is drained; all three slots after a run's last drain and at kernel start), so rows
+      // outside the run only ever add into slots that are re-zeroed before they carry a real row.  That keeps this loop
+      // free of per-instruction predicates: the issuing thread was the bottleneck of the first version of this kernel
+      // (~1100 instructions per row-step for 36 MMAs; ncu: it never waited for data or for the epilogue).
+      // Block j sits in slot (rho + j) % 3 for j = 0, 1 and (rho + 2) % 3 for j = 2, rho = r mod 3:
+      //   rho 0: [B0 B1 B2] -> slots 0,1,2 (one instruction);  rho 1: [B0 B1] -> 1,2 and [B2] -> 0;  rho 2: [B1 B2] -> 0,1 and [B0] -> 2
+      constexpr uint32_t idesc1 = make_idesc<CO>(), idesc2 = make_idesc<2 * CO>(), idesc3 = make_idesc<3 * CO>();
+      constexpr uint32_t kDescHi = (uint32_t)((((uint64_t)(8 * BK * 2) >> 4) << 32 | (1ULL << 46) | ((uint64_t)(BK == 64 ? 2 : 4) << 61)) >> 32);
+      const uint32_t w_lo = ((smem_u32(wsm) & 0x3FFFF) >> 4) | (1u << 16);
+      const uint32_t st_lo = ((smem_u32(stages) & 0x3FFFF) >> 4) | (1u << 16);
+      mbar_wait(wfull, 0);
+      tc_fence_after();
+      int s = 0;
+      uint32_t ph = 0;
+      int nd_cur = 1, nd_oth = 1;                               // drains signalled per bank (+1: the initial zeroing)
+      while (alive_cur || alive_oth) {
+        if (alive_cur) {
+          const ColWalker& k = cur;
+          const int rho = (k.r + 3) % 3;                          // r >= -1
+          // segment A (always) and segment B (rho != 0): TMEM column offset, weight-block offset (>> 4), instruction descriptor
+          const uint32_t bank = tmem_base + (uint32_t)(be * kBank);
+          const uint32_t dA = bank + (uint32_t)((rho == 2 ? 0 : rho) * CO), dB = bank + (uint32_t)((rho == 1 ? 0 : 2) * CO);
+          const uint32_t bA = rho == 2 ? (uint32_t)(SL::kW >> 4) : 0u, bB = rho == 1 ? (uint32_t)((2 * SL::kW) >> 4) : 0u;
+          const uint32_t iA = rho == 0 ? idesc3 : idesc2;
+          const bool two = rho != 0;
+          const bool edge = k.r <= k.h0;
+          mbar_wait(&acc_empty[be], (uint32_t)((nd_cur & 1) ^ 1));   // the slot the new output row takes is drained and zeroed
+          tc_fence_after();
+          for (int cb = 0; cb < kb; ++cb) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t a_lo = st_lo + (uint32_t)(s * (SL::kRow >> 4));
+            const uint32_t b_lo = w_lo + (uint32_t)(cb * ((9 * SL::kW) >> 4));
+            if (!edge) {
+#pragma unroll
+              for (int dwi = 0; dwi < 3; ++dwi) {
+#pragma unroll
+                for (int kk = 0; kk < BK / 16; ++kk) {
+                  const uint32_t al = a_lo + (uint32_t)(((dwi * BK * 2) >> 4) + 2 * kk);
+                  const uint32_t bl = b_lo + (uint32_t)(((dwi * 3 * SL::kW) >> 4) + 2 * kk);
+                  umma_bf16_lo(dA, al, bl + bA, kDescHi, iA);
+                  if (two) umma_bf16_lo(dB, al, bl + bB, kDescHi, idesc1);
+                }
+              }
+            } else {
+              // the first two row-steps of a run (r = h0 - 1, h0): only the blocks of rows inside the run, one by one -- the
+              // slots of rows h0 + 1 and h0 + 2 must still be zero when their first contribution arrives
+#pragma unroll
+              for (int dwi = 0; dwi < 3; ++dwi) {
+#pragma unroll
+                for (int kk = 0; kk < BK / 16; ++kk) {
+                  const uint32_t al = a_lo + (uint32_t)(((dwi * BK * 2) >> 4) + 2 * kk);
+                  const uint32_t bl = b_lo + (uint32_t)(((dwi * 3 * SL::kW) >> 4) + 2 * kk);
+                  if (k.r == k.h0) umma_bf16_lo(bank + (uint32_t)(rho * CO), al, bl, kDescHi, idesc1);
+                  umma_bf16_lo(bank + (uint32_t)(((rho + 1) % 3) * CO), al, bl + (uint32_t)(SL::kW >> 4), kDescHi, idesc1);
+                }
+              }
+            }
+            umma_commit(&empty[s]);
+            if (++s == nstages) { s = 0; ph ^= 1; }
+          }
+          if (k.r >= k.h0 + 1) {                                  // output row r - 1 is complete
+            umma_commit(&acc_full[be]);
+            ++nd_cur;
+          }
+          alive_cur = cur.next();
+        }
+        swap_chains();
+        { const int tn = nd_cur; nd_cur = nd_oth; nd_oth = tn; }
+      }
+    }
+  } else if (warp == 10) {
+    // ================================================================= TMA store warp (staged bf16 NHWC output)
+    if (lane == 0 && p.tma_out) {
+      int it = 0;
+      while (alive_cur || alive_oth) {
+        if (alive_cur) {
+          const ColWalker& k = cur;
+          if (k.r >= k.h0 + 1) {
+            mbar_wait(&out_full[it & 1], (uint32_t)((it >> 1) & 1));
+            tma_store_3d(&tmY, otile + (size_t)(it & 1) * SL::kOut, 0, k.tw * kRowW, k.b * p.H + k.r - 1);
+            if (it > 0) {
+              tma_store_wait_read1();
+              mbar_arrive(&out_empty[(it - 1) & 1]);
+            }
+            ++it;
+          }
+          alive_cur = cur.next();
+        }
+        swap_chains();
+      }
+      tma_store_wait_all();
+    }
+  } else {
+    // ================================================================= epilogue (warps 2..9)
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int m = quad * 32 + lane;
+    // zero this warp's part (its 32 TMEM lanes x CW columns) of all six accumulator slots, then open both banks
+    const uint32_t tpart = tmem_base + (uint32_t)(half * CW) + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+    for (int sl = 0; sl < 6; ++sl) tmem_zero<CW>(tpart + (uint32_t)((sl / 3) * kBank + (sl % 3) * CO));
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&acc_empty[0]);
+      mbar_arrive(&acc_empty[1]);
+    }
+    int nd_cur = 0, nd_oth = 0;
+    int it = 0;
+    while (alive_cur || alive_oth) {
+      if (alive_cur) {
+        const ColWalker& k = cur;
+        if (k.r >= k.h0 + 1) {
+          const int h = k.r - 1, tw = k.tw, b = k.b;
+          const int wo = tw * kRowW + m;
+          const bool valid = wo < p.W;
+          const size_t pix = ((size_t)b * p.H + h) * p.W + wo;
+          mbar_wait(&acc_full[be], (uint32_t)(nd_cur & 1));
+          ++nd_cur;
+          tc_fence_after();
+          uint32_t r[CW];
+          const uint32_t taddr = tmem_base + (uint32_t)(be * kBank + (h % 3) * CO + half * CW) + ((uint32_t)(quad * 32) << 16);
+          if (CW == 32) tmem_ld32(taddr, reinterpret_cast<uint32_t(&)[32]>(r));
+          else tmem_ld16(taddr, reinterpret_cast<uint32_t(&)[16]>(r));
+          // the drained slot carries output row r + 2 next: zero it; after the run's last row zero the whole bank (rows
+          // outside the run have added into the other two slots)
+          if (k.r == k.h1 + 1) {
+#pragma unroll
+            for (int sl = 0; sl < 3; ++sl) tmem_zero<CW>(tpart + (uint32_t)(be * kBank + sl * CO));
+          } else {
+            tmem_zero<CW>(taddr);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[be]);
+          const int cg = half * CW;
+          {
+            const float4* sb = reinterpret_cast<const float4*>(sbias + cg);   // warp-uniform address: one broadcast per load
+#pragma unroll
+            for (int qd = 0; qd < CW / 4; ++qd) {
+              const float4 bq = sb[qd];
+              r[4 * qd] = __float_as_uint(__uint_as_float(r[4 * qd]) + bq.x);
+              r[4 * qd + 1] = __float_as_uint(__uint_as_float(r[4 * qd + 1]) + bq.y);
+              r[4 * qd + 2] = __float_as_uint(__uint_as_float(r[4 * qd + 2]) + bq.z);
+              r[4 * qd + 3] = __float_as_uint(__uint_as_float(r[4 * qd + 3]) + bq.w);
+            }
+          }
+          if (p.tma_out) {
+            float v[CW];
+            if (valid) epilogue_values<CW>(p, r, nullptr, cg, pix, b, h, wo, v, true);
+            else {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) v[j] = 0.f;
+            }
+            unsigned char* tile = otile + (size_t)(it & 1) * SL::kOut;
+            mbar_wait(&out_empty[it & 1], (uint32_t)(((it >> 1) & 1) ^ 1));   // the store of two tiles ago has read this buffer
+            stage_tile_row<CO, CW>(tile, m, cg, v);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&out_full[it & 1]);
+          } else if (valid && cg < p.Cout) {
+            float v[CW];
+            epilogue_values<CW>(p, r, nullptr, cg, pix, b, h, wo, v, true);
+            store_direct<CW>(p, v, cg, pix, b, h, wo);
+          }
+          ++it;
+        }
+        alive_cur = cur.next();
+      }
+      swap_chains();
+      { const int tn = nd_cur; nd_cur = nd_oth; nd_oth = tn; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host: tensor maps
 bool make_w_map(CUtensorMap* m, const void* ptr, int rows, int K, int BK, int BN) {
   auto fn = encode_fn();
@@ -869,12 +1225,12 @@ int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, C
   return after_launch("conv3x3_tc_kernel");
 }
 
-bool make_row_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int BK) {
+bool make_row_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int BK, int rows = kHaloRows) {
   auto fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)kHaloCols, (cuuint32_t)kHaloRows, 1};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)kHaloCols, (cuuint32_t)rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -919,6 +1275,41 @@ int launch_row(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& 
   return after_launch("conv3x3_row_kernel");
 }
 
+template <int BK, int CO>
+int launch_col(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const CUtensorMap& ym, ConvParams p,
+               cudaStream_t st) {
+  using SL = ColSmem<BK, CO>;
+  auto kern = conv3x3_col_kernel<BK, CO>;
+  const int kb = p.kblocks1 + p.kblocks2;
+  // two CTAs per SM when the 6 * CO accumulator columns leave room (CO = 32) and two copies of the weights + rings fit
+  int per_sm = 6 * CO <= 256 ? 2 : 1;
+  int budget = (228 * 1024) / per_sm - 1024;
+  int stages = (budget - SL::total(kb, 0)) / SL::kRow;
+  if (per_sm == 2 && stages < 3) {
+    per_sm = 1;
+    budget = 227 * 1024;
+    stages = (budget - SL::total(kb, 0)) / SL::kRow;
+  }
+  if (stages > 8) stages = 8;
+  if (stages < 2) return 1;                                     // does not fit: caller falls back to the row kernel
+  const int smem = SL::total(kb, stages);
+  static int attr = 0;
+  if (attr < smem) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = smem;
+  }
+  p.tiles_w = (p.W + kRowW - 1) / kRowW;
+  p.nblk = 1;
+  const long long total = (long long)p.tiles_w * p.H * p.B;
+  long long grid = (long long)sm_count() * per_sm;
+  if (grid > total / 12) grid = total / 12;                      // at least ~12 output rows per chain (restart overhead)
+  if (grid < 1) grid = 1;
+  if (getenv("FALN_DEBUG")) fprintf(stderr, "conv3x3_col_kernel<%d,%d>: smem %d, %d stages, %d CTAs/SM, grid %lld\n", BK, CO, smem, stages, per_sm, grid);
+  launch_pdl(kern, dim3((unsigned)grid), dim3(352), (size_t)smem, st, a1, a2, w, ym, p, stages);
+  const int rc = after_launch("conv3x3_col_kernel");
+  return rc == 0 ? 0 : rc;
+}
+
 // Stride-1 layers with one N block (Cout_pad <= 64) on wide maps whose nine-tap weights fit in shared memory beside two
 // halo stages.  Returns 1 if the layer was launched here, 0 if the caller should use the tile kernel, < 0 on error.
 int try_row_kernel(const void* x, const void* x2, const void* wptr, int wrows, ConvParams& p, int BK, int C2, cudaStream_t st) {
@@ -944,6 +1335,21 @@ int try_row_kernel(const void* x, const void* x2, const void* wptr, int wrows, C
   if (!no_tma_out && !p.planar && !p.disp_out && p.Cout == wrows && p.out_c % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && make_out_map(&ym, p.out, (long long)p.B * p.H, p.W, p.out_c, wrows))
     p.tma_out = 1;
+  // column-walk kernel (vertical taps as N columns, each input row fetched once): opt-in with FALN_CONV_COL=1 -- parity-green
+  // but, as measured, still slower than the row kernel (see the kernel's header)
+  static const int use_col = getenv("FALN_CONV_COL") ? atoi(getenv("FALN_CONV_COL")) : 0;
+  if (use_col && !p.disp_out && p.H >= 8) {
+    CUtensorMap c1, c2;
+    if (!make_row_map(&c1, x, p.B, p.H, p.W, p.C1, BK, 1) || (x2 && !make_row_map(&c2, x2, p.B, p.H, p.W, C2, BK, 1))) {
+      set_error("conv3x3 column-walk kernel: cuTensorMapEncodeTiled failed");
+      return FALN_ERR_LAUNCH;
+    }
+    if (!x2) c2 = c1;
+    int rc;
+    if (BK == 64) rc = wrows == 64 ? launch_col<64, 64>(c1, c2, wm, ym, p, st) : launch_col<64, 32>(c1, c2, wm, ym, p, st);
+    else rc = wrows == 64 ? launch_col<32, 64>(c1, c2, wm, ym, p, st) : launch_col<32, 32>(c1, c2, wm, ym, p, st);
+    if (rc <= 0) return rc == 0 ? 1 : rc;                       // rc == 1: does not fit, fall through to the row kernel
+  }
   int rc;
   if (BK == 64) rc = wrows == 64 ? launch_row<64, 64, 2>(a1, a2, wm, ym, p, st) : launch_row<64, 32, 2>(a1, a2, wm, ym, p, st);
   else rc = wrows == 64 ? launch_row<32, 64, 3>(a1, a2, wm, ym, p, st) : launch_row<32, 32, 2>(a1, a2, wm, ym, p, st);

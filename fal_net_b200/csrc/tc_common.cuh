@@ -78,6 +78,37 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+
+// the same instruction with the descriptors' low words (start address >> 4 | LBO field) and a common high word: the issuing
+// thread adds 32-bit offsets only.  Always accumulates.
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+      : "memory");
+}
+// zero 32 lanes x CW (32 or 16) TMEM columns starting at taddr (this warp's lane quadrant is encoded in taddr)
+template <int CW>
+__device__ __forceinline__ void tmem_zero(uint32_t taddr) {
+  if (CW == 32) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        ::"r"(taddr), "r"(0u)
+        : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        ::"r"(taddr), "r"(0u)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------ host: tensor maps
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;

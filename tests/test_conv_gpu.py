@@ -44,6 +44,13 @@ def _ref(x, w, b, stride, act, res):
     (8, 6, 20, 256, 256, 256, 1, 1, True, False),    # iconv6: two sources
     (3, 1, 5, 128, 0, 128, 1, 2, True, False),       # one-row map
     (8, 6, 20, 256, 0, 64, 1, 0, True, False),       # one N block of 64
+    # wide maps, >= 8 rows (row kernel; the opt-in column-walk kernel runs the same shapes in test_column_walk_kernel_opt_in)
+    (3, 40, 640, 32, 0, 32, 1, 1, True, True),       # BK = 32, CO = 32, residual
+    (2, 33, 700, 64, 32, 64, 1, 1, True, False),     # two sources, three 32-channel K blocks (iconv1), ragged strip
+    (2, 24, 320, 128, 0, 64, 1, 2, True, False),     # two 64-channel K blocks (iconv2)
+    (1, 192, 640, 64, 0, 64, 1, 1, True, False),     # full-height strips cut into many chains
+    (8, 16, 200, 64, 0, 64, 1, 0, False, False),     # chains that cross strips and images
+    (1, 8, 192, 64, 0, 32, 1, 1, True, False),       # minimum height, CO = 32 with BK = 64
 ])
 def test_conv3x3_bf16_nhwc(B, H, W, C1, C2, Cout, stride, act, bias, res):
     from fal_net_b200 import conv_native as CN
@@ -160,6 +167,11 @@ def _elu_grad_from_y(y):
     (5, 3, 10, 512, 512, 1, 1, False, False),
     (8, 11, 39, 256, 256, 2, 0, False, False),     # stride 2, odd sizes
     (8, 6, 20, 512, 256, 1, 0, False, False),      # concat split: two row ranges of the re-packed weights
+    # more wide-map shapes
+    (2, 40, 640, 32, 32, 1, 1, False, True),
+    (2, 33, 320, 64, 64, 1, 1, True, False),       # accumulate into an existing gradient
+    (1, 50, 300, 64, 49, 1, 0, False, False),      # logits conv: Cout 49 padded to 64 on K
+    (3, 17, 200, 32, 64, 1, 2, False, False),      # 64 -> 32 channels, ReLU'
 ])
 def test_conv3x3_dgrad(B, H, W, Cin, Cout, stride, dact, accum, res):
     from fal_net_b200 import conv_native as CN
@@ -355,3 +367,48 @@ def test_const_channel_weight_gradient_against_autograd(H, W, stride):
         CN.const_channel_wgrad_into(gy, val, (H, W), stride, Cout, dW, 32)
         assert rel_err(dW[:, 32], ref[:, 0]) < 1e-5
         assert float(dW[:, :32].abs().max()) == 0.0
+
+
+_COL_SCRIPT = r"""
+import torch, torch.nn.functional as F
+from fal_net_b200 import conv_native as CN
+from tests.helpers import rel_err
+dev = torch.device("cuda:0"); CL = torch.channels_last
+g = torch.Generator().manual_seed(5)
+for (B, H, W, C1, C2, Cout, act, res) in [(3, 40, 640, 32, 0, 32, 1, True), (2, 33, 700, 64, 32, 64, 1, False), (1, 192, 640, 64, 0, 64, 1, False),
+                                           (8, 16, 200, 64, 0, 64, 0, False), (1, 8, 192, 64, 0, 32, 1, False), (2, 9, 640, 64, 0, 64, 1, False)]:
+    x = torch.randn(B, C1, H, W, generator=g).bfloat16().to(dev).contiguous(memory_format=CL)
+    x2 = torch.randn(B, C2, H, W, generator=g).bfloat16().to(dev).contiguous(memory_format=CL) if C2 else None
+    Cin = C1 + C2
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5).bfloat16().to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    r = torch.randn(B, Cout, H, W, generator=g).bfloat16().to(dev).contiguous(memory_format=CL) if res else None
+    y = CN.conv3x3_fwd(x, CN.pack_weight(w), b, 1, act, r, x2)
+    xin = x if x2 is None else torch.cat((x, x2), 1)
+    ref = F.conv2d(xin.float(), w.float(), b, 1, 1)
+    if r is not None: ref = ref + r.float()
+    if act == 1: ref = F.elu(ref)
+    e = rel_err(y.float(), ref); assert e < 8e-3, ("fwd", B, H, W, e)
+    if C2 == 0:
+        gy = torch.randn(B, Cout, H, W, generator=g).bfloat16().to(dev).contiguous(memory_format=CL)
+        ys = torch.randn(B, Cin, H, W, generator=g).bfloat16().to(dev).contiguous(memory_format=CL)
+        got = CN.conv3x3_dgrad(gy, CN.pack_weight_dgrad(w), (H, W), 1, dact=1, ysave=ys)
+        gr = torch.nn.grad.conv2d_input((B, Cin, H, W), w.float(), gy.float(), 1, 1)
+        gr = gr * torch.where(ys.float() > 0, torch.ones_like(gr), ys.float() + 1)
+        e = rel_err(got.float(), gr); assert e < 8e-3, ("dgrad", B, H, W, e)
+torch.cuda.synchronize(); print("COL_OK")
+"""
+
+
+def test_column_walk_kernel_opt_in():
+    """The column-walk kernel (FALN_CONV_COL=1; off by default, csrc/conv_tc.cu) is read once per process, so its parity check runs
+    in a child process: six wide-map shapes forward (bias / ELU / residual / two sources) and data gradient (ELU') against fp32
+    torch on the same bf16 operands, and the debug log must show that the kernel was the one launched."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FALN_CONV_COL="1", FALN_DEBUG="1", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", _COL_SCRIPT], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "COL_OK" in r.stdout, r.stderr[-2000:]
+    assert "conv3x3_col_kernel" in r.stderr
