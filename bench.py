@@ -918,19 +918,29 @@ def run_gpu(a, wl, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAda
     out_host = torch.empty(1, pin_memory=True)
     if graphed is not None:
         graphed.prefetch(*host[0])                        # the input pipeline: batch i+1 is uploaded while step i runs
+    pending, loss_sum = None, 0.0
     for i in range(a.steps):
         l, r = host[i % nb]
         if graphed is not None:
-            loss = graphed.run()                          # consumes the staged batch (every H2D copy is inside the timed region)
+            # consumes the staged batch (every H2D copy is inside the timed region) and queues the D2H copy of this step's loss
+            ticket = graphed.run_async()
             if i + 1 < a.steps:
                 graphed.prefetch(*host[(i + 1) % nb])
+            if pending is not None:
+                loss_sum += graphed.loss_value(pending)    # the user reads EVERY step's loss, one step behind the device
+            pending = ticket
         else:
             ld = l.to(dev, non_blocking=True)
             rd = r.to(dev, non_blocking=True) if wl in ("stage1", "stage2") else None
             loss = run_step(ld, rd)
-        out_host.copy_(loss.detach().reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the user reads the loss every step
+            out_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # the user reads the result every step
+            loss_sum += float(out_host[0])
+    if pending is not None:
+        loss_sum += graphed.loss_value(pending)            # ... and the last one before the clock stops
     e1.record()
+    if not (loss_sum == loss_sum):
+        raise RuntimeError("e2e loop produced a NaN loss")
     sync_all()
     ms_e2e = e0.elapsed_time(e1) / a.steps
     t = torch.tensor([ms_e2e], device=dev)
@@ -944,7 +954,10 @@ def run_gpu(a, wl, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAda
         "dtype": "bf16 convolutions (fp32 accumulate) + fp32 MED/losses/Adam", "data": "synthetic",
         "config": cfg, "clocks": clk,
         "e2e": {"value": frames_per_step / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "readback": ("every step's loss is copied D2H behind the step and read by the host one step late "
+                             "(GraphedStep.run_async / loss_value); the last one before the clock stops") if graphed is not None
+                else "synchronous read of every step's result"},
         "gpu_launches": launches, "cuda_graph": graphed is not None,
         "library_conv_calls_in_timed_region": lib_convs,
         "roofline": roofline,

@@ -729,9 +729,9 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
       }
     }
   } else {
-    // ================================================================= epilogue (warps 2..9)
+    // ================================================================= epilogue (warps 2 .. EW + 1)
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;                           // column chunk 0 .. EW / 4 - 1 of the quadrant
     const int m = quad * 32 + lane;
     const bool issuer = warp == 2 && lane == 0;                 // issues the TMA stores of the staged output tiles
     // this thread's CW output channels never change: keep their bias in registers for the life of the CTA
@@ -893,8 +893,8 @@ struct ColSmem {
   static int total(int kb, int stages) { return kBars + 1024 + 9 * kb * kW + stages * kRow + 2 * kOut; }
 };
 
-template <int BK, int CO>
-__global__ void __launch_bounds__(352)
+template <int BK, int CO, int EW>
+__global__ void __launch_bounds__(96 + 32 * EW)
 conv3x3_col_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY, const ConvParams p,
                    const int nstages) {
@@ -902,14 +902,15 @@ conv3x3_col_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
   constexpr int kMaxStages = 12;
   constexpr uint32_t kTmemCols = 6 * CO <= 256 ? 256 : 512;
   constexpr int kBank = kTmemCols / 2;                          // TMEM columns between the two banks (3 * CO used)
-  constexpr int CW = CO / 2;
+  constexpr int CW = CO / (EW / 4);                             // columns per epilogue warp: EW / 4 warps share a lane quadrant
+  static_assert(CW == 32 || CW == 16, "epilogue chunk");
   extern __shared__ unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty = full + kMaxStages;
   uint64_t* acc_full = empty + kMaxStages;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* wfull = acc_empty + 2;
-  uint64_t* out_full = wfull + 1;                              // staged output tile complete (8 epilogue warps)
+  uint64_t* out_full = wfull + 1;                              // staged output tile complete (EW epilogue warps)
   uint64_t* out_empty = out_full + 2;                          // ... and read out by the TMA store (store warp)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(out_empty + 2);
   float* sbias = reinterpret_cast<float*>(smem_raw + 512);     // [CO] bias (zeros when the layer has none)
@@ -948,11 +949,11 @@ conv3x3_col_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 8);
+      mbar_init(&acc_empty[a], EW);
     }
     mbar_init(wfull, 1);
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&out_full[a], 8);
+      mbar_init(&out_full[a], EW);
       mbar_init(&out_empty[a], 1);
     }
     fence_barrier_init();
@@ -1071,7 +1072,7 @@ conv3x3_col_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
         { const int tn = nd_cur; nd_cur = nd_oth; nd_oth = tn; }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == 2 + EW) {
     // ================================================================= TMA store warp (staged bf16 NHWC output)
     if (lane == 0 && p.tma_out) {
       int it = 0;
@@ -1094,9 +1095,9 @@ conv3x3_col_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
       tma_store_wait_all();
     }
   } else {
-    // ================================================================= epilogue (warps 2..9)
+    // ================================================================= epilogue (warps 2 .. EW + 1)
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;                           // column chunk 0 .. EW / 4 - 1 of the quadrant
     const int m = quad * 32 + lane;
     // zero this warp's part (its 32 TMEM lanes x CW columns) of all six accumulator slots, then open both banks
     const uint32_t tpart = tmem_base + (uint32_t)(half * CW) + ((uint32_t)(quad * 32) << 16);
@@ -1275,11 +1276,11 @@ int launch_row(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& 
   return after_launch("conv3x3_row_kernel");
 }
 
-template <int BK, int CO>
+template <int BK, int CO, int EW>
 int launch_col(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const CUtensorMap& ym, ConvParams p,
                cudaStream_t st) {
   using SL = ColSmem<BK, CO>;
-  auto kern = conv3x3_col_kernel<BK, CO>;
+  auto kern = conv3x3_col_kernel<BK, CO, EW>;
   const int kb = p.kblocks1 + p.kblocks2;
   // two CTAs per SM when the 6 * CO accumulator columns leave room (CO = 32) and two copies of the weights + rings fit
   int per_sm = 6 * CO <= 256 ? 2 : 1;
@@ -1304,8 +1305,8 @@ int launch_col(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& 
   long long grid = (long long)sm_count() * per_sm;
   if (grid > total / 12) grid = total / 12;                      // at least ~12 output rows per chain (restart overhead)
   if (grid < 1) grid = 1;
-  if (getenv("FALN_DEBUG")) fprintf(stderr, "conv3x3_col_kernel<%d,%d>: smem %d, %d stages, %d CTAs/SM, grid %lld\n", BK, CO, smem, stages, per_sm, grid);
-  launch_pdl(kern, dim3((unsigned)grid), dim3(352), (size_t)smem, st, a1, a2, w, ym, p, stages);
+  if (getenv("FALN_DEBUG")) fprintf(stderr, "conv3x3_col_kernel<%d,%d,%d>: smem %d, %d stages, %d CTAs/SM, grid %lld\n", BK, CO, EW, smem, stages, per_sm, grid);
+  launch_pdl(kern, dim3((unsigned)grid), dim3(96 + 32 * EW), (size_t)smem, st, a1, a2, w, ym, p, stages);
   const int rc = after_launch("conv3x3_col_kernel");
   return rc == 0 ? 0 : rc;
 }
@@ -1346,8 +1347,14 @@ int try_row_kernel(const void* x, const void* x2, const void* wptr, int wrows, C
     }
     if (!x2) c2 = c1;
     int rc;
-    if (BK == 64) rc = wrows == 64 ? launch_col<64, 64>(c1, c2, wm, ym, p, st) : launch_col<64, 32>(c1, c2, wm, ym, p, st);
-    else rc = wrows == 64 ? launch_col<32, 64>(c1, c2, wm, ym, p, st) : launch_col<32, 32>(c1, c2, wm, ym, p, st);
+    // Sixteen epilogue warps (four per lane quadrant, 16 columns each; FALN_COL_EW=16) were measured for CO = 64, where one
+    // CTA per SM leaves the eight warps alone with the drain: SLOWER (64 -> 64 at 8x192x640 forward 92.7 vs 88.2 us, data
+    // gradient 89.0 vs 85.7 us; row kernel 80.4 / 79.6 us) -- the drain is not what holds this kernel back.  Eight is the default.
+    static const int ew64 = getenv("FALN_COL_EW") ? atoi(getenv("FALN_COL_EW")) : 8;
+    if (wrows == 64 && ew64 == 16)
+      rc = BK == 64 ? launch_col<64, 64, 16>(c1, c2, wm, ym, p, st) : launch_col<32, 64, 16>(c1, c2, wm, ym, p, st);
+    else if (BK == 64) rc = wrows == 64 ? launch_col<64, 64, 8>(c1, c2, wm, ym, p, st) : launch_col<64, 32, 8>(c1, c2, wm, ym, p, st);
+    else rc = wrows == 64 ? launch_col<32, 64, 8>(c1, c2, wm, ym, p, st) : launch_col<32, 32, 8>(c1, c2, wm, ym, p, st);
     if (rc <= 0) return rc == 0 ? 1 : rc;                       // rc == 1: does not fit, fall through to the row kernel
   }
   int rc;

@@ -343,6 +343,10 @@ class GraphedStep:
         self._staged = None                              # event: staged batch has landed on the device
         self._consumed = torch.cuda.Event()              # event: staged batch has been moved into the graph's inputs
         self._consumed.record()
+        # loss read-back ring (run_async / loss_value): every step's loss is copied to pinned host memory right behind the
+        # step; the host reads it one step late, so the device never waits for the host between two steps
+        self._loss_host = torch.empty(self.LOSS_RING, dtype=torch.float32).pin_memory()
+        self._loss_ev = [None] * self.LOSS_RING
 
     def _body(self):
         self.opt.zero_grad()
@@ -382,3 +386,26 @@ class GraphedStep:
         self.replays += 1
         self.opt.t += 1
         return self.loss
+
+    LOSS_RING = 4
+
+    def run_async(self, left=None, right=None) -> int:
+        """``run()`` plus an asynchronous device-to-host copy of this step's loss; returns a ticket for ``loss_value``.
+        The reference reads ``loss.item()`` right after every step (Train_Stage1_K.py:249,259), which drains the device
+        before the next step can be queued; here the host queues step i + 1 first and then reads the loss of step i."""
+        self.run(left, right)
+        k = self.replays % self.LOSS_RING
+        self._loss_host[k:k + 1].copy_(self.loss.reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._loss_ev[k] = (self.replays, ev)
+        return self.replays
+
+    def loss_value(self, ticket: int) -> float:
+        """Blocks until the loss of the step ``run_async`` returned ``ticket`` for is on the host, and returns it."""
+        k = ticket % self.LOSS_RING
+        ent = self._loss_ev[k]
+        if ent is None or ent[0] != ticket:
+            raise RuntimeError(f"loss of step {ticket} is no longer in the read-back ring (depth {self.LOSS_RING})")
+        ent[1].synchronize()
+        return float(self._loss_host[k])

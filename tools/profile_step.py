@@ -23,6 +23,8 @@ else:
     fix = None
     if wl == "stage2":
         torch.manual_seed(1); fix = models.FAL_netB(no_levels=49).to(dev).eval()
+        for p_ in fix.parameters():
+            p_.requires_grad_(False)      # frozen teacher (Train_Stage2_K.py): its weight packs are cached, not refreshed per step
     for _ in range(n):
         opt.zero_grad()
         if wl == "stage1":
