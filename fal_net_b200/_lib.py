@@ -41,6 +41,7 @@ _SIGNATURES = {
     "faln_occ_mask": [_p, _p, _p] + [_i] * 7 + [_p],
     "faln_adam": [_p] * 5 + [_ll] + [_f] * 5 + [_i, _f, _p],
     "faln_adam_dev": [_p] * 5 + [_ll, _p] + [_f] * 5 + [_p],
+    "faln_adam_dev_range": [_p] * 5 + [_ll, _p] + [_f] * 5 + [_i, _p],
     "faln_nchw_to_nhwc_bf16": [_p, _p] + [_i] * 6 + [_p],
     "faln_nhwc_bf16_to_planar": [_p, _p] + [_i] * 5 + [_ll, _p],
     "faln_planar_to_nhwc_bf16": [_p, _p] + [_i] * 5 + [_ll, _p],

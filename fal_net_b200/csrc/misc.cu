@@ -226,12 +226,14 @@ extern "C" int faln_adam(float* p, const float* g, float* m, float* v, void* w16
   return after_launch("adam_kernel");
 }
 
-extern "C" int faln_adam_dev(float* p, const float* g, float* m, float* v, void* w16, long long n, float* hp, float beta1,
-                             float beta2, float eps, float weight_decay, float grad_scale, faln_stream_t stream) {
+extern "C" int faln_adam_dev_range(float* p, const float* g, float* m, float* v, void* w16, long long n, float* hp,
+                                   float beta1, float beta2, float eps, float weight_decay, float grad_scale, int tick,
+                                   faln_stream_t stream) {
   FALN_REQUIRE(p && g && m && v && hp && n > 0 && (n & 3) == 0, "faln_adam_dev: n must be a positive multiple of 4");
   FALN_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                  reinterpret_cast<uintptr_t>(v)) & 15) == 0, "faln_adam_dev: arenas must be 16-byte aligned");
-  adam_tick_kernel<<<1, 32, 0, as_stream(stream)>>>(hp, beta1, beta2);
+  FALN_REQUIRE(w16 == nullptr || (reinterpret_cast<uintptr_t>(w16) & 7) == 0, "faln_adam_dev: w16 must be 8-byte aligned");
+  if (tick) adam_tick_kernel<<<1, 32, 0, as_stream(stream)>>>(hp, beta1, beta2);
   const long long n4 = n / 4;
   long long grid = (n4 + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
@@ -241,6 +243,11 @@ extern "C" int faln_adam_dev(float* p, const float* g, float* m, float* v, void*
       reinterpret_cast<float4*>(v), static_cast<__nv_bfloat162*>(w16), n4, 0.f, beta1, beta2, 0.f, eps, weight_decay,
       grad_scale, hp);
   return after_launch("adam_kernel");
+}
+
+extern "C" int faln_adam_dev(float* p, const float* g, float* m, float* v, void* w16, long long n, float* hp, float beta1,
+                             float beta2, float eps, float weight_decay, float grad_scale, faln_stream_t stream) {
+  return faln_adam_dev_range(p, g, m, v, w16, n, hp, beta1, beta2, eps, weight_decay, grad_scale, 1, stream);
 }
 
 extern "C" int faln_nchw_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, int W, int Cp, int flip_x,

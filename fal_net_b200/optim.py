@@ -25,3 +25,12 @@ def adam_step_dev_(p, g, m, v, hp, w16=None, *, beta1=0.5, beta2=0.999, eps=1e-8
                                   _lib.ptr(hp), float(beta1), float(beta2), float(eps), float(weight_decay),
                                   float(grad_scale), _lib.cur_stream())
     _lib.check(rc, "faln_adam_dev")
+
+
+def adam_range_dev_(p, g, m, v, hp, w16=None, *, tick, beta1=0.5, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    """``adam_step_dev_`` over one contiguous range of the arenas (all arguments are the range's slices); ``tick`` advances
+    the device-side step counter first -- the first range of a step ticks, the others do not."""
+    rc = _lib.lib().faln_adam_dev_range(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), _lib.ptr(w16), p.numel(),
+                                        _lib.ptr(hp), float(beta1), float(beta2), float(eps), float(weight_decay),
+                                        float(grad_scale), 1 if tick else 0, _lib.cur_stream())
+    _lib.check(rc, "faln_adam_dev_range")

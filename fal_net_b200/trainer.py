@@ -22,7 +22,8 @@ from . import optim
 
 class FlatAdamDDP:
     def __init__(self, model, lr, betas=(0.5, 0.999), eps=1e-8, weight_decay=0.0, bias_decay=0.0,
-                 bucket_mb: float = 16.0, process_group=None, overlap=True, _update=None):
+                 bucket_mb: float = 16.0, process_group=None, overlap=True, _update=None, tail_mb: float = 1.0,
+                 bucket_adam=None):
         named = model.used_parameters() if hasattr(model, "used_parameters") else list(model.named_parameters())
         named = [(n, p) for n, p in named if p.requires_grad]
         # arena order = reverse registration order ~ the order in which backward produces gradients
@@ -106,13 +107,44 @@ class FlatAdamDDP:
             if end - start >= cap or i == len(sizes) - 1:
                 self.buckets.append((start, end, members))
                 start, members = end, []
+        # The gradients that arrive LAST (the encoder's first layers) are the smallest tensors of the model: they get a
+        # bucket of their own (<= tail_mb), so that the only all-reduce nothing can hide is a latency-sized one, and the
+        # rest of the former last bucket (7 MB at 16 MB buckets) is reduced under the backward of those layers.
+        if os.environ.get("FALN_TAIL_MB", "") != "":
+            tail_mb = float(os.environ["FALN_TAIL_MB"])            # A/B switch (0 = no tail bucket)
+        if tail_mb and tail_mb > 0 and self.buckets:
+            s_, e_, mem = self.buckets[-1]
+            cap_t, tot, k = int(tail_mb * (1 << 20) / 4), 0, len(mem)
+            while k > 1 and tot + (sizes[mem[k - 1]] + 3) // 4 * 4 <= cap_t:
+                tot += (sizes[mem[k - 1]] + 3) // 4 * 4
+                k -= 1
+            if 0 < k < len(mem):
+                cut = offs[mem[k]]
+                self.buckets[-1] = (s_, cut, mem[:k])
+                self.buckets.append((cut, e_, mem[k:]))
+        # Adam bucket by bucket, right behind each bucket's all-reduce (or, on one GPU, as soon as the bucket's gradients
+        # are complete) on an optimiser stream beside the rest of backward; step() joins it and sweeps up what is left.
+        # Nothing in backward reads the fp32 / bf16 parameter arenas after a bucket's gradients exist (the data-gradient
+        # kernels read the separate [Cin,3,3,Cout] packs, refreshed after the join).  FALN_BUCKET_ADAM=0 switches it off.
+        # Measured on one B200 (100-step A/B/A/B): Stage-1 step 4.115 / 4.117 ms with the single Adam launch, 4.121 / 4.123 ms
+        # bucket by bucket -- on one GPU nothing waits, so the default there is the single launch; with an all-reduce in the
+        # step (world > 1) the bucket-wise update is the default.
+        if bucket_adam is None:
+            env = os.environ.get("FALN_BUCKET_ADAM", "")
+            bucket_adam = (self.world > 1) if env == "" else env != "0"
+        self.bucket_adam = bool(bucket_adam) and self.wdv is None
+        self.track = self.overlap or self.bucket_adam  # count gradient arrivals per bucket
+        self.comm_enabled = True                       # bench.py switches the all-reduce off to measure what it costs
+        self._opt_stream = None
+        self._adam_done = [False] * len(self.buckets)
+        self._ticked = False
         self._bucket_of = {}
         for b, (_, _, mem) in enumerate(self.buckets):
             for i in mem:
                 self._bucket_of[i] = b
         self._pending = [0] * len(self.buckets)
         self._works = []
-        if self.overlap:
+        if self.track:
             for i, p in enumerate(self.params):
                 p.register_post_accumulate_grad_hook(self._make_hook(i))
         self._reset_counts()
@@ -198,24 +230,63 @@ class FlatAdamDDP:
         return self._view(self.g, self._index[name])
 
     def mark_ready(self, name):
-        if self.overlap:
+        if self.track:
             self._hook(self._index[name])
 
     def completes_bucket(self, name):
-        """True if marking ``name`` ready will complete (and launch the all-reduce of) its bucket."""
-        return bool(self.overlap) and self._pending[self._bucket_of[self._index[name]]] == 1
+        """True if marking ``name`` ready will complete its bucket (launching its all-reduce and / or its Adam update)."""
+        return bool(self.track) and self._pending[self._bucket_of[self._index[name]]] == 1
 
     def _hook(self, i):
         b = self._bucket_of[i]
         self._pending[b] -= 1
         if self._pending[b] == 0:
             s, e, _ = self.buckets[b]
-            self._works.append(dist.all_reduce(self.g[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+            work = None
+            if self.overlap and self.comm_enabled:
+                work = dist.all_reduce(self.g[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+                self._works.append(work)
+            if self.bucket_adam:
+                self._adam_bucket(b, work)
+
+    def _adam_range(self, s, e, tick):
+        """Adam over arena elements [s, e): device-side hyper-parameters under a CUDA graph, host-side otherwise."""
+        w16 = self.w16[s:e] if self.w16 is not None else None
+        if self.device_hp:
+            optim.adam_range_dev_(self.p[s:e], self.g[s:e], self.m[s:e], self.v[s:e], self.hp, w16, tick=tick,
+                                  beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.wd,
+                                  grad_scale=1.0 / self.world)
+        else:
+            self._update(self.p[s:e], self.g[s:e], self.m[s:e], self.v[s:e], w16, lr=self.lr, beta1=self.betas[0],
+                         beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, step=self.t + 1,
+                         grad_scale=1.0 / self.world)
+
+    def _adam_bucket(self, b, work):
+        s, e, _ = self.buckets[b]
+        if self.p.is_cuda:
+            if self._opt_stream is None:
+                self._opt_stream = torch.cuda.Stream()
+            cur = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(cur)                              # the caller has joined the streams that produced the bucket's gradients
+            self._opt_stream.wait_event(ev)
+            with torch.cuda.stream(self._opt_stream):
+                if work is not None:
+                    work.wait()                         # stream-ordered: the optimiser stream waits for the reduced bucket
+                self._adam_range(s, e, tick=not self._ticked)
+        else:
+            if work is not None:
+                work.wait()
+            self._adam_range(s, e, tick=not self._ticked)
+        self._ticked = True
+        self._adam_done[b] = True
 
     def _reset_counts(self):
         for b, (_, _, mem) in enumerate(self.buckets):
             self._pending[b] = len(mem)
         self._works = []
+        self._adam_done = [False] * len(self.buckets)
+        self._ticked = False
 
     def _make_hook(self, i):
         def hook(_p):
@@ -235,7 +306,7 @@ class FlatAdamDDP:
             self.sync_shadow()
 
     def step(self):
-        if self.world > 1:
+        if self.world > 1 and self.comm_enabled:
             if self.overlap:
                 for w in self._works:
                     w.wait()
@@ -245,6 +316,19 @@ class FlatAdamDDP:
                         dist.all_reduce(self.g[s:e], op=dist.ReduceOp.SUM, group=self.pg)
             else:
                 dist.all_reduce(self.g, op=dist.ReduceOp.SUM, group=self.pg)
+        if self.bucket_adam and any(self._adam_done):
+            # the buckets updated behind their all-reduce: join the optimiser stream, then sweep up what never completed
+            if self._opt_stream is not None:
+                torch.cuda.current_stream().wait_stream(self._opt_stream)
+            for b, (s, e, _) in enumerate(self.buckets):
+                if not self._adam_done[b]:
+                    self._adam_range(s, e, tick=not self._ticked)
+                    self._ticked = True
+            self.t += 1
+            self._adam_done = [False] * len(self.buckets)
+            self._ticked = False
+            self._finish_step()
+            return
         self.t += 1
         if self.wdv is not None:                       # distinct decays: the kernel scales g by 1/world afterwards
             self.g.addcmul_(self.wdv, self.p, value=float(self.world))
@@ -254,6 +338,9 @@ class FlatAdamDDP:
         else:
             self._update(self.p, self.g, self.m, self.v, self.w16, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
                          eps=self.eps, weight_decay=self.wd, step=self.t, grad_scale=1.0 / self.world)
+        self._finish_step()
+
+    def _finish_step(self):
         # The [Cin,3,3,Cout] data-gradient packs are only needed by the NEXT step's backward: instead of re-packing here, on
         # the critical path right after Adam (55 us per step), the re-pack is started on the side stream at the beginning of
         # the next forward (start_repack) and overlaps it; packed_dgrad() waits for it / falls back to a synchronous re-pack.

@@ -157,6 +157,11 @@ int faln_adam(float* p, const float* g, float* m, float* v, void* w16, long long
  * {lr, step, (derived) lr/(1-beta1^step), (derived) 1/sqrt(1-beta2^step)}; each call advances hp[1] by one. */
 int faln_adam_dev(float* p, const float* g, float* m, float* v, void* w16, long long n, float* hp, float beta1,
                   float beta2, float eps, float weight_decay, float grad_scale, faln_stream_t stream);
+/* The same update over a RANGE of the arenas (p, g, m, v, w16 point at the range's first element, n % 4 == 0): lets the
+ * optimiser run bucket by bucket, right behind each bucket's gradient all-reduce, while the rest of backward is still
+ * executing.  tick != 0 advances the step counter hp[1] first (exactly one call per step must tick: the first one). */
+int faln_adam_dev_range(float* p, const float* g, float* m, float* v, void* w16, long long n, float* hp, float beta1,
+                        float beta2, float eps, float weight_decay, float grad_scale, int tick, faln_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Layout / elementwise helpers of the conv pipeline (bf16 NHWC activations).

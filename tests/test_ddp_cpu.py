@@ -40,15 +40,16 @@ def _cpu_update(p, g, m, v, w16, *, lr, beta1, beta2, eps, weight_decay, step, g
     O.adam_step({"p": p}, {"p": g * grad_scale}, {"p": m}, {"p": v}, step, lr, beta1, beta2, eps)
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, bucket_adam=True):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from fal_net_b200.trainer import FlatAdamDDP
     torch.manual_seed(0)
     model = _Tiny()
-    opt = FlatAdamDDP(model, lr=1e-2, bucket_mb=1e-4, _update=_cpu_update)     # tiny buckets -> several all-reduces
-    assert len(opt.buckets) >= 2
+    opt = FlatAdamDDP(model, lr=1e-2, bucket_mb=1e-4, _update=_cpu_update,      # tiny buckets -> several all-reduces
+                      bucket_adam=bucket_adam)
+    assert len(opt.buckets) >= 2 and opt.bucket_adam == bucket_adam
     opt.broadcast_parameters()
     # gradient-sink protocol of the hand-scheduled backward: marking the last member of a bucket launches its all-reduce
     # (the backward then makes its side stream wait for the sibling streams first, backbone.backward.ready)
@@ -63,20 +64,28 @@ def _worker(rank, world, port, out):
     assert len(opt._works) == 1
     for w in opt._works:
         w.wait()
+    assert opt._adam_done[b0] == bucket_adam                                    # ... and, bucket by bucket, its Adam update
     g = torch.Generator().manual_seed(100 + rank)                               # rank-offset data
     for _ in range(3):
         x = torch.randn(4, 7, generator=g)
         opt.zero_grad()
         model(x).pow(2).mean().backward()
+        if bucket_adam:
+            assert all(opt._adam_done)                                          # every bucket was updated behind its all-reduce
         opt.step()
+        assert opt.t == _ + 1 and not any(opt._adam_done)
     torch.save({k: v.detach().clone() for k, v in model.state_dict().items()}, os.path.join(out, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_bucketed_allreduce_matches_single_process(tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("bucket_adam", [True, False])
+def test_bucketed_allreduce_matches_single_process(tmp_path, bucket_adam):
     world, port = 2, _free_port()
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), bucket_adam), nprocs=world, join=True)
     sd = [torch.load(os.path.join(tmp_path, f"r{r}.pt")) for r in range(world)]
     for k in sd[0]:
         assert torch.equal(sd[0][k], sd[1][k]), k                               # replicas stay in lock-step
@@ -93,3 +102,24 @@ def test_bucketed_allreduce_matches_single_process(tmp_path):
     for k, v in ref.state_dict().items():
         assert torch.allclose(v, sd[0][k], rtol=1e-5, atol=1e-6), k
     assert torch.equal(ref.unused.weight, sd[0]["unused.weight"])               # never touched
+
+
+def test_gradient_buckets_of_the_real_model_end_in_a_small_tail():
+    """FAL_netB's gradient arena at the default 16 MB buckets: contiguous, complete, in gradient-ready order, and the bucket
+    that completes last (the encoder's first layers) is a latency-sized one (<= 1 MB) -- the only all-reduce that cannot
+    hide behind backward."""
+    sys.path.insert(0, ROOT)
+    from fal_net_b200 import models
+    from fal_net_b200.trainer import FlatAdamDDP
+    torch.manual_seed(0)
+    m = models.__dict__["FAL_netB"](None, no_levels=49)
+    opt = FlatAdamDDP(m, lr=1e-4, _update=_cpu_update)
+    assert opt.buckets[0][0] == 0 and opt.buckets[-1][1] == opt.n
+    for (s0, e0, _), (s1, _, _) in zip(opt.buckets, opt.buckets[1:]):
+        assert e0 == s1 and e0 > s0
+    assert sorted(i for _, _, mem in opt.buckets for i in mem) == list(range(len(opt.params)))
+    tail = opt.buckets[-1]
+    assert (tail[1] - tail[0]) * 4 <= (1 << 20) and len(opt.buckets) >= 4
+    assert "conv0.0.weight" in opt.names[tail[2][-1]]                          # the stem's weight gradient arrives last
+    one = FlatAdamDDP(models.__dict__["FAL_netB"](None, no_levels=49), lr=1e-4, _update=_cpu_update, tail_mb=0)
+    assert len(one.buckets) == len(opt.buckets) - 1

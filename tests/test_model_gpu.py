@@ -197,6 +197,49 @@ def test_graphed_step_matches_eager():
     assert rel_l2(pg, pe) < 1e-3
 
 
+def test_graphed_step_lagged_loss_readback():
+    """GraphedStep.run_async / loss_value (the end-to-end loop of bench.py): the host queues step i + 1 before it reads the
+    loss of step i; every ticket must return exactly what a synchronous ``run()`` of the same trajectory returns, with the
+    prefetch staging in between, and a ticket that has left the ring must be refused."""
+    from fal_net_b200 import steps
+    from fal_net_b200.trainer import FlatAdamDDP, GraphedStep
+    dev = _dev()
+    B, H, W = 2, 48, 160
+    host = [(images(B, H, W, 30 + i).pin_memory(), images(B, H, W, 40 + i).pin_memory()) for i in range(6)]
+    mn, mx = (t.to(dev) for t in disp_range(B))
+
+    def run(lagged):
+        m, _ = _model()
+        opt = FlatAdamDDP(m, lr=2e-4)
+        fn = lambda l, r: steps.stage1_loss(m, l, r, mn, mx, a_p=0.0)[0]
+        gs = GraphedStep(opt, fn, host[0][0].to(dev), host[0][1].to(dev), warmup=0)
+        out = []
+        if not lagged:
+            for l, r in host:
+                out.append(float(gs.run(l.to(dev), r.to(dev))))
+            return out, gs
+        gs.prefetch(*host[0])
+        pending = None
+        for i in range(len(host)):
+            t = gs.run_async()
+            if i + 1 < len(host):
+                gs.prefetch(*host[i + 1])
+            if pending is not None:
+                out.append(gs.loss_value(pending))
+            pending = t
+        out.append(gs.loss_value(pending))
+        return out, gs
+
+    sync, _ = run(False)
+    lag, gs = run(True)
+    assert len(lag) == len(sync) == len(host)
+    for a, b in zip(sync, lag):
+        assert abs(a - b) <= 5e-3 * abs(a), (sync, lag)      # same tolerance as graph vs eager (fp32 red.add order)
+    assert sync[0] != sync[-1]
+    with pytest.raises(RuntimeError):
+        gs.loss_value(1)                                     # six steps later the ring (depth 4) has re-used that slot
+
+
 def test_fused_disparity_epilogue_matches_unfused():
     """Inference: the logits layer with the softmax-expectation fused into its epilogue (the N planes never reach HBM)
     against the same layer writing fp32 logits followed by the disparity kernel (reference :215-229)."""
