@@ -71,6 +71,9 @@ def _embed3(w):
 # instead of nine, no up-sampled tensor).  Exact-2x levels only (every level of the 192x640 training crops); other sizes --
 # KITTI full resolution has odd levels -- keep the explicit up-sample.  FALN_NO_UP2=1 switches it off (A/B measurements).
 USE_UP2 = os.environ.get("FALN_NO_UP2", "0") in ("", "0")
+# ... and its weight gradient from the low-resolution input (FALN_NO_UP2_WGRAD=1: rebuild the up-sampled map on the side stream
+# and run the plain 3x3 weight-gradient kernel on it, the round-2 path before this kernel existed)
+USE_UP2_WGRAD = os.environ.get("FALN_NO_UP2_WGRAD", "0") in ("", "0")
 
 
 def _up2_packs(weight):
@@ -358,8 +361,16 @@ def backward(model, tape, g_logits, sink=None):
             # 3x3 data gradient and ELU' of the producer in one kernel)
             hw_up = (u.shape[2], u.shape[3])
             keep.append(h_in)
-            wgrad(pfx + f"deconv{lvl}.conv1.weight", g_u, (lambda h_=h_in, hw_=hw_up: CN.upsample_nearest(h_, hw_),),
-                  up.conv1.weight.shape[0])
+            if USE_UP2_WGRAD and h_in.shape[1] % 64 == 0 and g_u.shape[1] % 64 == 0 and up.conv1.weight.shape[2:] == (3, 3):
+                # ... and so does the weight gradient: sixteen quarter-resolution correlations of (h, g) folded into the nine
+                # taps (csrc/conv_wgrad.cu, conv3x3_wgrad_up2_kernel) -- no up-sampled tensor on either stream
+                def run(name=pfx + f"deconv{lvl}.conv1.weight", g_=g_u, h_=h_in, co=up.conv1.weight.shape[0]):
+                    CN.conv3x3_wgrad_up2(g_, h_, sink.grad_view(name), cout=co)
+                    ready(name)
+                on_side(run, g_u, h_in)
+            else:
+                wgrad(pfx + f"deconv{lvl}.conv1.weight", g_u, (lambda h_=h_in, hw_=hw_up: CN.upsample_nearest(h_, hw_),),
+                      up.conv1.weight.shape[0])
             g_h = CN.conv3x3_up2_dgrad(g_u, _up2_packs(up.conv1.weight)[1], dact=1, ysave=h_in)
             del g_u
         else:

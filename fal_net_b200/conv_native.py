@@ -406,6 +406,31 @@ def conv3x3_wgrad(g, x, dW, cout=None, cx=None, ci_off=0, stride=1, flags=0):
     return dW
 
 
+def conv3x3_wgrad_up2(g, x, dW, cout=None, cx=None, ci_off=0):
+    """dW[:cout, ci_off:ci_off+cx] += weight gradient of "nearest 2x up-sampling, then conv3x3" (the reference's deconv block,
+    /root/reference/models/FAL_netB.py:51-60) taken from the LOW-resolution input: g bf16 [B,Cg,2H,2W] channels_last
+    (pre-activation gradient on the up-sampled grid), x bf16 [B,Cxs,H,W] channels_last, dW as in ``conv3x3_wgrad``.
+    Cg and Cxs must be multiples of 64 (csrc/conv_wgrad.cu: conv3x3_wgrad_up2_kernel)."""
+    g, x = _nhwc(g), _nhwc(x)
+    B, Cg, Hg, Wg = g.shape
+    _, Cxs, H, W = x.shape
+    assert x.shape[0] == B and (Hg, Wg) == (2 * H, 2 * W), (g.shape, x.shape)
+    assert Cg % 64 == 0 and Cxs % 64 == 0, (Cg, Cxs)
+    assert dW.dtype == torch.float32 and dW.dim() == 4 and dW.shape[2:] == (3, 3)
+    assert dW.permute(0, 2, 3, 1).is_contiguous(), "dW must be channels_last (KRSC memory)"
+    cout = cout or dW.shape[0]
+    cx = cx or min(Cxs, dW.shape[1] - ci_off)
+    assert cout <= dW.shape[0] and ci_off + cx <= dW.shape[1]
+    # reference formulation of the work (nine taps on the up-sampled grid), like the folded forward / data gradient
+    ev = _timed("conv_wgrad", 2 * 9 * cx * cout * B * Hg * Wg, 2 * B * Hg * Wg * Cg + 2 * B * H * W * Cxs + 4 * 9 * cx * cout, 64)
+    rc = _lib.lib().faln_conv3x3_wgrad_up2(_lib.ptr(g), _lib.ptr(x), _lib.ptr(dW), B, H, W, Cg, Cxs, cout, cx, ci_off,
+                                           dW.shape[1], _lib.cur_stream())
+    _lib.check(rc, "faln_conv3x3_wgrad_up2")
+    if ev is not None:
+        ev.record()
+    return dW
+
+
 def border_sums(g, C=None):
     """[B,3,3,C] fp32 sums of the bf16 channels_last map g over the 3x3 border classes (first / interior / last row x col)."""
     g = _nhwc(g)

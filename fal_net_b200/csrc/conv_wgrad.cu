@@ -209,6 +209,167 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ folded deconv weight gradient
+// Weight gradient of "nearest 2x up-sampling, then conv3x3" (the reference's deconv block, models/FAL_netB.py:51-60) WITHOUT the
+// up-sampled tensor -- the counterpart of faln_conv3x3_up2_fwd / _dgrad (conv_tc.cu).  With up(h)[y, x] = h[y >> 1, x >> 1],
+// output pixel (2i + py, 2j + px) and tap (kh, kw) read h[i + a, j + b], a = floor((py + kh - 1) / 2), b likewise: per output
+// parity class only a 2 x 2 neighbourhood of SOURCE pixels is touched (a in {-1, 0} for py = 0, {0, 1} for py = 1), so
+//     dW[kh, kw] = sum over (py, px) of S[py, px][a(py, kh)][b(px, kw)],
+//     S[py, px][a][b][ci, co] = sum_{i, j} h[i + a, j + b, ci] * g[2i + py, 2j + px, co]
+// = sixteen quarter-resolution correlations instead of nine full-resolution ones (2.25 x fewer MMAs), and the low-resolution
+// map is read instead of a 4 x larger one that first had to be written.  Per 4 x 16 chunk of the LOW-resolution map the TMA unit
+// fetches the [64, 18, 6] halo box of h (the nine (a, b) windows are sub-rectangles of it, as in the stride-1 kernel above) and
+// FOUR parity-sub-sampled boxes of g (element strides 2, 2).  Instruction row ir of class (py, px) pairs the windows
+// (a_ir, b_lo), (a_ir, b_hi) -- 128 bytes apart in the halo tile -- into the M = 128 rows; 4 classes x 2 rows x 64 columns fill
+// the 512 TMEM columns.  The epilogue folds the classes that feed the same tap in registers (the (py, ir) pairs of a kh live in
+// different TMEM columns of the same lanes; the kw = 1 tap is fed by b_hi of px = 0 and b_lo of px = 1, i.e. by different lane
+// halves, and takes two reductions): 12 tap blocks of red.add per CTA against 9 for a plain 3 x 3 kernel.
+__global__ void __launch_bounds__(192)
+conv3x3_wgrad_up2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams p) {
+  constexpr int XROWB = 128, GROWB = 128, NB = 64, XC = 64;
+  constexpr int GBOX = kP * GROWB;
+  constexpr int kHaloBytes = kHaloW * kHaloH * XROWB;
+  extern __shared__ unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + 8;
+  uint64_t* acc_full = empty + 8;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  unsigned char* stages = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 256 + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = p.x_bytes + 4 * GBOX;
+  const int tx_bytes = kHaloBytes + 4 * GBOX;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cib = blockIdx.y % p.n_cib, cob = blockIdx.y / p.n_cib;
+  const int split = blockIdx.x, nsplit = gridDim.x;
+  const int my_chunks = (p.chunks - split + nsplit - 1) / nsplit;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmG);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ================================================================= TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_chunks; ++it) {
+        const int c = split + it * nsplit;
+        const int tw = c % p.tiles_w, th = (c / p.tiles_w) % p.tiles_h, b = c / (p.tiles_w * p.tiles_h);
+        const int i0 = th * kCR, j0 = tw * kTW;                  // low-resolution origin of the chunk
+        mbar_wait(&empty[s], ph ^ 1);
+        unsigned char* xs = stages + (size_t)s * stage_bytes;
+        unsigned char* gs = xs + p.x_bytes;
+        mbar_arrive_expect_tx(&full[s], tx_bytes);
+        tma_load_4d(xs, &tmX, cib * XC, j0 - 1, i0 - 1, b, &full[s]);
+#pragma unroll
+        for (int cl = 0; cl < 4; ++cl)                           // class (py, px) = (cl >> 1, cl & 1): g[2i + py, 2j + px]
+          tma_load_4d(gs + cl * GBOX, &tmG, cob * NB, 2 * j0 + (cl & 1), 2 * i0 + (cl >> 1), b, &full[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_mn(NB);
+      const uint64_t b_tmpl = make_desc_mn<GROWB>(0, GBOX);
+      const uint64_t a_tmpl = make_desc_mn<XROWB>(0, XROWB);     // LBO: the b_hi window starts one pixel (128 bytes) after b_lo
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_chunks; ++it) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t xs = smem_u32(stages + (size_t)s * stage_bytes);
+        const uint64_t xs16 = (uint64_t)(xs >> 4), gs16 = (uint64_t)((xs + p.x_bytes) >> 4);
+#pragma unroll
+        for (int k = 0; k < kP / 16; ++k) {
+#pragma unroll
+          for (int cl = 0; cl < 4; ++cl) {
+            const int py = cl >> 1, px = cl & 1;
+            const uint64_t bdesc = b_tmpl + gs16 + (uint64_t)((cl * GBOX + k * 16 * GROWB) >> 4);
+#pragma unroll
+            for (int ir = 0; ir < 2; ++ir) {
+              // halo row of chunk row k shifted by a = ir - 1 (py = 0) or ir (py = 1): k + a + 1; halo column of b_lo: px
+              const uint32_t o0 = (uint32_t)(((k + ir + py) * kHaloW + px) * XROWB);
+              umma_bf16(tmem_base + (uint32_t)((cl * 2 + ir) * NB), a_tmpl + xs16 + (uint64_t)(o0 >> 4), bdesc, idesc,
+                        (it | k) != 0);
+            }
+          }
+        }
+        umma_commit(&empty[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+  } else if (my_chunks > 0) {
+    // ================================================================= epilogue (warps 2..5): fold the classes, red.add into dW
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int half = m >> 6;                                     // 0: the b_lo windows, 1: the b_hi windows (warp-uniform)
+    const int ci = cib * XC + (m & 63);
+    const bool row_ok = ci < p.Cx;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    for (int q = 0; q < 6; ++q) {
+      const int step = (q + split) % 6;                          // CTAs of one channel block start at different places
+      const int kh = step >> 1, c0 = (step & 1) * 32;
+      // the (py, ir) accumulators of this kh: py = 0 uses a = -1 (ir 0) for kh = 0 and a = 0 (ir 1) otherwise; py = 1 uses
+      // a = 0 (ir 0) for kh = 0, 1 and a = 1 (ir 1) for kh = 2
+      const int ir0 = kh == 0 ? 0 : 1, ir1 = kh == 2 ? 1 : 0;
+      uint32_t r[32];
+      float s0[32], s1[32];                                      // sums over py of the px = 0 / px = 1 classes
+      tmem_ld32(tlane + (uint32_t)(((0 * 2 + 0) * 2 + ir0) * NB + c0), r);
+#pragma unroll
+      for (int n = 0; n < 32; ++n) s0[n] = __uint_as_float(r[n]);
+      tmem_ld32(tlane + (uint32_t)(((1 * 2 + 0) * 2 + ir1) * NB + c0), r);
+#pragma unroll
+      for (int n = 0; n < 32; ++n) s0[n] += __uint_as_float(r[n]);
+      tmem_ld32(tlane + (uint32_t)(((0 * 2 + 1) * 2 + ir0) * NB + c0), r);
+#pragma unroll
+      for (int n = 0; n < 32; ++n) s1[n] = __uint_as_float(r[n]);
+      tmem_ld32(tlane + (uint32_t)(((1 * 2 + 1) * 2 + ir1) * NB + c0), r);
+#pragma unroll
+      for (int n = 0; n < 32; ++n) s1[n] += __uint_as_float(r[n]);
+      if (!row_ok) continue;
+      // b_lo is b = -1 <-> kw = 0 for px = 0 and b = 0 <-> kw in {0, 1} for px = 1; b_hi is b = 0 <-> kw in {1, 2} for px = 0 and
+      // b = 1 <-> kw = 2 for px = 1
+      const int kw_both = half == 0 ? 0 : 2;                     // the tap both px classes feed from this lane half
+      const int co0 = cob * NB + c0;
+      float* dst = p.dW + ((size_t)co0 * 9 + kh * 3) * p.Cin_tot + p.ci_off + ci;
+#pragma unroll
+      for (int n = 0; n < 32; ++n) {
+        if (co0 + n < p.Cout) {
+          float* d = dst + (size_t)n * 9 * p.Cin_tot;
+          atomicAdd(d + (size_t)kw_both * p.Cin_tot, s0[n] + s1[n]);
+          atomicAdd(d + (size_t)p.Cin_tot, half == 0 ? s1[n] : s0[n]);        // kw = 1
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 template <int XROWB, int GROWB, bool HALO>
 int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mg, const WgradParams& p, int splits, int smem, cudaStream_t st) {
   auto kern = conv3x3_wgrad_kernel<XROWB, GROWB, HALO>;
@@ -312,7 +473,13 @@ extern "C" int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B
   // gpurun_out/s7_*) 300 % -> 5.33 ms, 200 % -> 5.07 ms, 100 % -> 4.75 ms.
   static const int fill_pct = getenv("FALN_WGRAD_FILL_PCT") ? atoi(getenv("FALN_WGRAD_FILL_PCT")) : 100;
   int splits = ((fill_pct > 0 ? fill_pct : 100) * sm_count() / 100) / nblk;
-  if (splits > p.chunks / 4) splits = p.chunks / 4;
+  // FALN_WGRAD_MIN_CHUNKS: least number of 64-pixel chunks per CTA.  Every split adds a full set of red.add's for the
+  // channel block (9 x XC x NB floats) and one more CTA beside the data-gradient chain.  Measured on B200 (100-step runs,
+  // twice each): Stage-1 step 4.125 ms at 4, 4.105 at 12, 4.087 at 16, 4.133 at 24, 4.190 at 32, 4.645 at 64 (each small-map
+  // kernel alone is FASTER with more, smaller CTAs: 15.4 us at 4 vs 17.8 at 8 vs 22.7 at 16 -- it is the footprint beside the
+  // critical chain that counts); Stage-2 13.46 / 13.48 / 13.46 ms at 4 / 16 / 32.
+  static const int min_chunks = getenv("FALN_WGRAD_MIN_CHUNKS") ? atoi(getenv("FALN_WGRAD_MIN_CHUNKS")) : 16;
+  if (splits > p.chunks / (min_chunks > 0 ? min_chunks : 16)) splits = p.chunks / (min_chunks > 0 ? min_chunks : 16);
   if (splits < 1) splits = 1;
   CUtensorMap mx, mg;
   const bool ok_x = p.halo ? make_halo_map(&mx, x, B, H, W, Cxs) : make_act_map(&mx, x, B, H, W, Cxs, XC, stride, kCR);
@@ -327,6 +494,56 @@ extern "C" int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B
     return p.halo ? launch_wgrad<128, 64, true>(mx, mg, p, splits, smem, st) : launch_wgrad<128, 64, false>(mx, mg, p, splits, smem, st);
   if (XC == 32 && GC == 64) return launch_wgrad<64, 128, false>(mx, mg, p, splits, smem, st);
   return launch_wgrad<64, 64, false>(mx, mg, p, splits, smem, st);
+}
+
+// Weight gradient of the folded deconv block (nearest 2x up-sampling + conv3x3, see conv3x3_wgrad_up2_kernel):
+// g  [B,2H,2W,Cg] bf16 NHWC: gradient w.r.t. the conv's pre-activation output (on the UP-SAMPLED grid)
+// x  [B,H,W,Cxs]  bf16 NHWC: the block's LOW-resolution input; Cg, Cxs multiples of 64
+// dW [Cout,3,3,Cin_tot] fp32 (KRSC): columns [ci_off, ci_off + Cx) are accumulated into
+extern "C" int faln_conv3x3_wgrad_up2(const void* g, const void* x, float* dW, int B, int H, int W, int Cg, int Cxs, int Cout,
+                                      int Cx, int ci_off, int Cin_tot, faln_stream_t stream) {
+  FALN_REQUIRE(g && x && dW && B > 0 && H > 0 && W > 0, "faln_conv3x3_wgrad_up2: null pointer / bad shape");
+  FALN_REQUIRE(Cg % 64 == 0 && Cxs % 64 == 0 && Cg > 0 && Cxs > 0, "faln_conv3x3_wgrad_up2: channel strides must be multiples of 64");
+  FALN_REQUIRE(Cout > 0 && Cout <= Cg && Cx > 0 && Cx <= Cxs && ci_off >= 0 && ci_off + Cx <= Cin_tot,
+               "faln_conv3x3_wgrad_up2: channel ranges out of bounds");
+  WgradParams p{};
+  p.B = B; p.Hg = H; p.Wg = W; p.stride = 1;
+  p.tiles_w = (W + kTW - 1) / kTW; p.tiles_h = (H + kCR - 1) / kCR;
+  p.chunks = B * p.tiles_w * p.tiles_h;
+  p.NB = 64;
+  p.n_cib = (Cx + 63) / 64;
+  p.n_cob = (Cout + 63) / 64;
+  p.irows = 8; p.halo = 1;
+  p.tx_x = kHaloW * kHaloH * 128;
+  p.x_bytes = (p.tx_x + 1023) / 1024 * 1024;
+  p.Cx = Cx; p.Cout = Cout; p.ci_off = ci_off; p.Cin_tot = Cin_tot; p.dW = dW;
+  const int stage_bytes = p.x_bytes + 4 * kP * 128;
+  static const int ring_kb = getenv("FALN_WGRAD_SMEM_KB") ? atoi(getenv("FALN_WGRAD_SMEM_KB")) : 200;
+  p.stages = ((ring_kb > 0 ? ring_kb : 200) * 1024) / stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages < 2) p.stages = 2;
+  const int smem = 256 + 1024 + p.stages * stage_bytes;
+  const int nblk = p.n_cib * p.n_cob;
+  static const int fill_pct = getenv("FALN_WGRAD_FILL_PCT") ? atoi(getenv("FALN_WGRAD_FILL_PCT")) : 100;
+  // a chunk is 4 x 16 low-resolution pixels = 256 output pixels (32 instructions): a quarter of the plain kernel's chunk floor
+  static const int min_chunks = getenv("FALN_WGRAD_UP2_MIN_CHUNKS") ? atoi(getenv("FALN_WGRAD_UP2_MIN_CHUNKS")) : 4;
+  int splits = ((fill_pct > 0 ? fill_pct : 100) * sm_count() / 100) / nblk;
+  if (splits > p.chunks / (min_chunks > 0 ? min_chunks : 4)) splits = p.chunks / (min_chunks > 0 ? min_chunks : 4);
+  if (splits < 1) splits = 1;
+  CUtensorMap mx, mg;
+  if (!make_halo_map(&mx, x, B, H, W, Cxs) || !make_act_map(&mg, g, B, 2 * H, 2 * W, Cg, 64, 2, kCR)) {
+    set_error("faln_conv3x3_wgrad_up2: cuTensorMapEncodeTiled failed (driver entry point missing or bad tensor geometry)");
+    return FALN_ERR_LAUNCH;
+  }
+  auto kern = conv3x3_wgrad_up2_kernel;
+  static int attr_set = 0;
+  if (attr_set < smem) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_set = smem;
+  }
+  dim3 grid(splits, nblk, 1);
+  launch_pdl(kern, grid, dim3(192), (size_t)smem, as_stream(stream), mx, mg, p);
+  return after_launch("conv3x3_wgrad_up2_kernel");
 }
 
 // out [B,3,3,C] fp32 += per-sample sums of g [B,H,W,Cs] (bf16 NHWC, channels [0,C)) over the nine border classes

@@ -228,6 +228,13 @@ int faln_conv3x3_logits_disp(const void* x, const void* x2, const void* w, const
  * flags: 0 normally; bit 0 disables the halo-tile path (validation only). */
 int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B, int H, int W, int Cg, int Cxs, int Cout, int Cx,
                        int ci_off, int Cin_tot, int stride, unsigned flags, faln_stream_t stream);
+/* Weight gradient of the reference's deconv block -- F.interpolate(scale 2, nearest) then conv3x3
+ * (/root/reference/models/FAL_netB.py:51-60) -- taken straight from the LOW-resolution input, the counterpart of
+ * faln_conv3x3_up2_fwd / _dgrad: sixteen quarter-resolution correlations folded into the nine taps (2.25x fewer MMAs, no
+ * up-sampled tensor).  g [B,2H,2W,Cg] bf16 NHWC (pre-activation gradient on the up-sampled grid), x [B,H,W,Cxs] bf16 NHWC,
+ * dW [Cout,3,3,Cin_tot] fp32 KRSC accumulated in columns [ci_off, ci_off + Cx).  Cg, Cxs multiples of 64. */
+int faln_conv3x3_wgrad_up2(const void* g, const void* x, float* dW, int B, int H, int W, int Cg, int Cxs, int Cout, int Cx,
+                           int ci_off, int Cin_tot, faln_stream_t stream);
 /* out [B,3,3,C] fp32 += sums of g [B,H,W,Cs] (bf16 NHWC) per sample over the 3x3 border classes (first / interior / last
  * row x column): the weight gradient of a spatially constant input channel (reference :145,208-209) is a 9-term
  * combination of these.  H, W >= 2. */

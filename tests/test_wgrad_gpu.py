@@ -70,3 +70,40 @@ def test_const_channel_wgrad(stride, H, W):
     (ref,) = torch.autograd.grad(F.conv2d(plane, w, None, stride, 1), w, g16.float())
     got = CN.const_channel_wgrad(g16, val, (H, W), stride, C)
     assert float((got - ref[:, 0]).abs().max() / ref.abs().max()) < 1e-4
+
+
+UP2_CASES = [
+    # B, H, W (low resolution), Cin, Cout
+    (2, 6, 20, 64, 64),
+    (1, 5, 17, 128, 64),          # ragged chunks: 5 rows, 17 columns
+    (2, 3, 10, 512, 256),
+    (3, 12, 40, 256, 128),
+    (8, 48, 160, 128, 64),
+    (8, 96, 320, 64, 64),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", UP2_CASES)
+def test_folded_deconv_wgrad_matches_fp32(B, H, W, Cin, Cout):
+    """Weight gradient of F.interpolate(scale 2, nearest) + conv3x3 (reference models/FAL_netB.py:51-60) from the LOW-resolution
+    input (conv3x3_wgrad_up2_kernel: sixteen quarter-resolution correlations folded into nine taps) against fp32 autograd of
+    the reference formulation on the same bf16 operands, and against the plain kernel run on the up-sampled map."""
+    from fal_net_b200 import conv_native as CN
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(B * 100 + H + Cin)
+    h16 = torch.randn(B, Cin, H, W, device=dev, generator=gen).to(torch.bfloat16).contiguous(memory_format=CL)
+    g16 = torch.randn(B, Cout, 2 * H, 2 * W, device=dev, generator=gen).to(torch.bfloat16).contiguous(memory_format=CL)
+    w = torch.zeros(Cout, Cin, 3, 3, device=dev, dtype=torch.float32, requires_grad=True)
+    y = F.conv2d(F.interpolate(h16.float(), scale_factor=2, mode="nearest"), w, None, 1, 1)
+    (ref,) = torch.autograd.grad(y, w, g16.float())
+    dW = torch.full((Cout, Cin + 16, 3, 3), 0.25, device=dev).contiguous(memory_format=CL)
+    CN.conv3x3_wgrad_up2(g16, h16, dW, cout=Cout, cx=Cin, ci_off=8)
+    torch.cuda.synchronize()
+    got = dW[:, 8:8 + Cin] - 0.25
+    scale = ref.abs().max()
+    assert float((got - ref).abs().max() / scale) < 2e-3, float((got - ref).abs().max() / scale)
+    assert float((dW[:, :8] - 0.25).abs().max()) == 0 and float((dW[:, 8 + Cin:] - 0.25).abs().max()) == 0
+    plain = torch.zeros(Cout, Cin, 3, 3, device=dev).contiguous(memory_format=CL)
+    CN.conv3x3_wgrad(g16, CN.upsample_nearest(h16, (2 * H, 2 * W)), plain, cout=Cout, cx=Cin)
+    assert float((got - plain).abs().max() / scale) < 2e-3
