@@ -50,6 +50,7 @@ _SIGNATURES = {
     "faln_conv3x3_dgrad": [_p] * 5 + [_i] * 12 + [_p],
     "faln_conv3x3_wgrad": [_p] * 3 + [_i] * 10 + [_u, _p],
     "faln_conv3x3_wgrad_up2": [_p] * 3 + [_i] * 9 + [_p],
+    "faln_conv3x3_wgrad_bias": [_p] * 4 + [_i] * 10 + [_u, _p],
     "faln_f32_to_bf16": [_p, _p, _ll, _p],
     "faln_pack_dgrad_batched": [_p, _p, _p, _i, _i, _p],
     "faln_border_sum_nhwc": [_p, _p] + [_i] * 5 + [_p],

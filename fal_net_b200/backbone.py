@@ -73,6 +73,12 @@ def _embed3(w):
 USE_UP2 = os.environ.get("FALN_NO_UP2", "0") in ("", "0")
 # ... and its weight gradient from the low-resolution input (FALN_NO_UP2_WGRAD=1: rebuild the up-sampled map on the side stream
 # and run the plain 3x3 weight-gradient kernel on it, the round-2 path before this kernel existed)
+# measurement aid only (wrong gradients!): leave the bias-gradient sums out, to see what they cost inside the overlapped step
+_SKIP_BIAS_SUMS = os.environ.get("FALN_DEBUG_SKIP_BIAS_SUMS", "0") not in ("", "0")
+# Bias gradients from the spare operand slot of the layer's weight-gradient launch (FALN_NO_FUSED_BIAS_GRAD=1: one channel-sum
+# launch per biased layer on the bias stream instead -- 13 launches that re-read every gradient map; measured as 2.7 % of the
+# Stage-1 step by leaving them out, FALN_DEBUG_SKIP_BIAS_SUMS).
+FUSE_BIAS_GRAD = os.environ.get("FALN_NO_FUSED_BIAS_GRAD", "0") in ("", "0")
 USE_UP2_WGRAD = os.environ.get("FALN_NO_UP2_WGRAD", "0") in ("", "0")
 
 
@@ -261,6 +267,9 @@ def backward(model, tape, g_logits, sink=None):
     sides = _side_streams(dev)
     keep = []                                                  # tensors the side streams read stay alive until the join
     turn = [0]
+    used = []                                                  # side streams that received work in THIS backward: only those are
+    #                                                            joined (inside a graph capture a stream that never forked from the
+    #                                                            capturing stream must not be waited on)
 
     def on_side(fn, *tensors, bias=False):
         if not USE_SIDE_STREAM:
@@ -275,6 +284,8 @@ def backward(model, tape, g_logits, sink=None):
         ev = torch.cuda.Event()
         ev.record(main)
         side.wait_event(ev)
+        if side not in used:
+            used.append(side)
         with torch.cuda.stream(side):
             fn()
 
@@ -283,7 +294,7 @@ def backward(model, tape, g_logits, sink=None):
         the current side stream, so that stream first waits for the gradients its siblings are still producing."""
         if USE_SIDE_STREAM and len(sides) > 1 and getattr(sink, "completes_bucket", lambda n: False)(name):
             cur = torch.cuda.current_stream(dev)
-            for other in sides:
+            for other in used:
                 if other is not cur:
                     ev = torch.cuda.Event()
                     ev.record(other)
@@ -292,13 +303,19 @@ def backward(model, tape, g_logits, sink=None):
 
     def bias_grad(name, g, C):
         def run():
-            CN.channel_sum(g, sink.grad_view(name), C)
+            if not _SKIP_BIAS_SUMS:
+                CN.channel_sum(g, sink.grad_view(name), C)
             ready(name)
         on_side(run, g, bias=True)
 
-    def wgrad(name, g_pre, sources, cout, stride=1, const=None):
+    def wgrad(name, g_pre, sources, cout, stride=1, const=None, bias=None):
         """sources: the conv's (concatenated) inputs, in channel order; const = (value[B], in_hw) of a trailing constant
-        input plane."""
+        input plane; bias = name of the layer's bias: its gradient (sum of g_pre over pixels) is taken along by the first
+        source's launch (the kernel's spare operand slot reads ones, csrc/conv_wgrad.cu)."""
+        if bias is not None and not FUSE_BIAS_GRAD:
+            bias_grad(bias, g_pre, cout)
+            bias = None
+
         def run():
             dW = dst = sink.grad_view(name)
             if dW.shape[2:] != (3, 3):          # separable kernel: full 3x3 gradient into scratch, keep the taps that exist
@@ -307,12 +324,15 @@ def backward(model, tape, g_logits, sink=None):
             for x in sources:
                 x = x() if callable(x) else x                  # lazily built input (the up-sampled map of a folded deconv)
                 cx = min(x.shape[1], dW.shape[1] - off)
-                CN.conv3x3_wgrad(g_pre, x, dW, cout=cout, cx=cx, ci_off=off, stride=stride)
+                CN.conv3x3_wgrad(g_pre, x, dW, cout=cout, cx=cx, ci_off=off, stride=stride,
+                                 dbias=sink.grad_view(bias) if (bias is not None and off == 0) else None)
                 off += cx
             if dW is not dst:
                 dst.add_(dW[:, :, :, 1:2] if dst.shape[2:] == (3, 1) else dW[:, :, 1:2, :])
             if const is not None:
                 CN.const_channel_wgrad_into(g_pre, const[0], const[1], stride, cout, dW, off)
+            if bias is not None:
+                ready(bias)
             ready(name)
         on_side(run, g_pre, *[x for x in sources if not callable(x)])
 
@@ -321,11 +341,14 @@ def backward(model, tape, g_logits, sink=None):
     g = layout.planar_to_nhwc_bf16(g_logits, Np).permute(0, 3, 1, 2)            # bf16 [B,Np,H,W] channels_last view
     h2, xu, u, _ = tape["dec1"]
     s0 = tape["conv0"][2]
-    bias_grad("conv0.bias", g, N)
+    if not FUSE_BIAS_GRAD:
+        bias_grad("conv0.bias", g, N)
 
     def folded():
         gwf = torch.zeros(N, 3, 3, u.shape[1] + s0.shape[1], device=dev, dtype=torch.float32).permute(0, 3, 1, 2)
-        CN.conv3x3_wgrad(g, u, gwf, cout=N, ci_off=0)
+        CN.conv3x3_wgrad(g, u, gwf, cout=N, ci_off=0, dbias=sink.grad_view("conv0.bias") if FUSE_BIAS_GRAD else None)
+        if FUSE_BIAS_GRAD:
+            ready("conv0.bias")
         CN.conv3x3_wgrad(g, s0, gwf, cout=N, ci_off=u.shape[1])
         # adjoint of the fold, one launch: dW0 = <gW', W_iconv1>, dW_iconv1 = W0^T gW'
         CN.fold_logit_conv_bwd(gwf, bb.iconv1.weight, model.conv0.weight, sink.grad_view(pfx + "iconv1.weight"),
@@ -348,8 +371,7 @@ def backward(model, tape, g_logits, sink=None):
         if lvl > 1:
             ic = getattr(bb, f"iconv{lvl}")[0]
             cout = ic.weight.shape[0]
-            bias_grad(pfx + f"iconv{lvl}.0.bias", g_h, cout)
-            wgrad(pfx + f"iconv{lvl}.0.weight", g_h, (u, skip), cout)
+            wgrad(pfx + f"iconv{lvl}.0.weight", g_h, (u, skip), cout, bias=pfx + f"iconv{lvl}.0.bias")
             wd = _wd(ic.weight)
             C1 = u.shape[1]
             hw = (u.shape[2], u.shape[3])
@@ -392,23 +414,22 @@ def backward(model, tape, g_logits, sink=None):
         g_r = CN.conv3x3_dgrad(g_s, _wd(blk.conv2.weight), hw, dact=1, ysave=r)
         wgrad(pfx + f"{name}_1.conv1.weight", g_r, (a,), cout)
         g_a = CN.conv3x3_dgrad(g_r, _wd(blk.conv1.weight), hw, dact=1, ysave=a, residual=g_s)   # (dgrad + skip path) * ELU'
-        bias_grad(pfx + f"{name}.0.bias", g_a, cout)
-        wname = pfx + f"{name}.0.weight"
+        wname, bname = pfx + f"{name}.0.weight", pfx + f"{name}.0.bias"
         if i == 0:
             # the 3-channel image as a 32-channel (zero-padded) bf16 NHWC tensor: same tensor-core path, cx = 3
             img16 = layout.planar_to_nhwc_bf16(tape["image"].float().contiguous(), 32).permute(0, 3, 1, 2)
-            wgrad(wname, g_a, (img16,), cout)
+            wgrad(wname, g_a, (img16,), cout, bias=bname)
             break
         prev = tape[ENC[i - 1][0]][2]
         Cp = prev.shape[1]
         # conv1.0's 33rd input is the constant max_disp/100 plane
         wgrad(wname, g_a, (prev,), cout, stride,
-              const=(tape["flow_val"], (prev.shape[2], prev.shape[3])) if i == 1 else None)
+              const=(tape["flow_val"], (prev.shape[2], prev.shape[3])) if i == 1 else None, bias=bname)
         # stride-2 dgrad into the previous skip: add to what the decoder left there, then ELU'(s_{i-1})
         g_s = CN.conv3x3_dgrad(g_a, _wd(head.weight, Cp), (prev.shape[2], prev.shape[3]), stride=stride,
                                out=G_skip.pop(i - 1), accum=True, dact=1, ysave=prev)
         del g_r, g_a
-    for side in sides:                                                            # join: gradients complete, `keep` may go
+    for side in used:                                                             # join: gradients complete, `keep` may go
         main.wait_stream(side)
     del keep
     return sink

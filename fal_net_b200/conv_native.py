@@ -383,24 +383,27 @@ def channel_sum(g, out, C=None):
     return out
 
 
-def conv3x3_wgrad(g, x, dW, cout=None, cx=None, ci_off=0, stride=1, flags=0):
+def conv3x3_wgrad(g, x, dW, cout=None, cx=None, ci_off=0, stride=1, flags=0, dbias=None):
     """dW[:cout, ci_off:ci_off+cx] += weight gradient of a 3x3 conv (pad 1) on the tcgen05 kernel (csrc/conv_wgrad.cu).
     g: bf16 [B,Cg,Hg,Wg] channels_last (pre-activation gradient), x: bf16 [B,Cxs,H,W] channels_last (the conv's input, or
     one source of a concatenated input), dW: fp32 [Cout,Cin_tot,3,3] in ``torch.channels_last`` memory format (= KRSC in
-    memory; typically a view of the flat gradient arena), accumulated in place with split-K fp32 reductions."""
+    memory; typically a view of the flat gradient arena), accumulated in place with split-K fp32 reductions.
+    dbias: optional fp32 [>= cout], contiguous: += sum of g over (b, h, w), the layer's bias gradient, computed by the same
+    launch from the kernel's spare operand-window slot (no extra pass over g)."""
     g, x = _nhwc(g), _nhwc(x)
     B, Cg, Hg, Wg = g.shape
     _, Cxs, H, W = x.shape
     assert x.shape[0] == B and (Hg, Wg) == ((H - 1) // stride + 1, (W - 1) // stride + 1), (g.shape, x.shape, stride)
+    assert dbias is None or (dbias.dtype == torch.float32 and dbias.is_contiguous() and dbias.numel() >= (cout or dW.shape[0]))
     assert dW.dtype == torch.float32 and dW.dim() == 4 and dW.shape[2:] == (3, 3)
     assert dW.permute(0, 2, 3, 1).is_contiguous(), "dW must be channels_last (KRSC memory)"
     cout = cout or dW.shape[0]
     cx = cx or min(Cxs, dW.shape[1] - ci_off)
     assert cout <= dW.shape[0] and ci_off + cx <= dW.shape[1]
     ev = _timed("conv_wgrad", 2 * 9 * cx * cout * B * Hg * Wg, 2 * B * Hg * Wg * Cg + 2 * B * H * W * Cxs + 4 * 9 * cx * cout, 64)
-    rc = _lib.lib().faln_conv3x3_wgrad(_lib.ptr(g), _lib.ptr(x), _lib.ptr(dW), B, H, W, Cg, Cxs, cout, cx, ci_off,
-                                       dW.shape[1], stride, int(flags), _lib.cur_stream())
-    _lib.check(rc, "faln_conv3x3_wgrad")
+    rc = _lib.lib().faln_conv3x3_wgrad_bias(_lib.ptr(g), _lib.ptr(x), _lib.ptr(dW), _lib.ptr(dbias), B, H, W, Cg, Cxs, cout,
+                                            cx, ci_off, dW.shape[1], stride, int(flags), _lib.cur_stream())
+    _lib.check(rc, "faln_conv3x3_wgrad_bias")
     if ev is not None:
         ev.record()
     return dW

@@ -27,6 +27,11 @@
 //     [Cout, 3, 3, Cin_total] (KRSC, the layout of the flat gradient arena the fused Adam reads: lanes = consecutive ci,
 //     so every red.global.add.f32 is a coalesced 128-byte request); gradients of a concatenated input are two calls with
 //     different column offsets.  No workspace, no separate reduction kernel.
+//   * the bias gradient rides along: nine taps leave one window slot of the last instruction row unused (three for 32-channel
+//     blocks); that slot reads a block of bf16 ONES, so its accumulator rows are sum_pixels 1 * g[pixel, co] -- the bias
+//     gradient of the layer, from operands the kernel streams anyway.  The CTAs of input-channel block 0 add one row of it to
+//     dbias.  (Before: a separate channel-sum launch per biased layer re-read every gradient map, 13 launches = 2.7 % of the
+//     Stage-1 step even on its own stream.)
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -52,6 +57,8 @@ struct WgradParams {
   int ci_off, Cin_tot;      // column offset / row length of dW
   int stages;
   float* dW;
+  float* dbias;             // optional [Cout] fp32: += sum over pixels of g (the conv's bias gradient), from the spare tap slot
+  int ones_off;             // halo path: byte offset (from the 1024-aligned stage base) of the 2 KB block of bf16 ones
 };
 
 // MN-major swizzled shared-memory matrix descriptor: start >> 4, LBO >> 4 at [16,30) (distance between the 64- / 32-channel
@@ -105,6 +112,21 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     fence_proxy_async();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, alloc_cols);
+  if (p.dbias) {
+    // bf16 ones for the spare tap slot (generic-proxy stores, made visible to the tensor core's async proxy below):
+    // halo path: one 2 KB block (two 8-pixel atoms) behind the ring; box path: slot 9 of every stage, which no TMA load writes
+    constexpr uint32_t kOnes = 0x3F803F80u;
+    if (HALO) {
+      uint4* o = reinterpret_cast<uint4*>(stages + p.ones_off);
+      for (int i = threadIdx.x; i < 2048 / 16; i += 192) o[i] = make_uint4(kOnes, kOnes, kOnes, kOnes);
+    } else {
+      for (int s = 0; s < p.stages; ++s) {
+        uint4* o = reinterpret_cast<uint4*>(stages + (size_t)s * stage_bytes + 9 * XBOX);
+        for (int i = threadIdx.x; i < XBOX / 16; i += 192) o[i] = make_uint4(kOnes, kOnes, kOnes, kOnes);
+      }
+    }
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -143,6 +165,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       // everything but the stage base address is a compile-time constant: descriptors are (template + base >> 4)
       const uint64_t b_tmpl = make_desc_mn<GROWB>(0, GBOX);
       const uint64_t a_tmpl_box = make_desc_mn<XROWB>(0, XBOX);
+      const uint32_t ones_base = smem_u32(stages + p.ones_off);
       int s = 0;
       uint32_t ph = 0;
       for (int it = 0; it < my_chunks; ++it) {
@@ -161,7 +184,8 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
               // instruction row j = taps 2j, 2j+1: windows of the halo tile starting at halo row (k + kh) * 18 + kw
               const int t0 = 2 * j, t1 = 2 * j + 1;
               const uint32_t o0 = (uint32_t)(((k + t0 / 3) * kHaloW + t0 % 3) * XROWB);
-              const uint32_t o1 = (uint32_t)(((k + t1 / 3) * kHaloW + t1 % 3) * XROWB);
+              uint32_t o1 = (uint32_t)(((k + t1 / 3) * kHaloW + t1 % 3) * XROWB);
+              if (t1 == 9 && p.dbias) o1 = ones_base - xs;       // the spare slot: the block of ones (behind every stage)
               adesc = make_desc_mn<XROWB>(0, o1 - o0) + xs16 + (uint64_t)(o0 >> 4);
             } else {
               adesc = a_tmpl_box + xs16 + (uint64_t)((j * SPR * XBOX + k * 16 * XROWB) >> 4);
@@ -192,6 +216,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + j * NB + c0, r);
+        if (tap == 9 && (m % XC) == 0 && cib == 0 && p.dbias) {   // first row of the ones slot: sum over this CTA's pixels of g
+#pragma unroll
+          for (int n = 0; n < 32; ++n)
+            if (cob * NB + c0 + n < p.Cout) atomicAdd(p.dbias + cob * NB + c0 + n, __uint_as_float(r[n]));
+        }
         if (!row_ok) continue;
         const int co0 = cob * NB + c0;
         float* dst = p.dW + ((size_t)co0 * 9 + tap) * p.Cin_tot + p.ci_off + ci;
@@ -427,8 +456,10 @@ using namespace faln;
 // x  [B,H,W,Cxs]  bf16 NHWC: the conv's input (one source of a concatenated input per call; Cxs % 32 == 0)
 // dW [Cout, 3, 3, Cin_tot] fp32 (KRSC): columns [ci_off, ci_off + Cx) are ACCUMULATED into (caller zeroes them once per step)
 // flags: bit 0 = never use the halo path (validation: nine boxes per chunk instead)
-extern "C" int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B, int H, int W, int Cg, int Cxs, int Cout,
-                                  int Cx, int ci_off, int Cin_tot, int stride, unsigned flags, faln_stream_t stream) {
+// dbias [Cout] fp32 (may be NULL): += sum over (b, ho, wo) of g[b, ho, wo, co] -- the bias gradient, from the spare tap slot
+extern "C" int faln_conv3x3_wgrad_bias(const void* g, const void* x, float* dW, float* dbias, int B, int H, int W, int Cg,
+                                       int Cxs, int Cout, int Cx, int ci_off, int Cin_tot, int stride, unsigned flags,
+                                       faln_stream_t stream) {
   FALN_REQUIRE(g && x && dW && B > 0 && H > 0 && W > 0, "faln_conv3x3_wgrad: null pointer / bad shape");
   FALN_REQUIRE(stride == 1 || stride == 2, "faln_conv3x3_wgrad: stride must be 1 or 2");
   FALN_REQUIRE(Cg % 32 == 0 && Cxs % 32 == 0 && Cg > 0 && Cxs > 0, "faln_conv3x3_wgrad: channel strides must be multiples of 32");
@@ -458,6 +489,7 @@ extern "C" int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B
     p.x_bytes = p.irows * spr * xbox;
   }
   p.Cx = Cx; p.Cout = Cout; p.ci_off = ci_off; p.Cin_tot = Cin_tot; p.dW = dW;
+  p.dbias = dbias;
   const int stage_bytes = p.x_bytes + gbox;
   // FALN_WGRAD_SMEM_KB: shared memory the operand ring may take (tuning aid).  The kernel runs beside the data-gradient chain;
   // a CTA that fills the SM's shared memory keeps that chain's CTAs off the SM for as long as it runs.
@@ -465,7 +497,8 @@ extern "C" int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B
   p.stages = ((ring_kb > 0 ? ring_kb : 200) * 1024) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) p.stages = 2;
-  const int smem = 256 + 1024 + p.stages * stage_bytes;
+  p.ones_off = p.stages * stage_bytes;                       // halo path: 2 KB of bf16 ones behind the ring
+  const int smem = 256 + 1024 + p.stages * stage_bytes + (p.halo && dbias ? 2048 : 0);
   // split-K: about two CTAs per SM over the whole grid, at least ~4 chunks per CTA (prologue + epilogue amortisation)
   const int nblk = p.n_cib * p.n_cob;
   // FALN_WGRAD_FILL_PCT: CTAs the split-K aims for, in percent of the SM count.  The kernel runs on the gradient side
@@ -544,6 +577,11 @@ extern "C" int faln_conv3x3_wgrad_up2(const void* g, const void* x, float* dW, i
   dim3 grid(splits, nblk, 1);
   launch_pdl(kern, grid, dim3(192), (size_t)smem, as_stream(stream), mx, mg, p);
   return after_launch("conv3x3_wgrad_up2_kernel");
+}
+
+extern "C" int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B, int H, int W, int Cg, int Cxs, int Cout,
+                                  int Cx, int ci_off, int Cin_tot, int stride, unsigned flags, faln_stream_t stream) {
+  return faln_conv3x3_wgrad_bias(g, x, dW, nullptr, B, H, W, Cg, Cxs, Cout, Cx, ci_off, Cin_tot, stride, flags, stream);
 }
 
 // out [B,3,3,C] fp32 += per-sample sums of g [B,H,W,Cs] (bf16 NHWC, channels [0,C)) over the nine border classes

@@ -228,6 +228,12 @@ int faln_conv3x3_logits_disp(const void* x, const void* x2, const void* w, const
  * flags: 0 normally; bit 0 disables the halo-tile path (validation only). */
 int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B, int H, int W, int Cg, int Cxs, int Cout, int Cx,
                        int ci_off, int Cin_tot, int stride, unsigned flags, faln_stream_t stream);
+/* The same with the layer's BIAS gradient taken along: dbias [Cout] fp32 (NULL = none) += sum over (b, ho, wo) of
+ * g[b,ho,wo,co] -- replaces the sum autograd runs for nn.Conv2d(bias=True) (/root/reference/models/FAL_netB.py:35-48).  Nine
+ * taps leave one operand-window slot of the kernel's last MMA row unused; it reads ones, so the sum costs no extra pass over g.
+ * For a concatenated input pass dbias with ONE of the per-source calls only. */
+int faln_conv3x3_wgrad_bias(const void* g, const void* x, float* dW, float* dbias, int B, int H, int W, int Cg, int Cxs,
+                            int Cout, int Cx, int ci_off, int Cin_tot, int stride, unsigned flags, faln_stream_t stream);
 /* Weight gradient of the reference's deconv block -- F.interpolate(scale 2, nearest) then conv3x3
  * (/root/reference/models/FAL_netB.py:51-60) -- taken straight from the LOW-resolution input, the counterpart of
  * faln_conv3x3_up2_fwd / _dgrad: sixteen quarter-resolution correlations folded into the nine taps (2.25x fewer MMAs, no

@@ -48,8 +48,13 @@ def test_wgrad_matches_fp32(B, H, W, Cxs, Cg, cout, cx, stride, flags):
     ref = _ref_wgrad(x16, g16, cout, cx, stride)
     # write into columns [8, 8 + cx) of a wider gradient tensor that already holds something (accumulation semantics)
     dW = torch.full((cout, cx + 16, 3, 3), 0.5, device=dev).contiguous(memory_format=CL)
-    CN.conv3x3_wgrad(g16, x16, dW, cout=cout, cx=cx, ci_off=8, stride=stride, flags=flags)
+    # ... and take the bias gradient along (the kernel's spare operand slot reads ones): accumulated into dbias[:cout]
+    dbias = torch.full((cout + 3,), 2.0, device=dev)
+    CN.conv3x3_wgrad(g16, x16, dW, cout=cout, cx=cx, ci_off=8, stride=stride, flags=flags, dbias=dbias)
     torch.cuda.synchronize()
+    bref = g16.float()[:, :cout].sum(dim=(0, 2, 3))
+    assert float((dbias[:cout] - 2.0 - bref).abs().max() / bref.abs().max().clamp_min(1.0)) < 1e-3
+    assert float((dbias[cout:] - 2.0).abs().max()) == 0
     got = dW[:, 8:8 + cx] - 0.5
     scale = ref.abs().max()
     assert float((got - ref).abs().max() / scale) < 2e-3, float((got - ref).abs().max() / scale)
