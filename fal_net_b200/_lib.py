@@ -53,6 +53,7 @@ _SIGNATURES = {
     "faln_conv3x3_wgrad_bias": [_p] * 4 + [_i] * 10 + [_u, _p],
     "faln_f32_to_bf16": [_p, _p, _ll, _p],
     "faln_pack_dgrad_batched": [_p, _p, _p, _i, _i, _p],
+    "faln_pack_dgrad_flat": [_p] * 3 + [_i, _i, _p],
     "faln_border_sum_nhwc": [_p, _p] + [_i] * 5 + [_p],
     "faln_upsample_nearest_bwd_nhwc": [_p] * 3 + [_i] * 8 + [_p],
     "faln_maxpool2_bwd_nhwc": [_p] * 3 + [_i] * 5 + [_p],

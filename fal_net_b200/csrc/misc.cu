@@ -194,6 +194,59 @@ __global__ void __launch_bounds__(256) pack_dgrad_kernel(const __nv_bfloat16* __
   }
 }
 
+// The same re-pack over a FLAT tile list: jobs[j][5] holds the index of job j's first 32 x 32 tile in the concatenation of all
+// jobs' tiles, `total` their number.  A warp owns one tile per turn (no CTA barrier), moves bf16 PAIRS (4-byte accesses, 64-byte
+// row segments) and the grid holds exactly the work: the 2-D launch above starts max_tiles x njobs = 76 k blocks for 16.5 k tiles
+// of work (most blocks of the small layers exit at once) and took 55 us per step on the critical path right behind Adam.
+__global__ void __launch_bounds__(256) pack_dgrad_flat_kernel(const __nv_bfloat16* __restrict__ w16, __nv_bfloat16* __restrict__ wd16,
+                                                              const long long* __restrict__ jobs, int njobs, int total) {
+  __shared__ uint32_t tile[8][32][17];                      // per warp: 32 output-channel rows x 16 input-channel pairs (+1 pad)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, col = lane & 15;
+  for (int ft = blockIdx.x * 8 + warp; ft < total; ft += gridDim.x * 8) {
+    // the job whose tile range contains ft: the last one whose first tile is <= ft (prefix starts are ascending)
+    int j = 0;
+    for (int base = 0; base < njobs; base += 32) {
+      const int cand = base + lane;
+      const bool le = cand < njobs && (int)jobs[(size_t)cand * 6 + 5] <= ft;
+      const unsigned m = __ballot_sync(0xffffffffu, le);
+      if (m) j = base + 31 - __clz(m);
+    }
+    const long long* jb = jobs + (size_t)j * 6;
+    const int Cout = (int)jb[2], Cin_tot = (int)jb[3], Cin_used = (int)jb[4];
+    const int tci = Cin_used / 32, per_tap = (Cout / 32) * tci;
+    const int lt = ft - (int)jb[5];
+    const int t = lt / per_tap, r = lt % per_tap;
+    const int co0 = (r / tci) * 32, ci0 = (r % tci) * 32;
+    const __nv_bfloat16* src = w16 + jb[0];
+    __nv_bfloat16* dst = wd16 + jb[1];
+    if ((Cin_tot & 1) == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int co = 2 * i + half;
+        tile[warp][co][col] = *reinterpret_cast<const uint32_t*>(src + ((size_t)(co0 + co) * 9 + t) * Cin_tot + ci0 + 2 * col);
+      }
+    } else {                                                // odd row length (the 33-channel conv1.0): rows are not 4-byte aligned
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int co = 2 * i + half;
+        const __nv_bfloat16* q = src + ((size_t)(co0 + co) * 9 + t) * Cin_tot + ci0 + 2 * col;
+        const uint32_t lo = *reinterpret_cast<const unsigned short*>(q), hi = *reinterpret_cast<const unsigned short*>(q + 1);
+        tile[warp][co][col] = lo | (hi << 16);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int ci = 2 * i + half;                          // output row; the pair (co = 2 col, 2 col + 1) of it
+      const uint32_t a = tile[warp][2 * col][i], b = tile[warp][2 * col + 1][i];
+      const uint32_t v = half ? __byte_perm(a, b, 0x7632) : __byte_perm(a, b, 0x5410);
+      *reinterpret_cast<uint32_t*>(dst + ((size_t)(ci0 + ci) * 9 + t) * Cout + co0 + 2 * col) = v;
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4* __restrict__ src, __nv_bfloat162* __restrict__ dst,
                                                           long long n4) {
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
@@ -296,6 +349,17 @@ extern "C" int faln_pack_dgrad_batched(const void* w16, void* wd16, const long l
   pack_dgrad_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(w16),
                                                           static_cast<__nv_bfloat16*>(wd16), jobs);
   return after_launch("pack_dgrad_kernel");
+}
+
+extern "C" int faln_pack_dgrad_flat(const void* w16, void* wd16, const long long* jobs, int njobs, int total_tiles,
+                                    faln_stream_t stream) {
+  FALN_REQUIRE(w16 && wd16 && jobs && njobs > 0 && total_tiles > 0, "faln_pack_dgrad_flat: bad arguments");
+  long long grid = (total_tiles + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  pack_dgrad_flat_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(w16),
+                                                                   static_cast<__nv_bfloat16*>(wd16), jobs, njobs, total_tiles);
+  return after_launch("pack_dgrad_flat_kernel");
 }
 
 extern "C" int faln_f32_to_bf16(const float* src, void* dst, long long n, faln_stream_t stream) {

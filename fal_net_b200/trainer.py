@@ -57,18 +57,19 @@ class FlatAdamDDP:
         self._versions = [p._version for p in self.params]
         if dev.type == "cuda":
             self.w16 = torch.zeros(self.n, device=dev, dtype=torch.bfloat16)
-            jobs, o, max_tiles = [], 0, 1
+            jobs, o, max_tiles, total_tiles = [], 0, 1, 0
             for i, shp in enumerate(self.shapes):
                 if len(shp) == 4 and shp[2:] == (3, 3) and shp[0] % 32 == 0 and shp[1] >= 32:
                     cout, cin = shp[0], shp[1]
                     used = cin // 32 * 32
-                    jobs.append([offs[i], o, cout, cin, used, 0])
+                    jobs.append([offs[i], o, cout, cin, used, total_tiles])     # [5]: first tile of the job in the flat list
                     self._dgrad_off[i] = (o, used)
                     o += used * 9 * cout
                     max_tiles = max(max_tiles, 9 * (cout // 32) * (used // 32))
+                    total_tiles += 9 * (cout // 32) * (used // 32)
             self.wd16 = torch.zeros(max(o, 8), device=dev, dtype=torch.bfloat16)
             self._jobs = torch.tensor(jobs, dtype=torch.int64, device=dev) if jobs else None
-            self._max_tiles = max_tiles
+            self._max_tiles, self._total_tiles = max_tiles, total_tiles
             self.sync_shadow()
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         # The reference's two Adam param groups (Train_Stage1_K.py:177-181: bias_parameters with bias_decay, weight_parameters
@@ -184,9 +185,14 @@ class FlatAdamDDP:
         if self._jobs is None:
             return
         from . import _lib
-        _lib.check(_lib.lib().faln_pack_dgrad_batched(_lib.ptr(self.w16), _lib.ptr(self.wd16), _lib.ptr(self._jobs),
-                                                      self._jobs.shape[0], self._max_tiles, _lib.cur_stream()),
-                   "faln_pack_dgrad_batched")
+        if os.environ.get("FALN_PACK_DGRAD_2D", "0") not in ("", "0"):        # the first version: a max_tiles x njobs grid
+            _lib.check(_lib.lib().faln_pack_dgrad_batched(_lib.ptr(self.w16), _lib.ptr(self.wd16), _lib.ptr(self._jobs),
+                                                          self._jobs.shape[0], self._max_tiles, _lib.cur_stream()),
+                       "faln_pack_dgrad_batched")
+            return
+        _lib.check(_lib.lib().faln_pack_dgrad_flat(_lib.ptr(self.w16), _lib.ptr(self.wd16), _lib.ptr(self._jobs),
+                                                   self._jobs.shape[0], self._total_tiles, _lib.cur_stream()),
+                   "faln_pack_dgrad_flat")
 
     def _fresh(self, i):
         if self.params[i]._version != self._versions[i]:      # someone wrote the parameter through torch: re-derive

@@ -211,6 +211,10 @@ int faln_f32_to_bf16(const float* src, void* dst, long long n, faln_stream_t str
  * max_tiles >= max_j 9 * (Cout/32) * (Cin_used/32).  `jobs` is device memory. */
 int faln_pack_dgrad_batched(const void* w16, void* wd16, const long long* jobs, int njobs, int max_tiles,
                             faln_stream_t stream);
+/* The same over a flat tile list (no empty blocks, 4-byte accesses): jobs[6j+5] = index of job j's first 32x32 tile in the
+ * concatenation of all jobs' tiles (9 * (Cout/32) * (Cin_used/32) tiles per job), total_tiles their number. */
+int faln_pack_dgrad_flat(const void* w16, void* wd16, const long long* jobs, int njobs, int total_tiles,
+                         faln_stream_t stream);
 /* Inference form of the last layer (reference models/FAL_netB.py:174,215-229; Test_KITTI.py:196): the folded logits conv
  * with the softmax-expectation over the N disparity levels fused into its epilogue, disp [B,1,H,W] fp32 =
  * sum_n d_lvl[b,n] * softmax_n(conv3x3(cat(x, x2)) + bias).  The logit planes never reach HBM.  Stride 1, W >= 192,

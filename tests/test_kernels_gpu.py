@@ -181,3 +181,26 @@ def test_flat_adam_two_param_groups_like_the_reference():
         topt.step()
     for n, p in m.used_parameters():
         assert float((p.detach() - ref[n].detach()).abs().max()) < 2e-6, n
+
+
+def test_flat_dgrad_repack_equals_the_two_dimensional_launch():
+    """faln_pack_dgrad_flat (flat tile list, a warp per 32x32 tile, 4-byte accesses; odd row length of the 33-channel
+    conv1.0 included) writes bit for bit what faln_pack_dgrad_batched writes, for every 3x3 weight of FAL_netB."""
+    from fal_net_b200 import _lib, models
+    from fal_net_b200.trainer import FlatAdamDDP
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    m = models.__dict__["FAL_netB"](None, no_levels=49).to(dev)
+    opt = FlatAdamDDP(m, lr=1e-4)
+    assert opt._total_tiles == sum(9 * (int(j[2]) // 32) * (int(j[4]) // 32) for j in opt._jobs.tolist())
+    assert any(int(j[3]) % 2 == 1 for j in opt._jobs.tolist())          # the odd-pitch path is exercised
+    a = torch.zeros_like(opt.wd16)
+    b = torch.zeros_like(opt.wd16)
+    L = _lib.lib()
+    _lib.check(L.faln_pack_dgrad_batched(_lib.ptr(opt.w16), _lib.ptr(a), _lib.ptr(opt._jobs), opt._jobs.shape[0],
+                                         opt._max_tiles, _lib.cur_stream()), "2d")
+    _lib.check(L.faln_pack_dgrad_flat(_lib.ptr(opt.w16), _lib.ptr(b), _lib.ptr(opt._jobs), opt._jobs.shape[0],
+                                      opt._total_tiles, _lib.cur_stream()), "flat")
+    torch.cuda.synchronize()
+    assert float(a.float().abs().sum()) > 0
+    assert torch.equal(a.view(torch.int16), b.view(torch.int16))
