@@ -78,6 +78,11 @@ _SKIP_BIAS_SUMS = os.environ.get("FALN_DEBUG_SKIP_BIAS_SUMS", "0") not in ("", "
 # Bias gradients from the spare operand slot of the layer's weight-gradient launch (FALN_NO_FUSED_BIAS_GRAD=1: one channel-sum
 # launch per biased layer on the bias stream instead -- 13 launches that re-read every gradient map; measured as 2.7 % of the
 # Stage-1 step by leaving them out, FALN_DEBUG_SKIP_BIAS_SUMS).
+# FALN_PREP_ON_SIDE=1: start the small per-step weight transforms of the forward (folded deconv packs, folded logits layer,
+# constant-channel table) on the side stream beside the encoder instead of inline.  Measured on B200 (100-step runs, twice
+# each): Stage-1 step 3.811 ms on the side stream vs 3.784 ms inline -- SLOWER, like every other attempt to put work beside
+# the full-resolution layers that open the forward.  Off by default.
+PREP_ON_SIDE = os.environ.get("FALN_PREP_ON_SIDE", "0") not in ("", "0")
 FUSE_BIAS_GRAD = os.environ.get("FALN_NO_FUSED_BIAS_GRAD", "0") in ("", "0")
 USE_UP2_WGRAD = os.environ.get("FALN_NO_UP2_WGRAD", "0") in ("", "0")
 
@@ -85,6 +90,11 @@ USE_UP2_WGRAD = os.environ.get("FALN_NO_UP2_WGRAD", "0") in ("", "0")
 def _up2_packs(weight):
     """(forward, dgrad) folded packs of a deconv weight: one launch, refreshed once per optimiser step."""
     return _cached(weight, ("up2",), lambda: CN.pack_up2_weights(weight))
+
+
+def _ctab(weight, channel):
+    """Border-class table of the constant input channel (conv1.0's 33rd input), refreshed once per optimiser step."""
+    return _cached(weight, ("ctab", channel), lambda: CN.const_channel_table_of(weight, channel))
 
 
 def _wk(weight, cin=None):
@@ -142,6 +152,23 @@ def forward(model, image, max_disp, tape=None, disp_lvl=None):
     if tape is not None and sink is not None and hasattr(sink, "start_repack"):
         sink.start_repack(_side_streams(image.device)[0])      # data-gradient weight packs: overlapped with this forward
     flow_val = (max_disp.reshape(B).float() / 100.0).contiguous()                  # :208-209, constant plane per sample
+    # Optional (PREP_ON_SIDE, measured slower, off): the small per-step weight transforms (six folded deconv packs, the folded
+    # logits layer, the constant-channel table) start on the side stream beside the encoder; the inline calls below then hit
+    # the caches.
+    prep_ev = None
+    if tape is not None and USE_SIDE_STREAM and PREP_ON_SIDE and image.is_cuda:
+        main, side = torch.cuda.current_stream(image.device), _side_streams(image.device)[0]
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if USE_UP2 and image.shape[2] % 64 == 0 and image.shape[3] % 64 == 0:      # exact 2x at every level
+                for lvl, *_ in DEC:
+                    up = getattr(bb, f"deconv{lvl}")
+                    if up.conv1.weight.shape[1] % 32 == 0:
+                        _up2_packs(up.conv1.weight)
+            _folded_packs(model, None)
+            _ctab(getattr(bb, ENC[1][0])[0].weight, ENC[0][2])
+            prep_ev = torch.cuda.Event()
+            prep_ev.record(side)
     skips = []
     for i, (name, _, cout, stride) in enumerate(ENC):
         head = getattr(bb, name)[0]
@@ -149,7 +176,9 @@ def forward(model, image, max_disp, tape=None, disp_lvl=None):
             a = CN.stem_conv(image, head.weight, head.bias, 1)                     # reads the fp32 NCHW image directly
         else:
             C1 = skips[-1].shape[1]
-            ctab = CN.const_channel_table_of(head.weight, C1) if i == 1 else None
+            if i == 1 and prep_ev is not None:
+                torch.cuda.current_stream(image.device).wait_event(prep_ev)
+            ctab = _ctab(head.weight, C1) if i == 1 else None
             a = CN.conv3x3_fwd(skips[-1], _wk(head.weight, C1), head.bias, stride, 1, cout=cout, ctab=ctab,
                                cscale=flow_val if i == 1 else None)
         blk = getattr(bb, name + "_1")
