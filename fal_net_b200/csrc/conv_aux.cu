@@ -125,6 +125,36 @@ __global__ void __launch_bounds__(256) upsample_nearest_kernel(const uint4* __re
   }
 }
 
+// The same, one block row per OUTPUT row: the source row and the 64-bit bases are computed once per block, the column index
+// with 32-bit arithmetic, and every thread keeps four 16-byte loads in flight.  (The flat kernel above spends ~150 instructions
+// per 16 bytes on 64-bit div / mod: 563 us per Test pass of 8 x 375 x 1242 against ~175 us of DRAM time.)
+__global__ void __launch_bounds__(256) upsample_nearest_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                                    int Hi, int Wi, int Ho, int Wo, int C8, float sh, float sw) {
+  const int row = blockIdx.y;                       // b * Ho + ho
+  const int b = row / Ho, ho = row - b * Ho;
+  const int hi = min((int)floorf(ho * sh), Hi - 1);
+  const uint4* srow = src + ((long long)b * Hi + hi) * Wi * C8;
+  uint4* drow = dst + (long long)row * Wo * C8;
+  const int rowlen = Wo * C8;
+  for (int j0 = blockIdx.x * 1024 + threadIdx.x; j0 < rowlen; j0 += gridDim.x * 1024) {
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = j0 + 256 * k;
+      if (j < rowlen) {
+        const int wo = j / C8, c = j - wo * C8;
+        const int wi = min((int)floorf(wo * sw), Wi - 1);
+        v[k] = __ldg(srow + wi * C8 + c);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = j0 + 256 * k;
+      if (j < rowlen) drow[j] = v[k];
+    }
+  }
+}
+
 // 2x2 / stride-2 max pooling (floor mode), bf16 NHWC.
 __global__ void __launch_bounds__(256) maxpool2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int Hi,
                                                        int Wi, int C8) {
@@ -252,6 +282,58 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const uint4* __restri
   }
 }
 
+// The same, one thread per 2x2 WINDOW and 8-channel chunk: four x loads + one g_y load feed four stores (the per-pixel kernel
+// above loads the whole window again for each of its four pixels and pays 64-bit div / mod per 16 bytes).  One block row per
+// window row; odd trailing rows / columns are zero-filled by the threads of the last window row / column.
+__global__ void __launch_bounds__(256) maxpool2_bwd_win_kernel(const uint4* __restrict__ x, const uint4* __restrict__ g_y,
+                                                               uint4* __restrict__ g_x, int Hi, int Wi, int C8, int dact) {
+  const int Ho = Hi / 2, Wo = Wi / 2, Hw = (Hi + 1) / 2, Ww = (Wi + 1) / 2;   // windows incl. the partial trailing ones
+  const int row = blockIdx.y;                       // b * Hw + window row
+  const int b = row / Hw, ho = row - b * Hw;
+  const int rowlen = Ww * C8;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (int j = blockIdx.x * 256 + threadIdx.x; j < rowlen; j += gridDim.x * 256) {
+    const int wo = j / C8, c = j - wo * C8;
+    const int h0 = 2 * ho, w0 = 2 * wo;
+    const long long base = (((long long)b * Hi + h0) * Wi + w0) * C8 + c;
+    const long long dn = (long long)Wi * C8;
+    if (ho < Ho && wo < Wo) {
+      const uint4 q[4] = {__ldg(x + base), __ldg(x + base + C8), __ldg(x + base + dn), __ldg(x + base + dn + C8)};
+      const uint4 gy = __ldg(g_y + (((long long)b * Ho + ho) * Wo + wo) * C8 + c);
+      uint4 o[4];
+      const unsigned short* gv = reinterpret_cast<const unsigned short*>(&gy);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&q[k])[e]);
+        // first maximum in window scan order (ATen's max_pool2d_with_indices tie-breaking)
+        const bool g1 = v[1] > v[0];
+        const float m01 = g1 ? v[1] : v[0];
+        const bool g2 = v[2] > m01;
+        const float m012 = g2 ? v[2] : m01;
+        const bool g3 = v[3] > m012;
+        const int arg = g3 ? 3 : (g2 ? 2 : (g1 ? 1 : 0));
+        const float vmax = g3 ? v[3] : m012;
+        const bool live = !dact || vmax > 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          reinterpret_cast<unsigned short*>(&o[k])[e] = (live && arg == k) ? gv[e] : (unsigned short)0;
+      }
+      g_x[base] = o[0];
+      g_x[base + C8] = o[1];
+      g_x[base + dn] = o[2];
+      g_x[base + dn + C8] = o[3];
+    } else {
+      // partial trailing window: whatever pixels of it exist get a zero gradient (floor-mode pooling never reads them)
+      if (h0 < Hi && w0 < Wi) g_x[base] = zero;
+      if (h0 < Hi && w0 + 1 < Wi) g_x[base + C8] = zero;
+      if (h0 + 1 < Hi && w0 < Wi) g_x[base + dn] = zero;
+      if (h0 + 1 < Hi && w0 + 1 < Wi) g_x[base + dn + C8] = zero;
+    }
+  }
+}
+
 // Per-channel sums of a bf16 NHWC gradient (bias gradients): out[c] += sum over pixels of g[pix, c], fp32.
 // Block = 256 threads = (256 / C8) pixel lanes x C8 channel groups of 8; shared-memory tree over the pixel lanes, then one
 // atomicAdd per channel per block.
@@ -342,6 +424,16 @@ extern "C" int faln_upsample_nearest_nhwc(const void* src, void* dst, int B, int
                                           faln_stream_t stream) {
   FALN_REQUIRE(src && dst && B > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C % 8 == 0, "faln_upsample_nearest_nhwc: C %% 8");
   const long long n = (long long)B * Ho * Wo * (C / 8);
+  static const bool flat = getenv("FALN_EW_FLAT") != nullptr;      // A/B switch: the first-generation flat-index kernels
+  if (!flat && (long long)B * Ho <= 65535 && (long long)Wo * (C / 8) < (1LL << 30) && (long long)Wi * (C / 8) < (1LL << 30)) {
+    const int rowlen = Wo * (C / 8);
+    int gx = (rowlen + 1023) / 1024;
+    if (gx > 8) gx = 8;
+    upsample_nearest_rows_kernel<<<dim3(gx, B * Ho), 256, 0, as_stream(stream)>>>(
+        static_cast<const uint4*>(src), static_cast<uint4*>(dst), Hi, Wi, Ho, Wo, C / 8, (float)Hi / (float)Ho,
+        (float)Wi / (float)Wo);
+    return after_launch("upsample_nearest_rows_kernel");
+  }
   upsample_nearest_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(
       static_cast<const uint4*>(src), static_cast<uint4*>(dst), B, Hi, Wi, Ho, Wo, C / 8, (float)Hi / (float)Ho,
       (float)Wi / (float)Wo);
@@ -372,6 +464,16 @@ extern "C" int faln_maxpool2_bwd_nhwc(const void* x, const void* g_y, void* g_x,
                                       faln_stream_t stream) {
   FALN_REQUIRE(x && g_y && g_x && B > 0 && Hi >= 2 && Wi >= 2 && C % 8 == 0, "faln_maxpool2_bwd_nhwc: bad argument");
   const long long n = (long long)B * Hi * Wi * (C / 8);
+  static const bool flat = getenv("FALN_EW_FLAT") != nullptr;      // A/B switch: the first-generation flat-index kernel
+  const int Hw = (Hi + 1) / 2, Ww = (Wi + 1) / 2;
+  if (!flat && (long long)B * Hw <= 65535 && (long long)Wi * (C / 8) < (1LL << 30)) {
+    const int rowlen = Ww * (C / 8);
+    int gx = (rowlen + 255) / 256;
+    if (gx > 16) gx = 16;
+    maxpool2_bwd_win_kernel<<<dim3(gx, B * Hw), 256, 0, as_stream(stream)>>>(
+        static_cast<const uint4*>(x), static_cast<const uint4*>(g_y), static_cast<uint4*>(g_x), Hi, Wi, C / 8, dact);
+    return after_launch("maxpool2_bwd_win_kernel");
+  }
   maxpool2_bwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(g_y),
                                                                       static_cast<uint4*>(g_x), B, Hi, Wi, C / 8, dact);
   return after_launch("maxpool2_bwd_kernel");

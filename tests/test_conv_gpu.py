@@ -232,6 +232,16 @@ def test_upsample_pool_backward_and_channel_sum():
     F.max_pool2d(xr, 2, 2).backward(gy.float())
     ref = xr.grad * (x.float() > 0)
     assert rel_err(CN.maxpool2_bwd(x, gy, dact=2).float(), ref) < 1e-6
+    # ... with ties (ReLU outputs are full of equal zeros, bf16 values collide): the first maximum in scan order gets the
+    # gradient, as in ATen's max_pool2d_with_indices; even and odd sizes, several channel counts
+    for (Hh, Wh, C) in ((24, 80, 64), (13, 31, 128), (6, 20, 256)):
+        x = (torch.randn(2, C, Hh, Wh, generator=gen).clamp_min(0) * 4).round().div(4).bfloat16().to(dev).contiguous(memory_format=CL)
+        gy = torch.randn(2, C, Hh // 2, Wh // 2, generator=gen).bfloat16().to(dev).contiguous(memory_format=CL)
+        xr = x.float().requires_grad_(True)
+        F.max_pool2d(xr, 2, 2).backward(gy.float())
+        ref = xr.grad * (x.float() > 0)
+        got = CN.maxpool2_bwd(x, gy, dact=2).float()
+        assert torch.equal(got, ref), (Hh, Wh, C, float((got - ref).abs().max()))
     # channel sums (bias gradient), accumulating
     for C, Cs in ((64, 64), (49, 64), (256, 256), (32, 32), (512, 512)):
         g = torch.randn(2, Cs, 30, 50, generator=gen).bfloat16().to(dev).contiguous(memory_format=CL)
