@@ -249,6 +249,9 @@ def conv3x3_up2_dgrad(g, wd_fold, dact=0, ysave=None):
 # 64-channel VGG stem gains), Test flip-PP 7.73 vs 7.65 ms (loses) -- the extra pass over a 64 B/px patch tensor and the tile
 # kernel's per-pixel stores eat what the FMA pipe saves, and it rounds the input image to bf16.  Default: off.
 STEM_TC = __import__("os").environ.get("FALN_STEM_TC", "0") not in ("", "0")
+# The default: the fused tcgen05 stem (csrc/conv_tc.cu stem_mma_kernel; patch rows built in shared memory as bf16 hi + lo pairs).
+# FALN_STEM_FMA=1 selects the fp32-FMA kernel again.
+STEM_MMA = __import__("os").environ.get("FALN_STEM_FMA", "0") in ("", "0")
 
 
 def stem_conv(x, w, bias, act, flip_x=False):
@@ -266,6 +269,14 @@ def stem_conv(x, w, bias, act, flip_x=False):
         rc = _lib.lib().faln_stem_conv_tc(_lib.ptr(x), _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(y), _lib.ptr(col), _lib.ptr(wpack),
                                           B, H, W, Cout, int(act), int(flip_x), _lib.cur_stream())
         _lib.check(rc, "faln_stem_conv_tc")
+        if ev is not None:
+            ev.record()
+        return y
+    if STEM_MMA:
+        ev = _timed("conv_fwd", 2 * 27 * Cout * B * H * W, 12 * B * H * W + 2 * B * H * W * Cout, Cout)
+        rc = _lib.lib().faln_stem_conv_mma(_lib.ptr(x), _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(y), B, H, W, Cout, int(act),
+                                           int(flip_x), _lib.cur_stream())
+        _lib.check(rc, "faln_stem_conv_mma")
         if ev is not None:
             ev.record()
         return y

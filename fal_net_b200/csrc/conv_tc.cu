@@ -1814,6 +1814,176 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
 }  // namespace
 }  // namespace faln
 
+
+namespace faln {
+namespace {
+// ------------------------------------------------------------------------------------------ fused tensor-core stem
+// The 3 -> 32 / 3 -> 64 first layer (conv0.0 of the encoder, conv1_1 of the VGG slices) as ONE kernel on tcgen05: the fp32-FMA
+// stem kernel (conv_aux.cu) spends 864 (1728) FMAs per pixel and runs 4-5x off both its HBM and its issue bound, and the
+// im2col + GEMM pair above writes and re-reads a 64 B / px patch tensor.  Here a CTA of 128 threads owns 128 consecutive
+// pixels of an image row per turn; every thread gathers the 27 taps of ITS pixel straight from the fp32 NCHW image, splits
+// each into a bf16 high and low part (hi + lo carries 16 mantissa bits: the image is not rounded to bf16) and writes the row
+//     A[pixel] = [ hi(27) 0(5) | lo(27) 0(5) ]   (K = 64 bf16 = one 128-byte swizzle row)
+// of a K-major SWIZZLE_128B operand tile in shared memory -- the patch matrix never leaves the SM.  The weights sit beside it
+// as B[co] = [ w(27) 0(5) | w(27) 0(5) ] (bf16 like every other layer's), four K = 16 instructions produce the 128 x CO fp32
+// tile in TMEM, and the same threads read their pixel's row back (tcgen05.ld), add the bias, apply ELU / ReLU and store
+// bf16 NHWC.  No pipeline inside the CTA: 25 KB of shared memory and CO TMEM columns let eight CTAs share an SM and hide each
+// other's gather / MMA / store phases.
+template <int CO, int ACT>
+__global__ void __launch_bounds__(128)
+stem_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                __nv_bfloat16* __restrict__ y, int B, int H, int W, int tiles_w, long long total, int flip_x) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* At = base;                              // 128 rows x 128 B
+  unsigned char* Bt = base + 128 * 128;                  // CO rows x 128 B
+  float* sbias = reinterpret_cast<float*>(Bt + CO * 128);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sbias + CO);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  // one swizzled operand row: 8 chunks of 8 bf16; chunk j of row r lives at physical chunk j ^ (r & 7)
+  auto store_row = [](unsigned char* tile, int r, const uint32_t (&pk)[32]) {
+    unsigned char* row = tile + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4*>(row + ((j ^ (r & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  };
+  auto pack2 = [](float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  };
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, CO);
+  if (tid < CO) {
+    sbias[tid] = bias ? __ldg(bias + tid) : 0.f;
+    float wv[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) wv[k] = k < 27 ? __ldg(w + tid * 27 + k) : 0.f;
+    uint32_t pk[32];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) pk[k] = pk[16 + k] = pack2(wv[2 * k], wv[2 * k + 1]);
+    store_row(Bt, tid, pk);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint64_t adesc = make_desc<64>(smem_u32(At)), bdesc = make_desc<64>(smem_u32(Bt));
+  constexpr uint32_t idesc = make_idesc<CO>();
+  const long long hw = (long long)H * W;
+  uint32_t phase = 0;
+
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int tw = (int)(t % tiles_w);
+    const long long row = t / tiles_w;                   // b * H + y
+    const int yy0 = (int)(row % H);
+    const long long b = row / H;
+    const int xo = tw * 128 + tid;
+    // ---- gather the 27 taps of pixel (b, yy0, xo): fp32 NCHW, zero padding, optional horizontal flip of the source
+    float v[32];
+    const float* pb = x + b * 3 * hw;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int yy = yy0 + dy - 1;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int xx = xo + dx - 1;
+          const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+          const int xs = flip_x ? W - 1 - xx : xx;
+          v[c * 9 + dy * 3 + dx] = in ? __ldg(pb + c * hw + (long long)yy * W + xs) : 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 27; k < 32; ++k) v[k] = 0.f;
+    uint32_t pk[32];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+      const float2 hf = __bfloat1622float2(h);
+      pk[k] = *reinterpret_cast<const uint32_t*>(&h);
+      pk[16 + k] = pack2(v[2 * k] - hf.x, v[2 * k + 1] - hf.y);
+    }
+    store_row(At, tid, pk);
+    fence_proxy_async();                                 // generic-proxy stores -> visible to the tensor core's async proxy
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, idesc, kk != 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: this thread's pixel = TMEM lane 32 * warp + lane, CO columns, sixteen at a time
+    const bool valid = xo < W;
+    __nv_bfloat16* out = y + ((row * W) + xo) * CO;
+#pragma unroll
+    for (int c0 = 0; c0 < CO; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, r);
+      if (valid) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          f[j] = __uint_as_float(r[j]) + sbias[c0 + j];
+          if (ACT == 1) f[j] = elu1(f[j]);
+          if (ACT == 2) f[j] = fmaxf(f[j], 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          *reinterpret_cast<uint4*>(out + c0 + 8 * q) = make_uint4(pack2(f[8 * q], f[8 * q + 1]), pack2(f[8 * q + 2], f[8 * q + 3]),
+                                                                  pack2(f[8 * q + 4], f[8 * q + 5]), pack2(f[8 * q + 6], f[8 * q + 7]));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                                     // everyone has read the accumulator: the next tile may overwrite it and A
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, CO);
+  }
+}
+}  // namespace
+}  // namespace faln
+
+// The stem as one tcgen05 kernel (stem_mma_kernel): x [B,3,H,W] fp32 NCHW, w [Cout,3,3,3] fp32, bias [Cout] or NULL ->
+// y [B,H,W,Cout] bf16 NHWC, Cout = 32 or 64.  Same contract as faln_stem_conv (conv_aux.cu), which it replaces by default.
+extern "C" int faln_stem_conv_mma(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int Cout,
+                                  int act, int flip_x, faln_stream_t stream) {
+  FALN_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0, "faln_stem_conv_mma: bad argument");
+  FALN_REQUIRE(Cout == 32 || Cout == 64, "faln_stem_conv_mma: Cout must be 32 or 64 (got %d)", Cout);
+  FALN_REQUIRE(act >= 0 && act <= 2, "faln_stem_conv_mma: act must be 0 (none), 1 (ELU) or 2 (ReLU)");
+  FALN_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, "faln_stem_conv_mma: y must be 16-byte aligned");
+  const int tiles_w = (W + 127) / 128;
+  const long long total = (long long)B * H * tiles_w;
+  const int smem = 1024 + 128 * 128 + Cout * 128 + Cout * 4 + 64;
+  static const int per_sm = getenv("FALN_STEM_CTAS") ? atoi(getenv("FALN_STEM_CTAS")) : 8;
+  long long grid = (long long)sm_count() * (per_sm > 0 ? per_sm : 8);
+  if (grid > total) grid = total;
+  cudaStream_t st = as_stream(stream);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(y);
+#define FALN_STEM_MMA(C, A) stem_mma_kernel<C, A><<<(int)grid, 128, smem, st>>>(x, w, bias, out, B, H, W, tiles_w, total, flip_x)
+  if (Cout == 32) {
+    if (act == 0) FALN_STEM_MMA(32, 0); else if (act == 1) FALN_STEM_MMA(32, 1); else FALN_STEM_MMA(32, 2);
+  } else {
+    if (act == 0) FALN_STEM_MMA(64, 0); else if (act == 1) FALN_STEM_MMA(64, 1); else FALN_STEM_MMA(64, 2);
+  }
+#undef FALN_STEM_MMA
+  return after_launch("stem_mma_kernel");
+}
+
 // x [B,3,H,W] fp32 NCHW, w [Cout,3,3,3] fp32, bias [Cout] or NULL -> y [B,H,W,Cout] bf16 NHWC (Cout = 32 or 64).
 // col: scratch [B,H,W,32] bf16; wpack: scratch [Cout,32] bf16 (both written by this call).
 extern "C" int faln_stem_conv_tc(const float* x, const float* w, const float* bias, void* y, void* col, void* wpack, int B,

@@ -262,6 +262,11 @@ int faln_channel_sum_nhwc(const void* g, float* out, long long npix, int C, int 
  * (flip_x: x-reversed), w [Cout,3,3,3] fp32 (torch OIHW), Cout 32 or 64, writes bf16 NHWC [B,H,W,Cout]. */
 int faln_stem_conv(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int Cout,
                    int act, int flip_x, faln_stream_t stream);
+/* The same layer as ONE tcgen05 kernel (the default): every thread gathers the 27 taps of its pixel from the fp32 image, writes
+ * them as a bf16 hi + lo pair into a swizzled K = 64 operand row in shared memory (the patch matrix never reaches HBM and the
+ * image keeps 16 mantissa bits), four MMAs per 128 pixels, bias + activation epilogue out of TMEM.  Same arguments. */
+int faln_stem_conv_mma(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int Cout, int act,
+                       int flip_x, faln_stream_t stream);
 /* F.interpolate(mode='nearest') (:58) on bf16 NHWC: src index = min(floor(dst * in/out), in-1). */
 int faln_upsample_nearest_nhwc(const void* src, void* dst, int B, int Hi, int Wi, int Ho, int Wo, int C,
                                faln_stream_t stream);

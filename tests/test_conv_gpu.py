@@ -211,6 +211,38 @@ def test_conv3x3_dgrad(B, H, W, Cin, Cout, stride, dact, accum, res):
     assert e < 8e-3, e
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 19, 45), (1, 7, 300), (2, 12, 640), (1, 5, 1242)])
+def test_fused_tensor_core_stem(B, H, W):
+    """stem_mma_kernel (default stem: 27-tap patch rows built in shared memory as bf16 hi + lo pairs, four tcgen05 MMAs per 128
+    pixels) vs fp32 torch on the fp32 image with bf16-rounded weights -- the image itself must NOT be rounded to bf16 -- and vs
+    the fp32-FMA kernel it replaces; ragged last tile, several tiles per row, horizontal flip, both widths / activations."""
+    from fal_net_b200 import conv_native as CN
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(B * 7 + W)
+    x = torch.randn(B, 3, H, W, generator=g).to(dev)
+    assert CN.STEM_MMA
+    for Cout, act in ((32, 1), (64, 2), (32, 0)):
+        w = (torch.randn(Cout, 3, 3, 3, generator=g) * 0.3).to(dev)
+        b = torch.randn(Cout, generator=g).to(dev)
+        y = CN.stem_conv(x, w, b, act)
+        ref_w16 = _ref(x, w.bfloat16().float(), b, 1, act, None)
+        e = rel_err(y.float(), ref_w16)
+        assert e < 5e-3, (Cout, act, e)                                   # bf16 output rounding only (2^-9 of the max)
+        if act == 0:
+            # without the output's own bf16 rounding in the way: a bf16-rounded image would show ~4e-3 here
+            yy = y.float()
+            near = (yy - ref_w16).abs() <= (ref_w16.abs() * 2 ** -8 + 1e-3)
+            assert bool(near.all())
+        yf = CN.stem_conv(x, w, b, act, flip_x=True)
+        assert rel_err(yf.float(), _ref(torch.flip(x, dims=[3]), w.bfloat16().float(), b, 1, act, None)) < 5e-3
+        CN.STEM_MMA = False
+        try:
+            y_fma = CN.stem_conv(x, w, b, act)
+        finally:
+            CN.STEM_MMA = True
+        assert rel_err(y.float(), y_fma.float()) < 8e-3
+
+
 def test_upsample_pool_backward_and_channel_sum():
     from fal_net_b200 import conv_native as CN
     dev = torch.device("cuda:0")
