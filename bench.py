@@ -585,6 +585,16 @@ def conv_layer_table(tf_peak, hbm_peak, B=8, iters=8):
             t_od = timeit(lambda: CN.conv3x3_up2_dgrad(gy, wd_up))
             row["block_fwd"] = {"ours_folded_us": round(t_o, 1), "cudnn_interpolate_conv_elu_us": round(t_c, 1)}
             row["block_dgrad"] = {"ours_folded_us": round(t_od, 1)}
+            if cin % 64 == 0 and cout % 64 == 0:
+                # weight gradient of the block from the low-resolution input (conv3x3_wgrad_up2_kernel) against ours on the
+                # explicitly up-sampled map (the path before that kernel) and the library's interpolate + wgrad
+                t_ow = timeit(lambda: CN.conv3x3_wgrad_up2(gy, xl, dW, cout=cout, cx=cin))
+                t_pw = timeit(lambda: CN.conv3x3_wgrad(gy, CN.upsample_nearest(xl, (H, W)), dW, cout=cout, cx=cin))
+                t_cw = timeit(lambda: torch.ops.aten.convolution_backward(
+                    gy, F.interpolate(xl, scale_factor=2, mode="nearest"), w16, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                    [False, True, False]))
+                row["block_wgrad"] = {"ours_folded_us": round(t_ow, 1), "ours_upsample_plus_wgrad_us": round(t_pw, 1),
+                                      "cudnn_interpolate_wgrad_us": round(t_cw, 1)}
             del xl, xl32, wf_up, wd_up
         rows.append(row)
         del x, w, gy, w16, wk, wd, dW
@@ -930,14 +940,41 @@ def run_gpu(a, wl, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAda
                 loss_sum += graphed.loss_value(pending)    # the user reads EVERY step's loss, one step behind the device
             pending = ticket
         else:
-            ld = l.to(dev, non_blocking=True)
-            rd = r.to(dev, non_blocking=True) if wl in ("stage1", "stage2") else None
+            # no captured graph (inference): the same pipeline by hand -- batch i + 1 is uploaded on a copy stream while
+            # step i runs, and the result of step i - 1 is read while step i is queued
+            cur = torch.cuda.current_stream()
+            if i == 0:
+                copy_stream = torch.cuda.Stream()
+                res_ring = torch.empty(2, pin_memory=True)
+                with torch.cuda.stream(copy_stream):
+                    nxt = (l.to(dev, non_blocking=True), r.to(dev, non_blocking=True) if wl in ("stage1", "stage2") else None)
+                    up_ev = torch.cuda.Event()
+                    up_ev.record(copy_stream)
+            cur.wait_event(up_ev)
+            ld, rd = nxt
             loss = run_step(ld, rd)
-            out_host.copy_(loss.detach().reshape(1), non_blocking=True)
-            torch.cuda.current_stream().synchronize()      # the user reads the result every step
-            loss_sum += float(out_host[0])
+            if i + 1 < a.steps:
+                l2, r2 = host[(i + 1) % nb]
+                with torch.cuda.stream(copy_stream):
+                    nxt = (l2.to(dev, non_blocking=True), r2.to(dev, non_blocking=True) if wl in ("stage1", "stage2") else None)
+                    up_ev = torch.cuda.Event()
+                    up_ev.record(copy_stream)
+            for t_ in (ld, rd):
+                if t_ is not None:
+                    t_.record_stream(cur)                  # allocated on the copy stream, consumed on the compute stream
+            res_ring[i & 1:(i & 1) + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            ev_i = torch.cuda.Event()
+            ev_i.record(cur)
+            if pending is not None:
+                pending[0].synchronize()                   # the user reads EVERY step's result, one step behind the device
+                loss_sum += float(res_ring[pending[1]])
+            pending = (ev_i, i & 1)
     if pending is not None:
-        loss_sum += graphed.loss_value(pending)            # ... and the last one before the clock stops
+        if graphed is not None:
+            loss_sum += graphed.loss_value(pending)        # ... and the last one before the clock stops
+        else:
+            pending[0].synchronize()
+            loss_sum += float(res_ring[pending[1]])
     e1.record()
     if not (loss_sum == loss_sum):
         raise RuntimeError("e2e loop produced a NaN loss")
@@ -979,7 +1016,8 @@ def run_gpu(a, wl, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAda
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "readback": ("every step's loss is copied D2H behind the step and read by the host one step late "
                              "(GraphedStep.run_async / loss_value); the last one before the clock stops") if graphed is not None
-                else "synchronous read of every step's result"},
+                else "inputs of step i + 1 uploaded on a copy stream while step i runs; every step's result is copied D2H "
+                     "behind the step and read one step late; the last one before the clock stops"},
         "gpu_launches": launches, "cuda_graph": graphed is not None,
         "library_conv_calls_in_timed_region": lib_convs,
         "roofline": roofline,

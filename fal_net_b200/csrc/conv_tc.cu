@@ -1830,7 +1830,7 @@ namespace {
 // bf16 NHWC.  No pipeline inside the CTA: 25 KB of shared memory and CO TMEM columns let eight CTAs share an SM and hide each
 // other's gather / MMA / store phases.
 template <int CO, int ACT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 stem_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                 __nv_bfloat16* __restrict__ y, int B, int H, int W, int tiles_w, long long total, int flip_x) {
   extern __shared__ unsigned char smem_raw[];
@@ -1886,20 +1886,27 @@ stem_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
     const long long b = row / H;
     const int xo = tw * 128 + tid;
     // ---- gather the 27 taps of pixel (b, yy0, xo): fp32 NCHW, zero padding, optional horizontal flip of the source
+    // (column / row offsets and their bounds are shared by the three channels: ~3 instructions per tap)
     float v[32];
     const float* pb = x + b * 3 * hw;
+    int xoff[3], yoff[3];
+    bool okx[3], oky[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int xx = xo + d - 1, yy = yy0 + d - 1;
+      okx[d] = xx >= 0 && xx < W;
+      oky[d] = yy >= 0 && yy < H;
+      xoff[d] = flip_x ? W - 1 - xx : xx;
+      yoff[d] = yy * W;
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
+      const float* pc = pb + c * hw;
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy) {
-        const int yy = yy0 + dy - 1;
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const int xx = xo + dx - 1;
-          const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
-          const int xs = flip_x ? W - 1 - xx : xx;
-          v[c * 9 + dy * 3 + dx] = in ? __ldg(pb + c * hw + (long long)yy * W + xs) : 0.f;
-        }
+        for (int dx = 0; dx < 3; ++dx)
+          v[c * 9 + dy * 3 + dx] = (oky[dy] && okx[dx]) ? __ldg(pc + (yoff[dy] + xoff[dx])) : 0.f;
       }
     }
 #pragma unroll
@@ -1924,29 +1931,54 @@ stem_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- epilogue: this thread's pixel = TMEM lane 32 * warp + lane, CO columns, sixteen at a time
-    const bool valid = xo < W;
-    __nv_bfloat16* out = y + ((row * W) + xo) * CO;
+    // ---- epilogue: this thread's pixel = TMEM lane 32 * warp + lane, CO columns, sixteen at a time -> bf16 row in the
+    // (now free) A tile, swizzled so that a quarter-warp's 16-byte stores hit distinct banks; then the tile -- one CONTIGUOUS
+    // run of valid_px * CO * 2 bytes in the NHWC output -- is copied out with fully coalesced 16-byte stores (a thread
+    // writing its own 64 / 128-byte row straight to global memory touches 32 different sectors per instruction: twice the
+    // L1 -> L2 store traffic, measured)
+    constexpr int RB = CO * 2, CPR = RB / 16;            // row bytes, 16-byte chunks per row
+    const int swz = CPR == 8 ? (tid & 7) : ((tid >> 1) & 3);
 #pragma unroll
     for (int c0 = 0; c0 < CO; c0 += 16) {
       uint32_t r[16];
       tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, r);
-      if (valid) {
-        float f[16];
+      float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          f[j] = __uint_as_float(r[j]) + sbias[c0 + j];
-          if (ACT == 1) f[j] = elu1(f[j]);
-          if (ACT == 2) f[j] = fmaxf(f[j], 0.f);
-        }
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-          *reinterpret_cast<uint4*>(out + c0 + 8 * q) = make_uint4(pack2(f[8 * q], f[8 * q + 1]), pack2(f[8 * q + 2], f[8 * q + 3]),
-                                                                  pack2(f[8 * q + 4], f[8 * q + 5]), pack2(f[8 * q + 6], f[8 * q + 7]));
+      for (int q = 0; q < 4; ++q) {
+        const float4 bq = *reinterpret_cast<const float4*>(sbias + c0 + 4 * q);
+        f[4 * q] = __uint_as_float(r[4 * q]) + bq.x;
+        f[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bq.y;
+        f[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bq.z;
+        f[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bq.w;
       }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (ACT == 1) f[j] = elu1(f[j]);
+        if (ACT == 2) f[j] = fmaxf(f[j], 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        *reinterpret_cast<uint4*>(At + tid * RB + (((c0 / 8 + q) ^ swz) << 4)) =
+            make_uint4(pack2(f[8 * q], f[8 * q + 1]), pack2(f[8 * q + 2], f[8 * q + 3]), pack2(f[8 * q + 4], f[8 * q + 5]),
+                       pack2(f[8 * q + 6], f[8 * q + 7]));
     }
     tc_fence_before();
-    __syncthreads();                                     // everyone has read the accumulator: the next tile may overwrite it and A
+    __syncthreads();                                     // the staged tile is complete (and everyone has read the accumulator)
+    {
+      const int valid_px = min(128, W - tw * 128);
+      uint4* out = reinterpret_cast<uint4*>(y + ((row * W) + tw * 128) * CO);
+      const int nchunks = valid_px * CPR;
+#pragma unroll
+      for (int k = 0; k < CPR; ++k) {
+        const int i = tid + 128 * k;
+        if (i < nchunks) {
+          const int pp = i / CPR, q = i % CPR;
+          const int sw = CPR == 8 ? (pp & 7) : ((pp >> 1) & 3);
+          out[i] = *reinterpret_cast<const uint4*>(At + pp * RB + ((q ^ sw) << 4));
+        }
+      }
+    }
+    __syncthreads();                                     // the copy-out has read the tile: the next gather may overwrite A
   }
   tc_fence_before();
   __syncthreads();
