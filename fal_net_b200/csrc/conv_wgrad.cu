@@ -180,7 +180,12 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
           for (int j = 0; j < IROWS; ++j) {
             uint64_t adesc;
-            if (HALO) {
+            if (HALO && XC == 32) {
+              // 32-channel blocks: instruction row j = the taps of COLUMN kw = j; its four 32-channel atoms are the windows
+              // of kh = 0, 1, 2 (one halo row = 18 pixels = the uniform LBO apart) and a spare one (kh = 3, dropped)
+              const uint32_t o0 = (uint32_t)((k * kHaloW + j) * XROWB);
+              adesc = make_desc_mn<XROWB>(0, kHaloW * XROWB) + xs16 + (uint64_t)(o0 >> 4);
+            } else if (HALO) {
               // instruction row j = taps 2j, 2j+1: windows of the halo tile starting at halo row (k + kh) * 18 + kw
               const int t0 = 2 * j, t1 = 2 * j + 1;
               const uint32_t o0 = (uint32_t)(((k + t0 / 3) * kHaloW + t0 % 3) * XROWB);
@@ -210,7 +215,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     for (int q = 0; q < kSteps; ++q) {
       const int step = (q + split) % kSteps;
       const int j = step / (NB / 32), c0 = (step % (NB / 32)) * 32;
-      const int tap = j * SPR + m / XC;
+      const int tap = (HALO && XC == 32) ? (m / XC < 3 ? (m / XC) * 3 + j : 9) : j * SPR + m / XC;
       const int ci = cib * XC + (m % XC);
       const bool row_ok = tap < 9 && ci < p.Cx;
       {
@@ -413,15 +418,16 @@ int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mg, const WgradParams
 }
 
 // halo tensor map: box [64 channels, 18, 6, 1], 128B swizzle
-bool make_halo_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C) {
+bool make_halo_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int XC = 64) {
   auto fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)kHaloW, (cuuint32_t)kHaloH, 1};
+  cuuint32_t box[4] = {(cuuint32_t)XC, (cuuint32_t)kHaloW, (cuuint32_t)kHaloH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, XC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -478,12 +484,16 @@ extern "C" int faln_conv3x3_wgrad_bias(const void* g, const void* x, float* dW, 
   p.n_cob = (Cout + p.NB - 1) / p.NB;
   const int spr = 128 / XC;
   p.irows = (9 + spr - 1) / spr;
-  p.halo = (stride == 1 && XC == 64 && !(flags & 1u)) ? 1 : 0;
+  // halo tile: stride-1 layers; 32-channel blocks too (three instruction rows = tap columns), unless the bias gradient rides
+  // along -- the column grouping has no freely addressable spare slot for the ones (only the stem's weight gradient: box path).
+  // FALN_WGRAD_NO_HALO32=1: nine boxes per chunk for the 32-channel blocks, as before (A/B switch).
+  static const bool no_halo32 = getenv("FALN_WGRAD_NO_HALO32") != nullptr;
+  p.halo = (stride == 1 && !(flags & 1u) && (XC == 64 || (!dbias && !no_halo32))) ? 1 : 0;
   const int xbox = kP * XC * 2, gbox = kP * GC * 2;
   if (p.halo) {
-    p.tx_x = kHaloW * kHaloH * 128;
-    // the dummy tenth tap of the last instruction row reads up to halo row (3 + 3) * 18 + 16: keep it inside the stage
-    p.x_bytes = ((((kCR - 1 + 3) * kHaloW + kTW) * 128) + 1023) / 1024 * 1024;
+    p.tx_x = kHaloW * kHaloH * XC * 2;
+    // the spare window of the last instruction row(s) reads up to halo row (3 + 3) * 18 + 2 + 16: keep it inside the stage
+    p.x_bytes = ((((kCR - 1 + 3) * kHaloW + 2 + kTW) * XC * 2) + 1023) / 1024 * 1024;
   } else {
     p.tx_x = 9 * xbox;
     p.x_bytes = p.irows * spr * xbox;
@@ -515,7 +525,7 @@ extern "C" int faln_conv3x3_wgrad_bias(const void* g, const void* x, float* dW, 
   if (splits > p.chunks / (min_chunks > 0 ? min_chunks : 16)) splits = p.chunks / (min_chunks > 0 ? min_chunks : 16);
   if (splits < 1) splits = 1;
   CUtensorMap mx, mg;
-  const bool ok_x = p.halo ? make_halo_map(&mx, x, B, H, W, Cxs) : make_act_map(&mx, x, B, H, W, Cxs, XC, stride, kCR);
+  const bool ok_x = p.halo ? make_halo_map(&mx, x, B, H, W, Cxs, XC) : make_act_map(&mx, x, B, H, W, Cxs, XC, stride, kCR);
   if (!ok_x || !make_act_map(&mg, g, B, Hg, Wg, Cg, GC, 1, kCR)) {
     set_error("faln_conv3x3_wgrad: cuTensorMapEncodeTiled failed (driver entry point missing or bad tensor geometry)");
     return FALN_ERR_LAUNCH;
@@ -525,8 +535,9 @@ extern "C" int faln_conv3x3_wgrad_bias(const void* g, const void* x, float* dW, 
     return p.halo ? launch_wgrad<128, 128, true>(mx, mg, p, splits, smem, st) : launch_wgrad<128, 128, false>(mx, mg, p, splits, smem, st);
   if (XC == 64 && GC == 32)
     return p.halo ? launch_wgrad<128, 64, true>(mx, mg, p, splits, smem, st) : launch_wgrad<128, 64, false>(mx, mg, p, splits, smem, st);
-  if (XC == 32 && GC == 64) return launch_wgrad<64, 128, false>(mx, mg, p, splits, smem, st);
-  return launch_wgrad<64, 64, false>(mx, mg, p, splits, smem, st);
+  if (XC == 32 && GC == 64)
+    return p.halo ? launch_wgrad<64, 128, true>(mx, mg, p, splits, smem, st) : launch_wgrad<64, 128, false>(mx, mg, p, splits, smem, st);
+  return p.halo ? launch_wgrad<64, 64, true>(mx, mg, p, splits, smem, st) : launch_wgrad<64, 64, false>(mx, mg, p, splits, smem, st);
 }
 
 // Weight gradient of the folded deconv block (nearest 2x up-sampling + conv3x3, see conv3x3_wgrad_up2_kernel):

@@ -34,10 +34,12 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("with_bias", [True, False])
 @pytest.mark.parametrize("flags", [0, 1])
-@pytest.mark.parametrize("B,H,W,Cxs,Cg,cout,cx,stride", CASES)
-def test_wgrad_matches_fp32(B, H, W, Cxs, Cg, cout, cx, stride, flags):
-    """flags 0: production path (halo tile for stride-1 64-channel blocks); 1: nine boxes per chunk everywhere."""
+@pytest.mark.parametrize("B,H,W,Cxs,Cg,cout,cx,stride", CASES + [(8, 192, 640, 32, 32, 32, 32, 1)])
+def test_wgrad_matches_fp32(B, H, W, Cxs, Cg, cout, cx, stride, flags, with_bias):
+    """flags 0: production path (halo tile for stride-1 layers: 64-channel blocks pair two taps per MMA row, 32-channel blocks
+    -- without a bias gradient -- group the taps by column); 1: nine boxes per chunk everywhere."""
     from fal_net_b200 import conv_native as CN
     torch.backends.cudnn.allow_tf32 = False
     dev = torch.device("cuda:0")
@@ -49,12 +51,13 @@ def test_wgrad_matches_fp32(B, H, W, Cxs, Cg, cout, cx, stride, flags):
     # write into columns [8, 8 + cx) of a wider gradient tensor that already holds something (accumulation semantics)
     dW = torch.full((cout, cx + 16, 3, 3), 0.5, device=dev).contiguous(memory_format=CL)
     # ... and take the bias gradient along (the kernel's spare operand slot reads ones): accumulated into dbias[:cout]
-    dbias = torch.full((cout + 3,), 2.0, device=dev)
+    dbias = torch.full((cout + 3,), 2.0, device=dev) if with_bias else None
     CN.conv3x3_wgrad(g16, x16, dW, cout=cout, cx=cx, ci_off=8, stride=stride, flags=flags, dbias=dbias)
     torch.cuda.synchronize()
-    bref = g16.float()[:, :cout].sum(dim=(0, 2, 3))
-    assert float((dbias[:cout] - 2.0 - bref).abs().max() / bref.abs().max().clamp_min(1.0)) < 1e-3
-    assert float((dbias[cout:] - 2.0).abs().max()) == 0
+    if with_bias:
+        bref = g16.float()[:, :cout].sum(dim=(0, 2, 3))
+        assert float((dbias[:cout] - 2.0 - bref).abs().max() / bref.abs().max().clamp_min(1.0)) < 1e-3
+        assert float((dbias[cout:] - 2.0).abs().max()) == 0
     got = dW[:, 8:8 + cx] - 0.5
     scale = ref.abs().max()
     assert float((got - ref).abs().max() / scale) < 2e-3, float((got - ref).abs().max() / scale)
