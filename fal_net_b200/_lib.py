@@ -60,6 +60,7 @@ _SIGNATURES = {
     "faln_channel_sum_nhwc": [_p, _p, _ll, _i, _i, _p],
     "faln_stem_conv": [_p] * 4 + [_i] * 6 + [_p],
     "faln_stem_conv_mma": [_p] * 4 + [_i] * 6 + [_p],
+    "faln_stem_wgrad": [_p] * 4 + [_i] * 3 + [_p],
     "faln_upsample_nearest_nhwc": [_p, _p] + [_i] * 6 + [_p],
     "faln_maxpool2_nhwc": [_p, _p] + [_i] * 4 + [_p],
     "faln_stem_conv_tc": [_p] * 6 + [_i] * 6 + [_p],

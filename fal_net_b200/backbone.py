@@ -83,6 +83,9 @@ _SKIP_BIAS_SUMS = os.environ.get("FALN_DEBUG_SKIP_BIAS_SUMS", "0") not in ("", "
 # each): Stage-1 step 3.811 ms on the side stream vs 3.784 ms inline -- SLOWER, like every other attempt to put work beside
 # the full-resolution layers that open the forward.  Off by default.
 PREP_ON_SIDE = os.environ.get("FALN_PREP_ON_SIDE", "0") not in ("", "0")
+# The stem's weight / bias gradient from the fp32 image (stem_wgrad_mma_kernel); FALN_NO_STEM_WGRAD=1: the generic kernel on a
+# 32-channel bf16 copy of the image (a 63 MB transpose + a full 32 x 32-channel launch for 27 x 32 numbers).
+STEM_WGRAD_MMA = os.environ.get("FALN_NO_STEM_WGRAD", "0") in ("", "0")
 FUSE_BIAS_GRAD = os.environ.get("FALN_NO_FUSED_BIAS_GRAD", "0") in ("", "0")
 USE_UP2_WGRAD = os.environ.get("FALN_NO_UP2_WGRAD", "0") in ("", "0")
 
@@ -445,6 +448,14 @@ def backward(model, tape, g_logits, sink=None):
         g_a = CN.conv3x3_dgrad(g_r, _wd(blk.conv1.weight), hw, dact=1, ysave=a, residual=g_s)   # (dgrad + skip path) * ELU'
         wname, bname = pfx + f"{name}.0.weight", pfx + f"{name}.0.bias"
         if i == 0:
+            if STEM_WGRAD_MMA and cout == 32 and g_a.shape[1] == 32 and head.weight.shape[2:] == (3, 3):
+                # weight + bias gradient of the stem from the fp32 image itself (patch rows rebuilt in shared memory)
+                def run(g_=g_a, img=tape["image"]):
+                    CN.stem_wgrad(img, g_, sink.grad_view(wname), sink.grad_view(bname))
+                    ready(bname)
+                    ready(wname)
+                on_side(run, g_a, tape["image"])
+                break
             # the 3-channel image as a 32-channel (zero-padded) bf16 NHWC tensor: same tensor-core path, cx = 3
             img16 = layout.planar_to_nhwc_bf16(tape["image"].float().contiguous(), 32).permute(0, 3, 1, 2)
             wgrad(wname, g_a, (img16,), cout, bias=bname)

@@ -286,6 +286,24 @@ def stem_conv(x, w, bias, act, flip_x=False):
     return y
 
 
+def stem_wgrad(image, g, dW, dbias=None):
+    """dW += weight gradient of the 3 -> 32 stem conv (and dbias += its bias gradient) straight from the fp32 NCHW image
+    (csrc/conv_wgrad.cu stem_wgrad_mma_kernel): image [B,3,H,W] fp32, g bf16 [B,32,H,W] channels_last (pre-activation gradient),
+    dW fp32 [32,3,3,3] in channels_last (KRSC) memory, dbias fp32 [32]."""
+    image = _lib.f32c(image)
+    g = _nhwc(g)
+    B, C, H, W = image.shape
+    assert C == 3 and g.shape == (B, 32, H, W), (image.shape, g.shape)
+    assert dW.dtype == torch.float32 and dW.shape == (32, 3, 3, 3) and dW.permute(0, 2, 3, 1).is_contiguous()
+    assert dbias is None or (dbias.dtype == torch.float32 and dbias.is_contiguous() and dbias.numel() >= 32)
+    ev = _timed("conv_wgrad", 2 * 27 * 32 * B * H * W, 12 * B * H * W + 2 * B * H * W * 32, 32)
+    rc = _lib.lib().faln_stem_wgrad(_lib.ptr(image), _lib.ptr(g), _lib.ptr(dW), _lib.ptr(dbias), B, H, W, _lib.cur_stream())
+    _lib.check(rc, "faln_stem_wgrad")
+    if ev is not None:
+        ev.record()
+    return dW
+
+
 def upsample_nearest(x, size):
     x = _nhwc(x)
     B, C, Hi, Wi = x.shape

@@ -404,6 +404,141 @@ conv3x3_wgrad_up2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ stem weight gradient
+// Weight (and bias) gradient of the 3 -> 32 first layer from the fp32 NCHW image itself.  The generic kernel above needs the
+// image as a 32-channel bf16 NHWC tensor (a 63 MB transpose per step) and then spends a full 32 x 32-channel launch on 27 x 32
+// numbers.  Here the patch rows of the fused stem forward (conv_tc.cu, stem_mma_kernel: [hi(27) 1 0(4) | lo(27) 0(5)] per
+// pixel, K = taps there) are rebuilt in shared memory and read as the MN-major operand of dW^T[tap, co] = sum_pixels
+// patch[pixel, tap] * g[pixel, co]: M = the 64 hi / lo tap slots (+ 64 rows that are never read), N = 32, K = the 128 pixels of
+// the tile = eight instructions; the accumulator stays in TMEM for all tiles of the persistent CTA and is reduced once at the
+// end (hi + lo rows add into the same element; slot 27 holds ones, so its row is the bias gradient).
+__global__ void __launch_bounds__(128, 4)
+stem_wgrad_mma_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ g, float* __restrict__ dW,
+                      float* __restrict__ dbias, int B, int H, int W, int tiles_w, long long total) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* At = base;                              // 128 pixel rows x 128 B (64 tap slots)
+  unsigned char* Bt = base + 2 * 128 * 128;              // 128 pixel rows x 64 B (32 output channels); [At + 16 KB, Bt): rows 64..127 of M
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Bt + 128 * 64);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  auto pack2 = [](float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  };
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 32);
+  {  // the never-read second M atom: finite values (zeros) so that nothing odd is ever multiplied
+    uint4* z = reinterpret_cast<uint4*>(At + 128 * 128);
+    for (int i = tid; i < 128 * 128 / 16; i += 128) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t idesc = make_idesc_mn(32);
+  const uint64_t a_tmpl = make_desc_mn<128>(smem_u32(At), 128 * 128);     // LBO: the second 64-slot atom along M
+  const uint64_t b_tmpl = make_desc_mn<64>(smem_u32(Bt), 128 * 64);
+  const long long hw = (long long)H * W;
+  uint32_t phase = 0;
+  int it = 0;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    const int tw = (int)(t % tiles_w);
+    const long long row = t / tiles_w;                   // b * H + y
+    const int yy0 = (int)(row % H);
+    const long long b = row / H;
+    const int xo = tw * 128 + tid;
+    // ---- patch row of pixel (b, yy0, xo), as in stem_mma_kernel, with a ONE in slot 27
+    float v[32];
+    const float* pb = x + b * 3 * hw;
+    int xoff[3], yoff[3];
+    bool okx[3], oky[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int xx = xo + d - 1, yy = yy0 + d - 1;
+      okx[d] = xx >= 0 && xx < W;
+      oky[d] = yy >= 0 && yy < H;
+      xoff[d] = xx;
+      yoff[d] = yy * W;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* pc = pb + c * hw;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+          v[c * 9 + dy * 3 + dx] = (oky[dy] && okx[dx]) ? __ldg(pc + (yoff[dy] + xoff[dx])) : 0.f;
+      }
+    }
+    v[27] = 1.0f;
+#pragma unroll
+    for (int k = 28; k < 32; ++k) v[k] = 0.f;
+    uint32_t pk[32];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+      const float2 hf = __bfloat1622float2(h);
+      pk[k] = *reinterpret_cast<const uint32_t*>(&h);
+      pk[16 + k] = pack2(v[2 * k] - hf.x, v[2 * k + 1] - hf.y);
+    }
+    {
+      unsigned char* rowp = At + (tid >> 3) * 1024 + (tid & 7) * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(rowp + ((j ^ (tid & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    }
+    // ---- gradient rows of the tile: one contiguous run of valid_px * 64 bytes (NHWC, 32 channels); zeros beyond the row end
+    {
+      const int valid_px = min(128, W - tw * 128);
+      const uint4* gp = reinterpret_cast<const uint4*>(g + ((row * W) + tw * 128) * 32);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = tid + 128 * k, pp = i >> 2, q = i & 3;
+        const uint4 u = pp < valid_px ? __ldg(gp + i) : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(Bt + pp * 64 + ((q ^ ((pp >> 1) & 3)) << 4)) = u;
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)                     // K-step = 16 pixels = two 8-pixel atoms
+        umma_bf16(tmem_base, a_tmpl + (uint64_t)((ks * 16 * 128) >> 4), b_tmpl + (uint64_t)((ks * 16 * 64) >> 4), idesc,
+                  (it | ks) != 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);                               // the instructions have read the tiles: they may be overwritten
+    phase ^= 1;
+  }
+  tc_fence_after();
+  if (it > 0) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), r);
+    const int k = tid < 27 ? tid : ((tid >= 32 && tid < 59) ? tid - 32 : -1);
+    if (k >= 0) {
+      float* d = dW + (k % 9) * 3 + k / 9;               // dW [co][kh][kw][c] (KRSC), k = c * 9 + kh * 3 + kw
+#pragma unroll
+      for (int co = 0; co < 32; ++co) atomicAdd(d + co * 27, __uint_as_float(r[co]));
+    } else if (tid == 27 && dbias) {
+#pragma unroll
+      for (int co = 0; co < 32; ++co) atomicAdd(dbias + co, __uint_as_float(r[co]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
 template <int XROWB, int GROWB, bool HALO>
 int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mg, const WgradParams& p, int splits, int smem, cudaStream_t st) {
   auto kern = conv3x3_wgrad_kernel<XROWB, GROWB, HALO>;
@@ -588,6 +723,30 @@ extern "C" int faln_conv3x3_wgrad_up2(const void* g, const void* x, float* dW, i
   dim3 grid(splits, nblk, 1);
   launch_pdl(kern, grid, dim3(192), (size_t)smem, as_stream(stream), mx, mg, p);
   return after_launch("conv3x3_wgrad_up2_kernel");
+}
+
+// Weight and bias gradient of the 3 -> 32 stem (conv0.0) straight from the fp32 image (stem_wgrad_mma_kernel):
+// x [B,3,H,W] fp32 NCHW, g [B,H,W,32] bf16 NHWC (pre-activation gradient), dW [32,3,3,3] fp32 KRSC and dbias [32] (or NULL)
+// are accumulated into.
+extern "C" int faln_stem_wgrad(const float* x, const void* g, float* dW, float* dbias, int B, int H, int W,
+                               faln_stream_t stream) {
+  FALN_REQUIRE(x && g && dW && B > 0 && H > 0 && W > 0, "faln_stem_wgrad: bad argument");
+  FALN_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "faln_stem_wgrad: g must be 16-byte aligned");
+  FALN_REQUIRE((long long)B * 3 * H * W < (1LL << 31), "faln_stem_wgrad: tensor too large");
+  const int tiles_w = (W + 127) / 128;
+  const long long total = (long long)B * H * tiles_w;
+  const int smem = 1024 + 2 * 128 * 128 + 128 * 64 + 64;
+  static const int per_sm = getenv("FALN_STEM_WGRAD_CTAS") ? atoi(getenv("FALN_STEM_WGRAD_CTAS")) : 3;
+  long long grid = (long long)sm_count() * (per_sm > 0 ? per_sm : 3);
+  if (grid > total) grid = total;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(stem_wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  stem_wgrad_mma_kernel<<<(int)grid, 128, smem, as_stream(stream)>>>(x, static_cast<const __nv_bfloat16*>(g), dW, dbias, B, H, W,
+                                                                     tiles_w, total);
+  return after_launch("stem_wgrad_mma_kernel");
 }
 
 extern "C" int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B, int H, int W, int Cg, int Cxs, int Cout,

@@ -267,6 +267,10 @@ int faln_stem_conv(const float* x, const float* w, const float* bias, void* y, i
  * image keeps 16 mantissa bits), four MMAs per 128 pixels, bias + activation epilogue out of TMEM.  Same arguments. */
 int faln_stem_conv_mma(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int Cout, int act,
                        int flip_x, faln_stream_t stream);
+/* Weight and bias gradient of that first layer (3 -> 32, conv0.0 of /root/reference/models/FAL_netB.py:99) from the fp32 image
+ * itself -- autograd's grad_weight / grad_bias of the first nn.Conv2d: x [B,3,H,W] fp32 NCHW, g [B,H,W,32] bf16 NHWC
+ * (pre-activation gradient), dW [32,3,3,3] fp32 in KRSC memory ([co][kh][kw][c]) and dbias [32] (NULL = none) accumulated into. */
+int faln_stem_wgrad(const float* x, const void* g, float* dW, float* dbias, int B, int H, int W, faln_stream_t stream);
 /* F.interpolate(mode='nearest') (:58) on bf16 NHWC: src index = min(floor(dst * in/out), in-1). */
 int faln_upsample_nearest_nhwc(const void* src, void* dst, int B, int Hi, int Wi, int Ho, int Wo, int C,
                                faln_stream_t stream);

@@ -115,3 +115,25 @@ def test_folded_deconv_wgrad_matches_fp32(B, H, W, Cin, Cout):
     plain = torch.zeros(Cout, Cin, 3, 3, device=dev).contiguous(memory_format=CL)
     CN.conv3x3_wgrad(g16, CN.upsample_nearest(h16, (2 * H, 2 * W)), plain, cout=Cout, cx=Cin)
     assert float((got - plain).abs().max() / scale) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 19, 45), (1, 7, 300), (8, 192, 640), (1, 5, 1242)])
+def test_stem_weight_and_bias_gradient_from_the_image(B, H, W):
+    """stem_wgrad_mma_kernel: dW / dbias of the 3 -> 32 first layer from the fp32 NCHW image (patch rows as bf16 hi + lo pairs in
+    shared memory, the accumulator kept in TMEM across the tiles of a persistent CTA) vs fp32 autograd on the same operands;
+    accumulation semantics, ragged last tile, several tiles per row."""
+    from fal_net_b200 import conv_native as CN
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(B * 31 + W)
+    x = torch.randn(B, 3, H, W, device=dev, generator=gen)
+    g16 = torch.randn(B, 32, H, W, device=dev, generator=gen).to(torch.bfloat16).contiguous(memory_format=CL)
+    w = torch.zeros(32, 3, 3, 3, device=dev, requires_grad=True)
+    (ref,) = torch.autograd.grad(F.conv2d(x, w, None, 1, 1), w, g16.float())
+    bref = g16.float().sum(dim=(0, 2, 3))
+    dW = torch.full((32, 3, 3, 3), 0.5, device=dev).contiguous(memory_format=CL)
+    db = torch.full((32,), -1.0, device=dev)
+    CN.stem_wgrad(x, g16, dW, db)
+    torch.cuda.synchronize()
+    assert float((dW - 0.5 - ref).abs().max() / ref.abs().max()) < 1e-3, float((dW - 0.5 - ref).abs().max() / ref.abs().max())
+    assert float((db + 1.0 - bref).abs().max() / bref.abs().max().clamp_min(1.0)) < 1e-3
