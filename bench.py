@@ -867,17 +867,35 @@ def run_gpu(a, wl, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAda
     kinds = {}
     for kind, s0, s1, nbytes in timing:
         kinds.setdefault(kind, []).append((s0.elapsed_time(s1), nbytes))
-    med_stats = {k: {"launches_per_step": len(v) / n_prof, "avg_ms": sum(x for x, _ in v) / len(v),
+    # an event pair brackets its kernel in STREAM order: when the eager host falls behind for one launch, the pair also times
+    # the idle gap in front of the kernel (seen as one 3x sample among ten).  Samples beyond 1.5x the median are dropped.
+    for kind, v in list(kinds.items()):
+        med_t = sorted(x for x, _ in v)[len(v) // 2]
+        kept = [(x, nb_) for x, nb_ in v if x <= 1.5 * med_t]
+        kinds[kind] = kept if kept else v
+    n_med_samples = {k: len(v) for k, v in kinds.items()}
+    med_stats = {k: {"launches_per_step": round(sum(1 for kk, *_ in timing if kk == k) / n_prof, 3), "samples_kept": n_med_samples[k],
+                     "avg_ms": sum(x for x, _ in v) / len(v),
                      "gbs": sum(nb_ for _, nb_ in v) / sum(x for x, _ in v) / 1e6,
                      "frac": sum(nb_ for _, nb_ in v) / sum(x for x, _ in v) / 1e6 / hbm_peak,
-                     "share_of_step": sum(x for x, _ in v) / n_prof / ms} for k, v in kinds.items()}
+                     "share_of_step": (sum(x for x, _ in v) / len(v)) * (sum(1 for kk, *_ in timing if kk == k) / n_prof) / ms}
+                 for k, v in kinds.items()}
     # convolution kernels (tcgen05 tile / row / wgrad): tensor roofline from the algorithmic FLOPs; layer by layer the
     # bound is max(flops / tensor peak, bytes / HBM peak) because the <= 96-channel layers sit below the bf16 ridge
     fam = {}
     smem_gbs = smem_port_gbs()
+    # the same outlier rule per layer shape: a launch's time = the mean of its shape's samples within 1.5x their median
+    groups = {}
+    for kind, s0, s1, fl, nbytes, gemm_n in ctiming:
+        groups.setdefault((kind, fl, nbytes, gemm_n), []).append(s0.elapsed_time(s1))
+    shape_ms = {}
+    for key, ts in groups.items():
+        med_t = sorted(ts)[len(ts) // 2]
+        kept = [x for x in ts if x <= 1.5 * med_t] or ts
+        shape_ms[key] = sum(kept) / len(kept)
     for kind, s0, s1, fl, nbytes, gemm_n in ctiming:
         f = fam.setdefault(kind, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "bound_ms": 0.0, "bound_ss_ms": 0.0, "n": 0})
-        f["ms"] += s0.elapsed_time(s1)
+        f["ms"] += shape_ms[(kind, fl, nbytes, gemm_n)]
         f["flops"] += fl
         f["bytes"] += nbytes
         b0 = max(fl / (tf_peak * 1e9), nbytes / (hbm_peak * 1e6))
