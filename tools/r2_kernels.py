@@ -34,6 +34,9 @@ for cin, cout, H, W, stride in ((64, 64, 96, 320, 1), (64, 128, 96, 320, 2), (32
     gy = rnd(B, cout, (H - 1) // stride + 1, (W - 1) // stride + 1)
     dW = torch.zeros(cout, cin, 3, 3, device=dev).contiguous(memory_format=CL)
     CN.conv3x3_wgrad(gy, x, dW, cout=cout, cx=cin, stride=stride, dbias=torch.zeros(cout, device=dev))
+# the stem's weight + bias gradient from the image
+dW0 = torch.zeros(32, 3, 3, 3, device=dev).contiguous(memory_format=CL)
+CN.stem_wgrad(img, rnd(B, 32, 192, 640), dW0, torch.zeros(32, device=dev))
 torch.manual_seed(0)
 opt = FlatAdamDDP(models.FAL_netB(no_levels=49).to(dev), lr=1e-4)
 opt._repack_dgrad()
