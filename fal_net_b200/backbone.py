@@ -86,6 +86,11 @@ PREP_ON_SIDE = os.environ.get("FALN_PREP_ON_SIDE", "0") not in ("", "0")
 # The stem's weight / bias gradient from the fp32 image (stem_wgrad_mma_kernel); FALN_NO_STEM_WGRAD=1: the generic kernel on a
 # 32-channel bf16 copy of the image (a 63 MB transpose + a full 32 x 32-channel launch for 27 x 32 numbers).
 STEM_WGRAD_MMA = os.environ.get("FALN_NO_STEM_WGRAD", "0") in ("", "0")
+# Weight gradients of the small-map layers (at most SMALL_WGRAD_CHUNKS 64-pixel chunks: the 3x10 ... 12x40 maps of the 192x640
+# crop) are collected and launched as ONE grid per kernel configuration (CN.conv3x3_wgrad_multi).  FALN_NO_WGRAD_BATCH=1: one
+# launch per layer and source, as before.
+BATCH_SMALL_WGRAD = os.environ.get("FALN_NO_WGRAD_BATCH", "0") in ("", "0")
+SMALL_WGRAD_CHUNKS = int(os.environ.get("FALN_WGRAD_BATCH_CHUNKS", "96"))
 FUSE_BIAS_GRAD = os.environ.get("FALN_NO_FUSED_BIAS_GRAD", "0") in ("", "0")
 USE_UP2_WGRAD = os.environ.get("FALN_NO_UP2_WGRAD", "0") in ("", "0")
 
@@ -333,6 +338,21 @@ def backward(model, tape, g_logits, sink=None):
                     cur.wait_event(ev)
         sink.mark_ready(name)
 
+    pending, pending_names = [], []
+
+    def flush_small():
+        """Launch the collected small-map weight gradients as one batched grid on the side stream."""
+        if not pending:
+            return
+        jobs, names = list(pending), list(pending_names)
+        del pending[:], pending_names[:]
+
+        def run():
+            CN.conv3x3_wgrad_multi(jobs)
+            for n_ in names:
+                ready(n_)
+        on_side(run, *[t for j in jobs for t in (j["g"], j["x"])])
+
     def bias_grad(name, g, C):
         def run():
             if not _SKIP_BIAS_SUMS:
@@ -347,6 +367,21 @@ def backward(model, tape, g_logits, sink=None):
         if bias is not None and not FUSE_BIAS_GRAD:
             bias_grad(bias, g_pre, cout)
             bias = None
+        dst0 = sink.grad_view(name)
+        chunks = g_pre.shape[0] * ((g_pre.shape[3] + 15) // 16) * ((g_pre.shape[2] + 3) // 4)
+        if (BATCH_SMALL_WGRAD and chunks <= SMALL_WGRAD_CHUNKS and const is None and dst0.shape[2:] == (3, 3)
+                and not any(callable(x) for x in sources)):
+            # a small-map layer: its launch is a ~15 us latency chain that holds SMs beside the data-gradient chain.  Collected
+            # and launched with its neighbours as ONE grid (flush_small: when the first large layer follows, or at the end)
+            off = 0
+            for x in sources:
+                cx = min(x.shape[1], dst0.shape[1] - off)
+                pending.append(dict(g=g_pre, x=x, dW=dst0, cout=cout, cx=cx, ci_off=off, stride=stride,
+                                    dbias=sink.grad_view(bias) if (bias is not None and off == 0) else None))
+                off += cx
+            pending_names.extend([n_ for n_ in (bias, name) if n_ is not None])
+            return
+        flush_small()
 
         def run():
             dW = dst = sink.grad_view(name)
@@ -469,6 +504,7 @@ def backward(model, tape, g_logits, sink=None):
         g_s = CN.conv3x3_dgrad(g_a, _wd(head.weight, Cp), (prev.shape[2], prev.shape[3]), stride=stride,
                                out=G_skip.pop(i - 1), accum=True, dact=1, ysave=prev)
         del g_r, g_a
+    flush_small()
     for side in used:                                                             # join: gradients complete, `keep` may go
         main.wait_stream(side)
     del keep

@@ -3,6 +3,8 @@
 Activations: bf16 tensors of logical shape [B,C,H,W] in channels_last memory format (= NHWC in memory)."""
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -436,6 +438,51 @@ def conv3x3_wgrad(g, x, dW, cout=None, cx=None, ci_off=0, stride=1, flags=0, dbi
     if ev is not None:
         ev.record()
     return dW
+
+
+class _WgradJob(ctypes.Structure):
+    _fields_ = ([("g", ctypes.c_void_p), ("x", ctypes.c_void_p), ("dW", ctypes.c_void_p), ("dbias", ctypes.c_void_p)] +
+                [(n, ctypes.c_int) for n in ("B", "H", "W", "Cg", "Cxs", "Cout", "Cx", "ci_off", "Cin_tot", "stride")] +
+                [("flags", ctypes.c_uint)])
+
+
+def conv3x3_wgrad_multi(jobs):
+    """Several ``conv3x3_wgrad`` calls in as few launches as possible (csrc/conv_wgrad.cu conv3x3_wgrad_multi_kernel: jobs with
+    the same kernel configuration share one grid).  jobs: list of dicts with the keyword arguments of ``conv3x3_wgrad``
+    (g, x, dW, cout, cx, ci_off, stride, dbias).  Meant for the small-map layers, whose separate launches are latency chains."""
+    n = len(jobs)
+    if n == 0:
+        return
+    arr = (_WgradJob * n)()
+    keep, flops, nbytes = [], 0, 0
+    for i, j in enumerate(jobs):
+        g, x, dW = _nhwc(j["g"]), _nhwc(j["x"]), j["dW"]
+        stride = j.get("stride", 1)
+        B, Cg, Hg, Wg = g.shape
+        _, Cxs, H, W = x.shape
+        assert x.shape[0] == B and (Hg, Wg) == ((H - 1) // stride + 1, (W - 1) // stride + 1), (g.shape, x.shape, stride)
+        assert dW.dtype == torch.float32 and dW.dim() == 4 and dW.shape[2:] == (3, 3) and dW.permute(0, 2, 3, 1).is_contiguous()
+        cout = j.get("cout") or dW.shape[0]
+        ci_off = j.get("ci_off", 0)
+        cx = j.get("cx") or min(Cxs, dW.shape[1] - ci_off)
+        dbias = j.get("dbias")
+        assert cout <= dW.shape[0] and ci_off + cx <= dW.shape[1]
+        assert dbias is None or (dbias.dtype == torch.float32 and dbias.is_contiguous() and dbias.numel() >= cout)
+        keep.extend((g, x))
+        a = arr[i]
+        a.g, a.x, a.dW = g.data_ptr(), x.data_ptr(), dW.data_ptr()
+        a.dbias = dbias.data_ptr() if dbias is not None else None
+        a.B, a.H, a.W, a.Cg, a.Cxs, a.Cout, a.Cx, a.ci_off, a.Cin_tot, a.stride = B, H, W, Cg, Cxs, cout, cx, ci_off, dW.shape[1], stride
+        a.flags = 0
+        flops += 2 * 9 * cx * cout * B * Hg * Wg
+        nbytes += 2 * B * Hg * Wg * Cg + 2 * B * H * W * Cxs + 4 * 9 * cx * cout
+    if not keep[0].is_cuda:
+        raise RuntimeError("fal_net_b200 kernels need CUDA tensors (no CPU fallback)")
+    ev = _timed("conv_wgrad", flops, nbytes, 64)
+    rc = _lib.lib().faln_conv3x3_wgrad_multi(ctypes.cast(arr, ctypes.c_void_p), n, _lib.cur_stream())
+    _lib.check(rc, "faln_conv3x3_wgrad_multi")
+    if ev is not None:
+        ev.record()
 
 
 def conv3x3_wgrad_up2(g, x, dW, cout=None, cx=None, ci_off=0):

@@ -76,9 +76,11 @@ __device__ __forceinline__ uint32_t make_idesc_mn(int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// The body of one weight-gradient CTA: channel block `blk` (= cob * n_cib + cib), split `split` of `nsplit` over the chunks.
+// Shared by the one-layer kernel and the batched one (several small layers in one grid).
 template <int XROWB, int GROWB, bool HALO>
-__global__ void __launch_bounds__(192)
-conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams p) {
+__device__ __forceinline__ void wgrad_cta(const CUtensorMap& tmX, const CUtensorMap& tmG, const WgradParams& p, const int blk,
+                                          const int split, const int nsplit) {
   constexpr int XC = XROWB / 2;                        // channels per x box
   constexpr int NB = GROWB / 2;                        // output channels per block = channels of the g box
   constexpr int XBOX = kP * XROWB, GBOX = kP * GROWB;  // bytes per (non-halo) box
@@ -94,8 +96,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const int tx_bytes = p.tx_x + GBOX;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cib = blockIdx.y % p.n_cib, cob = blockIdx.y / p.n_cib;
-  const int split = blockIdx.x, nsplit = gridDim.x;
+  const int cib = blk % p.n_cib, cob = blk / p.n_cib;
   const int my_chunks = (p.chunks - split + nsplit - 1) / nsplit;  // chunks split, split + nsplit, ...
   constexpr uint32_t tmem_cols = IROWS * NB;
   constexpr uint32_t alloc_cols = tmem_cols <= 32 ? 32 : tmem_cols <= 64 ? 64 : tmem_cols <= 128 ? 128 : tmem_cols <= 256 ? 256 : 512;
@@ -243,6 +244,37 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   }
 }
 
+
+template <int XROWB, int GROWB, bool HALO>
+__global__ void __launch_bounds__(192)
+conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams p) {
+  wgrad_cta<XROWB, GROWB, HALO>(tmX, tmG, p, blockIdx.y, blockIdx.x, gridDim.x);
+}
+
+// Several (small) layers in ONE grid.  On the 3x10 ... 12x40 maps a weight-gradient launch is a chain of latencies -- barrier
+// init, TMEM allocation, first TMA round trip, a handful of chunks, the reduction: ~13 us + 0.6 us per chunk whatever the layer
+// -- during which its CTAs hold an SM's shared memory and all 512 TMEM columns and keep the data-gradient chain off it.  Ten such
+// launches in a row cost ~180 us of that; as one grid (every CTA finds its job by its block index) they cost one.
+constexpr int kMaxBatch = 12;
+struct WgradJob {
+  CUtensorMap mx, mg;
+  WgradParams p;
+  int splits, cta0;               // CTAs [cta0, cta0 + splits * n_cib * n_cob) belong to this job
+};
+struct WgradBatch {
+  WgradJob job[kMaxBatch];
+  int njobs;
+};
+template <int XROWB, int GROWB, bool HALO>
+__global__ void __launch_bounds__(192)
+conv3x3_wgrad_multi_kernel(const __grid_constant__ WgradBatch batch) {
+  int j = 0;
+  for (int k = 1; k < batch.njobs; ++k)
+    if ((int)blockIdx.x >= batch.job[k].cta0) j = k;
+  const WgradJob& job = batch.job[j];
+  const int local = (int)blockIdx.x - job.cta0;
+  wgrad_cta<XROWB, GROWB, HALO>(job.mx, job.mg, job.p, local / job.splits, local % job.splits, job.splits);
+}
 
 // ------------------------------------------------------------------------------------------ folded deconv weight gradient
 // Weight gradient of "nearest 2x up-sampling, then conv3x3" (the reference's deconv block, models/FAL_netB.py:51-60) WITHOUT the
@@ -597,10 +629,17 @@ using namespace faln;
 // x  [B,H,W,Cxs]  bf16 NHWC: the conv's input (one source of a concatenated input per call; Cxs % 32 == 0)
 // dW [Cout, 3, 3, Cin_tot] fp32 (KRSC): columns [ci_off, ci_off + Cx) are ACCUMULATED into (caller zeroes them once per step)
 // flags: bit 0 = never use the halo path (validation: nine boxes per chunk instead)
-// dbias [Cout] fp32 (may be NULL): += sum over (b, ho, wo) of g[b, ho, wo, co] -- the bias gradient, from the spare tap slot
-extern "C" int faln_conv3x3_wgrad_bias(const void* g, const void* x, float* dW, float* dbias, int B, int H, int W, int Cg,
-                                       int Cxs, int Cout, int Cx, int ci_off, int Cin_tot, int stride, unsigned flags,
-                                       faln_stream_t stream) {
+namespace {
+struct PreparedWgrad {
+  CUtensorMap mx, mg;
+  WgradParams p;
+  int splits, smem, key;          // key = template choice: bit 0 halo, bit 1 XC == 64, bit 2 GC == 64
+};
+
+// Everything a weight-gradient launch needs (parameters, tensor maps, split count, shared memory), shared by the one-layer and
+// the batched entry point.  max_splits > 0 caps the split count (batched launches aim for ONE wave over all their jobs).
+int prepare_wgrad(const void* g, const void* x, float* dW, float* dbias, int B, int H, int W, int Cg, int Cxs, int Cout, int Cx,
+                  int ci_off, int Cin_tot, int stride, unsigned flags, int ring_kb_cap, PreparedWgrad& out) {
   FALN_REQUIRE(g && x && dW && B > 0 && H > 0 && W > 0, "faln_conv3x3_wgrad: null pointer / bad shape");
   FALN_REQUIRE(stride == 1 || stride == 2, "faln_conv3x3_wgrad: stride must be 1 or 2");
   FALN_REQUIRE(Cg % 32 == 0 && Cxs % 32 == 0 && Cg > 0 && Cxs > 0, "faln_conv3x3_wgrad: channel strides must be multiples of 32");
@@ -639,7 +678,8 @@ extern "C" int faln_conv3x3_wgrad_bias(const void* g, const void* x, float* dW, 
   // FALN_WGRAD_SMEM_KB: shared memory the operand ring may take (tuning aid).  The kernel runs beside the data-gradient chain;
   // a CTA that fills the SM's shared memory keeps that chain's CTAs off the SM for as long as it runs.
   static const int ring_kb = getenv("FALN_WGRAD_SMEM_KB") ? atoi(getenv("FALN_WGRAD_SMEM_KB")) : 200;
-  p.stages = ((ring_kb > 0 ? ring_kb : 200) * 1024) / stage_bytes;
+  const int ring_use = (ring_kb_cap > 0 && ring_kb_cap < ring_kb) ? ring_kb_cap : ring_kb;
+  p.stages = ((ring_use > 0 ? ring_use : 200) * 1024) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) p.stages = 2;
   p.ones_off = p.stages * stage_bytes;                       // halo path: 2 KB of bf16 ones behind the ring
@@ -659,20 +699,120 @@ extern "C" int faln_conv3x3_wgrad_bias(const void* g, const void* x, float* dW, 
   static const int min_chunks = getenv("FALN_WGRAD_MIN_CHUNKS") ? atoi(getenv("FALN_WGRAD_MIN_CHUNKS")) : 16;
   if (splits > p.chunks / (min_chunks > 0 ? min_chunks : 16)) splits = p.chunks / (min_chunks > 0 ? min_chunks : 16);
   if (splits < 1) splits = 1;
-  CUtensorMap mx, mg;
+  CUtensorMap& mx = out.mx;
+  CUtensorMap& mg = out.mg;
   const bool ok_x = p.halo ? make_halo_map(&mx, x, B, H, W, Cxs, XC) : make_act_map(&mx, x, B, H, W, Cxs, XC, stride, kCR);
   if (!ok_x || !make_act_map(&mg, g, B, Hg, Wg, Cg, GC, 1, kCR)) {
     set_error("faln_conv3x3_wgrad: cuTensorMapEncodeTiled failed (driver entry point missing or bad tensor geometry)");
     return FALN_ERR_LAUNCH;
   }
+  out.p = p;
+  out.splits = splits;
+  out.smem = smem;
+  out.key = (p.halo ? 1 : 0) | (XC == 64 ? 2 : 0) | (GC == 64 ? 4 : 0);
+  return FALN_OK;
+}
+
+template <int XROWB, int GROWB, bool HALO>
+int launch_wgrad_multi(const WgradBatch& batch, int ctas, int smem, cudaStream_t st) {
+  auto kern = conv3x3_wgrad_multi_kernel<XROWB, GROWB, HALO>;
+  static int attr_set = 0;
+  if (attr_set < smem) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_set = smem;
+  }
+  launch_pdl(kern, dim3(ctas), dim3(192), (size_t)smem, st, batch);
+  return after_launch("conv3x3_wgrad_multi_kernel");
+}
+
+int launch_prepared(const PreparedWgrad& w, cudaStream_t st) {
+  switch (w.key) {
+    case 7: return launch_wgrad<128, 128, true>(w.mx, w.mg, w.p, w.splits, w.smem, st);
+    case 6: return launch_wgrad<128, 128, false>(w.mx, w.mg, w.p, w.splits, w.smem, st);
+    case 3: return launch_wgrad<128, 64, true>(w.mx, w.mg, w.p, w.splits, w.smem, st);
+    case 2: return launch_wgrad<128, 64, false>(w.mx, w.mg, w.p, w.splits, w.smem, st);
+    case 5: return launch_wgrad<64, 128, true>(w.mx, w.mg, w.p, w.splits, w.smem, st);
+    case 4: return launch_wgrad<64, 128, false>(w.mx, w.mg, w.p, w.splits, w.smem, st);
+    case 1: return launch_wgrad<64, 64, true>(w.mx, w.mg, w.p, w.splits, w.smem, st);
+    default: return launch_wgrad<64, 64, false>(w.mx, w.mg, w.p, w.splits, w.smem, st);
+  }
+}
+int launch_batch(int key, const WgradBatch& b, int ctas, int smem, cudaStream_t st) {
+  switch (key) {
+    case 7: return launch_wgrad_multi<128, 128, true>(b, ctas, smem, st);
+    case 6: return launch_wgrad_multi<128, 128, false>(b, ctas, smem, st);
+    case 3: return launch_wgrad_multi<128, 64, true>(b, ctas, smem, st);
+    case 2: return launch_wgrad_multi<128, 64, false>(b, ctas, smem, st);
+    case 5: return launch_wgrad_multi<64, 128, true>(b, ctas, smem, st);
+    case 4: return launch_wgrad_multi<64, 128, false>(b, ctas, smem, st);
+    case 1: return launch_wgrad_multi<64, 64, true>(b, ctas, smem, st);
+    default: return launch_wgrad_multi<64, 64, false>(b, ctas, smem, st);
+  }
+}
+}  // namespace
+
+// dbias [Cout] fp32 (may be NULL): += sum over (b, ho, wo) of g[b, ho, wo, co] -- the bias gradient, from the spare tap slot
+extern "C" int faln_conv3x3_wgrad_bias(const void* g, const void* x, float* dW, float* dbias, int B, int H, int W, int Cg,
+                                       int Cxs, int Cout, int Cx, int ci_off, int Cin_tot, int stride, unsigned flags,
+                                       faln_stream_t stream) {
+  PreparedWgrad w;
+  const int rc = prepare_wgrad(g, x, dW, dbias, B, H, W, Cg, Cxs, Cout, Cx, ci_off, Cin_tot, stride, flags, 0, w);
+  if (rc != FALN_OK) return rc;
+  return launch_prepared(w, as_stream(stream));
+}
+
+// Several layers' weight (and bias) gradients in as few launches as possible: jobs with the same kernel configuration (channel
+// block widths, halo / box path) share ONE grid (conv3x3_wgrad_multi_kernel); meant for the small-map layers, whose launches are
+// latency chains that hold SMs beside the data-gradient chain.  Every job is what one faln_conv3x3_wgrad_bias call takes.
+extern "C" int faln_conv3x3_wgrad_multi(const faln_wgrad_job_t* jobs, int njobs, faln_stream_t stream) {
+  FALN_REQUIRE(jobs && njobs > 0 && njobs <= 64, "faln_conv3x3_wgrad_multi: 1..64 jobs");
+  static PreparedWgrad prep[64];            // host scratch; the C ABI is called from one host thread per device at a time
+  static thread_local WgradBatch batch;
+  // a batched launch keeps its CTAs short-lived and small: 100 KB of operand ring (4 stages) per CTA
+  for (int i = 0; i < njobs; ++i) {
+    const faln_wgrad_job_t& j = jobs[i];
+    const int rc = prepare_wgrad(j.g, j.x, j.dW, j.dbias, j.B, j.H, j.W, j.Cg, j.Cxs, j.Cout, j.Cx, j.ci_off, j.Cin_tot, j.stride,
+                                 j.flags, 100, prep[i]);
+    if (rc != FALN_OK) return rc;
+  }
   cudaStream_t st = as_stream(stream);
-  if (XC == 64 && GC == 64)
-    return p.halo ? launch_wgrad<128, 128, true>(mx, mg, p, splits, smem, st) : launch_wgrad<128, 128, false>(mx, mg, p, splits, smem, st);
-  if (XC == 64 && GC == 32)
-    return p.halo ? launch_wgrad<128, 64, true>(mx, mg, p, splits, smem, st) : launch_wgrad<128, 64, false>(mx, mg, p, splits, smem, st);
-  if (XC == 32 && GC == 64)
-    return p.halo ? launch_wgrad<64, 128, true>(mx, mg, p, splits, smem, st) : launch_wgrad<64, 128, false>(mx, mg, p, splits, smem, st);
-  return p.halo ? launch_wgrad<64, 64, true>(mx, mg, p, splits, smem, st) : launch_wgrad<64, 64, false>(mx, mg, p, splits, smem, st);
+  bool done[64] = {false};
+  for (int i = 0; i < njobs; ++i) {
+    if (done[i]) continue;
+    // group = the not yet launched jobs with job i's configuration, kMaxBatch at a time
+    int idx[kMaxBatch], n = 0;
+    for (int k = i; k < njobs && n < kMaxBatch; ++k)
+      if (!done[k] && prep[k].key == prep[i].key) idx[n++] = k;
+    for (int k = 0; k < n; ++k) done[idx[k]] = true;
+    if (n == 1) {
+      const int rc = launch_prepared(prep[i], st);
+      if (rc != FALN_OK) return rc;
+      continue;
+    }
+    // one wave over the group: chunks are dealt so that every CTA gets about total_block_chunks / SMs of them
+    long long total = 0;
+    for (int k = 0; k < n; ++k) total += (long long)prep[idx[k]].p.chunks * prep[idx[k]].p.n_cib * prep[idx[k]].p.n_cob;
+    long long target = (total + sm_count() - 1) / sm_count();
+    if (target < 8) target = 8;
+    int ctas = 0, smem = 0;
+    for (int k = 0; k < n; ++k) {
+      PreparedWgrad& w = prep[idx[k]];
+      int splits = (int)((w.p.chunks + target - 1) / target);
+      if (splits < 1) splits = 1;
+      if (splits > w.p.chunks) splits = w.p.chunks;
+      batch.job[k].mx = w.mx;
+      batch.job[k].mg = w.mg;
+      batch.job[k].p = w.p;
+      batch.job[k].splits = splits;
+      batch.job[k].cta0 = ctas;
+      ctas += splits * w.p.n_cib * w.p.n_cob;
+      if (w.smem > smem) smem = w.smem;
+    }
+    batch.njobs = n;
+    const int rc = launch_batch(prep[i].key, batch, ctas, smem, st);
+    if (rc != FALN_OK) return rc;
+  }
+  return FALN_OK;
 }
 
 // Weight gradient of the folded deconv block (nearest 2x up-sampling + conv3x3, see conv3x3_wgrad_up2_kernel):

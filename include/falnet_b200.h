@@ -238,6 +238,18 @@ int faln_conv3x3_wgrad(const void* g, const void* x, float* dW, int B, int H, in
  * For a concatenated input pass dbias with ONE of the per-source calls only. */
 int faln_conv3x3_wgrad_bias(const void* g, const void* x, float* dW, float* dbias, int B, int H, int W, int Cg, int Cxs,
                             int Cout, int Cx, int ci_off, int Cin_tot, int stride, unsigned flags, faln_stream_t stream);
+/* Several layers' weight (+ bias) gradients at once: every job is what one faln_conv3x3_wgrad_bias call takes; jobs that map to
+ * the same kernel configuration share ONE grid.  For the small-map layers (3x10 ... 12x40), whose separate launches are ~15 us
+ * latency chains that hold SMs beside the data-gradient chain of loss.backward(). */
+typedef struct faln_wgrad_job {
+  const void* g;
+  const void* x;
+  float* dW;
+  float* dbias; /* NULL = no bias gradient */
+  int B, H, W, Cg, Cxs, Cout, Cx, ci_off, Cin_tot, stride;
+  unsigned flags;
+} faln_wgrad_job_t;
+int faln_conv3x3_wgrad_multi(const faln_wgrad_job_t* jobs, int njobs, faln_stream_t stream);
 /* Weight gradient of the reference's deconv block -- F.interpolate(scale 2, nearest) then conv3x3
  * (/root/reference/models/FAL_netB.py:51-60) -- taken straight from the LOW-resolution input, the counterpart of
  * faln_conv3x3_up2_fwd / _dgrad: sixteen quarter-resolution correlations folded into the nine taps (2.25x fewer MMAs, no

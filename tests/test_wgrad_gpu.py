@@ -137,3 +137,50 @@ def test_stem_weight_and_bias_gradient_from_the_image(B, H, W):
     torch.cuda.synchronize()
     assert float((dW - 0.5 - ref).abs().max() / ref.abs().max()) < 1e-3, float((dW - 0.5 - ref).abs().max() / ref.abs().max())
     assert float((db + 1.0 - bref).abs().max() / bref.abs().max().clamp_min(1.0)) < 1e-3
+
+
+def test_batched_small_map_wgrad_equals_separate_launches():
+    """faln_conv3x3_wgrad_multi: the small-map layers' weight (+ bias) gradients as one grid per kernel configuration (every CTA
+    finds its job by its block index) against one launch per job; mixed configurations (64 / 32-channel blocks, stride 1 / 2,
+    two sources of a concatenated input, a bias gradient) in one call."""
+    from fal_net_b200 import conv_native as CN
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(77)
+
+    def rnd(*shape):
+        return torch.randn(*shape, device=dev, generator=gen).to(torch.bfloat16).contiguous(memory_format=CL)
+    B = 8
+    specs = [  # (cin sources, cout, H, W, stride, bias)
+        ((256, 256), 256, 6, 20, 1, True),      # iconv6: two sources
+        ((512,), 512, 3, 10, 1, False),         # conv6_1
+        ((512,), 512, 3, 10, 1, False),
+        ((256,), 256, 6, 20, 1, False),         # conv5_1
+        ((256,), 256, 12, 40, 1, False),        # conv4_1
+        ((256,), 512, 6, 20, 2, True),          # conv6.0 (stride 2)
+        ((256,), 256, 12, 40, 2, True),         # conv5.0
+        ((128, 256), 256, 12, 40, 1, True),     # iconv5
+        ((32,), 32, 12, 40, 1, False),          # a 32-channel block
+    ]
+    jobs, refs = [], []
+    for srcs, cout, H, W, stride, bias in specs:
+        Hg, Wg = (H - 1) // stride + 1, (W - 1) // stride + 1
+        g = rnd(B, cout, Hg, Wg)
+        cin = sum(srcs)
+        dW_a = torch.zeros(cout, cin, 3, 3, device=dev).contiguous(memory_format=CL)
+        dW_b = torch.zeros(cout, cin, 3, 3, device=dev).contiguous(memory_format=CL)
+        db_a = torch.zeros(cout, device=dev) if bias else None
+        db_b = torch.zeros(cout, device=dev) if bias else None
+        off = 0
+        for c in srcs:
+            x = rnd(B, c, H, W)
+            jobs.append(dict(g=g, x=x, dW=dW_a, cout=cout, cx=c, ci_off=off, stride=stride, dbias=db_a if off == 0 else None))
+            CN.conv3x3_wgrad(g, x, dW_b, cout=cout, cx=c, ci_off=off, stride=stride, dbias=db_b if off == 0 else None)
+            off += c
+        refs.append((dW_a, dW_b, db_a, db_b))
+    CN.conv3x3_wgrad_multi(jobs)
+    torch.cuda.synchronize()
+    for dW_a, dW_b, db_a, db_b in refs:
+        scale = float(dW_b.abs().max())
+        assert scale > 0 and float((dW_a - dW_b).abs().max()) / scale < 2e-3          # split-K order differs
+        if db_a is not None:
+            assert float((db_a - db_b).abs().max()) / float(db_b.abs().max().clamp_min(1.0)) < 1e-3
