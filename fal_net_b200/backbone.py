@@ -86,11 +86,13 @@ PREP_ON_SIDE = os.environ.get("FALN_PREP_ON_SIDE", "0") not in ("", "0")
 # The stem's weight / bias gradient from the fp32 image (stem_wgrad_mma_kernel); FALN_NO_STEM_WGRAD=1: the generic kernel on a
 # 32-channel bf16 copy of the image (a 63 MB transpose + a full 32 x 32-channel launch for 27 x 32 numbers).
 STEM_WGRAD_MMA = os.environ.get("FALN_NO_STEM_WGRAD", "0") in ("", "0")
-# Weight gradients of the small-map layers (at most SMALL_WGRAD_CHUNKS 64-pixel chunks: the 3x10 ... 12x40 maps of the 192x640
-# crop) are collected and launched as ONE grid per kernel configuration (CN.conv3x3_wgrad_multi).  FALN_NO_WGRAD_BATCH=1: one
-# launch per layer and source, as before.
+# Weight gradients of the small- and mid-map layers (at most SMALL_WGRAD_CHUNKS 64-pixel chunks: the 3x10 ... 48x160 maps of the
+# 192x640 crop) are collected and launched as ONE grid per kernel configuration (CN.conv3x3_wgrad_multi) when the first larger
+# layer follows.  Measured on B200 (100-step runs, twice each, one box): Stage-1 step 3.734 ms without batching, 3.708 ms with a
+# 96-chunk limit (3x10 ... 12x40), 3.665 ms at 1000 (... 48x160), 3.717 at 4000, 3.711 with everything at the end of backward.
+# FALN_NO_WGRAD_BATCH=1: one launch per layer and source, as before.
 BATCH_SMALL_WGRAD = os.environ.get("FALN_NO_WGRAD_BATCH", "0") in ("", "0")
-SMALL_WGRAD_CHUNKS = int(os.environ.get("FALN_WGRAD_BATCH_CHUNKS", "96"))
+SMALL_WGRAD_CHUNKS = int(os.environ.get("FALN_WGRAD_BATCH_CHUNKS", "1000"))
 FUSE_BIAS_GRAD = os.environ.get("FALN_NO_FUSED_BIAS_GRAD", "0") in ("", "0")
 USE_UP2_WGRAD = os.environ.get("FALN_NO_UP2_WGRAD", "0") in ("", "0")
 
