@@ -68,6 +68,7 @@ _SIGNATURES = {
     "faln_conv3x3_up2_fwd": [_p] * 4 + [_i] * 8 + [_p],
     "faln_conv3x3_up2_dgrad": [_p] * 4 + [_i] * 8 + [_p],
     "faln_pack_up2_weights": [_p] + [_ll] * 4 + [_p, _p] + [_i] * 4 + [_p],
+    "faln_pack_up2_weights_multi": [_p, _i, _p],
     "faln_level_tables": [_p] * 4 + [_i] * 3 + [_p],
     "faln_fold_logit_conv": [_p, _p] + [_ll] * 4 + [_p, _p] + [_i] * 4 + [_p],
     "faln_fold_logit_conv_bwd": [_p] * 3 + [_ll] * 4 + [_p] + [_ll] * 4 + [_p, _i, _i, _p],

@@ -91,6 +91,7 @@ STEM_WGRAD_MMA = os.environ.get("FALN_NO_STEM_WGRAD", "0") in ("", "0")
 # layer follows.  Measured on B200 (100-step runs, twice each, one box): Stage-1 step 3.734 ms without batching, 3.708 ms with a
 # 96-chunk limit (3x10 ... 12x40), 3.665 ms at 1000 (... 48x160), 3.717 at 4000, 3.711 with everything at the end of backward.
 # FALN_NO_WGRAD_BATCH=1: one launch per layer and source, as before.
+UP2_PACKS_BATCHED = os.environ.get("FALN_NO_UP2_PACK_BATCH", "0") in ("", "0")
 BATCH_SMALL_WGRAD = os.environ.get("FALN_NO_WGRAD_BATCH", "0") in ("", "0")
 SMALL_WGRAD_CHUNKS = int(os.environ.get("FALN_WGRAD_BATCH_CHUNKS", "1000"))
 FUSE_BIAS_GRAD = os.environ.get("FALN_NO_FUSED_BIAS_GRAD", "0") in ("", "0")
@@ -100,6 +101,28 @@ USE_UP2_WGRAD = os.environ.get("FALN_NO_UP2_WGRAD", "0") in ("", "0")
 def _up2_packs(weight):
     """(forward, dgrad) folded packs of a deconv weight: one launch, refreshed once per optimiser step."""
     return _cached(weight, ("up2",), lambda: CN.pack_up2_weights(weight))
+
+
+def _up2_packs_all(weights):
+    """The folded packs of ALL deconv levels in one launch when any of them is stale (training: once per step) -- six launches
+    of ~5 us each sat in the forward's main chain, right in front of their consumers.  Fills the per-weight caches."""
+    stale = []
+    for w in weights:
+        if w.grad_fn is not None:
+            return
+        key = (w._version, GENERATION[0] if w.requires_grad else -1, w.data_ptr())
+        cache = getattr(w, "_faln_packs", None)
+        if cache is None or cache.get("key") != key or ("up2",) not in cache:
+            stale.append((w, key))
+    if len(stale) < 2:
+        return
+    packs = CN.pack_up2_weights_multi([w for w, _ in stale])
+    for (w, key), pk in zip(stale, packs):
+        cache = getattr(w, "_faln_packs", None)
+        if cache is None or cache.get("key") != key:
+            cache = {"key": key}
+            w._faln_packs = cache
+        cache[("up2",)] = pk
 
 
 def _ctab(weight, channel):
@@ -198,6 +221,9 @@ def forward(model, image, max_disp, tape=None, disp_lvl=None):
         if tape is not None:
             tape[name] = (a, r, s)
     h = skips[6]
+    if USE_UP2 and UP2_PACKS_BATCHED and image.shape[2] % 64 == 0 and image.shape[3] % 64 == 0:    # exact 2x at every level
+        _up2_packs_all([getattr(bb, f"deconv{lvl}").conv1.weight for lvl, *_ in DEC
+                        if getattr(bb, f"deconv{lvl}").conv1.weight.shape[1] % 32 == 0])
     for lvl, _, uout, _, iout in DEC:
         skip = skips[lvl - 1]
         up = getattr(bb, f"deconv{lvl}")

@@ -202,6 +202,37 @@ def pack_up2_weights(weight: torch.Tensor):
     return fwd, dg
 
 
+class _Up2PackJob(ctypes.Structure):
+    _fields_ = ([("w", ctypes.c_void_p)] + [(n, ctypes.c_longlong) for n in ("so", "sc", "sh", "sw")] +
+                [("fwd_pack", ctypes.c_void_p), ("dgrad_pack", ctypes.c_void_p)] +
+                [(n, ctypes.c_int) for n in ("Cout", "Cin", "Cout_pad", "Cin_pad")])
+
+
+def pack_up2_weights_multi(weights):
+    """``pack_up2_weights`` of several deconv weights in ONE launch; returns a list of (forward pack, dgrad pack)."""
+    n = len(weights)
+    assert 0 < n <= 8
+    arr = (_Up2PackJob * n)()
+    out = []
+    for i, weight in enumerate(weights):
+        w = weight.detach()
+        assert w.dtype == torch.float32 and w.dim() == 4 and w.shape[2:] == (3, 3) and w.is_cuda
+        Cout, Cin = w.shape[0], w.shape[1]
+        Cout_pad, Cin_pad = (Cout + 31) // 32 * 32, (Cin + 31) // 32 * 32
+        assert Cin % 32 == 0
+        fwd = torch.empty(Cout_pad, 16, Cin, device=w.device, dtype=torch.bfloat16)
+        dg = torch.empty(Cin_pad, 16, Cout_pad, device=w.device, dtype=torch.bfloat16)
+        a = arr[i]
+        a.w = w.data_ptr()
+        a.so, a.sc, a.sh, a.sw = w.stride()
+        a.fwd_pack, a.dgrad_pack = fwd.data_ptr(), dg.data_ptr()
+        a.Cout, a.Cin, a.Cout_pad, a.Cin_pad = Cout, Cin, Cout_pad, Cin_pad
+        out.append((fwd, dg))
+    _lib.check(_lib.lib().faln_pack_up2_weights_multi(ctypes.cast(arr, ctypes.c_void_p), n, _lib.cur_stream()),
+               "faln_pack_up2_weights_multi")
+    return out
+
+
 def conv3x3_up2_fwd(x, w_fold, bias=None, act=0, cout=None):
     """act(conv3x3(upsample_nearest_2x(x))) without the up-sampled tensor: x bf16 [B,C,H,W] channels_last (low resolution),
     w_fold from ``pack_up2_weights``; returns bf16 [B,Cout,2H,2W] channels_last."""

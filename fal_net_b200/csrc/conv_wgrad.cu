@@ -766,7 +766,7 @@ extern "C" int faln_conv3x3_wgrad_bias(const void* g, const void* x, float* dW, 
 // latency chains that hold SMs beside the data-gradient chain.  Every job is what one faln_conv3x3_wgrad_bias call takes.
 extern "C" int faln_conv3x3_wgrad_multi(const faln_wgrad_job_t* jobs, int njobs, faln_stream_t stream) {
   FALN_REQUIRE(jobs && njobs > 0 && njobs <= 64, "faln_conv3x3_wgrad_multi: 1..64 jobs");
-  static PreparedWgrad prep[64];            // host scratch; the C ABI is called from one host thread per device at a time
+  static thread_local PreparedWgrad prep[64];      // host scratch (per calling thread: forward and autograd threads may both call)
   static thread_local WgradBatch batch;
   // a batched launch keeps its CTAs short-lived and small: 100 KB of operand ring (4 stages) per CTA
   for (int i = 0; i < njobs; ++i) {

@@ -167,9 +167,9 @@ __device__ __forceinline__ void up2_group(int idx, int& lo, int& hi) {   // G / 
   lo = (idx == 1) ? 1 : (idx == 3 ? 2 : 0);
   hi = (idx == 0) ? 0 : (idx == 2 ? 1 : 2);
 }
-__global__ void __launch_bounds__(256) pack_up2_kernel(const float* __restrict__ w, W4 s, __nv_bfloat16* __restrict__ fwd,
-                                                       __nv_bfloat16* __restrict__ dg, int Cout, int Cin, int Cout_pad, int Cin_pad) {
-  const long long i = blockIdx.x * 256LL + threadIdx.x;
+__device__ __forceinline__ void pack_up2_body(const long long i, const float* __restrict__ w, const W4 s,
+                                              __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dg, int Cout, int Cin,
+                                              int Cout_pad, int Cin_pad) {
   if (i >= (long long)Cout_pad * Cin_pad) return;
   const int ci = (int)(i % Cin_pad), co = (int)(i / Cin_pad);
   float k[3][3];
@@ -226,6 +226,33 @@ __global__ void scalar_combine_kernel(Terms t, float* __restrict__ out) {
 }
 __global__ void scalar_scale_kernel(const float* __restrict__ g, Terms t, float* __restrict__ out) {
   if (threadIdx.x < t.n && blockIdx.x == 0) out[threadIdx.x] = t.w[threadIdx.x] * (*g);
+}
+
+__global__ void __launch_bounds__(256) pack_up2_kernel(const float* __restrict__ w, W4 s, __nv_bfloat16* __restrict__ fwd,
+                                                       __nv_bfloat16* __restrict__ dg, int Cout, int Cin, int Cout_pad, int Cin_pad) {
+  pack_up2_body(blockIdx.x * 256LL + threadIdx.x, w, s, fwd, dg, Cout, Cin, Cout_pad, Cin_pad);
+}
+
+// All deconv levels' folded packs in ONE launch (six launches of ~5 us each sat in the forward's main chain): every block finds
+// its job by its block index.
+struct Up2PackJob {
+  const float* w;
+  W4 s;
+  __nv_bfloat16* fwd;
+  __nv_bfloat16* dg;
+  int Cout, Cin, Cout_pad, Cin_pad, block0;
+};
+struct Up2PackBatch {
+  Up2PackJob job[8];
+  int njobs;
+};
+__global__ void __launch_bounds__(256) pack_up2_multi_kernel(const __grid_constant__ Up2PackBatch b) {
+  int j = 0;
+  for (int k = 1; k < b.njobs; ++k)
+    if ((int)blockIdx.x >= b.job[k].block0) j = k;
+  const Up2PackJob& q = b.job[j];
+  pack_up2_body(((long long)blockIdx.x - q.block0) * 256LL + threadIdx.x, q.w, q.s, q.fwd, q.dg, q.Cout, q.Cin, q.Cout_pad,
+                q.Cin_pad);
 }
 
 }  // namespace
@@ -318,4 +345,26 @@ extern "C" int faln_pack_up2_weights(const float* w, long long so, long long sc,
                                                                         static_cast<__nv_bfloat16*>(dgrad_pack), Cout, Cin,
                                                                         Cout_pad, Cin_pad);
   return after_launch("pack_up2_kernel");
+}
+
+// The folded packs of several deconv layers in one launch; each job is what one faln_pack_up2_weights call takes.
+extern "C" int faln_pack_up2_weights_multi(const faln_up2_pack_job_t* jobs, int njobs, faln_stream_t stream) {
+  FALN_REQUIRE(jobs && njobs > 0 && njobs <= 8, "faln_pack_up2_weights_multi: 1..8 jobs");
+  static thread_local Up2PackBatch b;
+  int blocks = 0;
+  for (int i = 0; i < njobs; ++i) {
+    const faln_up2_pack_job_t& j = jobs[i];
+    FALN_REQUIRE(j.w && j.fwd_pack && j.dgrad_pack && j.Cout > 0 && j.Cin > 0 && j.Cout_pad >= j.Cout && j.Cin_pad >= j.Cin,
+                 "faln_pack_up2_weights_multi: bad job");
+    b.job[i].w = j.w;
+    b.job[i].s = W4{j.so, j.sc, j.sh, j.sw};
+    b.job[i].fwd = static_cast<__nv_bfloat16*>(j.fwd_pack);
+    b.job[i].dg = static_cast<__nv_bfloat16*>(j.dgrad_pack);
+    b.job[i].Cout = j.Cout; b.job[i].Cin = j.Cin; b.job[i].Cout_pad = j.Cout_pad; b.job[i].Cin_pad = j.Cin_pad;
+    b.job[i].block0 = blocks;
+    blocks += (int)(((long long)j.Cout_pad * j.Cin_pad + 255) / 256);
+  }
+  b.njobs = njobs;
+  pack_up2_multi_kernel<<<blocks, 256, 0, as_stream(stream)>>>(b);
+  return after_launch("pack_up2_multi_kernel");
 }

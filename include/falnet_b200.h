@@ -309,6 +309,15 @@ int faln_conv3x3_up2_dgrad(const void* g, const void* wd, void* gx, const void* 
  * in fp32, rounded once to bf16.  fwd_pack [Cout_pad][16][Cin], dgrad_pack [Cin_pad][16][Cout_pad]. */
 int faln_pack_up2_weights(const float* w, long long so, long long sc, long long sh, long long sw, void* fwd_pack,
                           void* dgrad_pack, int Cout, int Cin, int Cout_pad, int Cin_pad, faln_stream_t stream);
+/* The same for several deconv layers in one launch. */
+typedef struct faln_up2_pack_job {
+  const float* w;
+  long long so, sc, sh, sw; /* element strides of w [Cout][Cin][3][3] */
+  void* fwd_pack;
+  void* dgrad_pack;
+  int Cout, Cin, Cout_pad, Cin_pad;
+} faln_up2_pack_job_t;
+int faln_pack_up2_weights_multi(const faln_up2_pack_job_t* jobs, int njobs, faln_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Small device-side helpers that keep ATen / cuBLAS launches out of a training step: csrc/small_ops.cu.
