@@ -52,6 +52,7 @@ _SIGNATURES = {
     "faln_conv3x3_wgrad_up2": [_p] * 3 + [_i] * 9 + [_p],
     "faln_conv3x3_wgrad_bias": [_p] * 4 + [_i] * 10 + [_u, _p],
     "faln_conv3x3_wgrad_multi": [_p, _i, _p],
+    "faln_conv3x3_wgrad_up2_multi": [_p, _i, _p],
     "faln_f32_to_bf16": [_p, _p, _ll, _p],
     "faln_pack_dgrad_batched": [_p, _p, _p, _i, _i, _p],
     "faln_pack_dgrad_flat": [_p] * 3 + [_i, _i, _p],

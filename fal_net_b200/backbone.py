@@ -94,6 +94,10 @@ STEM_WGRAD_MMA = os.environ.get("FALN_NO_STEM_WGRAD", "0") in ("", "0")
 UP2_PACKS_BATCHED = os.environ.get("FALN_NO_UP2_PACK_BATCH", "0") in ("", "0")
 BATCH_SMALL_WGRAD = os.environ.get("FALN_NO_WGRAD_BATCH", "0") in ("", "0")
 SMALL_WGRAD_CHUNKS = int(os.environ.get("FALN_WGRAD_BATCH_CHUNKS", "1000"))
+# the same for the folded deconv weight gradients (limit on the OUTPUT map's chunks; 0 = separate launches).  Measured on B200
+# (100-step runs, twice each): 3.669 / 3.665 ms batched up to 48x160 vs 3.657 / 3.668 ms separate -- no gain (four jobs that are
+# not back to back in the backward); off by default, the kernel stays for shapes where the levels are smaller.
+UP2_WGRAD_BATCH_CHUNKS = int(os.environ.get("FALN_WGRAD_UP2_BATCH", "0"))
 FUSE_BIAS_GRAD = os.environ.get("FALN_NO_FUSED_BIAS_GRAD", "0") in ("", "0")
 USE_UP2_WGRAD = os.environ.get("FALN_NO_UP2_WGRAD", "0") in ("", "0")
 
@@ -366,20 +370,21 @@ def backward(model, tape, g_logits, sink=None):
                     cur.wait_event(ev)
         sink.mark_ready(name)
 
-    pending, pending_names = [], []
+    pending, pending_up2, pending_names = [], [], []
 
     def flush_small():
-        """Launch the collected small-map weight gradients as one batched grid on the side stream."""
-        if not pending:
+        """Launch the collected small-map weight gradients as batched grids on the side stream."""
+        if not pending and not pending_up2:
             return
-        jobs, names = list(pending), list(pending_names)
-        del pending[:], pending_names[:]
+        jobs, jobs_up2, names = list(pending), list(pending_up2), list(pending_names)
+        del pending[:], pending_up2[:], pending_names[:]
 
         def run():
+            CN.conv3x3_wgrad_up2_multi(jobs_up2)
             CN.conv3x3_wgrad_multi(jobs)
             for n_ in names:
                 ready(n_)
-        on_side(run, *[t for j in jobs for t in (j["g"], j["x"])])
+        on_side(run, *[t for j in jobs + jobs_up2 for t in (j["g"], j["x"])])
 
     def bias_grad(name, g, C):
         def run():
@@ -481,10 +486,17 @@ def backward(model, tape, g_logits, sink=None):
             if USE_UP2_WGRAD and h_in.shape[1] % 64 == 0 and g_u.shape[1] % 64 == 0 and up.conv1.weight.shape[2:] == (3, 3):
                 # ... and so does the weight gradient: sixteen quarter-resolution correlations of (h, g) folded into the nine
                 # taps (csrc/conv_wgrad.cu, conv3x3_wgrad_up2_kernel) -- no up-sampled tensor on either stream
-                def run(name=pfx + f"deconv{lvl}.conv1.weight", g_=g_u, h_=h_in, co=up.conv1.weight.shape[0]):
-                    CN.conv3x3_wgrad_up2(g_, h_, sink.grad_view(name), cout=co)
-                    ready(name)
-                on_side(run, g_u, h_in)
+                lo_chunks = h_in.shape[0] * ((h_in.shape[3] + 15) // 16) * ((h_in.shape[2] + 3) // 4)
+                if BATCH_SMALL_WGRAD and 4 * lo_chunks <= UP2_WGRAD_BATCH_CHUNKS:
+                    # a small level: collected and launched with its neighbours as one grid (flush_small)
+                    pending_up2.append(dict(g=g_u, x=h_in, dW=sink.grad_view(pfx + f"deconv{lvl}.conv1.weight"),
+                                            cout=up.conv1.weight.shape[0]))
+                    pending_names.append(pfx + f"deconv{lvl}.conv1.weight")
+                else:
+                    def run(name=pfx + f"deconv{lvl}.conv1.weight", g_=g_u, h_=h_in, co=up.conv1.weight.shape[0]):
+                        CN.conv3x3_wgrad_up2(g_, h_, sink.grad_view(name), cout=co)
+                        ready(name)
+                    on_side(run, g_u, h_in)
             else:
                 wgrad(pfx + f"deconv{lvl}.conv1.weight", g_u, (lambda h_=h_in, hw_=hw_up: CN.upsample_nearest(h_, hw_),),
                       up.conv1.weight.shape[0])

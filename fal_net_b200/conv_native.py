@@ -516,6 +516,41 @@ def conv3x3_wgrad_multi(jobs):
         ev.record()
 
 
+def conv3x3_wgrad_up2_multi(jobs):
+    """Several ``conv3x3_wgrad_up2`` calls as one grid (csrc/conv_wgrad.cu conv3x3_wgrad_up2_multi_kernel); jobs: list of dicts
+    with keys g, x, dW, cout (optional)."""
+    n = len(jobs)
+    if n == 0:
+        return
+    if n == 1:
+        j = jobs[0]
+        conv3x3_wgrad_up2(j["g"], j["x"], j["dW"], cout=j.get("cout"))
+        return
+    arr = (_WgradJob * n)()
+    keep, flops, nbytes = [], 0, 0
+    for i, j in enumerate(jobs):
+        g, x, dW = _nhwc(j["g"]), _nhwc(j["x"]), j["dW"]
+        B, Cg, Hg, Wg = g.shape
+        _, Cxs, H, W = x.shape
+        assert x.shape[0] == B and (Hg, Wg) == (2 * H, 2 * W) and Cg % 64 == 0 and Cxs % 64 == 0, (g.shape, x.shape)
+        assert dW.dtype == torch.float32 and dW.dim() == 4 and dW.shape[2:] == (3, 3) and dW.permute(0, 2, 3, 1).is_contiguous()
+        assert g.is_cuda
+        cout = j.get("cout") or dW.shape[0]
+        cx = min(Cxs, dW.shape[1])
+        keep.extend((g, x))
+        a = arr[i]
+        a.g, a.x, a.dW, a.dbias = g.data_ptr(), x.data_ptr(), dW.data_ptr(), None
+        a.B, a.H, a.W, a.Cg, a.Cxs, a.Cout, a.Cx, a.ci_off, a.Cin_tot, a.stride = B, H, W, Cg, Cxs, cout, cx, 0, dW.shape[1], 1
+        a.flags = 0
+        flops += 2 * 9 * cx * cout * B * Hg * Wg
+        nbytes += 2 * B * Hg * Wg * Cg + 2 * B * H * W * Cxs + 4 * 9 * cx * cout
+    ev = _timed("conv_wgrad", flops, nbytes, 64)
+    rc = _lib.lib().faln_conv3x3_wgrad_up2_multi(ctypes.cast(arr, ctypes.c_void_p), n, _lib.cur_stream())
+    _lib.check(rc, "faln_conv3x3_wgrad_up2_multi")
+    if ev is not None:
+        ev.record()
+
+
 def conv3x3_wgrad_up2(g, x, dW, cout=None, cx=None, ci_off=0):
     """dW[:cout, ci_off:ci_off+cx] += weight gradient of "nearest 2x up-sampling, then conv3x3" (the reference's deconv block,
     /root/reference/models/FAL_netB.py:51-60) taken from the LOW-resolution input: g bf16 [B,Cg,2H,2W] channels_last

@@ -291,8 +291,8 @@ conv3x3_wgrad_multi_kernel(const __grid_constant__ WgradBatch batch) {
 // the 512 TMEM columns.  The epilogue folds the classes that feed the same tap in registers (the (py, ir) pairs of a kh live in
 // different TMEM columns of the same lanes; the kw = 1 tap is fed by b_hi of px = 0 and b_lo of px = 1, i.e. by different lane
 // halves, and takes two reductions): 12 tap blocks of red.add per CTA against 9 for a plain 3 x 3 kernel.
-__global__ void __launch_bounds__(192)
-conv3x3_wgrad_up2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams p) {
+__device__ __forceinline__ void wgrad_up2_cta(const CUtensorMap& tmX, const CUtensorMap& tmG, const WgradParams& p, const int blk,
+                                              const int split, const int nsplit) {
   constexpr int XROWB = 128, GROWB = 128, NB = 64, XC = 64;
   constexpr int GBOX = kP * GROWB;
   constexpr int kHaloBytes = kHaloW * kHaloH * XROWB;
@@ -306,8 +306,7 @@ conv3x3_wgrad_up2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   const int tx_bytes = kHaloBytes + 4 * GBOX;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cib = blockIdx.y % p.n_cib, cob = blockIdx.y / p.n_cib;
-  const int split = blockIdx.x, nsplit = gridDim.x;
+  const int cib = blk % p.n_cib, cob = blk / p.n_cib;
   const int my_chunks = (p.chunks - split + nsplit - 1) / nsplit;
 
   if (threadIdx.x == 0) {
@@ -436,6 +435,20 @@ conv3x3_wgrad_up2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   }
 }
 
+
+__global__ void __launch_bounds__(192)
+conv3x3_wgrad_up2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams p) {
+  wgrad_up2_cta(tmX, tmG, p, blockIdx.y, blockIdx.x, gridDim.x);
+}
+// several folded deconv layers in one grid (see conv3x3_wgrad_multi_kernel)
+__global__ void __launch_bounds__(192) conv3x3_wgrad_up2_multi_kernel(const __grid_constant__ WgradBatch batch) {
+  int j = 0;
+  for (int k = 1; k < batch.njobs; ++k)
+    if ((int)blockIdx.x >= batch.job[k].cta0) j = k;
+  const WgradJob& job = batch.job[j];
+  const int local = (int)blockIdx.x - job.cta0;
+  wgrad_up2_cta(job.mx, job.mg, job.p, local / job.splits, local % job.splits, job.splits);
+}
 
 // ------------------------------------------------------------------------------------------ stem weight gradient
 // Weight (and bias) gradient of the 3 -> 32 first layer from the fp32 NCHW image itself.  The generic kernel above needs the
@@ -819,8 +832,9 @@ extern "C" int faln_conv3x3_wgrad_multi(const faln_wgrad_job_t* jobs, int njobs,
 // g  [B,2H,2W,Cg] bf16 NHWC: gradient w.r.t. the conv's pre-activation output (on the UP-SAMPLED grid)
 // x  [B,H,W,Cxs]  bf16 NHWC: the block's LOW-resolution input; Cg, Cxs multiples of 64
 // dW [Cout,3,3,Cin_tot] fp32 (KRSC): columns [ci_off, ci_off + Cx) are accumulated into
-extern "C" int faln_conv3x3_wgrad_up2(const void* g, const void* x, float* dW, int B, int H, int W, int Cg, int Cxs, int Cout,
-                                      int Cx, int ci_off, int Cin_tot, faln_stream_t stream) {
+namespace {
+int prepare_wgrad_up2(const void* g, const void* x, float* dW, int B, int H, int W, int Cg, int Cxs, int Cout, int Cx, int ci_off,
+                      int Cin_tot, PreparedWgrad& out) {
   FALN_REQUIRE(g && x && dW && B > 0 && H > 0 && W > 0, "faln_conv3x3_wgrad_up2: null pointer / bad shape");
   FALN_REQUIRE(Cg % 64 == 0 && Cxs % 64 == 0 && Cg > 0 && Cxs > 0, "faln_conv3x3_wgrad_up2: channel strides must be multiples of 64");
   FALN_REQUIRE(Cout > 0 && Cout <= Cg && Cx > 0 && Cx <= Cxs && ci_off >= 0 && ci_off + Cx <= Cin_tot,
@@ -849,20 +863,74 @@ extern "C" int faln_conv3x3_wgrad_up2(const void* g, const void* x, float* dW, i
   int splits = ((fill_pct > 0 ? fill_pct : 100) * sm_count() / 100) / nblk;
   if (splits > p.chunks / (min_chunks > 0 ? min_chunks : 4)) splits = p.chunks / (min_chunks > 0 ? min_chunks : 4);
   if (splits < 1) splits = 1;
-  CUtensorMap mx, mg;
+  CUtensorMap& mx = out.mx;
+  CUtensorMap& mg = out.mg;
   if (!make_halo_map(&mx, x, B, H, W, Cxs) || !make_act_map(&mg, g, B, 2 * H, 2 * W, Cg, 64, 2, kCR)) {
     set_error("faln_conv3x3_wgrad_up2: cuTensorMapEncodeTiled failed (driver entry point missing or bad tensor geometry)");
     return FALN_ERR_LAUNCH;
   }
+  out.p = p;
+  out.splits = splits;
+  out.smem = smem;
+  out.key = 8;
+  return FALN_OK;
+}
+}  // namespace
+
+extern "C" int faln_conv3x3_wgrad_up2(const void* g, const void* x, float* dW, int B, int H, int W, int Cg, int Cxs, int Cout,
+                                      int Cx, int ci_off, int Cin_tot, faln_stream_t stream) {
+  PreparedWgrad w;
+  const int rc = prepare_wgrad_up2(g, x, dW, B, H, W, Cg, Cxs, Cout, Cx, ci_off, Cin_tot, w);
+  if (rc != FALN_OK) return rc;
   auto kern = conv3x3_wgrad_up2_kernel;
+  static int attr_set = 0;
+  if (attr_set < w.smem) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, w.smem);
+    attr_set = w.smem;
+  }
+  dim3 grid(w.splits, w.p.n_cib * w.p.n_cob, 1);
+  launch_pdl(kern, grid, dim3(192), (size_t)w.smem, as_stream(stream), w.mx, w.mg, w.p);
+  return after_launch("conv3x3_wgrad_up2_kernel");
+}
+
+// Several folded deconv layers' weight gradients in one grid (the small levels: see faln_conv3x3_wgrad_multi).  Every job is what
+// one faln_conv3x3_wgrad_up2 call takes (H, W = the LOW-resolution size; stride, flags and dbias are ignored).
+extern "C" int faln_conv3x3_wgrad_up2_multi(const faln_wgrad_job_t* jobs, int njobs, faln_stream_t stream) {
+  FALN_REQUIRE(jobs && njobs > 0 && njobs <= kMaxBatch, "faln_conv3x3_wgrad_up2_multi: 1..12 jobs");
+  static thread_local PreparedWgrad prep[kMaxBatch];
+  static thread_local WgradBatch batch;
+  long long total = 0;
+  for (int i = 0; i < njobs; ++i) {
+    const faln_wgrad_job_t& j = jobs[i];
+    const int rc = prepare_wgrad_up2(j.g, j.x, j.dW, j.B, j.H, j.W, j.Cg, j.Cxs, j.Cout, j.Cx, j.ci_off, j.Cin_tot, prep[i]);
+    if (rc != FALN_OK) return rc;
+    total += (long long)prep[i].p.chunks * prep[i].p.n_cib * prep[i].p.n_cob;
+  }
+  long long target = (total + sm_count() - 1) / sm_count();
+  if (target < 4) target = 4;
+  int ctas = 0, smem = 0;
+  for (int i = 0; i < njobs; ++i) {
+    PreparedWgrad& w = prep[i];
+    int splits = (int)((w.p.chunks + target - 1) / target);
+    if (splits < 1) splits = 1;
+    if (splits > w.p.chunks) splits = w.p.chunks;
+    batch.job[i].mx = w.mx;
+    batch.job[i].mg = w.mg;
+    batch.job[i].p = w.p;
+    batch.job[i].splits = splits;
+    batch.job[i].cta0 = ctas;
+    ctas += splits * w.p.n_cib * w.p.n_cob;
+    if (w.smem > smem) smem = w.smem;
+  }
+  batch.njobs = njobs;
+  auto kern = conv3x3_wgrad_up2_multi_kernel;
   static int attr_set = 0;
   if (attr_set < smem) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_set = smem;
   }
-  dim3 grid(splits, nblk, 1);
-  launch_pdl(kern, grid, dim3(192), (size_t)smem, as_stream(stream), mx, mg, p);
-  return after_launch("conv3x3_wgrad_up2_kernel");
+  launch_pdl(kern, dim3(ctas), dim3(192), (size_t)smem, as_stream(stream), batch);
+  return after_launch("conv3x3_wgrad_up2_multi_kernel");
 }
 
 // Weight and bias gradient of the 3 -> 32 stem (conv0.0) straight from the fp32 image (stem_wgrad_mma_kernel):

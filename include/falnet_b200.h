@@ -257,6 +257,8 @@ int faln_conv3x3_wgrad_multi(const faln_wgrad_job_t* jobs, int njobs, faln_strea
  * dW [Cout,3,3,Cin_tot] fp32 KRSC accumulated in columns [ci_off, ci_off + Cx).  Cg, Cxs multiples of 64. */
 int faln_conv3x3_wgrad_up2(const void* g, const void* x, float* dW, int B, int H, int W, int Cg, int Cxs, int Cout, int Cx,
                            int ci_off, int Cin_tot, faln_stream_t stream);
+/* Several folded deconv layers at once (one grid; H, W of a job = the LOW-resolution size; stride, flags, dbias ignored). */
+int faln_conv3x3_wgrad_up2_multi(const faln_wgrad_job_t* jobs, int njobs, faln_stream_t stream);
 /* out [B,3,3,C] fp32 += sums of g [B,H,W,Cs] (bf16 NHWC) per sample over the 3x3 border classes (first / interior / last
  * row x column): the weight gradient of a spatially constant input channel (reference :145,208-209) is a 9-term
  * combination of these.  H, W >= 2. */

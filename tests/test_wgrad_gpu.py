@@ -184,3 +184,27 @@ def test_batched_small_map_wgrad_equals_separate_launches():
         assert scale > 0 and float((dW_a - dW_b).abs().max()) / scale < 2e-3          # split-K order differs
         if db_a is not None:
             assert float((db_a - db_b).abs().max()) / float(db_b.abs().max().clamp_min(1.0)) < 1e-3
+
+
+def test_batched_folded_deconv_wgrad_equals_separate_launches():
+    """faln_conv3x3_wgrad_up2_multi: several folded deconv layers' weight gradients as one grid against one launch per layer."""
+    from fal_net_b200 import conv_native as CN
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(78)
+
+    def rnd(*shape):
+        return torch.randn(*shape, device=dev, generator=gen).to(torch.bfloat16).contiguous(memory_format=CL)
+    B = 8
+    jobs, refs = [], []
+    for cin, cout, H, W in ((512, 256, 3, 10), (256, 128, 6, 20), (256, 128, 12, 40), (256, 128, 24, 80)):
+        h, g = rnd(B, cin, H, W), rnd(B, cout, 2 * H, 2 * W)
+        a = torch.zeros(cout, cin, 3, 3, device=dev).contiguous(memory_format=CL)
+        b = torch.zeros(cout, cin, 3, 3, device=dev).contiguous(memory_format=CL)
+        jobs.append(dict(g=g, x=h, dW=a, cout=cout))
+        CN.conv3x3_wgrad_up2(g, h, b, cout=cout)
+        refs.append((a, b))
+    CN.conv3x3_wgrad_up2_multi(jobs)
+    torch.cuda.synchronize()
+    for a, b in refs:
+        scale = float(b.abs().max())
+        assert scale > 0 and float((a - b).abs().max()) / scale < 2e-3
