@@ -920,6 +920,18 @@ def run_gpu(a, wl, rank, world, dev, dist, _lib, med, models, steps, LF, FlatAda
                     # the same with the shared-memory operand port of SS-mode tcgen05.mma as a third per-layer bound
                     "frac_of_layerwise_roofline_ss": tot_bound_ss / tot_ms,
                     "smem_port": {"gbs": smem_gbs, "source": "nominal: 128 B/clk x 148 SMs x sm_max_mhz"},
+                    # `traffic` stays null for the family as a whole; per-launch DRAM traffic (dram__bytes_read.sum +
+                    # dram__bytes_write.sum) of its largest kernels from the committed `ncu --set full` captures
+                    # (profiles/r2g_conv_full.txt, profiles/r2q_new_kernels_full.txt) beside their algorithmic bytes:
+                    "traffic_ncu": [
+                        {"kernel": "conv3x3_row_kernel<64,64,2>", "layer": "deconv1 forward 64->64, 8x192x640", "dram_mb": 211.5,
+                         "algorithmic_mb": 251.7, "note": "part of the output is still in L2 when the kernel ends"},
+                        {"kernel": "conv3x3_wgrad_kernel<128,128,1>", "layer": "deconv1-sized weight gradient 64->64, 8x192x640",
+                         "dram_mb": 255.6, "algorithmic_mb": 251.8},
+                        {"kernel": "conv3x3_wgrad_up2_kernel", "layer": "deconv1 folded weight gradient (input 8x96x320x64)",
+                         "dram_mb": 161.7, "algorithmic_mb": 157.4},
+                        {"kernel": "conv3x3_row_kernel<32,32,2>", "layer": "conv0_1 forward 32->32, 8x192x640", "dram_mb": 87.5,
+                         "algorithmic_mb": 125.8, "note": "part of the output is still in L2 when the kernel ends"}],
                     "launches_per_step": sum(f["n"] for f in fam.values()) / n_prof, "ms_per_step": tot_ms / n_prof,
                     "share_of_step": tot_ms / n_prof / ms, "by_kernel": conv_stats}
     roofline_med = None
